@@ -262,7 +262,7 @@ def _res_bwd(sd, cfg, pfx, g_out, tape):
     return g_x + g_out
 
 
-def eps_analytic(sd, cfg, x, t, walls, n_cond=None):
+def eps_analytic(sd, cfg, x, t, walls, n_cond=None, return_tape=False):
     """same result as eps_autograd, via the hand-written VJP (Appendix G items 1-8)"""
     R = x.shape[0]
     n_cond = R if n_cond is None else n_cond
@@ -314,4 +314,102 @@ def eps_analytic(sd, cfg, x, t, walls, n_cond=None):
                 g = g + skip_g[ind]
             g = _res_bwd(sd, cfg, "downs.%d.1." % ind, g, tape)
             g = _res_bwd(sd, cfg, "downs.%d.0." % ind, g, tape)
+        if return_tape:
+            return g.transpose(1, 2).contiguous(), u.transpose(1, 2).contiguous(), tape
         return g.transpose(1, 2).contiguous(), u.transpose(1, 2).contiguous()
+
+
+# ----------------------------------------------------------------------------- parameter inventory
+
+def param_shapes(unet_kwargs):
+    """name -> shape of every parameter of TemporalUnet_WCond(**unet_kwargs), in the reference's
+    state_dict order (checked against the live reference in tests)."""
+    cfg = UnetCfg(unet_kwargs)
+    nc = unet_kwargs["network_config"]
+    dim, we = cfg.dim, cfg.wemb
+    tdim = dim + we
+    out = {}
+
+    def lin(name, o, i, bias=True):
+        out[name + ".weight"] = (o, i)
+        if bias:
+            out[name + ".bias"] = (o,)
+
+    def norm(name, n):
+        out[name + ".weight"] = (n,)
+        out[name + ".bias"] = (n,)
+
+    lin("time_mlp.1", dim * 4, dim)
+    lin("time_mlp.3", dim, dim * 4)
+    v = nc["vit1d_config"]
+    vd, td = v["embed_dim"], v["patch_size"] * v.get("channels", 1)
+    p = "wallLoc_encoder."
+    out[p + "cls_token"] = (1, 1, vd)
+    i = 1
+    fdim = td
+    if cfg.vit_octaves:
+        fdim = td * cfg.vit_octaves * 2
+        norm(p + "to_patch_embedding.2", fdim)
+        i = 3
+    lin(p + "to_patch_embedding.%d" % i, vd, fdim)
+    lin(p + "to_patch_embedding.%d" % (i + 1), vd * 4, vd)
+    lin(p + "to_patch_embedding.%d" % (i + 3), vd, vd * 4)
+    norm(p + "to_patch_embedding.%d" % (i + 4), vd)
+    mlp = vd * v["mlp_ratio"]
+    for l in range(v["depth"]):
+        q = p + "transformer.layers.%d." % l
+        norm(q + "0.norm", vd)
+        lin(q + "0.fn.to_qkv", 3 * v["num_heads"] * v["dim_head"], vd, bias=False)
+        norm(q + "1.norm", vd)
+        lin(q + "1.fn.net.0", mlp, vd)
+        lin(q + "1.fn.net.3", vd, mlp)
+
+    def cb(name, ci, co):
+        out[name + "block.0.weight"] = (co, ci, 5)
+        out[name + "block.0.bias"] = (co,)
+        norm(name + "block.2", co)
+
+    def res(name, ci, co):
+        cb(name + "blocks.0.", ci, co)
+        cb(name + "blocks.1.", co, co)
+        if cfg.time_mlp_config == 3:
+            lin(name + "time_mlp.0", tdim * 2, tdim)
+            lin(name + "time_mlp.2", co, tdim * 2)
+        elif cfg.time_mlp_config == 2:
+            lin(name + "time_mlp.1", co * 2, tdim)
+            lin(name + "time_mlp.3", co, co * 2)
+        else:
+            lin(name + "time_mlp.1", co, tdim)
+        if ci != co:
+            out[name + "residual_conv.weight"] = (co, ci, 1)
+            out[name + "residual_conv.bias"] = (co,)
+
+    io = list(zip(cfg.dims[:-1], cfg.dims[1:]))
+    for ind, (ci, co) in enumerate(io):
+        res("downs.%d.0." % ind, ci, co)
+        res("downs.%d.1." % ind, co, co)
+        if cfg.level_has_down(ind):
+            out["downs.%d.2.conv.weight" % ind] = (co, co, 3)
+            out["downs.%d.2.conv.bias" % ind] = (co,)
+    ups = {}
+    for ind, (ci, co) in enumerate(reversed(io[1:])):
+        res("ups.%d.0." % ind, co * 2, ci)
+        res("ups.%d.1." % ind, ci, ci)
+        if cfg.up_has_up(ind):
+            out["ups.%d.2.conv.weight" % ind] = (ci, ci, 4)
+            out["ups.%d.2.conv.bias" % ind] = (ci,)
+    mid = cfg.dims[-1]
+    res("mid_block1.", mid, mid)
+    res("mid_block2.", mid, mid)
+    cb("final_conv.0.", dim, dim)
+    out["final_conv.1.weight"] = (cfg.D, dim, 1)
+    out["final_conv.1.bias"] = (cfg.D,)
+    return out
+
+
+def synth_weights(unet_kwargs, seed):
+    """deterministic name-keyed weights for an architecture (no reference needed)"""
+    from . import synth
+    shapes = param_shapes(unet_kwargs)
+    tmpl = {k: torch.empty(s) for k, s in shapes.items()}
+    return synth.synth_state_dict(tmpl, seed)

@@ -1,0 +1,347 @@
+// Batched trajectory-vs-obstacle collision checkers (bandwidth/latency-bound scans).
+//
+// Replaces (reference file:line):
+//   RM2DCollisionChecker.check_1_traj_eps / check_single_traj   diffuser/guides/rm2d_colchk.py:49-93
+//   AbstractRobot._valid_state/_state_fp/_edge_fp/distance       pb_diff_envs/robot/abstract_robot.py:97-163
+//   Point2DRobot.no_collision                                    pb_diff_envs/robot/point2d_robot.py:50-54
+//   RectangleWallGroup.is_point_inside_wg                        pb_diff_envs/environment/rand_rec_group.py:216-237
+//   check_single_traj / check_collision (scorer)                 diffuser/guides/kuka_plan_utils.py:87-154
+//   KukaCollisionChecker.check_single_traj                       diffuser/guides/kuka_colchk.py:81-104
+//     (pybullet contact query replaced by the analytic sphere-link model of oracle/colchk.c)
+// Bit-exact contract: float32 interpolation without FMA contraction, float64 box test with
+// strict inequalities, integer check counts with the reference's early-exit order.
+// One warp owns one trajectory: lanes read consecutive waypoints (coalesced float2 / row
+// loads), evaluate segments in parallel and combine with ballot / prefix sums.
+#include "common.cuh"
+
+namespace pmp {
+namespace {
+
+constexpr int WARPS = 8;
+constexpr int MAXW = 32;  // walls per environment
+
+struct Maze {
+    const double* lo_m;  // [nw][2]  (c-h)-m
+    const double* hi_m;  // [nw][2]  (c+h)+m
+    int nw;
+    float lox, loy, hix, hiy;
+};
+
+__device__ __forceinline__ bool m2d_valid(const Maze& e, float x, float y) {
+    return x >= e.lox && y >= e.loy && x <= e.hix && y <= e.hiy;
+}
+__device__ __forceinline__ bool m2d_collides(const Maze& e, float x, float y) {
+    const double px = (double)x, py = (double)y;
+    for (int i = 0; i < e.nw; ++i)
+        if (px > e.lo_m[2 * i] && py > e.lo_m[2 * i + 1] && px < e.hi_m[2 * i] && py < e.hi_m[2 * i + 1]) return true;
+    return false;
+}
+// _state_fp: returns ok, bumps cnt by one only when the state is inside the limits
+__device__ __forceinline__ bool m2d_state_fp(const Maze& e, float x, float y, int& cnt) {
+    if (!m2d_valid(e, x, y)) return false;
+    cnt += 1;
+    return !m2d_collides(e, x, y);
+}
+
+__device__ bool m2d_edge_fp(const Maze& e, float ax, float ay, float bx, float by, double eps, int legacy_div,
+                            int& cnt) {
+    if (!m2d_valid(e, ax, ay) || !m2d_valid(e, bx, by)) return false;
+    if (!m2d_state_fp(e, ax, ay, cnt)) return false;
+    if (!m2d_state_fp(e, bx, by, cnt)) return false;
+    const float dx = __fsub_rn(bx, ax), dy = __fsub_rn(by, ay);
+    const float cx = fminf(fmaxf(bx, e.lox), e.hix), cy = fminf(fmaxf(by, e.loy), e.hiy);
+    const float fx = fabsf(__fsub_rn(cx, ax)), fy = fabsf(__fsub_rn(cy, ay));
+    const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
+    int K;
+    if (legacy_div) K = (int)__ddiv_rn((double)d, eps);
+    else K = (int)__fdiv_rn(d, (float)eps);
+    for (int k = 1; k < K; ++k) {
+        const float coef = (float)__ddiv_rn((double)k, (double)K);
+        const float px = __fadd_rn(ax, __fmul_rn(coef, dx));
+        const float py = __fadd_rn(ay, __fmul_rn(coef, dy));
+        if (!m2d_state_fp(e, px, py, cnt)) return false;
+    }
+    return true;
+}
+
+__device__ __forceinline__ void load_maze(Maze& e, double* sm, const double* cen, const double* hext, int env,
+                                          int nw, double margin, int lane) {
+    // each lane prepares one wall: identical double ops to the reference ((c-h)-m, (c+h)+m)
+    for (int i = lane; i < nw; i += 32) {
+        const double* c = cen + ((size_t)env * nw + i) * 2;
+        const double* h = hext + ((size_t)env * nw + i) * 2;
+        sm[2 * i] = __dsub_rn(__dsub_rn(c[0], h[0]), margin);
+        sm[2 * i + 1] = __dsub_rn(__dsub_rn(c[1], h[1]), margin);
+        sm[2 * MAXW + 2 * i] = __dadd_rn(__dadd_rn(c[0], h[0]), margin);
+        sm[2 * MAXW + 2 * i + 1] = __dadd_rn(__dadd_rn(c[1], h[1]), margin);
+    }
+    __syncwarp();
+    e.lo_m = sm;
+    e.hi_m = sm + 2 * MAXW;
+    e.nw = nw;
+}
+
+__global__ void __launch_bounds__(WARPS * 32) maze2d_swept_kernel(
+    const float* __restrict__ traj, const int32_t* __restrict__ env_id, int N, int H, const double* __restrict__ cen,
+    const double* __restrict__ hext, int nw, float lox, float loy, float hix, float hiy, double eps, double margin,
+    int legacy_div, uint8_t* __restrict__ valid, int32_t* __restrict__ nchk) {
+    __shared__ double sm[WARPS][4 * MAXW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * WARPS + warp;
+    if (n >= N) return;
+    Maze e;
+    e.lox = lox; e.loy = loy; e.hix = hix; e.hiy = hiy;
+    load_maze(e, sm[warp], cen, hext, env_id[n], nw, margin, lane);
+    const float2* t = reinterpret_cast<const float2*>(traj + (size_t)n * H * 2);
+    int total = 0;
+    bool ok_all = true;
+    for (int base = 0; base < H - 1 && ok_all; base += 32) {
+        const int seg = base + lane;
+        bool ok = true;
+        int cnt = 0;
+        if (seg < H - 1) {
+            const float2 a = t[seg], b = t[seg + 1];
+            ok = m2d_edge_fp(e, a.x, a.y, b.x, b.y, eps, legacy_div, cnt);
+        }
+        const unsigned fail = __ballot_sync(0xffffffffu, !ok);
+        const int first = fail ? (__ffs(fail) - 1) : 32;
+        int c = (lane <= first) ? cnt : 0;  // segments after the first failing one are never evaluated
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        total += c;
+        if (fail) ok_all = false;
+    }
+    if (lane == 0) {
+        valid[n] = ok_all ? 1 : 0;
+        nchk[n] = total;
+    }
+}
+
+__global__ void __launch_bounds__(WARPS * 32) maze2d_points_kernel(
+    const float* __restrict__ traj, const int32_t* __restrict__ env_id, int N, int H, const double* __restrict__ cen,
+    const double* __restrict__ hext, int nw, float lox, float loy, float hix, float hiy, double margin,
+    int32_t* __restrict__ ncol, uint8_t* __restrict__ ptcol) {
+    __shared__ double sm[WARPS][4 * MAXW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * WARPS + warp;
+    if (n >= N) return;
+    Maze e;
+    e.lox = lox; e.loy = loy; e.hix = hix; e.hiy = hiy;
+    load_maze(e, sm[warp], cen, hext, env_id[n], nw, margin, lane);
+    const float2* t = reinterpret_cast<const float2*>(traj + (size_t)n * H * 2);
+    int cnt = 0;
+    bool bad = false;
+    for (int base = 0; base < H; base += 32) {
+        const int i = base + lane;
+        bool col = false, oob = false;
+        if (i < H) {
+            const float2 p = t[i];
+            oob = !m2d_valid(e, p.x, p.y);
+            col = m2d_collides(e, p.x, p.y);
+            if (ptcol) ptcol[(size_t)n * H + i] = col ? 1 : 0;
+        }
+        cnt += __popc(__ballot_sync(0xffffffffu, col));
+        bad = bad || (__ballot_sync(0xffffffffu, oob) != 0u);
+    }
+    if (lane == 0) ncol[n] = bad ? -1 : cnt;
+}
+
+// ------------------------------------------------------------------------------ Kuka spheres
+constexpr int MAXSPH = 32;
+struct KukaP {
+    float fixed[7][12];
+    float sph[MAXSPH][5];
+    float base[2][3];
+    int n_sph, n_arms, nv;
+    float table_z;
+};
+
+__device__ __forceinline__ void fk_step(float (&T)[12], const float (&F)[12], float s, float c) {
+    float M[12];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float v = __fmul_rn(T[4 * a + 0], F[0 + b]);
+            v = __fadd_rn(v, __fmul_rn(T[4 * a + 1], F[4 + b]));
+            v = __fadd_rn(v, __fmul_rn(T[4 * a + 2], F[8 + b]));
+            M[4 * a + b] = v;
+        }
+        M[4 * a + 3] = __fadd_rn(M[4 * a + 3], T[4 * a + 3]);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float m0 = M[4 * a + 0], m1 = M[4 * a + 1];
+        T[4 * a + 0] = __fadd_rn(__fmul_rn(m0, c), __fmul_rn(m1, s));
+        T[4 * a + 1] = __fsub_rn(__fmul_rn(m1, c), __fmul_rn(m0, s));
+        T[4 * a + 2] = M[4 * a + 2];
+        T[4 * a + 3] = M[4 * a + 3];
+    }
+}
+
+__device__ bool kuka_waypoint(const KukaP& p, const float* __restrict__ q, const float* __restrict__ bc,
+                              const float* __restrict__ bh) {
+    float wc[2][MAXSPH][4];
+    for (int a = 0; a < p.n_arms; ++a) {
+        float T[12] = {1.f, 0.f, 0.f, p.base[a][0], 0.f, 1.f, 0.f, p.base[a][1], 0.f, 0.f, 1.f, p.base[a][2]};
+        int k = 0;
+        for (int l = 0; l <= 7; ++l) {
+            if (l > 0) {
+                const double qa = (double)q[7 * a + l - 1];
+                fk_step(T, p.fixed[l - 1], (float)sin(qa), (float)cos(qa));
+            }
+            // sphere table rows are sorted by link
+            while (k < p.n_sph && (int)p.sph[k][0] == l) {
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    float v = __fmul_rn(T[4 * ax + 0], p.sph[k][1]);
+                    v = __fadd_rn(v, __fmul_rn(T[4 * ax + 1], p.sph[k][2]));
+                    v = __fadd_rn(v, __fmul_rn(T[4 * ax + 2], p.sph[k][3]));
+                    wc[a][k][ax] = __fadd_rn(v, T[4 * ax + 3]);
+                }
+                wc[a][k][3] = p.sph[k][4];
+                ++k;
+            }
+        }
+    }
+    for (int a = 0; a < p.n_arms; ++a)
+        for (int k = 0; k < p.n_sph; ++k) {
+            const float r = wc[a][k][3], r2 = __fmul_rn(r, r);
+            if ((int)p.sph[k][0] != 0 && __fsub_rn(wc[a][k][2], r) < p.table_z) return true;
+            for (int v = 0; v < p.nv; ++v) {
+                float d2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    float dj = __fsub_rn(fabsf(__fsub_rn(wc[a][k][j], bc[3 * v + j])), bh[3 * v + j]);
+                    dj = fmaxf(dj, 0.f);
+                    d2 = __fadd_rn(d2, __fmul_rn(dj, dj));
+                }
+                if (d2 < r2) return true;
+            }
+        }
+    if (p.n_arms == 2)
+        for (int k = 0; k < p.n_sph; ++k)
+            for (int m = 0; m < p.n_sph; ++m) {
+                float d2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float dj = __fsub_rn(wc[0][k][j], wc[1][m][j]);
+                    d2 = __fadd_rn(d2, __fmul_rn(dj, dj));
+                }
+                const float rr = __fadd_rn(wc[0][k][3], wc[1][m][3]);
+                if (d2 < __fmul_rn(rr, rr)) return true;
+            }
+    return false;
+}
+
+__global__ void __launch_bounds__(WARPS * 32) kuka_kernel(const __grid_constant__ KukaP p,
+                                                          const float* __restrict__ traj,
+                                                          const int32_t* __restrict__ env_id, int N, int H,
+                                                          const float* __restrict__ boxc, const float* __restrict__ boxh,
+                                                          uint8_t* __restrict__ valid, int32_t* __restrict__ nchk,
+                                                          int32_t* __restrict__ ncol, uint8_t* __restrict__ ptcol) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * WARPS + warp;
+    if (n >= N) return;
+    const int D = 7 * p.n_arms;
+    const float* bc = boxc + (size_t)env_id[n] * p.nv * 3;
+    const float* bh = boxh + (size_t)env_id[n] * p.nv * 3;
+    int cnt = 0, first = -1;
+    for (int base = 0; base < H; base += 32) {
+        const int i = base + lane;
+        bool col = false;
+        if (i < H) {
+            col = kuka_waypoint(p, traj + ((size_t)n * H + i) * D, bc, bh);
+            if (ptcol) ptcol[(size_t)n * H + i] = col ? 1 : 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, col);
+        cnt += __popc(m);
+        if (first < 0 && m) first = base + __ffs(m) - 1;
+    }
+    if (lane == 0) {
+        valid[n] = cnt == 0 ? 1 : 0;
+        nchk[n] = first < 0 ? H : first + 1;
+        ncol[n] = cnt;
+    }
+}
+
+void kuka_fixed_host(float out[7][12]) {
+    static const double XYZ[7][3] = {{0, 0, 0.1575}, {0, 0, 0.2025}, {0, 0.2045, 0}, {0, 0, 0.2155},
+                                     {0, 0.1845, 0}, {0, 0, 0.2155}, {0, 0.081, 0}};
+    static const double RPY[7][3] = {{0, 0, 0},
+                                     {1.57079632679, 0, 3.14159265359},
+                                     {1.57079632679, 0, 3.14159265359},
+                                     {1.57079632679, 0, 0},
+                                     {-1.57079632679, 3.14159265359, 0},
+                                     {1.57079632679, 0, 0},
+                                     {-1.57079632679, 3.14159265359, 0}};
+    for (int i = 0; i < 7; ++i) {
+        const double r = RPY[i][0], pt = RPY[i][1], y = RPY[i][2];
+        const double cr = cos(r), sr = sin(r), cp = cos(pt), sp = sin(pt), cy = cos(y), sy = sin(y);
+        const double R[9] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
+                             sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+                             -sp,     cp * sr,                cp * cr};
+        for (int a = 0; a < 3; ++a) {
+            for (int b = 0; b < 3; ++b) out[i][4 * a + b] = (float)R[3 * a + b];
+            out[i][4 * a + 3] = (float)XYZ[i][a];
+        }
+    }
+}
+
+}  // namespace
+}  // namespace pmp
+
+using namespace pmp;
+
+extern "C" int pmp_colchk_maze2d_swept(const float* traj, const int32_t* env_id, int N, int H, const double* cen,
+                                       const double* hext, int nw, float lox, float loy, float hix, float hiy,
+                                       double eps, double margin, int legacy_div, uint8_t* valid, int32_t* nchk,
+                                       void* stream) {
+    PMP_REQUIRE(nw >= 0 && nw <= MAXW, "at most %d walls per environment (got %d)", MAXW, nw);
+    PMP_REQUIRE(H >= 2, "trajectory needs >= 2 waypoints");
+    PMP_REQUIRE(eps > 0, "collision eps must be > 0");
+    if (N == 0) return 0;
+    maze2d_swept_kernel<<<(N + WARPS - 1) / WARPS, WARPS * 32, 0, (cudaStream_t)stream>>>(
+        traj, env_id, N, H, cen, hext, nw, lox, loy, hix, hiy, eps, margin, legacy_div, valid, nchk);
+    PMP_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int pmp_colchk_maze2d_points(const float* traj, const int32_t* env_id, int N, int H, const double* cen,
+                                        const double* hext, int nw, float lox, float loy, float hix, float hiy,
+                                        double margin, int32_t* ncol, uint8_t* ptcol, void* stream) {
+    PMP_REQUIRE(nw >= 0 && nw <= MAXW, "at most %d walls per environment (got %d)", MAXW, nw);
+    if (N == 0) return 0;
+    maze2d_points_kernel<<<(N + WARPS - 1) / WARPS, WARPS * 32, 0, (cudaStream_t)stream>>>(
+        traj, env_id, N, H, cen, hext, nw, lox, loy, hix, hiy, margin, ncol, ptcol);
+    PMP_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int pmp_colchk_kuka(const float* traj, const int32_t* env_id, int N, int H, int n_arms,
+                               const float* base, const float* sph, int n_sph, const float* boxc, const float* boxh,
+                               int nv, float table_z, uint8_t* valid, int32_t* nchk, int32_t* ncol, uint8_t* ptcol,
+                               void* stream) {
+    PMP_REQUIRE(n_arms == 1 || n_arms == 2, "n_arms must be 1 or 2");
+    PMP_REQUIRE(n_sph >= 1 && n_sph <= MAXSPH, "1..%d link spheres supported (got %d)", MAXSPH, n_sph);
+    KukaP p;
+    kuka_fixed_host(p.fixed);
+    int prev = 0;
+    for (int k = 0; k < n_sph; ++k) {
+        for (int j = 0; j < 5; ++j) p.sph[k][j] = sph[5 * k + j];
+        const int l = (int)sph[5 * k];
+        PMP_REQUIRE(l >= prev && l <= 7, "sphere table must be sorted by link index 0..7");
+        prev = l;
+    }
+    for (int a = 0; a < n_arms; ++a)
+        for (int j = 0; j < 3; ++j) p.base[a][j] = base[3 * a + j];
+    p.n_sph = n_sph;
+    p.n_arms = n_arms;
+    p.nv = nv;
+    p.table_z = table_z;
+    if (N == 0) return 0;
+    kuka_kernel<<<(N + WARPS - 1) / WARPS, WARPS * 32, 0, (cudaStream_t)stream>>>(p, traj, env_id, N, H, boxc, boxh,
+                                                                                valid, nchk, ncol, ptcol);
+    PMP_LAUNCH_OK();
+    return 0;
+}

@@ -1,0 +1,153 @@
+// Shared declarations of the pmp_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/pmp_b200.h"
+
+namespace pmp {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define PMP_CUDA_OK(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            pmp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                           __LINE__);                                                       \
+            return PMP_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+#define PMP_REQUIRE(cond, ...)          \
+    do {                                \
+        if (!(cond)) {                  \
+            pmp::set_error(__VA_ARGS__); \
+            return PMP_ERR_ARG;         \
+        }                               \
+    } while (0)
+
+#define PMP_LAUNCH_OK()                                                                      \
+    do {                                                                                     \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess) {                                                             \
+            pmp::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),       \
+                           __FILE__, __LINE__);                                              \
+            return PMP_ERR_CUDA;                                                             \
+        }                                                                                    \
+        pmp::count_launch();                                                                 \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------
+// activation (SiLU in every shipped energy-mode config, Mish kept as a switch)
+__device__ __forceinline__ float act_fwd(float z, int act) {
+    if (act == 0) return z / (1.0f + expf(-z));
+    // mish(z) = z * tanh(softplus(z)), softplus with the PyTorch threshold of 20
+    float sp = z > 20.0f ? z : log1pf(expf(z));
+    return z * tanhf(sp);
+}
+__device__ __forceinline__ float act_bwd(float z, int act) {
+    if (act == 0) {
+        float s = 1.0f / (1.0f + expf(-z));
+        return s * (1.0f + z * (1.0f - s));
+    }
+    float sp = z > 20.0f ? z : log1pf(expf(z));
+    float th = tanhf(sp);
+    float sg = 1.0f / (1.0f + expf(-z));
+    return th + z * (1.0f - th * th) * sg;
+}
+
+// ----------------------------------------------------------------------------------------
+// implicit-GEMM convolution descriptor shared by the SIMT (fp32) and tcgen05 (bf16x3) cores.
+//
+// Activations are channels-last [R][Hrows][C] (the reference's own "b h t" layout, so the
+// U-Net input/output need no transpose).  One tile = S whole samples x HJ output rows per
+// sample (x one output phase) x NT output channels, so GroupNorm slabs (sample, group) never
+// straddle a tile.
+//   output row  ho = j*ostride + phase            (j < HJ)
+//   input  row  hi = j*istride + tap_shift[phase][tap]   (zero outside [0,Hin))
+//   weight slab    = tap_k[phase][tap]            of W1 laid out [KS][C1][N]
+struct ConvP {
+    // geometry
+    int R, Hout, Hin;
+    int S, HJ, HP;              // samples per tile, out rows per sample per phase, padded in rows (Hin+4)
+    int ostride, istride, nphase;
+    int ntaps[2];
+    int tap_k[2][5];
+    int tap_shift[2][5];
+    int arows;                  // smem rows allotted to the A tile (>= S*HP, == 2 mod 8)
+    // operand slab 1 (KS taps) and optional slab 2 (1x1, shift 0)
+    const float* A1; int lda1; int C1; const float* W1;
+    const float* A2; int lda2; int C2; const float* W2;
+    int N;                      // output channels
+    // ---- epilogue (all optional unless stated)
+    const float* bias;          // [N]
+    const float* bias2;         // [N] bias of the separate slab-2 accumulator
+    // forward GroupNorm(8) + activation
+    int gn_fwd;                 // 1: v = act(gamma*yhat+beta), saves yhat / rstd
+    int gn_bwd;                 // 1: gy = GroupNorm/act backward of v using saved yhat / rstd
+    const float* gamma; const float* beta;
+    float* yhat; int ldy;       // [R*Hout][ldy]  written by gn_fwd, read by gn_bwd
+    float* rstd;                // [R][8]
+    int act;
+    // embeddings added after the activation (temporal_dd.py:71)
+    const float* embT; const int64_t* tidx; int ldeT; int tmax;  // table row = clamp(t of the sample, 0, tmax)
+    const float* embR; int ldeR; int n_cond;           // per-row table, rows < n_cond only
+    int eoff;
+    // residual / skip terms
+    const float* ident; int ldi;    // + ident[row][n]
+    const float* addend; int ldad;  // + addend[row][n]
+    float* out; int ldo;            // result after all adds (may be null)
+    float* gy; int ldg;             // gn_bwd result
+    float* energy;                  // [R] += 0.5*sum v^2   (final 1x1 conv only)
+};
+
+int launch_conv_simt(const ConvP& p, cudaStream_t st);
+int launch_gn_bwd(const float* g, int ldgi, const float* yhat, int ldy, const float* rstd,
+                  const float* gamma, const float* beta, int act, float* gy, int ldg, int R,
+                  int Hl, int C, cudaStream_t st);
+int conv_simt_smem_bytes(const ConvP& p, int TN);
+
+// embeddings / wall encoder (embed.cu)
+struct VitW {
+    int token_dim, octaves, depth, dim, mlp, act;
+    float norm_factor;
+    const float *ln0_w, *ln0_b;         // LayerNorm(pe_dim) (only with positional encoding)
+    const float *l1_w, *l1_b;           // Linear(pe_dim -> dim)
+    const float *l2_w, *l2_b;           // Linear(dim -> 4 dim)
+    const float *l3_w, *l3_b;           // Linear(4 dim -> dim)
+    const float *ln1_w, *ln1_b;         // LayerNorm(dim)
+    const float *cls;                   // [dim]
+    const float *an_w[8], *an_b[8], *qkv[8];            // attention pre-norm + to_qkv [3dim,dim]
+    const float *fn_w[8], *fn_b[8], *f0_w[8], *f0_b[8], *f3_w[8], *f3_b[8];
+};
+int launch_vit(const VitW& w, const float* walls, int B, int n_tok, float* out, cudaStream_t st);
+// time MLP of the U-Net top level: temb[t] for a list of timesteps
+int launch_time_mlp(const float* w1, const float* b1, const float* w3, const float* b3, int dim,
+                    int act, float neg_k, const int64_t* t, int n, float* out /*[n][dim]*/, cudaStream_t st);
+// out[r][c] = (bias? bias[c]:0) + sum_j W[c][j0+j] * f(in[r][j]),  j < nin ; f = act or identity
+int launch_small_linear(const float* in, int ldin, int nin, const float* W, int ldw, int j0,
+                        const float* bias, int pre_act, int act, float* out, int ldo, int nout,
+                        int rows, int accumulate, cudaStream_t st);
+// hidden = act(Ht[t_r] + (r<n_cond ? Hw[r] : 0)) for time_mlp_config 3
+int launch_cfg3_hidden(const float* Ht, const int64_t* t, int tmax, const float* Hw, int n_cond, int R,
+                       int hid, int act, float* out, cudaStream_t st);
+
+// sampler (step.cu)
+int launch_step(int kind, const float* x, const float* const* ec, const float* const* eu,
+                const float* w, int K, int base, const float* coef, const float* noise,
+                uint64_t seed, uint64_t draw, uint64_t elem0, const float* start, const float* goal,
+                float* xo, float* trace, long trace_stride, int B, int H, int D, cudaStream_t st);
+int launch_init_noise(float* x, const float* noise, uint64_t seed, uint64_t draw, uint64_t elem0,
+                      float var_temp, const float* start, const float* goal, float* trace,
+                      long trace_stride, int B, int H, int D, cudaStream_t st);
+int launch_unnormalize(const float* x, const float* lo, const float* hi, float* out, int64_t rows,
+                       int D, cudaStream_t st);
+int launch_pick_first_valid(const uint8_t* valid, const int32_t* nchk, int n_prob, int n_samp,
+                            int32_t* chosen, uint8_t* success, int32_t* total, cudaStream_t st);
+int launch_fill_i64(int64_t* p, int64_t v, size_t n, cudaStream_t st);
+
+}  // namespace pmp

@@ -1,0 +1,1077 @@
+// Host-side engine: model handle, weight re-layout, the U-Net forward + analytic backward
+// program, the reverse-diffusion loop and the C ABI (include/pmp_b200.h).
+//
+// Replaces (reference file:line):
+//   TemporalUnet_WCond.__init__/forward      diffuser/models/temporal_cond.py:67-334
+//   ResidualTemporalBlock_dd                 diffuser/models/temporal_dd.py:9-74
+//   torch.autograd.grad(E, x)                diffuser/models/temporal_cond.py:321  (hand-written VJP)
+//   GaussianDiffusionPB.p_sample_loop etc.   diffuser/models/diffusion_pb.py:249-281, 628-664
+//   PolicyCompose.*_sample_loop              diffuser/guides/policies_compose.py:270-350
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pmp {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n); }
+
+struct HostT {
+    std::vector<int64_t> shape;
+    std::vector<float> v;
+    int64_t numel() const { return (int64_t)v.size(); }
+};
+
+// forward activation view
+struct Act {
+    float* p = nullptr;
+    int ld = 0, C = 0, Hl = 0;
+    int blk = -1;  // residual block that produced it (its CB1 GroupNorm must be differentiated), -1: none
+};
+struct Grad {
+    float* raw = nullptr;
+    int ldr = 0;
+    float* gy = nullptr;  // dense [R*Hl][C]
+};
+
+struct CBW {  // Conv1dBlock_dd: conv k5 + GroupNorm(8) + act
+    int Cin = 0, Cout = 0;
+    size_t Wf = 0, Wb = 0, bias = 0, gamma = 0, beta = 0;  // offsets into the packed arena
+    // saved for backward (per eps evaluation)
+    float* yhat = nullptr;
+    float* rstd = nullptr;
+};
+struct ResB {
+    std::string pfx;
+    int Cin = 0, Cout = 0;
+    CBW cb[2];
+    bool has_res = false;
+    size_t Rf = 0, Rb = 0, Rbias = 0;
+    int eoff = 0;       // channel offset in the embedding tables
+    size_t tmW = 0, tmB = 0;      // cfg 0: Linear(128->Cout); cfg 3: second Linear(256->Cout)
+    size_t tm0W = 0, tm0B = 0;    // cfg 3: first Linear(128->256)
+};
+struct PlainConv {  // down / up sampling
+    int C = 0, KS = 0;
+    size_t Wf = 0, Wb = 0, bias = 0;
+    bool present = false;
+};
+
+}  // namespace pmp
+
+using namespace pmp;
+
+struct pmp_model {
+    pmp_arch arch;
+    int device = 0;
+    bool finalized = false;
+    std::map<std::string, HostT> hw;  // raw reference-layout weights
+    std::vector<int> dims;            // [D, dim*m0, dim*m1, ...]
+    int nl = 0;
+    std::vector<ResB> blocks;         // downs (2 per level), mid1, mid2, ups (2 per level)
+    std::vector<PlainConv> downc, upc;
+    CBW finalcb;
+    size_t fin1Wf = 0, fin1Wb = 0, fin1b = 0;
+    size_t tW1 = 0, tB1 = 0, tW3 = 0, tB3 = 0;
+    VitW vit;
+    int Ctot = 0;   // sum of Cout over residual blocks (embedding table width)
+    int hid = 0;    // cfg3 hidden width per block (2*time_dim)
+    float* arena = nullptr;   // packed weights on device
+    size_t arena_n = 0;
+    float* temb_tab = nullptr;  // [T][dim]
+    float* embT = nullptr;      // cfg0: [T][Ctot] ; cfg3: Ht [T][nblk*hid]
+    // per-call tables (grown on demand)
+    float* embR = nullptr; size_t embR_n = 0;   // cfg0: [B][Ctot]; cfg3: Hw [B][nblk*hid]
+    float* embE = nullptr; size_t embE_n = 0;   // cfg3 per step: [R][Ctot]
+    float* hidb = nullptr; size_t hidb_n = 0;   // cfg3 per step hidden [R][nblk*hid]
+    float* ws = nullptr; size_t ws_n = 0;       // activation workspace (floats)
+    int row_chunk = 2048;
+    int gemm_path = 0;
+    std::map<std::string, std::pair<float*, int64_t>> dbg;
+    bool has_down(int L) const { return !(L >= nl - 1 || L >= arch.down_times); }
+    bool has_up(int ind) const { return !(ind >= nl - 1 || ind < (nl - arch.down_times - 1)); }
+    const float* A(size_t off) const { return arena + off; }
+};
+
+namespace pmp {
+
+static int grow(float** p, size_t* cur, size_t need) {
+    if (*cur >= need) return 0;
+    if (*p) PMP_CUDA_OK(cudaFree(*p));
+    *p = nullptr;
+    *cur = 0;
+    PMP_CUDA_OK(cudaMalloc((void**)p, need * sizeof(float)));
+    *cur = need;
+    return 0;
+}
+
+// ------------------------------------------------------------------ weight packing
+struct Packer {
+    std::vector<float> buf;
+    size_t add(const std::vector<float>& v) {
+        size_t off = (buf.size() + 3) & ~(size_t)3;  // 16-byte aligned
+        buf.resize(off + v.size());
+        memcpy(buf.data() + off, v.data(), v.size() * sizeof(float));
+        return off;
+    }
+};
+
+static const HostT* find(const pmp_model* m, const std::string& k) {
+    auto it = m->hw.find(k);
+    return it == m->hw.end() ? nullptr : &it->second;
+}
+#define NEED(var, key)                                                    \
+    const HostT* var = find(m, key);                                      \
+    if (!var) {                                                           \
+        set_error("weight '%s' was not set", std::string(key).c_str());   \
+        return PMP_ERR_STATE;                                             \
+    }
+
+// Conv1d weight [Cout][Cin][KS] -> forward [KS][Cin][Cout]; backward [KS][Cout][Cin] with flipped taps
+static void conv_fwd_layout(const HostT& w, std::vector<float>& o) {
+    const int Co = (int)w.shape[0], Ci = (int)w.shape[1], K = (int)w.shape[2];
+    o.resize(w.v.size());
+    for (int co = 0; co < Co; ++co)
+        for (int ci = 0; ci < Ci; ++ci)
+            for (int k = 0; k < K; ++k) o[((size_t)k * Ci + ci) * Co + co] = w.v[((size_t)co * Ci + ci) * K + k];
+}
+static void conv_bwd_layout(const HostT& w, std::vector<float>& o, bool flip) {
+    const int Co = (int)w.shape[0], Ci = (int)w.shape[1], K = (int)w.shape[2];
+    o.resize(w.v.size());
+    for (int co = 0; co < Co; ++co)
+        for (int ci = 0; ci < Ci; ++ci)
+            for (int k = 0; k < K; ++k) {
+                const int kk = flip ? (K - 1 - k) : k;
+                o[((size_t)kk * Co + co) * Ci + ci] = w.v[((size_t)co * Ci + ci) * K + k];
+            }
+}
+// ConvTranspose1d weight [Cin][Cout][KS] -> forward [KS][Cin][Cout]; backward [KS][Cout][Cin]
+static void convT_layouts(const HostT& w, std::vector<float>& f, std::vector<float>& b) {
+    const int Ci = (int)w.shape[0], Co = (int)w.shape[1], K = (int)w.shape[2];
+    f.resize(w.v.size());
+    b.resize(w.v.size());
+    for (int ci = 0; ci < Ci; ++ci)
+        for (int co = 0; co < Co; ++co)
+            for (int k = 0; k < K; ++k) {
+                const float v = w.v[((size_t)ci * Co + co) * K + k];
+                f[((size_t)k * Ci + ci) * Co + co] = v;
+                b[((size_t)k * Co + co) * Ci + ci] = v;
+            }
+}
+
+static int pack_cb(pmp_model* m, Packer& pk, const std::string& pfx, CBW& cb) {
+    NEED(w, pfx + "block.0.weight");
+    NEED(b, pfx + "block.0.bias");
+    NEED(g, pfx + "block.2.weight");
+    NEED(be, pfx + "block.2.bias");
+    PMP_REQUIRE(w->shape.size() == 3 && w->shape[2] == 5, "%sblock.0.weight must be [Cout,Cin,5]", pfx.c_str());
+    cb.Cout = (int)w->shape[0];
+    cb.Cin = (int)w->shape[1];
+    PMP_REQUIRE(cb.Cout % 8 == 0, "GroupNorm(8) needs Cout %% 8 == 0");
+    std::vector<float> t;
+    conv_fwd_layout(*w, t);
+    cb.Wf = pk.add(t);
+    conv_bwd_layout(*w, t, true);
+    cb.Wb = pk.add(t);
+    cb.bias = pk.add(b->v);
+    cb.gamma = pk.add(g->v);
+    cb.beta = pk.add(be->v);
+    return 0;
+}
+
+static int pack_res(pmp_model* m, Packer& pk, const std::string& pfx, int Cin, int Cout, ResB& rb) {
+    rb.pfx = pfx;
+    rb.Cin = Cin;
+    rb.Cout = Cout;
+    int rc;
+    if ((rc = pack_cb(m, pk, pfx + "blocks.0.", rb.cb[0]))) return rc;
+    if ((rc = pack_cb(m, pk, pfx + "blocks.1.", rb.cb[1]))) return rc;
+    PMP_REQUIRE(rb.cb[0].Cin == Cin && rb.cb[0].Cout == Cout && rb.cb[1].Cin == Cout && rb.cb[1].Cout == Cout,
+                "%s: conv shapes do not match the architecture (%d->%d)", pfx.c_str(), Cin, Cout);
+    rb.has_res = find(m, pfx + "residual_conv.weight") != nullptr;
+    PMP_REQUIRE(rb.has_res == (Cin != Cout), "%s: residual_conv presence does not match Cin/Cout", pfx.c_str());
+    if (rb.has_res) {
+        NEED(w, pfx + "residual_conv.weight");
+        NEED(b, pfx + "residual_conv.bias");
+        std::vector<float> t;
+        conv_fwd_layout(*w, t);
+        rb.Rf = pk.add(t);
+        conv_bwd_layout(*w, t, false);
+        rb.Rb = pk.add(t);
+        rb.Rbias = pk.add(b->v);
+    }
+    const int tdim = m->arch.dim + m->arch.wall_embed_dim;
+    if (m->arch.time_mlp_config == 3) {
+        NEED(w0, pfx + "time_mlp.0.weight");
+        NEED(b0, pfx + "time_mlp.0.bias");
+        NEED(w2, pfx + "time_mlp.2.weight");
+        NEED(b2, pfx + "time_mlp.2.bias");
+        PMP_REQUIRE(w0->shape[0] == 2 * tdim && w0->shape[1] == tdim && w2->shape[0] == Cout && w2->shape[1] == 2 * tdim,
+                    "%stime_mlp shapes unexpected", pfx.c_str());
+        rb.tm0W = pk.add(w0->v);
+        rb.tm0B = pk.add(b0->v);
+        rb.tmW = pk.add(w2->v);
+        rb.tmB = pk.add(b2->v);
+    } else {
+        NEED(w1, pfx + "time_mlp.1.weight");
+        NEED(b1, pfx + "time_mlp.1.bias");
+        PMP_REQUIRE(w1->shape[0] == Cout && w1->shape[1] == tdim, "%stime_mlp.1.weight must be [%d,%d]", pfx.c_str(), Cout, tdim);
+        rb.tmW = pk.add(w1->v);
+        rb.tmB = pk.add(b1->v);
+    }
+    return 0;
+}
+
+static int finalize_model(pmp_model* m) {
+    const pmp_arch& a = m->arch;
+    PMP_REQUIRE(a.n_mults >= 2 && a.n_mults <= PMP_MAX_LEVELS, "n_mults must be 2..%d", PMP_MAX_LEVELS);
+    PMP_REQUIRE(a.time_mlp_config == 0 || a.time_mlp_config == 3, "time_mlp_config %d is not built (0 or 3)", a.time_mlp_config);
+    PMP_REQUIRE(a.wall_embed_dim == 64 && a.dim == 64, "only dim = wall_embed_dim = 64 is built");
+    m->nl = a.n_mults;
+    m->dims.assign(1, a.transition_dim);
+    for (int i = 0; i < a.n_mults; ++i) m->dims.push_back(a.dim * a.dim_mults[i]);
+    Packer pk;
+    int rc;
+    m->blocks.clear();
+    char nm[128];
+    for (int L = 0; L < m->nl; ++L) {
+        for (int j = 0; j < 2; ++j) {
+            snprintf(nm, sizeof nm, "downs.%d.%d.", L, j);
+            ResB rb;
+            if ((rc = pack_res(m, pk, nm, j == 0 ? m->dims[L] : m->dims[L + 1], m->dims[L + 1], rb))) return rc;
+            m->blocks.push_back(rb);
+        }
+    }
+    {
+        ResB rb1, rb2;
+        if ((rc = pack_res(m, pk, "mid_block1.", m->dims[m->nl], m->dims[m->nl], rb1))) return rc;
+        if ((rc = pack_res(m, pk, "mid_block2.", m->dims[m->nl], m->dims[m->nl], rb2))) return rc;
+        m->blocks.push_back(rb1);
+        m->blocks.push_back(rb2);
+    }
+    for (int ind = 0; ind < m->nl - 1; ++ind) {
+        const int Ls = m->nl - 1 - ind;            // skip level consumed
+        const int Cs = m->dims[Ls + 1], Co = m->dims[Ls];
+        for (int j = 0; j < 2; ++j) {
+            snprintf(nm, sizeof nm, "ups.%d.%d.", ind, j);
+            ResB rb;
+            if ((rc = pack_res(m, pk, nm, j == 0 ? 2 * Cs : Co, Co, rb))) return rc;
+            m->blocks.push_back(rb);
+        }
+    }
+    int off = 0;
+    for (auto& b : m->blocks) {
+        b.eoff = off;
+        off += b.Cout;
+    }
+    m->Ctot = off;
+    m->hid = 2 * (a.dim + a.wall_embed_dim);
+    // down / up sampling convs
+    m->downc.assign(m->nl, PlainConv());
+    m->upc.assign(m->nl, PlainConv());
+    for (int L = 0; L < m->nl; ++L) {
+        if (!m->has_down(L)) continue;
+        snprintf(nm, sizeof nm, "downs.%d.2.conv.", L);
+        NEED(w, std::string(nm) + "weight");
+        NEED(b, std::string(nm) + "bias");
+        PMP_REQUIRE(w->shape.size() == 3 && w->shape[2] == 3 && w->shape[0] == m->dims[L + 1], "%sweight shape", nm);
+        PlainConv& pc = m->downc[L];
+        pc.present = true; pc.C = m->dims[L + 1]; pc.KS = 3;
+        std::vector<float> t;
+        conv_fwd_layout(*w, t); pc.Wf = pk.add(t);
+        conv_bwd_layout(*w, t, false); pc.Wb = pk.add(t);
+        pc.bias = pk.add(b->v);
+    }
+    for (int ind = 0; ind < m->nl - 1; ++ind) {
+        if (!m->has_up(ind)) continue;
+        snprintf(nm, sizeof nm, "ups.%d.2.conv.", ind);
+        NEED(w, std::string(nm) + "weight");
+        NEED(b, std::string(nm) + "bias");
+        const int C = m->dims[m->nl - 1 - ind];
+        PMP_REQUIRE(w->shape.size() == 3 && w->shape[2] == 4 && w->shape[0] == C, "%sweight shape", nm);
+        PlainConv& pc = m->upc[ind];
+        pc.present = true; pc.C = C; pc.KS = 4;
+        std::vector<float> f, bw;
+        convT_layouts(*w, f, bw);
+        pc.Wf = pk.add(f); pc.Wb = pk.add(bw);
+        pc.bias = pk.add(b->v);
+    }
+    if ((rc = pack_cb(m, pk, "final_conv.0.", m->finalcb))) return rc;
+    {
+        NEED(w, "final_conv.1.weight");
+        NEED(b, "final_conv.1.bias");
+        PMP_REQUIRE(w->shape[0] == a.transition_dim && w->shape[1] == a.dim, "final_conv.1.weight shape");
+        std::vector<float> t;
+        conv_fwd_layout(*w, t); m->fin1Wf = pk.add(t);
+        conv_bwd_layout(*w, t, false); m->fin1Wb = pk.add(t);
+        m->fin1b = pk.add(b->v);
+    }
+    {
+        NEED(w1, "time_mlp.1.weight"); NEED(b1, "time_mlp.1.bias");
+        NEED(w3, "time_mlp.3.weight"); NEED(b3, "time_mlp.3.bias");
+        m->tW1 = pk.add(w1->v); m->tB1 = pk.add(b1->v); m->tW3 = pk.add(w3->v); m->tB3 = pk.add(b3->v);
+    }
+    // ---- ViT
+    size_t v_ln0w = 0, v_ln0b = 0, v_l1w, v_l1b, v_l2w, v_l2b, v_l3w, v_l3b, v_ln1w, v_ln1b, v_cls;
+    size_t v_l[8][9];
+    {
+        const std::string p = "wallLoc_encoder.";
+        int i = 1;
+        if (a.vit_octaves) {
+            NEED(g, p + "to_patch_embedding.2.weight"); NEED(b, p + "to_patch_embedding.2.bias");
+            v_ln0w = pk.add(g->v); v_ln0b = pk.add(b->v);
+            i = 3;
+        }
+        snprintf(nm, sizeof nm, "to_patch_embedding.%d.", i);
+        NEED(l1w, p + nm + "weight"); NEED(l1b, p + nm + "bias");
+        snprintf(nm, sizeof nm, "to_patch_embedding.%d.", i + 1);
+        NEED(l2w, p + nm + "weight"); NEED(l2b, p + nm + "bias");
+        snprintf(nm, sizeof nm, "to_patch_embedding.%d.", i + 3);
+        NEED(l3w, p + nm + "weight"); NEED(l3b, p + nm + "bias");
+        snprintf(nm, sizeof nm, "to_patch_embedding.%d.", i + 4);
+        NEED(n1w, p + nm + "weight"); NEED(n1b, p + nm + "bias");
+        NEED(cls, p + "cls_token");
+        const int fdim = a.vit_octaves ? a.vit_token_dim * a.vit_octaves * 2 : a.vit_token_dim;
+        PMP_REQUIRE(l1w->shape[1] == fdim && l1w->shape[0] == 64, "wall encoder first Linear must be [64,%d]", fdim);
+        v_l1w = pk.add(l1w->v); v_l1b = pk.add(l1b->v); v_l2w = pk.add(l2w->v); v_l2b = pk.add(l2b->v);
+        v_l3w = pk.add(l3w->v); v_l3b = pk.add(l3b->v); v_ln1w = pk.add(n1w->v); v_ln1b = pk.add(n1b->v);
+        v_cls = pk.add(cls->v);
+        PMP_REQUIRE(a.vit_depth >= 1 && a.vit_depth <= 8, "vit depth");
+        for (int l = 0; l < a.vit_depth; ++l) {
+            snprintf(nm, sizeof nm, "transformer.layers.%d.", l);
+            const std::string q = p + nm;
+            NEED(anw, q + "0.norm.weight"); NEED(anb, q + "0.norm.bias"); NEED(qkv, q + "0.fn.to_qkv.weight");
+            NEED(fnw, q + "1.norm.weight"); NEED(fnb, q + "1.norm.bias");
+            NEED(f0w, q + "1.fn.net.0.weight"); NEED(f0b, q + "1.fn.net.0.bias");
+            NEED(f3w, q + "1.fn.net.3.weight"); NEED(f3b, q + "1.fn.net.3.bias");
+            if (find(m, q + "0.fn.to_out.0.weight")) {
+                set_error("wall encoder with an attention output projection is not built");
+                return PMP_ERR_ARG;
+            }
+            v_l[l][0] = pk.add(anw->v); v_l[l][1] = pk.add(anb->v); v_l[l][2] = pk.add(qkv->v);
+            v_l[l][3] = pk.add(fnw->v); v_l[l][4] = pk.add(fnb->v); v_l[l][5] = pk.add(f0w->v);
+            v_l[l][6] = pk.add(f0b->v); v_l[l][7] = pk.add(f3w->v); v_l[l][8] = pk.add(f3b->v);
+        }
+    }
+    // ---- upload
+    if (m->arena) cudaFree(m->arena);
+    m->arena = nullptr;
+    m->arena_n = pk.buf.size();
+    PMP_CUDA_OK(cudaMalloc((void**)&m->arena, m->arena_n * sizeof(float)));
+    PMP_CUDA_OK(cudaMemcpy(m->arena, pk.buf.data(), m->arena_n * sizeof(float), cudaMemcpyHostToDevice));
+    VitW& v = m->vit;
+    memset(&v, 0, sizeof v);
+    v.token_dim = a.vit_token_dim; v.octaves = a.vit_octaves; v.depth = a.vit_depth; v.dim = 64;
+    v.mlp = 64 * a.vit_mlp_ratio; v.act = a.vit_act; v.norm_factor = a.vit_norm_factor;
+    if (a.vit_octaves) { v.ln0_w = m->A(v_ln0w); v.ln0_b = m->A(v_ln0b); }
+    v.l1_w = m->A(v_l1w); v.l1_b = m->A(v_l1b); v.l2_w = m->A(v_l2w); v.l2_b = m->A(v_l2b);
+    v.l3_w = m->A(v_l3w); v.l3_b = m->A(v_l3b); v.ln1_w = m->A(v_ln1w); v.ln1_b = m->A(v_ln1b);
+    v.cls = m->A(v_cls);
+    for (int l = 0; l < a.vit_depth; ++l) {
+        v.an_w[l] = m->A(v_l[l][0]); v.an_b[l] = m->A(v_l[l][1]); v.qkv[l] = m->A(v_l[l][2]);
+        v.fn_w[l] = m->A(v_l[l][3]); v.fn_b[l] = m->A(v_l[l][4]); v.f0_w[l] = m->A(v_l[l][5]);
+        v.f0_b[l] = m->A(v_l[l][6]); v.f3_w[l] = m->A(v_l[l][7]); v.f3_b[l] = m->A(v_l[l][8]);
+    }
+    // ---- time-embedding tables: temb[t] and the t-only part of every block embedding
+    const int T = a.n_timesteps;
+    PMP_REQUIRE(T >= 1 && T <= 100000, "n_timesteps out of range");
+    cudaStream_t st = 0;
+    int64_t* tdev = nullptr;
+    PMP_CUDA_OK(cudaMalloc((void**)&tdev, T * sizeof(int64_t)));
+    std::vector<int64_t> th(T);
+    for (int i = 0; i < T; ++i) th[i] = i;
+    PMP_CUDA_OK(cudaMemcpy(tdev, th.data(), T * sizeof(int64_t), cudaMemcpyHostToDevice));
+    if (m->temb_tab) cudaFree(m->temb_tab);
+    if (m->embT) cudaFree(m->embT);
+    PMP_CUDA_OK(cudaMalloc((void**)&m->temb_tab, (size_t)T * a.dim * sizeof(float)));
+    const float neg_k = (float)(-(log(10000.0) / (double)(a.dim / 2 - 1)));
+    if ((rc = launch_time_mlp(m->A(m->tW1), m->A(m->tB1), m->A(m->tW3), m->A(m->tB3), a.dim, a.act, neg_k, tdev, T,
+                              m->temb_tab, st)))
+        return rc;
+    const int tdim = a.dim + a.wall_embed_dim;
+    const int nblk = (int)m->blocks.size();
+    if (a.time_mlp_config == 0) {
+        PMP_CUDA_OK(cudaMalloc((void**)&m->embT, (size_t)T * m->Ctot * sizeof(float)));
+        for (auto& b : m->blocks)
+            if ((rc = launch_small_linear(m->temb_tab, a.dim, a.dim, m->A(b.tmW), tdim, 0, m->A(b.tmB), 1, a.act,
+                                          m->embT + b.eoff, m->Ctot, b.Cout, T, 0, st)))
+                return rc;
+    } else {
+        PMP_CUDA_OK(cudaMalloc((void**)&m->embT, (size_t)T * nblk * m->hid * sizeof(float)));
+        for (int i = 0; i < nblk; ++i)
+            if ((rc = launch_small_linear(m->temb_tab, a.dim, a.dim, m->A(m->blocks[i].tm0W), tdim, 0,
+                                          m->A(m->blocks[i].tm0B), 0, a.act, m->embT + (size_t)i * m->hid,
+                                          nblk * m->hid, m->hid, T, 0, st)))
+                return rc;
+    }
+    PMP_CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(tdev);
+    m->finalized = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------ conv geometry helpers
+static void finish_geom(ConvP& p) {
+    p.S = 128 / p.HJ;
+    if (p.S < 1) p.S = 1;
+    p.HP = p.Hin + 4;
+    while (p.S > 1 && p.S * p.HP > 320) --p.S;
+    int ar = p.S * p.HP;
+    while ((ar & 7) != 2) ++ar;
+    p.arows = ar;
+}
+static ConvP geom_s1(int R, int Hl, int KS) {
+    ConvP p;
+    memset(&p, 0, sizeof p);
+    p.R = R; p.Hout = Hl; p.Hin = Hl; p.HJ = Hl; p.ostride = 1; p.istride = 1; p.nphase = 1;
+    p.ntaps[0] = KS;
+    for (int k = 0; k < KS; ++k) { p.tap_k[0][k] = k; p.tap_shift[0][k] = k - KS / 2; }
+    finish_geom(p);
+    return p;
+}
+// stride-2 gather: hi = 2*ho - 1 + k  (Downsample1d forward KS=3; Upsample1d backward KS=4)
+static ConvP geom_s2(int R, int Hout, int KS) {
+    ConvP p;
+    memset(&p, 0, sizeof p);
+    p.R = R; p.Hout = Hout; p.Hin = 2 * Hout; p.HJ = Hout; p.ostride = 1; p.istride = 2; p.nphase = 1;
+    p.ntaps[0] = KS;
+    for (int k = 0; k < KS; ++k) { p.tap_k[0][k] = k; p.tap_shift[0][k] = k - 1; }
+    finish_geom(p);
+    return p;
+}
+// stride-2 scatter as two output phases: ho = 2j+phase, hi = (ho + 1 - k)/2
+// (Upsample1d forward KS=4; Downsample1d backward KS=3)
+static ConvP geom_t2(int R, int Hin, int KS) {
+    ConvP p;
+    memset(&p, 0, sizeof p);
+    p.R = R; p.Hout = 2 * Hin; p.Hin = Hin; p.HJ = Hin; p.ostride = 2; p.istride = 1; p.nphase = 2;
+    if (KS == 4) {
+        p.ntaps[0] = 2; p.tap_k[0][0] = 1; p.tap_shift[0][0] = 0; p.tap_k[0][1] = 3; p.tap_shift[0][1] = -1;
+        p.ntaps[1] = 2; p.tap_k[1][0] = 0; p.tap_shift[1][0] = 1; p.tap_k[1][1] = 2; p.tap_shift[1][1] = 0;
+    } else {
+        p.ntaps[0] = 1; p.tap_k[0][0] = 1; p.tap_shift[0][0] = 0;
+        p.ntaps[1] = 2; p.tap_k[1][0] = 0; p.tap_shift[1][0] = 1; p.tap_k[1][1] = 2; p.tap_shift[1][1] = 0;
+    }
+    finish_geom(p);
+    return p;
+}
+
+// ------------------------------------------------------------------ one eps evaluation
+struct Ctx {
+    pmp_model* m;
+    cudaStream_t st;
+    bool dry;          // only count workspace
+    size_t used = 0;   // floats
+    int R, H, n_cond;
+    const int64_t* t;
+    const float* embRow;   // cfg0: embR rows of this chunk; cfg3: E rows of this chunk
+    int rc = 0;
+    float* alloc(size_t n) {
+        n = (n + 3) & ~(size_t)3;
+        float* p = dry ? nullptr : m->ws + used;
+        used += n;
+        return p;
+    }
+    void conv(const ConvP& p) {
+        if (dry || rc) return;
+        rc = launch_conv_simt(p, st);
+    }
+    void dbg(const std::string& name, float* p, int64_t n) {
+        if (!dry) m->dbg[name] = std::make_pair(p, n);
+    }
+};
+
+static void set_emb(Ctx& c, ConvP& p, const ResB& b) {
+    const pmp_model* m = c.m;
+    if (m->arch.time_mlp_config == 0) {
+        p.embT = m->embT; p.tidx = c.t; p.ldeT = m->Ctot; p.tmax = m->arch.n_timesteps - 1;
+        p.embR = c.embRow; p.ldeR = m->Ctot; p.n_cond = c.n_cond;
+    } else {
+        p.embR = c.embRow; p.ldeR = m->Ctot; p.n_cond = c.R;
+    }
+    p.eoff = b.eoff;
+}
+
+// out = ResidualTemporalBlock_dd(x)   (temporal_dd.py:71-74)
+static void res_fwd(Ctx& c, int bi, const Act& x, Act& out) {
+    pmp_model* m = c.m;
+    ResB& b = m->blocks[bi];
+    const int R = c.R, Hl = x.Hl, Co = b.Cout;
+    for (int j = 0; j < 2; ++j) {
+        b.cb[j].yhat = c.alloc((size_t)R * Hl * Co);
+        b.cb[j].rstd = c.alloc((size_t)R * 8);
+        c.dbg("yhat:" + b.pfx + (j ? "blocks.1." : "blocks.0."), b.cb[j].yhat, (int64_t)R * Hl * Co);
+    }
+    float* mid = c.alloc((size_t)R * Hl * Co);
+    ConvP p = geom_s1(R, Hl, 5);
+    p.A1 = x.p; p.lda1 = x.ld; p.C1 = b.Cin; p.W1 = m->A(b.cb[0].Wf); p.N = Co;
+    p.bias = m->A(b.cb[0].bias); p.gn_fwd = 1; p.gamma = m->A(b.cb[0].gamma); p.beta = m->A(b.cb[0].beta);
+    p.yhat = b.cb[0].yhat; p.ldy = Co; p.rstd = b.cb[0].rstd; p.act = m->arch.act;
+    set_emb(c, p, b);
+    p.out = mid; p.ldo = Co;
+    c.conv(p);
+    ConvP q = geom_s1(R, Hl, 5);
+    q.A1 = mid; q.lda1 = Co; q.C1 = Co; q.W1 = m->A(b.cb[1].Wf); q.N = Co;
+    q.bias = m->A(b.cb[1].bias); q.gn_fwd = 1; q.gamma = m->A(b.cb[1].gamma); q.beta = m->A(b.cb[1].beta);
+    q.yhat = b.cb[1].yhat; q.ldy = Co; q.rstd = b.cb[1].rstd; q.act = m->arch.act;
+    if (b.has_res) {
+        q.A2 = x.p; q.lda2 = x.ld; q.C2 = b.Cin; q.W2 = m->A(b.Rf); q.bias2 = m->A(b.Rbias);
+    } else {
+        q.ident = x.p; q.ldi = x.ld;
+    }
+    q.out = out.p; q.ldo = out.ld;
+    c.conv(q);
+    out.C = Co; out.Hl = Hl; out.blk = bi;
+    c.dbg("out:" + b.pfx, out.p, out.ld == Co ? (int64_t)R * Hl * Co : 0);
+}
+
+// standalone GroupNorm backward through the CB1 of the block that produced `x`
+static void gn_bwd_of(Ctx& c, const Act& x, const float* raw, int ldr, float* gy) {
+    if (c.dry || c.rc) return;
+    pmp_model* m = c.m;
+    const CBW& cb = m->blocks[x.blk].cb[1];
+    c.rc = launch_gn_bwd(raw, ldr, cb.yhat, x.C, cb.rstd, m->A(cb.gamma), m->A(cb.beta), m->arch.act, gy, x.C, c.R,
+                         x.Hl, x.C, c.st);
+}
+
+// launches a backward conv `p` whose result is the gradient w.r.t. activation `x`;
+// emits raw (+addend) and, when `x` came out of a residual block, the GroupNorm-backward'ed
+// gradient for that block's second conv (fused when one tile holds whole slabs)
+static Grad emit_grad(Ctx& c, ConvP& p, const Act& x, const float* addend, int ldad, float* raw_dst, int ld_dst,
+                      bool fusable) {
+    Grad g;
+    g.raw = raw_dst ? raw_dst : c.alloc((size_t)c.R * x.Hl * x.C);
+    g.ldr = raw_dst ? ld_dst : x.C;
+    p.out = g.raw; p.ldo = g.ldr;
+    p.addend = addend; p.ldad = ldad;
+    p.act = c.m->arch.act;
+    if (x.blk >= 0) {
+        g.gy = c.alloc((size_t)c.R * x.Hl * x.C);
+        if (fusable && p.N == x.C) {
+            const CBW& cb = c.m->blocks[x.blk].cb[1];
+            p.gn_bwd = 1; p.gamma = c.m->A(cb.gamma); p.beta = c.m->A(cb.beta);
+            p.yhat = cb.yhat; p.ldy = x.C; p.rstd = cb.rstd; p.gy = g.gy; p.ldg = x.C;
+            c.conv(p);
+        } else {
+            c.conv(p);
+            gn_bwd_of(c, x, g.raw, g.ldr, g.gy);
+        }
+    } else {
+        c.conv(p);
+    }
+    return g;
+}
+
+// gradient through a residual block: gout = dE/d(out) -> dE/d(x)   
+static Grad res_bwd(Ctx& c, int bi, const Grad& gout, const Act& x, const float* addend, int ldad, float* raw_dst,
+                    int ld_dst) {
+    pmp_model* m = c.m;
+    ResB& b = m->blocks[bi];
+    const int R = c.R, Hl = x.Hl, Co = b.Cout;
+    float* gy0 = c.alloc((size_t)R * Hl * Co);
+    ConvP p = geom_s1(R, Hl, 5);
+    p.A1 = gout.gy; p.lda1 = Co; p.C1 = Co; p.W1 = m->A(b.cb[1].Wb); p.N = Co;
+    p.gn_bwd = 1; p.gamma = m->A(b.cb[0].gamma); p.beta = m->A(b.cb[0].beta);
+    p.yhat = b.cb[0].yhat; p.ldy = Co; p.rstd = b.cb[0].rstd; p.gy = gy0; p.ldg = Co; p.act = m->arch.act;
+    c.conv(p);
+    ConvP q = geom_s1(R, Hl, 5);
+    q.A1 = gy0; q.lda1 = Co; q.C1 = Co; q.W1 = m->A(b.cb[0].Wb); q.N = b.Cin;
+    if (b.has_res) {
+        q.A2 = gout.raw; q.lda2 = gout.ldr; q.C2 = Co; q.W2 = m->A(b.Rb);
+    } else {
+        q.ident = gout.raw; q.ldi = gout.ldr;
+    }
+    Grad g = emit_grad(c, q, x, addend, ldad, raw_dst, ld_dst, true);
+    c.dbg("gx:" + b.pfx, g.raw, g.ldr == x.C ? (int64_t)R * Hl * x.C : 0);
+    return g;
+}
+
+static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, float* u_out) {
+    pmp_model* m = c.m;
+    const int R = c.R, H = c.H, nl = m->nl, D = m->arch.transition_dim;
+    std::vector<int> Hl(nl);
+    Hl[0] = H;
+    for (int L = 1; L < nl; ++L) Hl[L] = m->has_down(L - 1) ? Hl[L - 1] / 2 : Hl[L - 1];
+    // concat buffers for skip levels 1..nl-1: [R][Hl][2*C]; level 0 skip is never consumed
+    std::vector<float*> cat(nl, nullptr);
+    for (int L = 1; L < nl; ++L) cat[L] = c.alloc((size_t)R * Hl[L] * 2 * m->dims[L + 1]);
+    std::vector<Act> lvl_in(nl), lvl_a(nl), lvl_b(nl);
+    Act cur;
+    cur.p = const_cast<float*>(x_in); cur.ld = D; cur.C = D; cur.Hl = H; cur.blk = -1;
+    for (int L = 0; L < nl; ++L) {
+        const int C = m->dims[L + 1];
+        lvl_in[L] = cur;
+        Act a; a.p = c.alloc((size_t)R * Hl[L] * C); a.ld = C;
+        res_fwd(c, 2 * L, cur, a);
+        Act b;
+        if (L >= 1) { b.p = cat[L] + C; b.ld = 2 * C; } else { b.p = c.alloc((size_t)R * Hl[L] * C); b.ld = C; }
+        res_fwd(c, 2 * L + 1, a, b);
+        lvl_a[L] = a; lvl_b[L] = b;
+        if (m->has_down(L)) {
+            Act d; d.p = c.alloc((size_t)R * (Hl[L] / 2) * C); d.ld = C; d.C = C; d.Hl = Hl[L] / 2; d.blk = -1;
+            ConvP p = geom_s2(R, Hl[L] / 2, 3);
+            p.A1 = b.p; p.lda1 = b.ld; p.C1 = C; p.W1 = m->A(m->downc[L].Wf); p.N = C; p.bias = m->A(m->downc[L].bias);
+            p.out = d.p; p.ldo = d.ld;
+            c.conv(p);
+            cur = d;
+        } else {
+            cur = b;
+        }
+    }
+    const int bmid = 2 * nl;
+    const int Cm = m->dims[nl];
+    Act mid_in = cur;
+    Act m1; m1.p = c.alloc((size_t)R * Hl[nl - 1] * Cm); m1.ld = Cm;
+    res_fwd(c, bmid, cur, m1);
+    Act m2; m2.p = cat[nl - 1]; m2.ld = 2 * Cm;
+    res_fwd(c, bmid + 1, m1, m2);
+    cur = m2;
+    std::vector<Act> up_in(nl), up_a(nl), up_b(nl), up_out(nl);
+    for (int ind = 0; ind < nl - 1; ++ind) {
+        const int Ls = nl - 1 - ind, Cs = m->dims[Ls + 1], Co = m->dims[Ls], h = Hl[Ls];
+        Act catv; catv.p = cat[Ls]; catv.ld = 2 * Cs; catv.C = 2 * Cs; catv.Hl = h; catv.blk = -1;
+        up_in[ind] = cur;   // first half of the concat (view), with its producer
+        Act a; a.p = c.alloc((size_t)R * h * Co); a.ld = Co;
+        res_fwd(c, bmid + 2 + 2 * ind, catv, a);
+        const bool up = m->has_up(ind);
+        const bool last = ind == nl - 2;
+        Act b;
+        if (!up && !last) { b.p = cat[Ls - 1]; b.ld = 2 * Co; } else { b.p = c.alloc((size_t)R * h * Co); b.ld = Co; }
+        res_fwd(c, bmid + 3 + 2 * ind, a, b);
+        up_a[ind] = a; up_b[ind] = b;
+        if (up) {
+            Act o; o.C = Co; o.Hl = 2 * h; o.blk = -1;
+            if (!last) { o.p = cat[Ls - 1]; o.ld = 2 * Co; } else { o.p = c.alloc((size_t)R * 2 * h * Co); o.ld = Co; }
+            ConvP p = geom_t2(R, h, 4);
+            p.A1 = b.p; p.lda1 = b.ld; p.C1 = Co; p.W1 = m->A(m->upc[ind].Wf); p.N = Co; p.bias = m->A(m->upc[ind].bias);
+            p.out = o.p; p.ldo = o.ld;
+            c.conv(p);
+            cur = o;
+        } else {
+            cur = b;
+        }
+        up_out[ind] = cur;
+    }
+    if (!c.dry && cur.Hl != H) {
+        set_error("U-Net output horizon %d != input horizon %d (down/up sampling mismatch)", cur.Hl, H);
+        return PMP_ERR_ARG;
+    }
+    // final_conv: Conv1dBlock_dd(dim,dim,5) + Conv1d(dim, D, 1)
+    const int C0 = m->dims[1];
+    CBW& fcb = m->finalcb;
+    fcb.yhat = c.alloc((size_t)R * H * C0);
+    fcb.rstd = c.alloc((size_t)R * 8);
+    float* f = c.alloc((size_t)R * H * C0);
+    {
+        ConvP p = geom_s1(R, H, 5);
+        p.A1 = cur.p; p.lda1 = cur.ld; p.C1 = C0; p.W1 = m->A(fcb.Wf); p.N = C0; p.bias = m->A(fcb.bias);
+        p.gn_fwd = 1; p.gamma = m->A(fcb.gamma); p.beta = m->A(fcb.beta); p.yhat = fcb.yhat; p.ldy = C0;
+        p.rstd = fcb.rstd; p.act = m->arch.act; p.out = f; p.ldo = C0;
+        c.conv(p);
+    }
+    float* u = u_out ? u_out : c.alloc((size_t)R * H * D);
+    {
+        if (energy && !c.dry && !c.rc) {
+            cudaError_t e = cudaMemsetAsync(energy, 0, (size_t)R * sizeof(float), c.st);
+            if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return PMP_ERR_CUDA; }
+        }
+        ConvP p = geom_s1(R, H, 1);
+        p.A1 = f; p.lda1 = C0; p.C1 = C0; p.W1 = m->A(m->fin1Wf); p.N = D; p.bias = m->A(m->fin1b);
+        p.out = u; p.ldo = D; p.energy = energy;
+        c.conv(p);
+    }
+    c.dbg("u", u, (int64_t)R * H * D);
+
+    // ================= backward: seed g_u = u (E = 0.5*sum u^2) =================
+    float* gyf = c.alloc((size_t)R * H * C0);
+    {
+        ConvP p = geom_s1(R, H, 1);
+        p.A1 = u; p.lda1 = D; p.C1 = D; p.W1 = m->A(m->fin1Wb); p.N = C0;
+        p.gn_bwd = 1; p.gamma = m->A(fcb.gamma); p.beta = m->A(fcb.beta); p.yhat = fcb.yhat; p.ldy = C0;
+        p.rstd = fcb.rstd; p.gy = gyf; p.ldg = C0; p.act = m->arch.act;
+        c.conv(p);
+    }
+    Grad g;
+    {
+        // gradient w.r.t. the input of final_conv (= up_out[nl-2])
+        ConvP p = geom_s1(R, H, 5);
+        p.A1 = gyf; p.lda1 = C0; p.C1 = C0; p.W1 = m->A(fcb.Wb); p.N = C0;
+        g = emit_grad(c, p, up_out[nl - 2], nullptr, 0, nullptr, 0, true);
+    }
+    std::vector<float*> skipg(nl, nullptr);
+    std::vector<int> skipld(nl, 0);
+    for (int ind = nl - 2; ind >= 0; --ind) {
+        const int Ls = nl - 1 - ind, Cs = m->dims[Ls + 1], Co = m->dims[Ls], h = Hl[Ls];
+        if (m->has_up(ind)) {
+            // Upsample1d backward: strided conv with the same weight (App. G item 6)
+            ConvP p = geom_s2(R, h, 4);
+            p.A1 = g.raw; p.lda1 = g.ldr; p.C1 = Co; p.W1 = m->A(m->upc[ind].Wb); p.N = Co;
+            g = emit_grad(c, p, up_b[ind], nullptr, 0, nullptr, 0, true);
+        }
+        g = res_bwd(c, bmid + 3 + 2 * ind, g, up_a[ind], nullptr, 0, nullptr, 0);
+        Act catv; catv.C = 2 * Cs; catv.Hl = h; catv.blk = -1;
+        Grad gc = res_bwd(c, bmid + 2 + 2 * ind, g, catv, nullptr, 0, nullptr, 0);
+        // split the concat gradient: [:Cs] continues along the up path, [Cs:] goes to the skip
+        skipg[Ls] = gc.raw + Cs; skipld[Ls] = 2 * Cs;
+        g = Grad();
+        g.raw = gc.raw; g.ldr = 2 * Cs;
+        if (up_in[ind].blk >= 0) {
+            g.gy = c.alloc((size_t)R * h * Cs);
+            gn_bwd_of(c, up_in[ind], g.raw, g.ldr, g.gy);
+        }
+    }
+    g = res_bwd(c, bmid + 1, g, m1, nullptr, 0, nullptr, 0);
+    {
+        // mid_block1 input == output of the last down level (also skip nl-1)
+        const bool sk = nl - 1 >= 1;
+        g = res_bwd(c, bmid, g, mid_in, sk ? skipg[nl - 1] : nullptr, sk ? skipld[nl - 1] : 0, nullptr, 0);
+    }
+    for (int L = nl - 1; L >= 0; --L) {
+        g = res_bwd(c, 2 * L + 1, g, lvl_a[L], nullptr, 0, nullptr, 0);
+        if (L == 0) {
+            res_bwd(c, 0, g, lvl_in[0], nullptr, 0, eps_out, D);
+            break;
+        }
+        const bool prev_down = m->has_down(L - 1);
+        if (!prev_down) {
+            // input of this level is the previous level's block output (also skip L-1 when L-1 >= 1)
+            const bool sk = L - 1 >= 1;
+            g = res_bwd(c, 2 * L, g, lvl_in[L], sk ? skipg[L - 1] : nullptr, sk ? skipld[L - 1] : 0, nullptr, 0);
+        } else {
+            g = res_bwd(c, 2 * L, g, lvl_in[L], nullptr, 0, nullptr, 0);
+            // Downsample1d backward: transposed conv, output_padding 1 (App. G item 5)
+            const int C = m->dims[L];
+            ConvP p = geom_t2(R, Hl[L], 3);
+            p.A1 = g.raw; p.lda1 = g.ldr; p.C1 = C; p.W1 = m->A(m->downc[L - 1].Wb); p.N = C;
+            const bool sk = L - 1 >= 1;
+            g = emit_grad(c, p, lvl_b[L - 1], sk ? skipg[L - 1] : nullptr, sk ? skipld[L - 1] : 0, nullptr, 0, false);
+        }
+    }
+    return c.rc;
+}
+
+static size_t wall_table_width(const pmp_model* m) {
+    return m->arch.time_mlp_config == 0 ? (size_t)m->Ctot : (size_t)m->blocks.size() * m->hid;
+}
+
+// the wall-only part of every block embedding (constant over diffusion steps) for n_cond plans:
+// cfg0: tab [n_cond][Ctot] = W[:,64:] act(wemb);  cfg3: tab [n_cond][nblk*hid] = W0[:,64:] wemb
+static int prepare_wall_tables(pmp_model* m, const float* wemb, int n_cond, float* tab, cudaStream_t st) {
+    const pmp_arch& a = m->arch;
+    const int tdim = a.dim + a.wall_embed_dim;
+    const int nblk = (int)m->blocks.size();
+    int rc;
+    if (n_cond == 0) return 0;
+    if (a.time_mlp_config == 0) {
+        for (auto& b : m->blocks)
+            if ((rc = launch_small_linear(wemb, a.wall_embed_dim, a.wall_embed_dim, m->A(b.tmW), tdim, a.dim, nullptr, 1,
+                                          a.act, tab + b.eoff, m->Ctot, b.Cout, n_cond, 0, st)))
+                return rc;
+    } else {
+        for (int i = 0; i < nblk; ++i)
+            if ((rc = launch_small_linear(wemb, a.wall_embed_dim, a.wall_embed_dim, m->A(m->blocks[i].tm0W), tdim, a.dim,
+                                          nullptr, 0, a.act, tab + (size_t)i * m->hid, nblk * m->hid, m->hid, n_cond,
+                                          0, st)))
+                return rc;
+    }
+    return 0;
+}
+
+static size_t workspace_floats(pmp_model* m, int R, int H) {
+    Ctx c;
+    c.m = m; c.st = 0; c.dry = true; c.R = R; c.H = H; c.n_cond = 0; c.t = nullptr; c.embRow = nullptr;
+    run_unet(c, nullptr, nullptr, nullptr, nullptr);
+    return c.used;
+}
+
+// eps for R rows given prepared wall tables (rows < n_cond conditional)
+static int eps_rows(pmp_model* m, const float* x, const int64_t* t, const float* wall_tab, int n_cond, int R, int H,
+                    float* eps, float* energy, float* u, cudaStream_t st) {
+    const int D = m->arch.transition_dim;
+    PMP_REQUIRE(H % 4 == 0 && H >= 32 && H <= 128, "horizon %d unsupported (multiple of 4 in [32,128])", H);
+    const int chunk = m->row_chunk;
+    int rc;
+    const int Rc_max = R < chunk ? R : chunk;
+    const size_t need = workspace_floats(m, Rc_max, H);
+    if ((rc = grow(&m->ws, &m->ws_n, need))) return rc;
+    const int nblk = (int)m->blocks.size();
+    for (int r0 = 0; r0 < R; r0 += chunk) {
+        const int Rc = (R - r0) < chunk ? (R - r0) : chunk;
+        int nc = n_cond - r0;
+        nc = nc < 0 ? 0 : (nc > Rc ? Rc : nc);
+        Ctx c;
+        c.m = m; c.st = st; c.dry = false; c.R = Rc; c.H = H; c.n_cond = nc; c.t = t + r0;
+        if (m->arch.time_mlp_config == 0) {
+            c.embRow = wall_tab ? wall_tab + (size_t)r0 * m->Ctot : nullptr;
+        } else {
+            // per-step block embeddings: E = W2 * act(Ht[t] + Hw[r]) + b2
+            if ((rc = grow(&m->hidb, &m->hidb_n, (size_t)chunk * nblk * m->hid))) return rc;
+            if ((rc = grow(&m->embE, &m->embE_n, (size_t)chunk * m->Ctot))) return rc;
+            const float* Hw = (wall_tab && nc > 0) ? wall_tab + (size_t)r0 * nblk * m->hid : nullptr;
+            if ((rc = launch_cfg3_hidden(m->embT, c.t, m->arch.n_timesteps - 1, Hw, Hw ? nc : 0, Rc, nblk * m->hid,
+                                         m->arch.act, m->hidb, st)))
+                return rc;
+            for (int i = 0; i < nblk; ++i) {
+                const ResB& b = m->blocks[i];
+                if ((rc = launch_small_linear(m->hidb + (size_t)i * m->hid, nblk * m->hid, m->hid, m->A(b.tmW), m->hid, 0,
+                                              m->A(b.tmB), 0, m->arch.act, m->embE + b.eoff, m->Ctot, b.Cout, Rc, 0, st)))
+                    return rc;
+            }
+            c.embRow = m->embE;
+        }
+        m->dbg.clear();
+        rc = run_unet(c, x + (size_t)r0 * H * D, eps + (size_t)r0 * H * D, energy ? energy + r0 : nullptr,
+                      u ? u + (size_t)r0 * H * D : nullptr);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace pmp
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char* pmp_last_error(void) { return g_err; }
+int pmp_abi_version(void) { return PMP_ABI_VERSION; }
+uint64_t pmp_launch_count(void) { return g_launches.load(); }
+
+int pmp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+int pmp_model_create(const pmp_arch* arch, int device, pmp_model** out) {
+    PMP_REQUIRE(arch && out, "null argument");
+    int n = 0;
+    PMP_CUDA_OK(cudaGetDeviceCount(&n));
+    PMP_REQUIRE(device >= 0 && device < n, "device %d not available (%d visible)", device, n);
+    cudaDeviceProp p;
+    PMP_CUDA_OK(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, p.major, p.minor);
+        return PMP_ERR_CUDA;
+    }
+    PMP_CUDA_OK(cudaSetDevice(device));
+    pmp_model* m = new pmp_model();
+    m->arch = *arch;
+    m->device = device;
+    if (m->arch.down_times <= 0) m->arch.down_times = 1 << 20;
+    *out = m;
+    return 0;
+}
+
+void pmp_model_destroy(pmp_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    float* bufs[] = {m->arena, m->temb_tab, m->embT, m->embR, m->embE, m->hidb, m->ws};
+    for (float* b : bufs)
+        if (b) cudaFree(b);
+    delete m;
+}
+
+int pmp_model_set_weight(pmp_model* m, const char* key, const float* data, const int64_t* shape, int ndim,
+                         int on_device) {
+    PMP_REQUIRE(m && key && data && shape && ndim >= 1 && ndim <= 4, "bad argument");
+    HostT t;
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+        PMP_REQUIRE(shape[i] > 0, "weight '%s': non-positive dimension", key);
+        t.shape.push_back(shape[i]);
+        n *= shape[i];
+    }
+    t.v.resize((size_t)n);
+    if (on_device) {
+        PMP_CUDA_OK(cudaSetDevice(m->device));
+        PMP_CUDA_OK(cudaMemcpy(t.v.data(), data, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+        memcpy(t.v.data(), data, (size_t)n * sizeof(float));
+    }
+    m->hw[key] = std::move(t);
+    m->finalized = false;
+    return 0;
+}
+
+int pmp_model_finalize(pmp_model* m) {
+    PMP_REQUIRE(m, "null model");
+    PMP_CUDA_OK(cudaSetDevice(m->device));
+    return finalize_model(m);
+}
+
+int pmp_model_set_row_chunk(pmp_model* m, int rows) {
+    PMP_REQUIRE(m && rows >= 2, "row chunk must be >= 2");
+    m->row_chunk = rows;
+    return 0;
+}
+
+int pmp_model_set_gemm_path(pmp_model* m, int path) {
+    PMP_REQUIRE(m && (path == 0 || path == 1), "gemm path must be 0 or 1");
+    m->gemm_path = path;
+    return 0;
+}
+
+size_t pmp_model_workspace_bytes(const pmp_model* m) { return m ? m->ws_n * sizeof(float) : 0; }
+
+int pmp_wall_embed(pmp_model* m, const float* walls, int B, int wall_len, float* wemb, void* stream) {
+    PMP_REQUIRE(m && m->finalized, "model not finalized");
+    PMP_REQUIRE(wall_len > 0 && wall_len % m->arch.vit_token_dim == 0, "wall vector length %d is not a multiple of %d",
+                wall_len, m->arch.vit_token_dim);
+    PMP_CUDA_OK(cudaSetDevice(m->device));
+    return launch_vit(m->vit, walls, B, wall_len / m->arch.vit_token_dim, wemb, (cudaStream_t)stream);
+}
+
+int pmp_unet_eps(pmp_model* m, const float* x, const int64_t* t, const float* wemb, int n_cond, int R, int H,
+                 float* eps, float* energy, float* u, void* stream) {
+    PMP_REQUIRE(m && m->finalized, "model not finalized");
+    PMP_REQUIRE(x && t && eps && R >= 1 && n_cond >= 0 && n_cond <= R, "bad argument");
+    PMP_REQUIRE(n_cond == 0 || wemb, "wemb required for conditional rows");
+    PMP_CUDA_OK(cudaSetDevice(m->device));
+    int rc;
+    if ((rc = grow(&m->embR, &m->embR_n, (size_t)(n_cond > 0 ? n_cond : 1) * wall_table_width(m)))) return rc;
+    if ((rc = prepare_wall_tables(m, wemb, n_cond, m->embR, (cudaStream_t)stream))) return rc;
+    return eps_rows(m, x, t, m->embR, n_cond, R, H, eps, energy, u, (cudaStream_t)stream);
+}
+
+int pmp_step(int kind, const float* x, const float* const* ec, const float* const* eu, const float* w, int K,
+             int base, const float* coef, const float* noise, uint64_t seed, uint64_t offset, const float* start,
+             const float* goal, float* xo, int B, int H, int D, void* stream) {
+    PMP_REQUIRE(x && ec && eu && w && coef && xo, "null argument");
+    PMP_REQUIRE(kind == PMP_STEP_DDPM || kind == PMP_STEP_DDIM, "bad step kind");
+    return launch_step(kind, x, ec, eu, w, K, base, coef, noise, seed, offset, 0, start, goal, xo, nullptr, 0, B, H, D,
+                       (cudaStream_t)stream);
+}
+
+int pmp_init_noise(float* x, const float* noise, uint64_t seed, uint64_t offset, float var_temp, const float* start,
+                   const float* goal, int B, int H, int D, void* stream) {
+    PMP_REQUIRE(x, "null argument");
+    return launch_init_noise(x, noise, seed, offset, 0, var_temp, start, goal, nullptr, 0, B, H, D,
+                             (cudaStream_t)stream);
+}
+
+int pmp_unnormalize(const float* x, const float* lo, const float* hi, float* out, int64_t rows, int D, void* stream) {
+    PMP_REQUIRE(x && lo && hi && out, "null argument");
+    return launch_unnormalize(x, lo, hi, out, rows, D, (cudaStream_t)stream);
+}
+
+int pmp_pick_first_valid(const uint8_t* valid, const int32_t* nchk, int n_prob, int n_samp, int32_t* chosen,
+                         uint8_t* success, int32_t* total, void* stream) {
+    PMP_REQUIRE(valid && nchk && chosen && success && total && n_samp >= 1, "bad argument");
+    return launch_pick_first_valid(valid, nchk, n_prob, n_samp, chosen, success, total, (cudaStream_t)stream);
+}
+
+int pmp_sample(const pmp_sample_args* a, void* stream) {
+    PMP_REQUIRE(a, "null argument");
+    PMP_REQUIRE(a->K >= 1 && a->K <= PMP_MAX_COMPOSE, "K out of range");
+    PMP_REQUIRE(a->B >= 1 && a->n_steps >= 1 && a->t_host && a->coef_host && a->x_dev && a->start_dev && a->goal_dev,
+                "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = a->K, B = a->B, H = a->H, D = a->D;
+    for (int k = 0; k < K; ++k) {
+        PMP_REQUIRE(a->models[k] && a->models[k]->finalized, "model %d not finalized", k);
+        PMP_REQUIRE(a->models[k]->arch.transition_dim == D, "model %d has transition_dim %d, expected %d", k,
+                    a->models[k]->arch.transition_dim, D);
+        PMP_REQUIRE(a->wemb_dev[k], "wemb_dev[%d] is null", k);
+    }
+    PMP_CUDA_OK(cudaSetDevice(a->models[0]->device));
+    // plans per pass: the CFG pair doubles the rows
+    int chunk = a->models[0]->row_chunk;
+    for (int k = 1; k < K; ++k)
+        if (a->models[k]->row_chunk < chunk) chunk = a->models[k]->row_chunk;
+    int Bc = chunk / 2;
+    if (Bc < 1) Bc = 1;
+    if (Bc > B) Bc = B;
+    const size_t tile = (size_t)Bc * H * D;
+    float* x2 = nullptr;
+    float* epsb = nullptr;
+    int64_t* t2 = nullptr;
+    PMP_CUDA_OK(cudaMallocAsync((void**)&x2, 2 * tile * sizeof(float), st));
+    PMP_CUDA_OK(cudaMallocAsync((void**)&epsb, (size_t)K * 2 * tile * sizeof(float), st));
+    PMP_CUDA_OK(cudaMallocAsync((void**)&t2, (size_t)2 * Bc * sizeof(int64_t), st));
+    float* wtab[PMP_MAX_COMPOSE] = {};
+    for (int k = 0; k < K; ++k)
+        PMP_CUDA_OK(cudaMallocAsync((void**)&wtab[k], (size_t)Bc * wall_table_width(a->models[k]) * sizeof(float), st));
+    const long tstride = (long)(a->n_steps + 1) * H * D;
+    int rc = 0;
+    for (int b0 = 0; b0 < B && !rc; b0 += Bc) {
+        const int Bn = (B - b0) < Bc ? (B - b0) : Bc;
+        const size_t n = (size_t)Bn * H * D;
+        float* x = a->x_dev + (size_t)b0 * H * D;
+        const float* start = a->start_dev + (size_t)b0 * D;
+        const float* goal = a->goal_dev + (size_t)b0 * D;
+        const uint64_t elem0 = (a->row_offset + (uint64_t)b0) * (uint64_t)(H * D);
+        float* tr = a->trace_dev ? a->trace_dev + (size_t)b0 * tstride : nullptr;
+        const size_t nstride = (size_t)B * H * D;
+        const float* nz = a->noise_dev ? a->noise_dev + (size_t)b0 * H * D : nullptr;
+        if ((rc = launch_init_noise(x, nz, a->seed, 0, elem0, a->var_temp, start, goal, tr, tstride, Bn, H, D, st))) break;
+        for (int k = 0; k < K && !rc; ++k)
+            rc = prepare_wall_tables(a->models[k], a->wemb_dev[k] + (size_t)b0 * a->models[k]->arch.wall_embed_dim, Bn,
+                                     wtab[k], st);
+        for (int s = 0; s < a->n_steps && !rc; ++s) {
+            if ((rc = launch_fill_i64(t2, (int64_t)a->t_host[s], (size_t)2 * Bn, st))) break;
+            const float* ec[PMP_MAX_COMPOSE];
+            const float* eu[PMP_MAX_COMPOSE];
+            if (cudaMemcpyAsync(x2, x, n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+                cudaMemcpyAsync(x2 + n, x, n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+                set_error("cudaMemcpyAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = PMP_ERR_CUDA;
+                break;
+            }
+            for (int k = 0; k < K && !rc; ++k) {
+                float* e2 = epsb + (size_t)k * 2 * tile;
+                rc = eps_rows(a->models[k], x2, t2, wtab[k], Bn, 2 * Bn, H, e2, nullptr, nullptr, st);
+                ec[k] = e2;
+                eu[k] = e2 + n;
+            }
+            if (rc) break;
+            const float* nzs = a->noise_dev ? a->noise_dev + (size_t)(s + 1) * nstride + (size_t)b0 * H * D : nullptr;
+            rc = launch_step(a->kind, x, ec, eu, a->w, K, a->base, a->coef_host + 8 * s, nzs, a->seed, (uint64_t)(s + 1),
+                             elem0, start, goal, x, tr ? tr + (size_t)(s + 1) * H * D : nullptr, tstride, Bn, H, D, st);
+        }
+    }
+    cudaFreeAsync(x2, st);
+    cudaFreeAsync(epsb, st);
+    cudaFreeAsync(t2, st);
+    for (int k = 0; k < K; ++k) cudaFreeAsync(wtab[k], st);
+    return rc;
+}
+
+int64_t pmp_debug_fetch(pmp_model* m, const char* name, float* host_out, int64_t capacity) {
+    if (!m || !name) return -1;
+    auto it = m->dbg.find(name);
+    if (it == m->dbg.end() || it->second.second == 0) return -1;
+    const int64_t n = it->second.second;
+    if (host_out) {
+        if (capacity < n) return -2;
+        cudaSetDevice(m->device);
+        if (cudaDeviceSynchronize() != cudaSuccess) return -3;
+        if (cudaMemcpy(host_out, it->second.first, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return -3;
+    }
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+"""GPU diagnostic (not a pytest file): layer-by-layer comparison of the CUDA U-Net forward /
+analytic backward with the CPU oracle.  Usage: python tests/gpu_diag_unet.py [family ...]"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "potential-motion-plan-release_b200"))
+
+from oracle import synth, unet_ref  # noqa: E402
+import pmp_b200  # noqa: E402
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def main(fams):
+    dev = torch.device("cuda:0")
+    for fam in fams:
+        a = synth.arch(fam)
+        cfg = unet_ref.UnetCfg(a["unet"])
+        sd = unet_ref.synth_weights(a["unet"], 1)
+        B, H, D = 3, a["horizon"], a["obs_dim"]
+        pr = synth.make_problems(fam, B, 3)
+        g = torch.Generator().manual_seed(11)
+        x = torch.randn(2 * B, H, D, generator=g)
+        t = torch.tensor([37] * (2 * B))
+        walls = torch.tensor(pr["walls"]).repeat(2, 1)
+        t0 = time.time()
+        eps_ref, u_ref, tape = unet_ref.eps_analytic(sd, cfg, x, t, walls, n_cond=B, return_tape=True)
+        eps_ag = unet_ref.eps_autograd(sd, cfg, x, t, walls, n_cond=B)
+        print("[%s] oracle %.2fs  analytic-vs-autograd %.2e" % (fam, time.time() - t0, rel(eps_ref, eps_ag)))
+        eng = pmp_b200.UnetEngine(a["unet"], sd, dev)
+        wemb = eng.wall_embed(torch.tensor(pr["walls"]))
+        wemb_ref = unet_ref.wall_embed(sd, cfg, torch.tensor(pr["walls"]))
+        print("  wall_embed rel err %.3e" % rel(wemb.cpu().numpy(), wemb_ref.numpy()))
+        eps, en, u = eng.eps(x, t, wemb, n_cond=B, want_energy=True, want_u=True)
+        torch.cuda.synchronize()
+        for pfx, (yh, r) in tape.items():
+            got = eng.debug_fetch("yhat:" + pfx)
+            if got is None:
+                continue
+            R_, C_, H_ = yh.shape
+            got = got.reshape(R_, H_, C_).transpose(0, 2, 1)
+            print("  yhat %-28s rel err %.3e" % (pfx, rel(got, yh.numpy())))
+        print("  u    rel err %.3e" % rel(u.cpu().numpy(), u_ref.numpy()))
+        print("  E    rel err %.3e" % rel(en.cpu().numpy(), (0.5 * u_ref * u_ref).sum(dim=(1, 2)).numpy()))
+        print("  eps  rel err %.3e   (max|eps| %.3f)" % (rel(eps.cpu().numpy(), eps_ag.numpy()), eps_ag.abs().max()))
+        for name in ("gx:ups.1.1.", "gx:ups.1.0.", "gx:ups.0.1.", "gx:ups.0.0.", "gx:mid_block2.", "gx:mid_block1.",
+                     "gx:downs.2.1.", "gx:downs.2.0.", "gx:downs.1.1.", "gx:downs.1.0.", "gx:downs.0.1."):
+            got = eng.debug_fetch(name)
+            if got is not None:
+                print("  %-20s finite=%s absmax=%.3e" % (name, bool(np.isfinite(got).all()), float(np.abs(got).max())))
+        # timing at a moderate batch
+        Bt = 512
+        xt = torch.randn(2 * Bt, H, D, device=dev)
+        tt = torch.full((2 * Bt,), 50, device=dev, dtype=torch.long)
+        wt = wemb[:1].repeat(Bt, 1)
+        eng.eps(xt, tt, wt, n_cond=Bt)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            eng.eps(xt, tt, wt, n_cond=Bt)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print("  eps-eval %d rows: %.2f ms  -> %.1f us/row" % (2 * Bt, ms, 1e3 * ms / (2 * Bt)))
+        del eng
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or ["m2d", "kuka", "dualkuka"])
