@@ -146,41 +146,48 @@ def state_dict_digest(sd):
 
 def maze2d_walls(rng, nw, hext, maze=5.0, gap=0.15):
     """random non-overlapping square walls (rand_rec_group.py:73-147, 242-251); returns
-    centres [nw,2] float64 sorted lexicographically"""
-    acc = []
-    while len(acc) < nw:
-        c = rng.uniform(hext + gap, maze - hext - gap, size=2)
-        ok = True
-        for a in acc:
-            if not (a[0] + hext + gap < c[0] - hext or a[0] - hext - gap > c[0] + hext
-                    or a[1] + hext + gap < c[1] - hext or a[1] - hext - gap > c[1] + hext):
-                ok = False
-                break
-        if ok:
+    centres [nw,2] float64 sorted lexicographically.  Greedy placement restarts when stuck."""
+    while True:
+        acc, tries = [], 0
+        while len(acc) < nw and tries < 200:
+            tries += 1
+            c = rng.uniform(hext + gap, maze - hext - gap, size=2)
+            if any(_box_overlap(a, c, hext, gap) for a in acc):
+                continue
             acc.append(c)
+        if len(acc) == nw:
+            break
     acc = np.array(acc, dtype=np.float64)
     order = np.lexsort((acc[:, 1], acc[:, 0]))
     return acc[order]
 
 
-_CONCAVE_QUADS = np.array([[-1, -1], [-1, 1], [1, 1], [1, -1]], dtype=np.float64)
+_CONCAVE_QUADS = np.array([[-1, 1], [1, 1], [1, -1], [-1, -1]], dtype=np.float64)
+
+
+def _box_overlap(a, b, hext, gap):
+    return not (a[0] + hext + gap < b[0] - hext or a[0] - hext - gap > b[0] + hext
+                or a[1] + hext + gap < b[1] - hext or a[1] - hext - gap > b[1] + hext)
 
 
 def maze2d_concave(rng, n_obj=7, hext=0.25, maze=5.0, gap=0.15):
     """concave obstacles (rand_rec_group_43.py:44-61,134-142): each object = 3 of the 4
-    quadrant squares around a centre; `mode` (1..4) names the missing quadrant.
-    Returns (tokens [n_obj,3] (cx,cy,mode) float64, boxes [3*n_obj,2] centres float64)."""
-    toks, boxes = [], []
-    while len(toks) < n_obj:
-        c = rng.uniform(2 * hext + gap, maze - 2 * hext - gap, size=2)
-        if any(np.all(np.abs(c - t[:2]) < 4 * hext + gap) for t in toks):
-            continue
-        mode = int(rng.integers(0, 4))
-        toks.append(np.array([c[0], c[1], mode + 1.0]))
-        for q in range(4):
-            if q != mode:
-                boxes.append(c + hext * _CONCAVE_QUADS[q])
-    return np.array(toks), np.array(boxes)
+    quadrant squares (order 1:(-,+) 2:(+,+) 3:(+,-) 4:(-,-)) around a centre, the deleted
+    quadrant index is `mode`; overlap is tested per small square.  Restarts when stuck.
+    Returns (tokens [n_obj,3] (cx,cy,mode+1) float64, boxes [3*n_obj,2] centres float64)."""
+    while True:
+        toks, boxes, tries = [], [], 0
+        while len(toks) < n_obj and tries < 400:
+            tries += 1
+            c = rng.uniform(2 * hext + gap, maze - 2 * hext - gap, size=2)
+            mode = int(rng.integers(0, 4))
+            new = [c + hext * _CONCAVE_QUADS[q] for q in range(4) if q != mode]
+            if any(_box_overlap(b, nb, hext, gap) for b in boxes for nb in new):
+                continue
+            toks.append(np.array([c[0], c[1], mode + 1.0]))
+            boxes.extend(new)
+        if len(toks) == n_obj:
+            return np.array(toks), np.array(boxes)
 
 
 def point_in_boxes(p, centers, hext, margin=0.01):

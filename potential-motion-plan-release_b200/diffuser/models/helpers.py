@@ -1,0 +1,38 @@
+"""Sampler helpers with the reference's names (diffuser/models/helpers.py:147-172, 211-254)."""
+import numpy as np
+import torch
+from torch import nn
+
+
+def extract(a, t, x_shape):
+    return a.gather(-1, t).reshape(t.shape[0], *((1,) * (len(x_shape) - 1)))
+
+
+def cosine_beta_schedule(timesteps, s=0.008, dtype=torch.float32):
+    n = timesteps + 1
+    grid = np.linspace(0, n, n)
+    acp = np.cos(((grid / n) + s) / (1 + s) * np.pi * 0.5) ** 2
+    acp = acp / acp[0]
+    return torch.tensor(np.clip(1 - (acp[1:] / acp[:-1]), a_min=0, a_max=0.999), dtype=dtype)
+
+
+def apply_conditioning(x, conditions, action_dim):
+    for t, val in conditions.items():
+        x[:, t, action_dim:] = val.clone()
+    return x
+
+
+class WeightedStateL2(nn.Module):
+    """holds `loss_fn.weights` so checkpoints load strictly (helpers.py:211-254); the training
+    loss itself (double backward through the U-Net) is outside the built hot path."""
+
+    def __init__(self, weights):
+        super().__init__()
+        self.register_buffer('weights', weights)
+
+    def forward(self, pred, targ):
+        loss = ((pred - targ) ** 2 * self.weights).mean()
+        return loss, {'a0_loss': loss}
+
+
+Losses = {'state_l2': WeightedStateL2}

@@ -1,0 +1,171 @@
+"""TemporalUnet_WCond: drop-in for diffuser/models/temporal_cond.py:63-334.
+
+Same constructor kwargs, parameter names / shapes / initialisation order (so
+`torch.manual_seed(s); TemporalUnet_WCond(**kw)` reproduces the reference's random init and
+reference checkpoints load with strict=True), but `forward` is not PyTorch: it hands the
+weights to libpmp_b200.so once and evaluates eps = dE/dx with hand-written sm_100a kernels
+(U-Net forward + analytic backward) instead of torch.autograd.grad (temporal_cond.py:321).
+The nn.Modules below are parameter containers only; they are never called.
+"""
+import torch
+from torch import nn
+
+import pmp_b200
+
+
+def _slots(n, filled):
+    """nn.Sequential with parameter-bearing modules at the reference's indices"""
+    return nn.Sequential(*[filled.get(i, nn.Identity()) for i in range(n)])
+
+
+def _conv_block(cin, cout):
+    # Conv1dBlock_dd (helpers.py:74-97): block.0 conv k5, block.2 GroupNorm(8)
+    m = nn.Module()
+    m.block = _slots(5, {0: nn.Conv1d(cin, cout, 5, padding=2), 2: nn.GroupNorm(8, cout)})
+    return m
+
+
+def _res_block(cin, cout, tdim, tm_cfg):
+    # ResidualTemporalBlock_dd (temporal_dd.py:9-55); construction order = RNG order
+    m = nn.Module()
+    m.blocks = nn.ModuleList([_conv_block(cin, cout), _conv_block(cout, cout)])
+    if tm_cfg == 3:
+        m.time_mlp = _slots(4, {0: nn.Linear(tdim, tdim * 2), 2: nn.Linear(tdim * 2, cout)})
+    elif tm_cfg == 2:
+        m.time_mlp = _slots(5, {1: nn.Linear(tdim, cout * 2), 3: nn.Linear(cout * 2, cout)})
+    else:
+        m.time_mlp = _slots(3, {1: nn.Linear(tdim, cout)})
+    m.residual_conv = nn.Conv1d(cin, cout, 1) if cin != cout else nn.Identity()
+    return m
+
+
+def _sampler(conv):
+    m = nn.Module()
+    m.conv = conv
+    return m
+
+
+def _vit(cfg):
+    # ViT1D (vit_vanilla.py:87-230)
+    dim, td = cfg['embed_dim'], cfg['patch_size'] * cfg.get('channels', 1)
+    tf = cfg.get('tf_config', {})
+    pe = tf.get('wall_sinPosEmb', False)
+    m = nn.Module()
+    if pe:
+        fdim = td * pe['num_octaves'] * 2
+        m.to_patch_embedding = _slots(8, {2: nn.LayerNorm(fdim), 3: nn.Linear(fdim, dim), 4: nn.Linear(dim, dim * 4),
+                                          6: nn.Linear(dim * 4, dim), 7: nn.LayerNorm(dim)})
+    else:
+        m.to_patch_embedding = _slots(6, {1: nn.Linear(td, dim), 2: nn.Linear(dim, dim * 4),
+                                          4: nn.Linear(dim * 4, dim), 5: nn.LayerNorm(dim)})
+    m.cls_token = nn.Parameter(torch.randn(1, 1, dim))
+    inner = cfg['num_heads'] * cfg['dim_head']
+    mlp = dim * cfg['mlp_ratio']
+    layers = []
+    for _ in range(cfg['depth']):
+        # PreNorm registers `norm` before `fn`, but `fn` is constructed first (RNG order)
+        attn, afn = nn.Module(), nn.Module()
+        afn.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        attn.norm = nn.LayerNorm(dim)
+        attn.fn = afn
+        ff, ffn = nn.Module(), nn.Module()
+        ffn.net = _slots(5, {0: nn.Linear(dim, mlp), 3: nn.Linear(mlp, dim)})
+        ff.norm = nn.LayerNorm(dim)
+        ff.fn = ffn
+        layers.append(nn.ModuleList([attn, ff]))
+    m.transformer = nn.Module()
+    m.transformer.layers = nn.ModuleList(layers)
+    return m
+
+
+class TemporalUnet_WCond(nn.Module):
+
+    def __init__(self, horizon, transition_dim, cond_dim, dim=32, dim_mults=(1, 2, 4, 8), num_walls=3,
+                 wall_embed_dim=32, wall_sinPosEmb={}, network_config={}):
+        super().__init__()
+        self._ctor = dict(horizon=horizon, transition_dim=transition_dim, cond_dim=cond_dim, dim=dim,
+                          dim_mults=tuple(dim_mults), num_walls=num_walls, wall_embed_dim=wall_embed_dim,
+                          wall_sinPosEmb=wall_sinPosEmb, network_config=network_config)
+        nc = network_config
+        self.network_config = nc
+        self.cat_t_w = nc.get('cat_t_w', False)
+        self.resblock_ksize = nc.get('resblock_ksize', 5)
+        self.use_downup_sample = nc.get('use_downup_sample', True)
+        self.energy_mode = nc.get('energy_mode', False)
+        self.energy_param_type = nc.get('energy_param_type', None)
+        self.conv_zero_init = nc.get('conv_zero_init', False)
+        self.wallLoc_encoder_type = nc.get('wallLoc_encoder', 'mlp').lower()
+        self.concept_drop_prob = nc.get('concept_drop_prob', -1.0)
+        self.last_conv_ksize = nc.get('last_conv_ksize', 1)
+        self.force_residual_conv = nc.get('force_residual_conv', False)
+        self.time_mlp_config = nc.get('time_mlp_config', False)
+        self.down_times = nc.get('down_times', 1e5)
+        assert self.use_downup_sample and self.resblock_ksize == 5, 'the default settings'
+        assert not self.force_residual_conv and self.last_conv_ksize == 1
+        # the configurations the sm_100a kernels are built for (every shipped config satisfies them)
+        pmp_b200._lib.make_arch(self._ctor)
+        if self.conv_zero_init or self.energy_param_type != 'L2':
+            raise NotImplementedError('only energy_param_type="L2" without conv_zero_init is built')
+        tm_cfg = int(self.time_mlp_config or 0)
+        if tm_cfg not in (0, 3):
+            raise NotImplementedError('time_mlp_config %r is not built' % (self.time_mlp_config,))
+
+        dims = [transition_dim] + [dim * m for m in dim_mults]
+        in_out = list(zip(dims[:-1], dims[1:]))
+        tdim = dim + wall_embed_dim
+        n_res = len(in_out)
+        self.time_mlp = _slots(4, {1: nn.Linear(dim, dim * 4), 3: nn.Linear(dim * 4, dim)})
+        self.vit1d_config = nc['vit1d_config']
+        self.wallLoc_encoder = _vit(self.vit1d_config)
+        self.downs = nn.ModuleList()
+        self.ups = nn.ModuleList()
+        for ind, (ci, co) in enumerate(in_out):
+            last = ind >= n_res - 1 or ind >= self.down_times
+            self.downs.append(nn.ModuleList([
+                _res_block(ci, co, tdim, tm_cfg), _res_block(co, co, tdim, tm_cfg),
+                _sampler(nn.Conv1d(co, co, 3, 2, 1)) if not last else nn.Identity()]))
+        mid = dims[-1]
+        self.mid_block1 = _res_block(mid, mid, tdim, tm_cfg)
+        self.mid_block2 = _res_block(mid, mid, tdim, tm_cfg)
+        for ind, (ci, co) in enumerate(reversed(in_out[1:])):
+            last = ind >= n_res - 1 or ind < (n_res - self.down_times - 1)
+            self.ups.append(nn.ModuleList([
+                _res_block(co * 2, ci, tdim, tm_cfg), _res_block(ci, ci, tdim, tm_cfg),
+                _sampler(nn.ConvTranspose1d(ci, ci, 4, 2, 1)) if not last else nn.Identity()]))
+        self.final_conv = nn.Sequential(_conv_block(dim, dim), nn.Conv1d(dim, transition_dim, 1))
+        self._engine = None
+        self._engine_sig = None
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _signature(self):
+        ps = list(self.parameters())
+        return (ps[0].device, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps[:4]))
+
+    def engine(self, n_timesteps=100):
+        """the pmp_b200.UnetEngine holding this module's current weights (rebuilt when they change)"""
+        sig = (self._signature(), n_timesteps)
+        if self._engine is None or self._engine_sig != sig:
+            dev = next(self.parameters()).device
+            self._engine = pmp_b200.UnetEngine(self._ctor, self.state_dict(), dev, n_timesteps=n_timesteps)
+            self._engine_sig = sig
+        return self._engine
+
+    def forward(self, x, cond, time, walls_loc, use_dropout=True, force_dropout=False, half_fd=False):
+        """x [B,H,D], time [B] long, walls_loc [B,Wd] -> eps = dE/dx [B,H,D] (eval / energy mode).
+        force_dropout+half_fd: the second half of the batch is the unconditional CFG half
+        (temporal_cond.py:272-279)."""
+        if self.training or use_dropout:
+            raise NotImplementedError('the training path (concept dropout + double backward) is not part of the '
+                                      'B200 hot path; call .eval() and pass use_dropout=False')
+        R = x.shape[0]
+        if force_dropout:
+            if half_fd:
+                assert R % 2 == 0
+                n_cond = R // 2
+            else:
+                n_cond = 0
+        else:
+            n_cond = R
+        eng = self.engine()
+        wemb = eng.wall_embed(walls_loc[:n_cond]) if n_cond > 0 else None
+        return eng.eps(x, time, wemb, n_cond=n_cond)

@@ -42,7 +42,10 @@ def main(fams):
         print("  wall_embed rel err %.3e" % rel(wemb.cpu().numpy(), wemb_ref.numpy()))
         eps, en, u = eng.eps(x, t, wemb, n_cond=B, want_energy=True, want_u=True)
         torch.cuda.synchronize()
-        for pfx, (yh, r) in tape.items():
+        for pfx, val in tape.items():
+            if not isinstance(val, tuple):
+                continue
+            yh, r = val
             got = eng.debug_fetch("yhat:" + pfx)
             if got is None:
                 continue
