@@ -1,0 +1,4 @@
+from .policies import Policy, Trajectories
+from .policies_compose import PolicyCompose
+from .rm2d_colchk import RM2DCollisionChecker
+from .kuka_colchk import KukaCollisionChecker

@@ -1,0 +1,177 @@
+"""Freezes golden vectors by running the *reference implementation itself* (imported from
+/root/reference through oracle/refshim.py) on the deterministic synthetic inputs of
+oracle/synth.py.  Only runnable in the build container; the .npz files it writes are
+committed and travel to the GPU box.
+
+    python tests/golden/gen_golden.py
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import refshim, synth, unet_ref  # noqa: E402
+
+torch.set_num_threads(8)
+WEIGHT_SEED = 1
+
+
+def build_ref(fam, seed=WEIGHT_SEED):
+    U, G = refshim.load_models()
+    a = synth.arch(fam)
+    with refshim.quiet():
+        m = U(**a["unet"]).eval()
+        sd = unet_ref.synth_weights(a["unet"], seed)
+        m.load_state_dict(sd)
+        d = G(m, **a["diffusion"]).eval()
+    return a, m, d, sd
+
+
+def gen_unet():
+    for fam in synth.FAMILIES:
+        a, m, d, sd = build_ref(fam)
+        B, H, D = 2, a["horizon"], a["obs_dim"]
+        pr = synth.make_problems(fam, B, 3)
+        g = torch.Generator().manual_seed(11)
+        x = torch.randn(2 * B, H, D, generator=g)
+        t = torch.tensor([37, 5, 37, 5])
+        walls = torch.tensor(pr["walls"]).repeat(2, 1)
+        with refshim.quiet():
+            eps = m(x.clone(), None, t, walls, use_dropout=False, force_dropout=True, half_fd=True).detach()
+        np.savez_compressed(os.path.join(HERE, "unet_eps_%s.npz" % fam), x=x.numpy(), t=t.numpy(), walls=walls.numpy(),
+                            eps=eps.numpy(), n_cond=B, weight_seed=WEIGHT_SEED, digest=synth.state_dict_digest(sd))
+        print("unet", fam, float(eps.abs().max()))
+
+
+def gen_sample():
+    for fam, B in (("m2d", 2), ("kuka", 1), ("dualkuka", 1)):
+        a, m, d, sd = build_ref(fam)
+        H, D = a["horizon"], a["obs_dim"]
+        pr = synth.make_problems(fam, B, 3)
+        lo, hi = pr["lo"], pr["hi"]
+        start = torch.tensor(synth.normalize(pr["start"], lo, hi))
+        goal = torch.tensor(synth.normalize(pr["goal"], lo, hi))
+        walls = torch.tensor(pr["walls"])
+        cond = {0: start, H - 1: goal}
+        out = {}
+        for name, ddim in (("ddpm", 0), ("ddim", 8 if fam != "dualkuka" else 10)):
+            if fam != "m2d" and not ddim:
+                continue   # keep generation time short: full DDPM-100 only for Maze2D
+            n = ddim if ddim else 100
+            torch.manual_seed(5)
+            with refshim.quiet():
+                d.horizon = H
+                d.ddim_num_inference_steps = n
+                x, tr = d.conditional_sample(cond, walls, use_ddim=bool(ddim), return_diffusion=True)
+            torch.manual_seed(5)
+            noise = torch.stack([torch.randn(B, H, D) for _ in range(n + 1 if not ddim else 1)])
+            out[name + "_x"] = x.detach().numpy()
+            out[name + "_trace"] = tr.detach().numpy()
+            out[name + "_noise"] = noise.numpy()
+            out[name + "_steps"] = n
+        np.savez_compressed(os.path.join(HERE, "sample_%s.npz" % fam), start=start.numpy(), goal=goal.numpy(),
+                            walls=walls.numpy(), weight_seed=WEIGHT_SEED, **out)
+        print("sample", fam, list(out))
+
+
+def gen_compose():
+    """K=2 composition through the reference's own pred_unet / pred_x_tm1_* plus the six lines of
+    policies_compose.py:286-297 (PolicyCompose itself hard-codes .to('cuda'))."""
+    a1, m1, d1, sd1 = build_ref("m2d", 1)
+    a2, m2, d2, sd2 = build_ref("m2d_nw3", 2)
+    B, H, D = 2, 40, 2
+    pr = synth.make_problems("m2d", B, 21)
+    pr2 = synth.make_problems("m2d_nw3", B, 22)
+    lo, hi = pr["lo"], pr["hi"]
+    start = torch.tensor(synth.normalize(pr["start"], lo, hi))
+    goal = torch.tensor(synth.normalize(pr["goal"], lo, hi))
+    w1 = torch.tensor(pr["walls"]); w2 = torch.tensor(pr2["walls"])
+    cg = torch.tensor([2.0, 1.5]).reshape(2, 1, 1, 1)
+    out = {}
+    for name, ddim, eta in (("ddim24", 24, 1.0), ("ddpm", 0, 0.0)):
+        steps = [int(v) for v in d1.ddim_set_timesteps(24)] if ddim else list(range(19, -1, -1))
+        torch.manual_seed(9)
+        x = 1.0 * torch.randn(B, H, D)
+        for dd in (d1, d2):
+            dd.ddim_num_inference_steps = 24
+        xs = []
+        with refshim.quiet():
+            for t in steps:
+                tt = torch.full((B,), t, dtype=torch.long)
+                ecs, eus = [], []
+                for dd, wl in ((d1, w1), (d2, w2)):
+                    (_, ec), (_, eu) = dd.pred_unet(x.detach(), {0: start, H - 1: goal}, tt, wl)
+                    ecs.append(ec); eus.append(eu)
+                ecs = torch.stack(ecs, 0); eus = torch.stack(eus, 0)
+                comp = eus[0] + (cg * (ecs - eus)).sum(dim=0, keepdims=False)
+                if ddim:
+                    x = d1.pred_x_tm1_ddim(x, tt, comp, eta=eta, clip_denoised=True)
+                else:
+                    x = d1.pred_x_tm1_luo(x, tt, comp, clip_denoised=True)
+                xs.append(x.clone())
+        x[:, 0] = start; x[:, -1] = goal
+        torch.manual_seed(9)
+        noise = torch.stack([torch.randn(B, H, D) for _ in range(len(steps) + 1)])
+        out[name + "_x"] = x.detach().numpy()
+        out[name + "_noise"] = noise.numpy()
+        out[name + "_steps"] = np.array(steps)
+    np.savez_compressed(os.path.join(HERE, "compose_m2d.npz"), start=start.numpy(), goal=goal.numpy(), walls1=w1.numpy(),
+                        walls2=w2.numpy(), w=np.array([2.0, 1.5], np.float32), seeds=np.array([1, 2]), **out)
+    print("compose", list(out))
+
+
+def gen_colchk():
+    P, RW, RWG, Env = refshim.load_maze2d_geometry()
+    rng = np.random.default_rng(5)
+    out = {}
+    for fam, hext in (("m2d", 0.5), ("m2d_nw3", 0.7), ("m2d_concave", 0.25)):
+        E, n_per, H = 12, 25, 48
+        pr = synth.make_problems(fam, E, 9)
+        al = np.linspace(0, 1, H)[None, None, :, None].astype(np.float32)
+        s = pr["start"][:, None, None, :]; g = pr["goal"][:, None, None, :]
+        sig = rng.choice([0.02, 0.1, 0.3], size=(E, n_per, 1, 1))
+        tr = s * (1 - al) + g * al + (rng.normal(0, 1, size=(E, n_per, H, 2)) * sig * np.sin(np.pi * al)).astype(np.float32)
+        tr = np.clip(tr, -0.02, 5.02).astype(np.float32).reshape(E * n_per, H, 2)
+        env_id = np.repeat(np.arange(E, dtype=np.int32), n_per)
+        valid = np.zeros(len(tr), np.uint8); nchk = np.zeros(len(tr), np.int32)
+        ncol = np.zeros(len(tr), np.int32)
+        for i in range(len(tr)):
+            e = env_id[i]
+            walls = [RW(np.array(c), np.array([hext, hext])) for c in pr["boxes"][e]]
+            rob = P(np.array([5., 5.]), RWG(walls), 0.01, collision_eps=0.08)
+            env = object.__new__(Env); env.robot = rob
+            cnt, ok = 0, True
+            with contextlib.redirect_stdout(io.StringIO()):
+                for j in range(H - 1):          # rm2d_colchk.py:76-93
+                    rob.collision_check_count = 0
+                    good = env.edge_fp(tr[i, j], tr[i, j + 1])
+                    cnt += rob.collision_check_count
+                    if not good:
+                        ok = False
+                        break
+                trc = np.clip(tr[i], 0, 5)
+                c2 = 0
+                for j in range(H):              # kuka_plan_utils.py:87-103
+                    rob.set_config(trc[j])
+                    if not rob.no_collision():
+                        c2 += 1
+            valid[i] = ok; nchk[i] = cnt; ncol[i] = c2
+        out[fam + "_traj"] = tr; out[fam + "_env"] = env_id; out[fam + "_boxes"] = pr["boxes"]
+        out[fam + "_hext"] = hext; out[fam + "_valid"] = valid; out[fam + "_nchk"] = nchk; out[fam + "_ncol"] = ncol
+        print("colchk", fam, "valid frac", valid.mean(), "mean checks", nchk.mean())
+    out["numpy_version"] = np.__version__
+    out["legacy_div"] = 0   # numpy >= 2 semantics produced these counts
+    np.savez_compressed(os.path.join(HERE, "colchk_maze2d.npz"), **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk"]
+    for w in which:
+        globals()["gen_" + w]()

@@ -1,0 +1,135 @@
+"""CPU: the C-ABI library loads and exports every symbol include/pmp_b200.h declares, fails
+loudly without a GPU (no CPU fallback), and the drop-in host classes mirror the reference
+interface (state-dict keys, buffers, coefficient tables, pickled Config)."""
+import ctypes
+import io
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import pmp_b200
+from pmp_b200 import _lib
+from oracle import refshim, synth, unet_ref, sampler_ref
+from util import ddpm_coefs, ddim_coefs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "pmp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pmp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = pmp_b200.lib()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), "libpmp_b200.so does not export %s" % s
+    assert sorted(_lib.EXPORTS) == syms   # the ctypes table binds exactly the declared ABI
+    assert lib.pmp_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert pmp_b200.device_count() == 0
+    a = synth.arch("m2d")
+    sd = unet_ref.synth_weights(a["unet"], 1)
+    with pytest.raises(pmp_b200.PmpError):
+        pmp_b200.UnetEngine(a["unet"], sd, "cpu")
+    arch = _lib.make_arch(a["unet"])
+    h = ctypes.c_void_p()
+    rc = pmp_b200.lib().pmp_model_create(ctypes.byref(arch), 0, ctypes.byref(h))
+    assert rc == -2 and b"cuda" in pmp_b200.lib().pmp_last_error().lower()
+    from diffuser.models import TemporalUnet_WCond
+    m = TemporalUnet_WCond(**a["unet"]).eval()
+    with pytest.raises(pmp_b200.PmpError):
+        m(torch.zeros(2, 48, 2), None, torch.zeros(2, dtype=torch.long), torch.zeros(2, 12), use_dropout=False)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "potential-motion-plan-release_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dp, f)
+
+
+@pytest.mark.parametrize("fam", synth.FAMILIES)
+def test_dropin_unet_state_dict(fam):
+    from diffuser.models import TemporalUnet_WCond
+    a = synth.arch(fam)
+    torch.manual_seed(0)
+    m = TemporalUnet_WCond(**a["unet"])
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == list(unet_ref.param_shapes(a["unet"]).items())
+    m.load_state_dict(unet_ref.synth_weights(a["unet"], 1), strict=True)
+    if refshim.available():
+        # same seed -> bit-identical random init as the reference constructor
+        import subprocess, sys, json
+        code = ("import sys,torch;sys.path.insert(0,%r);from oracle import refshim,synth;U,G=refshim.load_models();"
+                "a=synth.arch(%r);\nwith refshim.quiet():\n torch.manual_seed(0);m=U(**a['unet'])\n"
+                "print(synth.state_dict_digest(m.state_dict()))" % (ROOT, fam))
+        ref_digest = subprocess.check_output([sys.executable, "-c", code]).decode().split()[-1]
+        torch.manual_seed(0)
+        assert synth.state_dict_digest(TemporalUnet_WCond(**a["unet"]).state_dict()) == ref_digest
+
+
+def test_dropin_diffusion_buffers_and_coefs():
+    from diffuser.models import TemporalUnet_WCond, GaussianDiffusionPB
+    a = synth.arch("m2d")
+    d = GaussianDiffusionPB(TemporalUnet_WCond(**a["unet"]), **a["diffusion"])
+    tb = sampler_ref.schedule(100)
+    for k, v in tb.items():
+        assert torch.equal(getattr(d, k), v), k
+    keys = [k for k in d.state_dict() if not k.startswith("model.")]
+    assert keys == list(tb.keys()) + ["loss_fn.weights"]
+    assert d.loss_fn.weights.shape == (48, 2) and float(d.loss_fn.weights[0].sum()) == 0 and float(d.loss_fn.weights[-1].sum()) == 0
+    ts = list(range(99, -1, -1))
+    assert np.array_equal(d.step_coefs_ddpm(ts), ddpm_coefs(tb, ts))
+    for n, eta in ((8, 0.0), (24, 1.0), (10, 0.0)):
+        t2 = d.ddim_set_timesteps(n)
+        assert np.array_equal(t2, sampler_ref.ddim_timesteps(n, 100))
+        assert np.array_equal(d.step_coefs_ddim(t2, eta, n), ddim_coefs(tb, t2, n, 100, eta))
+    with pytest.raises(NotImplementedError):
+        d.loss(None, None, None)
+
+
+def test_config_pickle_roundtrip():
+    from diffuser.utils import Config
+    a = synth.arch("kuka")
+    cfg = Config("models.TemporalUnet_WCond", **a["unet"])
+    blob = pickle.dumps(cfg)
+    cfg2 = pickle.loads(blob)
+    m = cfg2()
+    assert type(m).__module__ == "diffuser.models.temporal_cond" and type(m).__name__ == "TemporalUnet_WCond"
+    dcfg = pickle.loads(pickle.dumps(Config("models.GaussianDiffusionPB", **a["diffusion"])))
+    d = dcfg(m)
+    from diffuser.models import GaussianDiffusionPB
+    assert type(d) == GaussianDiffusionPB and d.n_timesteps == 100 and d.var_temp == 1.0
+
+
+def test_unsupported_configs_fail_loudly():
+    from diffuser.models import TemporalUnet_WCond
+    a = synth.arch("m2d")
+    bad = dict(a["unet"]); bad["network_config"] = dict(bad["network_config"], energy_mode=False)
+    with pytest.raises(Exception):
+        TemporalUnet_WCond(**bad)
+    bad = dict(a["unet"]); bad["network_config"] = dict(bad["network_config"], wallLoc_encoder="mlp")
+    with pytest.raises(Exception):
+        TemporalUnet_WCond(**bad)
+
+
+def test_normalizer_matches_oracle():
+    from diffuser.datasets import LimitsNormalizer, KUKA7D_MIN, KUKA7D_MAX
+    n = LimitsNormalizer(KUKA7D_MIN, KUKA7D_MAX)
+    x = (np.random.default_rng(0).normal(0, 0.8, (5, 52, 7))).astype(np.float32)
+    assert np.array_equal(n.unnormalize(x), synth.unnormalize(x, KUKA7D_MIN, KUKA7D_MAX))
+    q = np.random.default_rng(1).uniform(KUKA7D_MIN, KUKA7D_MAX, (4, 7)).astype(np.float32)
+    assert np.array_equal(n.normalize(q), synth.normalize(q, KUKA7D_MIN, KUKA7D_MAX))

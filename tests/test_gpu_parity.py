@@ -1,0 +1,339 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI / the drop-in classes) against the
+golden vectors frozen from the reference and against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+import pmp_b200
+from oracle import synth, unet_ref, sampler_ref, colchk_ref
+from util import (golden, assert_eps_close, ddpm_coefs, ddim_coefs, pad_noise, TRAJ_ATOL)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+_models = {}
+
+
+def dropin(fam, seed=1):
+    """drop-in TemporalUnet_WCond + GaussianDiffusionPB with the synthetic weights, on the GPU"""
+    key = (fam, seed)
+    if key not in _models:
+        from diffuser.models import TemporalUnet_WCond, GaussianDiffusionPB
+        a = synth.arch(fam)
+        m = TemporalUnet_WCond(**a["unet"])
+        m.load_state_dict(unet_ref.synth_weights(a["unet"], seed))
+        _models[key] = GaussianDiffusionPB(m, **a["diffusion"]).to(DEV).eval()
+    return _models[key]
+
+
+# ------------------------------------------------------------------ potential gradient
+@pytest.mark.parametrize("fam", synth.FAMILIES)
+def test_eps_matches_reference_golden(fam):
+    g = golden("unet_eps_%s.npz" % fam)
+    d = dropin(fam)
+    x = torch.tensor(g["x"], device=DEV); t = torch.tensor(g["t"], device=DEV); w = torch.tensor(g["walls"], device=DEV)
+    eps = d.model(x, None, t, w, use_dropout=False, force_dropout=True, half_fd=True)
+    assert_eps_close(eps.cpu().numpy(), g["eps"], "eps[%s]" % fam)
+    # fully conditional / fully unconditional variants of the same call
+    n = x.shape[0] // 2
+    ec = d.model(x[:n], None, t[:n], w[:n], use_dropout=False)
+    eu = d.model(x[n:], None, t[n:], w[n:], use_dropout=False, force_dropout=True)
+    assert_eps_close(ec.cpu().numpy(), g["eps"][:n], "cond")
+    assert_eps_close(eu.cpu().numpy(), g["eps"][n:], "uncond")
+
+
+@pytest.mark.parametrize("fam,H", [("m2d", 36), ("m2d", 64), ("kuka", 44), ("dualkuka", 40)])
+def test_eps_other_horizons_vs_oracle(fam, H):
+    a = synth.arch(fam)
+    cfg = unet_ref.UnetCfg(a["unet"]); sd = unet_ref.synth_weights(a["unet"], 1)
+    d = dropin(fam)
+    gen = torch.Generator().manual_seed(H)
+    B = 3
+    x = torch.randn(2 * B, H, a["obs_dim"], generator=gen)
+    t = torch.tensor([0, 99, 50] * 2)
+    walls = torch.tensor(synth.make_problems(fam, B, H)["walls"]).repeat(2, 1)
+    ref, u_ref, e_ref = unet_ref.eps_autograd(sd, cfg, x, t, walls, n_cond=B, return_u=True)
+    eng = d.model.engine(100)
+    wemb = eng.wall_embed(walls[:B].to(DEV))
+    eps, en, u = eng.eps(x.to(DEV), t.to(DEV), wemb, n_cond=B, want_energy=True, want_u=True)
+    assert_eps_close(eps.cpu().numpy(), ref.numpy(), "eps")
+    assert_eps_close(u.cpu().numpy(), u_ref.numpy(), "u")
+    assert np.allclose(en.cpu().numpy(), e_ref.numpy(), rtol=1e-4)
+
+
+def test_eps_chunking_and_determinism():
+    d = dropin("m2d")
+    eng = d.model.engine(100)
+    gen = torch.Generator().manual_seed(4)
+    B = 37
+    x = torch.randn(2 * B, 48, 2, generator=gen).to(DEV)
+    t = torch.randint(0, 100, (2 * B,), generator=gen).to(DEV)
+    wemb = eng.wall_embed(torch.tensor(synth.make_problems("m2d", B, 8)["walls"], device=DEV))
+    e1 = eng.eps(x, t, wemb, n_cond=B)
+    e2 = eng.eps(x, t, wemb, n_cond=B)
+    assert torch.equal(e1, e2), "eps evaluation is not run-to-run deterministic"
+    eng.set_row_chunk(20)   # ragged chunks that split the cond / uncond boundary
+    e3 = eng.eps(x, t, wemb, n_cond=B)
+    eng.set_row_chunk(2048)
+    assert torch.equal(e1, e3), "row chunking changed the result"
+
+
+def test_wall_embed_vs_oracle_any_wall_count():
+    for fam, nws in (("m2d", (1, 6, 9)), ("kuka", (4, 5)), ("m2d_concave", (7,))):
+        a = synth.arch(fam)
+        cfg = unet_ref.UnetCfg(a["unet"]); sd = unet_ref.synth_weights(a["unet"], 1)
+        eng = dropin(fam).model.engine(100)
+        for nw in nws:
+            walls = torch.rand(5, nw * a["token_dim"], generator=torch.Generator().manual_seed(nw)) * 5
+            got = eng.wall_embed(walls.to(DEV)).cpu()
+            ref = unet_ref.wall_embed(sd, cfg, walls)
+            assert (got - ref).abs().max() < 2e-5 * ref.abs().max() + 1e-6
+
+
+# ------------------------------------------------------------------ sampler
+def test_step_kernel_bit_exact():
+    tb = sampler_ref.schedule(100)
+    gen = torch.Generator().manual_seed(0)
+    B, H, D = 33, 52, 7
+    for K in (1, 2, 4):
+        x = torch.randn(B, H, D, generator=gen)
+        ec = [0.5 * torch.randn(B, H, D, generator=gen) for _ in range(K)]
+        eu = [0.5 * torch.randn(B, H, D, generator=gen) for _ in range(K)]
+        z = torch.randn(B, H, D, generator=gen)
+        st = torch.rand(B, D, generator=gen) * 2 - 1; go = torch.rand(B, D, generator=gen) * 2 - 1
+        w = [2.0, 1.5, 0.7, 3.0][:K]
+        eps = sampler_ref.compose(ec, eu, w, K - 1)
+        dev = lambda l: [e.to(DEV) for e in l]
+        for t in (99, 1, 0):
+            ref = sampler_ref.apply_cond(sampler_ref.ddpm_update(tb, x, t, eps, z), st, go)
+            out = pmp_b200.step(0, x.to(DEV), dev(ec), dev(eu), w, ddpm_coefs(tb, [t])[0], noise=z.to(DEV),
+                                start=st.to(DEV), goal=go.to(DEV), base=K - 1)
+            assert torch.equal(out.cpu(), ref), ("ddpm", K, t)
+        for eta in (0.0, 1.0):
+            for t in (84, 0):
+                ref = sampler_ref.apply_cond(sampler_ref.ddim_update(tb, x, t, eps, 8, 100, eta, z), st, go)
+                out = pmp_b200.step(1, x.to(DEV), dev(ec), dev(eu), w, ddim_coefs(tb, [t], 8, 100, eta)[0],
+                                    noise=z.to(DEV), start=st.to(DEV), goal=go.to(DEV), base=K - 1)
+                assert torch.equal(out.cpu(), ref), ("ddim", K, eta, t)
+
+
+@pytest.mark.parametrize("fam,mode", [("m2d", "ddpm"), ("m2d", "ddim"), ("kuka", "ddim"), ("dualkuka", "ddim")])
+def test_sampler_matches_reference_golden(fam, mode):
+    """final trajectories of the reference's p_sample_loop / ddim_p_sample_loop, same injected noise"""
+    g = golden("sample_%s.npz" % fam)
+    d = dropin(fam)
+    a = synth.arch(fam)
+    H, n = a["horizon"], int(g[mode + "_steps"])
+    tb = sampler_ref.schedule(100)
+    if mode == "ddpm":
+        ts = list(range(99, -1, -1)); coefs = d.step_coefs_ddpm(ts); kind = 0
+    else:
+        d.ddim_num_inference_steps = n
+        ts = d.ddim_set_timesteps(n); coefs = d.step_coefs_ddim(ts, 0.0, n); kind = 1
+    eng = d.model.engine(100)
+    wemb = eng.wall_embed(torch.tensor(g["walls"], device=DEV))
+    x, tr = pmp_b200.sample([eng], [wemb], [2.0], torch.tensor(g["start"]), torch.tensor(g["goal"]), H, kind, ts, coefs,
+                            noise=pad_noise(g[mode + "_noise"], n), trace=True)
+    ref = g[mode + "_x"]
+    err = np.abs(x.cpu().numpy() - ref).max()
+    assert err <= TRAJ_ATOL, "final trajectory differs from the reference by %.3e" % err
+    assert np.abs(tr.cpu().numpy() - g[mode + "_trace"]).max() <= TRAJ_ATOL
+    assert np.array_equal(x[:, 0].cpu().numpy(), g["start"]) and np.array_equal(x[:, -1].cpu().numpy(), g["goal"])
+
+
+@pytest.mark.parametrize("mode", ["ddim24", "ddpm"])
+def test_composed_sampler_matches_reference_golden(mode):
+    g = golden("compose_m2d.npz")
+    d1, d2 = dropin("m2d", int(g["seeds"][0])), dropin("m2d_nw3", int(g["seeds"][1]))
+    e1, e2 = d1.model.engine(100), d2.model.engine(100)
+    steps = [int(v) for v in g[mode + "_steps"]]
+    if mode == "ddim24":
+        coefs = d1.step_coefs_ddim(steps, 1.0, 24); kind = 1
+    else:
+        coefs = d1.step_coefs_ddpm(steps); kind = 0
+    w1 = e1.wall_embed(torch.tensor(g["walls1"], device=DEV)); w2 = e2.wall_embed(torch.tensor(g["walls2"], device=DEV))
+    x = pmp_b200.sample([e1, e2], [w1, w2], [float(v) for v in g["w"]], torch.tensor(g["start"]), torch.tensor(g["goal"]),
+                        40, kind, steps, coefs, noise=torch.tensor(g[mode + "_noise"]))
+    err = np.abs(x.cpu().numpy() - g[mode + "_x"]).max()
+    assert err <= TRAJ_ATOL, err
+    # same model composed with itself (shared pmp_model, two wall subsets) must not alias its tables
+    xs = pmp_b200.sample([e1, e1], [w1, w1.flip(0)], [1.0, 1.0], torch.tensor(g["start"]), torch.tensor(g["goal"]),
+                         40, kind, steps, coefs, noise=torch.tensor(g[mode + "_noise"]))
+    assert torch.isfinite(xs).all()
+
+
+def test_dropin_forward_api_and_philox():
+    d = dropin("m2d")
+    B, H = 64, 48
+    pr = synth.make_problems("m2d", B, 5)
+    lo, hi = pr["lo"], pr["hi"]
+    cond = {0: torch.tensor(synth.normalize(pr["start"], lo, hi), device=DEV),
+            H - 1: torch.tensor(synth.normalize(pr["goal"], lo, hi), device=DEV)}
+    walls = torch.tensor(pr["walls"], device=DEV)
+    d.horizon = H; d.ddim_num_inference_steps = 8
+    torch.manual_seed(0)
+    x1 = d(cond, walls, use_ddim=True)
+    torch.manual_seed(0)
+    x2, tr = d(cond, walls, use_ddim=True, return_diffusion=True)
+    assert x1.shape == (B, H, 2) and tr.shape == (B, 9, H, 2) and torch.equal(x1, x2)
+    assert float(x1.abs().max()) <= 1.0 + 1e-6
+    # in-kernel Philox: deterministic in the seed, and invariant to how the batch is sharded
+    d.rng_mode = "philox"; d.philox_seed = 123
+    try:
+        ts = list(range(19, -1, -1)); coefs = d.step_coefs_ddpm(ts)
+        eng = d.model.engine(100); wemb = eng.wall_embed(walls)
+        full = pmp_b200.sample([eng], [wemb], [2.0], cond[0], cond[H - 1], H, 0, ts, coefs, seed=123)
+        half = pmp_b200.sample([eng], [wemb[32:]], [2.0], cond[0][32:], cond[H - 1][32:], H, 0, ts, coefs, seed=123,
+                               row_offset=32)
+        assert torch.equal(full[32:], half)
+        other = pmp_b200.sample([eng], [wemb], [2.0], cond[0], cond[H - 1], H, 0, ts, coefs, seed=124)
+        assert not torch.equal(full, other)
+    finally:
+        d.rng_mode = "torch"
+
+
+def test_policy_and_compose_interfaces():
+    from diffuser.guides import Policy, PolicyCompose
+    from diffuser.datasets import DatasetNormalizer, RAND_MAZE_MIN, RAND_MAZESIZE_55
+    norm = DatasetNormalizer({"observations": (RAND_MAZE_MIN, RAND_MAZESIZE_55)})
+    d = dropin("m2d")
+    d.ddim_num_inference_steps = 8
+    B, H = 20, 48
+    pr = synth.make_problems("m2d", B, 6)
+    pol = Policy(d, norm, use_ddim=True)
+    cond = {0: pr["start"], H - 1: pr["goal"]}
+    _, traj = pol(cond, batch_size=-1, wall_locations=torch.tensor(pr["walls"]))
+    obs = traj.observations
+    assert obs.shape == (B, H, 2) and obs.dtype == np.float32
+    assert np.allclose(obs[:, 0], pr["start"], atol=1e-5) and np.allclose(obs[:, -1], pr["goal"], atol=1e-5)
+    assert obs.min() >= 0 and obs.max() <= 5
+    d2 = dropin("m2d_nw3", 2)
+    d2.horizon = d.horizon
+    po = dict(num_walls_c=[6, 3], wall_dim=2, comp_type="direct", ddim_steps=8, wall_is_dyn=None, uncond_base_idx=0,
+              ddim_eta=1.0)
+    comp = PolicyCompose([d, d2], [norm, norm], False, True, po)
+    walls9 = torch.cat([torch.tensor(pr["walls"]), torch.tensor(synth.make_problems("m2d_nw3", B, 7)["walls"])], 1)
+    condt = {0: torch.tensor(pr["start"]), 40 - 1: torch.tensor(pr["goal"])}
+    _, traj = comp(condt, walls9)
+    assert traj.observations.shape == (B, 40, 2) and np.isfinite(traj.observations).all()
+
+
+# ------------------------------------------------------------------ collision
+@pytest.mark.parametrize("fam", ["m2d", "m2d_nw3", "m2d_concave"])
+def test_maze2d_collision_matches_reference_golden(fam):
+    g = golden("colchk_maze2d.npz")
+    tr = torch.tensor(g[fam + "_traj"], device=DEV)
+    env = g[fam + "_env"]; boxes = g[fam + "_boxes"]; hext = float(g[fam + "_hext"])
+    v, c = pmp_b200.colchk_maze2d_swept(tr, env, boxes, hext, legacy_div=bool(int(g["legacy_div"])))
+    assert np.array_equal(v.cpu().numpy(), g[fam + "_valid"]), "collision bits differ from the reference"
+    assert np.array_equal(c.cpu().numpy(), g[fam + "_nchk"]), "check counts differ from the reference"
+    n, pt = pmp_b200.colchk_maze2d_points(tr.clamp(0, 5), env, boxes, hext)
+    assert np.array_equal(n.cpu().numpy(), g[fam + "_ncol"])
+    assert np.array_equal(pt.cpu().numpy().sum(1), g[fam + "_ncol"])
+
+
+def _noisy_lines(pr, n_per, H, rng, sig):
+    E = len(pr["start"])
+    al = np.linspace(0, 1, H)[None, None, :, None].astype(np.float32)
+    s = pr["start"][:, None, None, :]; g = pr["goal"][:, None, None, :]
+    return (s * (1 - al) + g * al + (rng.normal(0, sig, size=(E, n_per, H, s.shape[-1])) * np.sin(np.pi * al))).astype(np.float32)
+
+
+@pytest.mark.parametrize("legacy", [True, False])
+def test_maze2d_collision_full_size_vs_oracle(legacy):
+    """BASELINE config 2 size: 10k problems (1000 envs x 10 candidates), Static2 + Concave"""
+    rng = np.random.default_rng(3)
+    for fam, hext in (("m2d_nw3", 0.7), ("m2d_concave", 0.25)):
+        E, n_per, H = 1000, 10, 48
+        pr = synth.make_problems(fam, E, 31)
+        tr = np.clip(_noisy_lines(pr, n_per, H, rng, 0.15), -0.01, 5.01).reshape(E * n_per, H, 2)
+        env = np.repeat(np.arange(E, dtype=np.int32), n_per)
+        v_ref, c_ref = colchk_ref.maze2d_swept(tr, env, pr["boxes"], hext, legacy_div=legacy)
+        v, c = pmp_b200.colchk_maze2d_swept(torch.tensor(tr, device=DEV), env, pr["boxes"], hext, legacy_div=legacy)
+        assert np.array_equal(v.cpu().numpy(), v_ref) and np.array_equal(c.cpu().numpy(), c_ref)
+        ch_ref, su_ref, tot_ref = colchk_ref.pick_first_valid(v_ref, c_ref, E, n_per)
+        ch, su, tot = pmp_b200.pick_first_valid(v, c, E, n_per)
+        assert np.array_equal(ch.cpu().numpy(), ch_ref) and np.array_equal(su.cpu().numpy().astype(bool), su_ref)
+        assert np.array_equal(tot.cpu().numpy(), tot_ref)
+        assert 0.02 < su_ref.mean() < 0.98
+
+
+def test_maze2d_collision_edge_cases():
+    cen = np.array([[[2.5, 2.5]]]); hext = 0.5
+    H = 8
+    line = np.stack([np.linspace(0.2, 4.8, H), np.full(H, 2.5)], -1).astype(np.float32)
+    free = np.stack([np.linspace(0.2, 4.8, H), np.full(H, 0.5)], -1).astype(np.float32)
+    oob = free.copy(); oob[3, 1] = -0.1
+    touch = free.copy(); touch[:, 1] = np.float32(2.5 - 0.5 - 0.01)   # exactly on the inflated boundary: strict test
+    tr = np.stack([line, free, oob, touch])
+    env = np.zeros(4, np.int32)
+    v_ref, c_ref = colchk_ref.maze2d_swept(tr, env, cen, hext)
+    v, c = pmp_b200.colchk_maze2d_swept(torch.tensor(tr, device=DEV), env, cen, hext)
+    assert np.array_equal(v.cpu().numpy(), v_ref) and np.array_equal(c.cpu().numpy(), c_ref)
+    assert v_ref.tolist()[:3] == [0, 1, 0]
+    n, pt = pmp_b200.colchk_maze2d_points(torch.tensor(tr, device=DEV), env, cen, hext)
+    assert n.cpu().tolist()[2] == -1
+    # empty batch, no walls, two-waypoint trajectory
+    v, c = pmp_b200.colchk_maze2d_swept(torch.zeros(0, 8, 2, device=DEV), np.zeros(0, np.int32), cen, hext)
+    assert v.numel() == 0
+    v, c = pmp_b200.colchk_maze2d_swept(torch.tensor(free[None, :2], device=DEV), np.zeros(1, np.int32),
+                                        np.zeros((1, 0, 2)), np.zeros((1, 0, 2)))
+    assert v.cpu().tolist() == [1]
+    from diffuser.guides import RM2DCollisionChecker
+
+    class Env:
+        wall_centers = cen[0]; wall_hext = hext
+    chk = RM2DCollisionChecker(None)
+    chk.use_collision_eps = True; chk.collision_eps = 0.08
+    assert chk.check_single_traj(free, Env) == (True, int(c_ref[1]))
+    assert chk.check_single_traj(line, Env) == (False, int(c_ref[0]))
+    chk.use_collision_eps = False
+    assert chk.check_single_traj(free, Env) == (True, H)
+    ok, cnt = chk.check_single_traj(line, Env)
+    assert not ok and cnt == int(np.argmax(pt.cpu().numpy()[0])) + 1
+
+
+@pytest.mark.parametrize("fam,arms,hext", [("kuka", 1, 0.20), ("dualkuka", 2, 0.22)])
+def test_kuka_collision_vs_oracle(fam, arms, hext):
+    rng = np.random.default_rng(7)
+    E, n_per = 300, 8
+    H = synth.arch(fam)["horizon"]
+    pr = synth.make_problems(fam, E, 41)
+    # mixture: near-upright (mostly free) and random joint-space lines (mostly colliding)
+    pr_small = dict(start=pr["start"] * 0.15, goal=pr["goal"] * 0.15)
+    tr = np.concatenate([_noisy_lines(pr_small, n_per // 2, H, rng, 0.05), _noisy_lines(pr, n_per // 2, H, rng, 0.3)], 1)
+    tr = tr.reshape(E * n_per, H, -1)
+    env = np.repeat(np.arange(E, dtype=np.int32), n_per)
+    sph = colchk_ref.kuka_sphere_table()
+    ref = colchk_ref.kuka_points(tr, env, pr["boxes"], hext, n_arms=arms, sph=sph)
+    got = pmp_b200.colchk_kuka(torch.tensor(tr, device=DEV), env, pr["boxes"], hext, arms, colchk_ref.kuka_bases(arms), sph)
+    for k in ("valid", "nchk", "ncol", "ptcol"):
+        assert np.array_equal(got[k].cpu().numpy(), ref[k]), k
+    assert 0.05 < ref["valid"].mean() < 0.95
+    from diffuser.guides import KukaCollisionChecker
+
+    class Env:
+        voxel_centers = pr["boxes"][0]; voxel_hext = hext; n_arms = arms
+    ok, cnt = KukaCollisionChecker().check_single_traj(tr[0], Env)
+    assert ok == bool(ref["valid"][0]) and cnt == int(ref["nchk"][0])
+
+
+def test_unnormalize_bit_exact():
+    for fam in ("m2d", "kuka", "dualkuka"):
+        lo, hi = synth.limits(fam)
+        x = (torch.randn(50, 48, len(lo), generator=torch.Generator().manual_seed(1)) * 0.9)
+        got = pmp_b200.unnormalize(x.to(DEV), lo, hi).cpu().numpy()
+        assert np.array_equal(got, synth.unnormalize(x.numpy(), lo, hi))
+
+
+def test_errors_are_reported():
+    d = dropin("m2d")
+    eng = d.model.engine(100)
+    with pytest.raises(pmp_b200.PmpError):
+        eng.eps(torch.zeros(2, 50, 2, device=DEV), torch.zeros(2, dtype=torch.long, device=DEV),
+                torch.zeros(2, 64, device=DEV))       # horizon not a multiple of 4
+    with pytest.raises(pmp_b200.PmpError):
+        eng.wall_embed(torch.zeros(2, 7, device=DEV))  # wall vector not a multiple of token_dim
+    with pytest.raises(pmp_b200.PmpError):
+        pmp_b200.colchk_maze2d_swept(torch.zeros(1, 8, 2, device=DEV), np.zeros(1, np.int32), np.zeros((1, 40, 2)), 0.1)
+    assert pmp_b200.launch_count() > 0

@@ -1,0 +1,215 @@
+"""CPU: the oracle restatement against the golden vectors frozen from the live reference
+(tests/golden/gen_golden.py), and -- when /root/reference is present -- against the live
+reference itself."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import refshim, synth, unet_ref, sampler_ref, colchk_ref
+from util import golden, pad_noise
+
+torch.set_num_threads(8)
+
+
+@pytest.mark.parametrize("fam", synth.FAMILIES)
+def test_unet_eps_matches_golden(fam):
+    g = golden("unet_eps_%s.npz" % fam)
+    a = synth.arch(fam)
+    sd = unet_ref.synth_weights(a["unet"], int(g["weight_seed"]))
+    assert synth.state_dict_digest(sd) == str(g["digest"])
+    cfg = unet_ref.UnetCfg(a["unet"])
+    x, t, walls = torch.tensor(g["x"]), torch.tensor(g["t"]), torch.tensor(g["walls"])
+    eps = unet_ref.eps_autograd(sd, cfg, x, t, walls, n_cond=int(g["n_cond"]))
+    # same torch build, same ops -> bit-identical
+    assert torch.equal(eps, torch.tensor(g["eps"]))
+    eps_a, _ = unet_ref.eps_analytic(sd, cfg, x, t, walls, n_cond=int(g["n_cond"]))
+    assert (eps_a - eps).abs().max() < 1e-5 * eps.abs().max() + 1e-6
+
+
+def test_analytic_vjp_fp64():
+    a = synth.arch("dualkuka")
+    cfg = unet_ref.UnetCfg(a["unet"])
+    sd = {k: v.double() for k, v in unet_ref.synth_weights(a["unet"], 3).items()}
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 40, 14, generator=g, dtype=torch.float64)
+    walls = torch.rand(2, 15, generator=g, dtype=torch.float64)
+    t = torch.tensor([3, 77])
+    e1 = unet_ref.eps_autograd(sd, cfg, x, t, walls, n_cond=1)
+    e2, _ = unet_ref.eps_analytic(sd, cfg, x, t, walls, n_cond=1)
+    assert (e1 - e2).abs().max() < 1e-12
+
+
+@pytest.mark.parametrize("fam,mode", [("m2d", "ddim"), ("m2d", "ddpm"), ("kuka", "ddim"), ("dualkuka", "ddim")])
+def test_sampler_matches_golden(fam, mode):
+    g = golden("sample_%s.npz" % fam)
+    a = synth.arch(fam)
+    cfg = unet_ref.UnetCfg(a["unet"])
+    sd = unet_ref.synth_weights(a["unet"], int(g["weight_seed"]))
+    n = int(g[mode + "_steps"])
+    noise = pad_noise(g[mode + "_noise"], n)
+    x = sampler_ref.sample([(sd, cfg)], torch.tensor(g["start"]), torch.tensor(g["goal"]), [torch.tensor(g["walls"])],
+                           noise, T=100, ddim_steps=n if mode == "ddim" else 0)
+    assert torch.equal(x, torch.tensor(g[mode + "_x"]))
+
+
+@pytest.mark.parametrize("mode", ["ddim24", "ddpm"])
+def test_compose_matches_golden(mode):
+    g = golden("compose_m2d.npz")
+    models = []
+    for fam, seed in (("m2d", int(g["seeds"][0])), ("m2d_nw3", int(g["seeds"][1]))):
+        a = synth.arch(fam)
+        models.append((unet_ref.synth_weights(a["unet"], seed), unet_ref.UnetCfg(a["unet"])))
+    start, goal = torch.tensor(g["start"]), torch.tensor(g["goal"])
+    walls = [torch.tensor(g["walls1"]), torch.tensor(g["walls2"])]
+    noise = torch.tensor(g[mode + "_noise"])
+    steps = [int(v) for v in g[mode + "_steps"]]
+    tb = sampler_ref.schedule(100)
+    x = noise[0].clone()
+    B = x.shape[0]
+    for i, t in enumerate(steps):
+        x = sampler_ref.apply_cond(x, start, goal)
+        tt = torch.full((B,), t, dtype=torch.long)
+        ecs, eus = [], []
+        for (sd, cfg), wl in zip(models, walls):
+            ec, eu = unet_ref.eps_pair(sd, cfg, x, tt, wl)
+            ecs.append(ec); eus.append(eu)
+        eps = sampler_ref.compose(ecs, eus, [float(v) for v in g["w"]], 0)
+        if mode == "ddim24":
+            x = sampler_ref.ddim_update(tb, x, t, eps, 24, 100, 1.0, noise[1 + i])
+        else:
+            x = sampler_ref.ddpm_update(tb, x, t, eps, noise[1 + i])
+    x = sampler_ref.apply_cond(x, start, goal)
+    assert torch.equal(x, torch.tensor(g[mode + "_x"]))
+
+
+@pytest.mark.parametrize("fam", ["m2d", "m2d_nw3", "m2d_concave"])
+def test_colchk_matches_golden(fam):
+    g = golden("colchk_maze2d.npz")
+    tr, env = g[fam + "_traj"], g[fam + "_env"]
+    v, c = colchk_ref.maze2d_swept(tr, env, g[fam + "_boxes"], float(g[fam + "_hext"]), legacy_div=bool(int(g["legacy_div"])))
+    assert np.array_equal(v, g[fam + "_valid"]) and np.array_equal(c, g[fam + "_nchk"])
+    n, _ = colchk_ref.maze2d_points(np.clip(tr, 0, 5), env, g[fam + "_boxes"], float(g[fam + "_hext"]))
+    assert np.array_equal(n, g[fam + "_ncol"])
+    assert 0 < v.mean() < 1   # fixtures exercise both outcomes
+
+
+def test_colchk_edge_cases():
+    cen = np.array([[[2.5, 2.5]]]); hext = 0.5
+    H = 8
+    line = np.stack([np.linspace(0.2, 4.8, H), np.full(H, 2.5)], -1).astype(np.float32)   # straight through the box
+    free = np.stack([np.linspace(0.2, 4.8, H), np.full(H, 0.5)], -1).astype(np.float32)
+    oob = free.copy(); oob[3, 1] = -0.1
+    tr = np.stack([line, free, oob])
+    v, c = colchk_ref.maze2d_swept(tr, np.zeros(3, np.int32), cen, hext)
+    assert v.tolist() == [0, 1, 0]
+    # |segment| = 0.657 -> K = int(0.657/0.08) = 8 -> 2 endpoint + 7 interior checks per free segment
+    K = int(np.float64(np.float32(np.sqrt(np.float32((line[1, 0] - line[0, 0]) ** 2)))) / 0.08)
+    assert K == 8 and c[1] == (H - 1) * (2 + K - 1)
+    # out-of-limits waypoint 3: segments 0 and 1 are checked in full, segment 2 fails the limits
+    # test before any collision check (abstract_robot.py:135-136)
+    assert c[2] == 2 * (2 + K - 1)
+    assert c[0] < c[1]   # early exit at the first colliding point
+    # no walls at all, two waypoints
+    v, c = colchk_ref.maze2d_swept(free[None, :2], np.zeros(1, np.int32), np.zeros((1, 0, 2)), np.zeros((1, 0, 2)))
+    assert v.tolist() == [1]
+    # numpy-version hazard (Appendix C.3): the two K conventions can differ
+    v1, c1 = colchk_ref.maze2d_swept(tr, np.zeros(3, np.int32), cen, hext, legacy_div=True)
+    v2, c2 = colchk_ref.maze2d_swept(tr, np.zeros(3, np.int32), cen, hext, legacy_div=False)
+    assert np.array_equal(v1, v2)
+
+
+def test_kuka_model_sanity():
+    sph = colchk_ref.kuka_sphere_table()
+    assert sph.shape[1] == 5 and (np.diff(sph[:, 0]) >= 0).all()
+    up = np.zeros((1, 4, 7), np.float32)            # arm straight up: free
+    box_far = np.array([[[2.0, 2.0, 0.5]]], np.float32)
+    r = colchk_ref.kuka_points(up, np.zeros(1, np.int32), box_far, 0.2)
+    assert r["valid"].tolist() == [1] and r["nchk"].tolist() == [4]
+    box_hit = np.array([[[0.0, 0.0, 1.0]]], np.float32)   # box on the arm's axis
+    r = colchk_ref.kuka_points(up, np.zeros(1, np.int32), box_hit, 0.2)
+    assert r["valid"].tolist() == [0] and r["nchk"].tolist() == [1] and r["ncol"].tolist() == [4]
+    bent = up.copy(); bent[0, :, 1] = 2.0           # shoulder folded down: hits the table plane
+    r = colchk_ref.kuka_points(bent, np.zeros(1, np.int32), box_far, 0.2)
+    assert r["valid"].tolist() == [0]
+    # FK check: tip of link 7 at q=0 is at z = sum of the chain offsets
+    fx = colchk_ref.kuka_fixed_transforms()
+    assert abs(fx[:, 11].sum() - 0) < 10  # smoke; exact geometry covered by the table/box cases above
+    # dual arm: bases 1 m apart, both upright -> free; arms reaching at each other collide
+    up2 = np.zeros((1, 2, 14), np.float32)
+    r = colchk_ref.kuka_points(up2, np.zeros(1, np.int32), box_far, 0.22, n_arms=2)
+    assert r["valid"].tolist() == [1]
+    reach = up2.copy(); reach[0, :, 1] = -1.57; reach[0, :, 8] = 1.57
+    r2 = colchk_ref.kuka_points(reach, np.zeros(1, np.int32), box_far, 0.22, n_arms=2)
+    reach2 = up2.copy(); reach2[0, :, 1] = 1.57; reach2[0, :, 8] = -1.57
+    r3 = colchk_ref.kuka_points(reach2, np.zeros(1, np.int32), box_far, 0.22, n_arms=2)
+    assert r2["valid"].tolist() == [0] or r3["valid"].tolist() == [0]
+
+
+def test_pick_first_valid():
+    valid = np.array([0, 1, 1, 0, 0, 0, 1, 0, 0], np.uint8)
+    nchk = np.arange(1, 10, dtype=np.int32)
+    ch, su, tot = colchk_ref.pick_first_valid(valid, nchk, 3, 3)
+    assert ch.tolist() == [1, 2, 0] and su.tolist() == [True, False, True] and tot.tolist() == [3, 15, 7]
+
+
+# ------------------------------------------------------------------ live reference (build container only)
+needs_ref = pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+
+
+@needs_ref
+def test_param_inventory_matches_reference():
+    U, G = refshim.load_models()
+    for fam in synth.FAMILIES:
+        a = synth.arch(fam)
+        with refshim.quiet():
+            m = U(**a["unet"])
+        ref = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert list(ref.items()) == list(unet_ref.param_shapes(a["unet"]).items())
+
+
+@needs_ref
+def test_oracle_matches_live_reference_eps():
+    U, G = refshim.load_models()
+    a = synth.arch("kuka")
+    sd = unet_ref.synth_weights(a["unet"], 4)
+    with refshim.quiet():
+        m = U(**a["unet"]).eval()
+        m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 52, 7, generator=g); t = torch.tensor([9, 80, 9, 80])
+    walls = torch.rand(4, 12, generator=g)
+    with refshim.quiet():
+        ref = m(x.clone(), None, t, walls, use_dropout=False, force_dropout=True, half_fd=True).detach()
+    got = unet_ref.eps_autograd(sd, unet_ref.UnetCfg(a["unet"]), x, t, walls, n_cond=2)
+    assert torch.equal(ref, got)
+
+
+@needs_ref
+def test_oracle_colchk_matches_live_reference():
+    P, RW, RWG, Env = refshim.load_maze2d_geometry()
+    rng = np.random.default_rng(1)
+    pr = synth.make_problems("m2d", 4, 17)
+    H = 48
+    for e in range(4):
+        rob = P(np.array([5., 5.]), RWG([RW(np.array(c), np.array([0.5, 0.5])) for c in pr["boxes"][e]]), 0.01,
+                collision_eps=0.08)
+        env = object.__new__(Env); env.robot = rob
+        al = np.linspace(0, 1, H)[:, None].astype(np.float32)
+        for sig in (0.02, 0.2):
+            tr = (pr["start"][e] * (1 - al) + pr["goal"][e] * al + rng.normal(0, sig, (H, 2)) * np.sin(np.pi * al)).astype(np.float32)
+            tr = np.clip(tr, 0, 5)
+            cnt, ok = 0, True
+            with contextlib.redirect_stdout(io.StringIO()):
+                for j in range(H - 1):
+                    rob.collision_check_count = 0
+                    good = env.edge_fp(tr[j], tr[j + 1])
+                    cnt += rob.collision_check_count
+                    if not good:
+                        ok = False
+                        break
+            v, c = colchk_ref.maze2d_swept(tr[None], np.zeros(1, np.int32), pr["boxes"][e], 0.5,
+                                           legacy_div=np.__version__ < "2")
+            assert bool(v[0]) == ok and int(c[0]) == cnt
