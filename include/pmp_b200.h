@@ -195,6 +195,13 @@ int pmp_pick_first_valid(const uint8_t *valid_dev, const int32_t *nchk_dev, int 
 
 /* ---- introspection for tests / bench: number of kernels this library launched so far. */
 uint64_t pmp_launch_count(void);
+/* per-launch CUDA-event timing of the implicit-GEMM conv kernels (class 0: fp32 SIMT core,
+ * class 1: tcgen05 core).  While enabled every conv launch is bracketed by two events on its
+ * stream; pmp_profile_read waits for them, returns summed milliseconds, algorithmic FLOPs
+ * (2*M*N*K of the convolution, independent of how many tensor passes the kernel makes) and
+ * launch counts per class, and clears the records. */
+int pmp_profile_enable(int on);
+int pmp_profile_read(int n_classes, double *ms, double *flops, int64_t *launches);
 /* debug: copy an internal activation of the last pmp_unet_eps call (first row chunk) to the
  * host; name e.g. "yhat:downs.0.0.blocks.0." ; returns element count or <0 */
 int64_t pmp_debug_fetch(pmp_model *m, const char *name, float *host_out, int64_t capacity);

@@ -31,6 +31,35 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n); }
 
+// ---- optional per-launch CUDA-event profiler for the conv kernels (bench.py roofline)
+struct ProfRec { cudaEvent_t a, b; double flops; int cls; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+static double conv_flops(const ConvP& p) {
+    double k = 0;
+    for (int ph = 0; ph < p.nphase; ++ph) k += (double)p.ntaps[ph] * p.C1;
+    k /= p.nphase;   // each output row belongs to exactly one phase
+    if (p.A2) k += p.C2;
+    return 2.0 * (double)p.R * p.Hout * p.N * k;
+}
+static int prof_launch_conv(const ConvP& p, cudaStream_t st, int cls, int (*fn)(const ConvP&, cudaStream_t)) {
+    if (!g_prof_on) return fn(p, st);
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!g_prof_pool.empty()) {
+        ev = g_prof_pool.back();
+        g_prof_pool.pop_back();
+    } else {
+        PMP_CUDA_OK(cudaEventCreate(&ev.first));
+        PMP_CUDA_OK(cudaEventCreate(&ev.second));
+    }
+    PMP_CUDA_OK(cudaEventRecord(ev.first, st));
+    int rc = fn(p, st);
+    PMP_CUDA_OK(cudaEventRecord(ev.second, st));
+    g_prof.push_back(ProfRec{ev.first, ev.second, conv_flops(p), cls});
+    return rc;
+}
+
 struct HostT {
     std::vector<int64_t> shape;
     std::vector<float> v;
@@ -489,7 +518,7 @@ struct Ctx {
     }
     void conv(const ConvP& p) {
         if (dry || rc) return;
-        rc = launch_conv_simt(p, st);
+        rc = prof_launch_conv(p, st, 0, launch_conv_simt);
     }
     void dbg(const std::string& name, float* p, int64_t n) {
         if (!dry) m->dbg[name] = std::make_pair(p, n);
@@ -1057,6 +1086,25 @@ int pmp_sample(const pmp_sample_args* a, void* stream) {
     cudaFreeAsync(t2, st);
     for (int k = 0; k < K; ++k) cudaFreeAsync(wtab[k], st);
     return rc;
+}
+
+int pmp_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return 0;
+}
+
+int pmp_profile_read(int n_classes, double* ms, double* flops, int64_t* launches) {
+    PMP_REQUIRE(ms && flops && launches && n_classes >= 1, "bad argument");
+    for (int i = 0; i < n_classes; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
+    for (auto& r : g_prof) {
+        PMP_CUDA_OK(cudaEventSynchronize(r.b));
+        float t = 0;
+        PMP_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+        if (r.cls < n_classes) { ms[r.cls] += t; flops[r.cls] += r.flops; launches[r.cls] += 1; }
+        g_prof_pool.push_back(std::make_pair(r.a, r.b));
+    }
+    g_prof.clear();
+    return 0;
 }
 
 int64_t pmp_debug_fetch(pmp_model* m, const char* name, float* host_out, int64_t capacity) {

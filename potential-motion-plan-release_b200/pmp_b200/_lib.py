@@ -68,6 +68,8 @@ _PROTOS = {
     "pmp_pick_first_valid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
     "pmp_launch_count": (C.c_uint64, []),
+    "pmp_profile_enable": (C.c_int, [C.c_int]),
+    "pmp_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pmp_debug_fetch": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
 }
 
@@ -115,6 +117,19 @@ def device_count():
 
 def launch_count():
     return int(lib().pmp_launch_count())
+
+
+def profile_enable(on=True):
+    _check(lib().pmp_profile_enable(1 if on else 0))
+
+
+def profile_read(n_classes=2):
+    """[(ms, algorithmic flops, launches)] per conv-kernel class since the last read"""
+    ms = (C.c_double * n_classes)()
+    fl = (C.c_double * n_classes)()
+    ln = (C.c_int64 * n_classes)()
+    _check(lib().pmp_profile_read(n_classes, ms, fl, ln))
+    return [(ms[i], fl[i], int(ln[i])) for i in range(n_classes)]
 
 
 class UnetEngine:
