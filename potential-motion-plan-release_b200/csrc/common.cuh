@@ -1,6 +1,7 @@
 // Shared declarations of the pmp_b200 CUDA library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -103,12 +104,30 @@ struct ConvP {
     float* out; int ldo;            // result after all adds (may be null)
     float* gy; int ldg;             // gn_bwd result
     float* energy;                  // [R] += 0.5*sum v^2   (final 1x1 conv only)
+    // BF16x3 operand planes (v ~= hi + lo) of `out` / `gy`, same [row][ld] indexing, for consumers
+    // that run on the tcgen05 core (null when the consumer is a SIMT conv)
+    __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+    __nv_bfloat16* gy_hi; __nv_bfloat16* gy_lo;
+    // operand planes of the inputs (A1 / A2) and BF16x3 weights laid out [tap][N][C] (K-major),
+    // used only by the tcgen05 core
+    const __nv_bfloat16* A1_hi; const __nv_bfloat16* A1_lo;
+    const __nv_bfloat16* A2_hi; const __nv_bfloat16* A2_lo;
+    const __nv_bfloat16* W1_hi; const __nv_bfloat16* W1_lo;
+    const __nv_bfloat16* W2_hi; const __nv_bfloat16* W2_lo;
 };
 
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
 int launch_conv_simt(const ConvP& p, cudaStream_t st);
+// tcgen05 core; returns 1 (and launches nothing) when the op does not fit it
+int launch_conv_tc(const ConvP& p, cudaStream_t st);
+bool conv_tc_eligible(const ConvP& p);
 int launch_gn_bwd(const float* g, int ldgi, const float* yhat, int ldy, const float* rstd,
-                  const float* gamma, const float* beta, int act, float* gy, int ldg, int R,
-                  int Hl, int C, cudaStream_t st);
+                  const float* gamma, const float* beta, int act, float* gy, int ldg,
+                  __nv_bfloat16* gy_hi, __nv_bfloat16* gy_lo, int R, int Hl, int C, cudaStream_t st);
 int conv_simt_smem_bytes(const ConvP& p, int TN);
 
 // embeddings / wall encoder (embed.cu)

@@ -319,6 +319,11 @@ __global__ void __launch_bounds__(NTHREADS) conv_simt_kernel(const __grid_consta
                 for (int j = 0; j < TN; ++j)
                     if (vc[j]) o[j] = acc[i][j];
             }
+            if (p.out_hi) {
+#pragma unroll
+                for (int j = 0; j < TN; ++j)
+                    if (vc[j]) split_bf16(acc[i][j], p.out_hi[orow[i] * p.ldo + nb + j], p.out_lo[orow[i] * p.ldo + nb + j]);
+            }
         }
     }
 
@@ -384,7 +389,11 @@ __global__ void __launch_bounds__(NTHREADS) conv_simt_kernel(const __grid_consta
             float* o = p.gy + orow[i] * p.ldg + nb;
 #pragma unroll
             for (int j = 0; j < TN; ++j)
-                if (vc[j]) o[j] = rs * (acc[i][j] - m1 - yh[i][j] * m2);
+                if (vc[j]) {
+                    const float gv = rs * (acc[i][j] - m1 - yh[i][j] * m2);
+                    o[j] = gv;
+                    if (p.gy_hi) split_bf16(gv, p.gy_hi[orow[i] * p.ldg + nb + j], p.gy_lo[orow[i] * p.ldg + nb + j]);
+                }
         }
     }
 }
@@ -396,7 +405,9 @@ __global__ void __launch_bounds__(128) gn_bwd_kernel(const float* __restrict__ g
                                                      const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, int act,
-                                                     float* __restrict__ gy, int ldg, int Hl, int C) {
+                                                     float* __restrict__ gy, int ldg,
+                                                     __nv_bfloat16* __restrict__ gy_hi,
+                                                     __nv_bfloat16* __restrict__ gy_lo, int Hl, int C) {
     const int r = blockIdx.x >> 3, grp = blockIdx.x & 7;
     const int gs = C >> 3, n = Hl * gs;
     __shared__ float red[2][4];
@@ -429,7 +440,9 @@ __global__ void __launch_bounds__(128) gn_bwd_kernel(const float* __restrict__ g
         const float y = yhat[row * ldy + c];
         const float ga = gamma[c];
         const float gyh = g[row * ldgi + c] * act_bwd(ga * y + beta[c], act) * ga;
-        gy[row * ldg + c] = rs * (gyh - m1 - y * m2);
+        const float gv = rs * (gyh - m1 - y * m2);
+        gy[row * ldg + c] = gv;
+        if (gy_hi) split_bf16(gv, gy_hi[row * ldg + c], gy_lo[row * ldg + c]);
     }
 }
 
@@ -478,9 +491,9 @@ int launch_conv_simt(const ConvP& p, cudaStream_t st) {
 }
 
 int launch_gn_bwd(const float* g, int ldgi, const float* yhat, int ldy, const float* rstd,
-                  const float* gamma, const float* beta, int act, float* gy, int ldg, int R, int Hl,
-                  int C, cudaStream_t st) {
-    gn_bwd_kernel<<<R * 8, 128, 0, st>>>(g, ldgi, yhat, ldy, rstd, gamma, beta, act, gy, ldg, Hl, C);
+                  const float* gamma, const float* beta, int act, float* gy, int ldg,
+                  __nv_bfloat16* gy_hi, __nv_bfloat16* gy_lo, int R, int Hl, int C, cudaStream_t st) {
+    gn_bwd_kernel<<<R * 8, 128, 0, st>>>(g, ldgi, yhat, ldy, rstd, gamma, beta, act, gy, ldg, gy_hi, gy_lo, Hl, C);
     PMP_LAUNCH_OK();
     return 0;
 }

@@ -1,0 +1,652 @@
+// tcgen05 / TMEM / TMA implicit-GEMM Conv1d (k=5, pad 2, stride 1; plus an optional 1x1 slab)
+// with the fused U-Net epilogues, in error-compensated BF16x3 arithmetic.
+//
+// Replaces the cuDNN conv + native GroupNorm + SiLU + embedding/residual adds of
+//   Conv1dBlock_dd / ResidualTemporalBlock_dd   diffuser/models/helpers.py:88-94, temporal_dd.py:71-74
+// and their backward-data counterparts inside torch.autograd.grad (temporal_cond.py:321).
+//
+// GEMM view: M = (samples x horizon) rows, N = output channels, K = taps x input channels.
+//   * one tile = S whole samples (S*H <= 128 rows) x NT channels, so GroupNorm slabs never
+//     straddle tiles and the conv halo is produced by TMA out-of-bounds zero fill: the A tile of
+//     tap k is ONE 3-D box (64 channels, H rows, S samples) of the channels-last activation
+//     tensor started at row k-2;
+//   * operands are BF16 pairs (v ~= hi + lo, |error| ~ 2^-17 |v|); each K block issues
+//     hi*hi + hi*lo + lo*hi into the same FP32 TMEM accumulator -> ~2^-16 relative product
+//     error, which keeps eps within the 1e-3 parity budget where single-pass BF16/TF32 does not
+//     (SURVEY.md 7.3 item 1); algorithmic FLOPs are 1/3 of the issued tensor FLOPs;
+//   * persistent CTAs, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner),
+//     warps 2..5 epilogue; smem ring of NSTAGE stages, two TMEM accumulator stages so the
+//     epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+
+#include <map>
+#include <tuple>
+
+#include <string.h>
+
+#include "common.cuh"
+
+namespace pmp {
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int BK = 64;                      // channels per K block = one 128-byte swizzle row
+constexpr int A_TILE_BYTES = 128 * BK * 2;  // 16 KB per BF16 plane
+constexpr int MAXSEG = 5;                   // samples touched by 32 consecutive rows (H >= 8)
+
+struct TcP {
+    ConvP e;
+    int tilesM, tilesN, ntiles;
+    int kpt;        // K blocks per tap = C1 / 64
+    int nkb1, nkb2; // K blocks of slab 1 / slab 2
+    alignas(64) CUtensorMap mA1h;
+    alignas(64) CUtensorMap mA1l;
+    alignas(64) CUtensorMap mA2h;
+    alignas(64) CUtensorMap mA2l;
+    alignas(64) CUtensorMap mW1h;
+    alignas(64) CUtensorMap mW1l;
+    alignas(64) CUtensorMap mW2h;
+    alignas(64) CUtensorMap mW2l;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, BF16 inputs, FP32 accumulate, M=128
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// K-major, 128-byte swizzle, rows of 64 BF16: 8-row groups 1024 B apart (SBO = 64 x 16 B), LBO = 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int GS>
+__device__ __forceinline__ float group_reduce(float v) {
+    // sum over the lanes of one GroupNorm group inside a 32-column chunk
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (GS >= 16) v += __shfl_xor_sync(0xffffffffu, v, 8);
+    if (GS >= 32) v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+}
+
+template <int NT, int GS, bool ACC2>
+struct Cfg {
+    static constexpr int B_TILE_BYTES = NT * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    static constexpr int NSTAGE = NT == 64 ? 4 : (NT == 128 ? 3 : 2);
+    static constexpr int ACC_COLS = NT * (ACC2 ? 2 : 1);
+    static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
+    static constexpr int G = GS ? NT / GS : 1;
+    static constexpr int NCH = NT / 32;
+    // smem: stages | transpose buffers | row/slab partials | slab stats | column params | row info | barriers
+    static constexpr int TBUF_FLOATS = 4 * 32 * 33;
+    static constexpr int PART_FLOATS = 128 * 8 * 2;
+    static constexpr int STAT_FLOATS = 256;
+    static constexpr int COL_FLOATS = 4 * NT;
+    static constexpr int ROW_INTS = 2 * 128;
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES +
+                                      (TBUF_FLOATS + PART_FLOATS + STAT_FLOATS + COL_FLOATS + ROW_INTS) * 4 + 256 + 1024;
+};
+
+template <int NT, int GS, bool ACC2>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcP P) {
+    using C = Cfg<NT, GS, ACC2>;
+    constexpr int G = C::G, NCH = C::NCH, NSTAGE = C::NSTAGE, NACC = C::NACC;
+    const ConvP& p = P.e;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* tbuf = reinterpret_cast<float*>(smem + NSTAGE * C::STAGE_BYTES);
+    float* spart = tbuf + C::TBUF_FLOATS;
+    float* sstat = spart + C::PART_FLOATS;
+    float* scol = sstat + C::STAT_FLOATS;                 // bias | gamma | beta | bias2, NT each
+    int* srow = reinterpret_cast<int*>(scol + C::COL_FLOATS);   // [128] output row index (or -1), [128] global sample
+    uint64_t* bars = reinterpret_cast<uint64_t*>(srow + C::ROW_INTS);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NSTAGE;
+    uint64_t* tfull = bars + 2 * NSTAGE;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.S, HJ = p.HJ, N = p.N;
+    const uint32_t bytesA = (uint32_t)(S * HJ * BK * 2);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&P.mA1h); prefetch_tmap(&P.mA1l); prefetch_tmap(&P.mW1h); prefetch_tmap(&P.mW1l);
+        if (P.nkb2) { prefetch_tmap(&P.mA2h); prefetch_tmap(&P.mA2l); prefetch_tmap(&P.mW2h); prefetch_tmap(&P.mW2l); }
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+                const int r0 = (tile / P.tilesN) * S, n0 = (tile % P.tilesN) * NT;
+                for (int kb = 0; kb < P.nkb1 + P.nkb2; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + s * C::STAGE_BYTES;
+                    mbar_expect_tx(&full[s], 2 * bytesA + 2 * C::B_TILE_BYTES);
+                    if (kb < P.nkb1) {
+                        const int tap = kb / P.kpt, c0 = (kb - tap * P.kpt) * BK;
+                        const int sh = p.tap_shift[0][tap], wr = p.tap_k[0][tap] * N + n0;
+                        tma_load_3d(st, &P.mA1h, &full[s], c0, sh, r0);
+                        tma_load_3d(st + A_TILE_BYTES, &P.mA1l, &full[s], c0, sh, r0);
+                        tma_load_2d(st + 2 * A_TILE_BYTES, &P.mW1h, &full[s], c0, wr);
+                        tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &P.mW1l, &full[s], c0, wr);
+                    } else {
+                        const int c0 = (kb - P.nkb1) * BK;
+                        tma_load_3d(st, &P.mA2h, &full[s], c0, 0, r0);
+                        tma_load_3d(st + A_TILE_BYTES, &P.mA2l, &full[s], c0, 0, r0);
+                        tma_load_2d(st + 2 * A_TILE_BYTES, &P.mW2h, &full[s], c0, n0);
+                        tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &P.mW2l, &full[s], c0, n0);
+                    }
+                    if (++s == NSTAGE) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            // instruction descriptor: D=F32, A=B=BF16, both K-major, N=NT, M=128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+            int s = 0, as = 0;
+            uint32_t ph = 0, aph = 0;
+            for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+                mbar_wait(&tempty[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d1 = tmem_base + (uint32_t)(as * C::ACC_COLS);
+                const uint32_t d2 = ACC2 ? d1 + NT : d1;
+                uint32_t acc1 = 0, acc2 = ACC2 ? 0u : 1u;
+                for (int kb = 0; kb < P.nkb1 + P.nkb2; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+                    const uint64_t ah = make_desc(sa), al = make_desc(sa + A_TILE_BYTES);
+                    const uint64_t bh = make_desc(sa + 2 * A_TILE_BYTES), bl = make_desc(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES);
+                    const bool slab2 = kb >= P.nkb1;
+                    const uint32_t d = slab2 ? d2 : d1;
+                    uint32_t accum = slab2 ? (ACC2 ? acc2 : 1u) : acc1;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 2);   // 32 bytes per K=16 step, in 16-byte units
+                        tc_mma(d, ah + ko, bh + ko, idesc, accum);
+                        tc_mma(d, ah + ko, bl + ko, idesc, 1u);
+                        tc_mma(d, al + ko, bh + ko, idesc, 1u);
+                        accum = 1u;
+                    }
+                    if (slab2) acc2 = 1u; else acc1 = 1u;
+                    tc_commit(&empty[s]);   // frees the smem stage when these MMAs have read it
+                    if (++s == NSTAGE) { s = 0; ph ^= 1; }
+                }
+                tc_commit(&tfull[as]);      // accumulator complete
+                if (++as == NACC) { as = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        // ============================== epilogue (warps 2..5) ==============================
+        const int eq = warp & 3;                 // TMEM lane quarter this warp may read
+        const int etid = (warp - 2) * 32 + lane; // 0..127
+        float* tb = tbuf + (warp - 2) * 32 * 33;
+        const int act = p.act;
+        const float inv_cnt = 1.0f / (float)(HJ * (GS ? GS : 1));
+        int as = 0;
+        uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+            const int r0 = (tile / P.tilesN) * S, n0 = (tile % P.tilesN) * NT;
+            const int Sv = min(S, p.R - r0);
+            const int Mv = Sv * HJ;
+            // per-tile tables (previous tile's readers are past the closing epi_bar)
+            for (int i = etid; i < NT; i += 128) {
+                scol[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+                scol[NT + i] = p.gamma ? __ldg(p.gamma + n0 + i) : 0.f;
+                scol[2 * NT + i] = p.beta ? __ldg(p.beta + n0 + i) : 0.f;
+                scol[3 * NT + i] = p.bias2 ? __ldg(p.bias2 + n0 + i) : 0.f;
+            }
+            {
+                const int m = etid;
+                if (m < Mv) {
+                    const int s = m / HJ;
+                    srow[m] = (r0 + s) * p.Hout + (m - s * HJ);
+                    srow[128 + m] = r0 + s;
+                } else {
+                    srow[m] = -1;
+                    srow[128 + m] = 0;
+                }
+            }
+            if (p.gn_bwd)
+                for (int i = etid; i < 4 * MAXSEG * G * 2; i += 128) spart[i] = 0.f;
+            mbar_wait(&tfull[as], aph);
+            tc_fence_after();
+            epi_bar();
+            const uint32_t tacc = tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)(as * C::ACC_COLS);
+            const int mrow = eq * 32 + lane;                 // the row this thread holds after tcgen05.ld
+            const int s_first = (eq * 32) / HJ;              // first sample touched by this warp's rows
+            float v[32];
+
+            if (GS && p.gn_fwd) {
+                // ---- pass 1: per-row sums of y = acc + bias and y^2 for every group
+                float s1[G], s2[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) s1[g] = s2[g] = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    tmem_ld32(tacc + ch * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = v[j] + scol[ch * 32 + j];
+                        s1[(ch * 32 + j) / (GS ? GS : 1)] += x;
+                        s2[(ch * 32 + j) / (GS ? GS : 1)] += x * x;
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    spart[(mrow * G + g) * 2] = s1[g];
+                    spart[(mrow * G + g) * 2 + 1] = s2[g];
+                }
+                epi_bar();
+                if (etid < S * G) {
+                    const int s = etid / G, g = etid - s * G;
+                    float a = 0.f, b = 0.f;
+                    for (int j = 0; j < HJ; ++j) {
+                        a += spart[((s * HJ + j) * G + g) * 2];
+                        b += spart[((s * HJ + j) * G + g) * 2 + 1];
+                    }
+                    const float mean = a * inv_cnt;
+                    const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
+                    const float rs = 1.0f / sqrtf(var + 1e-5f);
+                    sstat[etid] = mean;
+                    sstat[128 + etid] = rs;
+                    if (s < Sv) p.rstd[(size_t)(r0 + s) * 8 + n0 / (GS ? GS : 1) + g] = rs;
+                }
+                epi_bar();
+            }
+
+            if (!(GS && p.gn_bwd)) {
+                // ---- forward (with or without GroupNorm) and plain backward: one output pass
+                const int srow_m = min(mrow / HJ, S - 1);
+#pragma unroll 1
+                for (int ch = 0; ch < NCH; ++ch) {
+                    tmem_ld32(tacc + ch * 32, v);
+                    if (GS && p.gn_fwd) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = ch * 32 + j;
+                            const int sl = srow_m * G + n / (GS ? GS : 1);
+                            v[j] = (v[j] + scol[n] - sstat[sl]) * sstat[128 + sl];   // yhat
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = v[j];
+                        __syncwarp();
+                        for (int r = 0; r < 32; ++r) {
+                            const int orow = srow[eq * 32 + r];
+                            if (orow >= 0) p.yhat[(size_t)orow * p.ldy + n0 + ch * 32 + lane] = tb[r * 33 + lane];
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = ch * 32 + j;
+                            v[j] = act_fwd(scol[NT + n] * v[j] + scol[2 * NT + n], act);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += scol[ch * 32 + j];
+                    }
+                    if (ACC2) {
+                        float w[32];
+                        tmem_ld32(tacc + NT + ch * 32, w);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += w[j] + scol[3 * NT + ch * 32 + j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = v[j];
+                    __syncwarp();
+                    const int n = n0 + ch * 32 + lane;
+                    for (int r = 0; r < 32; ++r) {
+                        const int orow = srow[eq * 32 + r];
+                        if (orow < 0) continue;
+                        const int rg = srow[128 + eq * 32 + r];
+                        float x = tb[r * 33 + lane];
+                        if (p.embT) {
+                            int64_t tt = p.tidx[rg];
+                            tt = tt < 0 ? 0 : (tt > p.tmax ? p.tmax : tt);
+                            x += __ldg(p.embT + (size_t)tt * p.ldeT + p.eoff + n);
+                        }
+                        if (p.embR && rg < p.n_cond) x += __ldg(p.embR + (size_t)rg * p.ldeR + p.eoff + n);
+                        if (p.ident) x += __ldg(p.ident + (size_t)orow * p.ldi + n);
+                        if (p.addend) x += __ldg(p.addend + (size_t)orow * p.ldad + n);
+                        if (p.out) p.out[(size_t)orow * p.ldo + n] = x;
+                        if (p.out_hi) split_bf16(x, p.out_hi[(size_t)orow * p.ldo + n], p.out_lo[(size_t)orow * p.ldo + n]);
+                    }
+                    __syncwarp();
+                }
+            } else {
+                // ---- backward with GroupNorm/activation backward, two passes
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        tmem_ld32(tacc + ch * 32, v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = v[j];
+                        __syncwarp();
+                        const int nl = ch * 32 + lane, n = n0 + nl;
+                        const int gl = nl / (GS ? GS : 1);
+                        const float gam = scol[NT + nl], bet = scol[2 * NT + nl];
+                        float q1 = 0.f, q2 = 0.f;
+                        int seg = 0;
+                        for (int r = 0; r < 32; ++r) {
+                            const int m = eq * 32 + r;
+                            const int orow = srow[m];
+                            float gyh = 0.f, y = 0.f;
+                            if (orow >= 0) {
+                                float x = tb[r * 33 + lane];
+                                if (p.ident) x += __ldg(p.ident + (size_t)orow * p.ldi + n);
+                                if (p.addend) x += __ldg(p.addend + (size_t)orow * p.ldad + n);
+                                if (pass == 0) {
+                                    if (p.out) p.out[(size_t)orow * p.ldo + n] = x;
+                                    if (p.out_hi) split_bf16(x, p.out_hi[(size_t)orow * p.ldo + n], p.out_lo[(size_t)orow * p.ldo + n]);
+                                }
+                                y = __ldg(p.yhat + (size_t)orow * p.ldy + n);
+                                gyh = x * act_bwd(gam * y + bet, act) * gam;
+                            }
+                            const int sm = m / HJ;   // sample of this row (warp uniform)
+                            if (pass == 0) {
+                                q1 += gyh;
+                                q2 += gyh * y;
+                                const bool last = (r == 31) || ((m + 1) / HJ != sm);
+                                if (last) {
+                                    const float t1 = group_reduce<GS>(q1), t2 = group_reduce<GS>(q2);
+                                    if ((lane & ((GS < 32 ? GS : 32) - 1)) == 0 && seg < MAXSEG) {
+                                        float* d = spart + (((warp - 2) * MAXSEG + seg) * G + gl) * 2;
+                                        d[0] += t1;
+                                        d[1] += t2;
+                                    }
+                                    q1 = q2 = 0.f;
+                                    ++seg;
+                                }
+                            } else if (orow >= 0) {
+                                const int sl = min(sm, S - 1) * G + gl;
+                                const float rs = __ldg(p.rstd + (size_t)srow[128 + m] * 8 + n0 / (GS ? GS : 1) + gl);
+                                const float gv = rs * (gyh - sstat[sl] - y * sstat[128 + sl]);
+                                p.gy[(size_t)orow * p.ldg + n] = gv;
+                                if (p.gy_hi) split_bf16(gv, p.gy_hi[(size_t)orow * p.ldg + n], p.gy_lo[(size_t)orow * p.ldg + n]);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    if (pass == 0) {
+                        epi_bar();
+                        if (etid < S * G) {
+                            // fixed-order combine of the per-warp segment partials of slab (s, g)
+                            const int s = etid / G, g = etid - s * G;
+                            float a = 0.f, b = 0.f;
+                            for (int w = 0; w < 4; ++w) {
+                                const int q = (w + 2) & 3;                  // TMEM quarter of epilogue warp w
+                                const int sg = s - (q * 32) / HJ;
+                                if (sg >= 0 && sg < MAXSEG && (q * 32) < Mv + HJ) {
+                                    a += spart[((w * MAXSEG + sg) * G + g) * 2];
+                                    b += spart[((w * MAXSEG + sg) * G + g) * 2 + 1];
+                                }
+                            }
+                            sstat[etid] = a * inv_cnt;
+                            sstat[128 + etid] = b * inv_cnt;
+                        }
+                        epi_bar();
+                    }
+                }
+            }
+            (void)s_first;
+            // release the accumulator stage
+            tc_fence_before();
+            epi_bar();
+            if (etid == 0) mbar_arrive(&tempty[as]);
+            if (++as == NACC) { as = 0; aph ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+    static EncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeFn>(ptr);
+    }
+    return fn;
+}
+
+using MapKey = std::tuple<const void*, int, int, int, int, int, int>;
+std::map<MapKey, CUtensorMap> g_maps;
+
+// activation plane [R][H][ld] BF16 -> 3-D map (C, H, R), box (64, H, S)
+int act_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int H, int R, int ld, int S) {
+    MapKey key(base, C, H, R, ld, S, 3);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+    EncodeFn enc = get_encode();
+    PMP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)R};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)H};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)H, (cuuint32_t)S};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation C=%d H=%d R=%d ld=%d S=%d) failed: %d", C, H, R, ld, S, (int)r);
+    g_maps[key] = *out;
+    return 0;
+}
+// weight plane [taps*N][C] BF16 -> 2-D map (C, taps*N), box (64, NT)
+int w_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int rows, int NT) {
+    MapKey key(base, C, rows, NT, 0, 0, 2);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+    EncodeFn enc = get_encode();
+    PMP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)NT};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight C=%d rows=%d NT=%d) failed: %d", C, rows, NT, (int)r);
+    g_maps[key] = *out;
+    return 0;
+}
+
+int g_num_sms = 0;
+
+template <int NT, int GS, bool ACC2>
+int launch_t(TcP& P, cudaStream_t st) {
+    using C = Cfg<NT, GS, ACC2>;
+    static bool configured = false;
+    if (!configured) {
+        PMP_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NT, GS, ACC2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES));
+        configured = true;
+    }
+    if (!g_num_sms) {
+        int dev = 0;
+        PMP_CUDA_OK(cudaGetDevice(&dev));
+        PMP_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int grid = P.ntiles < g_num_sms ? P.ntiles : g_num_sms;
+    conv_tc_kernel<NT, GS, ACC2><<<grid, TC_THREADS, C::SMEM_BYTES, st>>>(P);
+    PMP_LAUNCH_OK();
+    return 0;
+}
+
+int pick_nt(const ConvP& p) {
+    const bool gn = p.gn_fwd || p.gn_bwd;
+    if (gn) {
+        const int gs = p.N / 8;
+        if (gs == 8) return 64;
+        if (gs == 32 || gs == 64) return 128;
+        if (gs == 96) return 192;
+        return 0;
+    }
+    if (p.N % 128 == 0) return 128;
+    if (p.N % 64 == 0) return 64;
+    return 0;
+}
+}  // namespace
+
+bool conv_tc_eligible(const ConvP& p) {
+    if (p.nphase != 1 || p.istride != 1 || p.ostride != 1) return false;           // stride-1 convs only
+    if (!p.A1_hi || !p.A1_lo || !p.W1_hi || !p.W1_lo) return false;
+    if (p.C1 % BK != 0 || (p.lda1 % 8) != 0) return false;
+    if (p.A2 && (!p.A2_hi || !p.A2_lo || !p.W2_hi || !p.W2_lo || p.C2 % BK != 0 || (p.lda2 % 8) != 0)) return false;
+    if (p.energy) return false;
+    if (p.HJ < 8 || p.HJ > 128 || p.HJ > 256) return false;
+    const int nt = pick_nt(p);
+    if (!nt || p.N % nt != 0) return false;
+    if ((p.gn_fwd || p.gn_bwd) && (128 / p.HJ) * (nt / (p.N / 8)) > 128) return false;
+    return true;
+}
+
+int launch_conv_tc(const ConvP& p, cudaStream_t st) {
+    if (!conv_tc_eligible(p)) return 1;
+    TcP P;
+    memset(&P, 0, sizeof P);
+    P.e = p;
+    const int NT = pick_nt(p);
+    const int S = 128 / p.HJ;
+    P.e.S = S;
+    P.tilesM = (p.R + S - 1) / S;
+    P.tilesN = p.N / NT;
+    P.ntiles = P.tilesM * P.tilesN;
+    P.kpt = p.C1 / BK;
+    P.nkb1 = p.ntaps[0] * P.kpt;
+    P.nkb2 = p.A2 ? p.C2 / BK : 0;
+    int rc;
+    if ((rc = act_map(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S))) return rc;
+    if ((rc = act_map(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S))) return rc;
+    int maxk = 0;
+    for (int t = 0; t < p.ntaps[0]; ++t) maxk = p.tap_k[0][t] > maxk ? p.tap_k[0][t] : maxk;
+    if ((rc = w_map(&P.mW1h, p.W1_hi, p.C1, (maxk + 1) * p.N, NT))) return rc;
+    if ((rc = w_map(&P.mW1l, p.W1_lo, p.C1, (maxk + 1) * p.N, NT))) return rc;
+    if (p.A2) {
+        if ((rc = act_map(&P.mA2h, p.A2_hi, p.C2, p.Hin, p.R, p.lda2, S))) return rc;
+        if ((rc = act_map(&P.mA2l, p.A2_lo, p.C2, p.Hin, p.R, p.lda2, S))) return rc;
+        if ((rc = w_map(&P.mW2h, p.W2_hi, p.C2, p.N, NT))) return rc;
+        if ((rc = w_map(&P.mW2l, p.W2_lo, p.C2, p.N, NT))) return rc;
+    }
+    const bool gn = p.gn_fwd || p.gn_bwd;
+    const bool acc2 = (p.A2 != nullptr) && (p.bias2 != nullptr || p.gn_fwd);
+    const int gs = gn ? p.N / 8 : 0;
+    if (NT == 64) {
+        if (gs == 8) return acc2 ? launch_t<64, 8, true>(P, st) : launch_t<64, 8, false>(P, st);
+        return acc2 ? launch_t<64, 0, true>(P, st) : launch_t<64, 0, false>(P, st);
+    }
+    if (NT == 128) {
+        if (gs == 32) return acc2 ? launch_t<128, 32, true>(P, st) : launch_t<128, 32, false>(P, st);
+        if (gs == 64) return acc2 ? launch_t<128, 64, true>(P, st) : launch_t<128, 64, false>(P, st);
+        return acc2 ? launch_t<128, 0, true>(P, st) : launch_t<128, 0, false>(P, st);
+    }
+    if (NT == 192) return acc2 ? launch_t<192, 96, true>(P, st) : launch_t<192, 96, false>(P, st);
+    return 1;
+}
+
+}  // namespace pmp

@@ -78,9 +78,14 @@ struct Grad {
     float* gy = nullptr;  // dense [R*Hl][C]
 };
 
+struct TcW {  // BF16x3 weight planes [tap][N][C] in the 16-bit arena (element offsets)
+    bool ok = false;
+    size_t hi = 0, lo = 0;
+};
 struct CBW {  // Conv1dBlock_dd: conv k5 + GroupNorm(8) + act
     int Cin = 0, Cout = 0;
     size_t Wf = 0, Wb = 0, bias = 0, gamma = 0, beta = 0;  // offsets into the packed arena
+    TcW tcf, tcb;
     // saved for backward (per eps evaluation)
     float* yhat = nullptr;
     float* rstd = nullptr;
@@ -91,6 +96,7 @@ struct ResB {
     CBW cb[2];
     bool has_res = false;
     size_t Rf = 0, Rb = 0, Rbias = 0;
+    TcW tcRf, tcRb;
     int eoff = 0;       // channel offset in the embedding tables
     size_t tmW = 0, tmB = 0;      // cfg 0: Linear(128->Cout); cfg 3: second Linear(256->Cout)
     size_t tm0W = 0, tm0B = 0;    // cfg 3: first Linear(128->256)
@@ -122,6 +128,7 @@ struct pmp_model {
     int hid = 0;    // cfg3 hidden width per block (2*time_dim)
     float* arena = nullptr;   // packed weights on device
     size_t arena_n = 0;
+    __nv_bfloat16* arena16 = nullptr;   // BF16x3 weight planes for the tcgen05 core
     float* temb_tab = nullptr;  // [T][dim]
     float* embT = nullptr;      // cfg0: [T][Ctot] ; cfg3: Ht [T][nblk*hid]
     // per-call tables (grown on demand)
@@ -130,7 +137,7 @@ struct pmp_model {
     float* hidb = nullptr; size_t hidb_n = 0;   // cfg3 per step hidden [R][nblk*hid]
     float* ws = nullptr; size_t ws_n = 0;       // activation workspace (floats)
     int row_chunk = 2048;
-    int gemm_path = 0;
+    int gemm_path = 1;
     std::map<std::string, std::pair<float*, int64_t>> dbg;
     bool has_down(int L) const { return !(L >= nl - 1 || L >= arch.down_times); }
     bool has_up(int ind) const { return !(ind >= nl - 1 || ind < (nl - arch.down_times - 1)); }
@@ -157,6 +164,44 @@ struct Packer {
         buf.resize(off + v.size());
         memcpy(buf.data() + off, v.data(), v.size() * sizeof(float));
         return off;
+    }
+};
+
+// BF16 hi/lo split of a [K][C][N] fp32 weight, transposed to the K-major B-operand layout [K][N][C]
+struct Packer16 {
+    std::vector<uint16_t> buf;
+    static uint16_t bf16_rn(float f) {
+        uint32_t u;
+        memcpy(&u, &f, 4);
+        if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+        u += 0x7fffu + ((u >> 16) & 1u);
+        return (uint16_t)(u >> 16);
+    }
+    static float bf16_f(uint16_t h) {
+        uint32_t u = (uint32_t)h << 16;
+        float f;
+        memcpy(&f, &u, 4);
+        return f;
+    }
+    TcW add(const std::vector<float>& w /*[K][C][N]*/, int K, int C, int N) {
+        TcW t;
+        if (C % 64 != 0 || N % 64 != 0) return t;
+        const size_t n = (size_t)K * C * N;
+        size_t off = (buf.size() + 63) & ~(size_t)63;   // 128-byte aligned planes
+        const size_t stride = (n + 63) & ~(size_t)63;
+        buf.resize(off + 2 * stride);
+        for (int k = 0; k < K; ++k)
+            for (int c = 0; c < C; ++c)
+                for (int nn = 0; nn < N; ++nn) {
+                    const float v = w[((size_t)k * C + c) * N + nn];
+                    const uint16_t h = bf16_rn(v);
+                    const uint16_t l = bf16_rn(v - bf16_f(h));
+                    const size_t o = ((size_t)k * N + nn) * C + c;
+                    buf[off + o] = h;
+                    buf[off + stride + o] = l;
+                }
+        t.ok = true; t.hi = off; t.lo = off + stride;
+        return t;
     }
 };
 
@@ -203,7 +248,7 @@ static void convT_layouts(const HostT& w, std::vector<float>& f, std::vector<flo
             }
 }
 
-static int pack_cb(pmp_model* m, Packer& pk, const std::string& pfx, CBW& cb) {
+static int pack_cb(pmp_model* m, Packer& pk, Packer16& pk16, const std::string& pfx, CBW& cb) {
     NEED(w, pfx + "block.0.weight");
     NEED(b, pfx + "block.0.bias");
     NEED(g, pfx + "block.2.weight");
@@ -215,21 +260,23 @@ static int pack_cb(pmp_model* m, Packer& pk, const std::string& pfx, CBW& cb) {
     std::vector<float> t;
     conv_fwd_layout(*w, t);
     cb.Wf = pk.add(t);
+    cb.tcf = pk16.add(t, 5, cb.Cin, cb.Cout);
     conv_bwd_layout(*w, t, true);
     cb.Wb = pk.add(t);
+    cb.tcb = pk16.add(t, 5, cb.Cout, cb.Cin);
     cb.bias = pk.add(b->v);
     cb.gamma = pk.add(g->v);
     cb.beta = pk.add(be->v);
     return 0;
 }
 
-static int pack_res(pmp_model* m, Packer& pk, const std::string& pfx, int Cin, int Cout, ResB& rb) {
+static int pack_res(pmp_model* m, Packer& pk, Packer16& pk16, const std::string& pfx, int Cin, int Cout, ResB& rb) {
     rb.pfx = pfx;
     rb.Cin = Cin;
     rb.Cout = Cout;
     int rc;
-    if ((rc = pack_cb(m, pk, pfx + "blocks.0.", rb.cb[0]))) return rc;
-    if ((rc = pack_cb(m, pk, pfx + "blocks.1.", rb.cb[1]))) return rc;
+    if ((rc = pack_cb(m, pk, pk16, pfx + "blocks.0.", rb.cb[0]))) return rc;
+    if ((rc = pack_cb(m, pk, pk16, pfx + "blocks.1.", rb.cb[1]))) return rc;
     PMP_REQUIRE(rb.cb[0].Cin == Cin && rb.cb[0].Cout == Cout && rb.cb[1].Cin == Cout && rb.cb[1].Cout == Cout,
                 "%s: conv shapes do not match the architecture (%d->%d)", pfx.c_str(), Cin, Cout);
     rb.has_res = find(m, pfx + "residual_conv.weight") != nullptr;
@@ -240,8 +287,10 @@ static int pack_res(pmp_model* m, Packer& pk, const std::string& pfx, int Cin, i
         std::vector<float> t;
         conv_fwd_layout(*w, t);
         rb.Rf = pk.add(t);
+        rb.tcRf = pk16.add(t, 1, Cin, Cout);
         conv_bwd_layout(*w, t, false);
         rb.Rb = pk.add(t);
+        rb.tcRb = pk16.add(t, 1, Cout, Cin);
         rb.Rbias = pk.add(b->v);
     }
     const int tdim = m->arch.dim + m->arch.wall_embed_dim;
@@ -275,6 +324,7 @@ static int finalize_model(pmp_model* m) {
     m->dims.assign(1, a.transition_dim);
     for (int i = 0; i < a.n_mults; ++i) m->dims.push_back(a.dim * a.dim_mults[i]);
     Packer pk;
+    Packer16 pk16;
     int rc;
     m->blocks.clear();
     char nm[128];
@@ -282,14 +332,14 @@ static int finalize_model(pmp_model* m) {
         for (int j = 0; j < 2; ++j) {
             snprintf(nm, sizeof nm, "downs.%d.%d.", L, j);
             ResB rb;
-            if ((rc = pack_res(m, pk, nm, j == 0 ? m->dims[L] : m->dims[L + 1], m->dims[L + 1], rb))) return rc;
+            if ((rc = pack_res(m, pk, pk16, nm, j == 0 ? m->dims[L] : m->dims[L + 1], m->dims[L + 1], rb))) return rc;
             m->blocks.push_back(rb);
         }
     }
     {
         ResB rb1, rb2;
-        if ((rc = pack_res(m, pk, "mid_block1.", m->dims[m->nl], m->dims[m->nl], rb1))) return rc;
-        if ((rc = pack_res(m, pk, "mid_block2.", m->dims[m->nl], m->dims[m->nl], rb2))) return rc;
+        if ((rc = pack_res(m, pk, pk16, "mid_block1.", m->dims[m->nl], m->dims[m->nl], rb1))) return rc;
+        if ((rc = pack_res(m, pk, pk16, "mid_block2.", m->dims[m->nl], m->dims[m->nl], rb2))) return rc;
         m->blocks.push_back(rb1);
         m->blocks.push_back(rb2);
     }
@@ -299,7 +349,7 @@ static int finalize_model(pmp_model* m) {
         for (int j = 0; j < 2; ++j) {
             snprintf(nm, sizeof nm, "ups.%d.%d.", ind, j);
             ResB rb;
-            if ((rc = pack_res(m, pk, nm, j == 0 ? 2 * Cs : Co, Co, rb))) return rc;
+            if ((rc = pack_res(m, pk, pk16, nm, j == 0 ? 2 * Cs : Co, Co, rb))) return rc;
             m->blocks.push_back(rb);
         }
     }
@@ -340,7 +390,7 @@ static int finalize_model(pmp_model* m) {
         pc.Wf = pk.add(f); pc.Wb = pk.add(bw);
         pc.bias = pk.add(b->v);
     }
-    if ((rc = pack_cb(m, pk, "final_conv.0.", m->finalcb))) return rc;
+    if ((rc = pack_cb(m, pk, pk16, "final_conv.0.", m->finalcb))) return rc;
     {
         NEED(w, "final_conv.1.weight");
         NEED(b, "final_conv.1.bias");
@@ -403,6 +453,12 @@ static int finalize_model(pmp_model* m) {
     m->arena_n = pk.buf.size();
     PMP_CUDA_OK(cudaMalloc((void**)&m->arena, m->arena_n * sizeof(float)));
     PMP_CUDA_OK(cudaMemcpy(m->arena, pk.buf.data(), m->arena_n * sizeof(float), cudaMemcpyHostToDevice));
+    if (m->arena16) cudaFree(m->arena16);
+    m->arena16 = nullptr;
+    if (!pk16.buf.empty()) {
+        PMP_CUDA_OK(cudaMalloc((void**)&m->arena16, pk16.buf.size() * sizeof(uint16_t)));
+        PMP_CUDA_OK(cudaMemcpy(m->arena16, pk16.buf.data(), pk16.buf.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
     VitW& v = m->vit;
     memset(&v, 0, sizeof v);
     v.token_dim = a.vit_token_dim; v.octaves = a.vit_octaves; v.depth = a.vit_depth; v.dim = 64;
@@ -501,6 +557,8 @@ static ConvP geom_t2(int R, int Hin, int KS) {
 }
 
 // ------------------------------------------------------------------ one eps evaluation
+typedef __nv_bfloat16 bf16;
+
 struct Ctx {
     pmp_model* m;
     cudaStream_t st;
@@ -510,20 +568,65 @@ struct Ctx {
     const int64_t* t;
     const float* embRow;   // cfg0: embR rows of this chunk; cfg3: E rows of this chunk
     int rc = 0;
+    bool tc() const { return m->gemm_path == 1; }
     float* alloc(size_t n) {
         n = (n + 3) & ~(size_t)3;
         float* p = dry ? nullptr : m->ws + used;
         used += n;
         return p;
     }
+    // BF16x3 operand planes for an fp32 tensor of n elements (tensor-core path only)
+    void planes(size_t n, bf16** hi, bf16** lo) {
+        *hi = *lo = nullptr;
+        if (!tc()) return;
+        float* p = alloc(n);   // 2 planes x n x 2 bytes = n floats
+        if (!dry) {
+            *hi = reinterpret_cast<bf16*>(p);
+            *lo = *hi + ((n + 7) & ~(size_t)7);
+        }
+        used += 8;             // slack for the 16-byte rounding of the second plane
+    }
     void conv(const ConvP& p) {
         if (dry || rc) return;
+        if (tc() && conv_tc_eligible(p)) {
+            rc = prof_launch_conv(p, st, 1, launch_conv_tc);
+            return;
+        }
         rc = prof_launch_conv(p, st, 0, launch_conv_simt);
     }
-    void dbg(const std::string& name, float* p, int64_t n) {
-        if (!dry) m->dbg[name] = std::make_pair(p, n);
+    void dbg(const char* kind, const std::string& name, float* p, int64_t n) {
+        if (!dry) m->dbg[std::string(kind) + name] = std::make_pair(p, n);
     }
 };
+
+// forward activation view with its operand planes
+struct ActP : Act {
+    bf16* hi = nullptr;
+    bf16* lo = nullptr;
+};
+struct GradP {
+    float* raw = nullptr;
+    bf16 *raw_hi = nullptr, *raw_lo = nullptr;
+    int ldr = 0;
+    float* gy = nullptr;   // dense [R*Hl][C]
+    bf16 *gy_hi = nullptr, *gy_lo = nullptr;
+};
+
+static ActP new_act(Ctx& c, int C, int Hl) {
+    ActP a;
+    a.p = c.alloc((size_t)c.R * Hl * C);
+    c.planes((size_t)c.R * Hl * C, &a.hi, &a.lo);
+    a.ld = C; a.C = C; a.Hl = Hl; a.blk = -1;
+    return a;
+}
+static ActP view_act(const ActP& base, int off, int C) {
+    ActP a = base;
+    a.p = base.p ? base.p + off : nullptr;
+    a.hi = base.hi ? base.hi + off : nullptr;
+    a.lo = base.lo ? base.lo + off : nullptr;
+    a.C = C;
+    return a;
+}
 
 static void set_emb(Ctx& c, ConvP& p, const ResB& b) {
     const pmp_model* m = c.m;
@@ -535,70 +638,97 @@ static void set_emb(Ctx& c, ConvP& p, const ResB& b) {
     }
     p.eoff = b.eoff;
 }
+static void set_A1(ConvP& p, const float* a, const bf16* hi, const bf16* lo, int ld, int C) {
+    p.A1 = a; p.A1_hi = hi; p.A1_lo = lo; p.lda1 = ld; p.C1 = C;
+}
+static void set_A2(ConvP& p, const float* a, const bf16* hi, const bf16* lo, int ld, int C) {
+    p.A2 = a; p.A2_hi = hi; p.A2_lo = lo; p.lda2 = ld; p.C2 = C;
+}
+static void set_W1(const pmp_model* m, ConvP& p, size_t off, const TcW& t) {
+    p.W1 = m->A(off);
+    if (t.ok && m->arena16) { p.W1_hi = m->arena16 + t.hi; p.W1_lo = m->arena16 + t.lo; }
+}
+static void set_W2(const pmp_model* m, ConvP& p, size_t off, const TcW& t) {
+    p.W2 = m->A(off);
+    if (t.ok && m->arena16) { p.W2_hi = m->arena16 + t.hi; p.W2_lo = m->arena16 + t.lo; }
+}
 
-// out = ResidualTemporalBlock_dd(x)   (temporal_dd.py:71-74)
-static void res_fwd(Ctx& c, int bi, const Act& x, Act& out) {
+// out = ResidualTemporalBlock_dd(x)   (temporal_dd.py:71-74); `out` is pre-allocated (maybe a concat view)
+static void res_fwd(Ctx& c, int bi, const ActP& x, ActP& out) {
     pmp_model* m = c.m;
     ResB& b = m->blocks[bi];
     const int R = c.R, Hl = x.Hl, Co = b.Cout;
     for (int j = 0; j < 2; ++j) {
         b.cb[j].yhat = c.alloc((size_t)R * Hl * Co);
         b.cb[j].rstd = c.alloc((size_t)R * 8);
-        c.dbg("yhat:" + b.pfx + (j ? "blocks.1." : "blocks.0."), b.cb[j].yhat, (int64_t)R * Hl * Co);
+        c.dbg("yhat:", b.pfx + (j ? "blocks.1." : "blocks.0."), b.cb[j].yhat, (int64_t)R * Hl * Co);
     }
-    float* mid = c.alloc((size_t)R * Hl * Co);
+    ActP mid = new_act(c, Co, Hl);
     ConvP p = geom_s1(R, Hl, 5);
-    p.A1 = x.p; p.lda1 = x.ld; p.C1 = b.Cin; p.W1 = m->A(b.cb[0].Wf); p.N = Co;
+    set_A1(p, x.p, x.hi, x.lo, x.ld, b.Cin);
+    set_W1(m, p, b.cb[0].Wf, b.cb[0].tcf);
+    p.N = Co;
     p.bias = m->A(b.cb[0].bias); p.gn_fwd = 1; p.gamma = m->A(b.cb[0].gamma); p.beta = m->A(b.cb[0].beta);
     p.yhat = b.cb[0].yhat; p.ldy = Co; p.rstd = b.cb[0].rstd; p.act = m->arch.act;
     set_emb(c, p, b);
-    p.out = mid; p.ldo = Co;
+    p.out = mid.p; p.ldo = Co; p.out_hi = mid.hi; p.out_lo = mid.lo;
     c.conv(p);
     ConvP q = geom_s1(R, Hl, 5);
-    q.A1 = mid; q.lda1 = Co; q.C1 = Co; q.W1 = m->A(b.cb[1].Wf); q.N = Co;
+    set_A1(q, mid.p, mid.hi, mid.lo, Co, Co);
+    set_W1(m, q, b.cb[1].Wf, b.cb[1].tcf);
+    q.N = Co;
     q.bias = m->A(b.cb[1].bias); q.gn_fwd = 1; q.gamma = m->A(b.cb[1].gamma); q.beta = m->A(b.cb[1].beta);
     q.yhat = b.cb[1].yhat; q.ldy = Co; q.rstd = b.cb[1].rstd; q.act = m->arch.act;
     if (b.has_res) {
-        q.A2 = x.p; q.lda2 = x.ld; q.C2 = b.Cin; q.W2 = m->A(b.Rf); q.bias2 = m->A(b.Rbias);
+        set_A2(q, x.p, x.hi, x.lo, x.ld, b.Cin);
+        set_W2(m, q, b.Rf, b.tcRf);
+        q.bias2 = m->A(b.Rbias);
     } else {
         q.ident = x.p; q.ldi = x.ld;
     }
-    q.out = out.p; q.ldo = out.ld;
+    q.out = out.p; q.ldo = out.ld; q.out_hi = out.hi; q.out_lo = out.lo;
     c.conv(q);
     out.C = Co; out.Hl = Hl; out.blk = bi;
-    c.dbg("out:" + b.pfx, out.p, out.ld == Co ? (int64_t)R * Hl * Co : 0);
+    c.dbg("out:", b.pfx, out.p, out.ld == Co ? (int64_t)R * Hl * Co : 0);
 }
 
 // standalone GroupNorm backward through the CB1 of the block that produced `x`
-static void gn_bwd_of(Ctx& c, const Act& x, const float* raw, int ldr, float* gy) {
+static void gn_bwd_of(Ctx& c, const Act& x, const float* raw, int ldr, float* gy, bf16* gy_hi, bf16* gy_lo) {
     if (c.dry || c.rc) return;
     pmp_model* m = c.m;
     const CBW& cb = m->blocks[x.blk].cb[1];
-    c.rc = launch_gn_bwd(raw, ldr, cb.yhat, x.C, cb.rstd, m->A(cb.gamma), m->A(cb.beta), m->arch.act, gy, x.C, c.R,
-                         x.Hl, x.C, c.st);
+    c.rc = launch_gn_bwd(raw, ldr, cb.yhat, x.C, cb.rstd, m->A(cb.gamma), m->A(cb.beta), m->arch.act, gy, x.C, gy_hi,
+                         gy_lo, c.R, x.Hl, x.C, c.st);
 }
 
 // launches a backward conv `p` whose result is the gradient w.r.t. activation `x`;
 // emits raw (+addend) and, when `x` came out of a residual block, the GroupNorm-backward'ed
 // gradient for that block's second conv (fused when one tile holds whole slabs)
-static Grad emit_grad(Ctx& c, ConvP& p, const Act& x, const float* addend, int ldad, float* raw_dst, int ld_dst,
-                      bool fusable) {
-    Grad g;
-    g.raw = raw_dst ? raw_dst : c.alloc((size_t)c.R * x.Hl * x.C);
-    g.ldr = raw_dst ? ld_dst : x.C;
-    p.out = g.raw; p.ldo = g.ldr;
+static GradP emit_grad(Ctx& c, ConvP& p, const Act& x, const float* addend, int ldad, float* raw_dst, int ld_dst,
+                       bool fusable) {
+    GradP g;
+    const size_t n = (size_t)c.R * x.Hl * x.C;
+    if (raw_dst) {
+        g.raw = raw_dst; g.ldr = ld_dst;
+    } else {
+        g.raw = c.alloc(n); g.ldr = x.C;
+        c.planes(n, &g.raw_hi, &g.raw_lo);
+    }
+    p.out = g.raw; p.ldo = g.ldr; p.out_hi = g.raw_hi; p.out_lo = g.raw_lo;
     p.addend = addend; p.ldad = ldad;
     p.act = c.m->arch.act;
     if (x.blk >= 0) {
-        g.gy = c.alloc((size_t)c.R * x.Hl * x.C);
+        g.gy = c.alloc(n);
+        c.planes(n, &g.gy_hi, &g.gy_lo);
         if (fusable && p.N == x.C) {
             const CBW& cb = c.m->blocks[x.blk].cb[1];
             p.gn_bwd = 1; p.gamma = c.m->A(cb.gamma); p.beta = c.m->A(cb.beta);
             p.yhat = cb.yhat; p.ldy = x.C; p.rstd = cb.rstd; p.gy = g.gy; p.ldg = x.C;
+            p.gy_hi = g.gy_hi; p.gy_lo = g.gy_lo;
             c.conv(p);
         } else {
             c.conv(p);
-            gn_bwd_of(c, x, g.raw, g.ldr, g.gy);
+            gn_bwd_of(c, x, g.raw, g.ldr, g.gy, g.gy_hi, g.gy_lo);
         }
     } else {
         c.conv(p);
@@ -607,26 +737,35 @@ static Grad emit_grad(Ctx& c, ConvP& p, const Act& x, const float* addend, int l
 }
 
 // gradient through a residual block: gout = dE/d(out) -> dE/d(x)   
-static Grad res_bwd(Ctx& c, int bi, const Grad& gout, const Act& x, const float* addend, int ldad, float* raw_dst,
-                    int ld_dst) {
+static GradP res_bwd(Ctx& c, int bi, const GradP& gout, const Act& x, const float* addend, int ldad, float* raw_dst,
+                     int ld_dst) {
     pmp_model* m = c.m;
     ResB& b = m->blocks[bi];
     const int R = c.R, Hl = x.Hl, Co = b.Cout;
-    float* gy0 = c.alloc((size_t)R * Hl * Co);
+    const size_t n = (size_t)R * Hl * Co;
+    float* gy0 = c.alloc(n);
+    bf16 *gy0_hi, *gy0_lo;
+    c.planes(n, &gy0_hi, &gy0_lo);
     ConvP p = geom_s1(R, Hl, 5);
-    p.A1 = gout.gy; p.lda1 = Co; p.C1 = Co; p.W1 = m->A(b.cb[1].Wb); p.N = Co;
+    set_A1(p, gout.gy, gout.gy_hi, gout.gy_lo, Co, Co);
+    set_W1(m, p, b.cb[1].Wb, b.cb[1].tcb);
+    p.N = Co;
     p.gn_bwd = 1; p.gamma = m->A(b.cb[0].gamma); p.beta = m->A(b.cb[0].beta);
     p.yhat = b.cb[0].yhat; p.ldy = Co; p.rstd = b.cb[0].rstd; p.gy = gy0; p.ldg = Co; p.act = m->arch.act;
+    p.gy_hi = gy0_hi; p.gy_lo = gy0_lo;
     c.conv(p);
     ConvP q = geom_s1(R, Hl, 5);
-    q.A1 = gy0; q.lda1 = Co; q.C1 = Co; q.W1 = m->A(b.cb[0].Wb); q.N = b.Cin;
+    set_A1(q, gy0, gy0_hi, gy0_lo, Co, Co);
+    set_W1(m, q, b.cb[0].Wb, b.cb[0].tcb);
+    q.N = b.Cin;
     if (b.has_res) {
-        q.A2 = gout.raw; q.lda2 = gout.ldr; q.C2 = Co; q.W2 = m->A(b.Rb);
+        set_A2(q, gout.raw, gout.raw_hi, gout.raw_lo, gout.ldr, Co);
+        set_W2(m, q, b.Rb, b.tcRb);
     } else {
         q.ident = gout.raw; q.ldi = gout.ldr;
     }
-    Grad g = emit_grad(c, q, x, addend, ldad, raw_dst, ld_dst, true);
-    c.dbg("gx:" + b.pfx, g.raw, g.ldr == x.C ? (int64_t)R * Hl * x.C : 0);
+    GradP g = emit_grad(c, q, x, addend, ldad, raw_dst, ld_dst, true);
+    c.dbg("gx:", b.pfx, g.raw, g.ldr == x.C ? (int64_t)R * Hl * x.C : 0);
     return g;
 }
 
@@ -637,25 +776,25 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
     Hl[0] = H;
     for (int L = 1; L < nl; ++L) Hl[L] = m->has_down(L - 1) ? Hl[L - 1] / 2 : Hl[L - 1];
     // concat buffers for skip levels 1..nl-1: [R][Hl][2*C]; level 0 skip is never consumed
-    std::vector<float*> cat(nl, nullptr);
-    for (int L = 1; L < nl; ++L) cat[L] = c.alloc((size_t)R * Hl[L] * 2 * m->dims[L + 1]);
-    std::vector<Act> lvl_in(nl), lvl_a(nl), lvl_b(nl);
-    Act cur;
+    std::vector<ActP> cat(nl);
+    for (int L = 1; L < nl; ++L) cat[L] = new_act(c, 2 * m->dims[L + 1], Hl[L]);
+    std::vector<ActP> lvl_in(nl), lvl_a(nl), lvl_b(nl);
+    ActP cur;
     cur.p = const_cast<float*>(x_in); cur.ld = D; cur.C = D; cur.Hl = H; cur.blk = -1;
     for (int L = 0; L < nl; ++L) {
         const int C = m->dims[L + 1];
         lvl_in[L] = cur;
-        Act a; a.p = c.alloc((size_t)R * Hl[L] * C); a.ld = C;
+        ActP a = new_act(c, C, Hl[L]);
         res_fwd(c, 2 * L, cur, a);
-        Act b;
-        if (L >= 1) { b.p = cat[L] + C; b.ld = 2 * C; } else { b.p = c.alloc((size_t)R * Hl[L] * C); b.ld = C; }
+        ActP b = (L >= 1) ? view_act(cat[L], C, C) : new_act(c, C, Hl[L]);
         res_fwd(c, 2 * L + 1, a, b);
         lvl_a[L] = a; lvl_b[L] = b;
         if (m->has_down(L)) {
-            Act d; d.p = c.alloc((size_t)R * (Hl[L] / 2) * C); d.ld = C; d.C = C; d.Hl = Hl[L] / 2; d.blk = -1;
+            ActP d = new_act(c, C, Hl[L] / 2);
             ConvP p = geom_s2(R, Hl[L] / 2, 3);
-            p.A1 = b.p; p.lda1 = b.ld; p.C1 = C; p.W1 = m->A(m->downc[L].Wf); p.N = C; p.bias = m->A(m->downc[L].bias);
-            p.out = d.p; p.ldo = d.ld;
+            set_A1(p, b.p, nullptr, nullptr, b.ld, C);
+            p.W1 = m->A(m->downc[L].Wf); p.N = C; p.bias = m->A(m->downc[L].bias);
+            p.out = d.p; p.ldo = d.ld; p.out_hi = d.hi; p.out_lo = d.lo;
             c.conv(p);
             cur = d;
         } else {
@@ -664,31 +803,30 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
     }
     const int bmid = 2 * nl;
     const int Cm = m->dims[nl];
-    Act mid_in = cur;
-    Act m1; m1.p = c.alloc((size_t)R * Hl[nl - 1] * Cm); m1.ld = Cm;
+    ActP mid_in = cur;
+    ActP m1 = new_act(c, Cm, Hl[nl - 1]);
     res_fwd(c, bmid, cur, m1);
-    Act m2; m2.p = cat[nl - 1]; m2.ld = 2 * Cm;
+    ActP m2 = view_act(cat[nl - 1], 0, Cm);
     res_fwd(c, bmid + 1, m1, m2);
     cur = m2;
-    std::vector<Act> up_in(nl), up_a(nl), up_b(nl), up_out(nl);
+    std::vector<ActP> up_in(nl), up_a(nl), up_b(nl), up_out(nl);
     for (int ind = 0; ind < nl - 1; ++ind) {
-        const int Ls = nl - 1 - ind, Cs = m->dims[Ls + 1], Co = m->dims[Ls], h = Hl[Ls];
-        Act catv; catv.p = cat[Ls]; catv.ld = 2 * Cs; catv.C = 2 * Cs; catv.Hl = h; catv.blk = -1;
+        const int Ls = nl - 1 - ind, Co = m->dims[Ls], h = Hl[Ls];
         up_in[ind] = cur;   // first half of the concat (view), with its producer
-        Act a; a.p = c.alloc((size_t)R * h * Co); a.ld = Co;
-        res_fwd(c, bmid + 2 + 2 * ind, catv, a);
+        ActP a = new_act(c, Co, h);
+        res_fwd(c, bmid + 2 + 2 * ind, cat[Ls], a);
         const bool up = m->has_up(ind);
         const bool last = ind == nl - 2;
-        Act b;
-        if (!up && !last) { b.p = cat[Ls - 1]; b.ld = 2 * Co; } else { b.p = c.alloc((size_t)R * h * Co); b.ld = Co; }
+        ActP b = (!up && !last) ? view_act(cat[Ls - 1], 0, Co) : new_act(c, Co, h);
         res_fwd(c, bmid + 3 + 2 * ind, a, b);
         up_a[ind] = a; up_b[ind] = b;
         if (up) {
-            Act o; o.C = Co; o.Hl = 2 * h; o.blk = -1;
-            if (!last) { o.p = cat[Ls - 1]; o.ld = 2 * Co; } else { o.p = c.alloc((size_t)R * 2 * h * Co); o.ld = Co; }
+            ActP o = !last ? view_act(cat[Ls - 1], 0, Co) : new_act(c, Co, 2 * h);
+            o.Hl = 2 * h; o.blk = -1;
             ConvP p = geom_t2(R, h, 4);
-            p.A1 = b.p; p.lda1 = b.ld; p.C1 = Co; p.W1 = m->A(m->upc[ind].Wf); p.N = Co; p.bias = m->A(m->upc[ind].bias);
-            p.out = o.p; p.ldo = o.ld;
+            set_A1(p, b.p, nullptr, nullptr, b.ld, Co);
+            p.W1 = m->A(m->upc[ind].Wf); p.N = Co; p.bias = m->A(m->upc[ind].bias);
+            p.out = o.p; p.ldo = o.ld; p.out_hi = o.hi; p.out_lo = o.lo;
             c.conv(p);
             cur = o;
         } else {
@@ -705,10 +843,13 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
     CBW& fcb = m->finalcb;
     fcb.yhat = c.alloc((size_t)R * H * C0);
     fcb.rstd = c.alloc((size_t)R * 8);
+    c.dbg("yhat:", "final_conv.0.", fcb.yhat, (int64_t)R * H * C0);
     float* f = c.alloc((size_t)R * H * C0);
     {
         ConvP p = geom_s1(R, H, 5);
-        p.A1 = cur.p; p.lda1 = cur.ld; p.C1 = C0; p.W1 = m->A(fcb.Wf); p.N = C0; p.bias = m->A(fcb.bias);
+        set_A1(p, cur.p, cur.hi, cur.lo, cur.ld, C0);
+        set_W1(m, p, fcb.Wf, fcb.tcf);
+        p.N = C0; p.bias = m->A(fcb.bias);
         p.gn_fwd = 1; p.gamma = m->A(fcb.gamma); p.beta = m->A(fcb.beta); p.yhat = fcb.yhat; p.ldy = C0;
         p.rstd = fcb.rstd; p.act = m->arch.act; p.out = f; p.ldo = C0;
         c.conv(p);
@@ -720,26 +861,32 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
             if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return PMP_ERR_CUDA; }
         }
         ConvP p = geom_s1(R, H, 1);
-        p.A1 = f; p.lda1 = C0; p.C1 = C0; p.W1 = m->A(m->fin1Wf); p.N = D; p.bias = m->A(m->fin1b);
+        set_A1(p, f, nullptr, nullptr, C0, C0);
+        p.W1 = m->A(m->fin1Wf); p.N = D; p.bias = m->A(m->fin1b);
         p.out = u; p.ldo = D; p.energy = energy;
         c.conv(p);
     }
-    c.dbg("u", u, (int64_t)R * H * D);
+    c.dbg("", "u", u, (int64_t)R * H * D);
 
     // ================= backward: seed g_u = u (E = 0.5*sum u^2) =================
     float* gyf = c.alloc((size_t)R * H * C0);
+    bf16 *gyf_hi, *gyf_lo;
+    c.planes((size_t)R * H * C0, &gyf_hi, &gyf_lo);
     {
         ConvP p = geom_s1(R, H, 1);
-        p.A1 = u; p.lda1 = D; p.C1 = D; p.W1 = m->A(m->fin1Wb); p.N = C0;
+        set_A1(p, u, nullptr, nullptr, D, D);
+        p.W1 = m->A(m->fin1Wb); p.N = C0;
         p.gn_bwd = 1; p.gamma = m->A(fcb.gamma); p.beta = m->A(fcb.beta); p.yhat = fcb.yhat; p.ldy = C0;
-        p.rstd = fcb.rstd; p.gy = gyf; p.ldg = C0; p.act = m->arch.act;
+        p.rstd = fcb.rstd; p.gy = gyf; p.ldg = C0; p.gy_hi = gyf_hi; p.gy_lo = gyf_lo; p.act = m->arch.act;
         c.conv(p);
     }
-    Grad g;
+    GradP g;
     {
         // gradient w.r.t. the input of final_conv (= up_out[nl-2])
         ConvP p = geom_s1(R, H, 5);
-        p.A1 = gyf; p.lda1 = C0; p.C1 = C0; p.W1 = m->A(fcb.Wb); p.N = C0;
+        set_A1(p, gyf, gyf_hi, gyf_lo, C0, C0);
+        set_W1(m, p, fcb.Wb, fcb.tcb);
+        p.N = C0;
         g = emit_grad(c, p, up_out[nl - 2], nullptr, 0, nullptr, 0, true);
     }
     std::vector<float*> skipg(nl, nullptr);
@@ -749,19 +896,21 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
         if (m->has_up(ind)) {
             // Upsample1d backward: strided conv with the same weight (App. G item 6)
             ConvP p = geom_s2(R, h, 4);
-            p.A1 = g.raw; p.lda1 = g.ldr; p.C1 = Co; p.W1 = m->A(m->upc[ind].Wb); p.N = Co;
+            set_A1(p, g.raw, nullptr, nullptr, g.ldr, Co);
+            p.W1 = m->A(m->upc[ind].Wb); p.N = Co;
             g = emit_grad(c, p, up_b[ind], nullptr, 0, nullptr, 0, true);
         }
         g = res_bwd(c, bmid + 3 + 2 * ind, g, up_a[ind], nullptr, 0, nullptr, 0);
         Act catv; catv.C = 2 * Cs; catv.Hl = h; catv.blk = -1;
-        Grad gc = res_bwd(c, bmid + 2 + 2 * ind, g, catv, nullptr, 0, nullptr, 0);
+        GradP gc = res_bwd(c, bmid + 2 + 2 * ind, g, catv, nullptr, 0, nullptr, 0);
         // split the concat gradient: [:Cs] continues along the up path, [Cs:] goes to the skip
-        skipg[Ls] = gc.raw + Cs; skipld[Ls] = 2 * Cs;
-        g = Grad();
-        g.raw = gc.raw; g.ldr = 2 * Cs;
+        skipg[Ls] = gc.raw ? gc.raw + Cs : nullptr; skipld[Ls] = 2 * Cs;
+        g = GradP();
+        g.raw = gc.raw; g.raw_hi = gc.raw_hi; g.raw_lo = gc.raw_lo; g.ldr = 2 * Cs;
         if (up_in[ind].blk >= 0) {
             g.gy = c.alloc((size_t)R * h * Cs);
-            gn_bwd_of(c, up_in[ind], g.raw, g.ldr, g.gy);
+            c.planes((size_t)R * h * Cs, &g.gy_hi, &g.gy_lo);
+            gn_bwd_of(c, up_in[ind], g.raw, g.ldr, g.gy, g.gy_hi, g.gy_lo);
         }
     }
     g = res_bwd(c, bmid + 1, g, m1, nullptr, 0, nullptr, 0);
@@ -786,7 +935,8 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
             // Downsample1d backward: transposed conv, output_padding 1 (App. G item 5)
             const int C = m->dims[L];
             ConvP p = geom_t2(R, Hl[L], 3);
-            p.A1 = g.raw; p.lda1 = g.ldr; p.C1 = C; p.W1 = m->A(m->downc[L - 1].Wb); p.N = C;
+            set_A1(p, g.raw, nullptr, nullptr, g.ldr, C);
+            p.W1 = m->A(m->downc[L - 1].Wb); p.N = C;
             const bool sk = L - 1 >= 1;
             g = emit_grad(c, p, lvl_b[L - 1], sk ? skipg[L - 1] : nullptr, sk ? skipld[L - 1] : 0, nullptr, 0, false);
         }
@@ -917,6 +1067,7 @@ int pmp_model_create(const pmp_arch* arch, int device, pmp_model** out) {
 void pmp_model_destroy(pmp_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
+    if (m->arena16) cudaFree(m->arena16);
     float* bufs[] = {m->arena, m->temb_tab, m->embT, m->embR, m->embE, m->hidb, m->ws};
     for (float* b : bufs)
         if (b) cudaFree(b);

@@ -37,6 +37,8 @@ def main(fams):
         eps_ag = unet_ref.eps_autograd(sd, cfg, x, t, walls, n_cond=B)
         print("[%s] oracle %.2fs  analytic-vs-autograd %.2e" % (fam, time.time() - t0, rel(eps_ref, eps_ag)))
         eng = pmp_b200.UnetEngine(a["unet"], sd, dev)
+        eng.set_gemm_path(int(os.environ.get("PMP_GEMM_PATH", "1")))
+        print("  gemm path", os.environ.get("PMP_GEMM_PATH", "1"))
         wemb = eng.wall_embed(torch.tensor(pr["walls"]))
         wemb_ref = unet_ref.wall_embed(sd, cfg, torch.tensor(pr["walls"]))
         print("  wall_embed rel err %.3e" % rel(wemb.cpu().numpy(), wemb_ref.numpy()))
@@ -61,7 +63,7 @@ def main(fams):
             if got is not None:
                 print("  %-20s finite=%s absmax=%.3e" % (name, bool(np.isfinite(got).all()), float(np.abs(got).max())))
         # timing at a moderate batch
-        Bt = 512
+        Bt = int(os.environ.get("PMP_DIAG_BT", "512"))
         xt = torch.randn(2 * Bt, H, D, device=dev)
         tt = torch.full((2 * Bt,), 50, device=dev, dtype=torch.long)
         wt = wemb[:1].repeat(Bt, 1)
