@@ -29,7 +29,7 @@
 namespace pmp {
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int BK = 64;                      // channels per K block = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = 128 * BK * 2;  // 16 KB per BF16 plane
 constexpr int MAXSEG = 5;                   // samples touched by 32 consecutive rows (H >= 8)
@@ -127,7 +127,63 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+        "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])),
+        "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])),
+        "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
+        "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])),
+        "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// per-row 128-byte segment helpers (every thread handles its own row: 8 x 16-byte vectors)
+__device__ __forceinline__ void ld_row32(const float* __restrict__ p, float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void add_row32(const float* __restrict__ p, float (&v)[32]) {
+    float4 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = __ldg(reinterpret_cast<const float4*>(p) + i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        v[4 * i] += t[i].x; v[4 * i + 1] += t[i].y; v[4 * i + 2] += t[i].z; v[4 * i + 3] += t[i].w;
+    }
+}
+__device__ __forceinline__ void st_row32(float* __restrict__ p, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void st_planes32(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                            const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v[8 * i + 2 * k], h0, l0);
+            split_bf16(v[8 * i + 2 * k + 1], h1, l1);
+            h[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            l[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        reinterpret_cast<uint4*>(hi)[i] = make_uint4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<uint4*>(lo)[i] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
 
 template <int GS>
 __device__ __forceinline__ float group_reduce(float v) {
@@ -146,15 +202,16 @@ struct Cfg {
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int NSTAGE = NT == 64 ? 4 : (NT == 128 ? 3 : 2);
     static constexpr int ACC_COLS = NT * (ACC2 ? 2 : 1);
-    static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
+    // two accumulator stages when they fit next to the yhat stash of the GroupNorm-backward epilogue
+    static constexpr int NACC = (NT <= 128 && 2 * ACC_COLS <= 512) ? 2 : 1;
     static constexpr int G = GS ? NT / GS : 1;
     static constexpr int NCH = NT / 32;
     // smem: stages | transpose buffers | row/slab partials | slab stats | column params | row info | barriers
-    static constexpr int TBUF_FLOATS = 4 * 32 * 33;
-    static constexpr int PART_FLOATS = 128 * 8 * 2;
-    static constexpr int STAT_FLOATS = 256;
+    static constexpr int TBUF_FLOATS = 0;
+    static constexpr int PART_FLOATS = 2 * 128 * 8 * 2;
+    static constexpr int STAT_FLOATS = 384;
     static constexpr int COL_FLOATS = 4 * NT;
-    static constexpr int ROW_INTS = 2 * 128;
+    static constexpr int ROW_INTS = 4 * 128;
     static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES +
                                       (TBUF_FLOATS + PART_FLOATS + STAT_FLOATS + COL_FLOATS + ROW_INTS) * 4 + 256 + 1024;
 };
@@ -268,10 +325,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
         }
     } else {
-        // ============================== epilogue (warps 2..5) ==============================
-        const int eq = warp & 3;                 // TMEM lane quarter this warp may read
-        const int etid = (warp - 2) * 32 + lane; // 0..127
-        float* tb = tbuf + (warp - 2) * 32 * 33;
+        // ============================== epilogue (warps 2..9) ==============================
+        // Every thread owns ONE accumulator row (TMEM lane) and walks 32-column chunks; two warps
+        // share each TMEM lane quarter and take alternating chunks.  All global traffic is
+        // per-row 16-byte vectors (no shared-memory transposes); GroupNorm statistics are per-row
+        // partial sums combined in a fixed order, so results are run-to-run deterministic.
+        const int eq = warp & 3;                 // TMEM lane quarter this warp may access
+        const int hf = (warp - 2) >> 2;          // 0/1: which half of the chunks
+        const int etid = threadIdx.x - 64;       // 0..255
+        const int mrow = eq * 32 + lane;
         const int act = p.act;
         const float inv_cnt = 1.0f / (float)(HJ * (GS ? GS : 1));
         int as = 0;
@@ -280,62 +342,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int r0 = (tile / P.tilesN) * S, n0 = (tile % P.tilesN) * NT;
             const int Sv = min(S, p.R - r0);
             const int Mv = Sv * HJ;
-            // per-tile tables (previous tile's readers are past the closing epi_bar)
-            for (int i = etid; i < NT; i += 128) {
+            for (int i = etid; i < NT; i += 256) {
                 scol[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
                 scol[NT + i] = p.gamma ? __ldg(p.gamma + n0 + i) : 0.f;
                 scol[2 * NT + i] = p.beta ? __ldg(p.beta + n0 + i) : 0.f;
                 scol[3 * NT + i] = p.bias2 ? __ldg(p.bias2 + n0 + i) : 0.f;
             }
-            {
-                const int m = etid;
-                if (m < Mv) {
-                    const int s = m / HJ;
-                    srow[m] = (r0 + s) * p.Hout + (m - s * HJ);
-                    srow[128 + m] = r0 + s;
-                } else {
-                    srow[m] = -1;
-                    srow[128 + m] = 0;
+            if (GS)
+                for (int g = 0; g < G; ++g) {
+                    spart[((hf * 128 + mrow) * G + g) * 2] = 0.f;
+                    spart[((hf * 128 + mrow) * G + g) * 2 + 1] = 0.f;
                 }
-            }
-            if (p.gn_bwd)
-                for (int i = etid; i < 4 * MAXSEG * G * 2; i += 128) spart[i] = 0.f;
+            // per-row constants
+            const bool valid = mrow < Mv;
+            const int s_loc = min(mrow / HJ, S - 1);
+            const int rg = valid ? r0 + s_loc : 0;                              // global sample (row of R)
+            const size_t orow = valid ? (size_t)(r0 + s_loc) * p.Hout + (mrow - s_loc * HJ) : 0;
+            const int slab0 = s_loc * G;
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
             epi_bar();
             const uint32_t tacc = tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)(as * C::ACC_COLS);
-            const int mrow = eq * 32 + lane;                 // the row this thread holds after tcgen05.ld
-            const int s_first = (eq * 32) / HJ;              // first sample touched by this warp's rows
+            const uint32_t tstash = tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)(NACC * C::ACC_COLS + as * NT);
             float v[32];
 
             if (GS && p.gn_fwd) {
                 // ---- pass 1: per-row sums of y = acc + bias and y^2 for every group
-                float s1[G], s2[G];
-#pragma unroll
-                for (int g = 0; g < G; ++g) s1[g] = s2[g] = 0.f;
-#pragma unroll
-                for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll 1
+                for (int ch = hf; ch < NCH; ch += 2) {
                     tmem_ld32(tacc + ch * 32, v);
+                    constexpr int GPC = (GS && GS < 32) ? 32 / GS : 1;   // groups per chunk
+                    float s1[GPC], s2[GPC];
+#pragma unroll
+                    for (int g = 0; g < GPC; ++g) s1[g] = s2[g] = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float x = v[j] + scol[ch * 32 + j];
-                        s1[(ch * 32 + j) / (GS ? GS : 1)] += x;
-                        s2[(ch * 32 + j) / (GS ? GS : 1)] += x * x;
+                        s1[GPC > 1 ? j / (32 / GPC) : 0] += x;
+                        s2[GPC > 1 ? j / (32 / GPC) : 0] += x * x;
                     }
-                }
+                    const int g0 = (ch * 32) / (GS ? GS : 1);
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    spart[(mrow * G + g) * 2] = s1[g];
-                    spart[(mrow * G + g) * 2 + 1] = s2[g];
+                    for (int g = 0; g < GPC; ++g) {
+                        float* d = spart + ((hf * 128 + mrow) * G + g0 + g) * 2;
+                        d[0] += s1[g];
+                        d[1] += s2[g];
+                    }
                 }
                 epi_bar();
                 if (etid < S * G) {
                     const int s = etid / G, g = etid - s * G;
                     float a = 0.f, b = 0.f;
-                    for (int j = 0; j < HJ; ++j) {
-                        a += spart[((s * HJ + j) * G + g) * 2];
-                        b += spart[((s * HJ + j) * G + g) * 2 + 1];
-                    }
+                    for (int h2 = 0; h2 < 2; ++h2)
+                        for (int j = 0; j < HJ; ++j) {
+                            a += spart[((h2 * 128 + s * HJ + j) * G + g) * 2];
+                            b += spart[((h2 * 128 + s * HJ + j) * G + g) * 2 + 1];
+                        }
                     const float mean = a * inv_cnt;
                     const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
                     const float rs = 1.0f / sqrtf(var + 1e-5f);
@@ -348,30 +410,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
             if (!(GS && p.gn_bwd)) {
                 // ---- forward (with or without GroupNorm) and plain backward: one output pass
-                const int srow_m = min(mrow / HJ, S - 1);
+                int tt = 0;
+                if (p.embT && valid) {
+                    const int64_t t64 = p.tidx[rg];
+                    tt = (int)(t64 < 0 ? 0 : (t64 > p.tmax ? p.tmax : t64));
+                }
+                const float* eT = p.embT ? p.embT + (size_t)tt * p.ldeT + p.eoff + n0 : nullptr;
+                const float* eR = (p.embR && valid && rg < p.n_cond) ? p.embR + (size_t)rg * p.ldeR + p.eoff + n0 : nullptr;
+                const float* idp = p.ident ? p.ident + orow * p.ldi + n0 : nullptr;
+                const float* adp = p.addend ? p.addend + orow * p.ldad + n0 : nullptr;
 #pragma unroll 1
-                for (int ch = 0; ch < NCH; ++ch) {
+                for (int ch = hf; ch < NCH; ch += 2) {
                     tmem_ld32(tacc + ch * 32, v);
                     if (GS && p.gn_fwd) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const int n = ch * 32 + j;
-                            const int sl = srow_m * G + n / (GS ? GS : 1);
-                            v[j] = (v[j] + scol[n] - sstat[sl]) * sstat[128 + sl];   // yhat
+                            const int sl = slab0 + (ch * 32 + j) / (GS ? GS : 1);
+                            v[j] = (v[j] + scol[ch * 32 + j] - sstat[sl]) * sstat[128 + sl];   // yhat
                         }
+                        if (valid) st_row32(p.yhat + orow * p.ldy + n0 + ch * 32, v);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = v[j];
-                        __syncwarp();
-                        for (int r = 0; r < 32; ++r) {
-                            const int orow = srow[eq * 32 + r];
-                            if (orow >= 0) p.yhat[(size_t)orow * p.ldy + n0 + ch * 32 + lane] = tb[r * 33 + lane];
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int n = ch * 32 + j;
-                            v[j] = act_fwd(scol[NT + n] * v[j] + scol[2 * NT + n], act);
-                        }
+                        for (int j = 0; j < 32; ++j)
+                            v[j] = act_fwd(scol[NT + ch * 32 + j] * v[j] + scol[2 * NT + ch * 32 + j], act);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += scol[ch * 32 + j];
@@ -382,105 +442,91 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += w[j] + scol[3 * NT + ch * 32 + j];
                     }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = v[j];
-                    __syncwarp();
-                    const int n = n0 + ch * 32 + lane;
-                    for (int r = 0; r < 32; ++r) {
-                        const int orow = srow[eq * 32 + r];
-                        if (orow < 0) continue;
-                        const int rg = srow[128 + eq * 32 + r];
-                        float x = tb[r * 33 + lane];
-                        if (p.embT) {
-                            int64_t tt = p.tidx[rg];
-                            tt = tt < 0 ? 0 : (tt > p.tmax ? p.tmax : tt);
-                            x += __ldg(p.embT + (size_t)tt * p.ldeT + p.eoff + n);
-                        }
-                        if (p.embR && rg < p.n_cond) x += __ldg(p.embR + (size_t)rg * p.ldeR + p.eoff + n);
-                        if (p.ident) x += __ldg(p.ident + (size_t)orow * p.ldi + n);
-                        if (p.addend) x += __ldg(p.addend + (size_t)orow * p.ldad + n);
-                        if (p.out) p.out[(size_t)orow * p.ldo + n] = x;
-                        if (p.out_hi) split_bf16(x, p.out_hi[(size_t)orow * p.ldo + n], p.out_lo[(size_t)orow * p.ldo + n]);
+                    if (eT) add_row32(eT + ch * 32, v);
+                    if (eR) add_row32(eR + ch * 32, v);
+                    if (idp) add_row32(idp + ch * 32, v);
+                    if (adp) add_row32(adp + ch * 32, v);
+                    if (valid) {
+                        const size_t o = orow * p.ldo + n0 + ch * 32;
+                        if (p.out) st_row32(p.out + o, v);
+                        if (p.out_hi) st_planes32(p.out_hi + o, p.out_lo + o, v);
                     }
-                    __syncwarp();
                 }
             } else {
-                // ---- backward with GroupNorm/activation backward, two passes
+                // ---- backward with GroupNorm/activation backward.
+                // pass 0: x = acc (+ident +addend) -> raw output; g_yhat = x*act'(z)*gamma is written
+                // back over the accumulator and yhat is stashed in spare TMEM columns, so pass 1
+                // (after the slab means are known) touches no global input again.
+                const float* idp = p.ident ? p.ident + orow * p.ldi + n0 : nullptr;
+                const float* adp = p.addend ? p.addend + orow * p.ldad + n0 : nullptr;
+                const float* yp = p.yhat + orow * p.ldy + n0;
 #pragma unroll 1
-                for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll 1
-                    for (int ch = 0; ch < NCH; ++ch) {
-                        tmem_ld32(tacc + ch * 32, v);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = v[j];
-                        __syncwarp();
-                        const int nl = ch * 32 + lane, n = n0 + nl;
-                        const int gl = nl / (GS ? GS : 1);
-                        const float gam = scol[NT + nl], bet = scol[2 * NT + nl];
-                        float q1 = 0.f, q2 = 0.f;
-                        int seg = 0;
-                        for (int r = 0; r < 32; ++r) {
-                            const int m = eq * 32 + r;
-                            const int orow = srow[m];
-                            float gyh = 0.f, y = 0.f;
-                            if (orow >= 0) {
-                                float x = tb[r * 33 + lane];
-                                if (p.ident) x += __ldg(p.ident + (size_t)orow * p.ldi + n);
-                                if (p.addend) x += __ldg(p.addend + (size_t)orow * p.ldad + n);
-                                if (pass == 0) {
-                                    if (p.out) p.out[(size_t)orow * p.ldo + n] = x;
-                                    if (p.out_hi) split_bf16(x, p.out_hi[(size_t)orow * p.ldo + n], p.out_lo[(size_t)orow * p.ldo + n]);
-                                }
-                                y = __ldg(p.yhat + (size_t)orow * p.ldy + n);
-                                gyh = x * act_bwd(gam * y + bet, act) * gam;
-                            }
-                            const int sm = m / HJ;   // sample of this row (warp uniform)
-                            if (pass == 0) {
-                                q1 += gyh;
-                                q2 += gyh * y;
-                                const bool last = (r == 31) || ((m + 1) / HJ != sm);
-                                if (last) {
-                                    const float t1 = group_reduce<GS>(q1), t2 = group_reduce<GS>(q2);
-                                    if ((lane & ((GS < 32 ? GS : 32) - 1)) == 0 && seg < MAXSEG) {
-                                        float* d = spart + (((warp - 2) * MAXSEG + seg) * G + gl) * 2;
-                                        d[0] += t1;
-                                        d[1] += t2;
-                                    }
-                                    q1 = q2 = 0.f;
-                                    ++seg;
-                                }
-                            } else if (orow >= 0) {
-                                const int sl = min(sm, S - 1) * G + gl;
-                                const float rs = __ldg(p.rstd + (size_t)srow[128 + m] * 8 + n0 / (GS ? GS : 1) + gl);
-                                const float gv = rs * (gyh - sstat[sl] - y * sstat[128 + sl]);
-                                p.gy[(size_t)orow * p.ldg + n] = gv;
-                                if (p.gy_hi) split_bf16(gv, p.gy_hi[(size_t)orow * p.ldg + n], p.gy_lo[(size_t)orow * p.ldg + n]);
-                            }
-                        }
-                        __syncwarp();
+                for (int ch = hf; ch < NCH; ch += 2) {
+                    tmem_ld32(tacc + ch * 32, v);
+                    if (idp) add_row32(idp + ch * 32, v);
+                    if (adp) add_row32(adp + ch * 32, v);
+                    if (valid) {
+                        const size_t o = orow * p.ldo + n0 + ch * 32;
+                        if (p.out) st_row32(p.out + o, v);
+                        if (p.out_hi) st_planes32(p.out_hi + o, p.out_lo + o, v);
                     }
-                    if (pass == 0) {
-                        epi_bar();
-                        if (etid < S * G) {
-                            // fixed-order combine of the per-warp segment partials of slab (s, g)
-                            const int s = etid / G, g = etid - s * G;
-                            float a = 0.f, b = 0.f;
-                            for (int w = 0; w < 4; ++w) {
-                                const int q = (w + 2) & 3;                  // TMEM quarter of epilogue warp w
-                                const int sg = s - (q * 32) / HJ;
-                                if (sg >= 0 && sg < MAXSEG && (q * 32) < Mv + HJ) {
-                                    a += spart[((w * MAXSEG + sg) * G + g) * 2];
-                                    b += spart[((w * MAXSEG + sg) * G + g) * 2 + 1];
-                                }
-                            }
-                            sstat[etid] = a * inv_cnt;
-                            sstat[128 + etid] = b * inv_cnt;
+                    float y[32];
+                    ld_row32(yp + ch * 32, y);
+                    constexpr int GPC = (GS && GS < 32) ? 32 / GS : 1;
+                    float q1[GPC], q2[GPC];
+#pragma unroll
+                    for (int g = 0; g < GPC; ++g) q1[g] = q2[g] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float gam = scol[NT + ch * 32 + j];
+                        const float gyh = valid ? v[j] * act_bwd(gam * y[j] + scol[2 * NT + ch * 32 + j], act) * gam : 0.f;
+                        if (!valid) y[j] = 0.f;
+                        v[j] = gyh;
+                        q1[GPC > 1 ? j / (32 / GPC) : 0] += gyh;
+                        q2[GPC > 1 ? j / (32 / GPC) : 0] += gyh * y[j];
+                    }
+                    tmem_st32(tacc + ch * 32, v);
+                    tmem_st32(tstash + ch * 32, y);
+                    const int g0 = (ch * 32) / (GS ? GS : 1);
+#pragma unroll
+                    for (int g = 0; g < GPC; ++g) {
+                        float* d = spart + ((hf * 128 + mrow) * G + g0 + g) * 2;
+                        d[0] += q1[g];
+                        d[1] += q2[g];
+                    }
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                epi_bar();
+                if (etid < S * G) {
+                    const int s = etid / G, g = etid - s * G;
+                    float a = 0.f, b = 0.f;
+                    for (int h2 = 0; h2 < 2; ++h2)
+                        for (int j = 0; j < HJ; ++j) {
+                            a += spart[((h2 * 128 + s * HJ + j) * G + g) * 2];
+                            b += spart[((h2 * 128 + s * HJ + j) * G + g) * 2 + 1];
                         }
-                        epi_bar();
+                    sstat[etid] = a * inv_cnt;
+                    sstat[128 + etid] = b * inv_cnt;
+                    sstat[256 + etid] = (s < Sv) ? __ldg(p.rstd + (size_t)(r0 + s) * 8 + n0 / (GS ? GS : 1) + g) : 0.f;
+                }
+                epi_bar();
+#pragma unroll 1
+                for (int ch = hf; ch < NCH; ch += 2) {
+                    float y[32];
+                    tmem_ld32(tacc + ch * 32, v);
+                    tmem_ld32(tstash + ch * 32, y);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int sl = slab0 + (ch * 32 + j) / (GS ? GS : 1);
+                        v[j] = sstat[256 + sl] * (v[j] - sstat[sl] - y[j] * sstat[128 + sl]);
+                    }
+                    if (valid) {
+                        const size_t o = orow * p.ldg + n0 + ch * 32;
+                        st_row32(p.gy + o, v);
+                        if (p.gy_hi) st_planes32(p.gy_hi + o, p.gy_lo + o, v);
                     }
                 }
             }
-            (void)s_first;
             // release the accumulator stage
             tc_fence_before();
             epi_bar();

@@ -9,6 +9,7 @@
 //   PolicyCompose.*_sample_loop              diffuser/guides/policies_compose.py:270-350
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -32,7 +33,7 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n); }
 
 // ---- optional per-launch CUDA-event profiler for the conv kernels (bench.py roofline)
-struct ProfRec { cudaEvent_t a, b; double flops; int cls; };
+struct ProfRec { cudaEvent_t a, b; double flops; int cls; int R, Hout, N, C1, C2, taps, flags; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
@@ -56,7 +57,9 @@ static int prof_launch_conv(const ConvP& p, cudaStream_t st, int cls, int (*fn)(
     PMP_CUDA_OK(cudaEventRecord(ev.first, st));
     int rc = fn(p, st);
     PMP_CUDA_OK(cudaEventRecord(ev.second, st));
-    g_prof.push_back(ProfRec{ev.first, ev.second, conv_flops(p), cls});
+    g_prof.push_back(ProfRec{ev.first, ev.second, conv_flops(p), cls, p.R, p.Hout, p.N, p.C1, p.A2 ? p.C2 : 0,
+                             p.ntaps[0] + (p.nphase > 1 ? p.ntaps[1] : 0),
+                             p.gn_fwd | (p.gn_bwd << 1) | ((p.ident != nullptr) << 2) | ((p.istride > 1) << 3) | ((p.ostride > 1) << 4)});
     return rc;
 }
 
@@ -1247,14 +1250,21 @@ int pmp_profile_enable(int on) {
 int pmp_profile_read(int n_classes, double* ms, double* flops, int64_t* launches) {
     PMP_REQUIRE(ms && flops && launches && n_classes >= 1, "bad argument");
     for (int i = 0; i < n_classes; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
+    FILE* dump = nullptr;
+    if (const char* path = getenv("PMP_PROFILE_DUMP")) dump = fopen(path, "w");
+    if (dump) fprintf(dump, "cls,R,Hout,N,C1,C2,taps,flags,ms,algo_tflops\n");
     for (auto& r : g_prof) {
         PMP_CUDA_OK(cudaEventSynchronize(r.b));
         float t = 0;
         PMP_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+        if (dump)
+            fprintf(dump, "%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.1f\n", r.cls, r.R, r.Hout, r.N, r.C1, r.C2, r.taps, r.flags, t,
+                    r.flops / (t * 1e9));
         if (r.cls < n_classes) { ms[r.cls] += t; flops[r.cls] += r.flops; launches[r.cls] += 1; }
         g_prof_pool.push_back(std::make_pair(r.a, r.b));
     }
     g_prof.clear();
+    if (dump) fclose(dump);
     return 0;
 }
 

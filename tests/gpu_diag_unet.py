@@ -70,12 +70,18 @@ def main(fams):
         eng.eps(xt, tt, wt, n_cond=Bt)
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        pmp_b200.profile_enable(True)
         e0.record()
         for _ in range(3):
             eng.eps(xt, tt, wt, n_cond=Bt)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
+        prof = pmp_b200.profile_read(2)
+        pmp_b200.profile_enable(False)
         print("  eps-eval %d rows: %.2f ms  -> %.1f us/row" % (2 * Bt, ms, 1e3 * ms / (2 * Bt)))
+        for cls, (pms, pfl, pn) in zip(("simt", "tc"), prof):
+            if pn:
+                print("    conv_%s: %d launches, %.2f ms/eval, %.1f algorithmic TFLOP/s" % (cls, pn // 3, pms / 3, pfl / pms / 1e9))
         del eng
 
 
