@@ -38,7 +38,9 @@ struct TcP {
     ConvP e;
     int tilesM, tilesN, ntiles;
     int kpt;        // K blocks per tap = C1 / 64
-    int nkb1, nkb2; // K blocks of slab 1 / slab 2
+    int nkb2;       // K blocks of slab 2 (slab 1: ntaps[phase] * kpt)
+    int nphase;     // 2 for transposed (stride-2 scatter) convs: output rows 2j+phase
+    int mode4d;     // 1: stride-2 gather, A maps are 4-D (C, parity, H/2, R)
     alignas(64) CUtensorMap mA1h;
     alignas(64) CUtensorMap mA1l;
     alignas(64) CUtensorMap mA2h;
@@ -80,6 +82,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -263,20 +271,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             int s = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-                const int r0 = (tile / P.tilesN) * S, n0 = (tile % P.tilesN) * NT;
-                for (int kb = 0; kb < P.nkb1 + P.nkb2; ++kb) {
+                const int op = tile % P.nphase, t2 = tile / P.nphase;
+                const int r0 = (t2 / P.tilesN) * S, n0 = (t2 % P.tilesN) * NT;
+                const int nkb1 = p.ntaps[op] * P.kpt;
+                for (int kb = 0; kb < nkb1 + P.nkb2; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * C::STAGE_BYTES;
                     mbar_expect_tx(&full[s], 2 * bytesA + 2 * C::B_TILE_BYTES);
-                    if (kb < P.nkb1) {
+                    if (kb < nkb1) {
                         const int tap = kb / P.kpt, c0 = (kb - tap * P.kpt) * BK;
-                        const int sh = p.tap_shift[0][tap], wr = p.tap_k[0][tap] * N + n0;
-                        tma_load_3d(st, &P.mA1h, &full[s], c0, sh, r0);
-                        tma_load_3d(st + A_TILE_BYTES, &P.mA1l, &full[s], c0, sh, r0);
+                        const int sh = p.tap_shift[op][tap], wr = p.tap_k[op][tap] * N + n0;
+                        if (P.mode4d) {
+                            // input row 2j + sh = parity (sh & 1) of pair j + floor(sh / 2)
+                            const int par = sh & 1, js = (sh - par) >> 1;
+                            tma_load_4d(st, &P.mA1h, &full[s], c0, par, js, r0);
+                            tma_load_4d(st + A_TILE_BYTES, &P.mA1l, &full[s], c0, par, js, r0);
+                        } else {
+                            tma_load_3d(st, &P.mA1h, &full[s], c0, sh, r0);
+                            tma_load_3d(st + A_TILE_BYTES, &P.mA1l, &full[s], c0, sh, r0);
+                        }
                         tma_load_2d(st + 2 * A_TILE_BYTES, &P.mW1h, &full[s], c0, wr);
                         tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &P.mW1l, &full[s], c0, wr);
                     } else {
-                        const int c0 = (kb - P.nkb1) * BK;
+                        const int c0 = (kb - nkb1) * BK;
                         tma_load_3d(st, &P.mA2h, &full[s], c0, 0, r0);
                         tma_load_3d(st + A_TILE_BYTES, &P.mA2l, &full[s], c0, 0, r0);
                         tma_load_2d(st + 2 * A_TILE_BYTES, &P.mW2h, &full[s], c0, n0);
@@ -299,13 +316,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const uint32_t d1 = tmem_base + (uint32_t)(as * C::ACC_COLS);
                 const uint32_t d2 = ACC2 ? d1 + NT : d1;
                 uint32_t acc1 = 0, acc2 = ACC2 ? 0u : 1u;
-                for (int kb = 0; kb < P.nkb1 + P.nkb2; ++kb) {
+                const int nkb1 = p.ntaps[tile % P.nphase] * P.kpt;
+                for (int kb = 0; kb < nkb1 + P.nkb2; ++kb) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
                     const uint64_t ah = make_desc(sa), al = make_desc(sa + A_TILE_BYTES);
                     const uint64_t bh = make_desc(sa + 2 * A_TILE_BYTES), bl = make_desc(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES);
-                    const bool slab2 = kb >= P.nkb1;
+                    const bool slab2 = kb >= nkb1;
                     const uint32_t d = slab2 ? d2 : d1;
                     uint32_t accum = slab2 ? (ACC2 ? acc2 : 1u) : acc1;
 #pragma unroll
@@ -339,7 +357,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         int as = 0;
         uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-            const int r0 = (tile / P.tilesN) * S, n0 = (tile % P.tilesN) * NT;
+            const int op = tile % P.nphase, t2 = tile / P.nphase;
+            const int r0 = (t2 / P.tilesN) * S, n0 = (t2 % P.tilesN) * NT;
             const int Sv = min(S, p.R - r0);
             const int Mv = Sv * HJ;
             for (int i = etid; i < NT; i += 256) {
@@ -357,7 +376,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const bool valid = mrow < Mv;
             const int s_loc = min(mrow / HJ, S - 1);
             const int rg = valid ? r0 + s_loc : 0;                              // global sample (row of R)
-            const size_t orow = valid ? (size_t)(r0 + s_loc) * p.Hout + (mrow - s_loc * HJ) : 0;
+            const size_t orow = valid ? (size_t)(r0 + s_loc) * p.Hout + (size_t)((mrow - s_loc * HJ) * p.ostride + op) : 0;
             const int slab0 = s_loc * G;
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
@@ -583,6 +602,24 @@ int act_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int H, int R, in
     g_maps[key] = *out;
     return 0;
 }
+// stride-2 gather: rows (2j + parity) -> 4-D map (C, parity, H/2, R), box (64, 1, HJ, S)
+int act_map4(CUtensorMap* out, const __nv_bfloat16* base, int C, int Hin, int R, int ld, int S, int HJ) {
+    MapKey key(base, C, Hin, R, ld, S * 1000 + HJ, 4);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+    EncodeFn enc = get_encode();
+    PMP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[4] = {(cuuint64_t)C, 2, (cuuint64_t)(Hin / 2), (cuuint64_t)R};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 4, (cuuint64_t)ld * 2 * (cuuint64_t)Hin};
+    cuuint32_t box[4] = {(cuuint32_t)BK, 1, (cuuint32_t)HJ, (cuuint32_t)S};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(strided activation C=%d H=%d R=%d ld=%d) failed: %d", C, Hin, R, ld, (int)r);
+    g_maps[key] = *out;
+    return 0;
+}
 // weight plane [taps*N][C] BF16 -> 2-D map (C, taps*N), box (64, NT)
 int w_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int rows, int NT) {
     MapKey key(base, C, rows, NT, 0, 0, 2);
@@ -640,7 +677,13 @@ int pick_nt(const ConvP& p) {
 }  // namespace
 
 bool conv_tc_eligible(const ConvP& p) {
-    if (p.nphase != 1 || p.istride != 1 || p.ostride != 1) return false;           // stride-1 convs only
+    const bool s1 = p.nphase == 1 && p.istride == 1 && p.ostride == 1;             // conv k5 / 1x1
+    const bool s2 = p.nphase == 1 && p.istride == 2 && p.ostride == 1;             // stride-2 gather
+    const bool t2 = p.nphase == 2 && p.istride == 1 && p.ostride == 2;             // stride-2 scatter (2 phases)
+    if (!s1 && !s2 && !t2) return false;
+    if (!s1 && p.A2) return false;
+    if (t2 && (p.gn_fwd || p.gn_bwd)) return false;
+    if (s2 && (p.Hin & 1)) return false;
     if (!p.A1_hi || !p.A1_lo || !p.W1_hi || !p.W1_lo) return false;
     if (p.C1 % BK != 0 || (p.lda1 % 8) != 0) return false;
     if (p.A2 && (!p.A2_hi || !p.A2_lo || !p.W2_hi || !p.W2_lo || p.C2 % BK != 0 || (p.lda2 % 8) != 0)) return false;
@@ -662,15 +705,22 @@ int launch_conv_tc(const ConvP& p, cudaStream_t st) {
     P.e.S = S;
     P.tilesM = (p.R + S - 1) / S;
     P.tilesN = p.N / NT;
-    P.ntiles = P.tilesM * P.tilesN;
+    P.nphase = p.nphase;
+    P.mode4d = p.istride == 2 ? 1 : 0;
+    P.ntiles = P.tilesM * P.tilesN * P.nphase;
     P.kpt = p.C1 / BK;
-    P.nkb1 = p.ntaps[0] * P.kpt;
     P.nkb2 = p.A2 ? p.C2 / BK : 0;
     int rc;
-    if ((rc = act_map(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S))) return rc;
-    if ((rc = act_map(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S))) return rc;
+    if (P.mode4d) {
+        if ((rc = act_map4(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S, p.HJ))) return rc;
+        if ((rc = act_map4(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S, p.HJ))) return rc;
+    } else {
+        if ((rc = act_map(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S))) return rc;
+        if ((rc = act_map(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S))) return rc;
+    }
     int maxk = 0;
-    for (int t = 0; t < p.ntaps[0]; ++t) maxk = p.tap_k[0][t] > maxk ? p.tap_k[0][t] : maxk;
+    for (int ph = 0; ph < p.nphase; ++ph)
+        for (int t = 0; t < p.ntaps[ph]; ++t) maxk = p.tap_k[ph][t] > maxk ? p.tap_k[ph][t] : maxk;
     if ((rc = w_map(&P.mW1h, p.W1_hi, p.C1, (maxk + 1) * p.N, NT))) return rc;
     if ((rc = w_map(&P.mW1l, p.W1_lo, p.C1, (maxk + 1) * p.N, NT))) return rc;
     if (p.A2) {

@@ -107,6 +107,7 @@ struct ResB {
 struct PlainConv {  // down / up sampling
     int C = 0, KS = 0;
     size_t Wf = 0, Wb = 0, bias = 0;
+    TcW tcf, tcb;
     bool present = false;
 };
 
@@ -375,8 +376,8 @@ static int finalize_model(pmp_model* m) {
         PlainConv& pc = m->downc[L];
         pc.present = true; pc.C = m->dims[L + 1]; pc.KS = 3;
         std::vector<float> t;
-        conv_fwd_layout(*w, t); pc.Wf = pk.add(t);
-        conv_bwd_layout(*w, t, false); pc.Wb = pk.add(t);
+        conv_fwd_layout(*w, t); pc.Wf = pk.add(t); pc.tcf = pk16.add(t, 3, pc.C, pc.C);
+        conv_bwd_layout(*w, t, false); pc.Wb = pk.add(t); pc.tcb = pk16.add(t, 3, pc.C, pc.C);
         pc.bias = pk.add(b->v);
     }
     for (int ind = 0; ind < m->nl - 1; ++ind) {
@@ -391,6 +392,7 @@ static int finalize_model(pmp_model* m) {
         std::vector<float> f, bw;
         convT_layouts(*w, f, bw);
         pc.Wf = pk.add(f); pc.Wb = pk.add(bw);
+        pc.tcf = pk16.add(f, 4, C, C); pc.tcb = pk16.add(bw, 4, C, C);
         pc.bias = pk.add(b->v);
     }
     if ((rc = pack_cb(m, pk, pk16, "final_conv.0.", m->finalcb))) return rc;
@@ -795,8 +797,9 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
         if (m->has_down(L)) {
             ActP d = new_act(c, C, Hl[L] / 2);
             ConvP p = geom_s2(R, Hl[L] / 2, 3);
-            set_A1(p, b.p, nullptr, nullptr, b.ld, C);
-            p.W1 = m->A(m->downc[L].Wf); p.N = C; p.bias = m->A(m->downc[L].bias);
+            set_A1(p, b.p, b.hi, b.lo, b.ld, C);
+            set_W1(m, p, m->downc[L].Wf, m->downc[L].tcf);
+            p.N = C; p.bias = m->A(m->downc[L].bias);
             p.out = d.p; p.ldo = d.ld; p.out_hi = d.hi; p.out_lo = d.lo;
             c.conv(p);
             cur = d;
@@ -827,8 +830,9 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
             ActP o = !last ? view_act(cat[Ls - 1], 0, Co) : new_act(c, Co, 2 * h);
             o.Hl = 2 * h; o.blk = -1;
             ConvP p = geom_t2(R, h, 4);
-            set_A1(p, b.p, nullptr, nullptr, b.ld, Co);
-            p.W1 = m->A(m->upc[ind].Wf); p.N = Co; p.bias = m->A(m->upc[ind].bias);
+            set_A1(p, b.p, b.hi, b.lo, b.ld, Co);
+            set_W1(m, p, m->upc[ind].Wf, m->upc[ind].tcf);
+            p.N = Co; p.bias = m->A(m->upc[ind].bias);
             p.out = o.p; p.ldo = o.ld; p.out_hi = o.hi; p.out_lo = o.lo;
             c.conv(p);
             cur = o;
@@ -899,8 +903,9 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
         if (m->has_up(ind)) {
             // Upsample1d backward: strided conv with the same weight (App. G item 6)
             ConvP p = geom_s2(R, h, 4);
-            set_A1(p, g.raw, nullptr, nullptr, g.ldr, Co);
-            p.W1 = m->A(m->upc[ind].Wb); p.N = Co;
+            set_A1(p, g.raw, g.raw_hi, g.raw_lo, g.ldr, Co);
+            set_W1(m, p, m->upc[ind].Wb, m->upc[ind].tcb);
+            p.N = Co;
             g = emit_grad(c, p, up_b[ind], nullptr, 0, nullptr, 0, true);
         }
         g = res_bwd(c, bmid + 3 + 2 * ind, g, up_a[ind], nullptr, 0, nullptr, 0);
@@ -938,8 +943,9 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
             // Downsample1d backward: transposed conv, output_padding 1 (App. G item 5)
             const int C = m->dims[L];
             ConvP p = geom_t2(R, Hl[L], 3);
-            set_A1(p, g.raw, nullptr, nullptr, g.ldr, C);
-            p.W1 = m->A(m->downc[L - 1].Wb); p.N = C;
+            set_A1(p, g.raw, g.raw_hi, g.raw_lo, g.ldr, C);
+            set_W1(m, p, m->downc[L - 1].Wb, m->downc[L - 1].tcb);
+            p.N = C;
             const bool sk = L - 1 >= 1;
             g = emit_grad(c, p, lvl_b[L - 1], sk ? skipg[L - 1] : nullptr, sk ? skipld[L - 1] : 0, nullptr, 0, false);
         }
@@ -986,7 +992,16 @@ static int eps_rows(pmp_model* m, const float* x, const int64_t* t, const float*
                     float* eps, float* energy, float* u, cudaStream_t st) {
     const int D = m->arch.transition_dim;
     PMP_REQUIRE(H % 4 == 0 && H >= 32 && H <= 128, "horizon %d unsupported (multiple of 4 in [32,128])", H);
-    const int chunk = m->row_chunk;
+    // rows per pass: round the requested chunk down to a whole number of 148-tile waves of the deepest
+    // (most expensive) level, where one tile holds S = 128/H_deep samples and N is split in 4 tiles
+    int chunk = m->row_chunk;
+    {
+        int hd = H;
+        for (int L = 1; L < m->nl; ++L)
+            if (m->has_down(L - 1)) hd /= 2;
+        const int unit = (128 / hd) * 37;
+        if (chunk > unit) chunk = (chunk / unit) * unit;
+    }
     int rc;
     const int Rc_max = R < chunk ? R : chunk;
     const size_t need = workspace_floats(m, Rc_max, H);
