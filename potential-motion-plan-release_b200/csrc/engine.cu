@@ -987,21 +987,26 @@ static size_t workspace_floats(pmp_model* m, int R, int H) {
     return c.used;
 }
 
+// rows per pass: the requested chunk rounded down to a whole number of 148-tile waves of the deepest
+// (most expensive) level, where one tile holds S = 128/H_deep samples and N is split in 4 tiles
+static int aligned_chunk(const pmp_model* m, int H) {
+    int chunk = m->row_chunk;
+    int hd = H;
+    for (int L = 1; L < m->nl; ++L)
+        if (m->has_down(L - 1)) hd /= 2;
+    if (hd < 1) hd = 1;
+    int unit = (128 / hd) * 37;
+    if (unit & 1) unit *= 2;   // keep the CFG pair (2 rows per plan) inside one chunk
+    if (chunk > unit) chunk = (chunk / unit) * unit;
+    return chunk;
+}
+
 // eps for R rows given prepared wall tables (rows < n_cond conditional)
 static int eps_rows(pmp_model* m, const float* x, const int64_t* t, const float* wall_tab, int n_cond, int R, int H,
                     float* eps, float* energy, float* u, cudaStream_t st) {
     const int D = m->arch.transition_dim;
     PMP_REQUIRE(H % 4 == 0 && H >= 32 && H <= 128, "horizon %d unsupported (multiple of 4 in [32,128])", H);
-    // rows per pass: round the requested chunk down to a whole number of 148-tile waves of the deepest
-    // (most expensive) level, where one tile holds S = 128/H_deep samples and N is split in 4 tiles
-    int chunk = m->row_chunk;
-    {
-        int hd = H;
-        for (int L = 1; L < m->nl; ++L)
-            if (m->has_down(L - 1)) hd /= 2;
-        const int unit = (128 / hd) * 37;
-        if (chunk > unit) chunk = (chunk / unit) * unit;
-    }
+    const int chunk = aligned_chunk(m, H);
     int rc;
     const int Rc_max = R < chunk ? R : chunk;
     const size_t need = workspace_floats(m, Rc_max, H);
@@ -1196,9 +1201,9 @@ int pmp_sample(const pmp_sample_args* a, void* stream) {
     }
     PMP_CUDA_OK(cudaSetDevice(a->models[0]->device));
     // plans per pass: the CFG pair doubles the rows
-    int chunk = a->models[0]->row_chunk;
+    int chunk = aligned_chunk(a->models[0], H);
     for (int k = 1; k < K; ++k)
-        if (a->models[k]->row_chunk < chunk) chunk = a->models[k]->row_chunk;
+        if (aligned_chunk(a->models[k], H) < chunk) chunk = aligned_chunk(a->models[k], H);
     int Bc = chunk / 2;
     if (Bc < 1) Bc = 1;
     if (Bc > B) Bc = B;
