@@ -155,7 +155,7 @@ def main():
     import torch.distributed as dist
     import pmp_b200
     from pmp_b200 import shard
-    from oracle import synth, unet_ref  # inputs / weights generators only (not on the measured path)
+    from pmp_b200 import workloads as synth   # synthetic inputs / weights (product side; oracle/ is not used here)
     from diffuser.models import TemporalUnet_WCond, GaussianDiffusionPB
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -171,7 +171,7 @@ def main():
     a = synth.arch(FAMILY)
     H, D = a["horizon"], a["obs_dim"]
     model = TemporalUnet_WCond(**a["unet"])
-    model.load_state_dict(unet_ref.synth_weights(a["unet"], 1))
+    model.load_state_dict(synth.synth_state_dict(model.state_dict(), 1))
     diffusion = GaussianDiffusionPB(model, **a["diffusion"]).to(dev).eval()
     diffusion.horizon = H
     eng = diffusion.model.engine(T_DIFF)

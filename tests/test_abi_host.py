@@ -133,3 +133,17 @@ def test_normalizer_matches_oracle():
     assert np.array_equal(n.unnormalize(x), synth.unnormalize(x, KUKA7D_MIN, KUKA7D_MAX))
     q = np.random.default_rng(1).uniform(KUKA7D_MIN, KUKA7D_MAX, (4, 7)).astype(np.float32)
     assert np.array_equal(n.normalize(q), synth.normalize(q, KUKA7D_MIN, KUKA7D_MAX))
+
+
+def test_workloads_match_oracle():
+    """bench.py draws its synthetic inputs from the product-side copy of the generators"""
+    from pmp_b200 import workloads
+    for fam in synth.FAMILIES:
+        assert workloads.arch(fam) == synth.arch(fam)
+        a, b = workloads.make_problems(fam, 7, 5), synth.make_problems(fam, 7, 5)
+        for k in a:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (fam, k)
+    a = synth.arch("m2d")
+    sd1 = unet_ref.synth_weights(a["unet"], 3)
+    sd2 = workloads.synth_state_dict({k: torch.empty(s) for k, s in unet_ref.param_shapes(a["unet"]).items()}, 3)
+    assert synth.state_dict_digest(sd1) == workloads.state_dict_digest(sd2)
