@@ -202,6 +202,10 @@ uint64_t pmp_launch_count(void);
  * launch counts per class, and clears the records. */
 int pmp_profile_enable(int on);
 int pmp_profile_read(int n_classes, double *ms, double *flops, int64_t *launches);
+/* debug: cumulative clock64() role timers of conv_tc_kernel (enabled by env PMP_TC_TIMERS=1):
+ * out8 = {mma_wait_tma, mma_wait_acc, mma_total, epi_wait_acc, epi_busy, tma_wait_stage, tiles, 0};
+ * returns 1 when the timers are disabled */
+int pmp_debug_counters(double *out8, int reset);
 /* debug: copy an internal activation of the last pmp_unet_eps call (first row chunk) to the
  * host; name e.g. "yhat:downs.0.0.blocks.0." ; returns element count or <0 */
 int64_t pmp_debug_fetch(pmp_model *m, const char *name, float *host_out, int64_t capacity);

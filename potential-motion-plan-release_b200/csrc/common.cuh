@@ -125,6 +125,9 @@ int launch_conv_simt(const ConvP& p, cudaStream_t st);
 // tcgen05 core; returns 1 (and launches nothing) when the op does not fit it
 int launch_conv_tc(const ConvP& p, cudaStream_t st);
 bool conv_tc_eligible(const ConvP& p);
+// operand-reuse main loop (conv_tc2.cu): stride-1 convs without a separate second accumulator
+int launch_conv_tc2(const ConvP& p, cudaStream_t st);
+bool conv_tc2_eligible(const ConvP& p);
 int launch_gn_bwd(const float* g, int ldgi, const float* yhat, int ldy, const float* rstd,
                   const float* gamma, const float* beta, int act, float* gy, int ldg,
                   __nv_bfloat16* gy_hi, __nv_bfloat16* gy_lo, int R, int Hl, int C, cudaStream_t st);

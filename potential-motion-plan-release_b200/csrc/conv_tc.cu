@@ -22,17 +22,24 @@
 #include <map>
 #include <tuple>
 
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace pmp {
 namespace {
+using namespace tc;
 
 constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int BK = 64;                      // channels per K block = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = 128 * BK * 2;  // 16 KB per BF16 plane
 constexpr int MAXSEG = 5;                   // samples touched by 32 consecutive rows (H >= 8)
+
+}  // namespace
+unsigned long long* tc_timer_buffer();
+namespace {
 
 struct TcP {
     ConvP e;
@@ -41,6 +48,7 @@ struct TcP {
     int nkb2;       // K blocks of slab 2 (slab 1: ntaps[phase] * kpt)
     int nphase;     // 2 for transposed (stride-2 scatter) convs: output rows 2j+phase
     int mode4d;     // 1: stride-2 gather, A maps are 4-D (C, parity, H/2, R)
+    unsigned long long* ctr;   // optional role timers (PMP_TC_TIMERS=1): see pmp_debug_counters
     alignas(64) CUtensorMap mA1h;
     alignas(64) CUtensorMap mA1l;
     alignas(64) CUtensorMap mA2h;
@@ -50,159 +58,6 @@ struct TcP {
     alignas(64) CUtensorMap mW2h;
     alignas(64) CUtensorMap mW2l;
 };
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, BF16 inputs, FP32 accumulate, M=128
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-// K-major, 128-byte swizzle, rows of 64 BF16: 8-row groups 1024 B apart (SBO = 64 x 16 B), LBO = 1
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
-        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
-        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
-        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
-        "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])),
-        "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])),
-        "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
-        "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])),
-        "r"(__float_as_uint(v[31]))
-        : "memory");
-}
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// per-row 128-byte segment helpers (every thread handles its own row: 8 x 16-byte vectors)
-__device__ __forceinline__ void ld_row32(const float* __restrict__ p, float (&v)[32]) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
-        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-    }
-}
-__device__ __forceinline__ void add_row32(const float* __restrict__ p, float (&v)[32]) {
-    float4 t[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t[i] = __ldg(reinterpret_cast<const float4*>(p) + i);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        v[4 * i] += t[i].x; v[4 * i + 1] += t[i].y; v[4 * i + 2] += t[i].z; v[4 * i + 3] += t[i].w;
-    }
-}
-__device__ __forceinline__ void st_row32(float* __restrict__ p, const float (&v)[32]) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
-__device__ __forceinline__ void st_planes32(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                            const float (&v)[32]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v[8 * i + 2 * k], h0, l0);
-            split_bf16(v[8 * i + 2 * k + 1], h1, l1);
-            h[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            l[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        }
-        reinterpret_cast<uint4*>(hi)[i] = make_uint4(h[0], h[1], h[2], h[3]);
-        reinterpret_cast<uint4*>(lo)[i] = make_uint4(l[0], l[1], l[2], l[3]);
-    }
-}
-
-template <int GS>
-__device__ __forceinline__ float group_reduce(float v) {
-    // sum over the lanes of one GroupNorm group inside a 32-column chunk
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    if (GS >= 16) v += __shfl_xor_sync(0xffffffffu, v, 8);
-    if (GS >= 32) v += __shfl_xor_sync(0xffffffffu, v, 16);
-    return v;
-}
 
 template <int NT, int GS, bool ACC2>
 struct Cfg {
@@ -231,7 +86,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const ConvP& p = P.e;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
     float* tbuf = reinterpret_cast<float*>(smem + NSTAGE * C::STAGE_BYTES);
     float* spart = tbuf + C::TBUF_FLOATS;
     float* sstat = spart + C::PART_FLOATS;
@@ -275,7 +130,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int r0 = (t2 / P.tilesN) * S, n0 = (t2 % P.tilesN) * NT;
                 const int nkb1 = p.ntaps[op] * P.kpt;
                 for (int kb = 0; kb < nkb1 + P.nkb2; ++kb) {
+                    const long long tw0 = P.ctr ? clock64() : 0;
                     mbar_wait(&empty[s], ph ^ 1);
+                    if (P.ctr) atomicAdd(P.ctr + 5, (unsigned long long)(clock64() - tw0));
                     uint8_t* st = smem + s * C::STAGE_BYTES;
                     mbar_expect_tx(&full[s], 2 * bytesA + 2 * C::B_TILE_BYTES);
                     if (kb < nkb1) {
@@ -310,15 +167,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
+            const long long tm0 = P.ctr ? clock64() : 0;
             for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+                const long long te0 = P.ctr ? clock64() : 0;
                 mbar_wait(&tempty[as], aph ^ 1);
+                if (P.ctr) atomicAdd(P.ctr + 1, (unsigned long long)(clock64() - te0));
                 tc_fence_after();
                 const uint32_t d1 = tmem_base + (uint32_t)(as * C::ACC_COLS);
                 const uint32_t d2 = ACC2 ? d1 + NT : d1;
                 uint32_t acc1 = 0, acc2 = ACC2 ? 0u : 1u;
                 const int nkb1 = p.ntaps[tile % P.nphase] * P.kpt;
                 for (int kb = 0; kb < nkb1 + P.nkb2; ++kb) {
+                    const long long tf0 = P.ctr ? clock64() : 0;
                     mbar_wait(&full[s], ph);
+                    if (P.ctr) atomicAdd(P.ctr + 0, (unsigned long long)(clock64() - tf0));
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
                     const uint64_t ah = make_desc(sa), al = make_desc(sa + A_TILE_BYTES);
@@ -341,6 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 tc_commit(&tfull[as]);      // accumulator complete
                 if (++as == NACC) { as = 0; aph ^= 1; }
             }
+            if (P.ctr) atomicAdd(P.ctr + 2, (unsigned long long)(clock64() - tm0));
         }
     } else {
         // ============================== epilogue (warps 2..9) ==============================
@@ -378,7 +241,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int rg = valid ? r0 + s_loc : 0;                              // global sample (row of R)
             const size_t orow = valid ? (size_t)(r0 + s_loc) * p.Hout + (size_t)((mrow - s_loc * HJ) * p.ostride + op) : 0;
             const int slab0 = s_loc * G;
+            const long long tq0 = (P.ctr && etid == 0) ? clock64() : 0;
             mbar_wait(&tfull[as], aph);
+            const long long tq1 = (P.ctr && etid == 0) ? clock64() : 0;
             tc_fence_after();
             epi_bar();
             const uint32_t tacc = tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)(as * C::ACC_COLS);
@@ -394,9 +259,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     float s1[GPC], s2[GPC];
 #pragma unroll
                     for (int g = 0; g < GPC; ++g) s1[g] = s2[g] = 0.f;
+                    add_lds32(scol + ch * 32, v);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float x = v[j] + scol[ch * 32 + j];
+                        const float x = v[j];
                         s1[GPC > 1 ? j / (32 / GPC) : 0] += x;
                         s2[GPC > 1 ? j / (32 / GPC) : 0] += x * x;
                     }
@@ -441,25 +307,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll 1
                 for (int ch = hf; ch < NCH; ch += 2) {
                     tmem_ld32(tacc + ch * 32, v);
+                    add_lds32(scol + ch * 32, v);   // + bias
                     if (GS && p.gn_fwd) {
+                        constexpr int GPC2 = (GS && GS < 32) ? 32 / GS : 1;
+                        float mu[GPC2], rsd[GPC2];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int sl = slab0 + (ch * 32 + j) / (GS ? GS : 1);
-                            v[j] = (v[j] + scol[ch * 32 + j] - sstat[sl]) * sstat[128 + sl];   // yhat
+                        for (int g = 0; g < GPC2; ++g) {
+                            const int sl = slab0 + (ch * 32) / (GS ? GS : 1) + g;
+                            mu[g] = sstat[sl];
+                            rsd[g] = sstat[128 + sl];
                         }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            v[j] = (v[j] - mu[GPC2 > 1 ? j / (32 / GPC2) : 0]) * rsd[GPC2 > 1 ? j / (32 / GPC2) : 0];   // yhat
                         if (valid) st_row32(p.yhat + orow * p.ldy + n0 + ch * 32, v);
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             v[j] = act_fwd(scol[NT + ch * 32 + j] * v[j] + scol[2 * NT + ch * 32 + j], act);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += scol[ch * 32 + j];
                     }
                     if (ACC2) {
                         float w[32];
                         tmem_ld32(tacc + NT + ch * 32, w);
+                        add_lds32(scol + 3 * NT + ch * 32, w);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += w[j] + scol[3 * NT + ch * 32 + j];
+                        for (int j = 0; j < 32; ++j) v[j] += w[j];
                     }
                     if (eT) add_row32(eT + ch * 32, v);
                     if (eR) add_row32(eR + ch * 32, v);
@@ -534,10 +405,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     float y[32];
                     tmem_ld32(tacc + ch * 32, v);
                     tmem_ld32(tstash + ch * 32, y);
+                    constexpr int GPC3 = (GS && GS < 32) ? 32 / GS : 1;
+                    float m1[GPC3], m2[GPC3], rsd[GPC3];
+#pragma unroll
+                    for (int g = 0; g < GPC3; ++g) {
+                        const int sl = slab0 + (ch * 32) / (GS ? GS : 1) + g;
+                        m1[g] = sstat[sl]; m2[g] = sstat[128 + sl]; rsd[g] = sstat[256 + sl];
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const int sl = slab0 + (ch * 32 + j) / (GS ? GS : 1);
-                        v[j] = sstat[256 + sl] * (v[j] - sstat[sl] - y[j] * sstat[128 + sl]);
+                        const int g = GPC3 > 1 ? j / (32 / GPC3) : 0;
+                        v[j] = rsd[g] * (v[j] - m1[g] - y[j] * m2[g]);
                     }
                     if (valid) {
                         const size_t o = orow * p.ldg + n0 + ch * 32;
@@ -550,6 +428,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             tc_fence_before();
             epi_bar();
             if (etid == 0) mbar_arrive(&tempty[as]);
+            if (P.ctr && etid == 0) {
+                atomicAdd(P.ctr + 3, (unsigned long long)(tq1 - tq0));
+                atomicAdd(P.ctr + 4, (unsigned long long)(clock64() - tq1));
+                atomicAdd(P.ctr + 6, 1ull);
+            }
             if (++as == NACC) { as = 0; aph ^= 1; }
         }
     }
@@ -640,6 +523,22 @@ int w_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int rows, int NT) 
 }
 
 int g_num_sms = 0;
+}  // namespace
+// role timers of conv_tc_kernel, enabled with PMP_TC_TIMERS=1: [0] MMA warp waiting for TMA data,
+// [1] MMA warp waiting for a free accumulator (epilogue behind), [2] MMA warp total, [3] epilogue waiting
+// for the accumulator, [4] epilogue busy, [5] TMA producer waiting for a free stage, [6] tiles
+unsigned long long* tc_timer_buffer() {
+    static unsigned long long* buf = nullptr;
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("PMP_TC_TIMERS");
+        on = (e && atoi(e)) ? 1 : 0;
+        if (on && cudaMalloc((void**)&buf, 8 * sizeof(unsigned long long)) == cudaSuccess)
+            cudaMemset(buf, 0, 8 * sizeof(unsigned long long));
+    }
+    return buf;
+}
+namespace {
 
 template <int NT, int GS, bool ACC2>
 int launch_t(TcP& P, cudaStream_t st) {
@@ -707,6 +606,7 @@ int launch_conv_tc(const ConvP& p, cudaStream_t st) {
     P.tilesN = p.N / NT;
     P.nphase = p.nphase;
     P.mode4d = p.istride == 2 ? 1 : 0;
+    P.ctr = tc_timer_buffer();
     P.ntiles = P.tilesM * P.tilesN * P.nphase;
     P.kpt = p.C1 / BK;
     P.nkb2 = p.A2 ? p.C2 / BK : 0;

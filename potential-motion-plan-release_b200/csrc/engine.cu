@@ -20,6 +20,7 @@
 #include "common.cuh"
 
 namespace pmp {
+unsigned long long* tc_timer_buffer();
 
 static thread_local char g_err[1024] = "";
 static std::atomic<uint64_t> g_launches{0};
@@ -573,7 +574,7 @@ struct Ctx {
     const int64_t* t;
     const float* embRow;   // cfg0: embR rows of this chunk; cfg3: E rows of this chunk
     int rc = 0;
-    bool tc() const { return m->gemm_path == 1; }
+    bool tc() const { return m->gemm_path >= 1; }
     float* alloc(size_t n) {
         n = (n + 3) & ~(size_t)3;
         float* p = dry ? nullptr : m->ws + used;
@@ -593,6 +594,10 @@ struct Ctx {
     }
     void conv(const ConvP& p) {
         if (dry || rc) return;
+        if (m->gemm_path == 2 && conv_tc2_eligible(p)) {
+            rc = prof_launch_conv(p, st, 1, launch_conv_tc2);
+            return;
+        }
         if (tc() && conv_tc_eligible(p)) {
             rc = prof_launch_conv(p, st, 1, launch_conv_tc);
             return;
@@ -995,7 +1000,7 @@ static int aligned_chunk(const pmp_model* m, int H) {
     for (int L = 1; L < m->nl; ++L)
         if (m->has_down(L - 1)) hd /= 2;
     if (hd < 1) hd = 1;
-    int unit = (128 / hd) * 37;
+    int unit = (128 / hd) * 37 * (m->gemm_path == 2 ? 2 : 1);
     if (unit & 1) unit *= 2;   // keep the CFG pair (2 rows per plan) inside one chunk
     if (chunk > unit) chunk = (chunk / unit) * unit;
     return chunk;
@@ -1132,7 +1137,7 @@ int pmp_model_set_row_chunk(pmp_model* m, int rows) {
 }
 
 int pmp_model_set_gemm_path(pmp_model* m, int path) {
-    PMP_REQUIRE(m && (path == 0 || path == 1), "gemm path must be 0 or 1");
+    PMP_REQUIRE(m && path >= 0 && path <= 2, "gemm path must be 0 (fp32 SIMT), 1 (tcgen05) or 2 (tcgen05 with operand reuse)");
     m->gemm_path = path;
     return 0;
 }
@@ -1286,6 +1291,18 @@ int pmp_profile_read(int n_classes, double* ms, double* flops, int64_t* launches
     g_prof.clear();
     if (dump) fclose(dump);
     return 0;
+}
+
+int pmp_debug_counters(double* out8, int reset) {
+    unsigned long long* buf = pmp::tc_timer_buffer();
+    unsigned long long h[8] = {0};
+    if (buf) {
+        cudaDeviceSynchronize();
+        cudaMemcpy(h, buf, sizeof h, cudaMemcpyDeviceToHost);
+        if (reset) cudaMemset(buf, 0, sizeof h);
+    }
+    for (int i = 0; i < 8; ++i) out8[i] = (double)h[i];
+    return buf ? 0 : 1;
 }
 
 int64_t pmp_debug_fetch(pmp_model* m, const char* name, float* host_out, int64_t capacity) {

@@ -1,0 +1,260 @@
+// PTX wrappers shared by the tcgen05 conv kernels (conv_tc.cu, conv_tc2.cu): mbarrier, TMA, tcgen05
+// MMA / commit / TMEM load-store, and per-row vector IO helpers of the epilogues.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace pmp {
+namespace tc {
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, BF16 inputs, FP32 accumulate, M=128
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// K-major, 128-byte swizzle, rows of 64 BF16: 8-row groups 1024 B apart (SBO = 64 x 16 B), LBO = 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+        "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])),
+        "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])),
+        "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
+        "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])),
+        "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// ---- per-warp staging tile: 32 rows x 128 bytes, 16-byte pieces XOR-swizzled by (row & 7).
+// It converts between the epilogue's thread-per-row register layout (what tcgen05.ld delivers) and
+// lane-per-column global accesses, so that every warp-level LDG/STG touches ONE 128-byte line of one
+// output row instead of 32 lines x 16 bytes (the LSU request rate, not bytes, bounded the epilogue).
+__device__ __forceinline__ int stg_off(int r, int w) { return r * 32 + ((((w >> 2) ^ (r & 7)) << 2) | (w & 3)); }
+__device__ __forceinline__ void stg_write_row(float* tb, int lane, const float (&v)[32]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        *reinterpret_cast<float4*>(tb + lane * 32 + ((k ^ (lane & 7)) << 2)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+__device__ __forceinline__ void stg_read_row(const float* tb, int lane, float (&v)[32]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 t = *reinterpret_cast<const float4*>(tb + lane * 32 + ((k ^ (lane & 7)) << 2));
+        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+    }
+}
+// u[j] = src[idx_row * ld + j] for the row owned by each lane (idx < 0: zeros); coalesced loads
+__device__ __forceinline__ void stg_load_rows(float* tb, int lane, int idx, const float* __restrict__ src, int ld,
+                                              float (&u)[32]) {
+#pragma unroll
+    for (int rb = 0; rb < 32; rb += 8) {
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int o = __shfl_sync(0xffffffffu, idx, rb + i);
+            t[i] = o >= 0 ? __ldg(src + (size_t)o * ld + lane) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tb[stg_off(rb + i, lane)] = t[i];
+    }
+    __syncwarp();
+    stg_read_row(tb, lane, u);
+    __syncwarp();
+}
+__device__ __forceinline__ void stg_add_rows(float* tb, int lane, int idx, const float* __restrict__ src, int ld,
+                                             float (&v)[32]) {
+    float u[32];
+    stg_load_rows(tb, lane, idx, src, ld, u);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += u[j];
+}
+// dst[idx_row * ld + j] = v[j] for every lane's row (idx < 0: skipped); coalesced stores
+__device__ __forceinline__ void stg_store_rows(float* tb, int lane, int idx, float* __restrict__ dst, int ld,
+                                               const float (&v)[32]) {
+    stg_write_row(tb, lane, v);
+    __syncwarp();
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+        const int o = __shfl_sync(0xffffffffu, idx, r);
+        if (o >= 0) dst[(size_t)o * ld + lane] = tb[stg_off(r, lane)];
+    }
+    __syncwarp();
+}
+// BF16x3 planes of v: hi/lo rows of 32 bf16 (64 bytes each) stored by half warps
+__device__ __forceinline__ void stg_store_planes(float* tb, int lane, int idx, __nv_bfloat16* __restrict__ hi,
+                                                 __nv_bfloat16* __restrict__ lo, int ld, const float (&v)[32]) {
+    float w[32];   // words 0..15: packed hi pairs, 16..31: packed lo pairs
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v[2 * k], h0, l0);
+        split_bf16(v[2 * k + 1], h1, l1);
+        w[k] = __uint_as_float((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16));
+        w[16 + k] = __uint_as_float((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16));
+    }
+    stg_write_row(tb, lane, w);
+    __syncwarp();
+    __nv_bfloat16* plane = lane < 16 ? hi : lo;
+    const int col = 2 * (lane & 15);
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+        const int o = __shfl_sync(0xffffffffu, idx, r);
+        if (o >= 0) *reinterpret_cast<uint32_t*>(plane + (size_t)o * ld + col) = __float_as_uint(tb[stg_off(r, lane)]);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// 32 consecutive floats of a shared-memory table (same address for every lane: broadcast)
+__device__ __forceinline__ void lds32(const float* p, float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 t = reinterpret_cast<const float4*>(p)[i];
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void add_lds32(const float* p, float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 t = reinterpret_cast<const float4*>(p)[i];
+        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    }
+}
+// per-row 128-byte segment helpers (every thread handles its own row: 8 x 16-byte vectors)
+__device__ __forceinline__ void ld_row32(const float* __restrict__ p, float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void add_row32(const float* __restrict__ p, float (&v)[32]) {
+    float4 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = __ldg(reinterpret_cast<const float4*>(p) + i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        v[4 * i] += t[i].x; v[4 * i + 1] += t[i].y; v[4 * i + 2] += t[i].z; v[4 * i + 3] += t[i].w;
+    }
+}
+__device__ __forceinline__ void st_row32(float* __restrict__ p, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void st_planes32(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                            const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v[8 * i + 2 * k], h0, l0);
+            split_bf16(v[8 * i + 2 * k + 1], h1, l1);
+            h[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            l[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        reinterpret_cast<uint4*>(hi)[i] = make_uint4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<uint4*>(lo)[i] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+template <int GS>
+__device__ __forceinline__ float group_reduce(float v) {
+    // sum over the lanes of one GroupNorm group inside a 32-column chunk
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (GS >= 16) v += __shfl_xor_sync(0xffffffffu, v, 8);
+    if (GS >= 32) v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+}
+
+
+}  // namespace tc
+}  // namespace pmp

@@ -79,6 +79,12 @@ def main(fams):
         prof = pmp_b200.profile_read(2)
         pmp_b200.profile_enable(False)
         print("  eps-eval %d rows: %.2f ms  -> %.1f us/row" % (2 * Bt, ms, 1e3 * ms / (2 * Bt)))
+        import ctypes as _C
+        ctr = (_C.c_double * 8)()
+        if pmp_b200.lib().pmp_debug_counters(ctr, 1) == 0 and ctr[6] > 0:
+            n = ctr[6]
+            print("    tc role timers per tile (cycles): mma_wait_tma %.0f  mma_wait_acc %.0f  mma_total %.0f | epi_wait %.0f  epi_busy %.0f | tma_wait_stage %.0f  (tiles %d)" % (
+                ctr[0] / n, ctr[1] / n, ctr[2] / n, ctr[3] / n, ctr[4] / n, ctr[5] / n, n))
         for cls, (pms, pfl, pn) in zip(("simt", "tc"), prof):
             if pn:
                 print("    conv_%s: %d launches, %.2f ms/eval, %.1f algorithmic TFLOP/s" % (cls, pn // 3, pms / 3, pfl / pms / 1e9))
