@@ -61,6 +61,29 @@ __device__ __forceinline__ float act_bwd(float z, int act) {
     return th + z * (1.0f - th * th) * sg;
 }
 
+// fast variants for the tensor-core epilogues: ex2.approx / rcp.approx based, ~1e-6 relative error,
+// an order of magnitude below the BF16x3 product error of that path (the fp32 SIMT path keeps the
+// IEEE versions above)
+__device__ __forceinline__ float act_fwd_fast(float z, int act) {
+    if (act == 0) return z * __frcp_rn(1.0f + __expf(-z));
+    return act_fwd(z, act);
+}
+__device__ __forceinline__ float act_bwd_fast(float z, int act) {
+    if (act == 0) {
+        const float s = __frcp_rn(1.0f + __expf(-z));
+        return s * fmaf(z, 1.0f - s, 1.0f);
+    }
+    return act_bwd(z, act);
+}
+// two floats -> packed BF16x3 words: hi pair and lo pair (one cvt.rn.bf16x2 each)
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // ----------------------------------------------------------------------------------------
 // implicit-GEMM convolution descriptor shared by the SIMT (fp32) and tcgen05 (bf16x3) cores.
 //
@@ -104,6 +127,12 @@ struct ConvP {
     float* out; int ldo;            // result after all adds (may be null)
     float* gy; int ldg;             // gn_bwd result
     float* energy;                  // [R] += 0.5*sum v^2   (final 1x1 conv only)
+    // small-K convolution evaluated on the CUDA cores inside the tensor kernel's epilogue (K = taps*D,
+    // D = trajectory dimension 2..14): out[row][n] += sum_t sum_d inl_x[(row + t - taps/2)][d] * inl_w[t][d][n]
+    // inl_mode 1: it IS the conv (no MMA slab; first conv / 1x1 seed), added before GroupNorm;
+    // inl_mode 2: residual 1x1 conv of the first block, added after GroupNorm (+ bias2)
+    const float* inl_x; int inl_ld; int inl_D; int inl_taps; int inl_mode;
+    const float* inl_w;
     // BF16x3 operand planes (v ~= hi + lo) of `out` / `gy`, same [row][ld] indexing, for consumers
     // that run on the tcgen05 core (null when the consumer is a SIMT conv)
     __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;

@@ -59,11 +59,37 @@ struct TcP {
     alignas(64) CUtensorMap mW2l;
 };
 
+// small-K conv on the CUDA cores for the row owned by this thread (weights staged in smem [t][d][NT])
+template <int NT>
+__device__ __forceinline__ void inline_conv(const ConvP& p, const float* sinl, int ch, int rg, int h, int Hl,
+                                            bool valid, float (&v)[32]) {
+    if (!valid) return;
+    const int half = p.inl_taps >> 1;
+    for (int t = 0; t < p.inl_taps; ++t) {
+        const int hh = h + t - half;
+        if (hh < 0 || hh >= Hl) continue;
+        const float* xr = p.inl_x + ((size_t)rg * Hl + hh) * p.inl_ld;
+        for (int d = 0; d < p.inl_D; ++d) {
+            const float xd = __ldg(xr + d);
+            const float4* w = reinterpret_cast<const float4*>(sinl + (t * p.inl_D + d) * NT + ch * 32);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float4 w4 = w[k];
+                v[4 * k] = fmaf(xd, w4.x, v[4 * k]);
+                v[4 * k + 1] = fmaf(xd, w4.y, v[4 * k + 1]);
+                v[4 * k + 2] = fmaf(xd, w4.z, v[4 * k + 2]);
+                v[4 * k + 3] = fmaf(xd, w4.w, v[4 * k + 3]);
+            }
+        }
+    }
+}
+
 template <int NT, int GS, bool ACC2>
 struct Cfg {
     static constexpr int B_TILE_BYTES = NT * BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-    static constexpr int NSTAGE = NT == 64 ? 4 : (NT == 128 ? 3 : 2);
+    static constexpr int NSTAGE = NT == 64 ? 3 : (NT == 128 ? 3 : 2);
+    static constexpr int INL_FLOATS = NT == 64 ? 5 * 16 * 64 : 0;   // inline small-K conv weights [taps][D<=16][64]
     static constexpr int ACC_COLS = NT * (ACC2 ? 2 : 1);
     // two accumulator stages when they fit next to the yhat stash of the GroupNorm-backward epilogue
     static constexpr int NACC = (NT <= 128 && 2 * ACC_COLS <= 512) ? 2 : 1;
@@ -76,7 +102,7 @@ struct Cfg {
     static constexpr int COL_FLOATS = 4 * NT;
     static constexpr int ROW_INTS = 4 * 128;
     static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES +
-                                      (TBUF_FLOATS + PART_FLOATS + STAT_FLOATS + COL_FLOATS + ROW_INTS) * 4 + 256 + 1024;
+                                      (TBUF_FLOATS + PART_FLOATS + STAT_FLOATS + COL_FLOATS + ROW_INTS + INL_FLOATS) * 4 + 256 + 1024;
 };
 
 template <int NT, int GS, bool ACC2>
@@ -92,7 +118,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     float* sstat = spart + C::PART_FLOATS;
     float* scol = sstat + C::STAT_FLOATS;                 // bias | gamma | beta | bias2, NT each
     int* srow = reinterpret_cast<int*>(scol + C::COL_FLOATS);   // [128] output row index (or -1), [128] global sample
-    uint64_t* bars = reinterpret_cast<uint64_t*>(srow + C::ROW_INTS);
+    float* sinl = reinterpret_cast<float*>(srow + C::ROW_INTS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sinl + C::INL_FLOATS);
     uint64_t* full = bars;
     uint64_t* empty = bars + NSTAGE;
     uint64_t* tfull = bars + 2 * NSTAGE;
@@ -225,11 +252,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int Sv = min(S, p.R - r0);
             const int Mv = Sv * HJ;
             for (int i = etid; i < NT; i += 256) {
-                scol[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
-                scol[NT + i] = p.gamma ? __ldg(p.gamma + n0 + i) : 0.f;
-                scol[2 * NT + i] = p.beta ? __ldg(p.beta + n0 + i) : 0.f;
-                scol[3 * NT + i] = p.bias2 ? __ldg(p.bias2 + n0 + i) : 0.f;
+                const bool cv = n0 + i < N;
+                scol[i] = (p.bias && cv) ? __ldg(p.bias + n0 + i) : 0.f;
+                scol[NT + i] = (p.gamma && cv) ? __ldg(p.gamma + n0 + i) : 0.f;
+                scol[2 * NT + i] = (p.beta && cv) ? __ldg(p.beta + n0 + i) : 0.f;
+                scol[3 * NT + i] = (p.bias2 && cv) ? __ldg(p.bias2 + n0 + i) : 0.f;
             }
+            if (C::INL_FLOATS && p.inl_x)
+                for (int i = etid; i < p.inl_taps * p.inl_D * NT; i += 256) {
+                    const int td = i / NT, nn = i - td * NT;
+                    sinl[i] = (n0 + nn < N) ? __ldg(p.inl_w + (size_t)td * N + n0 + nn) : 0.f;
+                }
             if (GS)
                 for (int g = 0; g < G; ++g) {
                     spart[((hf * 128 + mrow) * G + g) * 2] = 0.f;
@@ -249,6 +282,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t tacc = tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)(as * C::ACC_COLS);
             const uint32_t tstash = tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)(NACC * C::ACC_COLS + as * NT);
             float v[32];
+            const int hrow = mrow - s_loc * HJ;
+            if (C::INL_FLOATS && p.inl_mode == 1) {
+                // the convolution itself has K = taps*D <= 70: compute it here and park it in the (unused)
+                // accumulator so that the GroupNorm passes below run unchanged
+                for (int ch = hf; ch < NCH; ch += 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    inline_conv<NT>(p, sinl, ch, rg, hrow, HJ, valid, v);
+                    tmem_st32(tacc + ch * 32, v);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
 
             if (GS && p.gn_fwd) {
                 // ---- pass 1: per-row sums of y = acc + bias and y^2 for every group
@@ -275,14 +320,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     }
                 }
                 epi_bar();
+                {
+                    // slab (s, g): the 2*HJ row partials are summed by one thread in 4 independent
+                    // chains (fixed order -> deterministic) instead of one dependent LDS+FADD chain
+                }
                 if (etid < S * G) {
                     const int s = etid / G, g = etid - s * G;
-                    float a = 0.f, b = 0.f;
-                    for (int h2 = 0; h2 < 2; ++h2)
-                        for (int j = 0; j < HJ; ++j) {
-                            a += spart[((h2 * 128 + s * HJ + j) * G + g) * 2];
-                            b += spart[((h2 * 128 + s * HJ + j) * G + g) * 2 + 1];
+                    float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const float* base = spart + ((h2 * 128 + s * HJ) * G + g) * 2;
+                        int j = 0;
+                        for (; j + 4 <= HJ; j += 4) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                a4[u] += base[(j + u) * G * 2];
+                                b4[u] += base[(j + u) * G * 2 + 1];
+                            }
                         }
+                        for (; j < HJ; ++j) {
+                            a4[0] += base[j * G * 2];
+                            b4[0] += base[j * G * 2 + 1];
+                        }
+                    }
+                    const float a = (a4[0] + a4[1]) + (a4[2] + a4[3]), b = (b4[0] + b4[1]) + (b4[2] + b4[3]);
                     const float mean = a * inv_cnt;
                     const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
                     const float rs = 1.0f / sqrtf(var + 1e-5f);
@@ -323,7 +383,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         if (valid) st_row32(p.yhat + orow * p.ldy + n0 + ch * 32, v);
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            v[j] = act_fwd(scol[NT + ch * 32 + j] * v[j] + scol[2 * NT + ch * 32 + j], act);
+                            v[j] = act_fwd_fast(scol[NT + ch * 32 + j] * v[j] + scol[2 * NT + ch * 32 + j], act);
                     }
                     if (ACC2) {
                         float w[32];
@@ -331,6 +391,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         add_lds32(scol + 3 * NT + ch * 32, w);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += w[j];
+                    }
+                    if (C::INL_FLOATS && p.inl_mode == 2) {
+                        add_lds32(scol + 3 * NT + ch * 32, v);
+                        inline_conv<NT>(p, sinl, ch, rg, hrow, HJ, valid, v);
+                    }
+                    if (N < n0 + ch * 32 + 32) {
+                        // narrow output (N = trajectory dimension): masked scalar IO, optional energy
+                        if (valid) {
+                            float e = 0.f;
+                            for (int j = 0; j < 32; ++j) {
+                                const int n = n0 + ch * 32 + j;
+                                if (n >= N) break;
+                                float x = v[j];
+                                if (idp) x += __ldg(idp + ch * 32 + j);
+                                if (adp) x += __ldg(adp + ch * 32 + j);
+                                if (p.out) p.out[orow * p.ldo + n] = x;
+                                e = fmaf(0.5f * x, x, e);
+                            }
+                            if (p.energy) atomicAdd(p.energy + rg, e);
+                        }
+                        continue;
                     }
                     if (eT) add_row32(eT + ch * 32, v);
                     if (eR) add_row32(eR + ch * 32, v);
@@ -369,7 +450,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float gam = scol[NT + ch * 32 + j];
-                        const float gyh = valid ? v[j] * act_bwd(gam * y[j] + scol[2 * NT + ch * 32 + j], act) * gam : 0.f;
+                        const float gyh = valid ? v[j] * act_bwd_fast(gam * y[j] + scol[2 * NT + ch * 32 + j], act) * gam : 0.f;
                         if (!valid) y[j] = 0.f;
                         v[j] = gyh;
                         q1[GPC > 1 ? j / (32 / GPC) : 0] += gyh;
@@ -389,12 +470,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 epi_bar();
                 if (etid < S * G) {
                     const int s = etid / G, g = etid - s * G;
-                    float a = 0.f, b = 0.f;
-                    for (int h2 = 0; h2 < 2; ++h2)
-                        for (int j = 0; j < HJ; ++j) {
-                            a += spart[((h2 * 128 + s * HJ + j) * G + g) * 2];
-                            b += spart[((h2 * 128 + s * HJ + j) * G + g) * 2 + 1];
+                    float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const float* base = spart + ((h2 * 128 + s * HJ) * G + g) * 2;
+                        int j = 0;
+                        for (; j + 4 <= HJ; j += 4) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                a4[u] += base[(j + u) * G * 2];
+                                b4[u] += base[(j + u) * G * 2 + 1];
+                            }
                         }
+                        for (; j < HJ; ++j) {
+                            a4[0] += base[j * G * 2];
+                            b4[0] += base[j * G * 2 + 1];
+                        }
+                    }
+                    const float a = (a4[0] + a4[1]) + (a4[2] + a4[3]), b = (b4[0] + b4[1]) + (b4[2] + b4[3]);
                     sstat[etid] = a * inv_cnt;
                     sstat[128 + etid] = b * inv_cnt;
                     sstat[256 + etid] = (s < Sv) ? __ldg(p.rstd + (size_t)(r0 + s) * 8 + n0 / (GS ? GS : 1) + g) : 0.f;
@@ -570,7 +662,7 @@ int pick_nt(const ConvP& p) {
         return 0;
     }
     if (p.N % 128 == 0) return 128;
-    if (p.N % 64 == 0) return 64;
+    if (p.N % 64 == 0 || p.N < 64) return 64;
     return 0;
 }
 }  // namespace
@@ -583,13 +675,19 @@ bool conv_tc_eligible(const ConvP& p) {
     if (!s1 && p.A2) return false;
     if (t2 && (p.gn_fwd || p.gn_bwd)) return false;
     if (s2 && (p.Hin & 1)) return false;
-    if (!p.A1_hi || !p.A1_lo || !p.W1_hi || !p.W1_lo) return false;
-    if (p.C1 % BK != 0 || (p.lda1 % 8) != 0) return false;
-    if (p.A2 && (!p.A2_hi || !p.A2_lo || !p.W2_hi || !p.W2_lo || p.C2 % BK != 0 || (p.lda2 % 8) != 0)) return false;
-    if (p.energy) return false;
+    const bool inl_pre = p.inl_x && p.inl_mode == 1, inl_post = p.inl_x && p.inl_mode == 2;
+    if ((inl_pre || inl_post) && (!s1 || p.inl_D > 16 || p.inl_taps > 5 || p.N != 64)) return false;
+    if (!inl_pre) {
+        if (!p.A1_hi || !p.A1_lo || !p.W1_hi || !p.W1_lo) return false;
+        if (p.C1 % BK != 0 || (p.lda1 % 8) != 0) return false;
+    }
+    if (p.A2 && !inl_post &&
+        (!p.A2_hi || !p.A2_lo || !p.W2_hi || !p.W2_lo || p.C2 % BK != 0 || (p.lda2 % 8) != 0))
+        return false;
+    if (p.N < 64 && (p.gn_fwd || p.gn_bwd || p.out_hi || p.embT || p.embR || !s1)) return false;
     if (p.HJ < 8 || p.HJ > 128 || p.HJ > 256) return false;
     const int nt = pick_nt(p);
-    if (!nt || p.N % nt != 0) return false;
+    if (!nt || (p.N % nt != 0 && p.N >= 64)) return false;
     if ((p.gn_fwd || p.gn_bwd) && (128 / p.HJ) * (nt / (p.N / 8)) > 128) return false;
     return true;
 }
@@ -603,34 +701,37 @@ int launch_conv_tc(const ConvP& p, cudaStream_t st) {
     const int S = 128 / p.HJ;
     P.e.S = S;
     P.tilesM = (p.R + S - 1) / S;
-    P.tilesN = p.N / NT;
+    P.tilesN = (p.N + NT - 1) / NT;
+    const bool inl_pre = p.inl_x && p.inl_mode == 1, inl_post = p.inl_x && p.inl_mode == 2;
     P.nphase = p.nphase;
     P.mode4d = p.istride == 2 ? 1 : 0;
     P.ctr = tc_timer_buffer();
     P.ntiles = P.tilesM * P.tilesN * P.nphase;
-    P.kpt = p.C1 / BK;
-    P.nkb2 = p.A2 ? p.C2 / BK : 0;
+    P.kpt = inl_pre ? 0 : p.C1 / BK;
+    P.nkb2 = (p.A2 && !inl_post) ? p.C2 / BK : 0;
     int rc;
-    if (P.mode4d) {
-        if ((rc = act_map4(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S, p.HJ))) return rc;
-        if ((rc = act_map4(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S, p.HJ))) return rc;
-    } else {
-        if ((rc = act_map(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S))) return rc;
-        if ((rc = act_map(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S))) return rc;
+    if (!inl_pre) {
+        if (P.mode4d) {
+            if ((rc = act_map4(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S, p.HJ))) return rc;
+            if ((rc = act_map4(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S, p.HJ))) return rc;
+        } else {
+            if ((rc = act_map(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S))) return rc;
+            if ((rc = act_map(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S))) return rc;
+        }
+        int maxk = 0;
+        for (int ph = 0; ph < p.nphase; ++ph)
+            for (int t = 0; t < p.ntaps[ph]; ++t) maxk = p.tap_k[ph][t] > maxk ? p.tap_k[ph][t] : maxk;
+        if ((rc = w_map(&P.mW1h, p.W1_hi, p.C1, (maxk + 1) * p.N, NT))) return rc;
+        if ((rc = w_map(&P.mW1l, p.W1_lo, p.C1, (maxk + 1) * p.N, NT))) return rc;
     }
-    int maxk = 0;
-    for (int ph = 0; ph < p.nphase; ++ph)
-        for (int t = 0; t < p.ntaps[ph]; ++t) maxk = p.tap_k[ph][t] > maxk ? p.tap_k[ph][t] : maxk;
-    if ((rc = w_map(&P.mW1h, p.W1_hi, p.C1, (maxk + 1) * p.N, NT))) return rc;
-    if ((rc = w_map(&P.mW1l, p.W1_lo, p.C1, (maxk + 1) * p.N, NT))) return rc;
-    if (p.A2) {
+    if (p.A2 && !inl_post) {
         if ((rc = act_map(&P.mA2h, p.A2_hi, p.C2, p.Hin, p.R, p.lda2, S))) return rc;
         if ((rc = act_map(&P.mA2l, p.A2_lo, p.C2, p.Hin, p.R, p.lda2, S))) return rc;
         if ((rc = w_map(&P.mW2h, p.W2_hi, p.C2, p.N, NT))) return rc;
         if ((rc = w_map(&P.mW2l, p.W2_lo, p.C2, p.N, NT))) return rc;
     }
     const bool gn = p.gn_fwd || p.gn_bwd;
-    const bool acc2 = (p.A2 != nullptr) && (p.bias2 != nullptr || p.gn_fwd);
+    const bool acc2 = (p.A2 != nullptr) && !inl_post && (p.bias2 != nullptr || p.gn_fwd);
     const int gs = gn ? p.N / 8 : 0;
     if (NT == 64) {
         if (gs == 8) return acc2 ? launch_t<64, 8, true>(P, st) : launch_t<64, 8, false>(P, st);

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         lds32(scol + NT + ch * 32, ga);
                         lds32(scol + 2 * NT + ch * 32, be);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = act_fwd(ga[j] * v[j] + be[j], act);
+                        for (int j = 0; j < 32; ++j) v[j] = act_fwd_fast(ga[j] * v[j] + be[j], act);
                     }
                     if (p.embT) stg_add_rows(tb, lane, tt_i, p.embT + p.eoff + n0 + ch * 32, p.ldeT, v);
                     if (p.embR) stg_add_rows(tb, lane, er_i, p.embR + p.eoff + n0 + ch * 32, p.ldeR, v);
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const __grid_co
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float gam = ga[j];
-                        const float gyh = valid ? v[j] * act_bwd(gam * y[j] + be[j], act) * gam : 0.f;
+                        const float gyh = valid ? v[j] * act_bwd_fast(gam * y[j] + be[j], act) * gam : 0.f;
                         v[j] = gyh;
                         q1[GPC > 1 ? j / (32 / GPC) : 0] += gyh;
                         q2[GPC > 1 ? j / (32 / GPC) : 0] += valid ? gyh * y[j] : 0.f;

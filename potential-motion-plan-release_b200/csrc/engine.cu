@@ -127,6 +127,7 @@ struct pmp_model {
     std::vector<PlainConv> downc, upc;
     CBW finalcb;
     size_t fin1Wf = 0, fin1Wb = 0, fin1b = 0;
+    TcW fin1tc;
     size_t tW1 = 0, tB1 = 0, tW3 = 0, tB3 = 0;
     VitW vit;
     int Ctot = 0;   // sum of Cout over residual blocks (embedding table width)
@@ -190,7 +191,7 @@ struct Packer16 {
     }
     TcW add(const std::vector<float>& w /*[K][C][N]*/, int K, int C, int N) {
         TcW t;
-        if (C % 64 != 0 || N % 64 != 0) return t;
+        if (C % 64 != 0) return t;   // N may be narrow (trajectory dimension): TMA zero-fills / over-reads unused columns
         const size_t n = (size_t)K * C * N;
         size_t off = (buf.size() + 63) & ~(size_t)63;   // 128-byte aligned planes
         const size_t stride = (n + 63) & ~(size_t)63;
@@ -403,6 +404,7 @@ static int finalize_model(pmp_model* m) {
         PMP_REQUIRE(w->shape[0] == a.transition_dim && w->shape[1] == a.dim, "final_conv.1.weight shape");
         std::vector<float> t;
         conv_fwd_layout(*w, t); m->fin1Wf = pk.add(t);
+        m->fin1tc = pk16.add(t, 1, a.dim, a.transition_dim);
         conv_bwd_layout(*w, t, false); m->fin1Wb = pk.add(t);
         m->fin1b = pk.add(b->v);
     }
@@ -682,6 +684,9 @@ static void res_fwd(Ctx& c, int bi, const ActP& x, ActP& out) {
     p.yhat = b.cb[0].yhat; p.ldy = Co; p.rstd = b.cb[0].rstd; p.act = m->arch.act;
     set_emb(c, p, b);
     p.out = mid.p; p.ldo = Co; p.out_hi = mid.hi; p.out_lo = mid.lo;
+    if (b.Cin <= 16) {   // first block: K = 5*D, evaluated inline in the tensor kernel's epilogue
+        p.inl_x = x.p; p.inl_ld = x.ld; p.inl_D = b.Cin; p.inl_taps = 5; p.inl_mode = 1; p.inl_w = m->A(b.cb[0].Wf);
+    }
     c.conv(p);
     ConvP q = geom_s1(R, Hl, 5);
     set_A1(q, mid.p, mid.hi, mid.lo, Co, Co);
@@ -693,6 +698,9 @@ static void res_fwd(Ctx& c, int bi, const ActP& x, ActP& out) {
         set_A2(q, x.p, x.hi, x.lo, x.ld, b.Cin);
         set_W2(m, q, b.Rf, b.tcRf);
         q.bias2 = m->A(b.Rbias);
+        if (b.Cin <= 16) {
+            q.inl_x = x.p; q.inl_ld = x.ld; q.inl_D = b.Cin; q.inl_taps = 1; q.inl_mode = 2; q.inl_w = m->A(b.Rf);
+        }
     } else {
         q.ident = x.p; q.ldi = x.ld;
     }
@@ -857,13 +865,15 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
     fcb.rstd = c.alloc((size_t)R * 8);
     c.dbg("yhat:", "final_conv.0.", fcb.yhat, (int64_t)R * H * C0);
     float* f = c.alloc((size_t)R * H * C0);
+    bf16 *f_hi, *f_lo;
+    c.planes((size_t)R * H * C0, &f_hi, &f_lo);
     {
         ConvP p = geom_s1(R, H, 5);
         set_A1(p, cur.p, cur.hi, cur.lo, cur.ld, C0);
         set_W1(m, p, fcb.Wf, fcb.tcf);
         p.N = C0; p.bias = m->A(fcb.bias);
         p.gn_fwd = 1; p.gamma = m->A(fcb.gamma); p.beta = m->A(fcb.beta); p.yhat = fcb.yhat; p.ldy = C0;
-        p.rstd = fcb.rstd; p.act = m->arch.act; p.out = f; p.ldo = C0;
+        p.rstd = fcb.rstd; p.act = m->arch.act; p.out = f; p.ldo = C0; p.out_hi = f_hi; p.out_lo = f_lo;
         c.conv(p);
     }
     float* u = u_out ? u_out : c.alloc((size_t)R * H * D);
@@ -873,8 +883,9 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
             if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return PMP_ERR_CUDA; }
         }
         ConvP p = geom_s1(R, H, 1);
-        set_A1(p, f, nullptr, nullptr, C0, C0);
-        p.W1 = m->A(m->fin1Wf); p.N = D; p.bias = m->A(m->fin1b);
+        set_A1(p, f, f_hi, f_lo, C0, C0);
+        set_W1(m, p, m->fin1Wf, m->fin1tc);
+        p.N = D; p.bias = m->A(m->fin1b);
         p.out = u; p.ldo = D; p.energy = energy;
         c.conv(p);
     }
@@ -888,6 +899,7 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
         ConvP p = geom_s1(R, H, 1);
         set_A1(p, u, nullptr, nullptr, D, D);
         p.W1 = m->A(m->fin1Wb); p.N = C0;
+        if (D <= 16) { p.inl_x = u; p.inl_ld = D; p.inl_D = D; p.inl_taps = 1; p.inl_mode = 1; p.inl_w = m->A(m->fin1Wb); }
         p.gn_bwd = 1; p.gamma = m->A(fcb.gamma); p.beta = m->A(fcb.beta); p.yhat = fcb.yhat; p.ldy = C0;
         p.rstd = fcb.rstd; p.gy = gyf; p.ldg = C0; p.gy_hi = gyf_hi; p.gy_lo = gyf_lo; p.act = m->arch.act;
         c.conv(p);

@@ -232,13 +232,7 @@ __device__ __forceinline__ void st_planes32(__nv_bfloat16* __restrict__ hi, __nv
     for (int i = 0; i < 4; ++i) {
         uint32_t h[4], l[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v[8 * i + 2 * k], h0, l0);
-            split_bf16(v[8 * i + 2 * k + 1], h1, l1);
-            h[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            l[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        }
+        for (int k = 0; k < 4; ++k) split_bf16x2(v[8 * i + 2 * k], v[8 * i + 2 * k + 1], h[k], l[k]);
         reinterpret_cast<uint4*>(hi)[i] = make_uint4(h[0], h[1], h[2], h[3]);
         reinterpret_cast<uint4*>(lo)[i] = make_uint4(l[0], l[1], l[2], l[3]);
     }
