@@ -32,7 +32,7 @@ constexpr int BK2 = 32;                      // channels per chunk = one 64-byte
 constexpr int A_ROWS = 192;                  // smem rows per A plane (>= 4*S + 128)
 constexpr int A_PLANE = A_ROWS * BK2 * 2;    // 12 KB
 constexpr int A_STAGE = 4 * A_PLANE;         // 2 tiles x (hi, lo)
-constexpr int NSTA = 2, NSTB = 4;
+constexpr int NSTA = 2;
 
 struct Tc2P {
     ConvP e;
@@ -56,6 +56,7 @@ __device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
 
 template <int NT, int GS>
 struct Cfg2 {
+    static constexpr int NSTB = NT <= 128 ? 4 : 2;                  // B ring depth (smem budget)
     static constexpr int B_PLANE = NT * BK2 * 2;
     static constexpr int B_STAGE = 2 * B_PLANE;
     static constexpr int ACC_COLS = 2 * NT;                       // two M tiles
@@ -65,22 +66,21 @@ struct Cfg2 {
     static constexpr int PART_FLOATS = 2 * 128 * 8 * 2;
     static constexpr int STAT_FLOATS = 2 * 3 * 128;
     static constexpr int COL_FLOATS = 4 * NT;
-    static constexpr int STG_FLOATS = 8 * 32 * 32;                 // one 4 KB staging tile per epilogue warp
+    static constexpr int STG_FLOATS = 0;
     static constexpr int SMEM_BYTES = NSTA * A_STAGE + NSTB * B_STAGE + (STG_FLOATS + PART_FLOATS + STAT_FLOATS + COL_FLOATS) * 4 + 256 + 1024;
 };
 
 template <int NT, int GS>
 __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ Tc2P P) {
     using C = Cfg2<NT, GS>;
-    constexpr int G = C::G, NCH = C::NCH, NACC = C::NACC;
+    constexpr int G = C::G, NCH = C::NCH, NACC = C::NACC, NSTB = C::NSTB;
     const ConvP& p = P.e;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
     uint8_t* sA = smem;
     uint8_t* sB = smem + NSTA * A_STAGE;
-    float* stg = reinterpret_cast<float*>(sB + NSTB * C::B_STAGE);   // 1024-byte aligned
-    float* spart = stg + C::STG_FLOATS;
+    float* spart = reinterpret_cast<float*>(sB + NSTB * C::B_STAGE);
     float* sstat = spart + C::PART_FLOATS;
     float* scol = sstat + C::STAT_FLOATS;
     uint64_t* bars = reinterpret_cast<uint64_t*>(scol + C::COL_FLOATS);
@@ -220,8 +220,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const __grid_co
             const int h = mrow / S, s_loc = mrow - h * S;
             const bool valid = (h < Hl) && (r0 + s_loc < p.R) && !(P.dbg & 1);
             const int rg = valid ? r0 + s_loc : 0;
-            const int orow_i = valid ? rg * p.Hout + h : -1;        // output row of this thread, -1: none
-            float* tb = stg + (warp - 2) * 1024;
+            const size_t orow = valid ? (size_t)rg * p.Hout + h : 0;
             const int slab0 = ti * 128 + s_loc * G;
             float* mypart = spart + ((ti * 128 + mrow) * G) * 2;
             if (GS) {
@@ -301,19 +300,22 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const __grid_co
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             v[j] = (v[j] - mu[GPC > 1 ? j / (32 / GPC) : 0]) * rsd[GPC > 1 ? j / (32 / GPC) : 0];   // yhat
-                        stg_store_rows(tb, lane, orow_i, p.yhat + n0 + ch * 32, p.ldy, v);
+                        if (valid) st_row32(p.yhat + orow * p.ldy + n0 + ch * 32, v);
                         float ga[32], be[32];
                         lds32(scol + NT + ch * 32, ga);
                         lds32(scol + 2 * NT + ch * 32, be);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = act_fwd_fast(ga[j] * v[j] + be[j], act);
                     }
-                    if (p.embT) stg_add_rows(tb, lane, tt_i, p.embT + p.eoff + n0 + ch * 32, p.ldeT, v);
-                    if (p.embR) stg_add_rows(tb, lane, er_i, p.embR + p.eoff + n0 + ch * 32, p.ldeR, v);
-                    if (p.ident) stg_add_rows(tb, lane, orow_i, p.ident + n0 + ch * 32, p.ldi, v);
-                    if (p.addend) stg_add_rows(tb, lane, orow_i, p.addend + n0 + ch * 32, p.ldad, v);
-                    if (p.out) stg_store_rows(tb, lane, orow_i, p.out + n0 + ch * 32, p.ldo, v);
-                    if (p.out_hi) stg_store_planes(tb, lane, orow_i, p.out_hi + n0 + ch * 32, p.out_lo + n0 + ch * 32, p.ldo, v);
+                    if (tt_i >= 0) add_row32(p.embT + (size_t)tt_i * p.ldeT + p.eoff + n0 + ch * 32, v);
+                    if (er_i >= 0) add_row32(p.embR + (size_t)er_i * p.ldeR + p.eoff + n0 + ch * 32, v);
+                    if (p.ident) add_row32(p.ident + orow * p.ldi + n0 + ch * 32, v);
+                    if (p.addend) add_row32(p.addend + orow * p.ldad + n0 + ch * 32, v);
+                    if (valid) {
+                        const size_t o = orow * p.ldo + n0 + ch * 32;
+                        if (p.out) st_row32(p.out + o, v);
+                        if (p.out_hi) st_planes32(p.out_hi + o, p.out_lo + o, v);
+                    }
                 }
             } else {
                 // ---- backward with GroupNorm/activation backward.
@@ -322,12 +324,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const __grid_co
 #pragma unroll 1
                 for (int ch = 0; ch < NCH; ++ch) {
                     tmem_ld32(tacc + ch * 32, v);
-                    if (p.ident) stg_add_rows(tb, lane, orow_i, p.ident + n0 + ch * 32, p.ldi, v);
-                    if (p.addend) stg_add_rows(tb, lane, orow_i, p.addend + n0 + ch * 32, p.ldad, v);
-                    if (p.out) stg_store_rows(tb, lane, orow_i, p.out + n0 + ch * 32, p.ldo, v);
-                    if (p.out_hi) stg_store_planes(tb, lane, orow_i, p.out_hi + n0 + ch * 32, p.out_lo + n0 + ch * 32, p.ldo, v);
+                    if (p.ident) add_row32(p.ident + orow * p.ldi + n0 + ch * 32, v);
+                    if (p.addend) add_row32(p.addend + orow * p.ldad + n0 + ch * 32, v);
+                    if (valid) {
+                        const size_t o = orow * p.ldo + n0 + ch * 32;
+                        if (p.out) st_row32(p.out + o, v);
+                        if (p.out_hi) st_planes32(p.out_hi + o, p.out_lo + o, v);
+                    }
                     float y[32];
-                    stg_load_rows(tb, lane, orow_i, p.yhat + n0 + ch * 32, p.ldy, y);
+                    ld_row32(p.yhat + orow * p.ldy + n0 + ch * 32, y);
                     float q1[GPC], q2[GPC];
 #pragma unroll
                     for (int g = 0; g < GPC; ++g) q1[g] = q2[g] = 0.f;
@@ -371,7 +376,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 for (int ch = 0; ch < NCH; ++ch) {
                     float y[32];
                     tmem_ld32(tacc + ch * 32, v);
-                    stg_load_rows(tb, lane, orow_i, p.yhat + n0 + ch * 32, p.ldy, y);
+                    ld_row32(p.yhat + orow * p.ldy + n0 + ch * 32, y);
                     float m1[GPC], m2[GPC], rsd[GPC];
 #pragma unroll
                     for (int g = 0; g < GPC; ++g) {
@@ -383,8 +388,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const __grid_co
                         const int g = GPC > 1 ? j / (32 / GPC) : 0;
                         v[j] = rsd[g] * (v[j] - m1[g] - y[j] * m2[g]);
                     }
-                    stg_store_rows(tb, lane, orow_i, p.gy + n0 + ch * 32, p.ldg, v);
-                    if (p.gy_hi) stg_store_planes(tb, lane, orow_i, p.gy_hi + n0 + ch * 32, p.gy_lo + n0 + ch * 32, p.ldg, v);
+                    if (valid) {
+                        const size_t o = orow * p.ldg + n0 + ch * 32;
+                        st_row32(p.gy + o, v);
+                        if (p.gy_hi) st_planes32(p.gy_hi + o, p.gy_lo + o, v);
+                    }
                 }
             }
             // release the accumulator stage

@@ -109,84 +109,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// ---- per-warp staging tile: 32 rows x 128 bytes, 16-byte pieces XOR-swizzled by (row & 7).
-// It converts between the epilogue's thread-per-row register layout (what tcgen05.ld delivers) and
-// lane-per-column global accesses, so that every warp-level LDG/STG touches ONE 128-byte line of one
-// output row instead of 32 lines x 16 bytes (the LSU request rate, not bytes, bounded the epilogue).
-__device__ __forceinline__ int stg_off(int r, int w) { return r * 32 + ((((w >> 2) ^ (r & 7)) << 2) | (w & 3)); }
-__device__ __forceinline__ void stg_write_row(float* tb, int lane, const float (&v)[32]) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-        *reinterpret_cast<float4*>(tb + lane * 32 + ((k ^ (lane & 7)) << 2)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-}
-__device__ __forceinline__ void stg_read_row(const float* tb, int lane, float (&v)[32]) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float4 t = *reinterpret_cast<const float4*>(tb + lane * 32 + ((k ^ (lane & 7)) << 2));
-        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
-    }
-}
-// u[j] = src[idx_row * ld + j] for the row owned by each lane (idx < 0: zeros); coalesced loads
-__device__ __forceinline__ void stg_load_rows(float* tb, int lane, int idx, const float* __restrict__ src, int ld,
-                                              float (&u)[32]) {
-#pragma unroll
-    for (int rb = 0; rb < 32; rb += 8) {
-        float t[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int o = __shfl_sync(0xffffffffu, idx, rb + i);
-            t[i] = o >= 0 ? __ldg(src + (size_t)o * ld + lane) : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tb[stg_off(rb + i, lane)] = t[i];
-    }
-    __syncwarp();
-    stg_read_row(tb, lane, u);
-    __syncwarp();
-}
-__device__ __forceinline__ void stg_add_rows(float* tb, int lane, int idx, const float* __restrict__ src, int ld,
-                                             float (&v)[32]) {
-    float u[32];
-    stg_load_rows(tb, lane, idx, src, ld, u);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += u[j];
-}
-// dst[idx_row * ld + j] = v[j] for every lane's row (idx < 0: skipped); coalesced stores
-__device__ __forceinline__ void stg_store_rows(float* tb, int lane, int idx, float* __restrict__ dst, int ld,
-                                               const float (&v)[32]) {
-    stg_write_row(tb, lane, v);
-    __syncwarp();
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-        const int o = __shfl_sync(0xffffffffu, idx, r);
-        if (o >= 0) dst[(size_t)o * ld + lane] = tb[stg_off(r, lane)];
-    }
-    __syncwarp();
-}
-// BF16x3 planes of v: hi/lo rows of 32 bf16 (64 bytes each) stored by half warps
-__device__ __forceinline__ void stg_store_planes(float* tb, int lane, int idx, __nv_bfloat16* __restrict__ hi,
-                                                 __nv_bfloat16* __restrict__ lo, int ld, const float (&v)[32]) {
-    float w[32];   // words 0..15: packed hi pairs, 16..31: packed lo pairs
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v[2 * k], h0, l0);
-        split_bf16(v[2 * k + 1], h1, l1);
-        w[k] = __uint_as_float((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16));
-        w[16 + k] = __uint_as_float((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16));
-    }
-    stg_write_row(tb, lane, w);
-    __syncwarp();
-    __nv_bfloat16* plane = lane < 16 ? hi : lo;
-    const int col = 2 * (lane & 15);
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-        const int o = __shfl_sync(0xffffffffu, idx, r);
-        if (o >= 0) *reinterpret_cast<uint32_t*>(plane + (size_t)o * ld + col) = __float_as_uint(tb[stg_off(r, lane)]);
-    }
-    __syncwarp();
-}
-
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // 32 consecutive floats of a shared-memory table (same address for every lane: broadcast)

@@ -78,6 +78,33 @@ def test_eps_chunking_and_determinism():
     assert torch.equal(e1, e3), "row chunking changed the result"
 
 
+@pytest.mark.parametrize("fam", ["m2d", "dualkuka"])
+def test_gemm_paths_agree(fam):
+    """path 0 = exact fp32 CUDA-core convs, path 1 = tcgen05 BF16x3, path 2 = tcgen05 with operand reuse"""
+    a = synth.arch(fam)
+    cfg = unet_ref.UnetCfg(a["unet"]); sd = unet_ref.synth_weights(a["unet"], 1)
+    eng = dropin(fam).model.engine(100)
+    gen = torch.Generator().manual_seed(9)
+    B, H = 21, a["horizon"]
+    x = torch.randn(2 * B, H, a["obs_dim"], generator=gen)
+    t = torch.randint(0, 100, (2 * B,), generator=gen)
+    walls = torch.tensor(synth.make_problems(fam, B, 12)["walls"]).repeat(2, 1)
+    ref = unet_ref.eps_autograd(sd, cfg, x, t, walls, n_cond=B).numpy()
+    wemb = eng.wall_embed(walls[:B].to(DEV))
+    out = {}
+    try:
+        for path in (0, 1, 2):
+            eng.set_gemm_path(path)
+            out[path] = eng.eps(x.to(DEV), t.to(DEV), wemb, n_cond=B).cpu().numpy()
+    finally:
+        eng.set_gemm_path(1)
+    scale = np.abs(ref).max()
+    assert np.abs(out[0] - ref).max() <= 2e-5 * scale, "fp32 path"
+    for path in (1, 2):
+        assert np.abs(out[path] - ref).max() <= 3e-4 * scale, "tensor-core path %d: %.3e" % (path, np.abs(out[path] - ref).max() / scale)
+        assert_eps_close(out[path], ref, "path %d" % path)
+
+
 def test_wall_embed_vs_oracle_any_wall_count():
     for fam, nws in (("m2d", (1, 6, 9)), ("kuka", (4, 5)), ("m2d_concave", (7,))):
         a = synth.arch(fam)
