@@ -281,7 +281,7 @@ def main():
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             v_cpu, t_cpu = cpu_port_plans_per_sec(64, 5, threads)
             cpu = {"value": v_cpu, "unit": UNIT, "cores": threads, "kind": "port",

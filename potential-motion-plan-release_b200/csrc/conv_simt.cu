@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_simt_kernel(const __grid_consta
             for (int j = 0; j < TN; ++j)
                 if (vc[j]) {
                     const float gv = rs * (acc[i][j] - m1 - yh[i][j] * m2);
-                    o[j] = gv;
+                    if (p.gy) o[j] = gv;
                     if (p.gy_hi) split_bf16(gv, p.gy_hi[orow[i] * p.ldg + nb + j], p.gy_lo[orow[i] * p.ldg + nb + j]);
                 }
         }
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(128) gn_bwd_kernel(const float* __restrict__ g
         const float ga = gamma[c];
         const float gyh = g[row * ldgi + c] * act_bwd(ga * y + beta[c], act) * ga;
         const float gv = rs * (gyh - m1 - y * m2);
-        gy[row * ldg + c] = gv;
+        if (gy) gy[row * ldg + c] = gv;
         if (gy_hi) split_bf16(gv, gy_hi[row * ldg + c], gy_lo[row * ldg + c]);
     }
 }

@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     }
                     if (valid) {
                         const size_t o = orow * p.ldg + n0 + ch * 32;
-                        st_row32(p.gy + o, v);
+                        if (p.gy) st_row32(p.gy + o, v);
                         if (p.gy_hi) st_planes32(p.gy_hi + o, p.gy_lo + o, v);
                     }
                 }

@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const __grid_co
                     }
                     if (valid) {
                         const size_t o = orow * p.ldg + n0 + ch * 32;
-                        st_row32(p.gy + o, v);
+                        if (p.gy) st_row32(p.gy + o, v);
                         if (p.gy_hi) st_planes32(p.gy_hi + o, p.gy_lo + o, v);
                     }
                 }

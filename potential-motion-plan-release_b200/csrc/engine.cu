@@ -631,6 +631,9 @@ static ActP new_act(Ctx& c, int C, int Hl) {
     a.ld = C; a.C = C; a.Hl = Hl; a.blk = -1;
     return a;
 }
+// tensor consumed only as the A operand of a tensor-core conv: BF16 planes suffice (no fp32 copy)
+static bool planes_only(const Ctx& c, int C) { return c.tc() && (C % 64) == 0 && c.H <= 128; }
+
 static ActP view_act(const ActP& base, int off, int C) {
     ActP a = base;
     a.p = base.p ? base.p + off : nullptr;
@@ -676,6 +679,7 @@ static void res_fwd(Ctx& c, int bi, const ActP& x, ActP& out) {
         c.dbg("yhat:", b.pfx + (j ? "blocks.1." : "blocks.0."), b.cb[j].yhat, (int64_t)R * Hl * Co);
     }
     ActP mid = new_act(c, Co, Hl);
+    if (planes_only(c, Co)) mid.p = nullptr;   // only read by the second conv of this block
     ConvP p = geom_s1(R, Hl, 5);
     set_A1(p, x.p, x.hi, x.lo, x.ld, b.Cin);
     set_W1(m, p, b.cb[0].Wf, b.cb[0].tcf);
@@ -736,7 +740,7 @@ static GradP emit_grad(Ctx& c, ConvP& p, const Act& x, const float* addend, int 
     p.addend = addend; p.ldad = ldad;
     p.act = c.m->arch.act;
     if (x.blk >= 0) {
-        g.gy = c.alloc(n);
+        g.gy = planes_only(c, x.C) ? nullptr : c.alloc(n);      // only read by the next dgrad conv
         c.planes(n, &g.gy_hi, &g.gy_lo);
         if (fusable && p.N == x.C) {
             const CBW& cb = c.m->blocks[x.blk].cb[1];
@@ -761,7 +765,7 @@ static GradP res_bwd(Ctx& c, int bi, const GradP& gout, const Act& x, const floa
     ResB& b = m->blocks[bi];
     const int R = c.R, Hl = x.Hl, Co = b.Cout;
     const size_t n = (size_t)R * Hl * Co;
-    float* gy0 = c.alloc(n);
+    float* gy0 = planes_only(c, Co) ? nullptr : c.alloc(n);   // only read by the dgrad conv below
     bf16 *gy0_hi, *gy0_lo;
     c.planes(n, &gy0_hi, &gy0_lo);
     ConvP p = geom_s1(R, Hl, 5);
@@ -933,7 +937,7 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
         g = GradP();
         g.raw = gc.raw; g.raw_hi = gc.raw_hi; g.raw_lo = gc.raw_lo; g.ldr = 2 * Cs;
         if (up_in[ind].blk >= 0) {
-            g.gy = c.alloc((size_t)R * h * Cs);
+            g.gy = planes_only(c, Cs) ? nullptr : c.alloc((size_t)R * h * Cs);
             c.planes((size_t)R * h * Cs, &g.gy_hi, &g.gy_lo);
             gn_bwd_of(c, up_in[ind], g.raw, g.ldr, g.gy, g.gy_hi, g.gy_lo);
         }
