@@ -1,0 +1,63 @@
+"""Batched planning + scoring of one or many environments on the GPU.
+
+Covers, for static Maze2D and (sphere-model) Kuka environments, the per-environment pipeline of
+  RandMaze2DEnvPlanner.plan_an_env / option_1_pick_1_traj   diffuser/guides/rm2d_plan_env.py:54-235
+  KukaEnvPlanner.plan_an_env                                diffuser/guides/kuka_plan_env.py:54-200
+  check_collision / compute_kuka_avg_result                 diffuser/guides/kuka_plan_utils.py:110-220
+i.e. repeat every problem `samples_perprob` times, sample all candidates in one batch, take the
+first collision-free candidate of every problem (else the last), score the chosen paths with the
+per-waypoint check and aggregate the reference's statistics keys.  All environments of a call are
+planned in ONE batch (the reference loops over environments)."""
+import time
+
+import numpy as np
+import torch
+
+import pmp_b200
+from .kuka_colchk import KukaCollisionChecker, arm_bases, TABLE_Z
+
+
+def plan_envs(policy, starts, goals, walls, env_boxes, hext, horizon, samples_perprob=10, robot='maze2d',
+              n_arms=1, collision_eps=0.08, legacy_div=True):
+    """starts/goals [n_env, n_prob, D] (un-normalised numpy), walls [n_env, n_prob, wall_len] model input,
+    env_boxes [n_env, n_boxes, dim] obstacle centres for the checker, hext half extent.
+    Returns (result dict with the reference's keys, chosen paths [n_env*n_prob, H, D] numpy)."""
+    n_env, n_prob, D = starts.shape
+    n_p, n_s = n_env * n_prob, samples_perprob
+    rep = lambda a: np.repeat(a.reshape(n_p, -1), n_s, axis=0)
+    cond = {0: rep(starts).astype(np.float32), horizon - 1: rep(goals).astype(np.float32)}
+    wl = torch.as_tensor(rep(walls), dtype=torch.float32)
+    dev = policy.device
+    torch.cuda.synchronize(dev)
+    tic = time.time()
+    _, traj = policy(cond, batch_size=-1, wall_locations=wl)          # [n_p*n_s, H, D] numpy, un-normalised
+    batch_runtime = time.time() - tic
+    obs = torch.as_tensor(traj.observations, dtype=torch.float32, device=dev)
+    env_id = np.repeat(np.arange(n_env, dtype=np.int32), n_prob * n_s)
+    if robot == 'maze2d':
+        valid, nchk = pmp_b200.colchk_maze2d_swept(obs, env_id, env_boxes, hext, eps=collision_eps,
+                                                   legacy_div=legacy_div)
+    else:
+        chk = KukaCollisionChecker(device=dev)
+        r = pmp_b200.colchk_kuka(obs, env_id, env_boxes, hext, n_arms, arm_bases(n_arms), chk.sph, TABLE_Z)
+        valid, nchk = r['valid'], r['nchk']
+    chosen, suc, total = pmp_b200.pick_first_valid(valid, nchk, n_p, n_s)
+    idx = torch.arange(n_p, device=dev) * n_s + chosen.long()
+    paths = obs[idx]
+    env_p = np.repeat(np.arange(n_env, dtype=np.int32), n_prob)
+    if robot == 'maze2d':
+        ncol, _ = pmp_b200.colchk_maze2d_points(paths, env_p, env_boxes, hext)
+    else:
+        ncol = pmp_b200.colchk_kuka(paths, env_p, env_boxes, hext, n_arms, arm_bases(n_arms), chk.sph, TABLE_Z)['ncol']
+    success = (ncol == 0)
+    res = dict(num_samples=n_p,
+               traj_srate=float(success.float().mean().item()),
+               traj_norepl_srate=float(suc.float().mean().item()),
+               traj_repl_srate=0.0,
+               total_ncr=float(success.float().mean().item()),
+               total_svr=1.0,
+               avg_batch_time=batch_runtime / n_env,
+               avg_sample_time=batch_runtime / n_p,
+               total_num_colck=int(total.sum().item()),
+               avg_num_colck=float(total.float().mean().item()))
+    return res, paths.cpu().numpy()

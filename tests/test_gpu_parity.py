@@ -364,3 +364,21 @@ def test_errors_are_reported():
     with pytest.raises(pmp_b200.PmpError):
         pmp_b200.colchk_maze2d_swept(torch.zeros(1, 8, 2, device=DEV), np.zeros(1, np.int32), np.zeros((1, 40, 2)), 0.1)
     assert pmp_b200.launch_count() > 0
+
+
+def test_plan_entry_points():
+    """plan_rm2d / plan_kuka entry points: batched planning + first-valid pick + scoring, reference result keys"""
+    import importlib.util
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "potential-motion-plan-release_b200", "scripts")
+    spec = importlib.util.spec_from_file_location("plan_rm2d_b200", os.path.join(root, "plan_rm2d.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    keys = {"num_samples", "traj_srate", "traj_norepl_srate", "avg_batch_time", "avg_sample_time", "avg_num_colck",
+            "total_num_colck", "total_ncr", "total_svr", "traj_repl_srate"}
+    res = mod.main(["--plan_n_maze", "2", "--n_prob_env", "3", "--samples_perprob", "4"])
+    assert keys <= set(res) and res["num_samples"] == 6 and 0.0 <= res["traj_srate"] <= 1.0
+    assert res["avg_num_colck"] > 0
+    res = mod.main(["--family", "dualkuka", "--plan_n_maze", "2", "--n_prob_env", "2", "--samples_perprob", "3",
+                    "--ddim_steps", "10"], robot="kuka")
+    assert keys <= set(res) and res["num_samples"] == 4
