@@ -268,8 +268,12 @@ def main():
     tot_conv_ms = sum(r[0] for r in prof)
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     is_tc = prof[1][0] > prof[0][0]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if is_tc and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")   # from the committed ncu --set full capture
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-            "frac": achieved / pk["tf_sust"], "traffic": None,
+            "frac": achieved / pk["tf_sust"], "traffic": traffic,
             "kernel": "conv_tc_kernel (tcgen05 BF16x3 implicit GEMM)" if is_tc else "conv_simt_kernel (fp32 CUDA-core implicit GEMM)",
             "note": ("achieved = algorithmic conv FLOPs (2*M*N*K) / summed kernel time; the BF16x3 error-compensated "
                      "scheme issues 3 tensor passes per product, so issued tensor TFLOP/s = 3 x achieved (cap 0.333)")
