@@ -176,6 +176,8 @@ def main():
     diffusion.horizon = H
     eng = diffusion.model.engine(T_DIFF)
     eng.set_row_chunk(args.row_chunk)
+    if os.environ.get("PMP_GEMM_PATH"):
+        eng.set_gemm_path(int(os.environ["PMP_GEMM_PATH"]))
     Bp = args.batch
     # weak scaling: every rank plans its own Bp problems of a (world*Bp)-problem job
     lo_p, hi_p = shard.shard_range(world * Bp, rank, world)

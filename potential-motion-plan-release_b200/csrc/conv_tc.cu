@@ -44,11 +44,13 @@ namespace {
 struct TcP {
     ConvP e;
     int tilesM, tilesN, ntiles;
+    int npairs;     // CTA-pair schedule: ceil(tilesM / 2) * tilesN * nphase
     int kpt;        // K blocks per tap = C1 / 64
     int nkb2;       // K blocks of slab 2 (slab 1: ntaps[phase] * kpt)
     int nphase;     // 2 for transposed (stride-2 scatter) convs: output rows 2j+phase
     int mode4d;     // 1: stride-2 gather, A maps are 4-D (C, parity, H/2, R)
     unsigned long long* ctr;   // optional role timers (PMP_TC_TIMERS=1): see pmp_debug_counters
+    int dbg;        // diagnostics (PMP_TC_DEBUG): bit 0 = epilogue releases the accumulator without reading it
     alignas(64) CUtensorMap mA1h;
     alignas(64) CUtensorMap mA1l;
     alignas(64) CUtensorMap mA2h;
@@ -84,11 +86,12 @@ __device__ __forceinline__ void inline_conv(const ConvP& p, const float* sinl, i
     }
 }
 
-template <int NT, int GS, bool ACC2>
+template <int NT, int GS, bool ACC2, int CG>
 struct Cfg {
-    static constexpr int B_TILE_BYTES = NT * BK * 2;
+    // CG = 2: CTA pair (cta_group::2); each CTA stages its own 128 A rows and NT/2 of the B rows
+    static constexpr int B_TILE_BYTES = (NT / CG) * BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-    static constexpr int NSTAGE = NT == 64 ? 3 : (NT == 128 ? 3 : 2);
+    static constexpr int NSTAGE = CG == 2 ? (NT == 128 ? 4 : 3) : (NT == 64 ? 3 : (NT == 128 ? 3 : 2));
     static constexpr int INL_FLOATS = NT == 64 ? 5 * 16 * 64 : 0;   // inline small-K conv weights [taps][D<=16][64]
     static constexpr int ACC_COLS = NT * (ACC2 ? 2 : 1);
     // two accumulator stages when they fit next to the yhat stash of the GroupNorm-backward epilogue
@@ -105,9 +108,9 @@ struct Cfg {
                                       (TBUF_FLOATS + PART_FLOATS + STAT_FLOATS + COL_FLOATS + ROW_INTS + INL_FLOATS) * 4 + 256 + 1024;
 };
 
-template <int NT, int GS, bool ACC2>
+template <int NT, int GS, bool ACC2, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcP P) {
-    using C = Cfg<NT, GS, ACC2>;
+    using C = Cfg<NT, GS, ACC2, CG>;
     constexpr int G = C::G, NCH = C::NCH, NSTAGE = C::NSTAGE, NACC = C::NACC;
     const ConvP& p = P.e;
 
@@ -134,54 +137,79 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         prefetch_tmap(&P.mA1h); prefetch_tmap(&P.mA1l); prefetch_tmap(&P.mW1h); prefetch_tmap(&P.mW1l);
         if (P.nkb2) { prefetch_tmap(&P.mA2h); prefetch_tmap(&P.mA2l); prefetch_tmap(&P.mW2h); prefetch_tmap(&P.mW2l); }
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 1); }
+        // tempty: the epilogues of both CTAs of a pair release the accumulator stage to the leader's MMA warp
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // tile schedule: CG = 1: tile -> (phase, n tile, m tile); CG = 2: a cluster takes a PAIR of adjacent m
+    // tiles of the same (phase, n tile); rank r owns m tile 2*pair + r (a pair's odd tile may lie past the
+    // last row: its loads are zero-filled and its epilogue stores nothing)
+    const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;
+    const int sched0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int sched_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int nsched = CG == 2 ? P.npairs : P.ntiles;
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
         if (lane == 0) {
+            auto ld2 = [](void* d, const CUtensorMap* m, uint64_t* b, int c0, int c1) {
+                if (CG == 2) tma2_load_2d(d, m, b, c0, c1); else tma_load_2d(d, m, b, c0, c1);
+            };
+            auto ld3 = [](void* d, const CUtensorMap* m, uint64_t* b, int c0, int c1, int c2) {
+                if (CG == 2) tma2_load_3d(d, m, b, c0, c1, c2); else tma_load_3d(d, m, b, c0, c1, c2);
+            };
+            auto ld4 = [](void* d, const CUtensorMap* m, uint64_t* b, int c0, int c1, int c2, int c3) {
+                if (CG == 2) tma2_load_4d(d, m, b, c0, c1, c2, c3); else tma_load_4d(d, m, b, c0, c1, c2, c3);
+            };
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+            for (int tile = sched0; tile < nsched; tile += sched_step) {
                 const int op = tile % P.nphase, t2 = tile / P.nphase;
-                const int r0 = (t2 / P.tilesN) * S, n0 = (t2 % P.tilesN) * NT;
+                const int r0 = ((t2 / P.tilesN) * CG + (int)crank) * S, n0 = (t2 % P.tilesN) * NT;
+                const int nb0 = n0 + (int)crank * (NT / CG);   // first B row staged by this CTA
                 const int nkb1 = p.ntaps[op] * P.kpt;
                 for (int kb = 0; kb < nkb1 + P.nkb2; ++kb) {
                     const long long tw0 = P.ctr ? clock64() : 0;
                     mbar_wait(&empty[s], ph ^ 1);
                     if (P.ctr) atomicAdd(P.ctr + 5, (unsigned long long)(clock64() - tw0));
                     uint8_t* st = smem + s * C::STAGE_BYTES;
-                    mbar_expect_tx(&full[s], 2 * bytesA + 2 * C::B_TILE_BYTES);
+                    if (CG == 1 || crank == 0) mbar_expect_tx(&full[s], CG * (2 * bytesA + 2 * C::B_TILE_BYTES));
                     if (kb < nkb1) {
                         const int tap = kb / P.kpt, c0 = (kb - tap * P.kpt) * BK;
-                        const int sh = p.tap_shift[op][tap], wr = p.tap_k[op][tap] * N + n0;
+                        const int sh = p.tap_shift[op][tap], wr = p.tap_k[op][tap] * N + nb0;
                         if (P.mode4d) {
                             // input row 2j + sh = parity (sh & 1) of pair j + floor(sh / 2)
                             const int par = sh & 1, js = (sh - par) >> 1;
-                            tma_load_4d(st, &P.mA1h, &full[s], c0, par, js, r0);
-                            tma_load_4d(st + A_TILE_BYTES, &P.mA1l, &full[s], c0, par, js, r0);
+                            ld4(st, &P.mA1h, &full[s], c0, par, js, r0);
+                            ld4(st + A_TILE_BYTES, &P.mA1l, &full[s], c0, par, js, r0);
                         } else {
-                            tma_load_3d(st, &P.mA1h, &full[s], c0, sh, r0);
-                            tma_load_3d(st + A_TILE_BYTES, &P.mA1l, &full[s], c0, sh, r0);
+                            ld3(st, &P.mA1h, &full[s], c0, sh, r0);
+                            ld3(st + A_TILE_BYTES, &P.mA1l, &full[s], c0, sh, r0);
                         }
-                        tma_load_2d(st + 2 * A_TILE_BYTES, &P.mW1h, &full[s], c0, wr);
-                        tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &P.mW1l, &full[s], c0, wr);
+                        ld2(st + 2 * A_TILE_BYTES, &P.mW1h, &full[s], c0, wr);
+                        ld2(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &P.mW1l, &full[s], c0, wr);
                     } else {
                         const int c0 = (kb - nkb1) * BK;
-                        tma_load_3d(st, &P.mA2h, &full[s], c0, 0, r0);
-                        tma_load_3d(st + A_TILE_BYTES, &P.mA2l, &full[s], c0, 0, r0);
-                        tma_load_2d(st + 2 * A_TILE_BYTES, &P.mW2h, &full[s], c0, n0);
-                        tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &P.mW2l, &full[s], c0, n0);
+                        ld3(st, &P.mA2h, &full[s], c0, 0, r0);
+                        ld3(st + A_TILE_BYTES, &P.mA2l, &full[s], c0, 0, r0);
+                        ld2(st + 2 * A_TILE_BYTES, &P.mW2h, &full[s], c0, nb0);
+                        ld2(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &P.mW2l, &full[s], c0, nb0);
                     }
                     if (++s == NSTAGE) { s = 0; ph ^= 1; }
                 }
@@ -189,13 +217,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
     } else if (warp == 1) {
         // ============================== MMA issuer ==============================
-        if (lane == 0) {
-            // instruction descriptor: D=F32, A=B=BF16, both K-major, N=NT, M=128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+        if (lane == 0 && crank == 0) {
+            // instruction descriptor: D=F32, A=B=BF16, both K-major, N=NT, M=128 per CTA
+            const uint32_t idesc =
+                (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | (((128u * CG) >> 4) << 24);
+            auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+                if (CG == 2) tc_mma2(d, a, b, id, acc); else tc_mma(d, a, b, id, acc);
+            };
+            auto commit = [](uint64_t* bar) {
+                if (CG == 2) tc_commit2(bar); else tc_commit(bar);
+            };
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
             const long long tm0 = P.ctr ? clock64() : 0;
-            for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+            for (int tile = sched0; tile < nsched; tile += sched_step) {
                 const long long te0 = P.ctr ? clock64() : 0;
                 mbar_wait(&tempty[as], aph ^ 1);
                 if (P.ctr) atomicAdd(P.ctr + 1, (unsigned long long)(clock64() - te0));
@@ -218,16 +253,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);   // 32 bytes per K=16 step, in 16-byte units
-                        tc_mma(d, ah + ko, bh + ko, idesc, accum);
-                        tc_mma(d, ah + ko, bl + ko, idesc, 1u);
-                        tc_mma(d, al + ko, bh + ko, idesc, 1u);
+                        mma(d, ah + ko, bh + ko, idesc, accum);
+                        mma(d, ah + ko, bl + ko, idesc, 1u);
+                        mma(d, al + ko, bh + ko, idesc, 1u);
                         accum = 1u;
                     }
                     if (slab2) acc2 = 1u; else acc1 = 1u;
-                    tc_commit(&empty[s]);   // frees the smem stage when these MMAs have read it
+                    commit(&empty[s]);   // frees the smem stage (of both CTAs) when these MMAs have read it
                     if (++s == NSTAGE) { s = 0; ph ^= 1; }
                 }
-                tc_commit(&tfull[as]);      // accumulator complete
+                commit(&tfull[as]);      // accumulator complete
                 if (++as == NACC) { as = 0; aph ^= 1; }
             }
             if (P.ctr) atomicAdd(P.ctr + 2, (unsigned long long)(clock64() - tm0));
@@ -246,10 +281,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const float inv_cnt = 1.0f / (float)(HJ * (GS ? GS : 1));
         int as = 0;
         uint32_t aph = 0;
-        for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        for (int tile = sched0; tile < nsched; tile += sched_step) {
             const int op = tile % P.nphase, t2 = tile / P.nphase;
-            const int r0 = (t2 / P.tilesN) * S, n0 = (t2 % P.tilesN) * NT;
-            const int Sv = min(S, p.R - r0);
+            const int r0 = ((t2 / P.tilesN) * CG + (int)crank) * S, n0 = (t2 % P.tilesN) * NT;
+            const int Sv = max(0, min(S, p.R - r0));
             const int Mv = Sv * HJ;
             for (int i = etid; i < NT; i += 256) {
                 const bool cv = n0 + i < N;
@@ -279,6 +314,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const long long tq1 = (P.ctr && etid == 0) ? clock64() : 0;
             tc_fence_after();
             epi_bar();
+            if (P.dbg & 1) {
+                // main-loop-only timing runs: results are garbage
+                tc_fence_before();
+                epi_bar();
+                if (etid == 0) {
+                    if (CG == 2) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
+                }
+                if (++as == NACC) { as = 0; aph ^= 1; }
+                continue;
+            }
             const uint32_t tacc = tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)(as * C::ACC_COLS);
             const uint32_t tstash = tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)(NACC * C::ACC_COLS + as * NT);
             float v[32];
@@ -380,10 +425,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             v[j] = (v[j] - mu[GPC2 > 1 ? j / (32 / GPC2) : 0]) * rsd[GPC2 > 1 ? j / (32 / GPC2) : 0];   // yhat
-                        if (valid) st_row32(p.yhat + orow * p.ldy + n0 + ch * 32, v);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            v[j] = act_fwd_fast(scol[NT + ch * 32 + j] * v[j] + scol[2 * NT + ch * 32 + j], act);
+                        if (valid && !(P.dbg & 2)) st_row32(p.yhat + orow * p.ldy + n0 + ch * 32, v);
+                        act_affine32(scol + NT + ch * 32, scol + 2 * NT + ch * 32, v, act);
                     }
                     if (ACC2) {
                         float w[32];
@@ -413,11 +456,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         }
                         continue;
                     }
-                    if (eT) add_row32(eT + ch * 32, v);
-                    if (eR) add_row32(eR + ch * 32, v);
-                    if (idp) add_row32(idp + ch * 32, v);
-                    if (adp) add_row32(adp + ch * 32, v);
-                    if (valid) {
+                    if (eT && !(P.dbg & 8)) add_row32(eT + ch * 32, v);
+                    if (eR && !(P.dbg & 8)) add_row32(eR + ch * 32, v);
+                    if (idp && !(P.dbg & 4)) add_row32(idp + ch * 32, v);
+                    if (adp && !(P.dbg & 4)) add_row32(adp + ch * 32, v);
+                    if (valid && !(P.dbg & 2)) {
                         const size_t o = orow * p.ldo + n0 + ch * 32;
                         if (p.out) st_row32(p.out + o, v);
                         if (p.out_hi) st_planes32(p.out_hi + o, p.out_lo + o, v);
@@ -434,27 +477,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll 1
                 for (int ch = hf; ch < NCH; ch += 2) {
                     tmem_ld32(tacc + ch * 32, v);
-                    if (idp) add_row32(idp + ch * 32, v);
-                    if (adp) add_row32(adp + ch * 32, v);
-                    if (valid) {
+                    if (idp && !(P.dbg & 4)) add_row32(idp + ch * 32, v);
+                    if (adp && !(P.dbg & 4)) add_row32(adp + ch * 32, v);
+                    if (valid && !(P.dbg & 2)) {
                         const size_t o = orow * p.ldo + n0 + ch * 32;
                         if (p.out) st_row32(p.out + o, v);
                         if (p.out_hi) st_planes32(p.out_hi + o, p.out_lo + o, v);
                     }
                     float y[32];
-                    ld_row32(yp + ch * 32, y);
+                    if (!(P.dbg & 4)) ld_row32(yp + ch * 32, y);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) y[j] = 0.5f;
+                    }
                     constexpr int GPC = (GS && GS < 32) ? 32 / GS : 1;
                     float q1[GPC], q2[GPC];
 #pragma unroll
                     for (int g = 0; g < GPC; ++g) q1[g] = q2[g] = 0.f;
+                    if (!valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { v[j] = 0.f; y[j] = 0.f; }
+                    }
+                    act_affine_bwd32(scol + NT + ch * 32, scol + 2 * NT + ch * 32, y, v, act);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float gam = scol[NT + ch * 32 + j];
-                        const float gyh = valid ? v[j] * act_bwd_fast(gam * y[j] + scol[2 * NT + ch * 32 + j], act) * gam : 0.f;
-                        if (!valid) y[j] = 0.f;
-                        v[j] = gyh;
-                        q1[GPC > 1 ? j / (32 / GPC) : 0] += gyh;
-                        q2[GPC > 1 ? j / (32 / GPC) : 0] += gyh * y[j];
+                        q1[GPC > 1 ? j / (32 / GPC) : 0] += v[j];
+                        q2[GPC > 1 ? j / (32 / GPC) : 0] += v[j] * y[j];
                     }
                     tmem_st32(tacc + ch * 32, v);
                     tmem_st32(tstash + ch * 32, y);
@@ -509,7 +557,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         const int g = GPC3 > 1 ? j / (32 / GPC3) : 0;
                         v[j] = rsd[g] * (v[j] - m1[g] - y[j] * m2[g]);
                     }
-                    if (valid) {
+                    if (valid && !(P.dbg & 2)) {
                         const size_t o = orow * p.ldg + n0 + ch * 32;
                         if (p.gy) st_row32(p.gy + o, v);
                         if (p.gy_hi) st_planes32(p.gy_hi + o, p.gy_lo + o, v);
@@ -519,7 +567,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             // release the accumulator stage
             tc_fence_before();
             epi_bar();
-            if (etid == 0) mbar_arrive(&tempty[as]);
+            if (etid == 0) {
+                if (CG == 2) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
+            }
             if (P.ctr && etid == 0) {
                 atomicAdd(P.ctr + 3, (unsigned long long)(tq1 - tq0));
                 atomicAdd(P.ctr + 4, (unsigned long long)(clock64() - tq1));
@@ -531,9 +581,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();   // no CTA of a pair exits (or frees TMEM) while its peer may still signal it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        if (CG == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -632,12 +686,12 @@ unsigned long long* tc_timer_buffer() {
 }
 namespace {
 
-template <int NT, int GS, bool ACC2>
+template <int NT, int GS, bool ACC2, int CG>
 int launch_t(TcP& P, cudaStream_t st) {
-    using C = Cfg<NT, GS, ACC2>;
+    using C = Cfg<NT, GS, ACC2, CG>;
     static bool configured = false;
     if (!configured) {
-        PMP_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NT, GS, ACC2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PMP_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NT, GS, ACC2, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES));
         configured = true;
     }
@@ -646,8 +700,27 @@ int launch_t(TcP& P, cudaStream_t st) {
         PMP_CUDA_OK(cudaGetDevice(&dev));
         PMP_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    const int grid = P.ntiles < g_num_sms ? P.ntiles : g_num_sms;
-    conv_tc_kernel<NT, GS, ACC2><<<grid, TC_THREADS, C::SMEM_BYTES, st>>>(P);
+    if (CG == 1) {
+        const int grid = P.ntiles < g_num_sms ? P.ntiles : g_num_sms;
+        conv_tc_kernel<NT, GS, ACC2, CG><<<grid, TC_THREADS, C::SMEM_BYTES, st>>>(P);
+    } else {
+        // one cluster of two CTAs (the two SMs of a TPC) per tile pair, persistent over the pairs
+        const int nclusters = P.npairs < g_num_sms / 2 ? P.npairs : g_num_sms / 2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(2 * nclusters, 1, 1);
+        cfg.blockDim = dim3(TC_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        PMP_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NT, GS, ACC2, CG>, P));
+    }
     PMP_LAUNCH_OK();
     return 0;
 }
@@ -692,12 +765,21 @@ bool conv_tc_eligible(const ConvP& p) {
     return true;
 }
 
-int launch_conv_tc(const ConvP& p, cudaStream_t st) {
+// CTA pairs pay off where the main loop dominates (NT >= 128); the narrow level-0 tiles and the inline
+// small-K convolutions stay on single CTAs
+static bool pair_ok(const ConvP& p, int NT) {
+    if (NT < 128) return false;
+    if (p.inl_x) return false;
+    return true;
+}
+
+static int launch_conv_tc_cg(const ConvP& p, cudaStream_t st, int cg) {
     if (!conv_tc_eligible(p)) return 1;
     TcP P;
     memset(&P, 0, sizeof P);
     P.e = p;
     const int NT = pick_nt(p);
+    if (cg == 2 && !pair_ok(p, NT)) cg = 1;
     const int S = 128 / p.HJ;
     P.e.S = S;
     P.tilesM = (p.R + S - 1) / S;
@@ -706,9 +788,16 @@ int launch_conv_tc(const ConvP& p, cudaStream_t st) {
     P.nphase = p.nphase;
     P.mode4d = p.istride == 2 ? 1 : 0;
     P.ctr = tc_timer_buffer();
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("PMP_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+        P.dbg = dbg;
+    }
     P.ntiles = P.tilesM * P.tilesN * P.nphase;
+    P.npairs = ((P.tilesM + 1) / 2) * P.tilesN * P.nphase;
     P.kpt = inl_pre ? 0 : p.C1 / BK;
     P.nkb2 = (p.A2 && !inl_post) ? p.C2 / BK : 0;
+    const int brows = NT / cg;   // B rows staged per CTA
     int rc;
     if (!inl_pre) {
         if (P.mode4d) {
@@ -721,29 +810,42 @@ int launch_conv_tc(const ConvP& p, cudaStream_t st) {
         int maxk = 0;
         for (int ph = 0; ph < p.nphase; ++ph)
             for (int t = 0; t < p.ntaps[ph]; ++t) maxk = p.tap_k[ph][t] > maxk ? p.tap_k[ph][t] : maxk;
-        if ((rc = w_map(&P.mW1h, p.W1_hi, p.C1, (maxk + 1) * p.N, NT))) return rc;
-        if ((rc = w_map(&P.mW1l, p.W1_lo, p.C1, (maxk + 1) * p.N, NT))) return rc;
+        if ((rc = w_map(&P.mW1h, p.W1_hi, p.C1, (maxk + 1) * p.N, brows))) return rc;
+        if ((rc = w_map(&P.mW1l, p.W1_lo, p.C1, (maxk + 1) * p.N, brows))) return rc;
     }
     if (p.A2 && !inl_post) {
         if ((rc = act_map(&P.mA2h, p.A2_hi, p.C2, p.Hin, p.R, p.lda2, S))) return rc;
         if ((rc = act_map(&P.mA2l, p.A2_lo, p.C2, p.Hin, p.R, p.lda2, S))) return rc;
-        if ((rc = w_map(&P.mW2h, p.W2_hi, p.C2, p.N, NT))) return rc;
-        if ((rc = w_map(&P.mW2l, p.W2_lo, p.C2, p.N, NT))) return rc;
+        if ((rc = w_map(&P.mW2h, p.W2_hi, p.C2, p.N, brows))) return rc;
+        if ((rc = w_map(&P.mW2l, p.W2_lo, p.C2, p.N, brows))) return rc;
     }
     const bool gn = p.gn_fwd || p.gn_bwd;
     const bool acc2 = (p.A2 != nullptr) && !inl_post && (p.bias2 != nullptr || p.gn_fwd);
     const int gs = gn ? p.N / 8 : 0;
     if (NT == 64) {
-        if (gs == 8) return acc2 ? launch_t<64, 8, true>(P, st) : launch_t<64, 8, false>(P, st);
-        return acc2 ? launch_t<64, 0, true>(P, st) : launch_t<64, 0, false>(P, st);
+        if (gs == 8) return acc2 ? launch_t<64, 8, true, 1>(P, st) : launch_t<64, 8, false, 1>(P, st);
+        return acc2 ? launch_t<64, 0, true, 1>(P, st) : launch_t<64, 0, false, 1>(P, st);
+    }
+    if (cg == 2) {
+        if (NT == 128) {
+            if (gs == 32) return acc2 ? launch_t<128, 32, true, 2>(P, st) : launch_t<128, 32, false, 2>(P, st);
+            if (gs == 64) return acc2 ? launch_t<128, 64, true, 2>(P, st) : launch_t<128, 64, false, 2>(P, st);
+            return acc2 ? launch_t<128, 0, true, 2>(P, st) : launch_t<128, 0, false, 2>(P, st);
+        }
+        if (NT == 192) return acc2 ? launch_t<192, 96, true, 2>(P, st) : launch_t<192, 96, false, 2>(P, st);
+        return 1;
     }
     if (NT == 128) {
-        if (gs == 32) return acc2 ? launch_t<128, 32, true>(P, st) : launch_t<128, 32, false>(P, st);
-        if (gs == 64) return acc2 ? launch_t<128, 64, true>(P, st) : launch_t<128, 64, false>(P, st);
-        return acc2 ? launch_t<128, 0, true>(P, st) : launch_t<128, 0, false>(P, st);
+        if (gs == 32) return acc2 ? launch_t<128, 32, true, 1>(P, st) : launch_t<128, 32, false, 1>(P, st);
+        if (gs == 64) return acc2 ? launch_t<128, 64, true, 1>(P, st) : launch_t<128, 64, false, 1>(P, st);
+        return acc2 ? launch_t<128, 0, true, 1>(P, st) : launch_t<128, 0, false, 1>(P, st);
     }
-    if (NT == 192) return acc2 ? launch_t<192, 96, true>(P, st) : launch_t<192, 96, false>(P, st);
+    if (NT == 192) return acc2 ? launch_t<192, 96, true, 1>(P, st) : launch_t<192, 96, false, 1>(P, st);
     return 1;
 }
+
+int launch_conv_tc(const ConvP& p, cudaStream_t st) { return launch_conv_tc_cg(p, st, 1); }
+// CTA-pair main loop (cta_group::2) where it applies, single-CTA kernel otherwise
+int launch_conv_tc_pair(const ConvP& p, cudaStream_t st) { return launch_conv_tc_cg(p, st, 2); }
 
 }  // namespace pmp

@@ -601,7 +601,7 @@ struct Ctx {
             return;
         }
         if (tc() && conv_tc_eligible(p)) {
-            rc = prof_launch_conv(p, st, 1, launch_conv_tc);
+            rc = prof_launch_conv(p, st, 1, m->gemm_path == 3 ? launch_conv_tc_pair : launch_conv_tc);
             return;
         }
         rc = prof_launch_conv(p, st, 0, launch_conv_simt);
@@ -1016,7 +1016,7 @@ static int aligned_chunk(const pmp_model* m, int H) {
     for (int L = 1; L < m->nl; ++L)
         if (m->has_down(L - 1)) hd /= 2;
     if (hd < 1) hd = 1;
-    int unit = (128 / hd) * 37 * (m->gemm_path == 2 ? 2 : 1);
+    int unit = (128 / hd) * 37 * (m->gemm_path >= 2 ? 2 : 1);
     if (unit & 1) unit *= 2;   // keep the CFG pair (2 rows per plan) inside one chunk
     if (chunk > unit) chunk = (chunk / unit) * unit;
     return chunk;
@@ -1153,7 +1153,8 @@ int pmp_model_set_row_chunk(pmp_model* m, int rows) {
 }
 
 int pmp_model_set_gemm_path(pmp_model* m, int path) {
-    PMP_REQUIRE(m && path >= 0 && path <= 2, "gemm path must be 0 (fp32 SIMT), 1 (tcgen05) or 2 (tcgen05 with operand reuse)");
+    PMP_REQUIRE(m && path >= 0 && path <= 3,
+                "gemm path must be 0 (fp32 SIMT), 1 (tcgen05), 2 (tcgen05 with operand reuse) or 3 (tcgen05 CTA pairs)");
     m->gemm_path = path;
     return 0;
 }

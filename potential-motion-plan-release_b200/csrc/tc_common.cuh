@@ -71,6 +71,65 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: one MMA spans the two SMs of a TPC (M = 256, each CTA holds
+// its own 128 A rows and half of the B rows), so every SM reads half of B from shared memory.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(rank)
+        : "memory");
+}
+// TMA loads issued by either CTA of a pair; the transaction bytes are credited to the LEADER's barrier
+// (clearing the peer bit of the shared::cluster address selects the even CTA of the pair)
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+// completion of all prior MMAs of this thread arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B^T, M = 256 (128 rows per CTA), issued by the leader CTA only
+__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
 // K-major, 128-byte swizzle, rows of 64 BF16: 8-row groups 1024 B apart (SBO = 64 x 16 B), LBO = 1
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -157,6 +216,58 @@ __device__ __forceinline__ void st_planes32(__nv_bfloat16* __restrict__ hi, __nv
         for (int k = 0; k < 4; ++k) split_bf16x2(v[8 * i + 2 * k], v[8 * i + 2 * k + 1], h[k], l[k]);
         reinterpret_cast<uint4*>(hi)[i] = make_uint4(h[0], h[1], h[2], h[3]);
         reinterpret_cast<uint4*>(lo)[i] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+// ---- activation blocks of the epilogues.  SiLU (every shipped config) runs branch-free on
+// ex2.approx / rcp.approx (2 MUFU + 3 FP32 ops per element, ~3e-7 relative error, far below the BF16x3
+// product error); the 32 elements are independent straight-line code so the MUFU latency overlaps.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float silu_fast(float z) { return z * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * z)); }
+__device__ __forceinline__ float silu_bwd_fast(float z) {
+    const float s = rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * z));
+    return s * fmaf(z, 1.0f - s, 1.0f);
+}
+// v[j] = act(gamma[j] * v[j] + beta[j]) for 32 columns; gamma / beta are shared-memory tables
+__device__ __forceinline__ void act_affine32(const float* gam, const float* bet, float (&v)[32], int act) {
+    if (act == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 g4 = reinterpret_cast<const float4*>(gam)[q], b4 = reinterpret_cast<const float4*>(bet)[q];
+            v[4 * q] = silu_fast(fmaf(g4.x, v[4 * q], b4.x));
+            v[4 * q + 1] = silu_fast(fmaf(g4.y, v[4 * q + 1], b4.y));
+            v[4 * q + 2] = silu_fast(fmaf(g4.z, v[4 * q + 2], b4.z));
+            v[4 * q + 3] = silu_fast(fmaf(g4.w, v[4 * q + 3], b4.w));
+        }
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) v[j] = act_fwd(gam[j] * v[j] + bet[j], act);
+    }
+}
+// g[j] = g[j] * act'(gamma[j] * y[j] + beta[j]) * gamma[j]
+__device__ __forceinline__ void act_affine_bwd32(const float* gam, const float* bet, const float (&y)[32], float (&g)[32],
+                                                 int act) {
+    if (act == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 g4 = reinterpret_cast<const float4*>(gam)[q], b4 = reinterpret_cast<const float4*>(bet)[q];
+            g[4 * q] *= silu_bwd_fast(fmaf(g4.x, y[4 * q], b4.x)) * g4.x;
+            g[4 * q + 1] *= silu_bwd_fast(fmaf(g4.y, y[4 * q + 1], b4.y)) * g4.y;
+            g[4 * q + 2] *= silu_bwd_fast(fmaf(g4.z, y[4 * q + 2], b4.z)) * g4.z;
+            g[4 * q + 3] *= silu_bwd_fast(fmaf(g4.w, y[4 * q + 3], b4.w)) * g4.w;
+        }
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) g[j] *= act_bwd(gam[j] * y[j] + bet[j], act) * gam[j];
     }
 }
 
