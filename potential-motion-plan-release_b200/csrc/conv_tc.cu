@@ -22,6 +22,7 @@
 #include <map>
 #include <tuple>
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -50,6 +51,7 @@ struct TcP {
     int nphase;     // 2 for transposed (stride-2 scatter) convs: output rows 2j+phase
     int mode4d;     // 1: stride-2 gather, A maps are 4-D (C, parity, H/2, R)
     unsigned long long* ctr;   // optional role timers (PMP_TC_TIMERS=1): see pmp_debug_counters
+    int tmode;      // PMP_TC_TIMERS: 1 = role timers, 2 = epilogue phase laps (see pmp_debug_counters)
     int dbg;        // diagnostics (PMP_TC_DEBUG): bit 0 = epilogue releases the accumulator without reading it
     alignas(64) CUtensorMap mA1h;
     alignas(64) CUtensorMap mA1l;
@@ -59,6 +61,15 @@ struct TcP {
     alignas(64) CUtensorMap mW1l;
     alignas(64) CUtensorMap mW2h;
     alignas(64) CUtensorMap mW2l;
+    // TMA-store epilogue (TE kernels): fp32 maps of yhat / out / gy and BF16 maps of the operand planes,
+    // box = (32 channels, HJ rows, S samples) of the tile (4-D with the output phase for stride-2 scatter)
+    alignas(64) CUtensorMap mSy;
+    alignas(64) CUtensorMap mSo;
+    alignas(64) CUtensorMap mSoh;
+    alignas(64) CUtensorMap mSol;
+    alignas(64) CUtensorMap mSg;
+    alignas(64) CUtensorMap mSgh;
+    alignas(64) CUtensorMap mSgl;
 };
 
 // small-K conv on the CUDA cores for the row owned by this thread (weights staged in smem [t][d][NT])
@@ -86,37 +97,50 @@ __device__ __forceinline__ void inline_conv(const ConvP& p, const float* sinl, i
     }
 }
 
-template <int NT, int GS, bool ACC2, int CG>
+template <int NT, int GS, bool ACC2, int CG, bool TE>
 struct Cfg {
     // CG = 2: CTA pair (cta_group::2); each CTA stages its own 128 A rows and NT/2 of the B rows
-    static constexpr int B_TILE_BYTES = (NT / CG) * BK * 2;
-    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-    static constexpr int NSTAGE = CG == 2 ? (NT == 128 ? 4 : 3) : (NT == 64 ? 3 : (NT == 128 ? 3 : 2));
+    // TE: TMA-store epilogue (64 KB of staging tiles: per half of the epilogue warps one fp32 and two BF16 tiles)
+    // channels per K block: 64 (one 128-byte swizzle row) except for the 256-column tiles, which take 32-channel
+    // blocks (64-byte rows, SWIZZLE_64B) so that four stages of the same total size give the TMA more lookahead
+    static constexpr int BKC = NT == 256 ? 32 : 64;
+    static constexpr int A_BYTES = 128 * BKC * 2;
+    static constexpr int B_TILE_BYTES = (NT / CG) * BKC * 2;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_TILE_BYTES;
+    static constexpr int NSTAGE =
+        CG == 2 ? (NT == 256 ? 4 : (NT == 128 ? (TE ? 3 : 4) : 3)) : (NT == 64 ? (TE ? 2 : 3) : (NT == 128 ? 3 : 2));
+    static constexpr int STG_HALF_BYTES = 128 * 32 * 4 + 2 * 128 * 32 * 2;   // F | H | L
+    static constexpr int STG_BYTES = TE ? 2 * STG_HALF_BYTES : 0;
     static constexpr int INL_FLOATS = NT == 64 ? 5 * 16 * 64 : 0;   // inline small-K conv weights [taps][D<=16][64]
     static constexpr int ACC_COLS = NT * (ACC2 ? 2 : 1);
     // two accumulator stages when they fit next to the yhat stash of the GroupNorm-backward epilogue
-    static constexpr int NACC = (NT <= 128 && 2 * ACC_COLS <= 512) ? 2 : 1;
+    static constexpr int NACC = (NT != 192 && 2 * ACC_COLS <= 512) ? 2 : 1;
+    // the GroupNorm-backward epilogue parks yhat in spare TMEM columns between its two passes when there are
+    // any (NT <= 128); the 256-column tiles fill TMEM with their two accumulator stages and re-read yhat (L2)
+    static constexpr bool STASH = NACC * ACC_COLS + NACC * NT <= 512;
     static constexpr int G = GS ? NT / GS : 1;
     static constexpr int NCH = NT / 32;
-    // smem: stages | transpose buffers | row/slab partials | slab stats | column params | row info | barriers
+    // smem: stages | staging tiles | row/slab partials | slab stats | column params | row info | barriers
     static constexpr int TBUF_FLOATS = 0;
-    static constexpr int PART_FLOATS = 2 * 128 * 8 * 2;
+    static constexpr int PART_FLOATS = 2 * 128 * G * 2;
     static constexpr int STAT_FLOATS = 384;
     static constexpr int COL_FLOATS = 4 * NT;
     static constexpr int ROW_INTS = 4 * 128;
-    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES +
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + STG_BYTES +
                                       (TBUF_FLOATS + PART_FLOATS + STAT_FLOATS + COL_FLOATS + ROW_INTS + INL_FLOATS) * 4 + 256 + 1024;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-template <int NT, int GS, bool ACC2, int CG>
+template <int NT, int GS, bool ACC2, int CG, bool TE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcP P) {
-    using C = Cfg<NT, GS, ACC2, CG>;
+    using C = Cfg<NT, GS, ACC2, CG, TE>;
     constexpr int G = C::G, NCH = C::NCH, NSTAGE = C::NSTAGE, NACC = C::NACC;
     const ConvP& p = P.e;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
-    float* tbuf = reinterpret_cast<float*>(smem + NSTAGE * C::STAGE_BYTES);
+    uint8_t* stg = smem + NSTAGE * C::STAGE_BYTES;   // TE staging tiles (1024-byte aligned)
+    float* tbuf = reinterpret_cast<float*>(stg + C::STG_BYTES);
     float* spart = tbuf + C::TBUF_FLOATS;
     float* sstat = spart + C::PART_FLOATS;
     float* scol = sstat + C::STAT_FLOATS;                 // bias | gamma | beta | bias2, NT each
@@ -131,11 +155,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.S, HJ = p.HJ, N = p.N;
-    const uint32_t bytesA = (uint32_t)(S * HJ * BK * 2);
+    constexpr int BKC = C::BKC, A_TILE = C::A_BYTES;
+    const uint32_t bytesA = (uint32_t)(S * HJ * BKC * 2);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&P.mA1h); prefetch_tmap(&P.mA1l); prefetch_tmap(&P.mW1h); prefetch_tmap(&P.mW1l);
         if (P.nkb2) { prefetch_tmap(&P.mA2h); prefetch_tmap(&P.mA2l); prefetch_tmap(&P.mW2h); prefetch_tmap(&P.mW2l); }
+        if (TE) {
+            if (p.yhat && p.gn_fwd) prefetch_tmap(&P.mSy);
+            if (p.out) prefetch_tmap(&P.mSo);
+            if (p.out_hi) { prefetch_tmap(&P.mSoh); prefetch_tmap(&P.mSol); }
+            if (p.gy) prefetch_tmap(&P.mSg);
+            if (p.gy_hi) { prefetch_tmap(&P.mSgh); prefetch_tmap(&P.mSgl); }
+        }
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         // tempty: the epilogues of both CTAs of a pair release the accumulator stage to the leader's MMA warp
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CG); }
@@ -185,31 +217,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int nb0 = n0 + (int)crank * (NT / CG);   // first B row staged by this CTA
                 const int nkb1 = p.ntaps[op] * P.kpt;
                 for (int kb = 0; kb < nkb1 + P.nkb2; ++kb) {
-                    const long long tw0 = P.ctr ? clock64() : 0;
+                    if (P.dbg & 16) break;   // diagnostics: MMA-only runs read whatever is in shared memory
+                    const long long tw0 = (P.ctr && P.tmode == 1) ? clock64() : 0;
                     mbar_wait(&empty[s], ph ^ 1);
-                    if (P.ctr) atomicAdd(P.ctr + 5, (unsigned long long)(clock64() - tw0));
+                    if (P.ctr && P.tmode == 1) atomicAdd(P.ctr + 5, (unsigned long long)(clock64() - tw0));
                     uint8_t* st = smem + s * C::STAGE_BYTES;
                     if (CG == 1 || crank == 0) mbar_expect_tx(&full[s], CG * (2 * bytesA + 2 * C::B_TILE_BYTES));
                     if (kb < nkb1) {
-                        const int tap = kb / P.kpt, c0 = (kb - tap * P.kpt) * BK;
+                        const int tap = kb / P.kpt, c0 = (kb - tap * P.kpt) * BKC;
                         const int sh = p.tap_shift[op][tap], wr = p.tap_k[op][tap] * N + nb0;
                         if (P.mode4d) {
                             // input row 2j + sh = parity (sh & 1) of pair j + floor(sh / 2)
                             const int par = sh & 1, js = (sh - par) >> 1;
                             ld4(st, &P.mA1h, &full[s], c0, par, js, r0);
-                            ld4(st + A_TILE_BYTES, &P.mA1l, &full[s], c0, par, js, r0);
+                            ld4(st + A_TILE, &P.mA1l, &full[s], c0, par, js, r0);
                         } else {
                             ld3(st, &P.mA1h, &full[s], c0, sh, r0);
-                            ld3(st + A_TILE_BYTES, &P.mA1l, &full[s], c0, sh, r0);
+                            ld3(st + A_TILE, &P.mA1l, &full[s], c0, sh, r0);
                         }
-                        ld2(st + 2 * A_TILE_BYTES, &P.mW1h, &full[s], c0, wr);
-                        ld2(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &P.mW1l, &full[s], c0, wr);
+                        ld2(st + 2 * A_TILE, &P.mW1h, &full[s], c0, wr);
+                        ld2(st + 2 * A_TILE + C::B_TILE_BYTES, &P.mW1l, &full[s], c0, wr);
                     } else {
-                        const int c0 = (kb - nkb1) * BK;
+                        const int c0 = (kb - nkb1) * BKC;
                         ld3(st, &P.mA2h, &full[s], c0, 0, r0);
-                        ld3(st + A_TILE_BYTES, &P.mA2l, &full[s], c0, 0, r0);
-                        ld2(st + 2 * A_TILE_BYTES, &P.mW2h, &full[s], c0, nb0);
-                        ld2(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &P.mW2l, &full[s], c0, nb0);
+                        ld3(st + A_TILE, &P.mA2l, &full[s], c0, 0, r0);
+                        ld2(st + 2 * A_TILE, &P.mW2h, &full[s], c0, nb0);
+                        ld2(st + 2 * A_TILE + C::B_TILE_BYTES, &P.mW2l, &full[s], c0, nb0);
                     }
                     if (++s == NSTAGE) { s = 0; ph ^= 1; }
                 }
@@ -219,8 +252,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // ============================== MMA issuer ==============================
         if (lane == 0 && crank == 0) {
             // instruction descriptor: D=F32, A=B=BF16, both K-major, N=NT, M=128 per CTA
-            const uint32_t idesc =
-                (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | (((128u * CG) >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                                   ((uint32_t)(((P.dbg & 32) && NT == 128 && !ACC2 ? 256 : NT) >> 3) << 17) |   // dbg 32: N=256 rate probe
+                                   (((128u * CG) >> 4) << 24);
             auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
                 if (CG == 2) tc_mma2(d, a, b, id, acc); else tc_mma(d, a, b, id, acc);
             };
@@ -229,29 +263,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             };
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
-            const long long tm0 = P.ctr ? clock64() : 0;
+            const long long tm0 = (P.ctr && P.tmode == 1) ? clock64() : 0;
             for (int tile = sched0; tile < nsched; tile += sched_step) {
-                const long long te0 = P.ctr ? clock64() : 0;
+                const long long te0 = (P.ctr && P.tmode == 1) ? clock64() : 0;
                 mbar_wait(&tempty[as], aph ^ 1);
-                if (P.ctr) atomicAdd(P.ctr + 1, (unsigned long long)(clock64() - te0));
+                if (P.ctr && P.tmode == 1) atomicAdd(P.ctr + 1, (unsigned long long)(clock64() - te0));
                 tc_fence_after();
                 const uint32_t d1 = tmem_base + (uint32_t)(as * C::ACC_COLS);
                 const uint32_t d2 = ACC2 ? d1 + NT : d1;
                 uint32_t acc1 = 0, acc2 = ACC2 ? 0u : 1u;
                 const int nkb1 = p.ntaps[tile % P.nphase] * P.kpt;
                 for (int kb = 0; kb < nkb1 + P.nkb2; ++kb) {
-                    const long long tf0 = P.ctr ? clock64() : 0;
-                    mbar_wait(&full[s], ph);
-                    if (P.ctr) atomicAdd(P.ctr + 0, (unsigned long long)(clock64() - tf0));
+                    const long long tf0 = (P.ctr && P.tmode == 1) ? clock64() : 0;
+                    if (!(P.dbg & 16)) mbar_wait(&full[s], ph);
+                    if (P.ctr && P.tmode == 1) atomicAdd(P.ctr + 0, (unsigned long long)(clock64() - tf0));
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
-                    const uint64_t ah = make_desc(sa), al = make_desc(sa + A_TILE_BYTES);
-                    const uint64_t bh = make_desc(sa + 2 * A_TILE_BYTES), bl = make_desc(sa + 2 * A_TILE_BYTES + C::B_TILE_BYTES);
+                    const uint64_t ah = make_desc<BKC>(sa), al = make_desc<BKC>(sa + A_TILE);
+                    const uint64_t bh = make_desc<BKC>(sa + 2 * A_TILE), bl = make_desc<BKC>(sa + 2 * A_TILE + C::B_TILE_BYTES);
                     const bool slab2 = kb >= nkb1;
-                    const uint32_t d = slab2 ? d2 : d1;
+                    const uint32_t d = (P.dbg & 32) ? tmem_base : (slab2 ? d2 : d1);
                     uint32_t accum = slab2 ? (ACC2 ? acc2 : 1u) : acc1;
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
+                    for (int k = 0; k < BKC / 16; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);   // 32 bytes per K=16 step, in 16-byte units
                         mma(d, ah + ko, bh + ko, idesc, accum);
                         mma(d, ah + ko, bl + ko, idesc, 1u);
@@ -259,13 +293,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         accum = 1u;
                     }
                     if (slab2) acc2 = 1u; else acc1 = 1u;
-                    commit(&empty[s]);   // frees the smem stage (of both CTAs) when these MMAs have read it
+                    if (!(P.dbg & 16)) commit(&empty[s]);   // frees the smem stage (of both CTAs) when these MMAs have read it
                     if (++s == NSTAGE) { s = 0; ph ^= 1; }
                 }
                 commit(&tfull[as]);      // accumulator complete
                 if (++as == NACC) { as = 0; aph ^= 1; }
             }
-            if (P.ctr) atomicAdd(P.ctr + 2, (unsigned long long)(clock64() - tm0));
+            if (P.ctr && P.tmode == 1) atomicAdd(P.ctr + 2, (unsigned long long)(clock64() - tm0));
         }
     } else {
         // ============================== epilogue (warps 2..9) ==============================
@@ -281,6 +315,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const float inv_cnt = 1.0f / (float)(HJ * (GS ? GS : 1));
         int as = 0;
         uint32_t aph = 0;
+        long long tlap = 0;
+        auto lap = [&](int k) {
+            if (P.ctr && P.tmode == 2 && etid == 0) {
+                const long long now = clock64();
+                atomicAdd(P.ctr + k, (unsigned long long)(now - tlap));
+                tlap = now;
+            }
+        };
+        // TE: staging tiles of this half of the epilogue warps and the thread that issues its bulk stores
+        uint8_t* const sF = stg + hf * C::STG_HALF_BYTES;
+        uint8_t* const sH = sF + 128 * 32 * 4;
+        uint8_t* const sL = sH + 128 * 32 * 2;
+        const bool st_leader = (etid & 127) == 0;
+        // free the staging tiles of this half (the bulk stores of the previous chunk have read them)
+        auto stage_acquire = [&]() {
+            if (st_leader) bulk_wait_read0();
+            half_bar(hf);
+        };
+        // make the staged rows visible to the TMA engine and write them out as boxes of the tile
+        auto stage_release = [&](const CUtensorMap* mf, const CUtensorMap* mh, const CUtensorMap* ml, int c0, int op, int r0) {
+            fence_async_smem();
+            half_bar(hf);
+            if (st_leader) {
+                if (p.ostride == 2) {
+                    if (mf) tma_store_4d(mf, sF, c0, op, 0, r0);
+                    if (mh) { tma_store_4d(mh, sH, c0, op, 0, r0); tma_store_4d(ml, sL, c0, op, 0, r0); }
+                } else {
+                    if (mf) tma_store_3d(mf, sF, c0, 0, r0);
+                    if (mh) { tma_store_3d(mh, sH, c0, 0, r0); tma_store_3d(ml, sL, c0, 0, r0); }
+                }
+                bulk_commit();
+            }
+        };
         for (int tile = sched0; tile < nsched; tile += sched_step) {
             const int op = tile % P.nphase, t2 = tile / P.nphase;
             const int r0 = ((t2 / P.tilesN) * CG + (int)crank) * S, n0 = (t2 % P.tilesN) * NT;
@@ -310,8 +377,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const size_t orow = valid ? (size_t)(r0 + s_loc) * p.Hout + (size_t)((mrow - s_loc * HJ) * p.ostride + op) : 0;
             const int slab0 = s_loc * G;
             const long long tq0 = (P.ctr && etid == 0) ? clock64() : 0;
+            if (P.ctr && P.tmode == 2 && etid == 0 && tlap) atomicAdd(P.ctr + 5, (unsigned long long)(tq0 - tlap));   // preamble
             mbar_wait(&tfull[as], aph);
             const long long tq1 = (P.ctr && etid == 0) ? clock64() : 0;
+            tlap = tq1;
+            if (P.ctr && P.tmode == 2 && etid == 0) atomicAdd(P.ctr + 0, (unsigned long long)(tq1 - tq0));
             tc_fence_after();
             epi_bar();
             if (P.dbg & 1) {
@@ -364,6 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         d[1] += s2[g];
                     }
                 }
+                lap(1);
                 epi_bar();
                 {
                     // slab (s, g): the 2*HJ row partials are summed by one thread in 4 independent
@@ -396,6 +467,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     if (s < Sv) p.rstd[(size_t)(r0 + s) * 8 + n0 / (GS ? GS : 1) + g] = rs;
                 }
                 epi_bar();
+                lap(2);
             }
 
             if (!(GS && p.gn_bwd)) {
@@ -425,7 +497,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             v[j] = (v[j] - mu[GPC2 > 1 ? j / (32 / GPC2) : 0]) * rsd[GPC2 > 1 ? j / (32 / GPC2) : 0];   // yhat
-                        if (valid && !(P.dbg & 2)) st_row32(p.yhat + orow * p.ldy + n0 + ch * 32, v);
+                        if (TE) {
+                            stage_acquire();
+                            stage_f32(sF, mrow, v);
+                        } else if (valid && !(P.dbg & 2)) {
+                            st_row32(p.yhat + orow * p.ldy + n0 + ch * 32, v);
+                        }
                         act_affine32(scol + NT + ch * 32, scol + 2 * NT + ch * 32, v, act);
                     }
                     if (ACC2) {
@@ -460,7 +537,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     if (eR && !(P.dbg & 8)) add_row32(eR + ch * 32, v);
                     if (idp && !(P.dbg & 4)) add_row32(idp + ch * 32, v);
                     if (adp && !(P.dbg & 4)) add_row32(adp + ch * 32, v);
-                    if (valid && !(P.dbg & 2)) {
+                    if (TE) {
+                        // with GroupNorm the fp32 tile carries yhat, so an fp32 copy of the result (only kept for
+                        // identity residuals / SIMT consumers) goes out directly; without it the tile is free
+                        const bool gnf = GS && p.gn_fwd;
+                        if (!gnf) stage_acquire();
+                        if (p.out) {
+                            if (gnf) { if (valid) st_row32(p.out + orow * p.ldo + n0 + ch * 32, v); }
+                            else stage_f32(sF, mrow, v);
+                        }
+                        if (p.out_hi) stage_planes(sH, sL, mrow, v);
+                        stage_release(gnf ? &P.mSy : (p.out ? &P.mSo : nullptr), p.out_hi ? &P.mSoh : nullptr, &P.mSol,
+                                      n0 + ch * 32, op, r0);
+                    } else if (valid && !(P.dbg & 2)) {
                         const size_t o = orow * p.ldo + n0 + ch * 32;
                         if (p.out) st_row32(p.out + o, v);
                         if (p.out_hi) st_planes32(p.out_hi + o, p.out_lo + o, v);
@@ -479,16 +568,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     tmem_ld32(tacc + ch * 32, v);
                     if (idp && !(P.dbg & 4)) add_row32(idp + ch * 32, v);
                     if (adp && !(P.dbg & 4)) add_row32(adp + ch * 32, v);
-                    if (valid && !(P.dbg & 2)) {
-                        const size_t o = orow * p.ldo + n0 + ch * 32;
-                        if (p.out) st_row32(p.out + o, v);
-                        if (p.out_hi) st_planes32(p.out_hi + o, p.out_lo + o, v);
-                    }
                     float y[32];
                     if (!(P.dbg & 4)) ld_row32(yp + ch * 32, y);
                     else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) y[j] = 0.5f;
+                    }
+                    if (TE) {
+                        if (p.out || p.out_hi) {
+                            stage_acquire();
+                            if (p.out) stage_f32(sF, mrow, v);
+                            if (p.out_hi) stage_planes(sH, sL, mrow, v);
+                            stage_release(p.out ? &P.mSo : nullptr, p.out_hi ? &P.mSoh : nullptr, &P.mSol, n0 + ch * 32, op, r0);
+                        }
+                    } else if (valid && !(P.dbg & 2)) {
+                        const size_t o = orow * p.ldo + n0 + ch * 32;
+                        if (p.out) st_row32(p.out + o, v);
+                        if (p.out_hi) st_planes32(p.out_hi + o, p.out_lo + o, v);
                     }
                     constexpr int GPC = (GS && GS < 32) ? 32 / GS : 1;
                     float q1[GPC], q2[GPC];
@@ -505,7 +601,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         q2[GPC > 1 ? j / (32 / GPC) : 0] += v[j] * y[j];
                     }
                     tmem_st32(tacc + ch * 32, v);
-                    tmem_st32(tstash + ch * 32, y);
+                    if (C::STASH) tmem_st32(tstash + ch * 32, y);
                     const int g0 = (ch * 32) / (GS ? GS : 1);
 #pragma unroll
                     for (int g = 0; g < GPC; ++g) {
@@ -515,6 +611,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     }
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                lap(1);
                 epi_bar();
                 if (etid < S * G) {
                     const int s = etid / G, g = etid - s * G;
@@ -540,11 +637,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     sstat[256 + etid] = (s < Sv) ? __ldg(p.rstd + (size_t)(r0 + s) * 8 + n0 / (GS ? GS : 1) + g) : 0.f;
                 }
                 epi_bar();
+                lap(2);
 #pragma unroll 1
                 for (int ch = hf; ch < NCH; ch += 2) {
                     float y[32];
                     tmem_ld32(tacc + ch * 32, v);
-                    tmem_ld32(tstash + ch * 32, y);
+                    if (C::STASH) {
+                        tmem_ld32(tstash + ch * 32, y);
+                    } else {
+                        ld_row32(yp + ch * 32, y);
+                        if (!valid) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) y[j] = 0.f;
+                        }
+                    }
                     constexpr int GPC3 = (GS && GS < 32) ? 32 / GS : 1;
                     float m1[GPC3], m2[GPC3], rsd[GPC3];
 #pragma unroll
@@ -557,7 +663,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         const int g = GPC3 > 1 ? j / (32 / GPC3) : 0;
                         v[j] = rsd[g] * (v[j] - m1[g] - y[j] * m2[g]);
                     }
-                    if (valid && !(P.dbg & 2)) {
+                    if (TE) {
+                        stage_acquire();
+                        if (p.gy) stage_f32(sF, mrow, v);
+                        if (p.gy_hi) stage_planes(sH, sL, mrow, v);
+                        stage_release(p.gy ? &P.mSg : nullptr, p.gy_hi ? &P.mSgh : nullptr, &P.mSgl, n0 + ch * 32, op, r0);
+                    } else if (valid && !(P.dbg & 2)) {
                         const size_t o = orow * p.ldg + n0 + ch * 32;
                         if (p.gy) st_row32(p.gy + o, v);
                         if (p.gy_hi) st_planes32(p.gy_hi + o, p.gy_lo + o, v);
@@ -565,18 +676,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 }
             }
             // release the accumulator stage
+            lap(3);
             tc_fence_before();
             epi_bar();
             if (etid == 0) {
                 if (CG == 2) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
             }
             if (P.ctr && etid == 0) {
-                atomicAdd(P.ctr + 3, (unsigned long long)(tq1 - tq0));
-                atomicAdd(P.ctr + 4, (unsigned long long)(clock64() - tq1));
+                if (P.tmode == 1) {
+                    atomicAdd(P.ctr + 3, (unsigned long long)(tq1 - tq0));
+                    atomicAdd(P.ctr + 4, (unsigned long long)(clock64() - tq1));
+                } else {
+                    lap(4);
+                }
                 atomicAdd(P.ctr + 6, 1ull);
             }
             if (++as == NACC) { as = 0; aph ^= 1; }
         }
+        if (TE && st_leader) bulk_wait_read0();   // shared memory stays valid until the last stores have read it
     }
 
     tc_fence_before();
@@ -614,56 +731,92 @@ using MapKey = std::tuple<const void*, int, int, int, int, int, int>;
 std::map<MapKey, CUtensorMap> g_maps;
 
 // activation plane [R][H][ld] BF16 -> 3-D map (C, H, R), box (64, H, S)
-int act_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int H, int R, int ld, int S) {
-    MapKey key(base, C, H, R, ld, S, 3);
+int act_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int H, int R, int ld, int S, int bk) {
+    MapKey key(base, C, H, R, ld, S, 3 + 100 * bk);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return 0; }
     EncodeFn enc = get_encode();
     PMP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)R};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)H};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)H, (cuuint32_t)S};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)H, (cuuint32_t)S};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation C=%d H=%d R=%d ld=%d S=%d) failed: %d", C, H, R, ld, S, (int)r);
     g_maps[key] = *out;
     return 0;
 }
 // stride-2 gather: rows (2j + parity) -> 4-D map (C, parity, H/2, R), box (64, 1, HJ, S)
-int act_map4(CUtensorMap* out, const __nv_bfloat16* base, int C, int Hin, int R, int ld, int S, int HJ) {
-    MapKey key(base, C, Hin, R, ld, S * 1000 + HJ, 4);
+int act_map4(CUtensorMap* out, const __nv_bfloat16* base, int C, int Hin, int R, int ld, int S, int HJ, int bk) {
+    MapKey key(base, C, Hin, R, ld, S * 1000 + HJ, 4 + 100 * bk);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return 0; }
     EncodeFn enc = get_encode();
     PMP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[4] = {(cuuint64_t)C, 2, (cuuint64_t)(Hin / 2), (cuuint64_t)R};
     cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 4, (cuuint64_t)ld * 2 * (cuuint64_t)Hin};
-    cuuint32_t box[4] = {(cuuint32_t)BK, 1, (cuuint32_t)HJ, (cuuint32_t)S};
+    cuuint32_t box[4] = {(cuuint32_t)bk, 1, (cuuint32_t)HJ, (cuuint32_t)S};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(strided activation C=%d H=%d R=%d ld=%d) failed: %d", C, Hin, R, ld, (int)r);
     g_maps[key] = *out;
     return 0;
 }
 // weight plane [taps*N][C] BF16 -> 2-D map (C, taps*N), box (64, NT)
-int w_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int rows, int NT) {
-    MapKey key(base, C, rows, NT, 0, 0, 2);
+int w_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int rows, int NT, int bk) {
+    MapKey key(base, C, rows, NT, 0, 0, 2 + 100 * bk);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return 0; }
     EncodeFn enc = get_encode();
     PMP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)NT};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)NT};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight C=%d rows=%d NT=%d) failed: %d", C, rows, NT, (int)r);
+    g_maps[key] = *out;
+    return 0;
+}
+
+// output tensor [R][Hout][ld] (fp32 or BF16) -> store map with box (32, HJ, S): 3-D (C, H, R) for unit output
+// stride, 4-D (C, phase, H/2, R) for the stride-2 scatter of the transposed convs
+int st_map(CUtensorMap* out, const void* base, bool f32, int C, int Hout, int R, int ld, int S, int HJ, int ostride) {
+    MapKey key(base, C, Hout, R, ld, S * 1000 + HJ, (f32 ? 10 : 20) + ostride);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+    EncodeFn enc = get_encode();
+    PMP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t es = f32 ? 4 : 2;
+    const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapSwizzle sw = f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r;
+    if (ostride == 1) {
+        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Hout, (cuuint64_t)R};
+        cuuint64_t strides[2] = {(cuuint64_t)ld * es, (cuuint64_t)ld * es * (cuuint64_t)Hout};
+        cuuint32_t box[3] = {32, (cuuint32_t)HJ, (cuuint32_t)S};
+        cuuint32_t el[3] = {1, 1, 1};
+        r = enc(out, dt, 3, const_cast<void*>(base), dims, strides, box, el, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t dims[4] = {(cuuint64_t)C, 2, (cuuint64_t)(Hout / 2), (cuuint64_t)R};
+        cuuint64_t strides[3] = {(cuuint64_t)ld * es, (cuuint64_t)ld * es * 2, (cuuint64_t)ld * es * (cuuint64_t)Hout};
+        cuuint32_t box[4] = {32, 1, (cuuint32_t)HJ, (cuuint32_t)S};
+        cuuint32_t el[4] = {1, 1, 1, 1};
+        r = enc(out, dt, 4, const_cast<void*>(base), dims, strides, box, el, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    PMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(store C=%d H=%d R=%d ld=%d S=%d HJ=%d) failed: %d", C, Hout, R, ld, S,
+                HJ, (int)r);
     g_maps[key] = *out;
     return 0;
 }
@@ -686,12 +839,12 @@ unsigned long long* tc_timer_buffer() {
 }
 namespace {
 
-template <int NT, int GS, bool ACC2, int CG>
+template <int NT, int GS, bool ACC2, int CG, bool TE>
 int launch_t(TcP& P, cudaStream_t st) {
-    using C = Cfg<NT, GS, ACC2, CG>;
+    using C = Cfg<NT, GS, ACC2, CG, TE>;
     static bool configured = false;
     if (!configured) {
-        PMP_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NT, GS, ACC2, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PMP_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NT, GS, ACC2, CG, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES));
         configured = true;
     }
@@ -702,7 +855,7 @@ int launch_t(TcP& P, cudaStream_t st) {
     }
     if (CG == 1) {
         const int grid = P.ntiles < g_num_sms ? P.ntiles : g_num_sms;
-        conv_tc_kernel<NT, GS, ACC2, CG><<<grid, TC_THREADS, C::SMEM_BYTES, st>>>(P);
+        conv_tc_kernel<NT, GS, ACC2, CG, TE><<<grid, TC_THREADS, C::SMEM_BYTES, st>>>(P);
     } else {
         // one cluster of two CTAs (the two SMs of a TPC) per tile pair, persistent over the pairs
         const int nclusters = P.npairs < g_num_sms / 2 ? P.npairs : g_num_sms / 2;
@@ -719,21 +872,22 @@ int launch_t(TcP& P, cudaStream_t st) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        PMP_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NT, GS, ACC2, CG>, P));
+        PMP_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NT, GS, ACC2, CG, TE>, P));
     }
     PMP_LAUNCH_OK();
     return 0;
 }
 
-int pick_nt(const ConvP& p) {
+int pick_nt(const ConvP& p, bool wide = false) {
     const bool gn = p.gn_fwd || p.gn_bwd;
     if (gn) {
         const int gs = p.N / 8;
         if (gs == 8) return 64;
-        if (gs == 32 || gs == 64) return 128;
+        if (gs == 32 || gs == 64) return wide ? 256 : 128;
         if (gs == 96) return 192;
         return 0;
     }
+    if (wide && p.N % 256 == 0) return 256;
     if (p.N % 128 == 0) return 128;
     if (p.N % 64 == 0 || p.N < 64) return 64;
     return 0;
@@ -765,29 +919,37 @@ bool conv_tc_eligible(const ConvP& p) {
     return true;
 }
 
-// CTA pairs pay off where the main loop dominates (NT >= 128); the narrow level-0 tiles and the inline
-// small-K convolutions stay on single CTAs
-static bool pair_ok(const ConvP& p, int NT) {
-    if (NT < 128) return false;
-    if (p.inl_x) return false;
-    return true;
-}
-
-static int launch_conv_tc_cg(const ConvP& p, cudaStream_t st, int cg) {
+// mode 3 (gemm path 3): TMA-store epilogue, on CTA pairs (cta_group::2) for the 128-channel tiles -- the pair
+// halves the B operand staged per CTA, which frees the shared memory the staging tiles need; the narrow
+// level-0 tiles (NT = 64) keep single CTAs; the 192-channel tiles (Dual Kuka) use pairs with the direct epilogue
+static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     if (!conv_tc_eligible(p)) return 1;
     TcP P;
     memset(&P, 0, sizeof P);
     P.e = p;
-    const int NT = pick_nt(p);
-    if (cg == 2 && !pair_ok(p, NT)) cg = 1;
+    const bool inl_pre = p.inl_x && p.inl_mode == 1, inl_post = p.inl_x && p.inl_mode == 2;
+    const bool acc2 = (p.A2 != nullptr) && !inl_post && (p.bias2 != nullptr || p.gn_fwd);
+    // 256-column tiles (CTA pairs only) feed the tensor pipe best; a separate second accumulator does not fit next to them
+    const int NT = pick_nt(p, mode == 3 && !acc2 && !p.inl_x);
+    const int cg = (mode == 3 && NT >= 128 && !p.inl_x) ? 2 : 1;
+    const bool te = mode == 3 && (NT == 64 || ((NT == 128 || NT == 256) && cg == 2)) && p.N >= 64;
     const int S = 128 / p.HJ;
     P.e.S = S;
     P.tilesM = (p.R + S - 1) / S;
     P.tilesN = (p.N + NT - 1) / NT;
-    const bool inl_pre = p.inl_x && p.inl_mode == 1, inl_post = p.inl_x && p.inl_mode == 2;
     P.nphase = p.nphase;
     P.mode4d = p.istride == 2 ? 1 : 0;
     P.ctr = tc_timer_buffer();
+    if (P.ctr) {
+        // PMP_TC_TIMERS=1|2, optional PMP_TC_TIMER_MATCH="N:C1:g" (g = gn_fwd + 2*gn_bwd) restricts the timers to one shape
+        static int tmode = 0, mN = -1, mC = -1, mG = -1;
+        if (!tmode) {
+            tmode = atoi(getenv("PMP_TC_TIMERS"));
+            if (const char* e = getenv("PMP_TC_TIMER_MATCH")) sscanf(e, "%d:%d:%d", &mN, &mC, &mG);
+        }
+        P.tmode = tmode;
+        if (mN >= 0 && (p.N != mN || p.C1 != mC || (p.gn_fwd + 2 * p.gn_bwd) != mG)) P.ctr = nullptr;
+    }
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("PMP_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -795,57 +957,80 @@ static int launch_conv_tc_cg(const ConvP& p, cudaStream_t st, int cg) {
     }
     P.ntiles = P.tilesM * P.tilesN * P.nphase;
     P.npairs = ((P.tilesM + 1) / 2) * P.tilesN * P.nphase;
-    P.kpt = inl_pre ? 0 : p.C1 / BK;
-    P.nkb2 = (p.A2 && !inl_post) ? p.C2 / BK : 0;
+    const int bk = NT == 256 ? 32 : 64;   // Cfg::BKC
+    P.kpt = inl_pre ? 0 : p.C1 / bk;
+    P.nkb2 = (p.A2 && !inl_post) ? p.C2 / bk : 0;
     const int brows = NT / cg;   // B rows staged per CTA
     int rc;
     if (!inl_pre) {
         if (P.mode4d) {
-            if ((rc = act_map4(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S, p.HJ))) return rc;
-            if ((rc = act_map4(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S, p.HJ))) return rc;
+            if ((rc = act_map4(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S, p.HJ, bk))) return rc;
+            if ((rc = act_map4(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S, p.HJ, bk))) return rc;
         } else {
-            if ((rc = act_map(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S))) return rc;
-            if ((rc = act_map(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S))) return rc;
+            if ((rc = act_map(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S, bk))) return rc;
+            if ((rc = act_map(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S, bk))) return rc;
         }
         int maxk = 0;
         for (int ph = 0; ph < p.nphase; ++ph)
             for (int t = 0; t < p.ntaps[ph]; ++t) maxk = p.tap_k[ph][t] > maxk ? p.tap_k[ph][t] : maxk;
-        if ((rc = w_map(&P.mW1h, p.W1_hi, p.C1, (maxk + 1) * p.N, brows))) return rc;
-        if ((rc = w_map(&P.mW1l, p.W1_lo, p.C1, (maxk + 1) * p.N, brows))) return rc;
+        if ((rc = w_map(&P.mW1h, p.W1_hi, p.C1, (maxk + 1) * p.N, brows, bk))) return rc;
+        if ((rc = w_map(&P.mW1l, p.W1_lo, p.C1, (maxk + 1) * p.N, brows, bk))) return rc;
     }
     if (p.A2 && !inl_post) {
-        if ((rc = act_map(&P.mA2h, p.A2_hi, p.C2, p.Hin, p.R, p.lda2, S))) return rc;
-        if ((rc = act_map(&P.mA2l, p.A2_lo, p.C2, p.Hin, p.R, p.lda2, S))) return rc;
-        if ((rc = w_map(&P.mW2h, p.W2_hi, p.C2, p.N, brows))) return rc;
-        if ((rc = w_map(&P.mW2l, p.W2_lo, p.C2, p.N, brows))) return rc;
+        if ((rc = act_map(&P.mA2h, p.A2_hi, p.C2, p.Hin, p.R, p.lda2, S, bk))) return rc;
+        if ((rc = act_map(&P.mA2l, p.A2_lo, p.C2, p.Hin, p.R, p.lda2, S, bk))) return rc;
+        if ((rc = w_map(&P.mW2h, p.W2_hi, p.C2, p.N, brows, bk))) return rc;
+        if ((rc = w_map(&P.mW2l, p.W2_lo, p.C2, p.N, brows, bk))) return rc;
+    }
+    if (te) {
+        const int os = p.ostride;
+        if (p.yhat && p.gn_fwd && (rc = st_map(&P.mSy, p.yhat, true, p.N, p.Hout, p.R, p.ldy, S, p.HJ, os))) return rc;
+        if (p.out && (rc = st_map(&P.mSo, p.out, true, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os))) return rc;
+        if (p.out_hi) {
+            if ((rc = st_map(&P.mSoh, p.out_hi, false, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os))) return rc;
+            if ((rc = st_map(&P.mSol, p.out_lo, false, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os))) return rc;
+        }
+        if (p.gy && (rc = st_map(&P.mSg, p.gy, true, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os))) return rc;
+        if (p.gy_hi) {
+            if ((rc = st_map(&P.mSgh, p.gy_hi, false, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os))) return rc;
+            if ((rc = st_map(&P.mSgl, p.gy_lo, false, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os))) return rc;
+        }
     }
     const bool gn = p.gn_fwd || p.gn_bwd;
-    const bool acc2 = (p.A2 != nullptr) && !inl_post && (p.bias2 != nullptr || p.gn_fwd);
     const int gs = gn ? p.N / 8 : 0;
+    if (NT == 256) {
+        if (gs == 32) return launch_t<256, 32, false, 2, true>(P, st);
+        if (gs == 64) return launch_t<256, 64, false, 2, true>(P, st);
+        return launch_t<256, 0, false, 2, true>(P, st);
+    }
     if (NT == 64) {
-        if (gs == 8) return acc2 ? launch_t<64, 8, true, 1>(P, st) : launch_t<64, 8, false, 1>(P, st);
-        return acc2 ? launch_t<64, 0, true, 1>(P, st) : launch_t<64, 0, false, 1>(P, st);
+        if (te) {
+            if (gs == 8) return acc2 ? launch_t<64, 8, true, 1, true>(P, st) : launch_t<64, 8, false, 1, true>(P, st);
+            return acc2 ? launch_t<64, 0, true, 1, true>(P, st) : launch_t<64, 0, false, 1, true>(P, st);
+        }
+        if (gs == 8) return acc2 ? launch_t<64, 8, true, 1, false>(P, st) : launch_t<64, 8, false, 1, false>(P, st);
+        return acc2 ? launch_t<64, 0, true, 1, false>(P, st) : launch_t<64, 0, false, 1, false>(P, st);
     }
     if (cg == 2) {
         if (NT == 128) {
-            if (gs == 32) return acc2 ? launch_t<128, 32, true, 2>(P, st) : launch_t<128, 32, false, 2>(P, st);
-            if (gs == 64) return acc2 ? launch_t<128, 64, true, 2>(P, st) : launch_t<128, 64, false, 2>(P, st);
-            return acc2 ? launch_t<128, 0, true, 2>(P, st) : launch_t<128, 0, false, 2>(P, st);
+            if (gs == 32) return acc2 ? launch_t<128, 32, true, 2, true>(P, st) : launch_t<128, 32, false, 2, true>(P, st);
+            if (gs == 64) return acc2 ? launch_t<128, 64, true, 2, true>(P, st) : launch_t<128, 64, false, 2, true>(P, st);
+            return acc2 ? launch_t<128, 0, true, 2, true>(P, st) : launch_t<128, 0, false, 2, true>(P, st);
         }
-        if (NT == 192) return acc2 ? launch_t<192, 96, true, 2>(P, st) : launch_t<192, 96, false, 2>(P, st);
+        if (NT == 192) return acc2 ? launch_t<192, 96, true, 2, false>(P, st) : launch_t<192, 96, false, 2, false>(P, st);
         return 1;
     }
     if (NT == 128) {
-        if (gs == 32) return acc2 ? launch_t<128, 32, true, 1>(P, st) : launch_t<128, 32, false, 1>(P, st);
-        if (gs == 64) return acc2 ? launch_t<128, 64, true, 1>(P, st) : launch_t<128, 64, false, 1>(P, st);
-        return acc2 ? launch_t<128, 0, true, 1>(P, st) : launch_t<128, 0, false, 1>(P, st);
+        if (gs == 32) return acc2 ? launch_t<128, 32, true, 1, false>(P, st) : launch_t<128, 32, false, 1, false>(P, st);
+        if (gs == 64) return acc2 ? launch_t<128, 64, true, 1, false>(P, st) : launch_t<128, 64, false, 1, false>(P, st);
+        return acc2 ? launch_t<128, 0, true, 1, false>(P, st) : launch_t<128, 0, false, 1, false>(P, st);
     }
-    if (NT == 192) return acc2 ? launch_t<192, 96, true, 1>(P, st) : launch_t<192, 96, false, 1>(P, st);
+    if (NT == 192) return acc2 ? launch_t<192, 96, true, 1, false>(P, st) : launch_t<192, 96, false, 1, false>(P, st);
     return 1;
 }
 
-int launch_conv_tc(const ConvP& p, cudaStream_t st) { return launch_conv_tc_cg(p, st, 1); }
-// CTA-pair main loop (cta_group::2) where it applies, single-CTA kernel otherwise
-int launch_conv_tc_pair(const ConvP& p, cudaStream_t st) { return launch_conv_tc_cg(p, st, 2); }
+int launch_conv_tc(const ConvP& p, cudaStream_t st) { return launch_conv_tc_mode(p, st, 1); }
+// gemm path 3: CTA pairs + TMA-store epilogue where they apply, the single-CTA kernel otherwise
+int launch_conv_tc_pair(const ConvP& p, cudaStream_t st) { return launch_conv_tc_mode(p, st, 3); }
 
 }  // namespace pmp

@@ -130,9 +130,57 @@ __device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
-// K-major, 128-byte swizzle, rows of 64 BF16: 8-row groups 1024 B apart (SBO = 64 x 16 B), LBO = 1
+// ---- TMA-store epilogue: results are staged in shared memory in the layout of a swizzled TMA box
+// ([rows][32 columns]; fp32 rows of 128 B with SWIZZLE_128B, BF16 rows of 64 B with SWIZZLE_64B) and
+// written out by bulk tensor stores, so the LSU only sees conflict-free st.shared and global memory only
+// sees whole 128-byte lines.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores committed by this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy shared-memory writes of this thread become visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void half_bar(int hf) { asm volatile("bar.sync %0, 128;" ::"r"(2 + hf) : "memory"); }
+// row r (0..127) of a [128][32] fp32 staging tile, SWIZZLE_128B: 16-byte chunk c sits at c ^ (r & 7)
+__device__ __forceinline__ void stage_f32(uint8_t* tile, int r, const float (&v)[32]) {
+    uint8_t* row = tile + r * 128;
+    const int x = r & 7;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(row + ((c ^ x) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+// row r of two [128][32] BF16 staging tiles (hi / lo planes), SWIZZLE_64B: chunk c sits at c ^ ((r >> 1) & 3)
+__device__ __forceinline__ void stage_planes(uint8_t* thi, uint8_t* tlo, int r, const float (&v)[32]) {
+    uint8_t* rh = thi + r * 64;
+    uint8_t* rl = tlo + r * 64;
+    const int x = (r >> 1) & 3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) split_bf16x2(v[8 * c + 2 * k], v[8 * c + 2 * k + 1], h[k], l[k]);
+        *reinterpret_cast<uint4*>(rh + ((c ^ x) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(rl + ((c ^ x) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+// K-major operand tile descriptors.  BKC = 64: rows of 64 BF16 = 128 bytes, SWIZZLE_128B, 8-row groups 1024 B
+// apart (SBO = 64 x 16 B); BKC = 32: rows of 64 bytes, SWIZZLE_64B, 8-row groups 512 B apart.  LBO = 1 (unused).
+template <int BKC = 64>
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+    constexpr uint64_t sbo = BKC == 64 ? 64ull : 32ull;
+    constexpr uint64_t layout = BKC == 64 ? 2ull : 4ull;
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
