@@ -145,7 +145,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=int(os.environ.get("PMP_BENCH_BATCH", "3700")),
                     help="plans per step per GPU")
-    ap.add_argument("--row-chunk", type=int, default=int(os.environ.get("PMP_ROW_CHUNK", "4096")))
+    ap.add_argument("--row-chunk", type=int, default=int(os.environ.get("PMP_ROW_CHUNK", "8192")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -84,8 +84,10 @@ int pmp_model_set_weight(pmp_model *m, const char *key, const float *data,
 int pmp_model_finalize(pmp_model *m);
 /* rows of the CFG batch processed per pass through the U-Net (bounds the workspace). */
 int pmp_model_set_row_chunk(pmp_model *m, int rows);
-/* 0: fp32 CUDA-core implicit GEMM everywhere; 1: tcgen05 BF16x3 tensor-core path where the
- * shape allows (default = best available). */
+/* 0: fp32 CUDA-core implicit GEMM everywhere; 1: tcgen05 BF16x3 tensor-core path (single CTA per
+ * tile, direct epilogue stores); 2: operand-reuse variant of 1; 3 (default): tcgen05 BF16x3 on CTA
+ * pairs (cta_group::2, 256-column tiles) with the TMA-store epilogue.  1-3 fall back per op to the
+ * next simpler kernel where a shape does not fit; all tensor-core paths give bit-identical results. */
 int pmp_model_set_gemm_path(pmp_model *m, int path);
 size_t pmp_model_workspace_bytes(const pmp_model *m);
 

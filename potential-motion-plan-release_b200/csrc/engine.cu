@@ -143,7 +143,7 @@ struct pmp_model {
     float* hidb = nullptr; size_t hidb_n = 0;   // cfg3 per step hidden [R][nblk*hid]
     float* ws = nullptr; size_t ws_n = 0;       // activation workspace (floats)
     int row_chunk = 2048;
-    int gemm_path = 1;
+    int gemm_path = 3;   // 0 fp32 SIMT, 1 tcgen05 single CTA, 2 operand reuse, 3 CTA pairs + TMA-store epilogue (default)
     std::map<std::string, std::pair<float*, int64_t>> dbg;
     bool has_down(int L) const { return !(L >= nl - 1 || L >= arch.down_times); }
     bool has_up(int ind) const { return !(ind >= nl - 1 || ind < (nl - arch.down_times - 1)); }

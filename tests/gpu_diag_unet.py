@@ -37,8 +37,8 @@ def main(fams):
         eps_ag = unet_ref.eps_autograd(sd, cfg, x, t, walls, n_cond=B)
         print("[%s] oracle %.2fs  analytic-vs-autograd %.2e" % (fam, time.time() - t0, rel(eps_ref, eps_ag)))
         eng = pmp_b200.UnetEngine(a["unet"], sd, dev)
-        eng.set_gemm_path(int(os.environ.get("PMP_GEMM_PATH", "1")))
-        print("  gemm path", os.environ.get("PMP_GEMM_PATH", "1"))
+        eng.set_gemm_path(int(os.environ.get("PMP_GEMM_PATH", "3")))
+        print("  gemm path", os.environ.get("PMP_GEMM_PATH", "3"))
         wemb = eng.wall_embed(torch.tensor(pr["walls"]))
         wemb_ref = unet_ref.wall_embed(sd, cfg, torch.tensor(pr["walls"]))
         print("  wall_embed rel err %.3e" % rel(wemb.cpu().numpy(), wemb_ref.numpy()))

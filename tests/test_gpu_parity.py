@@ -98,7 +98,7 @@ def test_gemm_paths_agree(fam):
             eng.set_gemm_path(path)
             out[path] = eng.eps(x.to(DEV), t.to(DEV), wemb, n_cond=B).cpu().numpy()
     finally:
-        eng.set_gemm_path(1)
+        eng.set_gemm_path(3)
     scale = np.abs(ref).max()
     assert np.abs(out[0] - ref).max() <= 2e-5 * scale, "fp32 path"
     for path in (1, 2, 3):
