@@ -123,6 +123,9 @@ struct ConvP {
     int eoff;
     // residual / skip terms
     const float* ident; int ldi;    // + ident[row][n]
+    // the same term given as BF16x3 planes (hi + lo, same [row][ldi] indexing) when the producer kept no fp32
+    // copy (tcgen05 paths 1 and 3 only)
+    const __nv_bfloat16* ident_hi; const __nv_bfloat16* ident_lo;
     const float* addend; int ldad;  // + addend[row][n]
     float* out; int ldo;            // result after all adds (may be null)
     float* gy; int ldg;             // gn_bwd result

@@ -480,6 +480,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const float* eT = p.embT ? p.embT + (size_t)tt * p.ldeT + p.eoff + n0 : nullptr;
                 const float* eR = (p.embR && valid && rg < p.n_cond) ? p.embR + (size_t)rg * p.ldeR + p.eoff + n0 : nullptr;
                 const float* idp = p.ident ? p.ident + orow * p.ldi + n0 : nullptr;
+                const __nv_bfloat16* idh = p.ident_hi ? p.ident_hi + orow * p.ldi + n0 : nullptr;
+                const __nv_bfloat16* idl = p.ident_hi ? p.ident_lo + orow * p.ldi + n0 : nullptr;
                 const float* adp = p.addend ? p.addend + orow * p.ldad + n0 : nullptr;
 #pragma unroll 1
                 for (int ch = hf; ch < NCH; ch += 2) {
@@ -536,6 +538,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     if (eT && !(P.dbg & 8)) add_row32(eT + ch * 32, v);
                     if (eR && !(P.dbg & 8)) add_row32(eR + ch * 32, v);
                     if (idp && !(P.dbg & 4)) add_row32(idp + ch * 32, v);
+                    if (idh && !(P.dbg & 4)) add_planes32(idh + ch * 32, idl + ch * 32, v);
                     if (adp && !(P.dbg & 4)) add_row32(adp + ch * 32, v);
                     if (TE) {
                         // with GroupNorm the fp32 tile carries yhat, so an fp32 copy of the result (only kept for
@@ -561,12 +564,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 // back over the accumulator and yhat is stashed in spare TMEM columns, so pass 1
                 // (after the slab means are known) touches no global input again.
                 const float* idp = p.ident ? p.ident + orow * p.ldi + n0 : nullptr;
+                const __nv_bfloat16* idh = p.ident_hi ? p.ident_hi + orow * p.ldi + n0 : nullptr;
+                const __nv_bfloat16* idl = p.ident_hi ? p.ident_lo + orow * p.ldi + n0 : nullptr;
                 const float* adp = p.addend ? p.addend + orow * p.ldad + n0 : nullptr;
                 const float* yp = p.yhat + orow * p.ldy + n0;
 #pragma unroll 1
                 for (int ch = hf; ch < NCH; ch += 2) {
                     tmem_ld32(tacc + ch * 32, v);
                     if (idp && !(P.dbg & 4)) add_row32(idp + ch * 32, v);
+                    if (idh && !(P.dbg & 4)) add_planes32(idh + ch * 32, idl + ch * 32, v);
                     if (adp && !(P.dbg & 4)) add_row32(adp + ch * 32, v);
                     float y[32];
                     if (!(P.dbg & 4)) ld_row32(yp + ch * 32, y);
@@ -899,7 +905,7 @@ bool conv_tc_eligible(const ConvP& p) {
     const bool s2 = p.nphase == 1 && p.istride == 2 && p.ostride == 1;             // stride-2 gather
     const bool t2 = p.nphase == 2 && p.istride == 1 && p.ostride == 2;             // stride-2 scatter (2 phases)
     if (!s1 && !s2 && !t2) return false;
-    if (!s1 && p.A2) return false;
+    if (!s1 && (p.A2 || p.A2_hi)) return false;
     if (t2 && (p.gn_fwd || p.gn_bwd)) return false;
     if (s2 && (p.Hin & 1)) return false;
     const bool inl_pre = p.inl_x && p.inl_mode == 1, inl_post = p.inl_x && p.inl_mode == 2;
@@ -908,10 +914,10 @@ bool conv_tc_eligible(const ConvP& p) {
         if (!p.A1_hi || !p.A1_lo || !p.W1_hi || !p.W1_lo) return false;
         if (p.C1 % BK != 0 || (p.lda1 % 8) != 0) return false;
     }
-    if (p.A2 && !inl_post &&
+    if ((p.A2 || p.A2_hi) && !inl_post &&
         (!p.A2_hi || !p.A2_lo || !p.W2_hi || !p.W2_lo || p.C2 % BK != 0 || (p.lda2 % 8) != 0))
         return false;
-    if (p.N < 64 && (p.gn_fwd || p.gn_bwd || p.out_hi || p.embT || p.embR || !s1)) return false;
+    if (p.N < 64 && (p.gn_fwd || p.gn_bwd || p.out_hi || p.embT || p.embR || p.ident_hi || !s1)) return false;
     if (p.HJ < 8 || p.HJ > 128 || p.HJ > 256) return false;
     const int nt = pick_nt(p);
     if (!nt || (p.N % nt != 0 && p.N >= 64)) return false;
@@ -928,7 +934,7 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     memset(&P, 0, sizeof P);
     P.e = p;
     const bool inl_pre = p.inl_x && p.inl_mode == 1, inl_post = p.inl_x && p.inl_mode == 2;
-    const bool acc2 = (p.A2 != nullptr) && !inl_post && (p.bias2 != nullptr || p.gn_fwd);
+    const bool acc2 = (p.A2 != nullptr || p.A2_hi != nullptr) && !inl_post && (p.bias2 != nullptr || p.gn_fwd);
     // 256-column tiles (CTA pairs only) feed the tensor pipe best; a separate second accumulator does not fit next to them
     const int NT = pick_nt(p, mode == 3 && !acc2 && !p.inl_x);
     const int cg = (mode == 3 && NT >= 128 && !p.inl_x) ? 2 : 1;
@@ -959,7 +965,7 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     P.npairs = ((P.tilesM + 1) / 2) * P.tilesN * P.nphase;
     const int bk = NT == 256 ? 32 : 64;   // Cfg::BKC
     P.kpt = inl_pre ? 0 : p.C1 / bk;
-    P.nkb2 = (p.A2 && !inl_post) ? p.C2 / bk : 0;
+    P.nkb2 = ((p.A2 || p.A2_hi) && !inl_post) ? p.C2 / bk : 0;
     const int brows = NT / cg;   // B rows staged per CTA
     int rc;
     if (!inl_pre) {
@@ -976,7 +982,7 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
         if ((rc = w_map(&P.mW1h, p.W1_hi, p.C1, (maxk + 1) * p.N, brows, bk))) return rc;
         if ((rc = w_map(&P.mW1l, p.W1_lo, p.C1, (maxk + 1) * p.N, brows, bk))) return rc;
     }
-    if (p.A2 && !inl_post) {
+    if ((p.A2 || p.A2_hi) && !inl_post) {
         if ((rc = act_map(&P.mA2h, p.A2_hi, p.C2, p.Hin, p.R, p.lda2, S, bk))) return rc;
         if ((rc = act_map(&P.mA2l, p.A2_lo, p.C2, p.Hin, p.R, p.lda2, S, bk))) return rc;
         if ((rc = w_map(&P.mW2h, p.W2_hi, p.C2, p.N, brows, bk))) return rc;

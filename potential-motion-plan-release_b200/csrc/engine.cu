@@ -42,7 +42,7 @@ static double conv_flops(const ConvP& p) {
     double k = 0;
     for (int ph = 0; ph < p.nphase; ++ph) k += (double)p.ntaps[ph] * p.C1;
     k /= p.nphase;   // each output row belongs to exactly one phase
-    if (p.A2) k += p.C2;
+    if (p.A2 || p.A2_hi) k += p.C2;
     return 2.0 * (double)p.R * p.Hout * p.N * k;
 }
 static int prof_launch_conv(const ConvP& p, cudaStream_t st, int cls, int (*fn)(const ConvP&, cudaStream_t)) {
@@ -58,9 +58,9 @@ static int prof_launch_conv(const ConvP& p, cudaStream_t st, int cls, int (*fn)(
     PMP_CUDA_OK(cudaEventRecord(ev.first, st));
     int rc = fn(p, st);
     PMP_CUDA_OK(cudaEventRecord(ev.second, st));
-    g_prof.push_back(ProfRec{ev.first, ev.second, conv_flops(p), cls, p.R, p.Hout, p.N, p.C1, p.A2 ? p.C2 : 0,
+    g_prof.push_back(ProfRec{ev.first, ev.second, conv_flops(p), cls, p.R, p.Hout, p.N, p.C1, (p.A2 || p.A2_hi) ? p.C2 : 0,
                              p.ntaps[0] + (p.nphase > 1 ? p.ntaps[1] : 0),
-                             p.gn_fwd | (p.gn_bwd << 1) | ((p.ident != nullptr) << 2) | ((p.istride > 1) << 3) | ((p.ostride > 1) << 4)});
+                             p.gn_fwd | (p.gn_bwd << 1) | ((p.ident != nullptr || p.ident_hi != nullptr) << 2) | ((p.istride > 1) << 3) | ((p.ostride > 1) << 4)});
     return rc;
 }
 
@@ -75,6 +75,7 @@ struct Act {
     float* p = nullptr;
     int ld = 0, C = 0, Hl = 0;
     int blk = -1;  // residual block that produced it (its CB1 GroupNorm must be differentiated), -1: none
+    bool grad_f32 = false;   // its gradient is also consumed in fp32 (standalone GroupNorm backward / skip addend)
 };
 struct Grad {
     float* raw = nullptr;
@@ -143,6 +144,7 @@ struct pmp_model {
     float* hidb = nullptr; size_t hidb_n = 0;   // cfg3 per step hidden [R][nblk*hid]
     float* ws = nullptr; size_t ws_n = 0;       // activation workspace (floats)
     int row_chunk = 2048;
+    bool keep_fp32 = getenv("PMP_KEEP_FP32") != nullptr;   // diagnostics: fp32 copies of every activation / gradient
     int gemm_path = 3;   // 0 fp32 SIMT, 1 tcgen05 single CTA, 2 operand reuse, 3 CTA pairs + TMA-store epilogue (default)
     std::map<std::string, std::pair<float*, int64_t>> dbg;
     bool has_down(int L) const { return !(L >= nl - 1 || L >= arch.down_times); }
@@ -604,10 +606,17 @@ struct Ctx {
             rc = prof_launch_conv(p, st, 1, m->gemm_path == 3 ? launch_conv_tc_pair : launch_conv_tc);
             return;
         }
+        if ((!p.A1 && !p.inl_x) || (p.A2_hi && !p.A2) || (p.ident_hi && !p.ident)) {
+            // planes-only tensors are produced only where every consumer runs on the tensor-core kernel
+            set_error("internal: op (N=%d C1=%d H=%d) has BF16-plane-only operands but does not fit the tcgen05 kernel", p.N,
+                      p.C1, p.Hout);
+            rc = PMP_ERR_ARG;
+            return;
+        }
         rc = prof_launch_conv(p, st, 0, launch_conv_simt);
     }
     void dbg(const char* kind, const std::string& name, float* p, int64_t n) {
-        if (!dry) m->dbg[std::string(kind) + name] = std::make_pair(p, n);
+        if (!dry && p) m->dbg[std::string(kind) + name] = std::make_pair(p, n);
     }
 };
 
@@ -624,15 +633,19 @@ struct GradP {
     bf16 *gy_hi = nullptr, *gy_lo = nullptr;
 };
 
+// tensor consumed only as the A operand of a tensor-core conv: BF16 planes suffice (no fp32 copy)
+static bool planes_only(const Ctx& c, int C) { return c.tc() && (C % 64) == 0 && c.H <= 128; }
+// on gemm paths 1 and 3 the epilogue also takes residual terms as planes, so no activation or gradient between
+// 64-multiple-channel convs needs an fp32 copy at all (path 2's kernel still reads fp32 residuals)
+static bool planes_all(const Ctx& c, int C) { return planes_only(c, C) && c.m->gemm_path != 2 && !c.m->keep_fp32; }
+
 static ActP new_act(Ctx& c, int C, int Hl) {
     ActP a;
-    a.p = c.alloc((size_t)c.R * Hl * C);
+    a.p = planes_all(c, C) ? nullptr : c.alloc((size_t)c.R * Hl * C);
     c.planes((size_t)c.R * Hl * C, &a.hi, &a.lo);
     a.ld = C; a.C = C; a.Hl = Hl; a.blk = -1;
     return a;
 }
-// tensor consumed only as the A operand of a tensor-core conv: BF16 planes suffice (no fp32 copy)
-static bool planes_only(const Ctx& c, int C) { return c.tc() && (C % 64) == 0 && c.H <= 128; }
 
 static ActP view_act(const ActP& base, int off, int C) {
     ActP a = base;
@@ -707,6 +720,7 @@ static void res_fwd(Ctx& c, int bi, const ActP& x, ActP& out) {
         }
     } else {
         q.ident = x.p; q.ldi = x.ld;
+        if (!x.p) { q.ident_hi = x.hi; q.ident_lo = x.lo; }
     }
     q.out = out.p; q.ldo = out.ld; q.out_hi = out.hi; q.out_lo = out.lo;
     c.conv(q);
@@ -733,7 +747,10 @@ static GradP emit_grad(Ctx& c, ConvP& p, const Act& x, const float* addend, int 
     if (raw_dst) {
         g.raw = raw_dst; g.ldr = ld_dst;
     } else {
-        g.raw = c.alloc(n); g.ldr = x.C;
+        // fp32 copy of the raw gradient only for the standalone GroupNorm backward (non-fusable producers, concat
+        // gradients, which also feed the skip addend); residual / operand consumers read the planes
+        const bool need_f32 = !planes_all(c, x.C) || x.grad_f32 || (x.blk >= 0 && !(fusable && p.N == x.C));
+        g.raw = need_f32 ? c.alloc(n) : nullptr; g.ldr = x.C;
         c.planes(n, &g.raw_hi, &g.raw_lo);
     }
     p.out = g.raw; p.ldo = g.ldr; p.out_hi = g.raw_hi; p.out_lo = g.raw_lo;
@@ -785,6 +802,7 @@ static GradP res_bwd(Ctx& c, int bi, const GradP& gout, const Act& x, const floa
         set_W2(m, q, b.Rb, b.tcRb);
     } else {
         q.ident = gout.raw; q.ldi = gout.ldr;
+        if (!gout.raw) { q.ident_hi = gout.raw_hi; q.ident_lo = gout.raw_lo; }
     }
     GradP g = emit_grad(c, q, x, addend, ldad, raw_dst, ld_dst, true);
     c.dbg("gx:", b.pfx, g.raw, g.ldr == x.C ? (int64_t)R * Hl * x.C : 0);
@@ -930,7 +948,7 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
             g = emit_grad(c, p, up_b[ind], nullptr, 0, nullptr, 0, true);
         }
         g = res_bwd(c, bmid + 3 + 2 * ind, g, up_a[ind], nullptr, 0, nullptr, 0);
-        Act catv; catv.C = 2 * Cs; catv.Hl = h; catv.blk = -1;
+        Act catv; catv.C = 2 * Cs; catv.Hl = h; catv.blk = -1; catv.grad_f32 = true;
         GradP gc = res_bwd(c, bmid + 2 + 2 * ind, g, catv, nullptr, 0, nullptr, 0);
         // split the concat gradient: [:Cs] continues along the up path, [Cs:] goes to the skip
         skipg[Ls] = gc.raw ? gc.raw + Cs : nullptr; skipld[Ls] = 2 * Cs;

@@ -250,6 +250,25 @@ __device__ __forceinline__ void add_row32(const float* __restrict__ p, float (&v
         v[4 * i] += t[i].x; v[4 * i + 1] += t[i].y; v[4 * i + 2] += t[i].z; v[4 * i + 3] += t[i].w;
     }
 }
+// v[j] += hi[j] + lo[j] for 32 columns of a BF16x3 plane pair (4 + 4 16-byte vectors per row)
+__device__ __forceinline__ void add_planes32(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                             float (&v)[32]) {
+    uint4 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        h[i] = __ldg(reinterpret_cast<const uint4*>(hi) + i);
+        l[i] = __ldg(reinterpret_cast<const uint4*>(lo) + i);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t hw[4] = {h[i].x, h[i].y, h[i].z, h[i].w}, lw[4] = {l[i].x, l[i].y, l[i].z, l[i].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[8 * i + 2 * k] += __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
+            v[8 * i + 2 * k + 1] += __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u);
+        }
+    }
+}
 __device__ __forceinline__ void st_row32(float* __restrict__ p, const float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)

@@ -39,6 +39,8 @@ def main(fams):
         eng = pmp_b200.UnetEngine(a["unet"], sd, dev)
         eng.set_gemm_path(int(os.environ.get("PMP_GEMM_PATH", "3")))
         print("  gemm path", os.environ.get("PMP_GEMM_PATH", "3"))
+        if os.environ.get("PMP_ROW_CHUNK"):
+            eng.set_row_chunk(int(os.environ["PMP_ROW_CHUNK"]))
         wemb = eng.wall_embed(torch.tensor(pr["walls"]))
         wemb_ref = unet_ref.wall_embed(sd, cfg, torch.tensor(pr["walls"]))
         print("  wall_embed rel err %.3e" % rel(wemb.cpu().numpy(), wemb_ref.numpy()))
