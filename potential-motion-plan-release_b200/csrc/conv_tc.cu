@@ -222,11 +222,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     mbar_wait(&empty[s], ph ^ 1);
                     if (P.ctr && P.tmode == 1) atomicAdd(P.ctr + 5, (unsigned long long)(clock64() - tw0));
                     uint8_t* st = smem + s * C::STAGE_BYTES;
-                    if (CG == 1 || crank == 0) mbar_expect_tx(&full[s], CG * (2 * bytesA + 2 * C::B_TILE_BYTES));
+                    // dbg 64 (timing probe for operand reuse, garbage results): the A tile is only loaded for one tap of five
+                    const bool skipA = (P.dbg & 64) && kb < nkb1 && p.ntaps[op] == 5 && (kb / P.kpt) != 2;
+                    const bool skipB = (P.dbg & 128) && kb < nkb1 && p.ntaps[op] == 5 && (kb / P.kpt) != 2;   // same probe for B
+                    if (CG == 1 || crank == 0)
+                        mbar_expect_tx(&full[s], CG * ((skipA ? 0 : 2 * bytesA) + (skipB ? 0 : 2 * C::B_TILE_BYTES)));
                     if (kb < nkb1) {
                         const int tap = kb / P.kpt, c0 = (kb - tap * P.kpt) * BKC;
                         const int sh = p.tap_shift[op][tap], wr = p.tap_k[op][tap] * N + nb0;
-                        if (P.mode4d) {
+                        if (skipA) {
+                        } else if (P.mode4d) {
                             // input row 2j + sh = parity (sh & 1) of pair j + floor(sh / 2)
                             const int par = sh & 1, js = (sh - par) >> 1;
                             ld4(st, &P.mA1h, &full[s], c0, par, js, r0);
@@ -235,8 +240,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             ld3(st, &P.mA1h, &full[s], c0, sh, r0);
                             ld3(st + A_TILE, &P.mA1l, &full[s], c0, sh, r0);
                         }
-                        ld2(st + 2 * A_TILE, &P.mW1h, &full[s], c0, wr);
-                        ld2(st + 2 * A_TILE + C::B_TILE_BYTES, &P.mW1l, &full[s], c0, wr);
+                        if (!skipB) {
+                            ld2(st + 2 * A_TILE, &P.mW1h, &full[s], c0, wr);
+                            ld2(st + 2 * A_TILE + C::B_TILE_BYTES, &P.mW1l, &full[s], c0, wr);
+                        }
                     } else {
                         const int c0 = (kb - nkb1) * BKC;
                         ld3(st, &P.mA2h, &full[s], c0, 0, r0);
@@ -390,6 +397,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 epi_bar();
                 if (etid == 0) {
                     if (CG == 2) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
+                    if (P.ctr) atomicAdd(P.ctr + 6, 1ull);
                 }
                 if (++as == NACC) { as = 0; aph ^= 1; }
                 continue;
@@ -936,7 +944,9 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     const bool inl_pre = p.inl_x && p.inl_mode == 1, inl_post = p.inl_x && p.inl_mode == 2;
     const bool acc2 = (p.A2 != nullptr || p.A2_hi != nullptr) && !inl_post && (p.bias2 != nullptr || p.gn_fwd);
     // 256-column tiles (CTA pairs only) feed the tensor pipe best; a separate second accumulator does not fit next to them
-    const int NT = pick_nt(p, mode == 3 && !acc2 && !p.inl_x);
+    static int wide = -1;
+    if (wide < 0) { const char* e = getenv("PMP_TC_WIDE"); wide = e ? atoi(e) : 1; }
+    const int NT = pick_nt(p, wide && mode == 3 && !acc2 && !p.inl_x);
     const int cg = (mode == 3 && NT >= 128 && !p.inl_x) ? 2 : 1;
     const bool te = mode == 3 && (NT == 64 || ((NT == 128 || NT == 256) && cg == 2)) && p.N >= 64;
     const int S = 128 / p.HJ;
