@@ -34,25 +34,34 @@ def load_models():
         return _loaded["models"]
     if not available():
         raise RuntimeError("reference tree not present at %s" % REF_ROOT)
-    # the product mirror also defines a top-level `diffuser`; the two must
-    # never be mixed inside one interpreter
-    if "diffuser" in sys.modules and not getattr(sys.modules["diffuser"], "__file__", "").startswith(REF_ROOT):
-        raise RuntimeError("a non-reference `diffuser` package is already imported")
+    # the product mirror also defines a top-level `diffuser`: park its modules while the reference is imported
+    # and put them back afterwards (the reference classes keep their own module globals), so that both can be
+    # exercised by one test process in any order
+    parked = {k: sys.modules.pop(k) for k in list(sys.modules)
+              if (k == "diffuser" or k.startswith("diffuser.")) and
+              not (getattr(sys.modules[k], "__file__", None) or "").startswith(REF_ROOT)}
     sys.path.insert(0, REF_ROOT)
-    for n in ("colorama", "matplotlib", "matplotlib.pyplot"):
-        sys.modules.setdefault(n, MagicMock())
-    import diffuser  # noqa: empty __init__
+    try:
+        for n in ("colorama", "matplotlib", "matplotlib.pyplot"):
+            sys.modules.setdefault(n, MagicMock())
+        import diffuser  # noqa: empty __init__
 
-    u = types.ModuleType("diffuser.utils")
-    u.__path__ = [os.path.join(REF_ROOT, "diffuser", "utils")]
-    u.print_color = lambda s, *a, **k: None
-    u.Progress = u.Silent = _Silent
-    u.to_np = lambda x: x.detach().cpu().numpy()
-    sys.modules["diffuser.utils"] = u
-    diffuser.utils = u
-    import contextlib, io
-    with contextlib.redirect_stdout(io.StringIO()):
-        from diffuser.models import TemporalUnet_WCond, GaussianDiffusionPB
+        u = types.ModuleType("diffuser.utils")
+        u.__path__ = [os.path.join(REF_ROOT, "diffuser", "utils")]
+        u.print_color = lambda s, *a, **k: None
+        u.Progress = u.Silent = _Silent
+        u.to_np = lambda x: x.detach().cpu().numpy()
+        sys.modules["diffuser.utils"] = u
+        diffuser.utils = u
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            from diffuser.models import TemporalUnet_WCond, GaussianDiffusionPB
+    finally:
+        sys.path.remove(REF_ROOT)
+        # leave no reference module behind under the shared name: `quiet()` re-installs them around reference calls
+        _loaded["ref_modules"] = {k: sys.modules.pop(k) for k in list(sys.modules)
+                                  if k == "diffuser" or k.startswith("diffuser.")}
+        sys.modules.update(parked)
     _loaded["models"] = (TemporalUnet_WCond, GaussianDiffusionPB)
     return _loaded["models"]
 
@@ -83,13 +92,24 @@ def load_maze2d_geometry():
 
 
 class quiet:
-    """context manager silencing the reference's print() chatter"""
+    """context manager for calls into the reference: silences its print() chatter and, for the duration of the
+    call, makes `diffuser` resolve to the reference modules again (lazy imports inside reference code)"""
 
     def __enter__(self):
         import contextlib, io
         self._cm = contextlib.redirect_stdout(io.StringIO())
         self._cm.__enter__()
+        ref = _loaded.get("ref_modules", {})
+        self._parked = {k: sys.modules.pop(k) for k in list(sys.modules)
+                        if (k == "diffuser" or k.startswith("diffuser.")) and sys.modules[k] is not ref.get(k)}
+        sys.modules.update(ref)
         return self
 
     def __exit__(self, *a):
+        ref = _loaded.get("ref_modules", {})
+        for k in [k for k in sys.modules if k == "diffuser" or k.startswith("diffuser.")]:
+            if k not in ref:
+                ref[k] = sys.modules[k]      # lazily imported reference submodule
+            del sys.modules[k]
+        sys.modules.update(self._parked)
         return self._cm.__exit__(*a)
