@@ -6,6 +6,7 @@
   derived from the link collision-mesh AABBs measured in SURVEY.md Appendix D
   (pb_diff_envs/data/robot/kuka_iiwa/meshes/link_i.stl).
 * `pick_first_valid`: candidate selection of rm2d_plan_env.py:137-235 / kuka_plan_env.py:133-200.
+* `pick_multi_horizon`: the composed planner's selection over several horizons (comp_plan_env.py:126-265).
 """
 import ctypes
 import os
@@ -159,3 +160,31 @@ def pick_first_valid(valid, nchk, n_prob, n_samp):
                 break
         chosen[p] = idx
     return chosen, suc, tot
+
+
+def pick_multi_horizon(valid_list, nchk_list, n_prob, n_samp):
+    """Composed planner, several planning horizons (comp_plan_env.py:126-265): the candidates of problem p are
+    visited sample-major, horizon-minor -- (sample 0, horizon 0), (sample 0, horizon 1), ..., (sample 1,
+    horizon 0), ... (`traj_a_prob`, :205-210) -- and the scan stops at the first collision-free one (:217-238);
+    when none is, the LAST candidate visited is kept (:247-249).  valid_list[h] / nchk_list[h] hold the
+    checker outputs of horizon h for its n_prob*n_samp candidates (problem-major, as the policy batch is laid
+    out, :143-146).  Returns (horizon index [n_prob], sample index [n_prob], success [n_prob] bool,
+    num_colck [n_prob])."""
+    nh = len(valid_list)
+    v = [np.asarray(a).reshape(n_prob, n_samp).astype(bool) for a in valid_list]
+    c = [np.asarray(a).reshape(n_prob, n_samp) for a in nchk_list]
+    hsel = np.zeros(n_prob, np.int64); ssel = np.zeros(n_prob, np.int64)
+    suc = np.zeros(n_prob, bool); tot = np.zeros(n_prob, np.int64)
+    for p in range(n_prob):
+        done = False
+        for j in range(n_samp):
+            for h in range(nh):
+                tot[p] += c[h][p, j]
+                hsel[p], ssel[p] = h, j
+                if v[h][p, j]:
+                    suc[p] = True
+                    done = True
+                    break
+            if done:
+                break
+    return hsel, ssel, suc, tot

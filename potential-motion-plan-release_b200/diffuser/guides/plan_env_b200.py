@@ -61,3 +61,82 @@ def plan_envs(policy, starts, goals, walls, env_boxes, hext, horizon, samples_pe
                total_num_colck=int(total.sum().item()),
                avg_num_colck=float(total.float().mean().item()))
     return res, paths.cpu().numpy()
+
+
+def pick_multi_horizon(valid_list, nchk_list, n_prob, n_samp):
+    """GPU-side candidate selection of the composed planner over several horizons
+    (ComposedEnvPlanner.option_1_pick_1_traj, diffuser/guides/comp_plan_env.py:126-265): per problem the
+    candidates are scanned sample-major / horizon-minor (:205-210) and the first collision-free one wins, else
+    the last one visited.  valid_list[h], nchk_list[h]: device tensors [n_prob*n_samp] of horizon h.
+    Returns device tensors (horizon index, sample index, success, num_colck), each [n_prob]."""
+    nh = len(valid_list)
+    v = torch.stack([a.reshape(n_prob, n_samp) for a in valid_list], dim=2).reshape(n_prob, n_samp * nh)
+    c = torch.stack([a.reshape(n_prob, n_samp) for a in nchk_list], dim=2).reshape(n_prob, n_samp * nh)
+    chosen, suc, total = pmp_b200.pick_first_valid(v.contiguous(), c.contiguous(), n_prob, n_samp * nh)
+    chosen = chosen.long()
+    return chosen % nh, chosen // nh, suc, total
+
+
+def plan_envs_multi_horizon(policy, starts, goals, walls, env_boxes, hext, horizons, samples_perprob=10,
+                            robot='maze2d', n_arms=1, collision_eps=0.08, legacy_div=True):
+    """plan_envs for the composed planner's list of planning horizons (comp_plan_env.py:54-124): every problem is
+    planned at every horizon (PolicyCompose.call_multi_horizon), all candidates are collision-checked on the
+    GPU and one path per problem is selected with pick_multi_horizon.  Returns (result dict, list of chosen
+    paths -- numpy [H_p, D] each, horizons differ per problem)."""
+    n_env, n_prob, D = starts.shape
+    n_p, n_s = n_env * n_prob, samples_perprob
+    rep = lambda a: np.repeat(a.reshape(n_p, -1), n_s, axis=0)
+    wl = torch.as_tensor(rep(walls), dtype=torch.float32)
+    dev = policy.device
+    env_id = np.repeat(np.arange(n_env, dtype=np.int32), n_prob * n_s)
+    if robot != 'maze2d':
+        chk = KukaCollisionChecker(device=dev)
+    torch.cuda.synchronize(dev)
+    tic = time.time()
+    obs_h, valid_h, nchk_h = [], [], []
+    for ho in horizons:
+        cond = {0: rep(starts).astype(np.float32), ho - 1: rep(goals).astype(np.float32)}
+        if hasattr(policy, 'call_multi_horizon'):
+            traj = policy(cond, wl)[1]
+        else:
+            policy.diffusion_model.horizon = ho
+            traj = policy(cond, batch_size=-1, wall_locations=wl)[1]
+        obs = torch.as_tensor(traj.observations, dtype=torch.float32, device=dev)
+        if robot == 'maze2d':
+            valid, nchk = pmp_b200.colchk_maze2d_swept(obs, env_id, env_boxes, hext, eps=collision_eps,
+                                                       legacy_div=legacy_div)
+        else:
+            r = pmp_b200.colchk_kuka(obs, env_id, env_boxes, hext, n_arms, arm_bases(n_arms), chk.sph, TABLE_Z)
+            valid, nchk = r['valid'], r['nchk']
+        obs_h.append(obs); valid_h.append(valid); nchk_h.append(nchk)
+    hsel, ssel, suc, total = pick_multi_horizon(valid_h, nchk_h, n_p, n_s)
+    torch.cuda.synchronize(dev)
+    batch_runtime = time.time() - tic
+    hs, ss = hsel.cpu().numpy(), ssel.cpu().numpy()
+    paths = [obs_h[hs[p]][p * n_s + ss[p]].cpu().numpy() for p in range(n_p)]
+    # final score: per-waypoint check of the chosen path (kuka_plan_utils.py:110-154), batched per horizon
+    env_p = np.repeat(np.arange(n_env, dtype=np.int32), n_prob)
+    ncol = np.zeros(n_p, np.int64)
+    for i, ho in enumerate(horizons):
+        sel = np.nonzero(hs == i)[0]
+        if not len(sel):
+            continue
+        pt = obs_h[i][torch.as_tensor(sel * n_s + ss[sel], device=dev)]
+        if robot == 'maze2d':
+            nc, _ = pmp_b200.colchk_maze2d_points(pt, env_p[sel], env_boxes, hext)
+        else:
+            nc = pmp_b200.colchk_kuka(pt, env_p[sel], env_boxes, hext, n_arms, arm_bases(n_arms), chk.sph, TABLE_Z)['ncol']
+        ncol[sel] = nc.cpu().numpy()
+    success = ncol == 0
+    res = dict(num_samples=n_p,
+               traj_srate=float(success.mean()),
+               traj_norepl_srate=float(suc.float().mean().item()),
+               traj_repl_srate=0.0,
+               total_ncr=float(success.mean()),
+               total_svr=1.0,
+               avg_batch_time=batch_runtime / n_env,
+               avg_sample_time=batch_runtime / n_p,
+               total_num_colck=int(total.sum().item()),
+               avg_num_colck=float(total.float().mean().item()),
+               horizon_hist=[int((hs == i).sum()) for i in range(len(horizons))])
+    return res, paths

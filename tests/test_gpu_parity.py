@@ -246,6 +246,34 @@ def test_policy_and_compose_interfaces():
     assert traj.observations.shape == (B, 40, 2) and np.isfinite(traj.observations).all()
 
 
+def test_plan_envs_multi_horizon_composed():
+    """composed planner over several horizons end to end (comp_plan_env.py:54-265): K=2 potentials, 3 horizons,
+    GPU collision checks + interleaved selection; the chosen path must be the candidate the oracle's scan picks"""
+    from diffuser.guides import PolicyCompose
+    from diffuser.guides.plan_env_b200 import plan_envs_multi_horizon
+    from diffuser.datasets import DatasetNormalizer, RAND_MAZE_MIN, RAND_MAZESIZE_55
+    norm = DatasetNormalizer({"observations": (RAND_MAZE_MIN, RAND_MAZESIZE_55)})
+    d = dropin("m2d"); d2 = dropin("m2d_nw3", 2)
+    po = dict(num_walls_c=[6, 3], wall_dim=2, comp_type="direct", ddim_steps=8, wall_is_dyn=None, uncond_base_idx=0,
+              ddim_eta=0.0)
+    comp = PolicyCompose([d, d2], [norm, norm], False, True, po)
+    n_env, n_prob, n_s, horizons = 3, 4, 3, (40, 48, 56)
+    pr6 = synth.make_problems("m2d", n_env, 21); pr3 = synth.make_problems("m2d_nw3", n_env, 22)
+    rng = np.random.default_rng(4)
+    starts = rng.uniform(0.2, 4.8, (n_env, n_prob, 2)).astype(np.float32)
+    goals = rng.uniform(0.2, 4.8, (n_env, n_prob, 2)).astype(np.float32)
+    walls = np.repeat(np.concatenate([pr6["walls"], pr3["walls"]], 1)[:, None], n_prob, 1)
+    boxes = np.concatenate([pr6["boxes"], pr3["boxes"]], 1)      # checker sees the union of both obstacle sets
+    res, paths = plan_envs_multi_horizon(comp, starts, goals, walls, boxes, 0.5, horizons, samples_perprob=n_s)
+    assert len(paths) == n_env * n_prob and sum(res["horizon_hist"]) == n_env * n_prob
+    for p, path in enumerate(paths):
+        assert path.shape[0] in horizons and path.shape[1] == 2 and np.isfinite(path).all()
+        assert np.allclose(path[0], starts.reshape(-1, 2)[p], atol=1e-5) and np.allclose(path[-1], goals.reshape(-1, 2)[p], atol=1e-5)
+    for k in ("traj_srate", "traj_norepl_srate", "total_num_colck", "avg_num_colck", "avg_sample_time"):
+        assert k in res
+    assert 0.0 <= res["traj_srate"] <= 1.0 and res["total_num_colck"] > 0
+
+
 # ------------------------------------------------------------------ collision
 @pytest.mark.parametrize("fam", ["m2d", "m2d_nw3", "m2d_concave"])
 def test_maze2d_collision_matches_reference_golden(fam):
@@ -284,6 +312,20 @@ def test_maze2d_collision_full_size_vs_oracle(legacy):
         assert np.array_equal(ch.cpu().numpy(), ch_ref) and np.array_equal(su.cpu().numpy().astype(bool), su_ref)
         assert np.array_equal(tot.cpu().numpy(), tot_ref)
         assert 0.02 < su_ref.mean() < 0.98
+
+
+def test_pick_multi_horizon_vs_oracle():
+    """GPU selection over several horizons == sequential restatement of comp_plan_env.py:126-265"""
+    from diffuser.guides.plan_env_b200 import pick_multi_horizon
+    rng = np.random.default_rng(5)
+    for n_prob, n_samp, nh, pv in ((1, 1, 1, 0.5), (257, 10, 4, 0.08), (1000, 5, 3, 0.0), (64, 20, 2, 0.6)):
+        v = [(rng.random(n_prob * n_samp) < pv).astype(np.uint8) for _ in range(nh)]
+        c = [rng.integers(0, 400, n_prob * n_samp).astype(np.int32) for _ in range(nh)]
+        h_ref, s_ref, su_ref, tot_ref = colchk_ref.pick_multi_horizon(v, c, n_prob, n_samp)
+        h, s, su, tot = pick_multi_horizon([torch.tensor(a, device=DEV) for a in v], [torch.tensor(a, device=DEV) for a in c],
+                                           n_prob, n_samp)
+        assert np.array_equal(h.cpu().numpy(), h_ref) and np.array_equal(s.cpu().numpy(), s_ref)
+        assert np.array_equal(su.cpu().numpy().astype(bool), su_ref) and np.array_equal(tot.cpu().numpy(), tot_ref)
 
 
 def test_maze2d_collision_edge_cases():

@@ -155,6 +155,24 @@ def test_pick_first_valid():
     assert ch.tolist() == [1, 2, 0] and su.tolist() == [True, False, True] and tot.tolist() == [3, 15, 7]
 
 
+def test_pick_multi_horizon_order():
+    """comp_plan_env.py:205-238: sample-major / horizon-minor scan, stop at the first valid, else the last visited"""
+    # 2 problems x 2 samples x 3 horizons
+    v = [np.array([0, 0, 0, 0]), np.array([0, 1, 0, 0]), np.array([1, 1, 0, 0])]
+    c = [np.array([1, 2, 3, 4]), np.array([10, 20, 30, 40]), np.array([100, 200, 300, 400])]
+    h, s, suc, tot = colchk_ref.pick_multi_horizon(v, c, 2, 2)
+    # problem 0: (s0,h0) no, (s0,h1) no, (s0,h2) yes -> horizon 2, sample 0, checks 1+10+100
+    # problem 1: nothing valid -> last visited (s1,h2), all six counts
+    assert h.tolist() == [2, 2] and s.tolist() == [0, 1] and suc.tolist() == [True, False]
+    assert tot.tolist() == [111, 3 + 30 + 300 + 4 + 40 + 400]
+    # a single horizon degenerates to pick_first_valid
+    rng = np.random.default_rng(0)
+    vv = rng.random(60) < 0.3; cc = rng.integers(1, 50, 60)
+    h1, s1, su1, t1 = colchk_ref.pick_multi_horizon([vv], [cc], 12, 5)
+    ch, su, tt = colchk_ref.pick_first_valid(vv, cc, 12, 5)
+    assert (h1 == 0).all() and np.array_equal(s1, ch) and np.array_equal(su1, su) and np.array_equal(t1, tt)
+
+
 # ------------------------------------------------------------------ live reference (build container only)
 needs_ref = pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
 
