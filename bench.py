@@ -266,6 +266,7 @@ def main():
     e2e = world * Bp * args.steps / e2e_s
 
     pk = peaks()
+    pk_hbm = lambda: pk["hbm"]
     conv_ms, conv_fl, conv_n = max(prof, key=lambda r: r[0])
     tot_conv_ms = sum(r[0] for r in prof)
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
@@ -285,6 +286,51 @@ def main():
             "peak_source": pk["src"] + " bf16 sustained (burst %.1f)" % pk["tf_burst"],
             "whole_step_algorithmic_tflops": value / world * FLOP_PER_PLAN / 1e12}
 
+    # ---- HBM-bound kernels of the path, timed alone on inputs larger than L2: fused sampler update
+    # and swept collision check; achieved = algorithmic bytes / kernel time (CUDA events, 20 launches after warm-up)
+    aux = []
+    if rank == 0 and world == 1:
+        def timed(fn, reps=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(reps):
+                fn()
+            b_.record(); torch.cuda.synchronize()
+            return a_.elapsed_time(b_) / reps * 1e-3
+        nb = 400000                                           # plans: 4 x 154 MB of state per launch > 126 MB L2
+        xs = torch.randn(nb, H, D, device=dev); ec = torch.randn_like(xs); eu = torch.randn_like(xs); xo = torch.empty_like(xs)
+        sg = torch.zeros(nb, D, device=dev)
+        t_step = timed(lambda: pmp_b200.step(0, xs, [ec], [eu], [2.0], coefs[50], noise=None, seed=7, offset=0, start=sg,
+                                             goal=sg, out=xo))
+        by = 4.0 * H * D * 4 * nb                             # x + eps_c + eps_u read, x written (noise: in-kernel Philox)
+        aux.append({"kernel": "step_kernel (CFG + posterior + Philox noise + conditioning, K=1)", "bound": "hbm",
+                    "achieved": by / t_step / 1e9, "peak": pk_hbm(), "unit": "GB/s", "frac": by / t_step / 1e9 / pk_hbm(),
+                    "bytes_per_plan_step": 4 * H * D * 4, "plans_per_launch": nb, "ms": t_step * 1e3})
+        ntr = 1000000
+        E = boxes.shape[0]
+        al = torch.linspace(0, 1, H, device=dev)[None, :, None]
+        s_ = torch.rand(ntr, 1, 2, device=dev) * 4.6 + 0.2; g_ = torch.rand(ntr, 1, 2, device=dev) * 4.6 + 0.2
+        tr = (s_ * (1 - al) + g_ * al).contiguous()
+        eid = (torch.arange(ntr, device=dev) % E).to(torch.int32)
+        vb = torch.empty(ntr, dtype=torch.uint8, device=dev); nc_ = torch.empty(ntr, dtype=torch.int32, device=dev)
+        def chk():
+            rc = L.pmp_colchk_maze2d_swept(C.c_void_p(tr.data_ptr()), C.c_void_p(eid.data_ptr()), ntr, H,
+                                           C.c_void_p(boxes.data_ptr()), C.c_void_p(hext.data_ptr()), boxes.shape[1],
+                                           0.0, 0.0, 5.0, 5.0, 0.08, 0.01, 1, C.c_void_p(vb.data_ptr()),
+                                           C.c_void_p(nc_.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            assert rc == 0
+        t_chk = timed(chk)
+        by = (4.0 * H * D + 5) * ntr
+        aux.append({"kernel": "maze2d_swept_kernel (straight-line candidates, eps 0.08, 3 walls)", "bound": "hbm",
+                    "achieved": by / t_chk / 1e9, "peak": pk_hbm(), "unit": "GB/s", "frac": by / t_chk / 1e9 / pk_hbm(),
+                    "bytes_per_trajectory": 4 * H * D + 5, "trajectories_per_launch": ntr, "ms": t_chk * 1e3,
+                    "trajectories_per_s": ntr / t_chk,
+                    "note": "one warp per trajectory; all waypoints are read once (coalesced), walls from L2"})
+        del xs, ec, eu, xo, tr
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -302,7 +348,7 @@ def main():
                            pmp_b200.lib().pmp_model_workspace_bytes(eng.h) / 1e9),
                        "success_rate_random_init_weights": success_rate},
             "clocks": clk.summary(), "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}))
+            "gpu_launches": launches, "roofline": roof, "aux_rooflines": aux, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
 

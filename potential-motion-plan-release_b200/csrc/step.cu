@@ -10,6 +10,8 @@
 // Every float op is an explicitly rounded intrinsic in the reference's order (no FMA
 // contraction), so with identical eps the result is bit-identical to PyTorch.
 // HBM-bound: algorithmic bytes per element = 4*(1 + 2K + [noise] + 1).
+#include <stdint.h>
+
 #include "common.cuh"
 
 namespace pmp {
@@ -35,13 +37,96 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
-// one N(0,1) draw addressed by (global element index, draw index): sharding invariant
-__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t draw, uint64_t elem) {
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)elem, (uint32_t)(elem >> 32), (uint32_t)draw, (uint32_t)(draw >> 32)),
+// Four N(0,1) draws per Philox call, addressed by (global element index / 4, draw index): the value of an
+// element depends only on its GLOBAL index, so results are invariant to how the batch is sharded or chunked.
+// Both Box-Muller outputs of each uniform pair are used.
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t draw, uint64_t group) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), (uint32_t)draw, (uint32_t)(draw >> 32)),
                                   make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
     const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float u2 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    const float u3 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u4 = ((float)(r.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    // fast intrinsics (lg2/sin/cos.approx): the noise stream only has to be N(0,1)-distributed and reproducible,
+    // it has no bit-level counterpart in the reference (torch.randn streams are injected instead when parity matters)
+    const float ra = __fsqrt_rn(-2.0f * __logf(u1)), rb = __fsqrt_rn(-2.0f * __logf(u3));
+    float sa, ca, sb, cb;
+    __sincosf(6.283185307179586f * (u2 - 0.5f), &sa, &ca);
+    __sincosf(6.283185307179586f * (u4 - 0.5f), &sb, &cb);
+    return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+}
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t draw, uint64_t elem) {
+    const float4 z = philox_normal4(seed, draw, elem >> 2);
+    const int c = (int)(elem & 3);
+    return c == 0 ? z.x : (c == 1 ? z.y : (c == 2 ? z.z : z.w));
+}
+
+// the update of one element (explicitly rounded, reference op order): shared by the scalar and the float4 kernel
+__device__ __forceinline__ float step_elem(const StepP& p, float xv, float eps, float z) {
+    float x0 = __fsub_rn(__fmul_rn(p.coef[0], xv), __fmul_rn(p.coef[1], eps));
+    x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+    if (p.kind == PMP_STEP_DDPM) {
+        const float mean = __fadd_rn(__fmul_rn(p.coef[2], x0), __fmul_rn(p.coef[3], xv));
+        return __fadd_rn(mean, __fmul_rn(p.coef[4], z));
+    }
+    const float mo = __fdiv_rn(__fsub_rn(xv, __fmul_rn(p.coef[2], x0)), p.coef[3]);
+    float out = __fadd_rn(__fmul_rn(p.coef[4], x0), __fmul_rn(p.coef[5], mo));
+    if (p.coef[7] != 0.0f) out = __fadd_rn(out, __fmul_rn(p.coef[6], z));
+    return out;
+}
+
+// float4 variant (H*D and the global element offset are multiples of 4): 16-byte loads / stores, one Philox call
+// per thread.  HBM-bound: 4*(2 + 2K [+1 injected noise]) bytes per element.
+__global__ void __launch_bounds__(256) step_kernel4(const __grid_constant__ StepP p, const float* __restrict__ x,
+                                                    const float* __restrict__ noise, uint64_t seed, uint64_t draw,
+                                                    uint64_t elem0, const float* __restrict__ start,
+                                                    const float* __restrict__ goal, float* __restrict__ xo,
+                                                    float* __restrict__ trace, long trace_stride, int H, int D,
+                                                    size_t n4) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n4) return;
+    const size_t e = g * 4;
+    const int HD = H * D;
+    const size_t b = e / HD;
+    const int rem = (int)(e - b * HD);
+    const float4 xv4 = __ldg(reinterpret_cast<const float4*>(x + e));
+    const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+    float eps[4];
+    if (p.K == 1) {
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.ec[0] + e)), u4 = __ldg(reinterpret_cast<const float4*>(p.eu[0] + e));
+        const float c[4] = {c4.x, c4.y, c4.z, c4.w}, u[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) eps[j] = __fadd_rn(u[j], __fmul_rn(p.w[0], __fsub_rn(c[j], u[j])));
+    } else {
+        float s[4], ub[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < p.K; ++k) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.ec[k] + e)), u4 = __ldg(reinterpret_cast<const float4*>(p.eu[k] + e));
+            const float c[4] = {c4.x, c4.y, c4.z, c4.w}, u[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float t = __fmul_rn(p.w[k], __fsub_rn(c[j], u[j]));
+                s[j] = k == 0 ? t : __fadd_rn(s[j], t);
+                if (k == p.base) ub[j] = u[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) eps[j] = __fadd_rn(ub[j], s[j]);
+    }
+    const bool need_noise = (p.kind == PMP_STEP_DDPM) || (p.coef[7] != 0.0f);
+    float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (need_noise) z4 = noise ? __ldg(reinterpret_cast<const float4*>(noise + e)) : philox_normal4(seed, draw, (elem0 + e) >> 2);
+    const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        o[j] = step_elem(p, xv[j], eps[j], z[j]);
+        const int r = rem + j, h = r / D, d = r - h * D;
+        if (start && h == 0) o[j] = start[b * D + d];
+        if (goal && h == H - 1) o[j] = goal[b * D + d];
+    }
+    const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(xo + e) = o4;
+    if (trace) *reinterpret_cast<float4*>(trace + b * trace_stride + rem) = o4;
 }
 
 __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP p, const float* __restrict__ x,
@@ -66,20 +151,10 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
         for (int k = 1; k < p.K; ++k) s = __fadd_rn(s, __fmul_rn(p.w[k], __fsub_rn(p.ec[k][e], p.eu[k][e])));
         eps = __fadd_rn(p.eu[p.base][e], s);
     }
-    float x0 = __fsub_rn(__fmul_rn(p.coef[0], xv), __fmul_rn(p.coef[1], eps));
-    x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-    float out;
     const bool need_noise = (p.kind == PMP_STEP_DDPM) || (p.coef[7] != 0.0f);
     float z = 0.0f;
     if (need_noise) z = noise ? noise[e] : philox_normal(seed, draw, elem0 + e);
-    if (p.kind == PMP_STEP_DDPM) {
-        const float mean = __fadd_rn(__fmul_rn(p.coef[2], x0), __fmul_rn(p.coef[3], xv));
-        out = __fadd_rn(mean, __fmul_rn(p.coef[4], z));
-    } else {
-        const float mo = __fdiv_rn(__fsub_rn(xv, __fmul_rn(p.coef[2], x0)), p.coef[3]);
-        out = __fadd_rn(__fmul_rn(p.coef[4], x0), __fmul_rn(p.coef[5], mo));
-        if (p.coef[7] != 0.0f) out = __fadd_rn(out, __fmul_rn(p.coef[6], z));
-    }
+    float out = step_elem(p, xv, eps, z);
     if (start && h == 0) out = start[b * D + d];
     if (goal && h == H - 1) out = goal[b * D + d];
     xo[e] = out;
@@ -157,8 +232,15 @@ int launch_step(int kind, const float* x, const float* const* ec, const float* c
     p.kind = kind;
     const size_t n = (size_t)B * H * D;
     if (n == 0) return 0;
-    step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, x, noise, seed, draw, elem0, start, goal, xo, trace,
-                                                            trace_stride, H, D, n);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    bool vec = ((H * D) % 4 == 0) && (elem0 % 4 == 0) && al16(x) && al16(xo) && al16(noise) && al16(trace) && (trace_stride % 4 == 0);
+    for (int k = 0; k < K; ++k) vec = vec && al16(ec[k]) && al16(eu[k]);
+    if (vec)
+        step_kernel4<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(p, x, noise, seed, draw, elem0, start, goal, xo, trace,
+                                                                     trace_stride, H, D, n / 4);
+    else
+        step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, x, noise, seed, draw, elem0, start, goal, xo, trace,
+                                                                trace_stride, H, D, n);
     PMP_LAUNCH_OK();
     return 0;
 }

@@ -220,6 +220,24 @@ def test_dropin_forward_api_and_philox():
         d.rng_mode = "torch"
 
 
+def test_philox_normal_statistics():
+    """in-kernel Philox4x32-10 + Box-Muller (4 normals per call): N(0,1) moments, no correlation between the
+    components of a call, reproducible per seed, different across seeds / draws"""
+    x = torch.empty(8192, 48, 2, device=DEV)
+    pmp_b200.init_noise(x, None, 1234, None, None)
+    v = x.flatten().double()
+    assert abs(v.mean().item()) < 5e-3 and abs(v.std().item() - 1) < 5e-3
+    assert abs(((v - v.mean()) ** 4).mean().item() / v.var().item() ** 2 - 3.0) < 0.05
+    q = v.view(-1, 4)
+    c = torch.corrcoef(q.T)
+    assert (c - torch.eye(4, device=DEV, dtype=torch.double)).abs().max().item() < 1.2e-2   # 5 sigma for 196608 groups
+    assert abs((v[:-1] * v[1:]).mean().item()) < 5e-3
+    y = torch.empty_like(x); pmp_b200.init_noise(y, None, 1234, None, None)
+    z = torch.empty_like(x); pmp_b200.init_noise(z, None, 1235, None, None)
+    assert torch.equal(x, y) and not torch.equal(x, z)
+    assert (v.abs() > 4.0).float().mean().item() < 2e-4 and v.abs().max().item() < 7.0
+
+
 def test_policy_and_compose_interfaces():
     from diffuser.guides import Policy, PolicyCompose
     from diffuser.datasets import DatasetNormalizer, RAND_MAZE_MIN, RAND_MAZESIZE_55
