@@ -399,7 +399,18 @@ __global__ void __launch_bounds__(NTHREADS) conv_simt_kernel(const __grid_consta
 }
 
 // standalone GroupNorm/activation backward for gradients that are not produced whole-slab by
-// one conv tile (transposed-conv outputs, halves of a skip concat)
+// one conv tile (transposed-conv outputs, halves of a skip concat).  HBM-bound: one block per (sample, group)
+// slab, float4 loads of the gradient and yhat (the slab, <= 6 KB, is re-read from L1 in the second pass),
+// packed 8-byte stores of the BF16 hi / lo planes.
+__device__ __forceinline__ float gn_act_bwd(float z, int act) {
+    if (act == 0) {
+        float e, s;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.0f + e));
+        return s * fmaf(z, 1.0f - s, 1.0f);
+    }
+    return act_bwd(z, act);
+}
 __global__ void __launch_bounds__(128) gn_bwd_kernel(const float* __restrict__ g, int ldgi,
                                                      const float* __restrict__ yhat, int ldy,
                                                      const float* __restrict__ rstd,
@@ -409,17 +420,19 @@ __global__ void __launch_bounds__(128) gn_bwd_kernel(const float* __restrict__ g
                                                      __nv_bfloat16* __restrict__ gy_hi,
                                                      __nv_bfloat16* __restrict__ gy_lo, int Hl, int C) {
     const int r = blockIdx.x >> 3, grp = blockIdx.x & 7;
-    const int gs = C >> 3, n = Hl * gs;
+    const int gs = C >> 3, gs4 = gs >> 2, n4 = Hl * gs4;
     __shared__ float red[2][4];
     float q1 = 0.f, q2 = 0.f;
-    for (int e = threadIdx.x; e < n; e += 128) {
-        const int h = e / gs, c = grp * gs + (e - h * gs);
+    for (int e = threadIdx.x; e < n4; e += 128) {
+        const int h = e / gs4, c = grp * gs + 4 * (e - h * gs4);
         const size_t row = (size_t)r * Hl + h;
-        const float y = yhat[row * ldy + c];
-        const float ga = gamma[c];
-        const float gyh = g[row * ldgi + c] * act_bwd(ga * y + beta[c], act) * ga;
-        q1 += gyh;
-        q2 += gyh * y;
+        const float4 y = __ldg(reinterpret_cast<const float4*>(yhat + row * ldy + c));
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + row * ldgi + c));
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
+        const float a0 = gv.x * gn_act_bwd(fmaf(ga.x, y.x, be.x), act) * ga.x, a1 = gv.y * gn_act_bwd(fmaf(ga.y, y.y, be.y), act) * ga.y;
+        const float a2 = gv.z * gn_act_bwd(fmaf(ga.z, y.z, be.z), act) * ga.z, a3 = gv.w * gn_act_bwd(fmaf(ga.w, y.w, be.w), act) * ga.w;
+        q1 += (a0 + a1) + (a2 + a3);
+        q2 += (a0 * y.x + a1 * y.y) + (a2 * y.z + a3 * y.w);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -431,18 +444,29 @@ __global__ void __launch_bounds__(128) gn_bwd_kernel(const float* __restrict__ g
         red[1][threadIdx.x >> 5] = q2;
     }
     __syncthreads();
-    const float m1 = (red[0][0] + red[0][1] + red[0][2] + red[0][3]) / (float)n;
-    const float m2 = (red[1][0] + red[1][1] + red[1][2] + red[1][3]) / (float)n;
+    const float inv = 1.0f / (float)(Hl * gs);
+    const float m1 = (red[0][0] + red[0][1] + red[0][2] + red[0][3]) * inv;
+    const float m2 = (red[1][0] + red[1][1] + red[1][2] + red[1][3]) * inv;
     const float rs = rstd[(size_t)r * 8 + grp];
-    for (int e = threadIdx.x; e < n; e += 128) {
-        const int h = e / gs, c = grp * gs + (e - h * gs);
+    for (int e = threadIdx.x; e < n4; e += 128) {
+        const int h = e / gs4, c = grp * gs + 4 * (e - h * gs4);
         const size_t row = (size_t)r * Hl + h;
-        const float y = yhat[row * ldy + c];
-        const float ga = gamma[c];
-        const float gyh = g[row * ldgi + c] * act_bwd(ga * y + beta[c], act) * ga;
-        const float gv = rs * (gyh - m1 - y * m2);
-        if (gy) gy[row * ldg + c] = gv;
-        if (gy_hi) split_bf16(gv, gy_hi[row * ldg + c], gy_lo[row * ldg + c]);
+        const float4 y = __ldg(reinterpret_cast<const float4*>(yhat + row * ldy + c));
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + row * ldgi + c));
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float4 o;
+        o.x = rs * (gv.x * gn_act_bwd(fmaf(ga.x, y.x, be.x), act) * ga.x - m1 - y.x * m2);
+        o.y = rs * (gv.y * gn_act_bwd(fmaf(ga.y, y.y, be.y), act) * ga.y - m1 - y.y * m2);
+        o.z = rs * (gv.z * gn_act_bwd(fmaf(ga.z, y.z, be.z), act) * ga.z - m1 - y.z * m2);
+        o.w = rs * (gv.w * gn_act_bwd(fmaf(ga.w, y.w, be.w), act) * ga.w - m1 - y.w * m2);
+        if (gy) *reinterpret_cast<float4*>(gy + row * ldg + c) = o;
+        if (gy_hi) {
+            uint32_t h0, l0, h1, l1;
+            split_bf16x2(o.x, o.y, h0, l0);
+            split_bf16x2(o.z, o.w, h1, l1);
+            *reinterpret_cast<uint2*>(gy_hi + row * ldg + c) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(gy_lo + row * ldg + c) = make_uint2(l0, l1);
+        }
     }
 }
 
