@@ -6,7 +6,7 @@ import os
 import numpy as np
 import torch
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpmp_b200.so")
+LIB_PATH = os.environ.get("PMP_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpmp_b200.so")   # override: A/B timing of two builds
 MAX_LEVELS = 8
 MAX_COMPOSE = 8
 
