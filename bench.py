@@ -7,7 +7,8 @@
 One *step* = one pass of the hot path over one batch of synthetic planning problems:
 wall encoding (ViT) -> 100-step DDPM reverse diffusion (CFG pair, energy U-Net forward +
 analytic backward per step, fused posterior update) -> un-normalise -> swept-segment collision
-check -> success scoring.  Workload = BASELINE.json configs[1] (Maze2D Static2, 3 walls hExt 0.7).
+check -> success scoring.  Workload = BASELINE.json configs[1]: 10,000 synthetic problems per step, half Maze2D Static2 (3 walls, hExt 0.7),
+half Concave (7 concave obstacles), one model per family.
 
 value : whole-job plans/s with the inputs (start/goal/walls) already resident in HBM
 e2e   : the same metric through the drop-in public API (GaussianDiffusionPB.forward + GPU
@@ -29,6 +30,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "potential-motion-plan-release_b200"))
 
 FAMILY = "m2d_nw3"          # Maze2D Static2 (rSmaze_nw3_hExt07)
+FAMILY2 = "m2d_concave"     # Maze2D Concave (rSmazeC43_concave_nw7)
 T_DIFF = 100
 METRIC = "plans/sec (composed-potential DDPM sampling)"
 UNIT = "plans/s"
@@ -143,9 +145,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("PMP_BENCH_BATCH", "3700")),
-                    help="plans per step per GPU")
-    ap.add_argument("--row-chunk", type=int, default=int(os.environ.get("PMP_ROW_CHUNK", "8192")))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("PMP_BENCH_BATCH", "10000")),
+                    help="problems per step per GPU (BASELINE configs[1]: 10k, half Static2 / half Concave)")
+    ap.add_argument("--row-chunk", type=int, default=int(os.environ.get("PMP_ROW_CHUNK", "10360")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -168,65 +170,85 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    a = synth.arch(FAMILY)
-    H, D = a["horizon"], a["obs_dim"]
-    model = TemporalUnet_WCond(**a["unet"])
-    model.load_state_dict(synth.synth_state_dict(model.state_dict(), 1))
-    diffusion = GaussianDiffusionPB(model, **a["diffusion"]).to(dev).eval()
-    diffusion.horizon = H
-    eng = diffusion.model.engine(T_DIFF)
-    eng.set_row_chunk(args.row_chunk)
-    if os.environ.get("PMP_GEMM_PATH"):
-        eng.set_gemm_path(int(os.environ["PMP_GEMM_PATH"]))
+    # ---- BASELINE.json configs[1]: 10,000 synthetic problems per step, half Maze2D Static2 (3 walls, hExt 0.7) and
+    # half Concave (7 concave obstacles = 21 boxes, hExt 0.25), one model per family, collision-check success scoring
     Bp = args.batch
-    # weak scaling: every rank plans its own Bp problems of a (world*Bp)-problem job
-    lo_p, hi_p = shard.shard_range(world * Bp, rank, world)
-    pr = synth.make_problems(FAMILY, Bp, 1000 + rank)
-    lo, hi = pr["lo"], pr["hi"]
-    start_h = torch.tensor(synth.normalize(pr["start"], lo, hi)).pin_memory()
-    goal_h = torch.tensor(synth.normalize(pr["goal"], lo, hi)).pin_memory()
-    walls_h = torch.tensor(pr["walls"]).pin_memory()
-    boxes = torch.tensor(pr["boxes"]).to(dev)
-    hext = torch.full_like(boxes, float(pr["hext"]))
-    env_id = torch.arange(Bp, dtype=torch.int32, device=dev)
-    start_d, goal_d, walls_d = start_h.to(dev), goal_h.to(dev), walls_h.to(dev)
-    lo_d, hi_d = torch.tensor(lo, device=dev), torch.tensor(hi, device=dev)
-    ts = list(range(T_DIFF - 1, -1, -1))
-    coefs = diffusion.step_coefs_ddpm(ts)
+    parts = []
     L = pmp_b200.lib()
     import ctypes as C
+    ts = list(range(T_DIFF - 1, -1, -1))
+    off = 0
+    for pi, (fam, n) in enumerate(((FAMILY, Bp - Bp // 2), (FAMILY2, Bp // 2))):
+        if n == 0:
+            continue
+        a = synth.arch(fam)
+        H, D = a["horizon"], a["obs_dim"]
+        model = TemporalUnet_WCond(**a["unet"])
+        model.load_state_dict(synth.synth_state_dict(model.state_dict(), 1 + pi))
+        diffusion = GaussianDiffusionPB(model, **a["diffusion"]).to(dev).eval()
+        diffusion.horizon = H
+        diffusion.rng_mode = "philox"
+        eng = diffusion.model.engine(T_DIFF)
+        eng.set_row_chunk(args.row_chunk)
+        if os.environ.get("PMP_GEMM_PATH"):
+            eng.set_gemm_path(int(os.environ["PMP_GEMM_PATH"]))
+        pr = synth.make_problems(fam, n, 1000 + 10 * rank + pi)
+        lo, hi = pr["lo"], pr["hi"]
+        P_ = dict(fam=fam, n=n, H=H, D=D, diffusion=diffusion, eng=eng, off=off,
+                  start_h=torch.tensor(synth.normalize(pr["start"], lo, hi)).pin_memory(),
+                  goal_h=torch.tensor(synth.normalize(pr["goal"], lo, hi)).pin_memory(),
+                  walls_h=torch.tensor(pr["walls"]).pin_memory(),
+                  boxes=torch.tensor(pr["boxes"]).to(dev), lo_d=torch.tensor(lo, device=dev), hi_d=torch.tensor(hi, device=dev),
+                  env_id=torch.arange(n, dtype=torch.int32, device=dev), coefs=diffusion.step_coefs_ddpm(ts))
+        P_["hext"] = torch.full_like(P_["boxes"], float(pr["hext"]))
+        for k in ("start", "goal", "walls"):
+            P_[k + "_d"] = P_[k + "_h"].to(dev)
+        parts.append(P_)
+        off += n
+    H, D = parts[0]["H"], parts[0]["D"]
+    # weak scaling: every rank plans its own Bp problems of a (world*Bp)-problem job
+    lo_p, hi_p = shard.shard_range(world * Bp, rank, world)
 
-    def collide(x):
-        un = pmp_b200.unnormalize(x, lo_d, hi_d)
-        valid = torch.empty(Bp, dtype=torch.uint8, device=dev)
-        nchk = torch.empty(Bp, dtype=torch.int32, device=dev)
-        rc = L.pmp_colchk_maze2d_swept(C.c_void_p(un.data_ptr()), C.c_void_p(env_id.data_ptr()), Bp, H,
-                                       C.c_void_p(boxes.data_ptr()), C.c_void_p(hext.data_ptr()), boxes.shape[1],
-                                       0.0, 0.0, 5.0, 5.0, 0.08, 0.01, 1, C.c_void_p(valid.data_ptr()),
+    def collide(P_, x):
+        un = pmp_b200.unnormalize(x, P_["lo_d"], P_["hi_d"])
+        n = P_["n"]
+        valid = torch.empty(n, dtype=torch.uint8, device=dev)
+        nchk = torch.empty(n, dtype=torch.int32, device=dev)
+        rc = L.pmp_colchk_maze2d_swept(C.c_void_p(un.data_ptr()), C.c_void_p(P_["env_id"].data_ptr()), n, P_["H"],
+                                       C.c_void_p(P_["boxes"].data_ptr()), C.c_void_p(P_["hext"].data_ptr()),
+                                       P_["boxes"].shape[1], 0.0, 0.0, 5.0, 5.0, 0.08, 0.01, 1, C.c_void_p(valid.data_ptr()),
                                        C.c_void_p(nchk.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         assert rc == 0, L.pmp_last_error()
         return un, valid, nchk
 
     def step_resident(i):
-        wemb = eng.wall_embed(walls_d)
-        x = pmp_b200.sample([eng], [wemb], [2.0], start_d, goal_d, H, 0, ts, coefs, noise=None, seed=1234 + i,
-                            row_offset=lo_p)
-        un, valid, nchk = collide(x)
+        vs = []
+        for P_ in parts:
+            eng = P_["eng"]
+            wemb = eng.wall_embed(P_["walls_d"])
+            x = pmp_b200.sample([eng], [wemb], [2.0], P_["start_d"], P_["goal_d"], P_["H"], 0, ts, P_["coefs"], noise=None,
+                                seed=1234 + i, row_offset=lo_p + P_["off"])
+            un, valid, nchk = collide(P_, x)
+            vs.append(valid)
+        valid = torch.cat(vs)
         if world > 1:   # the only communication: final gather of success bits
             shard.gather_rows(valid[:, None], world * Bp, world)
         return valid
 
     def step_e2e(i):
-        cond = {0: start_h.to(dev, non_blocking=True), H - 1: goal_h.to(dev, non_blocking=True)}
-        walls = walls_h.to(dev, non_blocking=True)
-        diffusion.philox_seed = 99 + i
-        x = diffusion(cond, walls)                       # public drop-in API (GaussianDiffusionPB.forward)
-        un, valid, nchk = collide(x)
-        return un.cpu(), valid.cpu()                     # host trajectories + success bits
+        outs = []
+        for P_ in parts:
+            Hh = P_["H"]
+            cond = {0: P_["start_h"].to(dev, non_blocking=True), Hh - 1: P_["goal_h"].to(dev, non_blocking=True)}
+            walls = P_["walls_h"].to(dev, non_blocking=True)
+            P_["diffusion"].philox_seed = 99 + i
+            x = P_["diffusion"](cond, walls)                 # public drop-in API (GaussianDiffusionPB.forward)
+            un, valid, nchk = collide(P_, x)
+            outs.append((un.cpu(), valid.cpu()))             # host trajectories + success bits
+        return outs
 
-    diffusion.rng_mode = "philox"
-    h2d = (start_h.numel() + goal_h.numel() + walls_h.numel()) * 4
-    d2h = Bp * H * D * 4 + Bp
+    h2d = sum(P_["start_h"].numel() + P_["goal_h"].numel() + P_["walls_h"].numel() for P_ in parts) * 4
+    d2h = sum(P_["n"] * P_["H"] * P_["D"] * 4 + P_["n"] for P_ in parts)
 
     def barrier():
         if world > 1:
@@ -303,13 +325,14 @@ def main():
         nb = 400000                                           # plans: 4 x 154 MB of state per launch > 126 MB L2
         xs = torch.randn(nb, H, D, device=dev); ec = torch.randn_like(xs); eu = torch.randn_like(xs); xo = torch.empty_like(xs)
         sg = torch.zeros(nb, D, device=dev)
-        t_step = timed(lambda: pmp_b200.step(0, xs, [ec], [eu], [2.0], coefs[50], noise=None, seed=7, offset=0, start=sg,
+        t_step = timed(lambda: pmp_b200.step(0, xs, [ec], [eu], [2.0], parts[0]['coefs'][50], noise=None, seed=7, offset=0, start=sg,
                                              goal=sg, out=xo))
         by = 4.0 * H * D * 4 * nb                             # x + eps_c + eps_u read, x written (noise: in-kernel Philox)
         aux.append({"kernel": "step_kernel (CFG + posterior + Philox noise + conditioning, K=1)", "bound": "hbm",
                     "achieved": by / t_step / 1e9, "peak": pk_hbm(), "unit": "GB/s", "frac": by / t_step / 1e9 / pk_hbm(),
                     "bytes_per_plan_step": 4 * H * D * 4, "plans_per_launch": nb, "ms": t_step * 1e3})
         ntr = 1000000
+        boxes, hext = parts[0]['boxes'], parts[0]['hext']
         E = boxes.shape[0]
         al = torch.linspace(0, 1, H, device=dev)[None, :, None]
         s_ = torch.rand(ntr, 1, 2, device=dev) * 4.6 + 0.2; g_ = torch.rand(ntr, 1, 2, device=dev) * 4.6 + 0.2
@@ -342,10 +365,10 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 (fp32-accumulate, ~fp32-equivalent operands)", "data": "synthetic",
-            "config": {"workload": "maze2d_static2_nw3_hExt07 DDPM-100 H=48 cond_w=2 + swept collision scoring (eps 0.08)",
+            "config": {"workload": "maze2d static2 (nw3, hExt 0.7) + concave (nw7): %d + %d problems per step, DDPM-100 H=48 cond_w=2 + swept collision scoring (eps 0.08)" % tuple(P_["n"] for P_ in parts) if len(parts) == 2 else "maze2d_static2_nw3_hExt07 DDPM-100 H=48 cond_w=2 + swept collision scoring (eps 0.08)",
                        "plans_per_step_per_gpu": Bp, "row_chunk": args.row_chunk, "rng": "in-kernel Philox4x32-10",
-                       "l2": "per-step working set (%.1f GB of activations) exceeds the 126 MB L2" % (
-                           pmp_b200.lib().pmp_model_workspace_bytes(eng.h) / 1e9),
+                       "l2": "per-pass working set (%.1f GB of activations) exceeds the 126 MB L2" % (
+                           pmp_b200.lib().pmp_model_workspace_bytes(parts[0]["eng"].h) / 1e9),
                        "success_rate_random_init_weights": success_rate},
             "clocks": clk.summary(), "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roof, "aux_rooflines": aux, "cpu_baseline": cpu}))
