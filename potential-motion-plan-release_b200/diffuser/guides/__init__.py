@@ -2,3 +2,4 @@ from .policies import Policy, Trajectories
 from .policies_compose import PolicyCompose
 from .rm2d_colchk import RM2DCollisionChecker
 from .kuka_colchk import KukaCollisionChecker
+from .kuka_replan import KukaDiffusionReplanner

@@ -346,6 +346,71 @@ def test_pick_multi_horizon_vs_oracle():
         assert np.array_equal(su.cpu().numpy().astype(bool), su_ref) and np.array_equal(tot.cpu().numpy(), tot_ref)
 
 
+def test_batched_replanner_vs_oracle():
+    """KukaDiffusionReplanner.replan_batch (all problems together, GPU checks) == the sequential restatement of
+    kuka_replan.py:33-143 on identical re-sampled trajectories: new paths, success flags and check counts"""
+    from oracle import replan_ref
+    from diffuser.guides.kuka_replan import KukaDiffusionReplanner
+    from diffuser.guides import RM2DCollisionChecker
+    from diffuser.datasets import DatasetNormalizer, RAND_MAZE_MIN, RAND_MAZESIZE_55
+    norm = DatasetNormalizer({"observations": (RAND_MAZE_MIN, RAND_MAZESIZE_55)})
+    B, H, n_trial = 96, 48, 3
+    pr = synth.make_problems("m2d", B, 41)
+    rng = np.random.default_rng(8)
+    trajs = np.clip(_noisy_lines(pr, 1, H, rng, 0.05)[:, 0], 0.02, 4.98).astype(np.float32)
+    al = np.linspace(0, 1, H)[None, :, None]
+    NEW = []
+    for t in range(n_trial):
+        amp = rng.normal(0, 0.5, (B, 1, 2)); ph = rng.integers(1, 4, (B, 1, 1))
+        NEW.append(np.clip(trajs + amp * np.sin(np.pi * ph * al) ** 2, 0.02, 4.98).astype(np.float32))
+    roundtrip = lambda a: norm.unnormalize(torch.as_tensor(norm.normalize(a, "observations"), dtype=torch.float32).numpy(),
+                                           "observations").astype(np.float32)
+
+    class MockModel:                       # stands in for GaussianDiffusionPB.ddim_replan: row id travels in walls_loc
+        def __init__(self):
+            self.trial = 0
+        def ddim_replan(self, normed, cond, walls_loc, dn_steps):
+            ids = walls_loc[:, 0].long().cpu().numpy()
+            out = torch.as_tensor(norm.normalize(NEW[self.trial][ids], "observations"), dtype=torch.float32, device=normed.device)
+            self.trial += 1
+            return out
+
+    rp = KukaDiffusionReplanner(MockModel(), norm, dict(use_ddim=True, dn_steps=3, n_replan_trial=n_trial), DEV)
+    chk = RM2DCollisionChecker(normalizer=None, device=DEV); chk.use_collision_eps = True; chk.collision_eps = 0.08
+    rp.set_collision_checker(chk)
+    walls = torch.arange(B, dtype=torch.float32)[:, None].repeat(1, 12)
+    geom = dict(robot="maze2d", env_id=np.arange(B, dtype=np.int32), cen=pr["boxes"], hext=0.5)
+    new, suc, cnt = rp.replan_batch(trajs, walls, geom)
+    n_fix = n_fail = 0
+    for b in range(B):
+        ck = replan_ref.Maze2DChecker(pr["boxes"][b], 0.5)
+        r_new, r_suc, r_cnt = replan_ref.replan_collision_section(trajs[b], ck, lambda t, tr: roundtrip(NEW[t][b]), n_trial)
+        assert np.array_equal(new[b], r_new), "problem %d: replanned path differs" % b
+        assert bool(suc[b]) == r_suc and int(cnt[b]) == r_cnt, "problem %d: %s/%d vs %s/%d" % (b, suc[b], cnt[b], r_suc, r_cnt)
+        had = ck.point_collides(trajs[b]).any()
+        n_fix += int(had and r_suc); n_fail += int(had and not r_suc)
+    assert n_fix >= 3 and n_fail >= 3, (n_fix, n_fail)
+
+
+def test_replanner_single_trajectory_with_diffusion():
+    """reference signature (one trajectory, env object) through the real batched ddim_replan"""
+    from diffuser.guides.kuka_replan import KukaDiffusionReplanner
+    from diffuser.guides import RM2DCollisionChecker
+    from diffuser.datasets import DatasetNormalizer, RAND_MAZE_MIN, RAND_MAZESIZE_55
+    norm = DatasetNormalizer({"observations": (RAND_MAZE_MIN, RAND_MAZESIZE_55)})
+    d = dropin("m2d"); d.ddim_num_inference_steps = 8
+    rp = KukaDiffusionReplanner(d, norm, dict(use_ddim=True, dn_steps=3, n_replan_trial=2), DEV)
+    chk = RM2DCollisionChecker(normalizer=None, device=DEV); chk.use_collision_eps = True; chk.collision_eps = 0.08
+    rp.set_collision_checker(chk)
+    pr = synth.make_problems("m2d", 1, 5)
+    class Env: pass
+    env = Env(); env.wall_centers = pr["boxes"][0]; env.wall_hext = 0.5
+    H = 48
+    line = np.stack([np.linspace(0.3, 4.7, H), np.linspace(0.3, 4.7, H)], -1).astype(np.float32)
+    new, ok, cnt = rp.replan_collision_section_less_check(env, line, torch.tensor(pr["walls"][:1]))
+    assert new.shape == (H, 2) and np.isfinite(new).all() and isinstance(ok, bool) and cnt >= H
+
+
 def test_maze2d_collision_edge_cases():
     cen = np.array([[[2.5, 2.5]]]); hext = 0.5
     H = 8

@@ -173,6 +173,35 @@ def test_pick_multi_horizon_order():
     assert (h1 == 0).all() and np.array_equal(s1, ch) and np.array_equal(su1, su) and np.array_equal(t1, tt)
 
 
+def test_replan_oracle_sections_and_acceptance():
+    """oracle/replan_ref.py on a hand case: a straight line through one wall, re-sampled as a detour"""
+    from oracle import replan_ref
+    assert replan_ref.expanded_subtraj(48, 10, 12).tolist() == list(range(7, 15))      # 3 -> 8 waypoints, grown left first
+    assert replan_ref.expanded_subtraj(48, 0, 1).tolist() == list(range(0, 8))         # clipped at the start
+    assert [r.tolist() for r in replan_ref.split_runs([1, 2, 5, 6, 7])] == [[1, 2], [5, 6, 7]]
+    H = 48
+    cen = np.array([[2.5, 2.5]]); hext = 0.5
+    line = np.stack([np.linspace(0.5, 4.5, H), np.full(H, 2.5)], -1).astype(np.float32)
+    chk = replan_ref.Maze2DChecker(cen, hext)
+    col = np.nonzero(chk.point_collides(line))[0]
+    assert len(col) > 0 and col[0] > 0 and col[-1] < H - 1
+    bump = line.copy()
+    bump[:, 1] += 1.2 * np.sin(np.pi * np.linspace(0, 1, H)).astype(np.float32) ** 2          # passes above the wall
+    calls = []
+    def resample(trial, traj):
+        calls.append(trial)
+        return line if trial == 0 else bump          # first trial changes nothing -> rejected, second is the detour
+    new, ok, cnt = replan_ref.replan_collision_section(line, chk, resample)
+    assert calls == [0, 1] and ok and cnt > H
+    assert not chk.point_collides(new).any()
+    sec = replan_ref.expanded_subtraj(H, int(col[0]), int(col[-1]))
+    untouched = np.setdiff1d(np.arange(H), sec)
+    assert np.array_equal(new[untouched], line[untouched]) and np.array_equal(new[sec], bump[sec])
+    # nothing ever fits: all trials used, failure reported, trajectory unchanged
+    new2, ok2, cnt2 = replan_ref.replan_collision_section(line, chk, lambda trial, traj: line, n_replan_trial=3)
+    assert not ok2 and np.array_equal(new2, line) and cnt2 > H
+
+
 # ------------------------------------------------------------------ live reference (build container only)
 needs_ref = pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
 
