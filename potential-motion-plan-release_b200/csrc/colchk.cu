@@ -20,20 +20,36 @@ namespace {
 constexpr int WARPS = 8;
 constexpr int MAXW = 32;  // walls per environment
 
+// The reference tests a float32 point against float64 box bounds with strict inequalities
+// (rand_rec_group.py:216-237).  For a float32 x and a float64 bound T:
+//   (double)x > T  <=>  x >= up(T),   up(T)   = smallest float32 whose value exceeds T
+//   (double)x < T  <=>  x <= down(T), down(T) = largest  float32 whose value is below T
+// so the bounds are converted ONCE per wall and the per-point test is four float32 compares (exactly the
+// reference's truth value, NaNs included) instead of eight float64 ones.
 struct Maze {
-    const double* lo_m;  // [nw][2]  (c-h)-m
-    const double* hi_m;  // [nw][2]  (c+h)+m
+    const float* lo_f;  // [nw][2]  up((c-h)-m)
+    const float* hi_f;  // [nw][2]  down((c+h)+m)
     int nw;
     float lox, loy, hix, hiy;
 };
+
+__device__ __forceinline__ float strictly_above(double t) {
+    float f = __double2float_ru(t);
+    if ((double)f <= t) f = nextafterf(f, INFINITY);
+    return f;
+}
+__device__ __forceinline__ float strictly_below(double t) {
+    float f = __double2float_rd(t);
+    if ((double)f >= t) f = nextafterf(f, -INFINITY);
+    return f;
+}
 
 __device__ __forceinline__ bool m2d_valid(const Maze& e, float x, float y) {
     return x >= e.lox && y >= e.loy && x <= e.hix && y <= e.hiy;
 }
 __device__ __forceinline__ bool m2d_collides(const Maze& e, float x, float y) {
-    const double px = (double)x, py = (double)y;
     for (int i = 0; i < e.nw; ++i)
-        if (px > e.lo_m[2 * i] && py > e.lo_m[2 * i + 1] && px < e.hi_m[2 * i] && py < e.hi_m[2 * i + 1]) return true;
+        if (x >= e.lo_f[2 * i] && y >= e.lo_f[2 * i + 1] && x <= e.hi_f[2 * i] && y <= e.hi_f[2 * i + 1]) return true;
     return false;
 }
 // _state_fp: returns ok, bumps cnt by one only when the state is inside the limits
@@ -64,20 +80,21 @@ __device__ bool m2d_edge_fp(const Maze& e, float ax, float ay, float bx, float b
     return true;
 }
 
-__device__ __forceinline__ void load_maze(Maze& e, double* sm, const double* cen, const double* hext, int env,
+__device__ __forceinline__ void load_maze(Maze& e, float* sm, const double* cen, const double* hext, int env,
                                           int nw, double margin, int lane) {
-    // each lane prepares one wall: identical double ops to the reference ((c-h)-m, (c+h)+m)
+    // each lane prepares one wall: identical double ops to the reference ((c-h)-m, (c+h)+m), then the exact
+    // float32 thresholds
     for (int i = lane; i < nw; i += 32) {
         const double* c = cen + ((size_t)env * nw + i) * 2;
         const double* h = hext + ((size_t)env * nw + i) * 2;
-        sm[2 * i] = __dsub_rn(__dsub_rn(c[0], h[0]), margin);
-        sm[2 * i + 1] = __dsub_rn(__dsub_rn(c[1], h[1]), margin);
-        sm[2 * MAXW + 2 * i] = __dadd_rn(__dadd_rn(c[0], h[0]), margin);
-        sm[2 * MAXW + 2 * i + 1] = __dadd_rn(__dadd_rn(c[1], h[1]), margin);
+        sm[2 * i] = strictly_above(__dsub_rn(__dsub_rn(c[0], h[0]), margin));
+        sm[2 * i + 1] = strictly_above(__dsub_rn(__dsub_rn(c[1], h[1]), margin));
+        sm[2 * MAXW + 2 * i] = strictly_below(__dadd_rn(__dadd_rn(c[0], h[0]), margin));
+        sm[2 * MAXW + 2 * i + 1] = strictly_below(__dadd_rn(__dadd_rn(c[1], h[1]), margin));
     }
     __syncwarp();
-    e.lo_m = sm;
-    e.hi_m = sm + 2 * MAXW;
+    e.lo_f = sm;
+    e.hi_f = sm + 2 * MAXW;
     e.nw = nw;
 }
 
@@ -85,14 +102,22 @@ __global__ void __launch_bounds__(WARPS * 32) maze2d_swept_kernel(
     const float* __restrict__ traj, const int32_t* __restrict__ env_id, int N, int H, const double* __restrict__ cen,
     const double* __restrict__ hext, int nw, float lox, float loy, float hix, float hiy, double eps, double margin,
     int legacy_div, uint8_t* __restrict__ valid, int32_t* __restrict__ nchk) {
-    __shared__ double sm[WARPS][4 * MAXW];
+    __shared__ float sm[WARPS][4 * MAXW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.x * WARPS + warp;
     if (n >= N) return;
+    // the trajectory does not depend on the environment: its first 64 segments are requested before the
+    // env_id -> walls chain of dependent loads, so the two DRAM round trips overlap
+    const float2* t = reinterpret_cast<const float2*>(traj + (size_t)n * H * 2);
+    float2 pa[2], pb[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int seg = it * 32 + lane;
+        if (seg < H - 1) { pa[it] = __ldg(t + seg); pb[it] = __ldg(t + seg + 1); }
+    }
     Maze e;
     e.lox = lox; e.loy = loy; e.hix = hix; e.hiy = hiy;
     load_maze(e, sm[warp], cen, hext, env_id[n], nw, margin, lane);
-    const float2* t = reinterpret_cast<const float2*>(traj + (size_t)n * H * 2);
     int total = 0;
     bool ok_all = true;
     for (int base = 0; base < H - 1 && ok_all; base += 32) {
@@ -100,7 +125,7 @@ __global__ void __launch_bounds__(WARPS * 32) maze2d_swept_kernel(
         bool ok = true;
         int cnt = 0;
         if (seg < H - 1) {
-            const float2 a = t[seg], b = t[seg + 1];
+            const float2 a = base < 64 ? pa[base >> 5] : __ldg(t + seg), b = base < 64 ? pb[base >> 5] : __ldg(t + seg + 1);
             ok = m2d_edge_fp(e, a.x, a.y, b.x, b.y, eps, legacy_div, cnt);
         }
         const unsigned fail = __ballot_sync(0xffffffffu, !ok);
@@ -121,7 +146,7 @@ __global__ void __launch_bounds__(WARPS * 32) maze2d_points_kernel(
     const float* __restrict__ traj, const int32_t* __restrict__ env_id, int N, int H, const double* __restrict__ cen,
     const double* __restrict__ hext, int nw, float lox, float loy, float hix, float hiy, double margin,
     int32_t* __restrict__ ncol, uint8_t* __restrict__ ptcol) {
-    __shared__ double sm[WARPS][4 * MAXW];
+    __shared__ float sm[WARPS][4 * MAXW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.x * WARPS + warp;
     if (n >= N) return;

@@ -743,6 +743,12 @@ EncodeFn get_encode() {
 
 using MapKey = std::tuple<const void*, int, int, int, int, int, int>;
 std::map<MapKey, CUtensorMap> g_maps;
+// encoded tensor maps are cached per (address, shape): a steady workload re-uses a few hundred of them; a service
+// that sees many distinct batch sizes would grow the cache without bound, so it is simply dropped past a cap
+void remember_map(const MapKey& key, const CUtensorMap& m) {
+    if (g_maps.size() > 65536) g_maps.clear();
+    g_maps[key] = m;
+}
 
 // activation plane [R][H][ld] BF16 -> 3-D map (C, H, R), box (64, H, S)
 int act_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int H, int R, int ld, int S, int bk) {
@@ -760,7 +766,7 @@ int act_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int H, int R, in
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation C=%d H=%d R=%d ld=%d S=%d) failed: %d", C, H, R, ld, S, (int)r);
-    g_maps[key] = *out;
+    remember_map(key, *out);
     return 0;
 }
 // stride-2 gather: rows (2j + parity) -> 4-D map (C, parity, H/2, R), box (64, 1, HJ, S)
@@ -779,7 +785,7 @@ int act_map4(CUtensorMap* out, const __nv_bfloat16* base, int C, int Hin, int R,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(strided activation C=%d H=%d R=%d ld=%d) failed: %d", C, Hin, R, ld, (int)r);
-    g_maps[key] = *out;
+    remember_map(key, *out);
     return 0;
 }
 // weight plane [taps*N][C] BF16 -> 2-D map (C, taps*N), box (64, NT)
@@ -798,7 +804,7 @@ int w_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int rows, int NT, 
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight C=%d rows=%d NT=%d) failed: %d", C, rows, NT, (int)r);
-    g_maps[key] = *out;
+    remember_map(key, *out);
     return 0;
 }
 
@@ -831,7 +837,7 @@ int st_map(CUtensorMap* out, const void* base, bool f32, int C, int Hout, int R,
     }
     PMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(store C=%d H=%d R=%d ld=%d S=%d HJ=%d) failed: %d", C, Hout, R, ld, S,
                 HJ, (int)r);
-    g_maps[key] = *out;
+    remember_map(key, *out);
     return 0;
 }
 
