@@ -36,6 +36,7 @@ METRIC = "plans/sec (composed-potential DDPM sampling)"
 UNIT = "plans/s"
 # algorithmic conv FLOPs per plan for DDPM-100, Maze2D H=48: 4 * 0.385 GF * 100
 FLOP_PER_PLAN = 154.0e9
+FLOP_PER_PLAN_BY_WORKLOAD = {"maze2d": 154.0e9, "kuka": 167.0e9, "dualkuka": 475.7e9}   # SURVEY 8(d), DDPM-100
 
 
 def peaks():
@@ -149,6 +150,9 @@ def main():
                     help="problems per step per GPU (BASELINE configs[1]: 10k, half Static2 / half Concave)")
     ap.add_argument("--row-chunk", type=int, default=int(os.environ.get("PMP_ROW_CHUNK", "10360")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="maze2d", choices=["maze2d", "kuka", "dualkuka"],
+                    help="maze2d = BASELINE configs[1] (the bench line); kuka / dualkuka = configs[3] / [4] sampling with "
+                         "sphere-model collision scoring, extra measurements under the same harness")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -178,7 +182,8 @@ def main():
     import ctypes as C
     ts = list(range(T_DIFF - 1, -1, -1))
     off = 0
-    for pi, (fam, n) in enumerate(((FAMILY, Bp - Bp // 2), (FAMILY2, Bp // 2))):
+    fams = ((FAMILY, Bp - Bp // 2), (FAMILY2, Bp // 2)) if args.workload == "maze2d" else ((args.workload, Bp),)
+    for pi, (fam, n) in enumerate(fams):
         if n == 0:
             continue
         a = synth.arch(fam)
@@ -201,6 +206,7 @@ def main():
                   boxes=torch.tensor(pr["boxes"]).to(dev), lo_d=torch.tensor(lo, device=dev), hi_d=torch.tensor(hi, device=dev),
                   env_id=torch.arange(n, dtype=torch.int32, device=dev), coefs=diffusion.step_coefs_ddpm(ts))
         P_["hext"] = torch.full_like(P_["boxes"], float(pr["hext"]))
+        P_["boxes_np"], P_["hext_f"] = np.asarray(pr["boxes"], np.float32), float(pr["hext"])
         for k in ("start", "goal", "walls"):
             P_[k + "_d"] = P_[k + "_h"].to(dev)
         parts.append(P_)
@@ -209,9 +215,19 @@ def main():
     # weak scaling: every rank plans its own Bp problems of a (world*Bp)-problem job
     lo_p, hi_p = shard.shard_range(world * Bp, rank, world)
 
+    kuka_sph = None
+    if args.workload != "maze2d":
+        from diffuser.guides.kuka_colchk import sphere_table, arm_bases, TABLE_Z
+        kuka_sph = sphere_table()
+
     def collide(P_, x):
         un = pmp_b200.unnormalize(x, P_["lo_d"], P_["hi_d"])
         n = P_["n"]
+        if kuka_sph is not None:          # analytic sphere-link model (declared deviation from pybullet)
+            n_arms = 2 if P_["fam"] == "dualkuka" else 1
+            r = pmp_b200.colchk_kuka(un, P_["env_id"], P_["boxes_np"], P_["hext_f"], n_arms,
+                                     arm_bases(n_arms), kuka_sph, TABLE_Z)
+            return un, r["valid"], r["nchk"]
         valid = torch.empty(n, dtype=torch.uint8, device=dev)
         nchk = torch.empty(n, dtype=torch.int32, device=dev)
         rc = L.pmp_colchk_maze2d_swept(C.c_void_p(un.data_ptr()), C.c_void_p(P_["env_id"].data_ptr()), n, P_["H"],
@@ -306,12 +322,12 @@ def main():
             "issued_tensor_tflops": 3 * achieved if is_tc else 0.0,
             "launches": conv_n, "avg_launch_ms": conv_ms / max(conv_n, 1), "share_of_step": tot_conv_ms / ms,
             "peak_source": pk["src"] + " bf16 sustained (burst %.1f)" % pk["tf_burst"],
-            "whole_step_algorithmic_tflops": value / world * FLOP_PER_PLAN / 1e12}
+            "whole_step_algorithmic_tflops": value / world * FLOP_PER_PLAN_BY_WORKLOAD[args.workload] / 1e12}
 
     # ---- HBM-bound kernels of the path, timed alone on inputs larger than L2: fused sampler update
     # and swept collision check; achieved = algorithmic bytes / kernel time (CUDA events, 20 launches after warm-up)
     aux = []
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.workload == "maze2d":
         def timed(fn, reps=20):
             for _ in range(3):
                 fn()
@@ -356,7 +372,7 @@ def main():
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.workload == "maze2d":
             threads = os.cpu_count() or 1
             v_cpu, t_cpu = cpu_port_plans_per_sec(64, 5, threads)
             cpu = {"value": v_cpu, "unit": UNIT, "cores": threads, "kind": "port",
@@ -365,7 +381,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 (fp32-accumulate, ~fp32-equivalent operands)", "data": "synthetic",
-            "config": {"workload": "maze2d static2 (nw3, hExt 0.7) + concave (nw7): %d + %d problems per step, DDPM-100 H=48 cond_w=2 + swept collision scoring (eps 0.08)" % tuple(P_["n"] for P_ in parts) if len(parts) == 2 else "maze2d_static2_nw3_hExt07 DDPM-100 H=48 cond_w=2 + swept collision scoring (eps 0.08)",
+            "config": {"workload": ("maze2d static2 (nw3, hExt 0.7) + concave (nw7): %d + %d problems per step, DDPM-100 H=48 cond_w=2 + swept collision scoring (eps 0.08)" % tuple(P_["n"] for P_ in parts)) if args.workload == "maze2d" and len(parts) == 2 else "%s: %d problems per step, DDPM-100 H=%d cond_w=2 + collision scoring" % (parts[0]["fam"], parts[0]["n"], parts[0]["H"]),
                        "plans_per_step_per_gpu": Bp, "row_chunk": args.row_chunk, "rng": "in-kernel Philox4x32-10",
                        "l2": "per-pass working set (%.1f GB of activations) exceeds the 126 MB L2" % (
                            pmp_b200.lib().pmp_model_workspace_bytes(parts[0]["eng"].h) / 1e9),
