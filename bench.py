@@ -36,7 +36,8 @@ METRIC = "plans/sec (composed-potential DDPM sampling)"
 UNIT = "plans/s"
 # algorithmic conv FLOPs per plan for DDPM-100, Maze2D H=48: 4 * 0.385 GF * 100
 FLOP_PER_PLAN = 154.0e9
-FLOP_PER_PLAN_BY_WORKLOAD = {"maze2d": 154.0e9, "kuka": 167.0e9, "dualkuka": 475.7e9}   # SURVEY 8(d), DDPM-100
+FLOP_PER_PLAN_BY_WORKLOAD = {"maze2d": 154.0e9, "kuka": 167.0e9, "dualkuka": 475.7e9,    # SURVEY 8(d), DDPM-100
+                             "comp2": 2 * 154.0e9, "comp3": 3 * 154.0e9}   # K full CFG pairs (nominal: shared uncond halves are not discounted)
 
 
 def peaks():
@@ -150,7 +151,7 @@ def main():
                     help="problems per step per GPU (BASELINE configs[1]: 10k, half Static2 / half Concave)")
     ap.add_argument("--row-chunk", type=int, default=int(os.environ.get("PMP_ROW_CHUNK", "10360")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="maze2d", choices=["maze2d", "kuka", "dualkuka"],
+    ap.add_argument("--workload", default="maze2d", choices=["maze2d", "kuka", "dualkuka", "comp2", "comp3"],
                     help="maze2d = BASELINE configs[1] (the bench line); kuka / dualkuka = configs[3] / [4] sampling with "
                          "sphere-model collision scoring, extra measurements under the same harness")
     args = ap.parse_args()
@@ -182,7 +183,9 @@ def main():
     import ctypes as C
     ts = list(range(T_DIFF - 1, -1, -1))
     off = 0
-    fams = ((FAMILY, Bp - Bp // 2), (FAMILY2, Bp // 2)) if args.workload == "maze2d" else ((args.workload, Bp),)
+    comp = {"comp2": ("m2d", "m2d_nw3"), "comp3": ("m2d", "m2d", "m2d")}.get(args.workload)
+    fams = ((FAMILY, Bp - Bp // 2), (FAMILY2, Bp // 2)) if args.workload == "maze2d" else (
+        (("m2d", Bp),) if comp else ((args.workload, Bp),))
     for pi, (fam, n) in enumerate(fams):
         if n == 0:
             continue
@@ -209,6 +212,28 @@ def main():
         P_["boxes_np"], P_["hext_f"] = np.asarray(pr["boxes"], np.float32), float(pr["hext"])
         for k in ("start", "goal", "walls"):
             P_[k + "_d"] = P_[k + "_h"].to(dev)
+        P_["engs"], P_["walls_list_d"], P_["w"] = [eng], [P_["walls_d"]], [2.0]
+        if comp:
+            # K composed potentials: model k sees its own obstacle subset; the checker sees the union of all boxes
+            same = comp[1] == comp[0]
+            bx, hx = [P_["boxes"]], [P_["hext"]]
+            for k in range(1, len(comp)):
+                prk = synth.make_problems(comp[k], n, 2000 + 10 * rank + k)
+                if same:
+                    ek = eng
+                else:
+                    ak = synth.arch(comp[k])
+                    mk = TemporalUnet_WCond(**ak["unet"]); mk.load_state_dict(synth.synth_state_dict(mk.state_dict(), 1 + k))
+                    dk = GaussianDiffusionPB(mk, **ak["diffusion"]).to(dev).eval(); dk.horizon = H; dk.rng_mode = "philox"
+                    P_.setdefault("diffs", [diffusion]).append(dk)
+                    ek = dk.model.engine(T_DIFF); ek.set_row_chunk(args.row_chunk)
+                P_["engs"].append(ek)
+                P_["walls_list_d"].append(torch.tensor(prk["walls"]).to(dev))
+                P_["w"].append(2.0)
+                bk = torch.tensor(prk["boxes"]).to(dev)
+                bx.append(bk); hx.append(torch.full_like(bk, float(prk["hext"])))
+            P_["boxes"], P_["hext"] = torch.cat(bx, 1).contiguous(), torch.cat(hx, 1).contiguous()
+            P_["walls_h"] = torch.cat([w_.cpu() for w_ in P_["walls_list_d"]], 1).pin_memory()
         parts.append(P_)
         off += n
     H, D = parts[0]["H"], parts[0]["D"]
@@ -216,7 +241,7 @@ def main():
     lo_p, hi_p = shard.shard_range(world * Bp, rank, world)
 
     kuka_sph = None
-    if args.workload != "maze2d":
+    if args.workload in ("kuka", "dualkuka"):
         from diffuser.guides.kuka_colchk import sphere_table, arm_bases, TABLE_Z
         kuka_sph = sphere_table()
 
@@ -240,9 +265,8 @@ def main():
     def step_resident(i):
         vs = []
         for P_ in parts:
-            eng = P_["eng"]
-            wemb = eng.wall_embed(P_["walls_d"])
-            x = pmp_b200.sample([eng], [wemb], [2.0], P_["start_d"], P_["goal_d"], P_["H"], 0, ts, P_["coefs"], noise=None,
+            wembs = [e_.wall_embed(w_) for e_, w_ in zip(P_["engs"], P_["walls_list_d"])]
+            x = pmp_b200.sample(P_["engs"], wembs, P_["w"], P_["start_d"], P_["goal_d"], P_["H"], 0, ts, P_["coefs"], noise=None,
                                 seed=1234 + i, row_offset=lo_p + P_["off"])
             un, valid, nchk = collide(P_, x)
             vs.append(valid)
@@ -251,12 +275,43 @@ def main():
             shard.gather_rows(valid[:, None], world * Bp, world)
         return valid
 
+    _pol = {}
+
+    def comp_policy(P_):
+        if "p" not in _pol:
+            from diffuser.guides import PolicyCompose
+            from diffuser.datasets import DatasetNormalizer, RAND_MAZE_MIN, RAND_MAZESIZE_55
+            norm = DatasetNormalizer({"observations": (RAND_MAZE_MIN, RAND_MAZESIZE_55)})
+            dms = P_.get("diffs") or [P_["diffusion"]] * len(comp)
+            nwc = [w_.shape[1] // 2 for w_ in P_["walls_list_d"]]
+            po = dict(num_walls_c=nwc, wall_dim=2, comp_type="direct", ddim_steps=8, wall_is_dyn=None, uncond_base_idx=0,
+                      ddim_eta=0.0)
+            _pol["p"] = PolicyCompose(dms, [norm] * len(dms), False, False, po)
+            lo_, hi_ = P_["lo_d"].cpu().numpy(), P_["hi_d"].cpu().numpy()
+            P_["start_un"] = synth.unnormalize(P_["start_h"].numpy(), lo_, hi_)
+            P_["goal_un"] = synth.unnormalize(P_["goal_h"].numpy(), lo_, hi_)
+        return _pol["p"]
+
     def step_e2e(i):
         outs = []
         for P_ in parts:
             Hh = P_["H"]
             cond = {0: P_["start_h"].to(dev, non_blocking=True), Hh - 1: P_["goal_h"].to(dev, non_blocking=True)}
             walls = P_["walls_h"].to(dev, non_blocking=True)
+            if comp:
+                # public composition API: PolicyCompose.__call__ (un-normalised conditions in, Trajectories out)
+                traj = comp_policy(P_)({0: P_["start_un"], Hh - 1: P_["goal_un"]}, walls)[1]
+                un = torch.as_tensor(traj.observations, device=dev)
+                n_ = P_["n"]
+                valid = torch.empty(n_, dtype=torch.uint8, device=dev); nchk = torch.empty(n_, dtype=torch.int32, device=dev)
+                rc = L.pmp_colchk_maze2d_swept(C.c_void_p(un.data_ptr()), C.c_void_p(P_["env_id"].data_ptr()), n_, Hh,
+                                               C.c_void_p(P_["boxes"].data_ptr()), C.c_void_p(P_["hext"].data_ptr()),
+                                               P_["boxes"].shape[1], 0.0, 0.0, 5.0, 5.0, 0.08, 0.01, 1,
+                                               C.c_void_p(valid.data_ptr()), C.c_void_p(nchk.data_ptr()),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                assert rc == 0, L.pmp_last_error()
+                outs.append((traj.observations, valid.cpu()))
+                continue
             P_["diffusion"].philox_seed = 99 + i
             x = P_["diffusion"](cond, walls)                 # public drop-in API (GaussianDiffusionPB.forward)
             un, valid, nchk = collide(P_, x)
@@ -381,7 +436,10 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 (fp32-accumulate, ~fp32-equivalent operands)", "data": "synthetic",
-            "config": {"workload": ("maze2d static2 (nw3, hExt 0.7) + concave (nw7): %d + %d problems per step, DDPM-100 H=48 cond_w=2 + swept collision scoring (eps 0.08)" % tuple(P_["n"] for P_ in parts)) if args.workload == "maze2d" and len(parts) == 2 else "%s: %d problems per step, DDPM-100 H=%d cond_w=2 + collision scoring" % (parts[0]["fam"], parts[0]["n"], parts[0]["H"]),
+            "config": {"workload": ("maze2d static2 (nw3, hExt 0.7) + concave (nw7): %d + %d problems per step, DDPM-100 H=48 cond_w=2 + swept collision scoring (eps 0.08)" % tuple(P_["n"] for P_ in parts)) if args.workload == "maze2d" and len(parts) == 2 else "%s: %d problems per step, DDPM-100 H=%d cond_w=2 + collision scoring" % (
+                ({"comp2": "maze2d composition K=2 (two models: 6 walls + 3 walls)",
+                  "comp3": "maze2d composition K=3 (one model, three 6-wall subsets; shared unconditional half)"}.get(args.workload)
+                 or parts[0]["fam"]), parts[0]["n"], parts[0]["H"]),
                        "plans_per_step_per_gpu": Bp, "row_chunk": args.row_chunk, "rng": "in-kernel Philox4x32-10",
                        "l2": "per-pass working set (%.1f GB of activations) exceeds the 126 MB L2" % (
                            pmp_b200.lib().pmp_model_workspace_bytes(parts[0]["eng"].h) / 1e9),

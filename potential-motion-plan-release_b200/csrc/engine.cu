@@ -1258,6 +1258,7 @@ int pmp_sample(const pmp_sample_args* a, void* stream) {
     for (int k = 0; k < K; ++k)
         PMP_CUDA_OK(cudaMallocAsync((void**)&wtab[k], (size_t)Bc * wall_table_width(a->models[k]) * sizeof(float), st));
     const long tstride = (long)(a->n_steps + 1) * H * D;
+    const bool dedup = getenv("PMP_NO_UNCOND_DEDUP") == nullptr;   // switch for the equivalence test
     int rc = 0;
     for (int b0 = 0; b0 < B && !rc; b0 += Bc) {
         const int Bn = (B - b0) < Bc ? (B - b0) : Bc;
@@ -1285,6 +1286,18 @@ int pmp_sample(const pmp_sample_args* a, void* stream) {
             }
             for (int k = 0; k < K && !rc; ++k) {
                 float* e2 = epsb + (size_t)k * 2 * tile;
+                // the unconditional half does not see the walls: potentials that are the SAME network (the reference's
+                // "one model, K obstacle subsets" compositions, config/comp) share it bit for bit, so it is evaluated
+                // once and only the conditional rows are run for the repeats
+                int dup = -1;
+                for (int j = 0; j < k && dedup; ++j)
+                    if (a->models[j] == a->models[k]) { dup = j; break; }
+                if (dup >= 0) {
+                    rc = eps_rows(a->models[k], x2, t2, wtab[k], Bn, Bn, H, e2, nullptr, nullptr, st);
+                    ec[k] = e2;
+                    eu[k] = eu[dup];
+                    continue;
+                }
                 rc = eps_rows(a->models[k], x2, t2, wtab[k], Bn, 2 * Bn, H, e2, nullptr, nullptr, st);
                 ec[k] = e2;
                 eu[k] = e2 + n;

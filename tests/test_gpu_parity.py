@@ -1,5 +1,7 @@
 """GPU parity tests proper: the CUDA path (through the C ABI / the drop-in classes) against the
 golden vectors frozen from the reference and against the CPU oracle on the same seeded inputs."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -10,6 +12,7 @@ from util import (golden, assert_eps_close, ddpm_coefs, ddim_coefs, pad_noise, T
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 _models = {}
 
@@ -218,6 +221,39 @@ def test_dropin_forward_api_and_philox():
         assert not torch.equal(full, other)
     finally:
         d.rng_mode = "torch"
+
+
+def test_compose_same_model_shares_unconditional_half():
+    """K potentials that are one network (config/comp "gsd" compositions): the unconditional half is evaluated once;
+    the sampled trajectories must equal, bit for bit, those of the K-fold evaluation"""
+    import subprocess, sys, json as _json
+    code = r"""
+import sys, json, hashlib, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from oracle import synth, unet_ref
+import pmp_b200
+from diffuser.models import TemporalUnet_WCond, GaussianDiffusionPB
+DEV = "cuda:0"
+a = synth.arch("m2d")
+m = TemporalUnet_WCond(**a["unet"]); m.load_state_dict(unet_ref.synth_weights(a["unet"], 1))
+d = GaussianDiffusionPB(m, **a["diffusion"]).to(DEV).eval(); eng = d.model.engine(100)
+B, H = 24, 48
+pr = synth.make_problems("m2d", B, 3)
+lo, hi = pr["lo"], pr["hi"]
+start = torch.tensor(synth.normalize(pr["start"], lo, hi), device=DEV); goal = torch.tensor(synth.normalize(pr["goal"], lo, hi), device=DEV)
+w1 = eng.wall_embed(torch.tensor(pr["walls"], device=DEV)); w2 = eng.wall_embed(torch.tensor(pr["walls"][::-1].copy(), device=DEV))
+w3 = eng.wall_embed(torch.tensor(np.roll(pr["walls"], 5, 0), device=DEV))
+ts = d.ddim_set_timesteps(8); coefs = d.step_coefs_ddim(ts, 0.0, 8)
+x = pmp_b200.sample([eng, eng, eng], [w1, w2, w3], [2.0, 1.5, 1.0], start, goal, H, 1, ts, coefs, noise=None, seed=5, base=1)
+print(json.dumps({"sha": hashlib.sha256(x.cpu().numpy().tobytes()).hexdigest(), "launches": int(pmp_b200.launch_count())}))
+""" % (ROOT, os.path.join(ROOT, "potential-motion-plan-release_b200"))
+    outs = []
+    for env_extra in ({}, {"PMP_NO_UNCOND_DEDUP": "1"}):
+        env = dict(os.environ); env.update(env_extra)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(_json.loads(r.stdout.strip().splitlines()[-1]))
+    assert outs[0]["sha"] == outs[1]["sha"], "sharing the unconditional half changed the result"
 
 
 def test_philox_normal_statistics():
