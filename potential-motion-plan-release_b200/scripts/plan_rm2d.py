@@ -53,6 +53,10 @@ def main(argv=None, robot='maze2d'):
     ap.add_argument('--use_ddim', type=int, default=1)
     ap.add_argument('--cond_w', type=float, default=2.0)
     ap.add_argument('--logdir', default=None)
+    ap.add_argument('--problems', default=None,
+                    help='problem file of the reference (<dataset>-problems.hdf5, needs h5py) or its .npz conversion '
+                         '(pmp_b200.ingest); default: synthetic problems')
+    ap.add_argument('--hext', type=float, default=None, help='half extent of the obstacles in --problems')
     ap.add_argument('--device', default='cuda:0')
     args = ap.parse_args(argv)
     a, diffusion = load_diffusion(args.family, args.logdir, args.device)
@@ -61,6 +65,20 @@ def main(argv=None, robot='maze2d'):
     H = a['horizon']
     n_env, n_prob = args.plan_n_maze, args.n_prob_env
     starts, goals, walls, boxes = [], [], [], []
+    if args.problems:
+        from pmp_b200 import ingest
+        pd = ingest.load_problems(args.problems)
+        wd = 2 if robot == 'maze2d' else 3
+        s_, g_, w_, c_ = ingest.problem_arrays(pd, np.arange(n_env), n_prob, wd)
+        lo, hi = workloads.limits(args.family)
+        norm = DatasetNormalizer({'observations': (lo, hi)})
+        policy = Policy(diffusion, norm, use_ddim=bool(args.use_ddim))
+        hext = args.hext if args.hext is not None else workloads.make_problems(args.family, 1, 0)['hext']
+        res, _ = plan_envs(policy, s_, g_, w_, c_, hext, H, samples_perprob=args.samples_perprob, robot=robot,
+                           n_arms=2 if args.family == 'dualkuka' else 1)
+        res['config'] = vars(args)
+        print(json.dumps(res))
+        return res
     for e in range(n_env):
         # one obstacle layout per environment, n_prob start/goal pairs in it
         pr = workloads.make_problems(args.family, 1, 5000 + e)

@@ -147,3 +147,34 @@ def test_workloads_match_oracle():
     sd1 = unet_ref.synth_weights(a["unet"], 3)
     sd2 = workloads.synth_state_dict({k: torch.empty(s) for k, s in unet_ref.param_shapes(a["unet"]).items()}, 3)
     assert synth.state_dict_digest(sd1) == workloads.state_dict_digest(sd2)
+
+
+def test_problem_file_ingest_npz_roundtrip(tmp_path):
+    """pmp_b200.ingest: the reference's problem-file dict (problems, infos/wall_locations) -> planner arrays
+    (kuka_plan_utils.py:36-57, kuka_plan_env.py:285-313); HDF5 is refused loudly where h5py is missing"""
+    from pmp_b200 import ingest
+    rng = np.random.default_rng(0)
+    n_env, n_prob, nw = 5, 7, 3
+    cen = rng.uniform(0.7, 4.3, (n_env, 1, nw, 2))
+    d = {"problems": rng.uniform(0, 5, (n_env, n_prob, 2, 2)).astype(np.float32),
+         "infos/wall_locations": np.repeat(cen, n_prob, 1).reshape(n_env, n_prob, nw * 2).astype(np.float32),
+         "maze_idx": np.arange(n_env)}
+    p = str(tmp_path / "m2d-problems.npz")
+    ingest.save_problems_npz(d, p)
+    got = ingest.load_problems(p)
+    assert set(got) == set(d) and all(np.array_equal(got[k], d[k]) for k in d)
+    s, g, w, c = ingest.problem_arrays(got, [3, 1], prob_permaze=4, wall_dim=2, prob_start_idx=2)
+    assert s.shape == (2, 4, 2) and g.shape == (2, 4, 2) and w.shape == (2, 4, 6) and c.shape == (2, 3, 2)
+    assert np.array_equal(s[0], d["problems"][3, 2:6, 0]) and np.array_equal(g[1], d["problems"][1, 2:6, 1])
+    assert np.array_equal(w[0, 0], d["infos/wall_locations"][3, 2]) and np.allclose(c[0], cen[3, 0])
+    # training-set layout [n_env, n_prob, nw, >= wall_dim]: only the centre coordinates are kept
+    d4 = dict(d); d4["infos/wall_locations"] = np.concatenate([np.repeat(cen, n_prob, 1), np.ones((n_env, n_prob, nw, 2))], -1)
+    _, _, w4, c4 = ingest.problem_arrays(d4, [0], 2, 2)
+    assert w4.shape == (1, 2, 6) and np.allclose(c4[0], cen[0, 0])
+    with pytest.raises(ValueError):
+        ingest.problem_arrays(got, [0], prob_permaze=99, wall_dim=2)
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            ingest.load_problems(str(tmp_path / "x-problems.hdf5"))
