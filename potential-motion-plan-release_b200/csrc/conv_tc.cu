@@ -1,22 +1,30 @@
-// tcgen05 / TMEM / TMA implicit-GEMM Conv1d (k=5, pad 2, stride 1; plus an optional 1x1 slab)
-// with the fused U-Net epilogues, in error-compensated BF16x3 arithmetic.
+// tcgen05 / TMEM / TMA implicit-GEMM Conv1d (k=5, pad 2, stride 1; stride-2 gather / scatter; plus an optional
+// 1x1 slab) with the fused U-Net epilogues, in error-compensated BF16x3 arithmetic.
 //
 // Replaces the cuDNN conv + native GroupNorm + SiLU + embedding/residual adds of
 //   Conv1dBlock_dd / ResidualTemporalBlock_dd   diffuser/models/helpers.py:88-94, temporal_dd.py:71-74
+//   Downsample1d / Upsample1d                   diffuser/models/helpers.py:38-52
 // and their backward-data counterparts inside torch.autograd.grad (temporal_cond.py:321).
 //
 // GEMM view: M = (samples x horizon) rows, N = output channels, K = taps x input channels.
-//   * one tile = S whole samples (S*H <= 128 rows) x NT channels, so GroupNorm slabs never
-//     straddle tiles and the conv halo is produced by TMA out-of-bounds zero fill: the A tile of
-//     tap k is ONE 3-D box (64 channels, H rows, S samples) of the channels-last activation
-//     tensor started at row k-2;
-//   * operands are BF16 pairs (v ~= hi + lo, |error| ~ 2^-17 |v|); each K block issues
-//     hi*hi + hi*lo + lo*hi into the same FP32 TMEM accumulator -> ~2^-16 relative product
-//     error, which keeps eps within the 1e-3 parity budget where single-pass BF16/TF32 does not
-//     (SURVEY.md 7.3 item 1); algorithmic FLOPs are 1/3 of the issued tensor FLOPs;
-//   * persistent CTAs, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner),
-//     warps 2..5 epilogue; smem ring of NSTAGE stages, two TMEM accumulator stages so the
-//     epilogue of tile i overlaps the main loop of tile i+1.
+//   * one tile = S whole samples (S*H <= 128 rows) x NT channels, so GroupNorm slabs never straddle tiles and the
+//     conv halo is produced by TMA out-of-bounds zero fill: the A tile of tap k is ONE 3-D box (K-block channels,
+//     H rows, S samples) of the channels-last activation plane started at row k-2;
+//   * operands are BF16 pairs (v ~= hi + lo, |error| ~ 2^-17 |v|); each K block issues hi*hi + hi*lo + lo*hi into
+//     the same FP32 TMEM accumulator -> ~2^-16 relative product error, which keeps eps within the 1e-3 parity
+//     budget where single-pass BF16/TF32 does not; algorithmic FLOPs are 1/3 of the issued;
+//   * persistent CTAs, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2..9 epilogue;
+//     shared-memory ring of NSTAGE stages, two TMEM accumulator stages so the epilogue of tile i overlaps the main
+//     loop of tile i+1;
+//   * template <NT, GS, ACC2, CG, TE>: NT tile columns (64/128/192/256), GS GroupNorm group size (0: none), ACC2 a
+//     separate accumulator for the forward residual 1x1 conv, CG = 2 CTA pairs (tcgen05 cta_group::2: M = 256 over
+//     the two SMs of a TPC, each CTA stages its own A rows and half of the B rows; 256-column tiles use 32-channel
+//     K blocks / SWIZZLE_64B), TE the TMA-store epilogue (results staged in swizzled shared-memory tiles and written
+//     by cp.async.bulk.tensor stores).  DESIGN.md 3.1 has the measurements behind these choices.
+// Diagnostics (none of them on by default): PMP_TC_TIMERS=1|2 (+PMP_TC_TIMER_MATCH=N:C1:g) per-role / per-phase cycle
+// counters read through pmp_debug_counters; PMP_TC_DEBUG bit mask -- 1 no epilogue, 2 no direct stores, 4 no
+// identity/yhat loads, 8 no embedding, 16 MMA only (no TMA fill), 32 N=256 issue-rate probe, 64/128 A / B loaded for one
+// tap of five: timing probes whose results are garbage; PMP_TC_WIDE=0 keeps 128-column tiles.
 #include <cuda.h>
 
 #include <map>
