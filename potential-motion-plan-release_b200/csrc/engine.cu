@@ -143,7 +143,7 @@ struct pmp_model {
     float* embE = nullptr; size_t embE_n = 0;   // cfg3 per step: [R][Ctot]
     float* hidb = nullptr; size_t hidb_n = 0;   // cfg3 per step hidden [R][nblk*hid]
     float* ws = nullptr; size_t ws_n = 0;       // activation workspace (floats)
-    int row_chunk = 2048;
+    int row_chunk = 8192;   // rows of the CFG batch per pass (workspace ~1.8 MB per row for the Maze2D U-Net, grown on demand)
     bool keep_fp32 = getenv("PMP_KEEP_FP32") != nullptr;   // diagnostics: fp32 copies of every activation / gradient
     int gemm_path = 3;   // 0 fp32 SIMT, 1 tcgen05 single CTA, 2 operand reuse, 3 CTA pairs + TMA-store epilogue (default)
     std::map<std::string, std::pair<float*, int64_t>> dbg;

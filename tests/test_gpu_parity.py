@@ -300,6 +300,18 @@ def test_policy_and_compose_interfaces():
     assert traj.observations.shape == (B, 40, 2) and np.isfinite(traj.observations).all()
 
 
+def test_plan_rm2d_from_problem_file():
+    """scripts/plan_rm2d.py --problems <npz>: the ingest path end to end (problem dict -> plan_envs -> statistics)"""
+    import subprocess, sys, json as _json
+    script = os.path.join(ROOT, "potential-motion-plan-release_b200", "scripts", "plan_rm2d.py")
+    prob = os.path.join(ROOT, "tests", "golden", "m2d_synth-problems.npz")
+    r = subprocess.run([sys.executable, script, "--family", "m2d", "--plan_n_maze", "6", "--n_prob_env", "20",
+                        "--problems", prob], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = _json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["num_samples"] == 120 and 0.0 <= res["traj_srate"] <= 1.0 and res["total_num_colck"] > 0
+
+
 def test_plan_envs_multi_horizon_composed():
     """composed planner over several horizons end to end (comp_plan_env.py:54-265): K=2 potentials, 3 horizons,
     GPU collision checks + interleaved selection; the chosen path must be the candidate the oracle's scan picks"""
