@@ -86,8 +86,11 @@ int pmp_model_finalize(pmp_model *m);
 int pmp_model_set_row_chunk(pmp_model *m, int rows);
 /* 0: fp32 CUDA-core implicit GEMM everywhere; 1: tcgen05 BF16x3 tensor-core path (single CTA per
  * tile, direct epilogue stores); 2: operand-reuse variant of 1; 3 (default): tcgen05 BF16x3 on CTA
- * pairs (cta_group::2, 256-column tiles) with the TMA-store epilogue.  1-3 fall back per op to the
- * next simpler kernel where a shape does not fit; all tensor-core paths give bit-identical results. */
+ * pairs (cta_group::2, 256-column tiles) with the TMA-store epilogue (16 epilogue warps for the
+ * GroupNorm-backward epilogues); 4: path 3 with 16 epilogue warps everywhere.  1-4 fall back per op to
+ * the next simpler kernel where a shape does not fit; paths 1-3 without 16-warp epilogues give
+ * bit-identical results, the 16-warp epilogues sum the GroupNorm statistics in a different order
+ * (differences ~1e-7 relative). */
 int pmp_model_set_gemm_path(pmp_model *m, int path);
 size_t pmp_model_workspace_bytes(const pmp_model *m);
 

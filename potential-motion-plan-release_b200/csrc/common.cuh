@@ -159,6 +159,7 @@ int launch_conv_tc(const ConvP& p, cudaStream_t st);
 bool conv_tc_eligible(const ConvP& p);
 // same kernel with CTA pairs (cta_group::2, M = 256 across the two SMs of a TPC) for tiles of >= 128 channels
 int launch_conv_tc_pair(const ConvP& p, cudaStream_t st);
+int launch_conv_tc_pair16(const ConvP& p, cudaStream_t st);
 // operand-reuse main loop (conv_tc2.cu): stride-1 convs without a separate second accumulator
 int launch_conv_tc2(const ConvP& p, cudaStream_t st);
 bool conv_tc2_eligible(const ConvP& p);

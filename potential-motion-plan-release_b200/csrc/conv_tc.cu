@@ -81,9 +81,9 @@ struct TcP {
 };
 
 // small-K conv on the CUDA cores for the row owned by this thread (weights staged in smem [t][d][NT])
-template <int NT>
+template <int NT, int CW>
 __device__ __forceinline__ void inline_conv(const ConvP& p, const float* sinl, int ch, int rg, int h, int Hl,
-                                            bool valid, float (&v)[32]) {
+                                            bool valid, float (&v)[CW]) {
     if (!valid) return;
     const int half = p.inl_taps >> 1;
     for (int t = 0; t < p.inl_taps; ++t) {
@@ -92,9 +92,9 @@ __device__ __forceinline__ void inline_conv(const ConvP& p, const float* sinl, i
         const float* xr = p.inl_x + ((size_t)rg * Hl + hh) * p.inl_ld;
         for (int d = 0; d < p.inl_D; ++d) {
             const float xd = __ldg(xr + d);
-            const float4* w = reinterpret_cast<const float4*>(sinl + (t * p.inl_D + d) * NT + ch * 32);
+            const float4* w = reinterpret_cast<const float4*>(sinl + (t * p.inl_D + d) * NT + ch * CW);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < CW / 4; ++k) {
                 const float4 w4 = w[k];
                 v[4 * k] = fmaf(xd, w4.x, v[4 * k]);
                 v[4 * k + 1] = fmaf(xd, w4.y, v[4 * k + 1]);
@@ -105,8 +105,13 @@ __device__ __forceinline__ void inline_conv(const ConvP& p, const float* sinl, i
     }
 }
 
-template <int NT, int GS, bool ACC2, int CG, bool TE>
+template <int NT, int GS, bool ACC2, int CG, bool TE, int NG = 2>
 struct Cfg {
+    // NG epilogue warp groups of 4 warps (one per TMEM lane quarter): 2 groups walk 32-column chunks, 4 groups (16
+    // epilogue warps, path 4) walk 16-column chunks with half the live registers per thread
+    static constexpr int CW = NG == 4 ? 16 : 32;
+    static constexpr int THREADS = 64 + NG * 128;
+    static constexpr int ETHREADS = NG * 128;
     // CG = 2: CTA pair (cta_group::2); each CTA stages its own 128 A rows and NT/2 of the B rows
     // TE: TMA-store epilogue (64 KB of staging tiles: per half of the epilogue warps one fp32 and two BF16 tiles)
     // channels per K block: 64 (one 128-byte swizzle row) except for the 256-column tiles, which take 32-channel
@@ -117,8 +122,8 @@ struct Cfg {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_TILE_BYTES;
     static constexpr int NSTAGE =
         CG == 2 ? (NT == 256 ? 4 : (NT == 128 ? (TE ? 3 : 4) : 3)) : (NT == 64 ? (TE ? 2 : 3) : (NT == 128 ? 3 : 2));
-    static constexpr int STG_HALF_BYTES = 128 * 32 * 4 + 2 * 128 * 32 * 2;   // F | H | L
-    static constexpr int STG_BYTES = TE ? 2 * STG_HALF_BYTES : 0;
+    static constexpr int STG_HALF_BYTES = 128 * CW * 4 + 2 * 128 * CW * 2;   // F | H | L of one warp group
+    static constexpr int STG_BYTES = TE ? NG * STG_HALF_BYTES : 0;
     static constexpr int INL_FLOATS = NT == 64 ? 5 * 16 * 64 : 0;   // inline small-K conv weights [taps][D<=16][64]
     static constexpr int ACC_COLS = NT * (ACC2 ? 2 : 1);
     // two accumulator stages when they fit next to the yhat stash of the GroupNorm-backward epilogue
@@ -127,10 +132,15 @@ struct Cfg {
     // any (NT <= 128); the 256-column tiles fill TMEM with their two accumulator stages and re-read yhat (L2)
     static constexpr bool STASH = NACC * ACC_COLS + NACC * NT <= 512;
     static constexpr int G = GS ? NT / GS : 1;
-    static constexpr int NCH = NT / 32;
+    static constexpr int NCH = NT / CW;
+    // chunks per GroupNorm group: consecutive chunks go to consecutive warp groups, so a group's row partials have
+    // CPG distinct writers (needs CPG <= NG)
+    static constexpr int CPG = (GS > CW) ? GS / CW : 1;
+    static_assert(!GS || CPG <= NG || NG == 2, "a GroupNorm group spans more chunks than there are warp groups");
     // smem: stages | staging tiles | row/slab partials | slab stats | column params | row info | barriers
     static constexpr int TBUF_FLOATS = 0;
-    static constexpr int PART_FLOATS = 2 * 128 * G * 2;
+    static constexpr int PSLOTS = NG == 2 ? 2 : CPG;
+    static constexpr int PART_FLOATS = PSLOTS * 128 * G * 2;
     static constexpr int STAT_FLOATS = 384;
     static constexpr int COL_FLOATS = 4 * NT;
     static constexpr int ROW_INTS = 4 * 128;
@@ -139,9 +149,10 @@ struct Cfg {
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-template <int NT, int GS, bool ACC2, int CG, bool TE>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcP P) {
-    using C = Cfg<NT, GS, ACC2, CG, TE>;
+template <int NT, int GS, bool ACC2, int CG, bool TE, int NG>
+__global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_constant__ TcP P) {
+    using C = Cfg<NT, GS, ACC2, CG, TE, NG>;
+    constexpr int CW = C::CW, ETH = C::ETHREADS;
     constexpr int G = C::G, NCH = C::NCH, NSTAGE = C::NSTAGE, NACC = C::NACC;
     const ConvP& p = P.e;
 
@@ -323,8 +334,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // per-row 16-byte vectors (no shared-memory transposes); GroupNorm statistics are per-row
         // partial sums combined in a fixed order, so results are run-to-run deterministic.
         const int eq = warp & 3;                 // TMEM lane quarter this warp may access
-        const int hf = (warp - 2) >> 2;          // 0/1: which half of the chunks
-        const int etid = threadIdx.x - 64;       // 0..255
+        const int hf = (warp - 2) >> 2;          // warp group 0..NG-1: which chunks
+        const int etid = threadIdx.x - 64;       // 0..ETH-1
         const int mrow = eq * 32 + lane;
         const int act = p.act;
         const float inv_cnt = 1.0f / (float)(HJ * (GS ? GS : 1));
@@ -338,10 +349,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 tlap = now;
             }
         };
+        // writer slot of chunk ch in the row-partial table (NG = 2: the warp group; NG = 4: position of the chunk in its group)
+        auto pslot = [&](int ch) { return NG == 2 ? hf : (ch % C::CPG); };
         // TE: staging tiles of this half of the epilogue warps and the thread that issues its bulk stores
         uint8_t* const sF = stg + hf * C::STG_HALF_BYTES;
-        uint8_t* const sH = sF + 128 * 32 * 4;
-        uint8_t* const sL = sH + 128 * 32 * 2;
+        uint8_t* const sH = sF + 128 * CW * 4;
+        uint8_t* const sL = sH + 128 * CW * 2;
         const bool st_leader = (etid & 127) == 0;
         // free the staging tiles of this half (the bulk stores of the previous chunk have read them)
         auto stage_acquire = [&]() {
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int r0 = ((t2 / P.tilesN) * CG + (int)crank) * S, n0 = (t2 % P.tilesN) * NT;
             const int Sv = max(0, min(S, p.R - r0));
             const int Mv = Sv * HJ;
-            for (int i = etid; i < NT; i += 256) {
+            for (int i = etid; i < NT; i += ETH) {
                 const bool cv = n0 + i < N;
                 scol[i] = (p.bias && cv) ? __ldg(p.bias + n0 + i) : 0.f;
                 scol[NT + i] = (p.gamma && cv) ? __ldg(p.gamma + n0 + i) : 0.f;
@@ -376,15 +389,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 scol[3 * NT + i] = (p.bias2 && cv) ? __ldg(p.bias2 + n0 + i) : 0.f;
             }
             if (C::INL_FLOATS && p.inl_x)
-                for (int i = etid; i < p.inl_taps * p.inl_D * NT; i += 256) {
+                for (int i = etid; i < p.inl_taps * p.inl_D * NT; i += ETH) {
                     const int td = i / NT, nn = i - td * NT;
                     sinl[i] = (n0 + nn < N) ? __ldg(p.inl_w + (size_t)td * N + n0 + nn) : 0.f;
                 }
             if (GS)
-                for (int g = 0; g < G; ++g) {
-                    spart[((hf * 128 + mrow) * G + g) * 2] = 0.f;
-                    spart[((hf * 128 + mrow) * G + g) * 2 + 1] = 0.f;
-                }
+                for (int i = etid; i < C::PART_FLOATS; i += ETH) spart[i] = 0.f;
             // per-row constants
             const bool valid = mrow < Mv;
             const int s_loc = min(mrow / HJ, S - 1);
@@ -398,11 +408,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             tlap = tq1;
             if (P.ctr && P.tmode == 2 && etid == 0) atomicAdd(P.ctr + 0, (unsigned long long)(tq1 - tq0));
             tc_fence_after();
-            epi_bar();
+            epi_barw<ETH>();
             if (P.dbg & 1) {
                 // main-loop-only timing runs: results are garbage
                 tc_fence_before();
-                epi_bar();
+                epi_barw<ETH>();
                 if (etid == 0) {
                     if (CG == 2) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
                     if (P.ctr) atomicAdd(P.ctr + 6, 1ull);
@@ -412,16 +422,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
             const uint32_t tacc = tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)(as * C::ACC_COLS);
             const uint32_t tstash = tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)(NACC * C::ACC_COLS + as * NT);
-            float v[32];
+            float v[CW];
             const int hrow = mrow - s_loc * HJ;
             if (C::INL_FLOATS && p.inl_mode == 1) {
                 // the convolution itself has K = taps*D <= 70: compute it here and park it in the (unused)
                 // accumulator so that the GroupNorm passes below run unchanged
-                for (int ch = hf; ch < NCH; ch += 2) {
+                for (int ch = hf; ch < NCH; ch += NG) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                    inline_conv<NT>(p, sinl, ch, rg, hrow, HJ, valid, v);
-                    tmem_st32(tacc + ch * 32, v);
+                    for (int j = 0; j < CW; ++j) v[j] = 0.f;
+                    inline_conv<NT, CW>(p, sinl, ch, rg, hrow, HJ, valid, v);
+                    tmem_stw<CW>(tacc + ch * CW, v);
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
@@ -429,29 +439,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (GS && p.gn_fwd) {
                 // ---- pass 1: per-row sums of y = acc + bias and y^2 for every group
 #pragma unroll 1
-                for (int ch = hf; ch < NCH; ch += 2) {
-                    tmem_ld32(tacc + ch * 32, v);
-                    constexpr int GPC = (GS && GS < 32) ? 32 / GS : 1;   // groups per chunk
+                for (int ch = hf; ch < NCH; ch += NG) {
+                    tmem_ldw<CW>(tacc + ch * CW, v);
+                    constexpr int GPC = (GS && GS < CW) ? CW / GS : 1;   // groups per chunk
                     float s1[GPC], s2[GPC];
 #pragma unroll
                     for (int g = 0; g < GPC; ++g) s1[g] = s2[g] = 0.f;
-                    add_lds32(scol + ch * 32, v);
+                    add_ldsw<CW>(scol + ch * CW, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < CW; ++j) {
                         const float x = v[j];
-                        s1[GPC > 1 ? j / (32 / GPC) : 0] += x;
-                        s2[GPC > 1 ? j / (32 / GPC) : 0] += x * x;
+                        s1[GPC > 1 ? j / (CW / GPC) : 0] += x;
+                        s2[GPC > 1 ? j / (CW / GPC) : 0] += x * x;
                     }
-                    const int g0 = (ch * 32) / (GS ? GS : 1);
+                    const int g0 = (ch * CW) / (GS ? GS : 1);
 #pragma unroll
                     for (int g = 0; g < GPC; ++g) {
-                        float* d = spart + ((hf * 128 + mrow) * G + g0 + g) * 2;
+                        float* d = spart + ((pslot(ch) * 128 + mrow) * G + g0 + g) * 2;
                         d[0] += s1[g];
                         d[1] += s2[g];
                     }
                 }
                 lap(1);
-                epi_bar();
+                epi_barw<ETH>();
                 {
                     // slab (s, g): the 2*HJ row partials are summed by one thread in 4 independent
                     // chains (fixed order -> deterministic) instead of one dependent LDS+FADD chain
@@ -459,7 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (etid < S * G) {
                     const int s = etid / G, g = etid - s * G;
                     float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
-                    for (int h2 = 0; h2 < 2; ++h2) {
+                    for (int h2 = 0; h2 < C::PSLOTS; ++h2) {
                         const float* base = spart + ((h2 * 128 + s * HJ) * G + g) * 2;
                         int j = 0;
                         for (; j + 4 <= HJ; j += 4) {
@@ -482,7 +492,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     sstat[128 + etid] = rs;
                     if (s < Sv) p.rstd[(size_t)(r0 + s) * 8 + n0 / (GS ? GS : 1) + g] = rs;
                 }
-                epi_bar();
+                epi_barw<ETH>();
                 lap(2);
             }
 
@@ -500,50 +510,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const __nv_bfloat16* idl = p.ident_hi ? p.ident_lo + orow * p.ldi + n0 : nullptr;
                 const float* adp = p.addend ? p.addend + orow * p.ldad + n0 : nullptr;
 #pragma unroll 1
-                for (int ch = hf; ch < NCH; ch += 2) {
-                    tmem_ld32(tacc + ch * 32, v);
-                    add_lds32(scol + ch * 32, v);   // + bias
+                for (int ch = hf; ch < NCH; ch += NG) {
+                    tmem_ldw<CW>(tacc + ch * CW, v);
+                    add_ldsw<CW>(scol + ch * CW, v);   // + bias
                     if (GS && p.gn_fwd) {
-                        constexpr int GPC2 = (GS && GS < 32) ? 32 / GS : 1;
+                        constexpr int GPC2 = (GS && GS < CW) ? CW / GS : 1;
                         float mu[GPC2], rsd[GPC2];
 #pragma unroll
                         for (int g = 0; g < GPC2; ++g) {
-                            const int sl = slab0 + (ch * 32) / (GS ? GS : 1) + g;
+                            const int sl = slab0 + (ch * CW) / (GS ? GS : 1) + g;
                             mu[g] = sstat[sl];
                             rsd[g] = sstat[128 + sl];
                         }
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            v[j] = (v[j] - mu[GPC2 > 1 ? j / (32 / GPC2) : 0]) * rsd[GPC2 > 1 ? j / (32 / GPC2) : 0];   // yhat
+                        for (int j = 0; j < CW; ++j)
+                            v[j] = (v[j] - mu[GPC2 > 1 ? j / (CW / GPC2) : 0]) * rsd[GPC2 > 1 ? j / (CW / GPC2) : 0];   // yhat
                         if (TE) {
                             stage_acquire();
-                            stage_f32(sF, mrow, v);
+                            stage_f32w<CW>(sF, mrow, v);
                         } else if (valid && !(P.dbg & 2)) {
-                            st_row32(p.yhat + orow * p.ldy + n0 + ch * 32, v);
+                            st_roww<CW>(p.yhat + orow * p.ldy + n0 + ch * CW, v);
                         }
-                        act_affine32(scol + NT + ch * 32, scol + 2 * NT + ch * 32, v, act);
+                        act_affinew<CW>(scol + NT + ch * CW, scol + 2 * NT + ch * CW, v, act);
                     }
                     if (ACC2) {
-                        float w[32];
-                        tmem_ld32(tacc + NT + ch * 32, w);
-                        add_lds32(scol + 3 * NT + ch * 32, w);
+                        float w[CW];
+                        tmem_ldw<CW>(tacc + NT + ch * CW, w);
+                        add_ldsw<CW>(scol + 3 * NT + ch * CW, w);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += w[j];
+                        for (int j = 0; j < CW; ++j) v[j] += w[j];
                     }
                     if (C::INL_FLOATS && p.inl_mode == 2) {
-                        add_lds32(scol + 3 * NT + ch * 32, v);
-                        inline_conv<NT>(p, sinl, ch, rg, hrow, HJ, valid, v);
+                        add_ldsw<CW>(scol + 3 * NT + ch * CW, v);
+                        inline_conv<NT, CW>(p, sinl, ch, rg, hrow, HJ, valid, v);
                     }
-                    if (N < n0 + ch * 32 + 32) {
+                    if (N < n0 + ch * CW + CW) {
                         // narrow output (N = trajectory dimension): masked scalar IO, optional energy
                         if (valid) {
                             float e = 0.f;
-                            for (int j = 0; j < 32; ++j) {
-                                const int n = n0 + ch * 32 + j;
+                            for (int j = 0; j < CW; ++j) {
+                                const int n = n0 + ch * CW + j;
                                 if (n >= N) break;
                                 float x = v[j];
-                                if (idp) x += __ldg(idp + ch * 32 + j);
-                                if (adp) x += __ldg(adp + ch * 32 + j);
+                                if (idp) x += __ldg(idp + ch * CW + j);
+                                if (adp) x += __ldg(adp + ch * CW + j);
                                 if (p.out) p.out[orow * p.ldo + n] = x;
                                 e = fmaf(0.5f * x, x, e);
                             }
@@ -551,27 +561,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         }
                         continue;
                     }
-                    if (eT && !(P.dbg & 8)) add_row32(eT + ch * 32, v);
-                    if (eR && !(P.dbg & 8)) add_row32(eR + ch * 32, v);
-                    if (idp && !(P.dbg & 4)) add_row32(idp + ch * 32, v);
-                    if (idh && !(P.dbg & 4)) add_planes32(idh + ch * 32, idl + ch * 32, v);
-                    if (adp && !(P.dbg & 4)) add_row32(adp + ch * 32, v);
+                    if (eT && !(P.dbg & 8)) add_roww<CW>(eT + ch * CW, v);
+                    if (eR && !(P.dbg & 8)) add_roww<CW>(eR + ch * CW, v);
+                    if (idp && !(P.dbg & 4)) add_roww<CW>(idp + ch * CW, v);
+                    if (idh && !(P.dbg & 4)) add_planesw<CW>(idh + ch * CW, idl + ch * CW, v);
+                    if (adp && !(P.dbg & 4)) add_roww<CW>(adp + ch * CW, v);
                     if (TE) {
                         // with GroupNorm the fp32 tile carries yhat, so an fp32 copy of the result (only kept for
                         // identity residuals / SIMT consumers) goes out directly; without it the tile is free
                         const bool gnf = GS && p.gn_fwd;
                         if (!gnf) stage_acquire();
                         if (p.out) {
-                            if (gnf) { if (valid) st_row32(p.out + orow * p.ldo + n0 + ch * 32, v); }
-                            else stage_f32(sF, mrow, v);
+                            if (gnf) { if (valid) st_roww<CW>(p.out + orow * p.ldo + n0 + ch * CW, v); }
+                            else stage_f32w<CW>(sF, mrow, v);
                         }
-                        if (p.out_hi) stage_planes(sH, sL, mrow, v);
+                        if (p.out_hi) stage_planesw<CW>(sH, sL, mrow, v);
                         stage_release(gnf ? &P.mSy : (p.out ? &P.mSo : nullptr), p.out_hi ? &P.mSoh : nullptr, &P.mSol,
-                                      n0 + ch * 32, op, r0);
+                                      n0 + ch * CW, op, r0);
                     } else if (valid && !(P.dbg & 2)) {
-                        const size_t o = orow * p.ldo + n0 + ch * 32;
-                        if (p.out) st_row32(p.out + o, v);
-                        if (p.out_hi) st_planes32(p.out_hi + o, p.out_lo + o, v);
+                        const size_t o = orow * p.ldo + n0 + ch * CW;
+                        if (p.out) st_roww<CW>(p.out + o, v);
+                        if (p.out_hi) st_planesw<CW>(p.out_hi + o, p.out_lo + o, v);
                     }
                 }
             } else {
@@ -585,60 +595,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const float* adp = p.addend ? p.addend + orow * p.ldad + n0 : nullptr;
                 const float* yp = p.yhat + orow * p.ldy + n0;
 #pragma unroll 1
-                for (int ch = hf; ch < NCH; ch += 2) {
-                    tmem_ld32(tacc + ch * 32, v);
-                    if (idp && !(P.dbg & 4)) add_row32(idp + ch * 32, v);
-                    if (idh && !(P.dbg & 4)) add_planes32(idh + ch * 32, idl + ch * 32, v);
-                    if (adp && !(P.dbg & 4)) add_row32(adp + ch * 32, v);
-                    float y[32];
-                    if (!(P.dbg & 4)) ld_row32(yp + ch * 32, y);
+                for (int ch = hf; ch < NCH; ch += NG) {
+                    tmem_ldw<CW>(tacc + ch * CW, v);
+                    if (idp && !(P.dbg & 4)) add_roww<CW>(idp + ch * CW, v);
+                    if (idh && !(P.dbg & 4)) add_planesw<CW>(idh + ch * CW, idl + ch * CW, v);
+                    if (adp && !(P.dbg & 4)) add_roww<CW>(adp + ch * CW, v);
+                    float y[CW];
+                    if (!(P.dbg & 4)) ld_roww<CW>(yp + ch * CW, y);
                     else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) y[j] = 0.5f;
+                        for (int j = 0; j < CW; ++j) y[j] = 0.5f;
                     }
                     if (TE) {
                         if (p.out || p.out_hi) {
                             stage_acquire();
-                            if (p.out) stage_f32(sF, mrow, v);
-                            if (p.out_hi) stage_planes(sH, sL, mrow, v);
-                            stage_release(p.out ? &P.mSo : nullptr, p.out_hi ? &P.mSoh : nullptr, &P.mSol, n0 + ch * 32, op, r0);
+                            if (p.out) stage_f32w<CW>(sF, mrow, v);
+                            if (p.out_hi) stage_planesw<CW>(sH, sL, mrow, v);
+                            stage_release(p.out ? &P.mSo : nullptr, p.out_hi ? &P.mSoh : nullptr, &P.mSol, n0 + ch * CW, op, r0);
                         }
                     } else if (valid && !(P.dbg & 2)) {
-                        const size_t o = orow * p.ldo + n0 + ch * 32;
-                        if (p.out) st_row32(p.out + o, v);
-                        if (p.out_hi) st_planes32(p.out_hi + o, p.out_lo + o, v);
+                        const size_t o = orow * p.ldo + n0 + ch * CW;
+                        if (p.out) st_roww<CW>(p.out + o, v);
+                        if (p.out_hi) st_planesw<CW>(p.out_hi + o, p.out_lo + o, v);
                     }
-                    constexpr int GPC = (GS && GS < 32) ? 32 / GS : 1;
+                    constexpr int GPC = (GS && GS < CW) ? CW / GS : 1;
                     float q1[GPC], q2[GPC];
 #pragma unroll
                     for (int g = 0; g < GPC; ++g) q1[g] = q2[g] = 0.f;
                     if (!valid) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) { v[j] = 0.f; y[j] = 0.f; }
+                        for (int j = 0; j < CW; ++j) { v[j] = 0.f; y[j] = 0.f; }
                     }
-                    act_affine_bwd32(scol + NT + ch * 32, scol + 2 * NT + ch * 32, y, v, act);
+                    act_affine_bwdw<CW>(scol + NT + ch * CW, scol + 2 * NT + ch * CW, y, v, act);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        q1[GPC > 1 ? j / (32 / GPC) : 0] += v[j];
-                        q2[GPC > 1 ? j / (32 / GPC) : 0] += v[j] * y[j];
+                    for (int j = 0; j < CW; ++j) {
+                        q1[GPC > 1 ? j / (CW / GPC) : 0] += v[j];
+                        q2[GPC > 1 ? j / (CW / GPC) : 0] += v[j] * y[j];
                     }
-                    tmem_st32(tacc + ch * 32, v);
-                    if (C::STASH) tmem_st32(tstash + ch * 32, y);
-                    const int g0 = (ch * 32) / (GS ? GS : 1);
+                    tmem_stw<CW>(tacc + ch * CW, v);
+                    if (C::STASH) tmem_stw<CW>(tstash + ch * CW, y);
+                    const int g0 = (ch * CW) / (GS ? GS : 1);
 #pragma unroll
                     for (int g = 0; g < GPC; ++g) {
-                        float* d = spart + ((hf * 128 + mrow) * G + g0 + g) * 2;
+                        float* d = spart + ((pslot(ch) * 128 + mrow) * G + g0 + g) * 2;
                         d[0] += q1[g];
                         d[1] += q2[g];
                     }
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 lap(1);
-                epi_bar();
+                epi_barw<ETH>();
                 if (etid < S * G) {
                     const int s = etid / G, g = etid - s * G;
                     float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
-                    for (int h2 = 0; h2 < 2; ++h2) {
+                    for (int h2 = 0; h2 < C::PSLOTS; ++h2) {
                         const float* base = spart + ((h2 * 128 + s * HJ) * G + g) * 2;
                         int j = 0;
                         for (; j + 4 <= HJ; j += 4) {
@@ -658,49 +668,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     sstat[128 + etid] = b * inv_cnt;
                     sstat[256 + etid] = (s < Sv) ? __ldg(p.rstd + (size_t)(r0 + s) * 8 + n0 / (GS ? GS : 1) + g) : 0.f;
                 }
-                epi_bar();
+                epi_barw<ETH>();
                 lap(2);
 #pragma unroll 1
-                for (int ch = hf; ch < NCH; ch += 2) {
-                    float y[32];
-                    tmem_ld32(tacc + ch * 32, v);
+                for (int ch = hf; ch < NCH; ch += NG) {
+                    float y[CW];
+                    tmem_ldw<CW>(tacc + ch * CW, v);
                     if (C::STASH) {
-                        tmem_ld32(tstash + ch * 32, y);
+                        tmem_ldw<CW>(tstash + ch * CW, y);
                     } else {
-                        ld_row32(yp + ch * 32, y);
+                        ld_roww<CW>(yp + ch * CW, y);
                         if (!valid) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) y[j] = 0.f;
+                            for (int j = 0; j < CW; ++j) y[j] = 0.f;
                         }
                     }
-                    constexpr int GPC3 = (GS && GS < 32) ? 32 / GS : 1;
+                    constexpr int GPC3 = (GS && GS < CW) ? CW / GS : 1;
                     float m1[GPC3], m2[GPC3], rsd[GPC3];
 #pragma unroll
                     for (int g = 0; g < GPC3; ++g) {
-                        const int sl = slab0 + (ch * 32) / (GS ? GS : 1) + g;
+                        const int sl = slab0 + (ch * CW) / (GS ? GS : 1) + g;
                         m1[g] = sstat[sl]; m2[g] = sstat[128 + sl]; rsd[g] = sstat[256 + sl];
                     }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int g = GPC3 > 1 ? j / (32 / GPC3) : 0;
+                    for (int j = 0; j < CW; ++j) {
+                        const int g = GPC3 > 1 ? j / (CW / GPC3) : 0;
                         v[j] = rsd[g] * (v[j] - m1[g] - y[j] * m2[g]);
                     }
                     if (TE) {
                         stage_acquire();
-                        if (p.gy) stage_f32(sF, mrow, v);
-                        if (p.gy_hi) stage_planes(sH, sL, mrow, v);
-                        stage_release(p.gy ? &P.mSg : nullptr, p.gy_hi ? &P.mSgh : nullptr, &P.mSgl, n0 + ch * 32, op, r0);
+                        if (p.gy) stage_f32w<CW>(sF, mrow, v);
+                        if (p.gy_hi) stage_planesw<CW>(sH, sL, mrow, v);
+                        stage_release(p.gy ? &P.mSg : nullptr, p.gy_hi ? &P.mSgh : nullptr, &P.mSgl, n0 + ch * CW, op, r0);
                     } else if (valid && !(P.dbg & 2)) {
-                        const size_t o = orow * p.ldg + n0 + ch * 32;
-                        if (p.gy) st_row32(p.gy + o, v);
-                        if (p.gy_hi) st_planes32(p.gy_hi + o, p.gy_lo + o, v);
+                        const size_t o = orow * p.ldg + n0 + ch * CW;
+                        if (p.gy) st_roww<CW>(p.gy + o, v);
+                        if (p.gy_hi) st_planesw<CW>(p.gy_hi + o, p.gy_lo + o, v);
                     }
                 }
             }
             // release the accumulator stage
             lap(3);
             tc_fence_before();
-            epi_bar();
+            epi_barw<ETH>();
             if (etid == 0) {
                 if (CG == 2) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
             }
@@ -818,27 +828,29 @@ int w_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int rows, int NT, 
 
 // output tensor [R][Hout][ld] (fp32 or BF16) -> store map with box (32, HJ, S): 3-D (C, H, R) for unit output
 // stride, 4-D (C, phase, H/2, R) for the stride-2 scatter of the transposed convs
-int st_map(CUtensorMap* out, const void* base, bool f32, int C, int Hout, int R, int ld, int S, int HJ, int ostride) {
-    MapKey key(base, C, Hout, R, ld, S * 1000 + HJ, (f32 ? 10 : 20) + ostride);
+int st_map(CUtensorMap* out, const void* base, bool f32, int C, int Hout, int R, int ld, int S, int HJ, int ostride,
+           int cw) {
+    MapKey key(base, C, Hout, R, ld, S * 1000 + HJ, (f32 ? 10 : 20) + ostride + 1000 * cw);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return 0; }
     EncodeFn enc = get_encode();
     PMP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     const cuuint64_t es = f32 ? 4 : 2;
     const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    const CUtensorMapSwizzle sw = f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const int rowb = cw * (int)es;   // bytes per staged row: 128 / 64 / 32 -> the matching swizzle span
+    const CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUresult r;
     if (ostride == 1) {
         cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Hout, (cuuint64_t)R};
         cuuint64_t strides[2] = {(cuuint64_t)ld * es, (cuuint64_t)ld * es * (cuuint64_t)Hout};
-        cuuint32_t box[3] = {32, (cuuint32_t)HJ, (cuuint32_t)S};
+        cuuint32_t box[3] = {(cuuint32_t)cw, (cuuint32_t)HJ, (cuuint32_t)S};
         cuuint32_t el[3] = {1, 1, 1};
         r = enc(out, dt, 3, const_cast<void*>(base), dims, strides, box, el, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
         cuuint64_t dims[4] = {(cuuint64_t)C, 2, (cuuint64_t)(Hout / 2), (cuuint64_t)R};
         cuuint64_t strides[3] = {(cuuint64_t)ld * es, (cuuint64_t)ld * es * 2, (cuuint64_t)ld * es * (cuuint64_t)Hout};
-        cuuint32_t box[4] = {32, 1, (cuuint32_t)HJ, (cuuint32_t)S};
+        cuuint32_t box[4] = {(cuuint32_t)cw, 1, (cuuint32_t)HJ, (cuuint32_t)S};
         cuuint32_t el[4] = {1, 1, 1, 1};
         r = enc(out, dt, 4, const_cast<void*>(base), dims, strides, box, el, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -867,12 +879,12 @@ unsigned long long* tc_timer_buffer() {
 }
 namespace {
 
-template <int NT, int GS, bool ACC2, int CG, bool TE>
+template <int NT, int GS, bool ACC2, int CG, bool TE, int NG = 2>
 int launch_t(TcP& P, cudaStream_t st) {
-    using C = Cfg<NT, GS, ACC2, CG, TE>;
+    using C = Cfg<NT, GS, ACC2, CG, TE, NG>;
     static bool configured = false;
     if (!configured) {
-        PMP_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NT, GS, ACC2, CG, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PMP_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NT, GS, ACC2, CG, TE, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES));
         configured = true;
     }
@@ -883,14 +895,14 @@ int launch_t(TcP& P, cudaStream_t st) {
     }
     if (CG == 1) {
         const int grid = P.ntiles < g_num_sms ? P.ntiles : g_num_sms;
-        conv_tc_kernel<NT, GS, ACC2, CG, TE><<<grid, TC_THREADS, C::SMEM_BYTES, st>>>(P);
+        conv_tc_kernel<NT, GS, ACC2, CG, TE, NG><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(P);
     } else {
         // one cluster of two CTAs (the two SMs of a TPC) per tile pair, persistent over the pairs
         const int nclusters = P.npairs < g_num_sms / 2 ? P.npairs : g_num_sms / 2;
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
         cfg.gridDim = dim3(2 * nclusters, 1, 1);
-        cfg.blockDim = dim3(TC_THREADS, 1, 1);
+        cfg.blockDim = dim3(C::THREADS, 1, 1);
         cfg.dynamicSmemBytes = C::SMEM_BYTES;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -900,7 +912,7 @@ int launch_t(TcP& P, cudaStream_t st) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        PMP_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NT, GS, ACC2, CG, TE>, P));
+        PMP_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NT, GS, ACC2, CG, TE, NG>, P));
     }
     PMP_LAUNCH_OK();
     return 0;
@@ -960,9 +972,17 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     // 256-column tiles (CTA pairs only) feed the tensor pipe best; a separate second accumulator does not fit next to them
     static int wide = -1;
     if (wide < 0) { const char* e = getenv("PMP_TC_WIDE"); wide = e ? atoi(e) : 1; }
-    const int NT = pick_nt(p, wide && mode == 3 && !acc2 && !p.inl_x);
-    const int cg = (mode == 3 && NT >= 128 && !p.inl_x) ? 2 : 1;
-    const bool te = mode == 3 && (NT == 64 || ((NT == 128 || NT == 256) && cg == 2)) && p.N >= 64;
+    const int NT = pick_nt(p, wide && (mode == 3 || mode == 4) && !acc2 && !p.inl_x);
+    const bool m34 = mode == 3 || mode == 4;
+    const int cg = (m34 && NT >= 128 && !p.inl_x) ? 2 : 1;
+    const bool te = m34 && (NT == 64 || ((NT == 128 || NT == 256) && cg == 2)) && p.N >= 64;
+    // 16 epilogue warps on 16-column chunks: measured 5-8 % faster for the GroupNorm-backward epilogues (two TMEM
+    // passes, yhat + identity loads), neutral or slower for the forward ones -> path 3 uses them for the former only;
+    // path 4 forces them everywhere (A/B switch)
+    static int ng4_bwd = -1;
+    if (ng4_bwd < 0) { const char* e = getenv("PMP_TC_NG4_BWD"); ng4_bwd = e ? atoi(e) : 1; }
+    const bool ng4 = te && (mode == 4 || (mode == 3 && ng4_bwd && p.gn_bwd));
+    const int cw = ng4 ? 16 : 32;
     const int S = 128 / p.HJ;
     P.e.S = S;
     P.tilesM = (p.R + S - 1) / S;
@@ -1014,20 +1034,34 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     }
     if (te) {
         const int os = p.ostride;
-        if (p.yhat && p.gn_fwd && (rc = st_map(&P.mSy, p.yhat, true, p.N, p.Hout, p.R, p.ldy, S, p.HJ, os))) return rc;
-        if (p.out && (rc = st_map(&P.mSo, p.out, true, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os))) return rc;
+        if (p.yhat && p.gn_fwd && (rc = st_map(&P.mSy, p.yhat, true, p.N, p.Hout, p.R, p.ldy, S, p.HJ, os, cw))) return rc;
+        if (p.out && (rc = st_map(&P.mSo, p.out, true, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os, cw))) return rc;
         if (p.out_hi) {
-            if ((rc = st_map(&P.mSoh, p.out_hi, false, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os))) return rc;
-            if ((rc = st_map(&P.mSol, p.out_lo, false, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os))) return rc;
+            if ((rc = st_map(&P.mSoh, p.out_hi, false, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os, cw))) return rc;
+            if ((rc = st_map(&P.mSol, p.out_lo, false, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os, cw))) return rc;
         }
-        if (p.gy && (rc = st_map(&P.mSg, p.gy, true, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os))) return rc;
+        if (p.gy && (rc = st_map(&P.mSg, p.gy, true, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os, cw))) return rc;
         if (p.gy_hi) {
-            if ((rc = st_map(&P.mSgh, p.gy_hi, false, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os))) return rc;
-            if ((rc = st_map(&P.mSgl, p.gy_lo, false, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os))) return rc;
+            if ((rc = st_map(&P.mSgh, p.gy_hi, false, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os, cw))) return rc;
+            if ((rc = st_map(&P.mSgl, p.gy_lo, false, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os, cw))) return rc;
         }
     }
     const bool gn = p.gn_fwd || p.gn_bwd;
     const int gs = gn ? p.N / 8 : 0;
+    if (ng4) {
+        if (NT == 256) {
+            if (gs == 32) return launch_t<256, 32, false, 2, true, 4>(P, st);
+            if (gs == 64) return launch_t<256, 64, false, 2, true, 4>(P, st);
+            return launch_t<256, 0, false, 2, true, 4>(P, st);
+        }
+        if (NT == 128) {
+            if (gs == 32) return acc2 ? launch_t<128, 32, true, 2, true, 4>(P, st) : launch_t<128, 32, false, 2, true, 4>(P, st);
+            if (gs == 64) return acc2 ? launch_t<128, 64, true, 2, true, 4>(P, st) : launch_t<128, 64, false, 2, true, 4>(P, st);
+            return acc2 ? launch_t<128, 0, true, 2, true, 4>(P, st) : launch_t<128, 0, false, 2, true, 4>(P, st);
+        }
+        if (gs == 8) return acc2 ? launch_t<64, 8, true, 1, true, 4>(P, st) : launch_t<64, 8, false, 1, true, 4>(P, st);
+        return acc2 ? launch_t<64, 0, true, 1, true, 4>(P, st) : launch_t<64, 0, false, 1, true, 4>(P, st);
+    }
     if (NT == 256) {
         if (gs == 32) return launch_t<256, 32, false, 2, true>(P, st);
         if (gs == 64) return launch_t<256, 64, false, 2, true>(P, st);
@@ -1062,5 +1096,7 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
 int launch_conv_tc(const ConvP& p, cudaStream_t st) { return launch_conv_tc_mode(p, st, 1); }
 // gemm path 3: CTA pairs + TMA-store epilogue where they apply, the single-CTA kernel otherwise
 int launch_conv_tc_pair(const ConvP& p, cudaStream_t st) { return launch_conv_tc_mode(p, st, 3); }
+// gemm path 4: path 3 with 16 epilogue warps walking 16-column chunks
+int launch_conv_tc_pair16(const ConvP& p, cudaStream_t st) { return launch_conv_tc_mode(p, st, 4); }
 
 }  // namespace pmp

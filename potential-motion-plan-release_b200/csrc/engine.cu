@@ -603,7 +603,7 @@ struct Ctx {
             return;
         }
         if (tc() && conv_tc_eligible(p)) {
-            rc = prof_launch_conv(p, st, 1, m->gemm_path == 3 ? launch_conv_tc_pair : launch_conv_tc);
+            rc = prof_launch_conv(p, st, 1, m->gemm_path == 4 ? launch_conv_tc_pair16 : (m->gemm_path == 3 ? launch_conv_tc_pair : launch_conv_tc));
             return;
         }
         if ((!p.A1 && !p.inl_x) || (p.A2_hi && !p.A2) || (p.ident_hi && !p.ident)) {
@@ -1171,8 +1171,8 @@ int pmp_model_set_row_chunk(pmp_model* m, int rows) {
 }
 
 int pmp_model_set_gemm_path(pmp_model* m, int path) {
-    PMP_REQUIRE(m && path >= 0 && path <= 3,
-                "gemm path must be 0 (fp32 SIMT), 1 (tcgen05), 2 (tcgen05 with operand reuse) or 3 (tcgen05 CTA pairs)");
+    PMP_REQUIRE(m && path >= 0 && path <= 4,
+                "gemm path must be 0 (fp32 SIMT), 1 (tcgen05), 2 (operand reuse), 3 (CTA pairs) or 4 (CTA pairs, 16 epilogue warps)");
     m->gemm_path = path;
     return 0;
 }

@@ -338,6 +338,180 @@ __device__ __forceinline__ void act_affine_bwd32(const float* gam, const float* 
     }
 }
 
+
+// ------------------------------------------------------------------ chunk-width generic forms (CW = 32 or 16 columns
+// per thread and step).  The 16-column forms exist for the 16-warp epilogue: half the live registers per thread.
+template <int CW>
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[CW]) {
+    static_assert(CW == 16 || CW == 32, "chunk width");
+    uint32_t r[CW];
+    if constexpr (CW == 32) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+    } else {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr)
+            : "memory");
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int CW>
+__device__ __forceinline__ void tmem_stw(uint32_t taddr, const float (&v)[CW]) {
+    if constexpr (CW == 32) {
+        tmem_st32(taddr, v);
+    } else {
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+            "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+            ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+            "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+            "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+            "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+            "r"(__float_as_uint(v[15]))
+            : "memory");
+    }
+}
+template <int CW>
+__device__ __forceinline__ void add_ldsw(const float* p, float (&v)[CW]) {
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i) {
+        const float4 t = reinterpret_cast<const float4*>(p)[i];
+        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    }
+}
+template <int CW>
+__device__ __forceinline__ void ld_roww(const float* __restrict__ p, float (&v)[CW]) {
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+}
+template <int CW>
+__device__ __forceinline__ void add_roww(const float* __restrict__ p, float (&v)[CW]) {
+    float4 t[CW / 4];
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i) t[i] = __ldg(reinterpret_cast<const float4*>(p) + i);
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i) {
+        v[4 * i] += t[i].x; v[4 * i + 1] += t[i].y; v[4 * i + 2] += t[i].z; v[4 * i + 3] += t[i].w;
+    }
+}
+template <int CW>
+__device__ __forceinline__ void st_roww(float* __restrict__ p, const float (&v)[CW]) {
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i)
+        reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+template <int CW>
+__device__ __forceinline__ void add_planesw(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                            float (&v)[CW]) {
+    uint4 h[CW / 8], l[CW / 8];
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i) {
+        h[i] = __ldg(reinterpret_cast<const uint4*>(hi) + i);
+        l[i] = __ldg(reinterpret_cast<const uint4*>(lo) + i);
+    }
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i) {
+        const uint32_t hw[4] = {h[i].x, h[i].y, h[i].z, h[i].w}, lw[4] = {l[i].x, l[i].y, l[i].z, l[i].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[8 * i + 2 * k] += __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
+            v[8 * i + 2 * k + 1] += __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u);
+        }
+    }
+}
+template <int CW>
+__device__ __forceinline__ void st_planesw(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, const float (&v)[CW]) {
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) split_bf16x2(v[8 * i + 2 * k], v[8 * i + 2 * k + 1], h[k], l[k]);
+        reinterpret_cast<uint4*>(hi)[i] = make_uint4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<uint4*>(lo)[i] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+template <int CW>
+__device__ __forceinline__ void act_affinew(const float* gam, const float* bet, float (&v)[CW], int act) {
+    if (act == 0) {
+#pragma unroll
+        for (int q = 0; q < CW / 4; ++q) {
+            const float4 g4 = reinterpret_cast<const float4*>(gam)[q], b4 = reinterpret_cast<const float4*>(bet)[q];
+            v[4 * q] = silu_fast(fmaf(g4.x, v[4 * q], b4.x));
+            v[4 * q + 1] = silu_fast(fmaf(g4.y, v[4 * q + 1], b4.y));
+            v[4 * q + 2] = silu_fast(fmaf(g4.z, v[4 * q + 2], b4.z));
+            v[4 * q + 3] = silu_fast(fmaf(g4.w, v[4 * q + 3], b4.w));
+        }
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < CW; ++j) v[j] = act_fwd(gam[j] * v[j] + bet[j], act);
+    }
+}
+template <int CW>
+__device__ __forceinline__ void act_affine_bwdw(const float* gam, const float* bet, const float (&y)[CW], float (&g)[CW], int act) {
+    if (act == 0) {
+#pragma unroll
+        for (int q = 0; q < CW / 4; ++q) {
+            const float4 g4 = reinterpret_cast<const float4*>(gam)[q], b4 = reinterpret_cast<const float4*>(bet)[q];
+            g[4 * q] *= silu_bwd_fast(fmaf(g4.x, y[4 * q], b4.x)) * g4.x;
+            g[4 * q + 1] *= silu_bwd_fast(fmaf(g4.y, y[4 * q + 1], b4.y)) * g4.y;
+            g[4 * q + 2] *= silu_bwd_fast(fmaf(g4.z, y[4 * q + 2], b4.z)) * g4.z;
+            g[4 * q + 3] *= silu_bwd_fast(fmaf(g4.w, y[4 * q + 3], b4.w)) * g4.w;
+        }
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < CW; ++j) g[j] *= act_bwd(gam[j] * y[j] + bet[j], act) * gam[j];
+    }
+}
+// staging rows of CW columns: fp32 rows of CW*4 bytes (128: SWIZZLE_128B, 64: SWIZZLE_64B), BF16 rows of CW*2 bytes
+// (64: SWIZZLE_64B, 32: SWIZZLE_32B); the XOR term is the one the TMA store applies for that swizzle mode
+template <int RB>
+__device__ __forceinline__ int swz_xor(int r) {
+    return RB == 128 ? (r & 7) : (RB == 64 ? ((r >> 1) & 3) : ((r >> 2) & 1));
+}
+template <int CW>
+__device__ __forceinline__ void stage_f32w(uint8_t* tile, int r, const float (&v)[CW]) {
+    constexpr int RB = CW * 4;
+    uint8_t* row = tile + r * RB;
+    const int x = swz_xor<RB>(r);
+#pragma unroll
+    for (int c = 0; c < RB / 16; ++c)
+        *reinterpret_cast<float4*>(row + ((c ^ x) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+template <int CW>
+__device__ __forceinline__ void stage_planesw(uint8_t* thi, uint8_t* tlo, int r, const float (&v)[CW]) {
+    constexpr int RB = CW * 2;
+    uint8_t* rh = thi + r * RB;
+    uint8_t* rl = tlo + r * RB;
+    const int x = swz_xor<RB>(r);
+#pragma unroll
+    for (int c = 0; c < RB / 16; ++c) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) split_bf16x2(v[8 * c + 2 * k], v[8 * c + 2 * k + 1], h[k], l[k]);
+        *reinterpret_cast<uint4*>(rh + ((c ^ x) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(rl + ((c ^ x) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+template <int NTHREADS>
+__device__ __forceinline__ void epi_barw() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
+
 template <int GS>
 __device__ __forceinline__ float group_reduce(float v) {
     // sum over the lanes of one GroupNorm group inside a 32-column chunk

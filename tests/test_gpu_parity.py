@@ -84,7 +84,7 @@ def test_eps_chunking_and_determinism():
 @pytest.mark.parametrize("fam", ["m2d", "dualkuka"])
 def test_gemm_paths_agree(fam):
     """path 0 = exact fp32 CUDA-core convs, path 1 = tcgen05 BF16x3, path 2 = tcgen05 with operand reuse,
-    path 3 = tcgen05 CTA pairs (cta_group::2)"""
+    path 3 = tcgen05 CTA pairs (cta_group::2), path 4 = path 3 with 16 epilogue warps"""
     a = synth.arch(fam)
     cfg = unet_ref.UnetCfg(a["unet"]); sd = unet_ref.synth_weights(a["unet"], 1)
     eng = dropin(fam).model.engine(100)
@@ -97,14 +97,14 @@ def test_gemm_paths_agree(fam):
     wemb = eng.wall_embed(walls[:B].to(DEV))
     out = {}
     try:
-        for path in (0, 1, 2, 3):
+        for path in (0, 1, 2, 3, 4):
             eng.set_gemm_path(path)
             out[path] = eng.eps(x.to(DEV), t.to(DEV), wemb, n_cond=B).cpu().numpy()
     finally:
         eng.set_gemm_path(3)
     scale = np.abs(ref).max()
     assert np.abs(out[0] - ref).max() <= 2e-5 * scale, "fp32 path"
-    for path in (1, 2, 3):
+    for path in (1, 2, 3, 4):
         assert np.abs(out[path] - ref).max() <= 3e-4 * scale, "tensor-core path %d: %.3e" % (path, np.abs(out[path] - ref).max() / scale)
         assert_eps_close(out[path], ref, "path %d" % path)
 
