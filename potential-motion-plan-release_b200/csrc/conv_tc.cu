@@ -105,8 +105,12 @@ __device__ __forceinline__ void inline_conv(const ConvP& p, const float* sinl, i
     }
 }
 
-template <int NT, int GS, bool ACC2, int CG, bool TE, int NG = 2>
+template <int NT, int GS, bool ACC2, int CG, bool TE, int NG = 2, bool TEAM = false>
 struct Cfg {
+    // TEAM: the two epilogue warp groups work on ALTERNATE TILES (each walks all chunks of its own tile, with its own
+    // barrier and scratch tables) instead of on alternate chunks of one tile: two per-tile latency chains (TMEM load ->
+    // stats -> barrier -> reduce -> barrier -> output pass) overlap.  For the narrow, epilogue-bound 64-column tiles.
+    static_assert(!TEAM || (NG == 2 && !ACC2 && NT == 64), "team mode: 64-column tiles, one accumulator");
     // NG epilogue warp groups of 4 warps (one per TMEM lane quarter): 2 groups walk 32-column chunks, 4 groups (16
     // epilogue warps, path 4) walk 16-column chunks with half the live registers per thread
     static constexpr int CW = NG == 4 ? 16 : 32;
@@ -127,7 +131,7 @@ struct Cfg {
     static constexpr int INL_FLOATS = NT == 64 ? 5 * 16 * 64 : 0;   // inline small-K conv weights [taps][D<=16][64]
     static constexpr int ACC_COLS = NT * (ACC2 ? 2 : 1);
     // two accumulator stages when they fit next to the yhat stash of the GroupNorm-backward epilogue
-    static constexpr int NACC = (NT != 192 && 2 * ACC_COLS <= 512) ? 2 : 1;
+    static constexpr int NACC = TEAM ? 4 : ((NT != 192 && 2 * ACC_COLS <= 512) ? 2 : 1);
     // the GroupNorm-backward epilogue parks yhat in spare TMEM columns between its two passes when there are
     // any (NT <= 128); the 256-column tiles fill TMEM with their two accumulator stages and re-read yhat (L2)
     static constexpr bool STASH = NACC * ACC_COLS + NACC * NT <= 512;
@@ -139,19 +143,21 @@ struct Cfg {
     static_assert(!GS || CPG <= NG || NG == 2, "a GroupNorm group spans more chunks than there are warp groups");
     // smem: stages | staging tiles | row/slab partials | slab stats | column params | row info | barriers
     static constexpr int TBUF_FLOATS = 0;
-    static constexpr int PSLOTS = NG == 2 ? 2 : CPG;
+    static constexpr int PSLOTS = TEAM ? 1 : (NG == 2 ? 2 : CPG);
     static constexpr int PART_FLOATS = PSLOTS * 128 * G * 2;
+    static constexpr int NTEAM = TEAM ? 2 : 1;     // copies of the per-tile scratch tables
     static constexpr int STAT_FLOATS = 384;
     static constexpr int COL_FLOATS = 4 * NT;
     static constexpr int ROW_INTS = 4 * 128;
     static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + STG_BYTES +
-                                      (TBUF_FLOATS + PART_FLOATS + STAT_FLOATS + COL_FLOATS + ROW_INTS + INL_FLOATS) * 4 + 256 + 1024;
+                                      (TBUF_FLOATS + NTEAM * (PART_FLOATS + STAT_FLOATS + COL_FLOATS + INL_FLOATS) + ROW_INTS) * 4 +
+                                      256 + 1024;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-template <int NT, int GS, bool ACC2, int CG, bool TE, int NG>
+template <int NT, int GS, bool ACC2, int CG, bool TE, int NG, bool TEAM>
 __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_constant__ TcP P) {
-    using C = Cfg<NT, GS, ACC2, CG, TE, NG>;
+    using C = Cfg<NT, GS, ACC2, CG, TE, NG, TEAM>;
     constexpr int CW = C::CW, ETH = C::ETHREADS;
     constexpr int G = C::G, NCH = C::NCH, NSTAGE = C::NSTAGE, NACC = C::NACC;
     const ConvP& p = P.e;
@@ -160,17 +166,20 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
     uint8_t* stg = smem + NSTAGE * C::STAGE_BYTES;   // TE staging tiles (1024-byte aligned)
     float* tbuf = reinterpret_cast<float*>(stg + C::STG_BYTES);
-    float* spart = tbuf + C::TBUF_FLOATS;
+    // per-tile scratch tables (one set per epilogue team): row/slab partials | slab stats | column params | inline weights
+    const int team_of_warp = (TEAM && (threadIdx.x >> 5) >= 6) ? 1 : 0;
+    constexpr int SCR_FLOATS = C::PART_FLOATS + C::STAT_FLOATS + C::COL_FLOATS + C::INL_FLOATS;
+    float* spart = tbuf + C::TBUF_FLOATS + team_of_warp * SCR_FLOATS;
     float* sstat = spart + C::PART_FLOATS;
     float* scol = sstat + C::STAT_FLOATS;                 // bias | gamma | beta | bias2, NT each
-    int* srow = reinterpret_cast<int*>(scol + C::COL_FLOATS);   // [128] output row index (or -1), [128] global sample
-    float* sinl = reinterpret_cast<float*>(srow + C::ROW_INTS);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sinl + C::INL_FLOATS);
+    float* sinl = scol + C::COL_FLOATS;
+    int* srow = reinterpret_cast<int*>(tbuf + C::TBUF_FLOATS + C::NTEAM * SCR_FLOATS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(srow + C::ROW_INTS);
     uint64_t* full = bars;
     uint64_t* empty = bars + NSTAGE;
     uint64_t* tfull = bars + 2 * NSTAGE;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tempty = tfull + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.S, HJ = p.HJ, N = p.N;
@@ -189,7 +198,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
         }
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         // tempty: the epilogues of both CTAs of a pair release the accumulator stage to the leader's MMA warp
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CG); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -335,7 +344,16 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
         // partial sums combined in a fixed order, so results are run-to-run deterministic.
         const int eq = warp & 3;                 // TMEM lane quarter this warp may access
         const int hf = (warp - 2) >> 2;          // warp group 0..NG-1: which chunks
-        const int etid = threadIdx.x - 64;       // 0..ETH-1
+        const int etid0 = threadIdx.x - 64;      // 0..ETH-1
+        // cooperative loops, barriers and "thread 0" duties are per team in team mode, per CTA otherwise
+        const int etid = TEAM ? (etid0 & 127) : etid0;
+        constexpr int ESTEP = TEAM ? 128 : ETH;
+        auto ebar = [&]() {
+            if (TEAM) asm volatile("bar.sync %0, 128;" ::"r"(6 + hf) : "memory");
+            else epi_barw<ETH>();
+        };
+        const int ch0 = TEAM ? 0 : hf;           // first chunk and chunk step of this thread
+        constexpr int CHS = TEAM ? 1 : NG;
         const int mrow = eq * 32 + lane;
         const int act = p.act;
         const float inv_cnt = 1.0f / (float)(HJ * (GS ? GS : 1));
@@ -350,12 +368,12 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             }
         };
         // writer slot of chunk ch in the row-partial table (NG = 2: the warp group; NG = 4: position of the chunk in its group)
-        auto pslot = [&](int ch) { return NG == 2 ? hf : (ch % C::CPG); };
+        auto pslot = [&](int ch) { return TEAM ? 0 : (NG == 2 ? hf : (ch % C::CPG)); };
         // TE: staging tiles of this half of the epilogue warps and the thread that issues its bulk stores
         uint8_t* const sF = stg + hf * C::STG_HALF_BYTES;
         uint8_t* const sH = sF + 128 * CW * 4;
         uint8_t* const sL = sH + 128 * CW * 2;
-        const bool st_leader = (etid & 127) == 0;
+        const bool st_leader = (etid0 & 127) == 0;
         // free the staging tiles of this half (the bulk stores of the previous chunk have read them)
         auto stage_acquire = [&]() {
             if (st_leader) bulk_wait_read0();
@@ -376,12 +394,18 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                 bulk_commit();
             }
         };
-        for (int tile = sched0; tile < nsched; tile += sched_step) {
+        int it = 0;
+        for (int tile = sched0; tile < nsched; tile += sched_step, ++it) {
+            if (TEAM) {
+                if ((it & 1) != hf) continue;
+                as = it & 3;
+                aph = (uint32_t)((it >> 2) & 1);
+            }
             const int op = tile % P.nphase, t2 = tile / P.nphase;
             const int r0 = ((t2 / P.tilesN) * CG + (int)crank) * S, n0 = (t2 % P.tilesN) * NT;
             const int Sv = max(0, min(S, p.R - r0));
             const int Mv = Sv * HJ;
-            for (int i = etid; i < NT; i += ETH) {
+            for (int i = etid; i < NT; i += ESTEP) {
                 const bool cv = n0 + i < N;
                 scol[i] = (p.bias && cv) ? __ldg(p.bias + n0 + i) : 0.f;
                 scol[NT + i] = (p.gamma && cv) ? __ldg(p.gamma + n0 + i) : 0.f;
@@ -389,12 +413,12 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                 scol[3 * NT + i] = (p.bias2 && cv) ? __ldg(p.bias2 + n0 + i) : 0.f;
             }
             if (C::INL_FLOATS && p.inl_x)
-                for (int i = etid; i < p.inl_taps * p.inl_D * NT; i += ETH) {
+                for (int i = etid; i < p.inl_taps * p.inl_D * NT; i += ESTEP) {
                     const int td = i / NT, nn = i - td * NT;
                     sinl[i] = (n0 + nn < N) ? __ldg(p.inl_w + (size_t)td * N + n0 + nn) : 0.f;
                 }
             if (GS)
-                for (int i = etid; i < C::PART_FLOATS; i += ETH) spart[i] = 0.f;
+                for (int i = etid; i < C::PART_FLOATS; i += ESTEP) spart[i] = 0.f;
             // per-row constants
             const bool valid = mrow < Mv;
             const int s_loc = min(mrow / HJ, S - 1);
@@ -408,16 +432,16 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             tlap = tq1;
             if (P.ctr && P.tmode == 2 && etid == 0) atomicAdd(P.ctr + 0, (unsigned long long)(tq1 - tq0));
             tc_fence_after();
-            epi_barw<ETH>();
+            ebar();
             if (P.dbg & 1) {
                 // main-loop-only timing runs: results are garbage
                 tc_fence_before();
-                epi_barw<ETH>();
+                ebar();
                 if (etid == 0) {
                     if (CG == 2) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
                     if (P.ctr) atomicAdd(P.ctr + 6, 1ull);
                 }
-                if (++as == NACC) { as = 0; aph ^= 1; }
+                if (!TEAM && ++as == NACC) { as = 0; aph ^= 1; }
                 continue;
             }
             const uint32_t tacc = tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)(as * C::ACC_COLS);
@@ -427,7 +451,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             if (C::INL_FLOATS && p.inl_mode == 1) {
                 // the convolution itself has K = taps*D <= 70: compute it here and park it in the (unused)
                 // accumulator so that the GroupNorm passes below run unchanged
-                for (int ch = hf; ch < NCH; ch += NG) {
+                for (int ch = ch0; ch < NCH; ch += CHS) {
 #pragma unroll
                     for (int j = 0; j < CW; ++j) v[j] = 0.f;
                     inline_conv<NT, CW>(p, sinl, ch, rg, hrow, HJ, valid, v);
@@ -439,7 +463,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             if (GS && p.gn_fwd) {
                 // ---- pass 1: per-row sums of y = acc + bias and y^2 for every group
 #pragma unroll 1
-                for (int ch = hf; ch < NCH; ch += NG) {
+                for (int ch = ch0; ch < NCH; ch += CHS) {
                     tmem_ldw<CW>(tacc + ch * CW, v);
                     constexpr int GPC = (GS && GS < CW) ? CW / GS : 1;   // groups per chunk
                     float s1[GPC], s2[GPC];
@@ -461,7 +485,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                     }
                 }
                 lap(1);
-                epi_barw<ETH>();
+                ebar();
                 {
                     // slab (s, g): the 2*HJ row partials are summed by one thread in 4 independent
                     // chains (fixed order -> deterministic) instead of one dependent LDS+FADD chain
@@ -492,7 +516,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                     sstat[128 + etid] = rs;
                     if (s < Sv) p.rstd[(size_t)(r0 + s) * 8 + n0 / (GS ? GS : 1) + g] = rs;
                 }
-                epi_barw<ETH>();
+                ebar();
                 lap(2);
             }
 
@@ -510,7 +534,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                 const __nv_bfloat16* idl = p.ident_hi ? p.ident_lo + orow * p.ldi + n0 : nullptr;
                 const float* adp = p.addend ? p.addend + orow * p.ldad + n0 : nullptr;
 #pragma unroll 1
-                for (int ch = hf; ch < NCH; ch += NG) {
+                for (int ch = ch0; ch < NCH; ch += CHS) {
                     tmem_ldw<CW>(tacc + ch * CW, v);
                     add_ldsw<CW>(scol + ch * CW, v);   // + bias
                     if (GS && p.gn_fwd) {
@@ -595,7 +619,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                 const float* adp = p.addend ? p.addend + orow * p.ldad + n0 : nullptr;
                 const float* yp = p.yhat + orow * p.ldy + n0;
 #pragma unroll 1
-                for (int ch = hf; ch < NCH; ch += NG) {
+                for (int ch = ch0; ch < NCH; ch += CHS) {
                     tmem_ldw<CW>(tacc + ch * CW, v);
                     if (idp && !(P.dbg & 4)) add_roww<CW>(idp + ch * CW, v);
                     if (idh && !(P.dbg & 4)) add_planesw<CW>(idh + ch * CW, idl + ch * CW, v);
@@ -644,7 +668,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 lap(1);
-                epi_barw<ETH>();
+                ebar();
                 if (etid < S * G) {
                     const int s = etid / G, g = etid - s * G;
                     float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -668,10 +692,10 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                     sstat[128 + etid] = b * inv_cnt;
                     sstat[256 + etid] = (s < Sv) ? __ldg(p.rstd + (size_t)(r0 + s) * 8 + n0 / (GS ? GS : 1) + g) : 0.f;
                 }
-                epi_barw<ETH>();
+                ebar();
                 lap(2);
 #pragma unroll 1
-                for (int ch = hf; ch < NCH; ch += NG) {
+                for (int ch = ch0; ch < NCH; ch += CHS) {
                     float y[CW];
                     tmem_ldw<CW>(tacc + ch * CW, v);
                     if (C::STASH) {
@@ -710,7 +734,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             // release the accumulator stage
             lap(3);
             tc_fence_before();
-            epi_barw<ETH>();
+            ebar();
             if (etid == 0) {
                 if (CG == 2) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
             }
@@ -723,7 +747,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                 }
                 atomicAdd(P.ctr + 6, 1ull);
             }
-            if (++as == NACC) { as = 0; aph ^= 1; }
+            if (!TEAM && ++as == NACC) { as = 0; aph ^= 1; }
         }
         if (TE && st_leader) bulk_wait_read0();   // shared memory stays valid until the last stores have read it
     }
@@ -879,12 +903,12 @@ unsigned long long* tc_timer_buffer() {
 }
 namespace {
 
-template <int NT, int GS, bool ACC2, int CG, bool TE, int NG = 2>
+template <int NT, int GS, bool ACC2, int CG, bool TE, int NG = 2, bool TEAM = false>
 int launch_t(TcP& P, cudaStream_t st) {
-    using C = Cfg<NT, GS, ACC2, CG, TE, NG>;
+    using C = Cfg<NT, GS, ACC2, CG, TE, NG, TEAM>;
     static bool configured = false;
     if (!configured) {
-        PMP_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NT, GS, ACC2, CG, TE, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PMP_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NT, GS, ACC2, CG, TE, NG, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES));
         configured = true;
     }
@@ -895,7 +919,7 @@ int launch_t(TcP& P, cudaStream_t st) {
     }
     if (CG == 1) {
         const int grid = P.ntiles < g_num_sms ? P.ntiles : g_num_sms;
-        conv_tc_kernel<NT, GS, ACC2, CG, TE, NG><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(P);
+        conv_tc_kernel<NT, GS, ACC2, CG, TE, NG, TEAM><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(P);
     } else {
         // one cluster of two CTAs (the two SMs of a TPC) per tile pair, persistent over the pairs
         const int nclusters = P.npairs < g_num_sms / 2 ? P.npairs : g_num_sms / 2;
@@ -912,7 +936,7 @@ int launch_t(TcP& P, cudaStream_t st) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        PMP_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NT, GS, ACC2, CG, TE, NG>, P));
+        PMP_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NT, GS, ACC2, CG, TE, NG, TEAM>, P));
     }
     PMP_LAUNCH_OK();
     return 0;
@@ -1069,6 +1093,12 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     }
     if (NT == 64) {
         if (te) {
+            static int team = -1;
+            if (team < 0) { const char* e = getenv("PMP_TC_TEAM"); team = e ? atoi(e) : 1; }
+            if (team && !acc2) {
+                if (gs == 8) return launch_t<64, 8, false, 1, true, 2, true>(P, st);
+                return launch_t<64, 0, false, 1, true, 2, true>(P, st);
+            }
             if (gs == 8) return acc2 ? launch_t<64, 8, true, 1, true>(P, st) : launch_t<64, 8, false, 1, true>(P, st);
             return acc2 ? launch_t<64, 0, true, 1, true>(P, st) : launch_t<64, 0, false, 1, true>(P, st);
         }
