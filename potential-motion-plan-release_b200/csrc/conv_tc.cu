@@ -24,7 +24,7 @@
 // Diagnostics (none of them on by default): PMP_TC_TIMERS=1|2 (+PMP_TC_TIMER_MATCH=N:C1:g) per-role / per-phase cycle
 // counters read through pmp_debug_counters; PMP_TC_DEBUG bit mask -- 1 no epilogue, 2 no direct stores, 4 no
 // identity/yhat loads, 8 no embedding, 16 MMA only (no TMA fill), 32 N=256 issue-rate probe, 64/128 A / B loaded for one
-// tap of five: timing probes whose results are garbage; PMP_TC_WIDE=0 keeps 128-column tiles.
+// tap of five, 512 no TMA stores: timing probes whose results are garbage; PMP_TC_WIDE=0 keeps 128-column tiles.
 #include <cuda.h>
 
 #include <map>
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
         auto stage_release = [&](const CUtensorMap* mf, const CUtensorMap* mh, const CUtensorMap* ml, int c0, int op, int r0) {
             fence_async_smem();
             half_bar(hf);
-            if (st_leader) {
+            if (st_leader && !(P.dbg & 512)) {   // dbg 512: results staged but never stored (timing probe)
                 if (p.ostride == 2) {
                     if (mf) tma_store_4d(mf, sF, c0, op, 0, r0);
                     if (mh) { tma_store_4d(mh, sH, c0, op, 0, r0); tma_store_4d(ml, sL, c0, op, 0, r0); }
