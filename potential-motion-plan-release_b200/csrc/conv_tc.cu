@@ -24,7 +24,7 @@
 // Diagnostics (none of them on by default): PMP_TC_TIMERS=1|2 (+PMP_TC_TIMER_MATCH=N:C1:g) per-role / per-phase cycle
 // counters read through pmp_debug_counters; PMP_TC_DEBUG bit mask -- 1 no epilogue, 2 no direct stores, 4 no
 // identity/yhat loads, 8 no embedding, 16 MMA only (no TMA fill), 32 N=256 issue-rate probe, 64/128 A / B loaded for one
-// tap of five, 512 no TMA stores: timing probes whose results are garbage; PMP_TC_WIDE=0 keeps 128-column tiles.
+// tap of five, 512 no TMA stores, 2048 all stores to the first rows: timing probes whose results are garbage; PMP_TC_WIDE=0 keeps 128-column tiles.
 #include <cuda.h>
 
 #include <map>
@@ -381,6 +381,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
         };
         // make the staged rows visible to the TMA engine and write them out as boxes of the tile
         auto stage_release = [&](const CUtensorMap* mf, const CUtensorMap* mh, const CUtensorMap* ml, int c0, int op, int r0) {
+            if (P.dbg & 2048) r0 = (int)blockIdx.x * S;   // timing probe: every CTA keeps storing to its own first tile (same TMA work, no new HBM lines)
             fence_async_smem();
             half_bar(hf);
             if (st_leader && !(P.dbg & 512)) {   // dbg 512: results staged but never stored (timing probe)
