@@ -105,8 +105,15 @@ __device__ __forceinline__ void inline_conv(const ConvP& p, const float* sinl, i
     }
 }
 
-template <int NT, int GS, bool ACC2, int CG, bool TE, int NG = 2, bool TEAM = false>
+template <int NT, int GS, bool ACC2, int CG, bool TE, int NG = 2, bool TEAM = false, bool AR = false>
 struct Cfg {
+    // AR (A-operand reuse, stride-1 convs on the 256-column pair tiles): the haloed activation tile of a 32-channel
+    // block is loaded ONCE, position-major (row = h*S + s), and the taps are descriptor start offsets of S rows;
+    // only the weight tiles stream per tap.  Cuts the L2->SM operand traffic of a 5-tap conv by 40 %.
+    static_assert(!AR || (NT == 256 && CG == 2 && !ACC2 && !TEAM), "A reuse: 256-column pair tiles");
+    static constexpr int NA = 2;                        // haloed A buffers
+    static constexpr int A_BUF_ROWS = 192;              // (HJ + 4) * S <= 128 + 4 * 16
+    static constexpr int A_BUF_BYTES = A_BUF_ROWS * 32 * 2;   // per plane (32-channel K blocks)
     // TEAM: the two epilogue warp groups work on ALTERNATE TILES (each walks all chunks of its own tile, with its own
     // barrier and scratch tables) instead of on alternate chunks of one tile: two per-tile latency chains (TMEM load ->
     // stats -> barrier -> reduce -> barrier -> output pass) overlap.  For the narrow, epilogue-bound 64-column tiles.
@@ -125,7 +132,9 @@ struct Cfg {
     static constexpr int B_TILE_BYTES = (NT / CG) * BKC * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_TILE_BYTES;
     static constexpr int NSTAGE =
-        CG == 2 ? (NT == 256 ? 4 : (NT == 128 ? (TE ? 3 : 4) : 3)) : (NT == 64 ? (TE ? 2 : 3) : (NT == 128 ? 3 : 2));
+        AR ? 5 : (CG == 2 ? (NT == 256 ? 4 : (NT == 128 ? (TE ? 3 : 4) : 3)) : (NT == 64 ? (TE ? 2 : 3) : (NT == 128 ? 3 : 2)));
+    // AR: the ring holds the weight tiles only (NSTAGE stages of 2 planes), the A buffers sit in front of it
+    static constexpr int RING_BYTES = AR ? (NA * 2 * A_BUF_BYTES + NSTAGE * 2 * B_TILE_BYTES) : NSTAGE * STAGE_BYTES;
     static constexpr int STG_HALF_BYTES = 128 * CW * 4 + 2 * 128 * CW * 2;   // F | H | L of one warp group
     static constexpr int STG_BYTES = TE ? NG * STG_HALF_BYTES : 0;
     static constexpr int INL_FLOATS = NT == 64 ? 5 * 16 * 64 : 0;   // inline small-K conv weights [taps][D<=16][64]
@@ -149,22 +158,22 @@ struct Cfg {
     static constexpr int STAT_FLOATS = 384;
     static constexpr int COL_FLOATS = 4 * NT;
     static constexpr int ROW_INTS = 4 * 128;
-    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + STG_BYTES +
+    static constexpr int SMEM_BYTES = RING_BYTES + STG_BYTES +
                                       (TBUF_FLOATS + NTEAM * (PART_FLOATS + STAT_FLOATS + COL_FLOATS + INL_FLOATS) + ROW_INTS) * 4 +
                                       256 + 1024;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-template <int NT, int GS, bool ACC2, int CG, bool TE, int NG, bool TEAM>
+template <int NT, int GS, bool ACC2, int CG, bool TE, int NG, bool TEAM, bool AR>
 __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_constant__ TcP P) {
-    using C = Cfg<NT, GS, ACC2, CG, TE, NG, TEAM>;
+    using C = Cfg<NT, GS, ACC2, CG, TE, NG, TEAM, AR>;
     constexpr int CW = C::CW, ETH = C::ETHREADS;
     constexpr int G = C::G, NCH = C::NCH, NSTAGE = C::NSTAGE, NACC = C::NACC;
     const ConvP& p = P.e;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
-    uint8_t* stg = smem + NSTAGE * C::STAGE_BYTES;   // TE staging tiles (1024-byte aligned)
+    uint8_t* stg = smem + C::RING_BYTES;   // TE staging tiles (1024-byte aligned)
     float* tbuf = reinterpret_cast<float*>(stg + C::STG_BYTES);
     // per-tile scratch tables (one set per epilogue team): row/slab partials | slab stats | column params | inline weights
     const int team_of_warp = (TEAM && (threadIdx.x >> 5) >= 6) ? 1 : 0;
@@ -179,7 +188,9 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
     uint64_t* empty = bars + NSTAGE;
     uint64_t* tfull = bars + 2 * NSTAGE;
     uint64_t* tempty = tfull + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
+    uint64_t* afull = tempty + 4;          // AR: haloed A buffers
+    uint64_t* aempty = afull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.S, HJ = p.HJ, N = p.N;
@@ -199,6 +210,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         // tempty: the epilogues of both CTAs of a pair release the accumulator stage to the leader's MMA warp
         for (int i = 0; i < 4; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CG); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -239,6 +251,38 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             };
             int s = 0;
             uint32_t ph = 0;
+            if constexpr (AR) {
+                // A reuse: per 32-channel block ONE haloed, position-major activation tile (both planes), then one
+                // weight tile pair per tap through the ring
+                int ai = 0;
+                uint32_t aph = 0;
+                uint8_t* const bbase = smem + C::NA * 2 * C::A_BUF_BYTES;
+                const uint32_t bytesAh = (uint32_t)((HJ + 4) * S * BKC * 2);
+                for (int tile = sched0; tile < nsched; tile += sched_step) {
+                    const int r0 = ((tile / P.tilesN) * CG + (int)crank) * S, n0 = (tile % P.tilesN) * NT;
+                    const int nb0 = n0 + (int)crank * (NT / CG);
+                    for (int cb = 0; cb < P.kpt + P.nkb2; ++cb) {
+                        const bool sl2 = cb >= P.kpt;
+                        const int c0 = (sl2 ? cb - P.kpt : cb) * BKC;
+                        mbar_wait(&aempty[ai], aph ^ 1);
+                        uint8_t* ab = smem + ai * 2 * C::A_BUF_BYTES;
+                        if (crank == 0) mbar_expect_tx(&afull[ai], CG * 2 * bytesAh);
+                        tma2_load_3d(ab, sl2 ? &P.mA2h : &P.mA1h, &afull[ai], c0, r0, -2);
+                        tma2_load_3d(ab + C::A_BUF_BYTES, sl2 ? &P.mA2l : &P.mA1l, &afull[ai], c0, r0, -2);
+                        const int nt = sl2 ? 1 : p.ntaps[0];
+                        for (int tap = 0; tap < nt; ++tap) {
+                            mbar_wait(&empty[s], ph ^ 1);
+                            uint8_t* st = bbase + s * 2 * C::B_TILE_BYTES;
+                            if (crank == 0) mbar_expect_tx(&full[s], CG * 2 * C::B_TILE_BYTES);
+                            const int wr = sl2 ? nb0 : p.tap_k[0][tap] * N + nb0;
+                            tma2_load_2d(st, sl2 ? &P.mW2h : &P.mW1h, &full[s], c0, wr);
+                            tma2_load_2d(st + C::B_TILE_BYTES, sl2 ? &P.mW2l : &P.mW1l, &full[s], c0, wr);
+                            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+                        }
+                        if (++ai == C::NA) { ai = 0; aph ^= 1; }
+                    }
+                }
+            } else
             for (int tile = sched0; tile < nsched; tile += sched_step) {
                 const int op = tile % P.nphase, t2 = tile / P.nphase;
                 const int r0 = ((t2 / P.tilesN) * CG + (int)crank) * S, n0 = (t2 % P.tilesN) * NT;
@@ -298,6 +342,8 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             };
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
+            int ai = 0;            // AR: haloed A buffer ring
+            uint32_t aphA = 0;
             const long long tm0 = (P.ctr && P.tmode == 1) ? clock64() : 0;
             for (int tile = sched0; tile < nsched; tile += sched_step) {
                 const long long te0 = (P.ctr && P.tmode == 1) ? clock64() : 0;
@@ -307,6 +353,42 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                 const uint32_t d1 = tmem_base + (uint32_t)(as * C::ACC_COLS);
                 const uint32_t d2 = ACC2 ? d1 + NT : d1;
                 uint32_t acc1 = 0, acc2 = ACC2 ? 0u : 1u;
+                if constexpr (AR) {
+                    uint8_t* const bbase = smem + C::NA * 2 * C::A_BUF_BYTES;
+                    uint32_t accum = 0;
+                    for (int cb = 0; cb < P.kpt + P.nkb2; ++cb) {
+                        const bool sl2 = cb >= P.kpt;
+                        const long long tf0 = (P.ctr && P.tmode == 1) ? clock64() : 0;
+                        mbar_wait(&afull[ai], aphA);
+                        if (P.ctr && P.tmode == 1) atomicAdd(P.ctr + 0, (unsigned long long)(clock64() - tf0));
+                        tc_fence_after();
+                        const uint32_t abuf = smem_u32(smem + ai * 2 * C::A_BUF_BYTES);
+                        const int nt = sl2 ? 1 : p.ntaps[0];
+                        for (int tap = 0; tap < nt; ++tap) {
+                            const long long tf1 = (P.ctr && P.tmode == 1) ? clock64() : 0;
+                            mbar_wait(&full[s], ph);
+                            if (P.ctr && P.tmode == 1) atomicAdd(P.ctr + 0, (unsigned long long)(clock64() - tf1));
+                            tc_fence_after();
+                            // tap = start offset of (shift + 2) * S rows inside the haloed tile
+                            const uint32_t aoff = (uint32_t)(((sl2 ? 0 : p.tap_shift[0][tap]) + 2) * S * BKC * 2);
+                            const uint32_t sb = smem_u32(bbase + s * 2 * C::B_TILE_BYTES);
+                            const uint64_t ah = make_desc<BKC>(abuf + aoff), al = make_desc<BKC>(abuf + C::A_BUF_BYTES + aoff);
+                            const uint64_t bh = make_desc<BKC>(sb), bl = make_desc<BKC>(sb + C::B_TILE_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BKC / 16; ++k) {
+                                const uint64_t ko = (uint64_t)(k * 2);
+                                mma(d1, ah + ko, bh + ko, idesc, accum);
+                                mma(d1, ah + ko, bl + ko, idesc, 1u);
+                                mma(d1, al + ko, bh + ko, idesc, 1u);
+                                accum = 1u;
+                            }
+                            commit(&empty[s]);
+                            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+                        }
+                        commit(&aempty[ai]);      // the haloed tile may be overwritten (in both CTAs)
+                        if (++ai == C::NA) { ai = 0; aphA ^= 1; }
+                    }
+                } else {
                 const int nkb1 = p.ntaps[tile % P.nphase] * P.kpt;
                 for (int kb = 0; kb < nkb1 + P.nkb2; ++kb) {
                     const long long tf0 = (P.ctr && P.tmode == 1) ? clock64() : 0;
@@ -330,6 +412,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                     if (slab2) acc2 = 1u; else acc1 = 1u;
                     if (!(P.dbg & 16)) commit(&empty[s]);   // frees the smem stage (of both CTAs) when these MMAs have read it
                     if (++s == NSTAGE) { s = 0; ph ^= 1; }
+                }
                 }
                 commit(&tfull[as]);      // accumulator complete
                 if (++as == NACC) { as = 0; aph ^= 1; }
@@ -357,6 +440,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
         const int mrow = eq * 32 + lane;
         const int act = p.act;
         const float inv_cnt = 1.0f / (float)(HJ * (GS ? GS : 1));
+        const int RS = AR ? S : 1;               // row stride between consecutive positions of one sample
         int as = 0;
         uint32_t aph = 0;
         long long tlap = 0;
@@ -389,8 +473,9 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                     if (mf) tma_store_4d(mf, sF, c0, op, 0, r0);
                     if (mh) { tma_store_4d(mh, sH, c0, op, 0, r0); tma_store_4d(ml, sL, c0, op, 0, r0); }
                 } else {
-                    if (mf) tma_store_3d(mf, sF, c0, 0, r0);
-                    if (mh) { tma_store_3d(mh, sH, c0, 0, r0); tma_store_3d(ml, sL, c0, 0, r0); }
+                    const int c1 = AR ? r0 : 0, c2 = AR ? 0 : r0;   // position-major store maps are (C, R, H)
+                    if (mf) tma_store_3d(mf, sF, c0, c1, c2);
+                    if (mh) { tma_store_3d(mh, sH, c0, c1, c2); tma_store_3d(ml, sL, c0, c1, c2); }
                 }
                 bulk_commit();
             }
@@ -421,10 +506,12 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             if (GS)
                 for (int i = etid; i < C::PART_FLOATS; i += ESTEP) spart[i] = 0.f;
             // per-row constants
-            const bool valid = mrow < Mv;
-            const int s_loc = min(mrow / HJ, S - 1);
+            // accumulator row -> (sample, position): sample-major tiles, position-major (row = h*S + s) with A reuse
+            const int s_loc = AR ? (mrow % S) : min(mrow / HJ, S - 1);
+            const int hrow_ = AR ? (mrow / S) : (mrow - s_loc * HJ);
+            const bool valid = AR ? (hrow_ < HJ && s_loc < Sv) : (mrow < Mv);
             const int rg = valid ? r0 + s_loc : 0;                              // global sample (row of R)
-            const size_t orow = valid ? (size_t)(r0 + s_loc) * p.Hout + (size_t)((mrow - s_loc * HJ) * p.ostride + op) : 0;
+            const size_t orow = valid ? (size_t)(r0 + s_loc) * p.Hout + (size_t)(hrow_ * p.ostride + op) : 0;
             const int slab0 = s_loc * G;
             const long long tq0 = (P.ctr && etid == 0) ? clock64() : 0;
             if (P.ctr && P.tmode == 2 && etid == 0 && tlap) atomicAdd(P.ctr + 5, (unsigned long long)(tq0 - tlap));   // preamble
@@ -448,7 +535,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             const uint32_t tacc = tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)(as * C::ACC_COLS);
             const uint32_t tstash = tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)(NACC * C::ACC_COLS + as * NT);
             float v[CW];
-            const int hrow = mrow - s_loc * HJ;
+            const int hrow = hrow_;
             if (C::INL_FLOATS && p.inl_mode == 1) {
                 // the convolution itself has K = taps*D <= 70: compute it here and park it in the (unused)
                 // accumulator so that the GroupNorm passes below run unchanged
@@ -495,18 +582,18 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                     const int s = etid / G, g = etid - s * G;
                     float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
                     for (int h2 = 0; h2 < C::PSLOTS; ++h2) {
-                        const float* base = spart + ((h2 * 128 + s * HJ) * G + g) * 2;
+                        const float* base = spart + ((h2 * 128 + (AR ? s : s * HJ)) * G + g) * 2;   // + j * RS rows
                         int j = 0;
                         for (; j + 4 <= HJ; j += 4) {
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                a4[u] += base[(j + u) * G * 2];
-                                b4[u] += base[(j + u) * G * 2 + 1];
+                                a4[u] += base[(j + u) * RS * G * 2];
+                                b4[u] += base[(j + u) * RS * G * 2 + 1];
                             }
                         }
                         for (; j < HJ; ++j) {
-                            a4[0] += base[j * G * 2];
-                            b4[0] += base[j * G * 2 + 1];
+                            a4[0] += base[j * RS * G * 2];
+                            b4[0] += base[j * RS * G * 2 + 1];
                         }
                     }
                     const float a = (a4[0] + a4[1]) + (a4[2] + a4[3]), b = (b4[0] + b4[1]) + (b4[2] + b4[3]);
@@ -674,18 +761,18 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                     const int s = etid / G, g = etid - s * G;
                     float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
                     for (int h2 = 0; h2 < C::PSLOTS; ++h2) {
-                        const float* base = spart + ((h2 * 128 + s * HJ) * G + g) * 2;
+                        const float* base = spart + ((h2 * 128 + (AR ? s : s * HJ)) * G + g) * 2;   // + j * RS rows
                         int j = 0;
                         for (; j + 4 <= HJ; j += 4) {
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                a4[u] += base[(j + u) * G * 2];
-                                b4[u] += base[(j + u) * G * 2 + 1];
+                                a4[u] += base[(j + u) * RS * G * 2];
+                                b4[u] += base[(j + u) * RS * G * 2 + 1];
                             }
                         }
                         for (; j < HJ; ++j) {
-                            a4[0] += base[j * G * 2];
-                            b4[0] += base[j * G * 2 + 1];
+                            a4[0] += base[j * RS * G * 2];
+                            b4[0] += base[j * RS * G * 2 + 1];
                         }
                     }
                     const float a = (a4[0] + a4[1]) + (a4[2] + a4[3]), b = (b4[0] + b4[1]) + (b4[2] + b4[3]);
@@ -831,6 +918,26 @@ int act_map4(CUtensorMap* out, const __nv_bfloat16* base, int C, int Hin, int R,
     remember_map(key, *out);
     return 0;
 }
+// A reuse: haloed, position-major activation tile.  Map (C, R, H) -- the sample index runs faster than the
+// position in the box, so shared-memory row = h*S + s -- box (bk, S, HJ + 4) started at position -2.
+int act_map_pm(CUtensorMap* out, const __nv_bfloat16* base, int C, int H, int R, int ld, int S, int HJ, int bk) {
+    MapKey key(base, C, H, R, ld, S * 1000 + HJ, 5 + 100 * bk);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+    EncodeFn enc = get_encode();
+    PMP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)R, (cuuint64_t)H};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2 * (cuuint64_t)H, (cuuint64_t)ld * 2};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)S, (cuuint32_t)(HJ + 4)};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(position-major activation C=%d H=%d R=%d ld=%d S=%d) failed: %d", C, H, R,
+                ld, S, (int)r);
+    remember_map(key, *out);
+    return 0;
+}
 // weight plane [taps*N][C] BF16 -> 2-D map (C, taps*N), box (64, NT)
 int w_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int rows, int NT, int bk) {
     MapKey key(base, C, rows, NT, 0, 0, 2 + 100 * bk);
@@ -854,8 +961,8 @@ int w_map(CUtensorMap* out, const __nv_bfloat16* base, int C, int rows, int NT, 
 // output tensor [R][Hout][ld] (fp32 or BF16) -> store map with box (32, HJ, S): 3-D (C, H, R) for unit output
 // stride, 4-D (C, phase, H/2, R) for the stride-2 scatter of the transposed convs
 int st_map(CUtensorMap* out, const void* base, bool f32, int C, int Hout, int R, int ld, int S, int HJ, int ostride,
-           int cw) {
-    MapKey key(base, C, Hout, R, ld, S * 1000 + HJ, (f32 ? 10 : 20) + ostride + 1000 * cw);
+           int cw, bool pm = false) {
+    MapKey key(base, C, Hout, R, ld, S * 1000 + HJ, (f32 ? 10 : 20) + ostride + 1000 * cw + (pm ? 100000 : 0));
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return 0; }
     EncodeFn enc = get_encode();
@@ -865,7 +972,15 @@ int st_map(CUtensorMap* out, const void* base, bool f32, int C, int Hout, int R,
     const int rowb = cw * (int)es;   // bytes per staged row: 128 / 64 / 32 -> the matching swizzle span
     const CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUresult r;
-    if (ostride == 1) {
+    if (pm) {
+        // position-major staging tiles (A-reuse kernels): box (cw, S, HJ) of the (C, R, H) view
+        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)R, (cuuint64_t)Hout};
+        cuuint64_t strides[2] = {(cuuint64_t)ld * es * (cuuint64_t)Hout, (cuuint64_t)ld * es};
+        cuuint32_t box[3] = {(cuuint32_t)cw, (cuuint32_t)S, (cuuint32_t)HJ};
+        cuuint32_t el[3] = {1, 1, 1};
+        r = enc(out, dt, 3, const_cast<void*>(base), dims, strides, box, el, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (ostride == 1) {
         cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Hout, (cuuint64_t)R};
         cuuint64_t strides[2] = {(cuuint64_t)ld * es, (cuuint64_t)ld * es * (cuuint64_t)Hout};
         cuuint32_t box[3] = {(cuuint32_t)cw, (cuuint32_t)HJ, (cuuint32_t)S};
@@ -904,12 +1019,12 @@ unsigned long long* tc_timer_buffer() {
 }
 namespace {
 
-template <int NT, int GS, bool ACC2, int CG, bool TE, int NG = 2, bool TEAM = false>
+template <int NT, int GS, bool ACC2, int CG, bool TE, int NG = 2, bool TEAM = false, bool AR = false>
 int launch_t(TcP& P, cudaStream_t st) {
-    using C = Cfg<NT, GS, ACC2, CG, TE, NG, TEAM>;
+    using C = Cfg<NT, GS, ACC2, CG, TE, NG, TEAM, AR>;
     static bool configured = false;
     if (!configured) {
-        PMP_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NT, GS, ACC2, CG, TE, NG, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PMP_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NT, GS, ACC2, CG, TE, NG, TEAM, AR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES));
         configured = true;
     }
@@ -920,7 +1035,7 @@ int launch_t(TcP& P, cudaStream_t st) {
     }
     if (CG == 1) {
         const int grid = P.ntiles < g_num_sms ? P.ntiles : g_num_sms;
-        conv_tc_kernel<NT, GS, ACC2, CG, TE, NG, TEAM><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(P);
+        conv_tc_kernel<NT, GS, ACC2, CG, TE, NG, TEAM, AR><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(P);
     } else {
         // one cluster of two CTAs (the two SMs of a TPC) per tile pair, persistent over the pairs
         const int nclusters = P.npairs < g_num_sms / 2 ? P.npairs : g_num_sms / 2;
@@ -937,7 +1052,7 @@ int launch_t(TcP& P, cudaStream_t st) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        PMP_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NT, GS, ACC2, CG, TE, NG, TEAM>, P));
+        PMP_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NT, GS, ACC2, CG, TE, NG, TEAM, AR>, P));
     }
     PMP_LAUNCH_OK();
     return 0;
@@ -1036,8 +1151,17 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     P.kpt = inl_pre ? 0 : p.C1 / bk;
     P.nkb2 = ((p.A2 || p.A2_hi) && !inl_post) ? p.C2 / bk : 0;
     const int brows = NT / cg;   // B rows staged per CTA
+    static int ar_on = -1;
+    if (ar_on < 0) { const char* e = getenv("PMP_TC_AR"); ar_on = e ? atoi(e) : 1; }
+    // A-operand reuse for the stride-1 convs on the 256-column pair tiles
+    const bool ar = ar_on && m34 && NT == 256 && te && p.nphase == 1 && p.istride == 1 && p.ostride == 1;
     int rc;
-    if (!inl_pre) {
+    if (ar) {
+        if ((rc = act_map_pm(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S, p.HJ, bk))) return rc;
+        if ((rc = act_map_pm(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S, p.HJ, bk))) return rc;
+        if ((rc = w_map(&P.mW1h, p.W1_hi, p.C1, p.ntaps[0] * p.N, brows, bk))) return rc;
+        if ((rc = w_map(&P.mW1l, p.W1_lo, p.C1, p.ntaps[0] * p.N, brows, bk))) return rc;
+    } else if (!inl_pre) {
         if (P.mode4d) {
             if ((rc = act_map4(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S, p.HJ, bk))) return rc;
             if ((rc = act_map4(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S, p.HJ, bk))) return rc;
@@ -1051,7 +1175,12 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
         if ((rc = w_map(&P.mW1h, p.W1_hi, p.C1, (maxk + 1) * p.N, brows, bk))) return rc;
         if ((rc = w_map(&P.mW1l, p.W1_lo, p.C1, (maxk + 1) * p.N, brows, bk))) return rc;
     }
-    if ((p.A2 || p.A2_hi) && !inl_post) {
+    if ((p.A2 || p.A2_hi) && !inl_post && ar) {
+        if ((rc = act_map_pm(&P.mA2h, p.A2_hi, p.C2, p.Hin, p.R, p.lda2, S, p.HJ, bk))) return rc;
+        if ((rc = act_map_pm(&P.mA2l, p.A2_lo, p.C2, p.Hin, p.R, p.lda2, S, p.HJ, bk))) return rc;
+        if ((rc = w_map(&P.mW2h, p.W2_hi, p.C2, p.N, brows, bk))) return rc;
+        if ((rc = w_map(&P.mW2l, p.W2_lo, p.C2, p.N, brows, bk))) return rc;
+    } else if ((p.A2 || p.A2_hi) && !inl_post) {
         if ((rc = act_map(&P.mA2h, p.A2_hi, p.C2, p.Hin, p.R, p.lda2, S, bk))) return rc;
         if ((rc = act_map(&P.mA2l, p.A2_lo, p.C2, p.Hin, p.R, p.lda2, S, bk))) return rc;
         if ((rc = w_map(&P.mW2h, p.W2_hi, p.C2, p.N, brows, bk))) return rc;
@@ -1059,20 +1188,30 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     }
     if (te) {
         const int os = p.ostride;
-        if (p.yhat && p.gn_fwd && (rc = st_map(&P.mSy, p.yhat, true, p.N, p.Hout, p.R, p.ldy, S, p.HJ, os, cw))) return rc;
-        if (p.out && (rc = st_map(&P.mSo, p.out, true, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os, cw))) return rc;
+        if (p.yhat && p.gn_fwd && (rc = st_map(&P.mSy, p.yhat, true, p.N, p.Hout, p.R, p.ldy, S, p.HJ, os, cw, ar))) return rc;
+        if (p.out && (rc = st_map(&P.mSo, p.out, true, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os, cw, ar))) return rc;
         if (p.out_hi) {
-            if ((rc = st_map(&P.mSoh, p.out_hi, false, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os, cw))) return rc;
-            if ((rc = st_map(&P.mSol, p.out_lo, false, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os, cw))) return rc;
+            if ((rc = st_map(&P.mSoh, p.out_hi, false, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os, cw, ar))) return rc;
+            if ((rc = st_map(&P.mSol, p.out_lo, false, p.N, p.Hout, p.R, p.ldo, S, p.HJ, os, cw, ar))) return rc;
         }
-        if (p.gy && (rc = st_map(&P.mSg, p.gy, true, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os, cw))) return rc;
+        if (p.gy && (rc = st_map(&P.mSg, p.gy, true, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os, cw, ar))) return rc;
         if (p.gy_hi) {
-            if ((rc = st_map(&P.mSgh, p.gy_hi, false, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os, cw))) return rc;
-            if ((rc = st_map(&P.mSgl, p.gy_lo, false, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os, cw))) return rc;
+            if ((rc = st_map(&P.mSgh, p.gy_hi, false, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os, cw, ar))) return rc;
+            if ((rc = st_map(&P.mSgl, p.gy_lo, false, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os, cw, ar))) return rc;
         }
     }
     const bool gn = p.gn_fwd || p.gn_bwd;
     const int gs = gn ? p.N / 8 : 0;
+    if (ar) {
+        if (ng4) {
+            if (gs == 32) return launch_t<256, 32, false, 2, true, 4, false, true>(P, st);
+            if (gs == 64) return launch_t<256, 64, false, 2, true, 4, false, true>(P, st);
+            return launch_t<256, 0, false, 2, true, 4, false, true>(P, st);
+        }
+        if (gs == 32) return launch_t<256, 32, false, 2, true, 2, false, true>(P, st);
+        if (gs == 64) return launch_t<256, 64, false, 2, true, 2, false, true>(P, st);
+        return launch_t<256, 0, false, 2, true, 2, false, true>(P, st);
+    }
     if (ng4) {
         if (NT == 256) {
             if (gs == 32) return launch_t<256, 32, false, 2, true, 4>(P, st);
