@@ -110,7 +110,8 @@ struct Cfg {
     // AR (A-operand reuse, stride-1 convs on the 256-column pair tiles): the haloed activation tile of a 32-channel
     // block is loaded ONCE, position-major (row = h*S + s), and the taps are descriptor start offsets of S rows;
     // only the weight tiles stream per tap.  Cuts the L2->SM operand traffic of a 5-tap conv by 40 %.
-    static_assert(!AR || (NT == 256 && CG == 2 && !ACC2 && !TEAM), "A reuse: 256-column pair tiles");
+    static_assert(!AR || ((NT == 256 && CG == 2 && !TEAM) || (NT == 64 && CG == 1)), "A reuse: 256-column pair tiles, 64-column tiles");
+    static_assert(!AR || !ACC2, "A reuse: one accumulator");
     static constexpr int NA = 2;                        // haloed A buffers
     static constexpr int A_BUF_ROWS = 192;              // (HJ + 4) * S <= 128 + 4 * 16
     static constexpr int A_BUF_BYTES = A_BUF_ROWS * 32 * 2;   // per plane (32-channel K blocks)
@@ -127,7 +128,7 @@ struct Cfg {
     // TE: TMA-store epilogue (64 KB of staging tiles: per half of the epilogue warps one fp32 and two BF16 tiles)
     // channels per K block: 64 (one 128-byte swizzle row) except for the 256-column tiles, which take 32-channel
     // blocks (64-byte rows, SWIZZLE_64B) so that four stages of the same total size give the TMA more lookahead
-    static constexpr int BKC = NT == 256 ? 32 : 64;
+    static constexpr int BKC = (NT == 256 || AR) ? 32 : 64;
     static constexpr int A_BYTES = 128 * BKC * 2;
     static constexpr int B_TILE_BYTES = (NT / CG) * BKC * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_TILE_BYTES;
@@ -267,16 +268,16 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                         mbar_wait(&aempty[ai], aph ^ 1);
                         uint8_t* ab = smem + ai * 2 * C::A_BUF_BYTES;
                         if (crank == 0) mbar_expect_tx(&afull[ai], CG * 2 * bytesAh);
-                        tma2_load_3d(ab, sl2 ? &P.mA2h : &P.mA1h, &afull[ai], c0, r0, -2);
-                        tma2_load_3d(ab + C::A_BUF_BYTES, sl2 ? &P.mA2l : &P.mA1l, &afull[ai], c0, r0, -2);
+                        ld3(ab, sl2 ? &P.mA2h : &P.mA1h, &afull[ai], c0, r0, -2);
+                        ld3(ab + C::A_BUF_BYTES, sl2 ? &P.mA2l : &P.mA1l, &afull[ai], c0, r0, -2);
                         const int nt = sl2 ? 1 : p.ntaps[0];
                         for (int tap = 0; tap < nt; ++tap) {
                             mbar_wait(&empty[s], ph ^ 1);
                             uint8_t* st = bbase + s * 2 * C::B_TILE_BYTES;
                             if (crank == 0) mbar_expect_tx(&full[s], CG * 2 * C::B_TILE_BYTES);
                             const int wr = sl2 ? nb0 : p.tap_k[0][tap] * N + nb0;
-                            tma2_load_2d(st, sl2 ? &P.mW2h : &P.mW1h, &full[s], c0, wr);
-                            tma2_load_2d(st + C::B_TILE_BYTES, sl2 ? &P.mW2l : &P.mW1l, &full[s], c0, wr);
+                            ld2(st, sl2 ? &P.mW2h : &P.mW1h, &full[s], c0, wr);
+                            ld2(st + C::B_TILE_BYTES, sl2 ? &P.mW2l : &P.mW1l, &full[s], c0, wr);
                             if (++s == NSTAGE) { s = 0; ph ^= 1; }
                         }
                         if (++ai == C::NA) { ai = 0; aph ^= 1; }
@@ -1147,14 +1148,16 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     }
     P.ntiles = P.tilesM * P.tilesN * P.nphase;
     P.npairs = ((P.tilesM + 1) / 2) * P.tilesN * P.nphase;
-    const int bk = NT == 256 ? 32 : 64;   // Cfg::BKC
+    static int ar_on = -1;
+    if (ar_on < 0) { const char* e = getenv("PMP_TC_AR"); ar_on = e ? atoi(e) : 1; }   // 64-column tiles: measured neutral (-0.4 %), off by default
+    // A-operand reuse for the stride-1 convs on the 256-column pair tiles and (bit 1 of PMP_TC_AR) the 64-column tiles
+    const bool s1conv = p.nphase == 1 && p.istride == 1 && p.ostride == 1;
+    const bool ar = m34 && te && s1conv &&
+                    (((ar_on & 1) && NT == 256) || ((ar_on & 2) && NT == 64 && !p.inl_x && !acc2 && !ng4));
+    const int bk = (NT == 256 || ar) ? 32 : 64;   // Cfg::BKC
     P.kpt = inl_pre ? 0 : p.C1 / bk;
     P.nkb2 = ((p.A2 || p.A2_hi) && !inl_post) ? p.C2 / bk : 0;
     const int brows = NT / cg;   // B rows staged per CTA
-    static int ar_on = -1;
-    if (ar_on < 0) { const char* e = getenv("PMP_TC_AR"); ar_on = e ? atoi(e) : 1; }
-    // A-operand reuse for the stride-1 convs on the 256-column pair tiles
-    const bool ar = ar_on && m34 && NT == 256 && te && p.nphase == 1 && p.istride == 1 && p.ostride == 1;
     int rc;
     if (ar) {
         if ((rc = act_map_pm(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S, p.HJ, bk))) return rc;
@@ -1202,6 +1205,10 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     }
     const bool gn = p.gn_fwd || p.gn_bwd;
     const int gs = gn ? p.N / 8 : 0;
+    if (ar && NT == 64) {
+        if (gs == 8) return launch_t<64, 8, false, 1, true, 2, true, true>(P, st);
+        return launch_t<64, 0, false, 1, true, 2, true, true>(P, st);
+    }
     if (ar) {
         if (ng4) {
             if (gs == 32) return launch_t<256, 32, false, 2, true, 4, false, true>(P, st);
