@@ -365,7 +365,7 @@ def main():
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     is_tc = prof[1][0] > prof[0][0]
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1d_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1e_traffic.json")
     if is_tc and os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")   # from the committed ncu --set full capture
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
