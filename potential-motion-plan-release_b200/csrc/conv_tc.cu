@@ -16,15 +16,18 @@
 //   * persistent CTAs, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2..9 epilogue;
 //     shared-memory ring of NSTAGE stages, two TMEM accumulator stages so the epilogue of tile i overlaps the main
 //     loop of tile i+1;
-//   * template <NT, GS, ACC2, CG, TE>: NT tile columns (64/128/192/256), GS GroupNorm group size (0: none), ACC2 a
+//   * template <NT, GS, ACC2, CG, TE, NG, TEAM, AR>: NT tile columns (64/128/192/256), GS GroupNorm group size (0: none), ACC2 a
 //     separate accumulator for the forward residual 1x1 conv, CG = 2 CTA pairs (tcgen05 cta_group::2: M = 256 over
 //     the two SMs of a TPC, each CTA stages its own A rows and half of the B rows; 256-column tiles use 32-channel
 //     K blocks / SWIZZLE_64B), TE the TMA-store epilogue (results staged in swizzled shared-memory tiles and written
-//     by cp.async.bulk.tensor stores).  DESIGN.md 3.1 has the measurements behind these choices.
+//     by cp.async.bulk.tensor stores); NG = 4: 16 epilogue warps on 16-column chunks (GroupNorm-backward launches);
+//     TEAM: the two epilogue warp groups take alternate tiles (64-column forward tiles); AR: A-operand reuse -- the
+//     haloed, position-major activation tile of a channel block is loaded once and the taps are descriptor offsets
+//     (stride-1 convs on the 256-column pair tiles).  DESIGN.md 3.1 has the measurements behind these choices.
 // Diagnostics (none of them on by default): PMP_TC_TIMERS=1|2 (+PMP_TC_TIMER_MATCH=N:C1:g) per-role / per-phase cycle
 // counters read through pmp_debug_counters; PMP_TC_DEBUG bit mask -- 1 no epilogue, 2 no direct stores, 4 no
 // identity/yhat loads, 8 no embedding, 16 MMA only (no TMA fill), 32 N=256 issue-rate probe, 64/128 A / B loaded for one
-// tap of five, 512 no TMA stores, 2048 all stores to the first rows: timing probes whose results are garbage; PMP_TC_WIDE=0 keeps 128-column tiles.
+// tap of five, 512 no TMA stores, 2048 all stores to the first rows: timing probes whose results are garbage; PMP_TC_WIDE=0 keeps 128-column tiles, PMP_TC_AR=0 / PMP_TC_TEAM=0 / PMP_TC_NG4_BWD=0 switch the respective variants off.
 #include <cuda.h>
 
 #include <map>
