@@ -57,6 +57,8 @@ def main(argv=None, robot='maze2d'):
                     help='problem file of the reference (<dataset>-problems.hdf5, needs h5py) or its .npz conversion '
                          '(pmp_b200.ingest); default: synthetic problems')
     ap.add_argument('--hext', type=float, default=None, help='half extent of the obstacles in --problems')
+    ap.add_argument('--layouts', default=None, help='concave mazes: rand_rec2dgrp/<env_list_name>_eval.npy')
+    ap.add_argument('--concave43', default=None, help='concave mazes: rand_rec2dgrp/<env_list_name>_43_eval.pkl')
     ap.add_argument('--device', default='cuda:0')
     args = ap.parse_args(argv)
     a, diffusion = load_diffusion(args.family, args.logdir, args.device)
@@ -69,7 +71,15 @@ def main(argv=None, robot='maze2d'):
         from pmp_b200 import ingest
         pd = ingest.load_problems(args.problems)
         wd = 2 if robot == 'maze2d' else 3
-        s_, g_, w_, c_ = ingest.problem_arrays(pd, np.arange(n_env), n_prob, wd)
+        if args.family == 'm2d_concave':
+            # (cx, cy, mode) rows from the generator's pickle / layout, squares for the checker (ingest.py)
+            s_, g_, w_, c_ = ingest.concave_problem_arrays(
+                pd, np.arange(n_env), n_prob,
+                centers_modes=ingest.load_concave_43(args.concave43) if args.concave43 else None,
+                layouts=ingest.load_wall_layouts(args.layouts) if args.layouts else None,
+                hext=args.hext if args.hext is not None else 0.25)
+        else:
+            s_, g_, w_, c_ = ingest.problem_arrays(pd, np.arange(n_env), n_prob, wd)
         lo, hi = workloads.limits(args.family)
         norm = DatasetNormalizer({'observations': (lo, hi)})
         policy = Policy(diffusion, norm, use_ddim=bool(args.use_ddim))

@@ -171,7 +171,29 @@ def gen_colchk():
     np.savez_compressed(os.path.join(HERE, "colchk_maze2d.npz"), **out)
 
 
+def gen_concave():
+    """layouts drawn by the reference's own concave generator (sample_one_valid_env with the registration kwargs of
+    randSmaze2d-C43-ng3ks25k-ms55nw21-hExt05-v0, init_maze2d_gym_43.py:21-52) and the (cx, cy, mode) rows its
+    save_center_and_mode returns for them"""
+    refshim.load_maze2d_geometry()
+    from pb_diff_envs.environment.rand_rec_group_43 import RandRectangleGroup_43 as G
+    g = object.__new__(G)
+    g.num_walls = 21; g.rand_iter_limit = 1e5; g.two = 2
+    g.maze_size = np.array([5, 5]); g.half_extents = np.array([0.25, 0.25]); g.gap_betw_wall = 0.15
+    g.rng = np.random.default_rng(333)
+    layouts, modes0 = [], []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(24):
+            pos, _hext, env_modes = g.sample_one_valid_env()
+            layouts.append(pos); modes0.append(env_modes)
+    g.rec_loc_grp_list = np.array(layouts)
+    tokens = g.save_center_and_mode(is_save=False)
+    np.savez_compressed(os.path.join(HERE, "concave_layouts.npz"), layouts=g.rec_loc_grp_list, tokens=tokens,
+                        sampled_modes=np.array(modes0), hext=0.25)
+    print("concave", g.rec_loc_grp_list.shape, tokens.shape, "modes", np.bincount(tokens[..., 2].astype(int).ravel()))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk"]
+    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk", "concave"]
     for w in which:
         globals()["gen_" + w]()

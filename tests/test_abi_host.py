@@ -178,3 +178,79 @@ def test_problem_file_ingest_npz_roundtrip(tmp_path):
     except ImportError:
         with pytest.raises(ImportError):
             ingest.load_problems(str(tmp_path / "x-problems.hdf5"))
+
+
+def test_concave_layout_ingest_matches_reference_fixture(tmp_path):
+    """pmp_b200.ingest concave helpers against tests/golden/concave_layouts.npz (layouts drawn and converted by the
+    reference's own RandRectangleGroup_43, gen_golden.py concave) and against the loop restatement; bit-exact"""
+    from pmp_b200 import ingest
+    from oracle import ingest_ref
+    from util import golden
+    z = golden("concave_layouts.npz")
+    layouts, tokens, hext = z["layouts"], z["tokens"], float(z["hext"])
+    assert np.array_equal(ingest_ref.centers_and_modes(layouts), tokens)
+    got = ingest.concave_tokens_from_boxes(layouts)
+    assert got.dtype == np.float64 and np.array_equal(got, tokens)
+    assert np.array_equal(got[..., 2], z["sampled_modes"] + 1)            # mode = deleted quadrant + 1
+    # (centre, mode) -> squares: the generator's order, equal to the saved layout up to the rounding of its centres
+    boxes = ingest.concave_boxes(tokens[..., :2], tokens[..., 2], hext)
+    assert boxes.shape == layouts.shape and np.abs(boxes - layouts).max() < 1e-12
+    assert np.array_equal(ingest.concave_tokens_from_boxes(boxes)[..., 2], tokens[..., 2])
+    for e in range(3):
+        for o in range(7):
+            sq = ingest_ref.squares_of(tokens[e, o, :2], hext, int(tokens[e, o, 2]) - 1)
+            assert np.array_equal(sq, boxes[e, 3 * o:3 * o + 3])
+    # the two files the generator leaves behind: <name>_eval.npy and <name>_43_eval.pkl
+    npy = str(tmp_path / "grp_eval.npy"); np.save(npy, layouts)
+    assert np.array_equal(ingest.load_wall_layouts(npy), layouts)
+    pkl = str(tmp_path / "grp_43_eval.pkl")
+    with open(pkl, "wb") as f:
+        pickle.dump({"centers_43": tokens[..., :2].copy(), "mode_list": tokens[..., 2].astype(np.int64)}, f)
+    cen, modes = ingest.load_concave_43(pkl)
+    assert np.array_equal(cen, tokens[..., :2]) and np.array_equal(modes, tokens[..., 2].astype(np.int64))
+    wl = ingest.concave_wall_locations(cen, modes, n_probs=5)
+    assert wl.shape == (24, 5, 7, 3) and np.array_equal(wl, ingest_ref.val_wall_locations(cen, modes.astype(np.float64), 5))
+    d = {"problems": np.zeros((24, 5, 2, 2), np.float32), "infos/wall_locations": wl}
+    _, _, w, c = ingest.problem_arrays(d, [2, 7], prob_permaze=3, wall_dim=3)
+    assert w.shape == (2, 3, 21) and np.array_equal(w[1, 0], tokens[7].astype(np.float32).ravel())
+    assert c.shape == (2, 7, 3) and np.array_equal(c[0], tokens[2])
+    # malformed input fails loudly
+    bad = layouts.copy(); bad[0, 0, 1] += 0.01; bad[0, 0, 0] += 0.01
+    with pytest.raises(ValueError):
+        ingest.concave_tokens_from_boxes(bad)
+    with pytest.raises(ValueError):
+        ingest.concave_boxes(tokens[..., :2], np.zeros((24, 7)), hext)
+    evil = str(tmp_path / "evil.pkl")
+    with open(evil, "wb") as f:
+        pickle.dump({"centers_43": os.path.join}, f)
+    with pytest.raises(pickle.UnpicklingError):
+        ingest.load_concave_43(evil)
+
+
+def test_concave_problem_arrays_sources_agree():
+    """the three places a concave layout can come from (problem file squares, the .npy, the _43 pickle) give the same
+    model input and checker squares (plan_pb_diff_helper.py:128-134)"""
+    from pmp_b200 import ingest
+    from util import golden
+    z = golden("concave_layouts.npz")
+    layouts, tokens = z["layouts"], z["tokens"]
+    n_env, n_p = len(layouts), 4
+    rng = np.random.default_rng(1)
+    probs = rng.uniform(0, 5, (n_env, n_p, 2, 2)).astype(np.float32)
+    raw = {"problems": probs, "infos/wall_locations": np.repeat(layouts[:, None], n_p, 1)}
+    tok = {"problems": probs, "infos/wall_locations": np.repeat(tokens[:, None], n_p, 1)}
+    flat = {"problems": probs, "infos/wall_locations": np.zeros((n_env, n_p, 21), np.float32)}
+    idx = [5, 0, 11]
+    ref = ingest.concave_problem_arrays(raw, idx, 3, prob_start_idx=1)
+    assert ref[0].shape == (3, 3, 2) and ref[2].shape == (3, 3, 21) and ref[3].shape == (3, 21, 2)
+    assert np.array_equal(ref[0], probs[idx][:, 1:4, 0]) and np.array_equal(ref[1], probs[idx][:, 1:4, 1])
+    assert np.array_equal(ref[2][0, 2], tokens[5].astype(np.float32).ravel()) and np.array_equal(ref[3], layouts[idx])
+    cm = (tokens[..., :2], tokens[..., 2].astype(np.int64))
+    for d, kw in ((flat, dict(layouts=layouts)), (flat, dict(centers_modes=cm, layouts=layouts)), (raw, dict(centers_modes=cm))):
+        got = ingest.concave_problem_arrays(d, idx, 3, prob_start_idx=1, **kw)
+        assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+    for d, kw in ((tok, {}), (flat, dict(centers_modes=cm))):          # no squares on file: centre +- hext
+        got = ingest.concave_problem_arrays(d, idx, 3, prob_start_idx=1, hext=0.25, **kw)
+        assert all(np.array_equal(a, b) for a, b in zip(got[:3], ref[:3])) and np.abs(got[3] - ref[3]).max() < 1e-12
+    with pytest.raises(ValueError):
+        ingest.concave_problem_arrays(flat, idx, 3)

@@ -312,6 +312,35 @@ def test_plan_rm2d_from_problem_file():
     assert res["num_samples"] == 120 and 0.0 <= res["traj_srate"] <= 1.0 and res["total_num_colck"] > 0
 
 
+def test_plan_rm2d_concave_problem_file(tmp_path):
+    """scripts/plan_rm2d.py --family m2d_concave --problems <npz>: the problem file holds the 21 small squares per
+    maze; the (cx, cy, mode) model input is recomputed from them, with and without the generator's .npy / pickle"""
+    import subprocess, sys, json as _json, pickle as _pickle
+    from pmp_b200 import ingest
+    z = golden("concave_layouts.npz")
+    layouts, tokens = z["layouts"][:4], z["tokens"][:4]
+    n_env, n_p = 4, 5
+    rng = np.random.default_rng(2)
+    probs = np.stack([np.stack([np.stack(synth.maze2d_start_goal(rng, layouts[e], 0.25)) for _ in range(n_p)])
+                      for e in range(n_env)])
+    prob = str(tmp_path / "c43-problems.npz")
+    ingest.save_problems_npz({"problems": probs, "infos/wall_locations": np.repeat(layouts[:, None], n_p, 1)}, prob)
+    npy = str(tmp_path / "c43_eval.npy"); np.save(npy, layouts)
+    pkl = str(tmp_path / "c43_43_eval.pkl")
+    with open(pkl, "wb") as f:
+        _pickle.dump({"centers_43": tokens[..., :2].copy(), "mode_list": tokens[..., 2].astype(np.int64)}, f)
+    script = os.path.join(ROOT, "potential-motion-plan-release_b200", "scripts", "plan_rm2d.py")
+    out = []
+    for extra in ([], ["--layouts", npy, "--concave43", pkl]):
+        r = subprocess.run([sys.executable, script, "--family", "m2d_concave", "--plan_n_maze", "4", "--n_prob_env", "5",
+                            "--problems", prob] + extra, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out.append(_json.loads(r.stdout.strip().splitlines()[-1]))
+    assert out[0]["num_samples"] == 20 and out[0]["total_num_colck"] > 0
+    for k in ("traj_srate", "traj_norepl_srate", "total_num_colck"):     # same inputs -> same plans (seeded sampler)
+        assert out[0][k] == out[1][k]
+
+
 def test_plan_envs_multi_horizon_composed():
     """composed planner over several horizons end to end (comp_plan_env.py:54-265): K=2 potentials, 3 horizons,
     GPU collision checks + interleaved selection; the chosen path must be the candidate the oracle's scan picks"""
