@@ -45,12 +45,14 @@ def load_models():
         for n in ("colorama", "matplotlib", "matplotlib.pyplot"):
             sys.modules.setdefault(n, MagicMock())
         import diffuser  # noqa: empty __init__
+        import torch
 
         u = types.ModuleType("diffuser.utils")
         u.__path__ = [os.path.join(REF_ROOT, "diffuser", "utils")]
         u.print_color = lambda s, *a, **k: None
         u.Progress = u.Silent = _Silent
-        u.to_np = lambda x: x.detach().cpu().numpy()
+        u.to_np = lambda x: x.detach().cpu().numpy() if torch.is_tensor(x) else x      # utils/arrays.py:13-16
+        u.to_torch = lambda x, dtype=None, device=None: torch.as_tensor(x, dtype=dtype or torch.float32, device=device or "cpu")
         sys.modules["diffuser.utils"] = u
         diffuser.utils = u
         import contextlib, io
@@ -89,6 +91,33 @@ def load_maze2d_geometry():
     from pb_diff_envs.environment.abs_maze2d_env import AbsStaticMaze2DEnv
     _loaded["geom"] = (Point2DRobot, RectangleWall, RectangleWallGroup, AbsStaticMaze2DEnv)
     return _loaded["geom"]
+
+
+def load_replanner():
+    """Returns (KukaDiffusionReplanner, RM2DCollisionChecker, LimitsNormalizer) of the reference (kuka_replan.py,
+    rm2d_colchk.py, datasets/normalization.py); third-party modules they import but never touch on the Maze2D path
+    (imageio ...) are mocked"""
+    if "replan" in _loaded:
+        return _loaded["replan"]
+    load_models(); load_maze2d_geometry()
+    import importlib
+    with quiet():
+        sys.path.insert(0, REF_ROOT)
+        try:
+            for _ in range(20):
+                try:
+                    rp = importlib.import_module("diffuser.guides.kuka_replan")
+                    cc = importlib.import_module("diffuser.guides.rm2d_colchk")
+                    nm = importlib.import_module("diffuser.datasets.normalization")
+                    break
+                except ModuleNotFoundError as e:
+                    if e.name.startswith(("diffuser", "pb_diff_envs")):
+                        raise
+                    sys.modules[e.name] = MagicMock()
+        finally:
+            sys.path.remove(REF_ROOT)
+    _loaded["replan"] = (rp.KukaDiffusionReplanner, cc.RM2DCollisionChecker, nm.LimitsNormalizer)
+    return _loaded["replan"]
 
 
 class quiet:

@@ -11,9 +11,11 @@ The diffusion call (model.ddim_replan, kuka_replan.py:147-163) is injected as `r
 (un-normalised), so the deterministic part -- section finding, acceptance, check counts -- is compared bit for bit
 with the batched GPU replanner on identical re-sampled trajectories.
 
-Parity: the replanner has no test or fixture in the reference and needs its gym/pybullet environments to run, so
-this restatement is **unpinned** against the live reference (the Maze2D collision primitives it calls are pinned,
-tests/golden/colchk_maze2d.npz)."""
+Parity: **pinned** for Maze2D -- tests/golden/replan_maze2d.npz holds what the reference's own
+KukaDiffusionReplanner + RM2DCollisionChecker + Point2DRobot (imported through oracle/refshim.load_replanner, the
+diffusion call replaced by preset re-sampled trajectories) returned for 64 problems: new paths, success flags and
+check counts agree bit for bit (tests/test_oracle_golden.py::test_replan_oracle_matches_golden).  The Kuka variant
+differs only in the collision model, which is unpinned (pybullet, see oracle/__init__.py)."""
 import numpy as np
 
 from . import colchk_ref

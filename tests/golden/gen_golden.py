@@ -193,7 +193,64 @@ def gen_concave():
     print("concave", g.rec_loc_grp_list.shape, tokens.shape, "modes", np.bincount(tokens[..., 2].astype(int).ravel()))
 
 
+def gen_replan():
+    """the reference's own KukaDiffusionReplanner.replan_collision_section_less_check (kuka_replan.py:33-143) with its
+    RM2DCollisionChecker and Maze2D robot, on noisy straight lines; the diffusion call is replaced by preset
+    re-sampled trajectories (NEW[trial]) so that section finding, acceptance and check counting are what is frozen"""
+    P, RW, RWG, Env = refshim.load_maze2d_geometry()
+    Replanner, Checker, Limits = refshim.load_replanner()
+    B, H, n_trial, hext, eps = 64, 48, 3, 0.5, 0.08
+    pr = synth.make_problems("m2d", B, 41)
+    rng = np.random.default_rng(8)
+    al4 = np.linspace(0, 1, H)[None, None, :, None].astype(np.float32)
+    s = pr["start"][:, None, None, :]; g = pr["goal"][:, None, None, :]
+    trajs = (s * (1 - al4) + g * al4 + rng.normal(0, 0.05, size=(B, 1, H, 2)) * np.sin(np.pi * al4)).astype(np.float32)
+    trajs = np.clip(trajs[:, 0], 0.02, 4.98).astype(np.float32)
+    al = np.linspace(0, 1, H)[None, :, None]
+    NEW = []
+    for t in range(n_trial):
+        amp = rng.normal(0, 0.5, (B, 1, 2)); ph = rng.integers(1, 4, (B, 1, 1))
+        NEW.append(np.clip(trajs + amp * np.sin(np.pi * ph * al) ** 2, 0.02, 4.98).astype(np.float32))
+    NEW = np.stack(NEW)
+
+    class Norm:                                   # DatasetNormalizer interface over the reference's LimitsNormalizer
+        observation_dim = 2
+        lim = Limits(np.array([[0, 0], [5, 5]], np.float32))
+        def normalize(self, x, key): return self.lim.normalize(x)
+        def unnormalize(self, x, key): return self.lim.unnormalize(x)
+    norm = Norm()
+
+    class Model:
+        def ddim_replan(self, normed, cond, walls_loc, dn_steps):
+            b = int(walls_loc[0, 0].item())
+            out = torch.as_tensor(norm.normalize(NEW[self.trial, b], "observations"), dtype=torch.float32)
+            self.trial += 1
+            return out
+
+    new = trajs.copy(); suc = np.ones(B, np.uint8); cnt = np.full(B, H, np.int32); had = np.zeros(B, np.uint8)
+    for b in range(B):
+        walls = [RW(np.array(c), np.array([hext, hext])) for c in pr["boxes"][b]]
+        rob = P(np.array([5., 5.]), RWG(walls), 0.01, collision_eps=eps)
+        env = object.__new__(Env); env.robot = rob
+        with contextlib.redirect_stdout(io.StringIO()):
+            col = [not (rob.set_config(q) or rob.no_collision()) for q in trajs[b]]
+        if not any(col):
+            continue                               # the reference asserts it is never given a collision-free path
+        had[b] = 1
+        m = Model(); m.trial = 0
+        rp = Replanner(m, norm, dict(use_ddim=True, dn_steps=3, n_replan_trial=n_trial), torch.device("cpu"))
+        ck = Checker(norm); ck.use_collision_eps = True; ck.collision_eps = eps
+        rp.set_collision_checker(ck)
+        with refshim.quiet():
+            r_new, r_suc, r_cnt = rp.replan_collision_section_less_check(env, trajs[b].copy(), torch.full((1, 12), float(b)))
+        new[b] = r_new; suc[b] = bool(r_suc); cnt[b] = r_cnt
+    np.savez_compressed(os.path.join(HERE, "replan_maze2d.npz"), trajs=trajs, resampled=NEW, boxes=pr["boxes"], hext=hext,
+                        eps=eps, new=new, success=suc, num_colck=cnt, had_collision=had, numpy_version=np.__version__,
+                        legacy_div=0)
+    print("replan: %d with collisions, %d repaired, mean checks %.1f" % (had.sum(), (suc & had).sum(), cnt[had > 0].mean()))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk", "concave"]
+    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk", "concave", "replan"]
     for w in which:
         globals()["gen_" + w]()

@@ -469,6 +469,37 @@ def test_batched_replanner_vs_oracle():
     assert n_fix >= 3 and n_fail >= 3, (n_fix, n_fail)
 
 
+def test_batched_replanner_matches_reference_golden():
+    """replan_batch against what the reference's own replanner returned for the same inputs
+    (tests/golden/replan_maze2d.npz, gen_golden.py replan): paths, success flags, check counts, bit for bit"""
+    from diffuser.guides.kuka_replan import KukaDiffusionReplanner
+    from diffuser.guides import RM2DCollisionChecker
+    from diffuser.datasets import DatasetNormalizer, RAND_MAZE_MIN, RAND_MAZESIZE_55
+    norm = DatasetNormalizer({"observations": (RAND_MAZE_MIN, RAND_MAZESIZE_55)})
+    z = golden("replan_maze2d.npz")
+    trajs, NEW = z["trajs"], z["resampled"]
+    B = len(trajs)
+
+    class MockModel:
+        trial = 0
+        def ddim_replan(self, normed, cond, walls_loc, dn_steps):
+            ids = walls_loc[:, 0].long().cpu().numpy()
+            out = torch.as_tensor(norm.normalize(NEW[self.trial][ids], "observations"), dtype=torch.float32, device=normed.device)
+            self.trial += 1
+            return out
+
+    rp = KukaDiffusionReplanner(MockModel(), norm, dict(use_ddim=True, dn_steps=3, n_replan_trial=len(NEW)), DEV)
+    chk = RM2DCollisionChecker(normalizer=None, device=DEV, legacy_div=bool(z["legacy_div"]))     # numpy >= 2 counts
+    chk.use_collision_eps = True; chk.collision_eps = float(z["eps"])
+    rp.set_collision_checker(chk)
+    walls = torch.arange(B, dtype=torch.float32)[:, None].repeat(1, 12)
+    geom = dict(robot="maze2d", env_id=np.arange(B, dtype=np.int32), cen=z["boxes"], hext=float(z["hext"]))
+    new, suc, cnt = rp.replan_batch(trajs, walls, geom)
+    assert np.array_equal(np.asarray(new), z["new"])
+    assert np.array_equal(np.asarray(suc).astype(bool), z["success"].astype(bool))
+    assert np.array_equal(np.asarray(cnt).astype(np.int64), z["num_colck"].astype(np.int64))
+
+
 def test_replanner_single_trajectory_with_diffusion():
     """reference signature (one trajectory, env object) through the real batched ddim_replan"""
     from diffuser.guides.kuka_replan import KukaDiffusionReplanner

@@ -202,6 +202,26 @@ def test_replan_oracle_sections_and_acceptance():
     assert not ok2 and np.array_equal(new2, line) and cnt2 > H
 
 
+def test_replan_oracle_matches_golden():
+    """oracle/replan_ref.py against tests/golden/replan_maze2d.npz: outputs of the reference's own
+    KukaDiffusionReplanner + RM2DCollisionChecker + Maze2D robot on preset re-sampled trajectories
+    (gen_golden.py replan); new paths, success flags and collision-check counts, bit for bit"""
+    from oracle import replan_ref
+    z = golden("replan_maze2d.npz")
+    tr, NEW, boxes = z["trajs"], z["resampled"], z["boxes"]
+    lo = np.zeros(2, np.float32); hi = np.full(2, 5, np.float32)
+
+    def roundtrip(a):       # LimitsNormalizer.normalize -> float32 tensor -> unnormalize (normalization.py:142-162)
+        n = ((a - lo) / (hi - lo) * 2 - 1).astype(np.float32)
+        return ((n + 1) / 2. * (hi - lo) + lo).astype(np.float32)
+    assert z["had_collision"].sum() > 40 and 0 < (z["success"] & z["had_collision"]).sum() < z["had_collision"].sum()
+    for b in range(len(tr)):
+        ck = replan_ref.Maze2DChecker(boxes[b], float(z["hext"]), eps=float(z["eps"]), legacy_div=bool(z["legacy_div"]))
+        new, ok, cnt = replan_ref.replan_collision_section(tr[b], ck, lambda t, x: roundtrip(NEW[t][b]), len(NEW))
+        assert np.array_equal(new, z["new"][b]), "problem %d: path differs" % b
+        assert bool(ok) == bool(z["success"][b]) and cnt == int(z["num_colck"][b]), (b, ok, cnt)
+
+
 # ------------------------------------------------------------------ live reference (build container only)
 needs_ref = pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
 
