@@ -12,9 +12,8 @@ container through `oracle/refshim.py` and frozen as fixtures under
 `tests/golden/` by `tests/golden/gen_golden.py`.  The Kuka collision model is
 the exception: the reference delegates it to pybullet 3.2.5 (not vendored, not
 installable here), so the sphere-link model in `oracle/colchk_ref.py` is
-self-defined -> "parity unpinned" for that one function; so is
-`colchk_ref.pick_multi_horizon` (planner code that only runs inside the gym
-environments).  Pinned beyond the sampler: Maze2D collision checks
-(colchk_maze2d.npz), the replanner (replan_maze2d.npz), the concave layout
-arithmetic (concave_layouts.npz).
+self-defined -> "parity unpinned" for that one function.  Pinned beyond the
+sampler: Maze2D collision checks (colchk_maze2d.npz), the replanner
+(replan_maze2d.npz), the multi-horizon candidate selection
+(pick_multi_horizon.npz), the concave layout arithmetic (concave_layouts.npz).
 """

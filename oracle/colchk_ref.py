@@ -169,7 +169,7 @@ def pick_multi_horizon(valid_list, nchk_list, n_prob, n_samp):
     when none is, the LAST candidate visited is kept (:247-249).  valid_list[h] / nchk_list[h] hold the
     checker outputs of horizon h for its n_prob*n_samp candidates (problem-major, as the policy batch is laid
     out, :143-146).  Returns (horizon index [n_prob], sample index [n_prob], success [n_prob] bool,
-    num_colck [n_prob])."""
+    num_colck [n_prob]).  Pinned: tests/golden/pick_multi_horizon.npz holds what the reference method itself chose."""
     nh = len(valid_list)
     v = [np.asarray(a).reshape(n_prob, n_samp).astype(bool) for a in valid_list]
     c = [np.asarray(a).reshape(n_prob, n_samp) for a in nchk_list]

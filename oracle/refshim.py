@@ -50,7 +50,7 @@ def load_models():
         u = types.ModuleType("diffuser.utils")
         u.__path__ = [os.path.join(REF_ROOT, "diffuser", "utils")]
         u.print_color = lambda s, *a, **k: None
-        u.Progress = u.Silent = _Silent
+        u.Progress = u.Silent = u.Config = _Silent
         u.to_np = lambda x: x.detach().cpu().numpy() if torch.is_tensor(x) else x      # utils/arrays.py:13-16
         u.to_torch = lambda x, dtype=None, device=None: torch.as_tensor(x, dtype=dtype or torch.float32, device=device or "cpu")
         sys.modules["diffuser.utils"] = u
@@ -93,31 +93,41 @@ def load_maze2d_geometry():
     return _loaded["geom"]
 
 
-def load_replanner():
-    """Returns (KukaDiffusionReplanner, RM2DCollisionChecker, LimitsNormalizer) of the reference (kuka_replan.py,
-    rm2d_colchk.py, datasets/normalization.py); third-party modules they import but never touch on the Maze2D path
-    (imageio ...) are mocked"""
-    if "replan" in _loaded:
-        return _loaded["replan"]
+def _import_ref(*names):
+    """imports reference modules by name; third-party modules they import but the Maze2D path never touches
+    (imageio ...) are mocked as they come up"""
     load_models(); load_maze2d_geometry()
     import importlib
     with quiet():
         sys.path.insert(0, REF_ROOT)
         try:
-            for _ in range(20):
+            for _ in range(30):
                 try:
-                    rp = importlib.import_module("diffuser.guides.kuka_replan")
-                    cc = importlib.import_module("diffuser.guides.rm2d_colchk")
-                    nm = importlib.import_module("diffuser.datasets.normalization")
-                    break
+                    return [importlib.import_module(n) for n in names]
                 except ModuleNotFoundError as e:
                     if e.name.startswith(("diffuser", "pb_diff_envs")):
                         raise
                     sys.modules[e.name] = MagicMock()
         finally:
             sys.path.remove(REF_ROOT)
-    _loaded["replan"] = (rp.KukaDiffusionReplanner, cc.RM2DCollisionChecker, nm.LimitsNormalizer)
+    raise RuntimeError("could not import %s" % (names,))
+
+
+def load_replanner():
+    """Returns (KukaDiffusionReplanner, RM2DCollisionChecker, LimitsNormalizer) of the reference (kuka_replan.py,
+    rm2d_colchk.py, datasets/normalization.py)"""
+    if "replan" not in _loaded:
+        rp, cc, nm = _import_ref("diffuser.guides.kuka_replan", "diffuser.guides.rm2d_colchk",
+                                 "diffuser.datasets.normalization")
+        _loaded["replan"] = (rp.KukaDiffusionReplanner, cc.RM2DCollisionChecker, nm.LimitsNormalizer)
     return _loaded["replan"]
+
+
+def load_composed_planner():
+    """Returns ComposedEnvPlanner of the reference (comp_plan_env.py)"""
+    if "comp_planner" not in _loaded:
+        _loaded["comp_planner"] = _import_ref("diffuser.guides.comp_plan_env")[0].ComposedEnvPlanner
+    return _loaded["comp_planner"]
 
 
 class quiet:

@@ -250,7 +250,55 @@ def gen_replan():
     print("replan: %d with collisions, %d repaired, mean checks %.1f" % (had.sum(), (suc & had).sum(), cnt[had > 0].mean()))
 
 
+def gen_pick():
+    """the reference's own ComposedEnvPlanner.option_1_pick_1_traj (comp_plan_env.py:126-265) -- candidate scan over
+    several planning horizons with its RM2DCollisionChecker -- on noisy straight-line candidates, one maze at a time"""
+    P, RW, RWG, Env = refshim.load_maze2d_geometry()
+    Planner = refshim.load_composed_planner()
+    E, n_p, n_s, horizons, hext = 6, 8, 4, (40, 48, 56), 0.5
+    pr = synth.make_problems("m2d", E, 77)
+    rng = np.random.default_rng(12)
+    out = dict(boxes=pr["boxes"], hext=hext, horizons=np.array(horizons), n_prob=n_p, n_samp=n_s, eps=0.08,
+               legacy_div=0, numpy_version=np.__version__)
+    chosen_h = np.zeros((E, n_p), np.int64); suc = np.zeros((E, n_p), np.uint8); cnt = np.zeros((E, n_p), np.int64)
+    paths = np.zeros((E, n_p, max(horizons), 2), np.float32)
+    cands = [np.zeros((E, n_p * n_s, h, 2), np.float32) for h in horizons]
+
+    class Obj:
+        pass
+    for e in range(E):
+        walls = [RW(np.array(c), np.array([hext, hext])) for c in pr["boxes"][e]]
+        rob = P(np.array([5., 5.]), RWG(walls), 0.01, collision_eps=0.08)
+        env = object.__new__(Env); env.robot = rob
+        st = rng.uniform(0.2, 4.8, (n_p, 1, 1, 2)); gl = rng.uniform(0.2, 4.8, (n_p, 1, 1, 2))
+        near = np.clip(st + rng.uniform(-1.0, 1.0, st.shape), 0.2, 4.8)      # short hops: more collision-free candidates
+        gl = np.where(np.arange(n_p)[:, None, None, None] % 2 == 0, near, gl)
+        samples = []
+        for i_h, h in enumerate(horizons):
+            al = np.linspace(0, 1, h)[None, None, :, None]
+            sig = rng.choice([0.01, 0.05, 0.3], size=(n_p, n_s, 1, 1))
+            tj = st * (1 - al) + gl * al + rng.normal(0, 1, (n_p, n_s, h, 2)) * sig * np.sin(np.pi * al)
+            tj = np.clip(tj, 0.02, 4.98).astype(np.float32).reshape(n_p * n_s, h, 2)
+            cands[i_h][e] = tj
+            o = Obj(); o.observations = tj
+            samples.append(o)
+        pl = object.__new__(Planner)
+        pl.horizon_pl_list = list(horizons); pl.samples_perprob = n_s; pl.is_dyn_env = False; pl.is_kuka = False
+        pl.horizon_wtrajs = max(horizons)
+        pl.replanner = Obj(); pl.replanner.set_collision_checker = lambda c: None
+        with refshim.quiet():
+            d = pl.option_1_pick_1_traj(samples, env, n_p)
+        for p_ in range(n_p):
+            tj = d["modelout_path_list"][p_]
+            chosen_h[e, p_] = horizons.index(len(tj)); paths[e, p_, :len(tj)] = tj
+            suc[e, p_] = bool(d["suc_list"][p_]); cnt[e, p_] = d["num_colck_list"][p_]
+    out.update(chosen_h=chosen_h, success=suc, num_colck=cnt, paths=paths)
+    out.update({"cand_h%d" % h: c for h, c in zip(horizons, cands)})
+    np.savez_compressed(os.path.join(HERE, "pick_multi_horizon.npz"), **out)
+    print("pick: success %.2f, horizon hist %s, mean checks %.1f" % (suc.mean(), np.bincount(chosen_h.ravel(), minlength=3), cnt.mean()))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk", "concave", "replan"]
+    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk", "concave", "replan", "pick"]
     for w in which:
         globals()["gen_" + w]()

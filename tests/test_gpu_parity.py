@@ -423,6 +423,29 @@ def test_pick_multi_horizon_vs_oracle():
         assert np.array_equal(su.cpu().numpy().astype(bool), su_ref) and np.array_equal(tot.cpu().numpy(), tot_ref)
 
 
+def test_pick_multi_horizon_matches_reference_golden():
+    """GPU collision checks + selection against what the reference's own ComposedEnvPlanner.option_1_pick_1_traj chose
+    for the same candidates (tests/golden/pick_multi_horizon.npz): all mazes in one batch"""
+    from diffuser.guides.plan_env_b200 import pick_multi_horizon
+    z = golden("pick_multi_horizon.npz")
+    hz = [int(h) for h in z["horizons"]]; n_p = int(z["n_prob"]); n_s = int(z["n_samp"])
+    E = len(z["boxes"])
+    env = np.repeat(np.arange(E, dtype=np.int32), n_p * n_s)
+    V, C = [], []
+    for h in hz:
+        tj = torch.tensor(z["cand_h%d" % h].reshape(E * n_p * n_s, h, 2), device=DEV)
+        v, c = pmp_b200.colchk_maze2d_swept(tj, env, z["boxes"], float(z["hext"]), eps=float(z["eps"]),
+                                            legacy_div=bool(z["legacy_div"]))
+        V.append(v); C.append(c)
+    hs, ss, su, tot = pick_multi_horizon(V, C, E * n_p, n_s)
+    hs = hs.cpu().numpy(); ss = ss.cpu().numpy()
+    assert np.array_equal(hs, z["chosen_h"].ravel()) and np.array_equal(su.cpu().numpy().astype(bool), z["success"].ravel().astype(bool))
+    assert np.array_equal(tot.cpu().numpy().astype(np.int64), z["num_colck"].ravel())
+    for q in range(E * n_p):
+        path = z["cand_h%d" % hz[hs[q]]].reshape(E * n_p, n_s, hz[hs[q]], 2)[q, ss[q]]
+        assert np.array_equal(path, z["paths"].reshape(E * n_p, -1, 2)[q, :len(path)])
+
+
 def test_batched_replanner_vs_oracle():
     """KukaDiffusionReplanner.replan_batch (all problems together, GPU checks) == the sequential restatement of
     kuka_replan.py:33-143 on identical re-sampled trajectories: new paths, success flags and check counts"""

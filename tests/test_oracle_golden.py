@@ -173,6 +173,27 @@ def test_pick_multi_horizon_order():
     assert (h1 == 0).all() and np.array_equal(s1, ch) and np.array_equal(su1, su) and np.array_equal(t1, tt)
 
 
+def test_pick_multi_horizon_matches_golden():
+    """colchk_ref.maze2d_swept + pick_multi_horizon against tests/golden/pick_multi_horizon.npz: what the reference's
+    own ComposedEnvPlanner.option_1_pick_1_traj chose (gen_golden.py pick) -- horizon, path, success, check count"""
+    z = golden("pick_multi_horizon.npz")
+    hz = [int(h) for h in z["horizons"]]; n_p = int(z["n_prob"]); n_s = int(z["n_samp"])
+    assert 0.15 < z["success"].mean() < 0.85 and len(np.unique(z["chosen_h"])) == len(hz)
+    for e in range(len(z["boxes"])):
+        V, C = [], []
+        for h in hz:
+            tj = z["cand_h%d" % h][e]
+            v, c = colchk_ref.maze2d_swept(tj, np.zeros(len(tj), np.int32), z["boxes"][e][None], float(z["hext"]),
+                                           eps=float(z["eps"]), legacy_div=bool(z["legacy_div"]))
+            V.append(v); C.append(c)
+        hs, ss, su, tot = colchk_ref.pick_multi_horizon(V, C, n_p, n_s)
+        assert np.array_equal(hs, z["chosen_h"][e]) and np.array_equal(su, z["success"][e].astype(bool))
+        assert np.array_equal(tot, z["num_colck"][e])
+        for p in range(n_p):
+            path = z["cand_h%d" % hz[hs[p]]][e][p * n_s + ss[p]]
+            assert np.array_equal(path, z["paths"][e, p, :len(path)])
+
+
 def test_replan_oracle_sections_and_acceptance():
     """oracle/replan_ref.py on a hand case: a straight line through one wall, re-sampled as a detour"""
     from oracle import replan_ref
