@@ -17,6 +17,45 @@ import pmp_b200
 from .kuka_colchk import KukaCollisionChecker, arm_bases, TABLE_Z
 
 
+def compute_avg_result(ncol, norepl_suc, num_colck, n_env, n_prob, batch_runtime, repl_suc=None):
+    """global statistics of a planning run, with the reference's keys and its arithmetic in its order: per
+    environment the rates of check_collision (kuka_plan_utils.py:136-146: traj_srate = no_collision_rate =
+    #(collision count == 0) / n, se_valid_rate = 1), then the sample-weighted sums and ratios of
+    compute_kuka_avg_result (:175-213).  ncol [n_env*n_prob] per-waypoint collision counts of the chosen paths,
+    norepl_suc / repl_suc [n_env*n_prob] success flags of the candidate scan / of replanning, num_colck
+    [n_env*n_prob] collision checks spent; host arrays (a few bytes per problem).  batch_runtime is the time of the
+    one batch that planned all environments (the reference sums one batch per environment)."""
+    ncol = np.asarray(ncol).reshape(n_env, n_prob)
+    norepl = np.asarray(norepl_suc).astype(bool).reshape(n_env, n_prob)
+    repl = np.zeros((n_env, 0), bool) if repl_suc is None else np.asarray(repl_suc).astype(bool).reshape(n_env, -1)
+    colck = np.asarray(num_colck).astype(np.int64).reshape(n_env, n_prob)
+    total_num = 0
+    w_srate = w_svr = w_ncr = 0
+    n_norepl = n_repl = n_colck = 0
+    for e in range(n_env):
+        ok = ncol[e] == 0
+        srate = ok.sum() / n_prob
+        ncr = ok.sum() / n_prob
+        svr = np.ones(n_prob, bool).sum() / n_prob
+        total_num += n_prob
+        w_srate += srate * n_prob
+        w_ncr += ncr * n_prob
+        w_svr += svr * n_prob
+        n_norepl += norepl[e].sum()
+        n_repl += repl[e].sum()
+        n_colck += colck[e].sum().item()
+    return dict(num_samples=total_num,
+                traj_srate=float(w_srate / total_num),
+                traj_norepl_srate=float(n_norepl / total_num),
+                traj_repl_srate=float(n_repl / total_num),
+                total_ncr=float(w_ncr / total_num),
+                total_svr=float(w_svr / total_num),
+                avg_batch_time=batch_runtime / n_env,
+                avg_sample_time=batch_runtime / total_num,
+                total_num_colck=int(n_colck),
+                avg_num_colck=n_colck / total_num)
+
+
 def plan_envs(policy, starts, goals, walls, env_boxes, hext, horizon, samples_perprob=10, robot='maze2d',
               n_arms=1, collision_eps=0.08, legacy_div=True):
     """starts/goals [n_env, n_prob, D] (un-normalised numpy), walls [n_env, n_prob, wall_len] model input,
@@ -49,17 +88,7 @@ def plan_envs(policy, starts, goals, walls, env_boxes, hext, horizon, samples_pe
         ncol, _ = pmp_b200.colchk_maze2d_points(paths, env_p, env_boxes, hext)
     else:
         ncol = pmp_b200.colchk_kuka(paths, env_p, env_boxes, hext, n_arms, arm_bases(n_arms), chk.sph, TABLE_Z)['ncol']
-    success = (ncol == 0)
-    res = dict(num_samples=n_p,
-               traj_srate=float(success.float().mean().item()),
-               traj_norepl_srate=float(suc.float().mean().item()),
-               traj_repl_srate=0.0,
-               total_ncr=float(success.float().mean().item()),
-               total_svr=1.0,
-               avg_batch_time=batch_runtime / n_env,
-               avg_sample_time=batch_runtime / n_p,
-               total_num_colck=int(total.sum().item()),
-               avg_num_colck=float(total.float().mean().item()))
+    res = compute_avg_result(ncol.cpu().numpy(), suc.cpu().numpy(), total.cpu().numpy(), n_env, n_prob, batch_runtime)
     return res, paths.cpu().numpy()
 
 
@@ -127,16 +156,6 @@ def plan_envs_multi_horizon(policy, starts, goals, walls, env_boxes, hext, horiz
         else:
             nc = pmp_b200.colchk_kuka(pt, env_p[sel], env_boxes, hext, n_arms, arm_bases(n_arms), chk.sph, TABLE_Z)['ncol']
         ncol[sel] = nc.cpu().numpy()
-    success = ncol == 0
-    res = dict(num_samples=n_p,
-               traj_srate=float(success.mean()),
-               traj_norepl_srate=float(suc.float().mean().item()),
-               traj_repl_srate=0.0,
-               total_ncr=float(success.mean()),
-               total_svr=1.0,
-               avg_batch_time=batch_runtime / n_env,
-               avg_sample_time=batch_runtime / n_p,
-               total_num_colck=int(total.sum().item()),
-               avg_num_colck=float(total.float().mean().item()),
-               horizon_hist=[int((hs == i).sum()) for i in range(len(horizons))])
+    res = compute_avg_result(ncol, suc.cpu().numpy(), total.cpu().numpy(), n_env, n_prob, batch_runtime)
+    res['horizon_hist'] = [int((hs == i).sum()) for i in range(len(horizons))]
     return res, paths

@@ -266,6 +266,8 @@ def gen_pick():
 
     class Obj:
         pass
+    PU = refshim._import_ref("diffuser.guides.kuka_plan_utils")[0]
+    per_env = []
     for e in range(E):
         walls = [RW(np.array(c), np.array([hext, hext])) for c in pr["boxes"][e]]
         rob = P(np.array([5., 5.]), RWG(walls), 0.01, collision_eps=0.08)
@@ -288,11 +290,21 @@ def gen_pick():
         pl.replanner = Obj(); pl.replanner.set_collision_checker = lambda c: None
         with refshim.quiet():
             d = pl.option_1_pick_1_traj(samples, env, n_p)
+            # per-maze statistics of the chosen paths (plan_kuka_permaze_stat -> check_collision, kuka_plan_utils.py)
+            other = dict(replan_suc_list=[], no_replan_suc_list=list(d["suc_list"]), batch_runtime=0.125 * (e + 1),
+                         num_colck_list=list(d["num_colck_list"]))
+            per_env.append(PU.plan_kuka_permaze_stat(list(d["modelout_path_list"]), other, env))
         for p_ in range(n_p):
             tj = d["modelout_path_list"][p_]
             chosen_h[e, p_] = horizons.index(len(tj)); paths[e, p_, :len(tj)] = tj
             suc[e, p_] = bool(d["suc_list"][p_]); cnt[e, p_] = d["num_colck_list"][p_]
     out.update(chosen_h=chosen_h, success=suc, num_colck=cnt, paths=paths)
+    with refshim.quiet():
+        avg = PU.compute_kuka_avg_result(per_env)           # kuka_plan_utils.py:175-213
+    out["collision_cnts"] = np.array([d["collision_cnts"] for d in per_env])
+    out["batch_runtime_total"] = sum(d["batch_runtime"] for d in per_env)
+    out.update({"stat_" + k: np.float64(v) for k, v in avg.items()})
+    print("stats:", {k: float(v) for k, v in avg.items()})
     out.update({"cand_h%d" % h: c for h, c in zip(horizons, cands)})
     np.savez_compressed(os.path.join(HERE, "pick_multi_horizon.npz"), **out)
     print("pick: success %.2f, horizon hist %s, mean checks %.1f" % (suc.mean(), np.bincount(chosen_h.ravel(), minlength=3), cnt.mean()))

@@ -254,3 +254,51 @@ def test_concave_problem_arrays_sources_agree():
         assert all(np.array_equal(a, b) for a, b in zip(got[:3], ref[:3])) and np.abs(got[3] - ref[3]).max() < 1e-12
     with pytest.raises(ValueError):
         ingest.concave_problem_arrays(flat, idx, 3)
+
+
+def _import_plan_env_host():
+    """diffuser.guides.plan_env_b200.compute_avg_result is host arithmetic; importing the module needs no GPU"""
+    from diffuser.guides.plan_env_b200 import compute_avg_result
+    return compute_avg_result
+
+
+def test_result_statistics_match_reference_golden():
+    """compute_avg_result against what the reference's plan_kuka_permaze_stat + compute_kuka_avg_result
+    (kuka_plan_utils.py:110-213) returned for the chosen paths of tests/golden/pick_multi_horizon.npz"""
+    from util import golden
+    f = _import_plan_env_host()
+    z = golden("pick_multi_horizon.npz")
+    E, n_p = z["collision_cnts"].shape
+    res = f(z["collision_cnts"].ravel(), z["success"].ravel(), z["num_colck"].ravel(), E, n_p, float(z["batch_runtime_total"]))
+    keys = [k[5:] for k in z.files if k.startswith("stat_")]
+    assert set(keys) == set(res) and len(keys) == 10
+    for k in keys:
+        assert float(res[k]) == float(z["stat_" + k]), (k, res[k], float(z["stat_" + k]))
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+def test_result_statistics_match_live_reference():
+    """same, on random per-environment outcomes with sizes whose rates are not exact binary fractions"""
+    f = _import_plan_env_host()
+    PU = refshim._import_ref("diffuser.guides.kuka_plan_utils")[0]
+    rng = np.random.default_rng(3)
+    for n_env, n_prob in ((1, 1), (7, 3), (13, 21), (100, 20)):
+        ncol = rng.integers(0, 3, (n_env, n_prob)) * (rng.random((n_env, n_prob)) < 0.6)
+        nor = rng.random((n_env, n_prob)) < 0.7
+        rep = rng.random((n_env, n_prob)) < 0.2
+        colck = rng.integers(1, 5000, (n_env, n_prob))
+        t = rng.uniform(0.1, 2.0, n_env)
+        per_env = []
+        for e in range(n_env):
+            ok = ncol[e] == 0
+            per_env.append(dict(num_samples=n_prob, traj_srate=ok.sum() / n_prob, no_collision_rate=ok.sum() / n_prob,
+                                se_valid_rate=np.array([True] * n_prob).sum() / n_prob, batch_runtime=t[e],
+                                no_replan_suc_list=list(nor[e]), replan_suc_list=list(rep[e]), num_colck_list=list(colck[e])))
+        with refshim.quiet():
+            ref = PU.compute_kuka_avg_result(per_env)
+        got = f(ncol.ravel(), nor.ravel(), colck.ravel(), n_env, n_prob, sum(t.tolist()), repl_suc=rep.ravel())
+        for k in ref:
+            if k in ("avg_batch_time", "avg_sample_time"):      # the reference adds the per-maze times in its own order
+                assert abs(got[k] - ref[k]) <= 1e-12 * abs(ref[k])
+            else:
+                assert float(got[k]) == float(ref[k]), (k, got[k], ref[k])

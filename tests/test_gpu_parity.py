@@ -444,6 +444,18 @@ def test_pick_multi_horizon_matches_reference_golden():
     for q in range(E * n_p):
         path = z["cand_h%d" % hz[hs[q]]].reshape(E * n_p, n_s, hz[hs[q]], 2)[q, ss[q]]
         assert np.array_equal(path, z["paths"].reshape(E * n_p, -1, 2)[q, :len(path)])
+    # final scoring of the chosen paths (check_collision, kuka_plan_utils.py:104-146) and the global statistics
+    from diffuser.guides.plan_env_b200 import compute_avg_result
+    env_p = np.repeat(np.arange(E, dtype=np.int32), n_p)
+    ncol = np.zeros(E * n_p, np.int64)
+    for i, h in enumerate(hz):
+        sel = np.nonzero(hs == i)[0]
+        pt = torch.tensor(z["paths"].reshape(E * n_p, -1, 2)[sel, :h], device=DEV)
+        ncol[sel] = pmp_b200.colchk_maze2d_points(pt, env_p[sel], z["boxes"], float(z["hext"]))[0].cpu().numpy()
+    assert np.array_equal(ncol == 0, z["collision_cnts"].ravel() == 0)      # the reference pads the shorter paths
+    res = compute_avg_result(ncol, su.cpu().numpy(), tot.cpu().numpy(), E, n_p, float(z["batch_runtime_total"]))
+    for k in res:
+        assert float(res[k]) == float(z["stat_" + k]), k
 
 
 def test_batched_replanner_vs_oracle():
