@@ -302,3 +302,36 @@ def test_result_statistics_match_live_reference():
                 assert abs(got[k] - ref[k]) <= 1e-12 * abs(ref[k])
             else:
                 assert float(got[k]) == float(ref[k]), (k, got[k], ref[k])
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+def test_problem_batch_layout_matches_live_reference():
+    """problem file -> the [n_prob * n_samples] batch the sampler sees: ingest.problem_arrays + the problem-major
+    repeat of plan_envs against the reference's rm2d_kuka_preproc (preprocessing.py:36-67), kuka_obs_target_list
+    (kuka_plan_utils.py:36-57), fit_obs_target_tensor and get_wallLoc_tensor_single (kuka_plan_env.py:264-316)"""
+    from pmp_b200 import ingest
+    PU, PP, KP = refshim._import_ref("diffuser.guides.kuka_plan_utils", "diffuser.datasets.preprocessing",
+                                     "diffuser.guides.kuka_plan_env")
+    rng = np.random.default_rng(6)
+    for D, nw, wd_file, wd in ((2, 6, 2, 2), (7, 4, 6, 3), (14, 5, 6, 3)):
+        n_env, n_prob_file, n_prob, n_s = 5, 9, 4, 3
+        raw = {"problems": rng.uniform(-3, 3, (n_env, n_prob_file, 2, D)).astype(np.float32),
+               "infos/wall_locations": rng.uniform(-1, 1, (n_env, n_prob_file, nw, wd_file)).astype(np.float32)}
+        ref_d = {k: v.copy() for k, v in raw.items()}
+
+        class E_:
+            name = "kuka" if D > 2 else "maze2d"
+            is_eval = True
+        with refshim.quiet():
+            PP.rm2d_kuka_preproc(ref_d, wloc_select=tuple(range(wd)), env=E_)       # in place: [n_env, n_p, nw*wd]
+        for maze_idx in (0, 3):
+            pl = object.__new__(KP.KukaEnvPlanner)
+            pl.problems_dict = ref_d; pl.maze_idx = maze_idx
+            with refshim.quiet():
+                o, t = PU.kuka_obs_target_list(ref_d, maze_idx, n_prob)
+                o_t, t_t = pl.fit_obs_target_tensor(o, t, n_s)
+                w_t = pl.get_wallLoc_tensor_single(0, n_prob, n_s)
+            s_, g_, w_, _ = ingest.problem_arrays(raw, [maze_idx], n_prob, wd)
+            rep = lambda a: np.repeat(a.reshape(n_prob, -1), n_s, axis=0)              # plan_envs' batch layout
+            assert np.array_equal(rep(s_), o_t.numpy()) and np.array_equal(rep(g_), t_t.numpy())
+            assert np.array_equal(rep(w_), w_t.numpy())
