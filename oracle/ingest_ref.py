@@ -22,29 +22,23 @@ def squares_of(center, hext, mode0):
     return np.array(cl)
 
 
+# compute_mode_list's decision tree as a table: (first two squares share y, first and third share x) -> mode0
+_MODE0 = {(True, True): 2, (True, False): 3, (False, True): 1, (False, False): 0}
+
+
 def centers_and_modes(layouts):
-    """rand_rec_group_43.py:161-176, 190-211 -> [n_env, nw, 3] rows (cx, cy, mode in 1..4)"""
+    """rand_rec_group_43.py:161-176, 190-211 -> [n_env, nw, 3] rows (cx, cy, mode in 1..4), one obstacle (three
+    consecutive squares a, b, c) at a time with scalar float64 arithmetic"""
     out = []
-    for wlocs in layouts:
+    for squares in layouts:
         rows = []
-        for i in range(0, len(wlocs), 3):
-            x_max = max(wlocs[i][0], wlocs[i + 1][0])
-            x_min = min(wlocs[i][0], wlocs[i + 2][0])
-            x = (x_min + x_max) / 2
-            y = (wlocs[i][1] + wlocs[i + 2][1]) / 2
-            if wlocs[i][1] == wlocs[i + 1][1]:
-                if wlocs[i][0] == wlocs[i + 2][0]:
-                    mode = 2
-                else:
-                    assert wlocs[i + 1][0] == wlocs[i + 2][0]
-                    mode = 3
-            else:
-                if wlocs[i][0] == wlocs[i + 2][0]:
-                    mode = 1
-                else:
-                    assert wlocs[i][0] == wlocs[i + 1][0]
-                    mode = 0
-            rows.append([x, y, mode + 1])
+        for a, b, c in zip(squares[0::3], squares[1::3], squares[2::3]):
+            cx = (min(a[0], c[0]) + max(a[0], b[0])) / 2
+            cy = (a[1] + c[1]) / 2
+            same_y, same_x = bool(a[1] == b[1]), bool(a[0] == c[0])
+            if not same_x:          # the reference asserts the remaining coincidence
+                assert (b[0] == c[0]) if same_y else (a[0] == b[0])
+            rows.append([cx, cy, _MODE0[(same_y, same_x)] + 1])
         out.append(rows)
     return np.array(out, np.float64)
 
