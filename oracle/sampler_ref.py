@@ -146,3 +146,23 @@ def sample(models, start, goal, walls_list, noise, T=100, w=None, base=0, ddim_s
     if compose_mode:
         x = apply_cond(x, start, goal)
     return (x, log) if trace else x
+
+
+def ddim_replan(model, traj, walls, noise, ddim_steps, dn_steps, T=100, w=2.0):
+    """GaussianDiffusionPB.ddim_replan (diffusion_pb.py:311-346): q_sample the given trajectories [B,H,D] to the
+    dn_steps-th last DDIM timestep (q_sample, :445-455, with the given noise), then run those last dn_steps DDIM
+    updates (eta 0), start/goal re-imposed from the trajectory's own end points after every update.
+    Returns (x [B,H,D], the noisy trajectory before conditioning).  Pinned: tests/golden/resample_m2d.npz."""
+    sd, cfg = model
+    tb = schedule(T)
+    ts = ddim_timesteps(ddim_steps, T)
+    t0 = int(ts[-dn_steps])
+    noisy = tb["sqrt_alphas_cumprod"][t0] * traj + tb["sqrt_one_minus_alphas_cumprod"][t0] * noise
+    start, goal = traj[:, 0], traj[:, -1]
+    x = apply_cond(noisy.clone(), start, goal)
+    for t in ts[-dn_steps:]:
+        tt = torch.full((x.shape[0],), int(t), dtype=torch.long)
+        ec, eu = unet_ref.eps_pair(sd, cfg, x, tt, walls)
+        x = ddim_update(tb, x, int(t), compose([ec], [eu], [w]), ddim_steps, T, 0.0, None)
+        x = apply_cond(x, start, goal)
+    return x, noisy

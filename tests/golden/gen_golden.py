@@ -193,6 +193,38 @@ def gen_concave():
     print("concave", g.rec_loc_grp_list.shape, tokens.shape, "modes", np.bincount(tokens[..., 2].astype(int).ravel()))
 
 
+def gen_resample():
+    """the reference's GaussianDiffusionPB.ddim_replan (diffusion_pb.py:311-346: q_sample to the dn_steps-th last DDIM
+    timestep, then dn_steps DDIM steps with eta=0) on four Maze2D trajectories, one call each as the replanner does;
+    the q_sample noise is injected so that the product can be fed the same"""
+    fam, B, n, dn = "m2d", 4, 8, 3
+    a, m, d, sd = build_ref(fam)
+    H, D = a["horizon"], a["obs_dim"]
+    pr = synth.make_problems(fam, B, 17)
+    lo, hi = pr["lo"], pr["hi"]
+    rng = np.random.default_rng(21)
+    al = np.linspace(0, 1, H)[None, :, None]
+    tr = pr["start"][:, None] * (1 - al) + pr["goal"][:, None] * al + rng.normal(0, 0.1, (B, H, D)) * np.sin(np.pi * al)
+    x0 = torch.tensor(synth.normalize(np.clip(tr, lo, hi).astype(np.float32), lo, hi))
+    walls = torch.tensor(pr["walls"])
+    noise = torch.randn(B, H, D, generator=torch.Generator().manual_seed(9))
+    d.horizon = H; d.ddim_num_inference_steps = n
+    q_sample = d.q_sample
+    out, noisy = [], []
+    for b in range(B):
+        d.q_sample = lambda x_start, t, noise=None, b=b: q_sample(x_start, t, noise=noise_b[b])
+        noise_b = noise[:, None]
+        cond = {0: x0[b, None, 0], H - 1: x0[b, None, -1]}
+        with refshim.quiet():
+            out.append(d.ddim_replan(x0[b], cond, walls[b, None], torch.full((1,), dn, dtype=torch.long)).detach())
+            noisy.append(d.ddim_replan(x0[b], cond, walls[b, None], torch.full((1,), dn, dtype=torch.long), ret_noisy_traj=True)[0])
+    d.q_sample = q_sample
+    np.savez_compressed(os.path.join(HERE, "resample_m2d.npz"), x0=x0.numpy(), walls=walls.numpy(), noise=noise.numpy(),
+                        x=torch.stack(out).numpy(), noisy=torch.stack(noisy).numpy(), ddim_steps=n, dn_steps=dn,
+                        weight_seed=WEIGHT_SEED)
+    print("resample: max |x - x0| %.3f" % float((torch.stack(out) - x0).abs().max()))
+
+
 def gen_replan():
     """the reference's own KukaDiffusionReplanner.replan_collision_section_less_check (kuka_replan.py:33-143) with its
     RM2DCollisionChecker and Maze2D robot, on noisy straight lines; the diffusion call is replaced by preset
@@ -311,6 +343,6 @@ def gen_pick():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk", "concave", "replan", "pick"]
+    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk", "concave", "replan", "pick", "resample"]
     for w in which:
         globals()["gen_" + w]()

@@ -55,6 +55,17 @@ def test_sampler_matches_golden(fam, mode):
     assert torch.equal(x, torch.tensor(g[mode + "_x"]))
 
 
+def test_ddim_replan_matches_golden():
+    """sampler_ref.ddim_replan against the reference's GaussianDiffusionPB.ddim_replan (gen_golden.py resample)"""
+    g = golden("resample_m2d.npz")
+    a = synth.arch("m2d")
+    sd = unet_ref.synth_weights(a["unet"], int(g["weight_seed"]))
+    x, noisy = sampler_ref.ddim_replan((sd, unet_ref.UnetCfg(a["unet"])), torch.tensor(g["x0"]), torch.tensor(g["walls"]),
+                                       torch.tensor(g["noise"]), int(g["ddim_steps"]), int(g["dn_steps"]))
+    assert torch.equal(noisy, torch.tensor(g["noisy"]))
+    assert np.abs(x.numpy() - g["x"]).max() <= 2e-6, np.abs(x.numpy() - g["x"]).max()     # batch of 4 vs four batches of 1
+
+
 @pytest.mark.parametrize("mode", ["ddim24", "ddpm"])
 def test_compose_matches_golden(mode):
     g = golden("compose_m2d.npz")
