@@ -651,3 +651,28 @@ def test_plan_entry_points():
     res = mod.main(["--family", "dualkuka", "--plan_n_maze", "2", "--n_prob_env", "2", "--samples_perprob", "3",
                     "--ddim_steps", "10"], robot="kuka")
     assert keys <= set(res) and res["num_samples"] == 4
+
+
+def test_ddim_replan_matches_reference_golden():
+    """GaussianDiffusionPB.ddim_replan (partial re-noise + the last dn_steps DDIM steps, diffusion_pb.py:311-346) on a
+    batch of four against the reference's outputs for the same trajectories and q_sample noise
+    (tests/golden/resample_m2d.npz)"""
+    g = golden("resample_m2d.npz")
+    d = dropin("m2d", int(g["weight_seed"]))
+    H = g["x0"].shape[1]
+    d.horizon = H; d.ddim_num_inference_steps = int(g["ddim_steps"])
+    x0 = torch.tensor(g["x0"], device=DEV); noise = torch.tensor(g["noise"], device=DEV)
+    walls = torch.tensor(g["walls"], device=DEV)
+    cond = {0: x0[:, 0].clone(), H - 1: x0[:, -1].clone()}
+    dn = torch.full((1,), int(g["dn_steps"]), dtype=torch.long, device=DEV)
+    q_sample = d.q_sample
+    d.q_sample = lambda x_start, t, noise_=None: q_sample(x_start, t, noise=noise)
+    try:
+        noisy = d.ddim_replan(x0, cond, walls, dn, ret_noisy_traj=True)
+        x = d.ddim_replan(x0, cond, walls, dn)
+    finally:
+        del d.q_sample
+    assert np.abs(noisy.cpu().numpy() - g["noisy"]).max() <= 1e-6
+    err = np.abs(x.cpu().numpy() - g["x"]).max()
+    assert err <= TRAJ_ATOL, "re-sampled trajectories differ from the reference by %.3e" % err
+    assert torch.equal(x[:, 0], x0[:, 0]) and torch.equal(x[:, -1], x0[:, -1])
