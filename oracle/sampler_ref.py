@@ -148,21 +148,34 @@ def sample(models, start, goal, walls_list, noise, T=100, w=None, base=0, ddim_s
     return (x, log) if trace else x
 
 
-def ddim_replan(model, traj, walls, noise, ddim_steps, dn_steps, T=100, w=2.0):
-    """GaussianDiffusionPB.ddim_replan (diffusion_pb.py:311-346): q_sample the given trajectories [B,H,D] to the
-    dn_steps-th last DDIM timestep (q_sample, :445-455, with the given noise), then run those last dn_steps DDIM
-    updates (eta 0), start/goal re-imposed from the trajectory's own end points after every update.
-    Returns (x [B,H,D], the noisy trajectory before conditioning).  Pinned: tests/golden/resample_m2d.npz."""
-    sd, cfg = model
+def ddim_replan(models, traj, walls_list, noise, ddim_steps, dn_steps, T=100, w=None, base=0, compose_mode=False):
+    """Re-sampling of given trajectories [B,H,D]: q_sample (diffusion_pb.py:445-455, with the given noise) to the
+    dn_steps-th last DDIM timestep, then those last dn_steps DDIM updates (eta 0).
+    compose_mode False -> GaussianDiffusionPB.ddim_replan (diffusion_pb.py:311-346), one model: start/goal re-imposed
+                          from the trajectory's own end points after the noising and after every update;
+                 True  -> PolicyCompose.ddim_replan (policies_compose.py:399-447), K models: end points imposed on
+                          x_t before every evaluation only (pred_unet conditions in place), not after the last update.
+    Returns (x [B,H,D], the noisy trajectory before any conditioning).
+    Pinned: tests/golden/resample_m2d.npz, resample_compose_m2d.npz."""
+    K = len(models)
+    w = [2.0] * K if w is None else list(w)
     tb = schedule(T)
     ts = ddim_timesteps(ddim_steps, T)
     t0 = int(ts[-dn_steps])
     noisy = tb["sqrt_alphas_cumprod"][t0] * traj + tb["sqrt_one_minus_alphas_cumprod"][t0] * noise
     start, goal = traj[:, 0], traj[:, -1]
-    x = apply_cond(noisy.clone(), start, goal)
-    for t in ts[-dn_steps:]:
-        tt = torch.full((x.shape[0],), int(t), dtype=torch.long)
-        ec, eu = unet_ref.eps_pair(sd, cfg, x, tt, walls)
-        x = ddim_update(tb, x, int(t), compose([ec], [eu], [w]), ddim_steps, T, 0.0, None)
+    x = noisy.clone()
+    if not compose_mode:
         x = apply_cond(x, start, goal)
+    for t in ts[-dn_steps:]:
+        if compose_mode:
+            x = apply_cond(x, start, goal)
+        tt = torch.full((x.shape[0],), int(t), dtype=torch.long)
+        ecs, eus = [], []
+        for (sd, cfg), wl in zip(models, walls_list):
+            ec, eu = unet_ref.eps_pair(sd, cfg, x, tt, wl)
+            ecs.append(ec); eus.append(eu)
+        x = ddim_update(tb, x, int(t), compose(ecs, eus, w, base), ddim_steps, T, 0.0, None)
+        if not compose_mode:
+            x = apply_cond(x, start, goal)
     return x, noisy

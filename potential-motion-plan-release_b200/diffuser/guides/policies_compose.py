@@ -141,6 +141,28 @@ class PolicyCompose(Policy):
             eus.append(eu)
         return (None, torch.stack(ecs, 0)), (None, torch.stack(eus, 0))
 
+    def ddim_replan(self, traj, cond, wall_c, dn_steps):
+        """composed re-sampling of given trajectories (policies_compose.py:399-447): q_sample to the dn_steps-th
+        last DDIM timestep with the first model's schedule, then the last dn_steps composed DDIM updates; x_t is
+        conditioned before every evaluation and not after the last update, as in the reference.  traj [H,D] or
+        [B,H,D] normalised (the reference takes one trajectory; a batch is re-sampled together here), cond
+        {0: [B,D], H-1: [B,D]} normalised, wall_c [B, sum_k nw_k*dim]."""
+        dm0 = self.diffusion_model_list[0]
+        dev = self.device
+        input2d = traj.ndim == 2
+        x = dm0.ddim_get_noisy_traj(traj.to(dev), self.ddim_steps, dn_steps)
+        cond_list = [cond for _ in range(self.n_models)]
+        wall_c = self.wallLoc_preproc(torch.as_tensor(wall_c, dtype=torch.float32).to(dev))
+        w = [float(dm.condition_guidance_w) for dm in self.diffusion_model_list]
+        ts = dm0.ddim_set_timesteps(self.ddim_steps)
+        for t in ts[-dn_steps:]:
+            tt = torch.full((x.shape[0],), int(t), device=dev, dtype=torch.long)
+            (_, ec), (_, eu) = self.models_pred(x, cond_list, tt, wall_c)          # conditions x in place
+            coef = dm0.step_coefs_ddim([int(t)], self.ddim_eta, self.ddim_steps)[0]
+            noise = torch.randn_like(x) if self.ddim_eta > 0 else None
+            x = pmp_b200.step(1, x.contiguous(), list(ec), list(eu), w, coef, noise=noise, base=self.uncond_base_idx)
+        return x[0] if input2d else x
+
     def set_ddim_steps(self, ddim_steps):
         self.ddim_steps = ddim_steps
         for dm in self.diffusion_model_list:

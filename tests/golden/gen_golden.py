@@ -225,6 +225,46 @@ def gen_resample():
     print("resample: max |x - x0| %.3f" % float((torch.stack(out) - x0).abs().max()))
 
 
+def gen_resample_compose():
+    """the reference's PolicyCompose.ddim_replan (policies_compose.py:399-447) for K=2 (6 walls + 3 walls), one
+    trajectory per call; its constructor hard-codes .to('cuda'), so the object is built with object.__new__ and the
+    attributes the method reads"""
+    PC = refshim._import_ref("diffuser.guides.policies_compose")[0].PolicyCompose
+    a1, m1, d1, sd1 = build_ref("m2d", 1)
+    a2, m2, d2, sd2 = build_ref("m2d_nw3", 2)
+    B, H, D, n, dn = 3, 48, 2, 8, 3
+    pr = synth.make_problems("m2d", B, 31); pr2 = synth.make_problems("m2d_nw3", B, 32)
+    lo, hi = pr["lo"], pr["hi"]
+    rng = np.random.default_rng(23)
+    al = np.linspace(0, 1, H)[None, :, None]
+    tr = pr["start"][:, None] * (1 - al) + pr["goal"][:, None] * al + rng.normal(0, 0.1, (B, H, D)) * np.sin(np.pi * al)
+    x0 = torch.tensor(synth.normalize(np.clip(tr, lo, hi).astype(np.float32), lo, hi))
+    walls = torch.cat([torch.tensor(pr["walls"]), torch.tensor(pr2["walls"])], 1)
+    noise = torch.randn(B, H, D, generator=torch.Generator().manual_seed(10))
+    pc = object.__new__(PC)
+    pc.diffusion_model_list = [d1, d2]; pc.diffusion_model = d1; pc.n_models = 2
+    pc.cg_w = torch.tensor([2.0, 1.5]).reshape(2, 1, 1, 1)
+    pc.num_walls_c = torch.tensor([6, 3]); pc.wall_dim = 2; pc.comp_type = "direct"
+    pc.w_split_sizes = tuple((pc.num_walls_c * pc.wall_dim).to(torch.int32))
+    pc.use_normed_wallLoc = False; pc.use_mala_sampler = False; pc.uncond_base_idx = 0; pc.ddim_eta = 0.0
+    pc.is_dyn_env = False; pc.wall_is_dyn = None
+    for dd in (d1, d2):
+        dd.horizon = H
+    pc.set_ddim_steps(n)
+    q_sample = d1.q_sample
+    out = []
+    for b in range(B):
+        d1.q_sample = lambda x_start, t, noise_=None, b=b: q_sample(x_start, t, noise=noise[b, None])
+        cond = {0: x0[b, None, 0], H - 1: x0[b, None, -1]}
+        with refshim.quiet():
+            out.append(pc.ddim_replan(x0[b, None].clone(), cond, walls[b, None], dn).detach()[0])
+    d1.q_sample = q_sample
+    np.savez_compressed(os.path.join(HERE, "resample_compose_m2d.npz"), x0=x0.numpy(), walls=walls.numpy(),
+                        noise=noise.numpy(), x=torch.stack(out).numpy(), ddim_steps=n, dn_steps=dn,
+                        w=np.array([2.0, 1.5], np.float32), seeds=np.array([1, 2]))
+    print("resample_compose: max |x - x0| %.3f" % float((torch.stack(out) - x0).abs().max()))
+
+
 def gen_replan():
     """the reference's own KukaDiffusionReplanner.replan_collision_section_less_check (kuka_replan.py:33-143) with its
     RM2DCollisionChecker and Maze2D robot, on noisy straight lines; the diffusion call is replaced by preset
@@ -343,6 +383,6 @@ def gen_pick():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk", "concave", "replan", "pick", "resample"]
+    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk", "concave", "replan", "pick", "resample", "resample_compose"]
     for w in which:
         globals()["gen_" + w]()

@@ -676,3 +676,32 @@ def test_ddim_replan_matches_reference_golden():
     err = np.abs(x.cpu().numpy() - g["x"]).max()
     assert err <= TRAJ_ATOL, "re-sampled trajectories differ from the reference by %.3e" % err
     assert torch.equal(x[:, 0], x0[:, 0]) and torch.equal(x[:, -1], x0[:, -1])
+
+
+def test_composed_ddim_replan_matches_reference_golden():
+    """PolicyCompose.ddim_replan (K=2, policies_compose.py:399-447) on a batch of three against the reference
+    method's outputs for the same trajectories and q_sample noise (tests/golden/resample_compose_m2d.npz)"""
+    from diffuser.guides import PolicyCompose
+    from diffuser.datasets import DatasetNormalizer, RAND_MAZE_MIN, RAND_MAZESIZE_55
+    g = golden("resample_compose_m2d.npz")
+    norm = DatasetNormalizer({"observations": (RAND_MAZE_MIN, RAND_MAZESIZE_55)})
+    d1, d2 = dropin("m2d", int(g["seeds"][0])), dropin("m2d_nw3", int(g["seeds"][1]))
+    H = g["x0"].shape[1]
+    w_old = (d1.condition_guidance_w, d2.condition_guidance_w)
+    d1.horizon = d2.horizon = H
+    d1.condition_guidance_w, d2.condition_guidance_w = float(g["w"][0]), float(g["w"][1])
+    po = dict(num_walls_c=[6, 3], wall_dim=2, comp_type="direct", ddim_steps=int(g["ddim_steps"]), wall_is_dyn=None,
+              uncond_base_idx=0, ddim_eta=0.0)
+    comp = PolicyCompose([d1, d2], [norm, norm], False, True, po)
+    comp.set_ddim_steps(int(g["ddim_steps"]))
+    x0 = torch.tensor(g["x0"], device=DEV); noise = torch.tensor(g["noise"], device=DEV)
+    cond = {0: x0[:, 0].clone(), H - 1: x0[:, -1].clone()}
+    q_sample = d1.q_sample
+    d1.q_sample = lambda x_start, t, noise_=None: q_sample(x_start, t, noise=noise)
+    try:
+        x = comp.ddim_replan(x0.clone(), cond, torch.tensor(g["walls"]), int(g["dn_steps"]))
+    finally:
+        del d1.q_sample
+        d1.condition_guidance_w, d2.condition_guidance_w = w_old
+    err = np.abs(x.cpu().numpy() - g["x"]).max()
+    assert err <= TRAJ_ATOL, "composed re-sampling differs from the reference by %.3e" % err

@@ -56,14 +56,24 @@ def test_sampler_matches_golden(fam, mode):
 
 
 def test_ddim_replan_matches_golden():
-    """sampler_ref.ddim_replan against the reference's GaussianDiffusionPB.ddim_replan (gen_golden.py resample)"""
+    """sampler_ref.ddim_replan against the reference's GaussianDiffusionPB.ddim_replan (gen_golden.py resample) and
+    PolicyCompose.ddim_replan (gen_golden.py resample_compose); the reference ran one trajectory per call"""
     g = golden("resample_m2d.npz")
     a = synth.arch("m2d")
     sd = unet_ref.synth_weights(a["unet"], int(g["weight_seed"]))
-    x, noisy = sampler_ref.ddim_replan((sd, unet_ref.UnetCfg(a["unet"])), torch.tensor(g["x0"]), torch.tensor(g["walls"]),
+    x, noisy = sampler_ref.ddim_replan([(sd, unet_ref.UnetCfg(a["unet"]))], torch.tensor(g["x0"]), [torch.tensor(g["walls"])],
                                        torch.tensor(g["noise"]), int(g["ddim_steps"]), int(g["dn_steps"]))
     assert torch.equal(noisy, torch.tensor(g["noisy"]))
-    assert np.abs(x.numpy() - g["x"]).max() <= 2e-6, np.abs(x.numpy() - g["x"]).max()     # batch of 4 vs four batches of 1
+    assert np.abs(x.numpy() - g["x"]).max() <= 1e-5, np.abs(x.numpy() - g["x"]).max()    # batch of B vs B calls of 1
+    g = golden("resample_compose_m2d.npz")
+    models = []
+    for fam, seed in (("m2d", int(g["seeds"][0])), ("m2d_nw3", int(g["seeds"][1]))):
+        a = synth.arch(fam)
+        models.append((unet_ref.synth_weights(a["unet"], seed), unet_ref.UnetCfg(a["unet"])))
+    wl = torch.tensor(g["walls"])
+    x, _ = sampler_ref.ddim_replan(models, torch.tensor(g["x0"]), [wl[:, :12], wl[:, 12:]], torch.tensor(g["noise"]),
+                                   int(g["ddim_steps"]), int(g["dn_steps"]), w=[float(v) for v in g["w"]], compose_mode=True)
+    assert np.abs(x.numpy() - g["x"]).max() <= 1e-5, np.abs(x.numpy() - g["x"]).max()    # batch of B vs B calls of 1
 
 
 @pytest.mark.parametrize("mode", ["ddim24", "ddpm"])
