@@ -264,6 +264,9 @@ class GaussianDiffusionPB(nn.Module):
         return self.q_sample(traj, noise_t)
 
     def replan(self, traj, cond, walls_loc, dn_steps):
+        """DDPM re-sampling (diffusion_pb.py:283-309).  The reference method cannot run as written -- it passes a
+        sixth positional argument to its five-argument p_sample (:303) -- so unlike ddim_replan there is no reference
+        output to pin this one against; it follows the method's evident intent."""
         device = self.betas.device
         input2d = traj.ndim < 3
         if input2d:
