@@ -151,3 +151,28 @@ def replan_collision_section(traj, checker, resample, n_replan_trial=5):
         if is_success:
             break
     return new_traj, is_success, num_colck
+
+
+def replan_pred_trajs(candidates, suc, checker_of, resample, n_replan_trial=5, n_repl_max=6):
+    """KukaEnvPlanner.replan_pred_trajs (diffuser/guides/kuka_plan_env.py:207-260), sequential as in the reference:
+    for every problem whose candidate scan failed, up to min(6, #candidates) candidates are handed to the replanner
+    one after the other until one is repaired.  candidates[p]: list of [H,D] arrays in scan order, checker_of(p):
+    the problem's collision checker, resample(trial, traj) as in replan_collision_section.
+    Returns ({p: repaired path}, replan_suc_list [n_p] bool, extra collision checks [n_p])."""
+    suc = np.asarray(suc).astype(bool)
+    repl = suc.copy()
+    extra = np.zeros(len(suc), np.int64)
+    fixed = {}
+    for p in range(len(suc)):
+        if suc[p]:
+            continue
+        ok = False
+        for j in range(min(n_repl_max, len(candidates[p]))):
+            new, ok, cnt = replan_collision_section(candidates[p][j], checker_of(p), resample, n_replan_trial)
+            extra[p] += cnt
+            if ok:
+                break
+        repl[p] = ok
+        if ok:
+            fixed[p] = new
+    return fixed, repl, extra

@@ -56,8 +56,43 @@ def compute_avg_result(ncol, norepl_suc, num_colck, n_env, n_prob, batch_runtime
                 avg_num_colck=n_colck / total_num)
 
 
+def replan_failed(replanner, candidates, walls_p, env_p, geom, suc, n_repl_max=6):
+    """Replanning pass of the planners (KukaEnvPlanner.replan_pred_trajs, kuka_plan_env.py:207-260), batched: the
+    reference walks the failed problems one by one and feeds up to six of a problem's candidates (scan order) to the
+    replanner until one is repaired; here round r repairs candidate r of ALL still-failed problems with one
+    `replan_batch` per trajectory length.  candidates: {problem: list of [H_j, D] numpy candidates in scan order} for
+    the failed problems, walls_p [n_p, wall_len] model input per problem, env_p [n_p] environment of each problem,
+    geom: dict(robot, cen, hext[, n_arms]) as `replan_batch` takes it (env_id is filled in), suc [n_p] success flags of
+    the candidate scan.  Returns ({problem: repaired path}, success-after-replan [n_p] bool -- the reference's
+    replan_suc_list, which starts as a copy of suc -- and the collision checks spent per problem [n_p])."""
+    suc = np.asarray(suc).astype(bool)
+    repl_suc = suc.copy()
+    extra = np.zeros(len(suc), np.int64)
+    new_paths = {}
+    walls_p = torch.as_tensor(walls_p, dtype=torch.float32)
+    active = [int(p) for p in np.nonzero(~suc)[0]]
+    for r in range(n_repl_max):
+        by_len = {}
+        for p in active:
+            if r < len(candidates[p]):
+                by_len.setdefault(len(candidates[p][r]), []).append(p)
+        if not by_len:
+            break
+        for ps in by_len.values():
+            trajs = np.stack([np.asarray(candidates[p][r], np.float32) for p in ps])
+            g = dict(geom, env_id=np.asarray(env_p)[ps].astype(np.int32))
+            new, ok, cnt = replanner.replan_batch(trajs, walls_p[ps], g)
+            for i, p in enumerate(ps):
+                extra[p] += int(cnt[i])
+                if ok[i]:
+                    repl_suc[p] = True
+                    new_paths[p] = np.asarray(new[i], np.float32)
+        active = [p for p in active if not repl_suc[p]]
+    return new_paths, repl_suc, extra
+
+
 def plan_envs(policy, starts, goals, walls, env_boxes, hext, horizon, samples_perprob=10, robot='maze2d',
-              n_arms=1, collision_eps=0.08, legacy_div=True):
+              n_arms=1, collision_eps=0.08, legacy_div=True, replanner=None):
     """starts/goals [n_env, n_prob, D] (un-normalised numpy), walls [n_env, n_prob, wall_len] model input,
     env_boxes [n_env, n_boxes, dim] obstacle centres for the checker, hext half extent.
     Returns (result dict with the reference's keys, chosen paths [n_env*n_prob, H, D] numpy)."""
@@ -84,11 +119,21 @@ def plan_envs(policy, starts, goals, walls, env_boxes, hext, horizon, samples_pe
     idx = torch.arange(n_p, device=dev) * n_s + chosen.long()
     paths = obs[idx]
     env_p = np.repeat(np.arange(n_env, dtype=np.int32), n_prob)
+    repl_suc = None
+    if replanner is not None:      # do_replan: repair the problems whose candidates all collide (kuka_plan_env.py:207-260)
+        suc_h = suc.cpu().numpy().astype(bool)
+        cands = {int(p): list(obs[p * n_s:(p + 1) * n_s].cpu().numpy()) for p in np.nonzero(~suc_h)[0]}
+        geom = dict(robot=robot, cen=env_boxes, hext=hext, n_arms=n_arms)
+        fixed, repl_suc, extra = replan_failed(replanner, cands, walls.reshape(n_p, -1), env_p, geom, suc_h)
+        for p, path in fixed.items():
+            paths[p] = torch.as_tensor(path, device=dev)
+        total = total + torch.as_tensor(extra, device=dev).to(total.dtype)
     if robot == 'maze2d':
         ncol, _ = pmp_b200.colchk_maze2d_points(paths, env_p, env_boxes, hext)
     else:
         ncol = pmp_b200.colchk_kuka(paths, env_p, env_boxes, hext, n_arms, arm_bases(n_arms), chk.sph, TABLE_Z)['ncol']
-    res = compute_avg_result(ncol.cpu().numpy(), suc.cpu().numpy(), total.cpu().numpy(), n_env, n_prob, batch_runtime)
+    res = compute_avg_result(ncol.cpu().numpy(), suc.cpu().numpy(), total.cpu().numpy(), n_env, n_prob, batch_runtime,
+                             repl_suc=repl_suc)
     return res, paths.cpu().numpy()
 
 
@@ -107,7 +152,7 @@ def pick_multi_horizon(valid_list, nchk_list, n_prob, n_samp):
 
 
 def plan_envs_multi_horizon(policy, starts, goals, walls, env_boxes, hext, horizons, samples_perprob=10,
-                            robot='maze2d', n_arms=1, collision_eps=0.08, legacy_div=True):
+                            robot='maze2d', n_arms=1, collision_eps=0.08, legacy_div=True, replanner=None):
     """plan_envs for the composed planner's list of planning horizons (comp_plan_env.py:54-124): every problem is
     planned at every horizon (PolicyCompose.call_multi_horizon), all candidates are collision-checked on the
     GPU and one path per problem is selected with pick_multi_horizon.  Returns (result dict, list of chosen
@@ -143,19 +188,33 @@ def plan_envs_multi_horizon(policy, starts, goals, walls, env_boxes, hext, horiz
     batch_runtime = time.time() - tic
     hs, ss = hsel.cpu().numpy(), ssel.cpu().numpy()
     paths = [obs_h[hs[p]][p * n_s + ss[p]].cpu().numpy() for p in range(n_p)]
-    # final score: per-waypoint check of the chosen path (kuka_plan_utils.py:110-154), batched per horizon
     env_p = np.repeat(np.arange(n_env, dtype=np.int32), n_prob)
+    repl_suc = None
+    if replanner is not None:      # do_replan (comp_plan_env.py:112-114): candidates in scan order, sample-major
+        suc_h = suc.cpu().numpy().astype(bool)
+        cands = {int(p): [obs_h[i][p * n_s + j].cpu().numpy() for j in range(n_s) for i in range(len(horizons))]
+                 for p in np.nonzero(~suc_h)[0]}
+        geom = dict(robot=robot, cen=env_boxes, hext=hext, n_arms=n_arms)
+        fixed, repl_suc, extra = replan_failed(replanner, cands, walls.reshape(n_p, -1), env_p, geom, suc_h)
+        total = total + torch.as_tensor(extra, device=dev).to(total.dtype)
+        hsel_fixed = {p: list(horizons).index(len(path)) for p, path in fixed.items()}
+    # final score: per-waypoint check of the chosen path (kuka_plan_utils.py:110-154), batched per horizon
     ncol = np.zeros(n_p, np.int64)
+    if replanner is not None:
+        hs = hs.copy()
+        for p, path in fixed.items():
+            paths[p] = path
+            hs[p] = hsel_fixed[p]
     for i, ho in enumerate(horizons):
         sel = np.nonzero(hs == i)[0]
         if not len(sel):
             continue
-        pt = obs_h[i][torch.as_tensor(sel * n_s + ss[sel], device=dev)]
+        pt = torch.as_tensor(np.stack([paths[p] for p in sel]), dtype=torch.float32, device=dev)
         if robot == 'maze2d':
             nc, _ = pmp_b200.colchk_maze2d_points(pt, env_p[sel], env_boxes, hext)
         else:
             nc = pmp_b200.colchk_kuka(pt, env_p[sel], env_boxes, hext, n_arms, arm_bases(n_arms), chk.sph, TABLE_Z)['ncol']
         ncol[sel] = nc.cpu().numpy()
-    res = compute_avg_result(ncol, suc.cpu().numpy(), total.cpu().numpy(), n_env, n_prob, batch_runtime)
+    res = compute_avg_result(ncol, suc.cpu().numpy(), total.cpu().numpy(), n_env, n_prob, batch_runtime, repl_suc=repl_suc)
     res['horizon_hist'] = [int((hs == i).sum()) for i in range(len(horizons))]
     return res, paths

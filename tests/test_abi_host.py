@@ -335,3 +335,47 @@ def test_problem_batch_layout_matches_live_reference():
             rep = lambda a: np.repeat(a.reshape(n_prob, -1), n_s, axis=0)              # plan_envs' batch layout
             assert np.array_equal(rep(s_), o_t.numpy()) and np.array_equal(rep(g_), t_t.numpy())
             assert np.array_equal(rep(w_), w_t.numpy())
+
+
+def test_replan_failed_rounds_equal_sequential_reference_order():
+    """plan_env_b200.replan_failed (round r repairs candidate r of all still-failed problems at once) against the
+    sequential restatement of KukaEnvPlanner.replan_pred_trajs (kuka_plan_env.py:207-260); the replanner is a stand-in
+    whose replan_batch runs the pinned oracle per row, so only the orchestration is under test (no GPU)"""
+    from diffuser.guides.plan_env_b200 import replan_failed
+    from oracle import replan_ref
+    E_, n_prob, n_s, hext, n_trial = 4, 5, 7, 0.5, 2
+    pr = synth.make_problems("m2d", E_, 51)
+    rng = np.random.default_rng(14)
+    n_p = E_ * n_prob
+    env_p = np.repeat(np.arange(E_), n_prob)
+    horizons = (40, 48)
+
+    def resample(trial, traj):          # deterministic function of the trajectory only
+        al = np.linspace(0, 1, len(traj))[:, None]
+        return np.clip(traj + (0.45 if trial else -0.3) * np.sin(np.pi * al) ** 2, 0.02, 4.98).astype(np.float32)
+    cands = {}
+    suc = rng.random(n_p) < 0.3
+    for p in np.nonzero(~suc)[0]:
+        s, g = rng.uniform(0.3, 4.7, 2), rng.uniform(0.3, 4.7, 2)
+        cands[int(p)] = []
+        for j in range(n_s):
+            H = horizons[j % 2]
+            al = np.linspace(0, 1, H)[:, None]
+            cands[int(p)].append(np.clip(s * (1 - al) + g * al + rng.normal(0, 0.08, (H, 2)) * np.sin(np.pi * al), 0.02, 4.98).astype(np.float32))
+
+    class Stub:
+        calls = 0
+        def replan_batch(self, trajs, walls, geom):
+            Stub.calls += 1
+            assert len({len(t) for t in trajs}) == 1 and len(walls) == len(trajs) == len(geom["env_id"])
+            out = [replan_ref.replan_collision_section(t, replan_ref.Maze2DChecker(geom["cen"][e], geom["hext"]), resample, n_trial)
+                   for t, e in zip(trajs, geom["env_id"])]
+            return [o[0] for o in out], [o[1] for o in out], [o[2] for o in out]
+    walls_p = np.zeros((n_p, 12), np.float32)
+    got = replan_failed(Stub(), cands, walls_p, env_p, dict(robot="maze2d", cen=pr["boxes"], hext=hext), suc)
+    ref = replan_ref.replan_pred_trajs(cands, suc, lambda p: replan_ref.Maze2DChecker(pr["boxes"][env_p[p]], hext), resample, n_trial)
+    assert set(got[0]) == set(ref[0]) and all(np.array_equal(got[0][p], ref[0][p]) for p in ref[0])
+    assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+    n_failed = int((~suc).sum())
+    assert 0 < len(ref[0]) < n_failed and (got[1] >= suc).all()
+    assert Stub.calls <= 6 * len(horizons)                     # rounds x lengths, not problems x candidates

@@ -705,3 +705,36 @@ def test_composed_ddim_replan_matches_reference_golden():
         d1.condition_guidance_w, d2.condition_guidance_w = w_old
     err = np.abs(x.cpu().numpy() - g["x"]).max()
     assert err <= TRAJ_ATOL, "composed re-sampling differs from the reference by %.3e" % err
+
+
+def test_plan_envs_with_replanning():
+    """plan_envs(..., replanner=...): problems whose candidates all collide go through the batched replanner
+    (kuka_plan_env.py:207-260); statistics keep the reference's meaning (replan_suc_list starts from the scan's
+    successes) and the run is the plain one when nothing fails"""
+    from diffuser.guides import Policy, RM2DCollisionChecker
+    from diffuser.guides.kuka_replan import KukaDiffusionReplanner
+    from diffuser.guides.plan_env_b200 import plan_envs
+    from diffuser.datasets import DatasetNormalizer, RAND_MAZE_MIN, RAND_MAZESIZE_55
+    norm = DatasetNormalizer({"observations": (RAND_MAZE_MIN, RAND_MAZESIZE_55)})
+    d = dropin("m2d"); d.horizon = 48; d.ddim_num_inference_steps = 8
+    policy = Policy(d, norm, use_ddim=True)
+    rp = KukaDiffusionReplanner(d, norm, dict(use_ddim=True, dn_steps=3, n_replan_trial=2), DEV)
+    chk = RM2DCollisionChecker(normalizer=None, device=DEV); chk.use_collision_eps = True; chk.collision_eps = 0.08
+    rp.set_collision_checker(chk)
+    n_env, n_prob, n_s = 3, 4, 2
+    pr = synth.make_problems("m2d", n_env, 61)
+    rng = np.random.default_rng(9)
+    starts = rng.uniform(0.2, 4.8, (n_env, n_prob, 2)).astype(np.float32)
+    goals = rng.uniform(0.2, 4.8, (n_env, n_prob, 2)).astype(np.float32)
+    walls = np.repeat(pr["walls"][:, None], n_prob, 1)
+    torch.manual_seed(3)
+    res0, paths0 = plan_envs(policy, starts, goals, walls, pr["boxes"], 0.5, 48, samples_perprob=n_s)
+    torch.manual_seed(3)
+    res1, paths1 = plan_envs(policy, starts, goals, walls, pr["boxes"], 0.5, 48, samples_perprob=n_s, replanner=rp)
+    assert res0["traj_repl_srate"] == 0.0 and res1["traj_norepl_srate"] == res0["traj_norepl_srate"]
+    assert res1["traj_repl_srate"] >= res1["traj_norepl_srate"] and res1["traj_srate"] >= res0["traj_srate"]
+    if res0["traj_norepl_srate"] < 1.0:          # random weights: most candidates collide, so the replanner ran
+        assert res1["total_num_colck"] > res0["total_num_colck"]
+    assert paths1.shape == paths0.shape and np.isfinite(paths1).all()
+    same = [np.array_equal(a, b) for a, b in zip(paths0, paths1)]
+    assert sum(same) >= round(res0["traj_norepl_srate"] * n_env * n_prob)      # scan successes are left alone
