@@ -43,6 +43,24 @@ def load_diffusion(family, logdir, device):
     return a, diffusion.to(device).eval()
 
 
+def make_replanner(args, diffusion, norm, robot):
+    """KukaDiffusionReplanner + the planners' collision checker settings (comp_plan_env.py:166-177)"""
+    if not args.do_replan:
+        return None
+    from diffuser.guides import RM2DCollisionChecker, KukaCollisionChecker
+    from diffuser.guides.kuka_replan import KukaDiffusionReplanner
+    rp = KukaDiffusionReplanner(diffusion, norm, dict(use_ddim=True, dn_steps=args.repl_dn_steps, n_replan_trial=5),
+                                args.device)
+    if robot == 'maze2d':
+        chk = RM2DCollisionChecker(normalizer=None, device=args.device)
+        chk.use_collision_eps = True
+        chk.collision_eps = 0.08
+    else:
+        chk = KukaCollisionChecker(device=args.device)
+    rp.set_collision_checker(chk)
+    return rp
+
+
 def main(argv=None, robot='maze2d'):
     ap = argparse.ArgumentParser()
     ap.add_argument('--family', default='m2d' if robot == 'maze2d' else 'kuka', choices=workloads.FAMILIES)
@@ -59,6 +77,9 @@ def main(argv=None, robot='maze2d'):
     ap.add_argument('--hext', type=float, default=None, help='half extent of the obstacles in --problems')
     ap.add_argument('--layouts', default=None, help='concave mazes: rand_rec2dgrp/<env_list_name>_eval.npy')
     ap.add_argument('--concave43', default=None, help='concave mazes: rand_rec2dgrp/<env_list_name>_43_eval.pkl')
+    ap.add_argument('--do_replan', type=int, default=0,
+                    help='repair problems whose candidates all collide with the batched replanner (reference: do_replan)')
+    ap.add_argument('--repl_dn_steps', type=int, default=3)
     ap.add_argument('--device', default='cuda:0')
     args = ap.parse_args(argv)
     a, diffusion = load_diffusion(args.family, args.logdir, args.device)
@@ -85,7 +106,8 @@ def main(argv=None, robot='maze2d'):
         policy = Policy(diffusion, norm, use_ddim=bool(args.use_ddim))
         hext = args.hext if args.hext is not None else workloads.make_problems(args.family, 1, 0)['hext']
         res, _ = plan_envs(policy, s_, g_, w_, c_, hext, H, samples_perprob=args.samples_perprob, robot=robot,
-                           n_arms=2 if args.family == 'dualkuka' else 1)
+                           n_arms=2 if args.family == 'dualkuka' else 1,
+                           replanner=make_replanner(args, diffusion, norm, robot))
         res['config'] = vars(args)
         print(json.dumps(res))
         return res
@@ -109,7 +131,8 @@ def main(argv=None, robot='maze2d'):
     policy = Policy(diffusion, norm, use_ddim=bool(args.use_ddim))
     res, _ = plan_envs(policy, np.array(starts, np.float32), np.array(goals, np.float32), np.array(walls, np.float32),
                        np.array(boxes), pr['hext'], H, samples_perprob=args.samples_perprob, robot=robot,
-                       n_arms=2 if args.family == 'dualkuka' else 1)
+                       n_arms=2 if args.family == 'dualkuka' else 1,
+                       replanner=make_replanner(args, diffusion, norm, robot))
     res['config'] = vars(args)
     print(json.dumps(res))
     return res
