@@ -379,3 +379,22 @@ def test_replan_failed_rounds_equal_sequential_reference_order():
     n_failed = int((~suc).sum())
     assert 0 < len(ref[0]) < n_failed and (got[1] >= suc).all()
     assert Stub.calls <= 6 * len(horizons)                     # rounds x lengths, not problems x candidates
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+def test_normalizer_matches_live_reference():
+    """LimitsNormalizer (constant limits) against the reference class (datasets/normalization.py:137-162) built with the
+    same limits through its min_max argument; float32 / float64 inputs, in and out of range"""
+    from diffuser.datasets import LimitsNormalizer, KUKA7D_MIN, KUKA7D_MAX, RAND_MAZE_MIN, RAND_MAZESIZE_55
+    Ref = refshim.load_replanner()[2]
+    rng = np.random.default_rng(2)
+    for lo, hi in ((KUKA7D_MIN, KUKA7D_MAX), (RAND_MAZE_MIN, RAND_MAZESIZE_55)):
+        D = len(lo)
+        ref = Ref(np.stack([lo, hi]).astype(np.float32), (np.asarray(lo, np.float32), np.asarray(hi, np.float32)))
+        got = LimitsNormalizer(lo, hi)
+        for dt in (np.float32, np.float64):
+            q = rng.uniform(lo, hi, (6, 48, D)).astype(dt)
+            assert np.array_equal(got.normalize(q), ref.normalize(q)) and got.normalize(q).dtype == ref.normalize(q).dtype
+            for x in (rng.uniform(-1, 1, (6, 48, D)).astype(dt), rng.normal(0, 0.9, (6, 48, D)).astype(dt)):
+                a, b = got.unnormalize(x), ref.unnormalize(x)
+                assert a.dtype == b.dtype and np.array_equal(a, b)
