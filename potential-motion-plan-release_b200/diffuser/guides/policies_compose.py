@@ -23,7 +23,7 @@ class PolicyCompose(Policy):
         self.num_walls_c = torch.tensor(po_config['num_walls_c'])
         self.wall_dim = po_config['wall_dim']
         self.comp_type = po_config['comp_type']
-        assert self.comp_type in ['direct', 'share']
+        assert self.comp_type in ['direct', 'share', 'share-model2fix']
         self.use_ddim = use_ddim
         self.ddim_steps = po_config['ddim_steps']
         self.wall_is_dyn = po_config.get('wall_is_dyn', None)
@@ -57,14 +57,17 @@ class PolicyCompose(Policy):
         return utils.to_torch(conditions, dtype=torch.float32, device=self.device)
 
     def wallLoc_preproc(self, wall_c):
-        """[B, nw*dim] -> list (K) of per-model wall vectors (policies_compose.py:95-181)"""
+        """[B, nw*dim] -> list (K) of per-model wall vectors (policies_compose.py:95-181).
+        'direct': disjoint split by num_walls_c; a second model given one (two) obstacles gets them padded to three
+        with jittered copies, as the reference does for its 3-obstacle model.  'share' / 'share-model2fix' (two
+        models): the first num_walls_c[0] obstacles, and the last num_walls_c[0] (num_walls_c[1]) obstacles."""
         if self.comp_type == 'direct':
             wall_c = list(torch.split(wall_c, self.w_split_sizes, dim=1))
-            if self.n_models == 2 and self.w_split_sizes[1] == 2:
+            if self.w_split_sizes[1] == 2:
                 tmp = torch.repeat_interleave(wall_c[1], repeats=2, dim=1)
                 tmp = tmp + torch.randn_like(tmp) * 0.03
                 wall_c[1] = torch.cat([wall_c[1], tmp], dim=1)
-            elif self.n_models == 2 and self.w_split_sizes[1] == 4:
+            elif self.w_split_sizes[1] == 4:
                 tmp = torch.clone(wall_c[1][:, :2])
                 tmp = tmp + torch.randn_like(tmp) * 0.03
                 wall_c[1] = torch.cat([wall_c[1], tmp], dim=1)
@@ -74,8 +77,13 @@ class PolicyCompose(Policy):
         nw = round(nwd / self.wall_dim)
         wall_c = wall_c.reshape(B, -1, self.wall_dim)
         first = torch.clone(wall_c[:, :self.num_walls_c[0], :]).flatten(1, 2)
-        second = torch.clone(wall_c[:, (nw - int(self.num_walls_c[0])):, :]).flatten(1, 2)
-        assert first.shape == second.shape
+        if self.comp_type == 'share':
+            from_idx = nw - int(self.num_walls_c[0])
+        else:
+            from_idx = max(0, nw - int(self.num_walls_c[1]))
+        second = torch.clone(wall_c[:, from_idx:, :]).flatten(1, 2)
+        if self.comp_type == 'share':
+            assert first.shape == second.shape
         return [first, second]
 
     def call_multi_horizon(self, cond_mulho, wall_c):

@@ -398,3 +398,32 @@ def test_normalizer_matches_live_reference():
             for x in (rng.uniform(-1, 1, (6, 48, D)).astype(dt), rng.normal(0, 0.9, (6, 48, D)).astype(dt)):
                 a, b = got.unnormalize(x), ref.unnormalize(x)
                 assert a.dtype == b.dtype and np.array_equal(a, b)
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+def test_compose_wall_split_matches_live_reference():
+    """PolicyCompose.wallLoc_preproc against the reference method (policies_compose.py:95-181) for the three
+    composition types, including the jitter-padded one- and two-obstacle second model (same torch seed)"""
+    from diffuser.guides import PolicyCompose
+    RefPC = refshim._import_ref("diffuser.guides.policies_compose")[0].PolicyCompose
+    cases = [("direct", [6, 3], 2), ("direct", [6, 1], 2), ("direct", [6, 2], 2), ("direct", [4, 3, 2], 3),
+             ("direct", [3, 1, 3], 2), ("share", [6, 2], 2), ("share-model2fix", [6, 3], 2), ("share", [4, 1], 3)]
+    for comp_type, nwc, wd in cases:
+        objs = []
+        for cls in (RefPC, PolicyCompose):
+            o = object.__new__(cls)
+            o.comp_type = comp_type; o.num_walls_c = torch.tensor(nwc); o.wall_dim = wd; o.n_models = len(nwc)
+            o.is_dyn_env = False; o.wall_is_dyn = None
+            o.w_split_sizes = (tuple((o.num_walls_c * wd).to(torch.int32)) if cls is RefPC
+                               else tuple(int(v) for v in (o.num_walls_c * wd)))
+            objs.append(o)
+        n_total = sum(nwc) if comp_type == "direct" else (nwc[0] + nwc[1])
+        w = torch.randn(5, n_total * wd, generator=torch.Generator().manual_seed(1))
+        torch.manual_seed(4)
+        with refshim.quiet():
+            ref = objs[0].wallLoc_preproc(w.clone())
+        torch.manual_seed(4)
+        got = objs[1].wallLoc_preproc(w.clone())
+        assert len(ref) == len(got), (comp_type, nwc)
+        for a, b in zip(ref, got):
+            assert torch.equal(a, b), (comp_type, nwc)
