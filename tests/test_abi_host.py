@@ -427,3 +427,31 @@ def test_compose_wall_split_matches_live_reference():
         assert len(ref) == len(got), (comp_type, nwc)
         for a, b in zip(ref, got):
             assert torch.equal(a, b), (comp_type, nwc)
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+def test_replanner_helpers_match_live_reference():
+    """section helpers of the batched replanner (product and oracle copies) against the reference functions
+    (kuka_replan.py:176-253), exhaustively over the section positions of the planning horizons"""
+    from diffuser.guides import kuka_replan as prod
+    from oracle import replan_ref
+    R = refshim._import_ref("diffuser.guides.kuka_replan")[0]
+    for H in (40, 48, 56):
+        for st in range(H):
+            for end in range(st, min(H, st + 30)):
+                if end - st + 1 >= H - 1:
+                    continue
+                ref = R.KukaDiffusionReplanner.get_expanded_subtraj(None, H, st, end)
+                assert np.array_equal(prod.expanded_subtraj(H, st, end), ref)
+                assert np.array_equal(replan_ref.expanded_subtraj(H, st, end), ref)
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        arr = np.nonzero(rng.random(48) < rng.uniform(0.05, 0.9))[0]
+        if not len(arr):
+            continue
+        ref = R.split_sorted_array_into_subarrays(arr)
+        for f in (prod.split_sorted_array_into_subarrays, replan_ref.split_runs):
+            got = f(arr)
+            assert len(got) == len(ref) and all(np.array_equal(a, b) for a, b in zip(got, ref))
+    for D in (2, 7, 14):
+        assert prod.get_se_thres(np.zeros((4, D))) == R.get_se_thres(np.zeros((4, D))) == replan_ref.se_thres(np.zeros((4, D)))
