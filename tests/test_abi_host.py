@@ -455,3 +455,29 @@ def test_replanner_helpers_match_live_reference():
             assert len(got) == len(ref) and all(np.array_equal(a, b) for a, b in zip(got, ref))
     for D in (2, 7, 14):
         assert prod.get_se_thres(np.zeros((4, D))) == R.get_se_thres(np.zeros((4, D))) == replan_ref.se_thres(np.zeros((4, D)))
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+def test_solution_interp_matches_live_reference():
+    """sol_interp_pair (product) / sol_interp (oracle) against the reference's SolutionInterp
+    (pb_diff_envs/utils/kuka_utils_luo.py:10-55) for two-waypoint inputs (what steerTo_repl feeds it) and, for the
+    oracle, longer waypoint lists; float32 and float64 ends, including nearly coincident ones"""
+    from diffuser.guides.kuka_replan import sol_interp_pair
+    from oracle import replan_ref
+    SI = refshim._import_ref("pb_diff_envs.utils.kuka_utils_luo")[0].SolutionInterp
+    rng = np.random.default_rng(5)
+    for density in (3, 8):
+        ref_f = SI(density=density)
+        for D in (2, 7, 14):
+            for dt in (np.float32, np.float64):
+                for scale in (1.0, 0.05, 1e-4):
+                    a = rng.uniform(-2, 2, D).astype(dt); b = (a + rng.normal(0, scale, D)).astype(dt)
+                    with refshim.quiet():
+                        ref = np.asarray(ref_f([a, b]))
+                    got = sol_interp_pair(a, b, density)
+                    assert got.shape == ref.shape and np.array_equal(got, ref), (density, D, dt, scale)
+                    assert np.array_equal(replan_ref.sol_interp([a, b], density), ref)
+                pts = [rng.uniform(-2, 2, D).astype(dt) for _ in range(5)]
+                with refshim.quiet():
+                    ref = np.asarray(ref_f(pts))
+                assert np.array_equal(replan_ref.sol_interp(pts, density), ref)
