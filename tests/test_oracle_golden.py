@@ -322,3 +322,33 @@ def test_oracle_colchk_matches_live_reference():
             v, c = colchk_ref.maze2d_swept(tr[None], np.zeros(1, np.int32), pr["boxes"][e], 0.5,
                                            legacy_div=np.__version__ < "2")
             assert bool(v[0]) == ok and int(c[0]) == cnt
+
+
+@needs_ref
+def test_pick_first_valid_matches_live_reference_planner():
+    """colchk_ref.maze2d_swept + pick_first_valid against the reference's single-horizon candidate scan
+    (RandMaze2DEnvPlanner.option_1_pick_1_traj, rm2d_plan_env.py:137-235) run here on the horizon-48 candidates of
+    tests/golden/pick_multi_horizon.npz"""
+    P, RW, RWG, Env = refshim.load_maze2d_geometry()
+    Planner = refshim._import_ref("diffuser.guides.rm2d_plan_env")[0].RandMaze2DEnvPlanner
+    z = golden("pick_multi_horizon.npz")
+    n_p, n_s, hext = int(z["n_prob"]), int(z["n_samp"]), float(z["hext"])
+
+    class Obj:
+        pass
+    for e in range(3):
+        tj = z["cand_h48"][e]
+        walls = [RW(np.array(c), np.array([hext, hext])) for c in z["boxes"][e]]
+        env = object.__new__(Env); env.robot = P(np.array([5., 5.]), RWG(walls), 0.01, collision_eps=0.08)
+        pl = object.__new__(Planner)
+        pl.samples_perprob = n_s; pl.horizon = 48; pl.is_dyn_env = False
+        pl.replanner = Obj(); pl.replanner.set_collision_checker = lambda c: None
+        o = Obj(); o.observations = tj
+        with refshim.quiet():
+            d = pl.option_1_pick_1_traj(o, env, n_p)
+        v, c = colchk_ref.maze2d_swept(tj, np.zeros(len(tj), np.int32), z["boxes"][e][None], hext, eps=float(z["eps"]),
+                                       legacy_div=bool(z["legacy_div"]))
+        ch, su, tot = colchk_ref.pick_first_valid(v, c, n_p, n_s)
+        assert [bool(s) for s in d["suc_list"]] == su.tolist() and list(d["num_colck_list"]) == tot.tolist()
+        for p in range(n_p):
+            assert np.array_equal(d["modelout_path_list"][p], tj[p * n_s + ch[p]])
