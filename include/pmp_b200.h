@@ -200,6 +200,10 @@ int pmp_pick_first_valid(const uint8_t *valid_dev, const int32_t *nchk_dev, int 
 
 /* ---- introspection for tests / bench: number of kernels this library launched so far. */
 uint64_t pmp_launch_count(void);
+/* library-wide options.  "uncond_dedup" (default 1): compositions whose potentials are the SAME network
+ * (config/comp: one model, K obstacle subsets) evaluate the wall-independent unconditional half once per step
+ * instead of K times (bit-identical, policies_compose.py:286-297); 0 switches the sharing off. */
+int pmp_set_option(const char *name, int value);
 /* per-launch CUDA-event timing of the implicit-GEMM conv kernels (class 0: fp32 SIMT core,
  * class 1: tcgen05 core).  While enabled every conv launch is bracketed by two events on its
  * stream; pmp_profile_read waits for them, returns summed milliseconds, algorithmic FLOPs
@@ -207,7 +211,8 @@ uint64_t pmp_launch_count(void);
  * launch counts per class, and clears the records. */
 int pmp_profile_enable(int on);
 int pmp_profile_read(int n_classes, double *ms, double *flops, int64_t *launches);
-/* debug: cumulative clock64() role timers of conv_tc_kernel (enabled by env PMP_TC_TIMERS=1):
+/* debug (diagnostic builds only, `make diag`: the release library has the timers and every work-skipping probe
+ * compiled out and always returns 1): cumulative clock64() role timers of conv_tc_kernel (env PMP_TC_TIMERS=1):
  * out8 = {mma_wait_tma, mma_wait_acc, mma_total, epi_wait_acc, epi_busy, tma_wait_stage, tiles, 0};
  * returns 1 when the timers are disabled */
 int pmp_debug_counters(double *out8, int reset);

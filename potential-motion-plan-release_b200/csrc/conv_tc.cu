@@ -44,6 +44,16 @@ namespace pmp {
 namespace {
 using namespace tc;
 
+// Diagnostics (role / phase timers, work-skipping timing probes) exist only in -DPMP_DIAG builds
+// (`make diag` -> libpmp_b200_diag.so); the release library compiles them out.
+#ifdef PMP_DIAG
+#define DBGF(bit) ((P.dbg & (bit)) != 0)
+#define CTRP (P.ctr)
+#else
+#define DBGF(bit) (false)
+#define CTRP (static_cast<unsigned long long*>(nullptr))
+#endif
+
 constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int BK = 64;                      // channels per K block = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = 128 * BK * 2;  // 16 KB per BF16 plane
@@ -81,6 +91,10 @@ struct TcP {
     alignas(64) CUtensorMap mSg;
     alignas(64) CUtensorMap mSgh;
     alignas(64) CUtensorMap mSgl;
+    // TMA-LOAD side of the epilogue: the identity / residual term given as BF16 planes (box geometry of the store
+    // maps); the saved yhat of a GroupNorm-backward launch is loaded through mSy
+    alignas(64) CUtensorMap mIh;
+    alignas(64) CUtensorMap mIl;
 };
 
 // small-K conv on the CUDA cores for the row owned by this thread (weights staged in smem [t][d][NT])
@@ -135,11 +149,18 @@ struct Cfg {
     static constexpr int A_BYTES = 128 * BKC * 2;
     static constexpr int B_TILE_BYTES = (NT / CG) * BKC * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_TILE_BYTES;
+    // PIPE (TE kernels on the 256-column tiles, and the 16-warp 64-column ones): the epilogue's staging is split into
+    // OUTPUT tiles (F | H | L) and INPUT tiles for the identity planes (Ih | Il; yhat of a GroupNorm-backward launch
+    // comes in through F, which is not an output there), so that the TMA load of the NEXT chunk's inputs and the drain
+    // of the PREVIOUS chunk's bulk stores overlap the arithmetic of the current one (measured before: 0.9-1.9 k cycles
+    // of exposed drain per chunk and 1.1-1.7 k per load, 30-45 % of the epilogue).  Paid for with one ring stage.
+    static constexpr bool PIPE = TE && !TEAM && (NT == 256 || (NT == 64 && NG == 4));
     static constexpr int NSTAGE =
-        AR ? 5 : (CG == 2 ? (NT == 256 ? 4 : (NT == 128 ? (TE ? 3 : 4) : 3)) : (NT == 64 ? (TE ? 2 : 3) : (NT == 128 ? 3 : 2)));
+        AR ? (PIPE ? 4 : 5)
+           : (CG == 2 ? (NT == 256 ? (PIPE ? 3 : 4) : (NT == 128 ? (TE ? 3 : 4) : 3)) : (NT == 64 ? (TE ? 2 : 3) : (NT == 128 ? 3 : 2)));
     // AR: the ring holds the weight tiles only (NSTAGE stages of 2 planes), the A buffers sit in front of it
     static constexpr int RING_BYTES = AR ? (NA * 2 * A_BUF_BYTES + NSTAGE * 2 * B_TILE_BYTES) : NSTAGE * STAGE_BYTES;
-    static constexpr int STG_HALF_BYTES = 128 * CW * 4 + 2 * 128 * CW * 2;   // F | H | L of one warp group
+    static constexpr int STG_HALF_BYTES = 128 * CW * 4 + 2 * 128 * CW * 2 + (PIPE ? 2 * 128 * CW * 2 : 0);   // F | H | L (| Ih | Il) of one warp group
     static constexpr int STG_BYTES = TE ? NG * STG_HALF_BYTES : 0;
     static constexpr int INL_FLOATS = NT == 64 ? 5 * 16 * 64 : 0;   // inline small-K conv weights [taps][D<=16][64]
     static constexpr int ACC_COLS = NT * (ACC2 ? 2 : 1);
@@ -156,7 +177,11 @@ struct Cfg {
     static_assert(!GS || CPG <= NG || NG == 2, "a GroupNorm group spans more chunks than there are warp groups");
     // smem: stages | staging tiles | row/slab partials | slab stats | column params | row info | barriers
     static constexpr int TBUF_FLOATS = 0;
-    static constexpr int PSLOTS = TEAM ? 1 : (NG == 2 ? 2 : CPG);
+    // NG = 4: every warp group takes a CONTIGUOUS range of NCH / 4 chunks (64 columns >= one GroupNorm group), so a
+    // (row, group) partial has one writer; NG = 2: the two groups alternate chunks (two writers)
+    static constexpr bool CONTIG = NG == 4 && !TEAM;
+    static_assert(!CONTIG || !GS || (NT / NG) % GS == 0 || GS % (NT / NG) == 0, "chunk ranges vs GroupNorm groups");
+    static constexpr int PSLOTS = TEAM ? 1 : (NG == 2 ? (CPG >= 2 ? 2 : 1) : ((GS > NT / NG) ? GS / (NT / NG) : 1));
     static constexpr int PART_FLOATS = PSLOTS * 128 * G * 2;
     static constexpr int NTEAM = TEAM ? 2 : 1;     // copies of the per-tile scratch tables
     static constexpr int STAT_FLOATS = 384;
@@ -194,7 +219,8 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
     uint64_t* tempty = tfull + 4;
     uint64_t* afull = tempty + 4;          // AR: haloed A buffers
     uint64_t* aempty = afull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
+    uint64_t* lfull = aempty + 2;          // TE: epilogue input tiles (yhat, identity planes) landed, one per warp group
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lfull + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.S, HJ = p.HJ, N = p.N;
@@ -210,11 +236,14 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             if (p.out_hi) { prefetch_tmap(&P.mSoh); prefetch_tmap(&P.mSol); }
             if (p.gy) prefetch_tmap(&P.mSg);
             if (p.gy_hi) { prefetch_tmap(&P.mSgh); prefetch_tmap(&P.mSgl); }
+            if (p.yhat && p.gn_bwd) prefetch_tmap(&P.mSy);
+            if (p.ident_hi) { prefetch_tmap(&P.mIh); prefetch_tmap(&P.mIl); }
         }
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         // tempty: the epilogues of both CTAs of a pair release the accumulator stage to the leader's MMA warp
         for (int i = 0; i < 4; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CG); }
         for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+        for (int i = 0; i < 4; ++i) mbar_init(&lfull[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -293,14 +322,14 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                 const int nb0 = n0 + (int)crank * (NT / CG);   // first B row staged by this CTA
                 const int nkb1 = p.ntaps[op] * P.kpt;
                 for (int kb = 0; kb < nkb1 + P.nkb2; ++kb) {
-                    if (P.dbg & 16) break;   // diagnostics: MMA-only runs read whatever is in shared memory
-                    const long long tw0 = (P.ctr && P.tmode == 1) ? clock64() : 0;
+                    if (DBGF(16)) break;   // diagnostics: MMA-only runs read whatever is in shared memory
+                    const long long tw0 = (CTRP && P.tmode == 1) ? clock64() : 0;
                     mbar_wait(&empty[s], ph ^ 1);
-                    if (P.ctr && P.tmode == 1) atomicAdd(P.ctr + 5, (unsigned long long)(clock64() - tw0));
+                    if (CTRP && P.tmode == 1) atomicAdd(CTRP + 5, (unsigned long long)(clock64() - tw0));
                     uint8_t* st = smem + s * C::STAGE_BYTES;
                     // dbg 64 (timing probe for operand reuse, garbage results): the A tile is only loaded for one tap of five
-                    const bool skipA = (P.dbg & 64) && kb < nkb1 && p.ntaps[op] == 5 && (kb / P.kpt) != 2;
-                    const bool skipB = (P.dbg & 128) && kb < nkb1 && p.ntaps[op] == 5 && (kb / P.kpt) != 2;   // same probe for B
+                    const bool skipA = DBGF(64) && kb < nkb1 && p.ntaps[op] == 5 && (kb / P.kpt) != 2;
+                    const bool skipB = DBGF(128) && kb < nkb1 && p.ntaps[op] == 5 && (kb / P.kpt) != 2;   // same probe for B
                     if (CG == 1 || crank == 0)
                         mbar_expect_tx(&full[s], CG * ((skipA ? 0 : 2 * bytesA) + (skipB ? 0 : 2 * C::B_TILE_BYTES)));
                     if (kb < nkb1) {
@@ -336,7 +365,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
         if (lane == 0 && crank == 0) {
             // instruction descriptor: D=F32, A=B=BF16, both K-major, N=NT, M=128 per CTA
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
-                                   ((uint32_t)(((P.dbg & 32) && NT == 128 && !ACC2 ? 256 : NT) >> 3) << 17) |   // dbg 32: N=256 rate probe
+                                   ((uint32_t)((DBGF(32) && NT == 128 && !ACC2 ? 256 : NT) >> 3) << 17) |   // dbg 32: N=256 rate probe
                                    (((128u * CG) >> 4) << 24);
             auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
                 if (CG == 2) tc_mma2(d, a, b, id, acc); else tc_mma(d, a, b, id, acc);
@@ -348,11 +377,11 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             uint32_t ph = 0, aph = 0;
             int ai = 0;            // AR: haloed A buffer ring
             uint32_t aphA = 0;
-            const long long tm0 = (P.ctr && P.tmode == 1) ? clock64() : 0;
+            const long long tm0 = (CTRP && P.tmode == 1) ? clock64() : 0;
             for (int tile = sched0; tile < nsched; tile += sched_step) {
-                const long long te0 = (P.ctr && P.tmode == 1) ? clock64() : 0;
+                const long long te0 = (CTRP && P.tmode == 1) ? clock64() : 0;
                 mbar_wait(&tempty[as], aph ^ 1);
-                if (P.ctr && P.tmode == 1) atomicAdd(P.ctr + 1, (unsigned long long)(clock64() - te0));
+                if (CTRP && P.tmode == 1) atomicAdd(CTRP + 1, (unsigned long long)(clock64() - te0));
                 tc_fence_after();
                 const uint32_t d1 = tmem_base + (uint32_t)(as * C::ACC_COLS);
                 const uint32_t d2 = ACC2 ? d1 + NT : d1;
@@ -362,16 +391,16 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                     uint32_t accum = 0;
                     for (int cb = 0; cb < P.kpt + P.nkb2; ++cb) {
                         const bool sl2 = cb >= P.kpt;
-                        const long long tf0 = (P.ctr && P.tmode == 1) ? clock64() : 0;
+                        const long long tf0 = (CTRP && P.tmode == 1) ? clock64() : 0;
                         mbar_wait(&afull[ai], aphA);
-                        if (P.ctr && P.tmode == 1) atomicAdd(P.ctr + 0, (unsigned long long)(clock64() - tf0));
+                        if (CTRP && P.tmode == 1) atomicAdd(CTRP + 0, (unsigned long long)(clock64() - tf0));
                         tc_fence_after();
                         const uint32_t abuf = smem_u32(smem + ai * 2 * C::A_BUF_BYTES);
                         const int nt = sl2 ? 1 : p.ntaps[0];
                         for (int tap = 0; tap < nt; ++tap) {
-                            const long long tf1 = (P.ctr && P.tmode == 1) ? clock64() : 0;
+                            const long long tf1 = (CTRP && P.tmode == 1) ? clock64() : 0;
                             mbar_wait(&full[s], ph);
-                            if (P.ctr && P.tmode == 1) atomicAdd(P.ctr + 0, (unsigned long long)(clock64() - tf1));
+                            if (CTRP && P.tmode == 1) atomicAdd(CTRP + 0, (unsigned long long)(clock64() - tf1));
                             tc_fence_after();
                             // tap = start offset of (shift + 2) * S rows inside the haloed tile
                             const uint32_t aoff = (uint32_t)(((sl2 ? 0 : p.tap_shift[0][tap]) + 2) * S * BKC * 2);
@@ -395,15 +424,15 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                 } else {
                 const int nkb1 = p.ntaps[tile % P.nphase] * P.kpt;
                 for (int kb = 0; kb < nkb1 + P.nkb2; ++kb) {
-                    const long long tf0 = (P.ctr && P.tmode == 1) ? clock64() : 0;
-                    if (!(P.dbg & 16)) mbar_wait(&full[s], ph);
-                    if (P.ctr && P.tmode == 1) atomicAdd(P.ctr + 0, (unsigned long long)(clock64() - tf0));
+                    const long long tf0 = (CTRP && P.tmode == 1) ? clock64() : 0;
+                    if (!DBGF(16)) mbar_wait(&full[s], ph);
+                    if (CTRP && P.tmode == 1) atomicAdd(CTRP + 0, (unsigned long long)(clock64() - tf0));
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
                     const uint64_t ah = make_desc<BKC>(sa), al = make_desc<BKC>(sa + A_TILE);
                     const uint64_t bh = make_desc<BKC>(sa + 2 * A_TILE), bl = make_desc<BKC>(sa + 2 * A_TILE + C::B_TILE_BYTES);
                     const bool slab2 = kb >= nkb1;
-                    const uint32_t d = (P.dbg & 32) ? tmem_base : (slab2 ? d2 : d1);
+                    const uint32_t d = DBGF(32) ? tmem_base : (slab2 ? d2 : d1);
                     uint32_t accum = slab2 ? (ACC2 ? acc2 : 1u) : acc1;
 #pragma unroll
                     for (int k = 0; k < BKC / 16; ++k) {
@@ -414,14 +443,14 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                         accum = 1u;
                     }
                     if (slab2) acc2 = 1u; else acc1 = 1u;
-                    if (!(P.dbg & 16)) commit(&empty[s]);   // frees the smem stage (of both CTAs) when these MMAs have read it
+                    if (!DBGF(16)) commit(&empty[s]);   // frees the smem stage (of both CTAs) when these MMAs have read it
                     if (++s == NSTAGE) { s = 0; ph ^= 1; }
                 }
                 }
                 commit(&tfull[as]);      // accumulator complete
                 if (++as == NACC) { as = 0; aph ^= 1; }
             }
-            if (P.ctr && P.tmode == 1) atomicAdd(P.ctr + 2, (unsigned long long)(clock64() - tm0));
+            if (CTRP && P.tmode == 1) atomicAdd(CTRP + 2, (unsigned long long)(clock64() - tm0));
         }
     } else {
         // ============================== epilogue (warps 2..9) ==============================
@@ -439,8 +468,11 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             if (TEAM) asm volatile("bar.sync %0, 128;" ::"r"(6 + hf) : "memory");
             else epi_barw<ETH>();
         };
-        const int ch0 = TEAM ? 0 : hf;           // first chunk and chunk step of this thread
-        constexpr int CHS = TEAM ? 1 : NG;
+        // chunks of this thread: [ch0, chE) in steps of CHS
+        const int ch0 = TEAM ? 0 : (C::CONTIG ? hf * (NCH / NG) : hf);
+        constexpr int CHS = (TEAM || C::CONTIG) ? 1 : NG;
+        const int chE = C::CONTIG ? ch0 + NCH / NG : NCH;
+        constexpr bool PIPE = C::PIPE;
         const int mrow = eq * 32 + lane;
         const int act = p.act;
         const float inv_cnt = 1.0f / (float)(HJ * (GS ? GS : 1));
@@ -449,30 +481,38 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
         uint32_t aph = 0;
         long long tlap = 0;
         auto lap = [&](int k) {
-            if (P.ctr && P.tmode == 2 && etid == 0) {
+            if (CTRP && P.tmode == 2 && etid == 0) {
                 const long long now = clock64();
-                atomicAdd(P.ctr + k, (unsigned long long)(now - tlap));
+                atomicAdd(CTRP + k, (unsigned long long)(now - tlap));
                 tlap = now;
             }
         };
         // writer slot of chunk ch in the row-partial table (NG = 2: the warp group; NG = 4: position of the chunk in its group)
-        auto pslot = [&](int ch) { return TEAM ? 0 : (NG == 2 ? hf : (ch % C::CPG)); };
+        auto pslot = [&](int ch) {
+            (void)ch;
+            return (TEAM || C::PSLOTS == 1) ? 0 : hf % C::PSLOTS;
+        };
         // TE: staging tiles of this half of the epilogue warps and the thread that issues its bulk stores
         uint8_t* const sF = stg + hf * C::STG_HALF_BYTES;
         uint8_t* const sH = sF + 128 * CW * 4;
         uint8_t* const sL = sH + 128 * CW * 2;
+        uint8_t* const sIh = PIPE ? sL + 128 * CW * 2 : sH;    // identity planes in: own tiles (PIPE) or in place
+        uint8_t* const sIl = PIPE ? sIh + 128 * CW * 2 : sL;
         const bool st_leader = (etid0 & 127) == 0;
         // free the staging tiles of this half (the bulk stores of the previous chunk have read them)
         auto stage_acquire = [&]() {
+            const long long ta = (CTRP && P.tmode == 3 && etid0 == 0) ? clock64() : 0;
             if (st_leader) bulk_wait_read0();
+            if (CTRP && P.tmode == 3 && etid0 == 0) atomicAdd(CTRP + 0, (unsigned long long)(clock64() - ta));   // store drain
             half_bar(hf);
+            if (CTRP && P.tmode == 3 && etid0 == 0) { atomicAdd(CTRP + 1, (unsigned long long)(clock64() - ta)); atomicAdd(CTRP + 3, 1ull); }   // + barrier
         };
         // make the staged rows visible to the TMA engine and write them out as boxes of the tile
         auto stage_release = [&](const CUtensorMap* mf, const CUtensorMap* mh, const CUtensorMap* ml, int c0, int op, int r0) {
-            if (P.dbg & 2048) r0 = (int)blockIdx.x * S;   // timing probe: every CTA keeps storing to its own first tile (same TMA work, no new HBM lines)
+            if (DBGF(2048)) r0 = (int)blockIdx.x * S;   // timing probe: every CTA keeps storing to its own first tile (same TMA work, no new HBM lines)
             fence_async_smem();
             half_bar(hf);
-            if (st_leader && !(P.dbg & 512)) {   // dbg 512: results staged but never stored (timing probe)
+            if (st_leader && !DBGF(512)) {   // dbg 512: results staged but never stored (timing probe)
                 if (p.ostride == 2) {
                     if (mf) tma_store_4d(mf, sF, c0, op, 0, r0);
                     if (mh) { tma_store_4d(mh, sH, c0, op, 0, r0); tma_store_4d(ml, sL, c0, op, 0, r0); }
@@ -484,6 +524,27 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                 bulk_commit();
             }
         };
+        // TE: the epilogue's own INPUT tiles -- the saved yhat of a GroupNorm-backward launch and the identity /
+        // residual planes -- come in through the same staging tiles by TMA loads (whole 128-byte lines, asynchronous)
+        // instead of per-row 16-byte global loads, which cost one L1 wavefront per row and instruction; every thread
+        // then reads (and later overwrites, in place) only its own row
+        uint32_t lph = 0;
+        const uint32_t box_rows = (uint32_t)(S * HJ);
+        auto stage_load = [&](const CUtensorMap* mf, const CUtensorMap* mh, const CUtensorMap* ml, int c0, int r0) {
+            if (st_leader) {
+                mbar_expect_tx(&lfull[hf], box_rows * CW * ((mf ? 4u : 0u) + (mh ? 4u : 0u)));
+                const int c1 = AR ? r0 : 0, c2 = AR ? 0 : r0;
+                if (mf) tma_load_3d(sF, mf, &lfull[hf], c0, c1, c2);
+                if (mh) { tma_load_3d(sIh, mh, &lfull[hf], c0, c1, c2); tma_load_3d(sIl, ml, &lfull[hf], c0, c1, c2); }
+            }
+        };
+        auto stage_load_wait = [&]() {
+            const long long ta = (CTRP && P.tmode == 3 && etid0 == 0) ? clock64() : 0;
+            mbar_wait(&lfull[hf], lph);
+            lph ^= 1;
+            if (CTRP && P.tmode == 3 && etid0 == 0) { atomicAdd(CTRP + 2, (unsigned long long)(clock64() - ta)); atomicAdd(CTRP + 4, 1ull); }   // load landed
+        };
+        const bool tl_id = TE && p.ident_hi != nullptr;   // the host only selects TE kernels for unit-stride identity terms
         int it = 0;
         for (int tile = sched0; tile < nsched; tile += sched_step, ++it) {
             if (TEAM) {
@@ -517,21 +578,27 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             const int rg = valid ? r0 + s_loc : 0;                              // global sample (row of R)
             const size_t orow = valid ? (size_t)(r0 + s_loc) * p.Hout + (size_t)(hrow_ * p.ostride + op) : 0;
             const int slab0 = s_loc * G;
-            const long long tq0 = (P.ctr && etid == 0) ? clock64() : 0;
-            if (P.ctr && P.tmode == 2 && etid == 0 && tlap) atomicAdd(P.ctr + 5, (unsigned long long)(tq0 - tlap));   // preamble
+            if (PIPE) {
+                // inputs of this thread group's first chunk: in flight while the accumulator is still being computed
+                // (the input tiles are free: every thread has passed the last input barrier of the previous tile)
+                if (GS && p.gn_bwd) stage_load(&P.mSy, tl_id ? &P.mIh : nullptr, &P.mIl, n0 + ch0 * CW, r0);
+                else if (tl_id) stage_load(nullptr, &P.mIh, &P.mIl, n0 + ch0 * CW, r0);
+            }
+            const long long tq0 = (CTRP && etid == 0) ? clock64() : 0;
+            if (CTRP && P.tmode == 2 && etid == 0 && tlap) atomicAdd(CTRP + 5, (unsigned long long)(tq0 - tlap));   // preamble
             mbar_wait(&tfull[as], aph);
-            const long long tq1 = (P.ctr && etid == 0) ? clock64() : 0;
+            const long long tq1 = (CTRP && etid == 0) ? clock64() : 0;
             tlap = tq1;
-            if (P.ctr && P.tmode == 2 && etid == 0) atomicAdd(P.ctr + 0, (unsigned long long)(tq1 - tq0));
+            if (CTRP && P.tmode == 2 && etid == 0) atomicAdd(CTRP + 0, (unsigned long long)(tq1 - tq0));
             tc_fence_after();
             ebar();
-            if (P.dbg & 1) {
+            if (DBGF(1)) {
                 // main-loop-only timing runs: results are garbage
                 tc_fence_before();
                 ebar();
                 if (etid == 0) {
                     if (CG == 2) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
-                    if (P.ctr) atomicAdd(P.ctr + 6, 1ull);
+                    if (CTRP) atomicAdd(CTRP + 6, 1ull);
                 }
                 if (!TEAM && ++as == NACC) { as = 0; aph ^= 1; }
                 continue;
@@ -543,7 +610,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             if (C::INL_FLOATS && p.inl_mode == 1) {
                 // the convolution itself has K = taps*D <= 70: compute it here and park it in the (unused)
                 // accumulator so that the GroupNorm passes below run unchanged
-                for (int ch = ch0; ch < NCH; ch += CHS) {
+                for (int ch = ch0; ch < chE; ch += CHS) {
 #pragma unroll
                     for (int j = 0; j < CW; ++j) v[j] = 0.f;
                     inline_conv<NT, CW>(p, sinl, ch, rg, hrow, HJ, valid, v);
@@ -555,7 +622,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             if (GS && p.gn_fwd) {
                 // ---- pass 1: per-row sums of y = acc + bias and y^2 for every group
 #pragma unroll 1
-                for (int ch = ch0; ch < NCH; ch += CHS) {
+                for (int ch = ch0; ch < chE; ch += CHS) {
                     tmem_ldw<CW>(tacc + ch * CW, v);
                     constexpr int GPC = (GS && GS < CW) ? CW / GS : 1;   // groups per chunk
                     float s1[GPC], s2[GPC];
@@ -622,11 +689,11 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                 const float* eT = p.embT ? p.embT + (size_t)tt * p.ldeT + p.eoff + n0 : nullptr;
                 const float* eR = (p.embR && valid && rg < p.n_cond) ? p.embR + (size_t)rg * p.ldeR + p.eoff + n0 : nullptr;
                 const float* idp = p.ident ? p.ident + orow * p.ldi + n0 : nullptr;
-                const __nv_bfloat16* idh = p.ident_hi ? p.ident_hi + orow * p.ldi + n0 : nullptr;
-                const __nv_bfloat16* idl = p.ident_hi ? p.ident_lo + orow * p.ldi + n0 : nullptr;
+                const __nv_bfloat16* idh = (!TE && p.ident_hi) ? p.ident_hi + orow * p.ldi + n0 : nullptr;
+                const __nv_bfloat16* idl = (!TE && p.ident_hi) ? p.ident_lo + orow * p.ldi + n0 : nullptr;
                 const float* adp = p.addend ? p.addend + orow * p.ldad + n0 : nullptr;
 #pragma unroll 1
-                for (int ch = ch0; ch < NCH; ch += CHS) {
+                for (int ch = ch0; ch < chE; ch += CHS) {
                     tmem_ldw<CW>(tacc + ch * CW, v);
                     add_ldsw<CW>(scol + ch * CW, v);   // + bias
                     if (GS && p.gn_fwd) {
@@ -641,13 +708,21 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
 #pragma unroll
                         for (int j = 0; j < CW; ++j)
                             v[j] = (v[j] - mu[GPC2 > 1 ? j / (CW / GPC2) : 0]) * rsd[GPC2 > 1 ? j / (CW / GPC2) : 0];   // yhat
-                        if (TE) {
+                        if constexpr (PIPE) {
+                            // yhat is parked over the accumulator chunk it came from until the output tiles are free
+                            // (after the arithmetic below): no extra live registers
+                            tmem_stw<CW>(tacc + ch * CW, v);
+                        } else if (TE) {
                             stage_acquire();
+                            if (tl_id) stage_load(nullptr, &P.mIh, &P.mIl, n0 + ch * CW, r0);
                             stage_f32w<CW>(sF, mrow, v);
-                        } else if (valid && !(P.dbg & 2)) {
+                        } else if (valid && !DBGF(2)) {
                             st_roww<CW>(p.yhat + orow * p.ldy + n0 + ch * CW, v);
                         }
                         act_affinew<CW>(scol + NT + ch * CW, scol + 2 * NT + ch * CW, v, act);
+                    } else if (TE && !PIPE) {
+                        stage_acquire();
+                        if (tl_id) stage_load(nullptr, &P.mIh, &P.mIl, n0 + ch * CW, r0);
                     }
                     if (ACC2) {
                         float w[CW];
@@ -677,24 +752,43 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                         }
                         continue;
                     }
-                    if (eT && !(P.dbg & 8)) add_roww<CW>(eT + ch * CW, v);
-                    if (eR && !(P.dbg & 8)) add_roww<CW>(eR + ch * CW, v);
-                    if (idp && !(P.dbg & 4)) add_roww<CW>(idp + ch * CW, v);
-                    if (idh && !(P.dbg & 4)) add_planesw<CW>(idh + ch * CW, idl + ch * CW, v);
-                    if (adp && !(P.dbg & 4)) add_roww<CW>(adp + ch * CW, v);
+                    if (eT && !DBGF(8)) add_roww<CW>(eT + ch * CW, v);
+                    if (eR && !DBGF(8)) add_roww<CW>(eR + ch * CW, v);
+                    if (idp && !DBGF(4)) add_roww<CW>(idp + ch * CW, v);
+                    if constexpr (TE) {
+                        if (tl_id) {
+                            stage_load_wait();
+                            add_unstage_planesw<CW>(sIh, sIl, mrow, v);
+                        }
+                    } else if (idh && !DBGF(4)) {
+                        add_planesw<CW>(idh + ch * CW, idl + ch * CW, v);
+                    }
+                    if (adp && !DBGF(4)) add_roww<CW>(adp + ch * CW, v);
                     if (TE) {
                         // with GroupNorm the fp32 tile carries yhat, so an fp32 copy of the result (only kept for
                         // identity residuals / SIMT consumers) goes out directly; without it the tile is free
                         const bool gnf = GS && p.gn_fwd;
-                        if (!gnf) stage_acquire();
+                        if (PIPE) {
+                            // one barrier: the previous chunk's stores have drained (output tiles free) and every
+                            // thread has consumed this chunk's identity rows (input tiles free for the next load)
+                            stage_acquire();
+                            if (tl_id && ch + CHS < chE) stage_load(nullptr, &P.mIh, &P.mIl, n0 + (ch + CHS) * CW, r0);
+                        }
                         if (p.out) {
                             if (gnf) { if (valid) st_roww<CW>(p.out + orow * p.ldo + n0 + ch * CW, v); }
                             else stage_f32w<CW>(sF, mrow, v);
                         }
                         if (p.out_hi) stage_planesw<CW>(sH, sL, mrow, v);
+                        if constexpr (PIPE) {
+                            if (gnf) {
+                                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                                tmem_ldw<CW>(tacc + ch * CW, v);
+                                stage_f32w<CW>(sF, mrow, v);
+                            }
+                        }
                         stage_release(gnf ? &P.mSy : (p.out ? &P.mSo : nullptr), p.out_hi ? &P.mSoh : nullptr, &P.mSol,
                                       n0 + ch * CW, op, r0);
-                    } else if (valid && !(P.dbg & 2)) {
+                    } else if (valid && !DBGF(2)) {
                         const size_t o = orow * p.ldo + n0 + ch * CW;
                         if (p.out) st_roww<CW>(p.out + o, v);
                         if (p.out_hi) st_planesw<CW>(p.out_hi + o, p.out_lo + o, v);
@@ -706,30 +800,54 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                 // back over the accumulator and yhat is stashed in spare TMEM columns, so pass 1
                 // (after the slab means are known) touches no global input again.
                 const float* idp = p.ident ? p.ident + orow * p.ldi + n0 : nullptr;
-                const __nv_bfloat16* idh = p.ident_hi ? p.ident_hi + orow * p.ldi + n0 : nullptr;
-                const __nv_bfloat16* idl = p.ident_hi ? p.ident_lo + orow * p.ldi + n0 : nullptr;
+                const __nv_bfloat16* idh = (!TE && p.ident_hi) ? p.ident_hi + orow * p.ldi + n0 : nullptr;
+                const __nv_bfloat16* idl = (!TE && p.ident_hi) ? p.ident_lo + orow * p.ldi + n0 : nullptr;
                 const float* adp = p.addend ? p.addend + orow * p.ldad + n0 : nullptr;
-                const float* yp = p.yhat + orow * p.ldy + n0;
+                const float* yp = TE ? nullptr : p.yhat + orow * p.ldy + n0;
 #pragma unroll 1
-                for (int ch = ch0; ch < NCH; ch += CHS) {
+                for (int ch = ch0; ch < chE; ch += CHS) {
+                    if (TE && !PIPE) {
+                        // yhat (fp32 tile) and the identity planes of this chunk arrive by TMA
+                        stage_acquire();
+                        stage_load(&P.mSy, tl_id ? &P.mIh : nullptr, &P.mIl, n0 + ch * CW, r0);
+                    }
                     tmem_ldw<CW>(tacc + ch * CW, v);
-                    if (idp && !(P.dbg & 4)) add_roww<CW>(idp + ch * CW, v);
-                    if (idh && !(P.dbg & 4)) add_planesw<CW>(idh + ch * CW, idl + ch * CW, v);
-                    if (adp && !(P.dbg & 4)) add_roww<CW>(adp + ch * CW, v);
+                    if (idp && !DBGF(4)) add_roww<CW>(idp + ch * CW, v);
+                    if constexpr (!TE) {
+                        if (idh && !DBGF(4)) add_planesw<CW>(idh + ch * CW, idl + ch * CW, v);
+                    }
+                    if (adp && !DBGF(4)) add_roww<CW>(adp + ch * CW, v);
                     float y[CW];
-                    if (!(P.dbg & 4)) ld_roww<CW>(yp + ch * CW, y);
+                    if constexpr (TE) {
+                        stage_load_wait();
+                        unstage_f32w<CW>(sF, mrow, y);
+                        if (tl_id) add_unstage_planesw<CW>(sIh, sIl, mrow, v);
+                    } else if (!DBGF(4)) ld_roww<CW>(yp + ch * CW, y);
                     else {
 #pragma unroll
                         for (int j = 0; j < CW; ++j) y[j] = 0.5f;
                     }
-                    if (TE) {
+                    uint32_t ph[PIPE ? CW / 2 : 1], pl[PIPE ? CW / 2 : 1];   // raw output planes, packed, until the tiles are free
+                    if (PIPE) {
+                        // every thread holds its inputs: the next chunk's (or, re-reading yhat, pass 1's first) load starts
+                        half_bar(hf);
+                        if (ch + CHS < chE) stage_load(&P.mSy, tl_id ? &P.mIh : nullptr, &P.mIl, n0 + (ch + CHS) * CW, r0);
+                        else if (!C::STASH) stage_load(&P.mSy, nullptr, nullptr, n0 + ch0 * CW, r0);
+                        if (p.out && valid) st_roww<CW>(p.out + orow * p.ldo + n0 + ch * CW, v);   // fp32 copy: not on the default path
+                        if constexpr (PIPE) {
+                            if (p.out_hi) {
+#pragma unroll
+                                for (int k = 0; k < CW / 2; ++k) split_bf16x2(v[2 * k], v[2 * k + 1], ph[k], pl[k]);
+                            }
+                        }
+                    } else if (TE) {
                         if (p.out || p.out_hi) {
-                            stage_acquire();
+                            // in place: every thread overwrites the row it has just read
                             if (p.out) stage_f32w<CW>(sF, mrow, v);
                             if (p.out_hi) stage_planesw<CW>(sH, sL, mrow, v);
                             stage_release(p.out ? &P.mSo : nullptr, p.out_hi ? &P.mSoh : nullptr, &P.mSol, n0 + ch * CW, op, r0);
                         }
-                    } else if (valid && !(P.dbg & 2)) {
+                    } else if (valid && !DBGF(2)) {
                         const size_t o = orow * p.ldo + n0 + ch * CW;
                         if (p.out) st_roww<CW>(p.out + o, v);
                         if (p.out_hi) st_planesw<CW>(p.out_hi + o, p.out_lo + o, v);
@@ -750,6 +868,14 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                     }
                     tmem_stw<CW>(tacc + ch * CW, v);
                     if (C::STASH) tmem_stw<CW>(tstash + ch * CW, y);
+                    if constexpr (PIPE) {
+                        if (p.out_hi) {
+                            // the previous chunk's stores drained while the arithmetic above ran
+                            stage_acquire();
+                            stage_packedw<CW>(sH, sL, mrow, ph, pl);
+                            stage_release(nullptr, &P.mSoh, &P.mSol, n0 + ch * CW, op, r0);
+                        }
+                    }
                     const int g0 = (ch * CW) / (GS ? GS : 1);
 #pragma unroll
                     for (int g = 0; g < GPC; ++g) {
@@ -787,13 +913,26 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                 ebar();
                 lap(2);
 #pragma unroll 1
-                for (int ch = ch0; ch < NCH; ch += CHS) {
+                for (int ch = ch0; ch < chE; ch += CHS) {
                     float y[CW];
+                    if (TE && !PIPE) {
+                        stage_acquire();
+                        if (!C::STASH) stage_load(&P.mSy, nullptr, nullptr, n0 + ch * CW, r0);
+                    }
                     tmem_ldw<CW>(tacc + ch * CW, v);
                     if (C::STASH) {
                         tmem_ldw<CW>(tstash + ch * CW, y);
                     } else {
-                        ld_roww<CW>(yp + ch * CW, y);
+                        if constexpr (TE) {
+                            stage_load_wait();
+                            unstage_f32w<CW>(sF, mrow, y);
+                            if (PIPE) {
+                                half_bar(hf);
+                                if (ch + CHS < chE) stage_load(&P.mSy, nullptr, nullptr, n0 + (ch + CHS) * CW, r0);
+                            }
+                        } else {
+                            ld_roww<CW>(yp + ch * CW, y);
+                        }
                         if (!valid) {
 #pragma unroll
                             for (int j = 0; j < CW; ++j) y[j] = 0.f;
@@ -811,12 +950,16 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                         const int g = GPC3 > 1 ? j / (CW / GPC3) : 0;
                         v[j] = rsd[g] * (v[j] - m1[g] - y[j] * m2[g]);
                     }
-                    if (TE) {
+                    if (PIPE) {
                         stage_acquire();
+                        if (p.gy && valid) st_roww<CW>(p.gy + orow * p.ldg + n0 + ch * CW, v);   // fp32 copy: not on the default path
+                        if (p.gy_hi) stage_planesw<CW>(sH, sL, mrow, v);
+                        stage_release(nullptr, p.gy_hi ? &P.mSgh : nullptr, &P.mSgl, n0 + ch * CW, op, r0);
+                    } else if (TE) {
                         if (p.gy) stage_f32w<CW>(sF, mrow, v);
                         if (p.gy_hi) stage_planesw<CW>(sH, sL, mrow, v);
                         stage_release(p.gy ? &P.mSg : nullptr, p.gy_hi ? &P.mSgh : nullptr, &P.mSgl, n0 + ch * CW, op, r0);
-                    } else if (valid && !(P.dbg & 2)) {
+                    } else if (valid && !DBGF(2)) {
                         const size_t o = orow * p.ldg + n0 + ch * CW;
                         if (p.gy) st_roww<CW>(p.gy + o, v);
                         if (p.gy_hi) st_planesw<CW>(p.gy_hi + o, p.gy_lo + o, v);
@@ -830,14 +973,14 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
             if (etid == 0) {
                 if (CG == 2) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
             }
-            if (P.ctr && etid == 0) {
+            if (CTRP && etid == 0) {
                 if (P.tmode == 1) {
-                    atomicAdd(P.ctr + 3, (unsigned long long)(tq1 - tq0));
-                    atomicAdd(P.ctr + 4, (unsigned long long)(clock64() - tq1));
+                    atomicAdd(CTRP + 3, (unsigned long long)(tq1 - tq0));
+                    atomicAdd(CTRP + 4, (unsigned long long)(clock64() - tq1));
                 } else {
                     lap(4);
                 }
-                atomicAdd(P.ctr + 6, 1ull);
+                atomicAdd(CTRP + 6, 1ull);
             }
             if (!TEAM && ++as == NACC) { as = 0; aph ^= 1; }
         }
@@ -1006,11 +1149,23 @@ int st_map(CUtensorMap* out, const void* base, bool f32, int C, int Hout, int R,
 }
 
 int g_num_sms = 0;
+
+// A/B switches of the kernel variants: read from the environment in -DPMP_DIAG builds only
+int diag_env(const char* name, int dflt) {
+#ifdef PMP_DIAG
+    if (const char* e = getenv(name)) return atoi(e);
+#endif
+    (void)name;
+    return dflt;
+}
 }  // namespace
 // role timers of conv_tc_kernel, enabled with PMP_TC_TIMERS=1: [0] MMA warp waiting for TMA data,
 // [1] MMA warp waiting for a free accumulator (epilogue behind), [2] MMA warp total, [3] epilogue waiting
 // for the accumulator, [4] epilogue busy, [5] TMA producer waiting for a free stage, [6] tiles
 unsigned long long* tc_timer_buffer() {
+#ifndef PMP_DIAG
+    return nullptr;
+#else
     static unsigned long long* buf = nullptr;
     static int on = -1;
     if (on < 0) {
@@ -1020,6 +1175,7 @@ unsigned long long* tc_timer_buffer() {
             cudaMemset(buf, 0, 8 * sizeof(unsigned long long));
     }
     return buf;
+#endif
 }
 namespace {
 
@@ -1115,16 +1271,17 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     const bool acc2 = (p.A2 != nullptr || p.A2_hi != nullptr) && !inl_post && (p.bias2 != nullptr || p.gn_fwd);
     // 256-column tiles (CTA pairs only) feed the tensor pipe best; a separate second accumulator does not fit next to them
     static int wide = -1;
-    if (wide < 0) { const char* e = getenv("PMP_TC_WIDE"); wide = e ? atoi(e) : 1; }
+    if (wide < 0) wide = diag_env("PMP_TC_WIDE", 1);
     const int NT = pick_nt(p, wide && (mode == 3 || mode == 4) && !acc2 && !p.inl_x);
     const bool m34 = mode == 3 || mode == 4;
     const int cg = (m34 && NT >= 128 && !p.inl_x) ? 2 : 1;
-    const bool te = m34 && (NT == 64 || ((NT == 128 || NT == 256) && cg == 2)) && p.N >= 64;
+    const bool te = m34 && (NT == 64 || ((NT == 128 || NT == 256) && cg == 2)) && p.N >= 64 &&
+                    !(p.ident_hi && p.ostride != 1);   // identity planes come in by TMA load (unit-stride box maps)
     // 16 epilogue warps on 16-column chunks: measured 5-8 % faster for the GroupNorm-backward epilogues (two TMEM
     // passes, yhat + identity loads), neutral or slower for the forward ones -> path 3 uses them for the former only;
     // path 4 forces them everywhere (A/B switch)
     static int ng4_bwd = -1;
-    if (ng4_bwd < 0) { const char* e = getenv("PMP_TC_NG4_BWD"); ng4_bwd = e ? atoi(e) : 1; }
+    if (ng4_bwd < 0) ng4_bwd = diag_env("PMP_TC_NG4_BWD", 1);
     const bool ng4 = te && (mode == 4 || (mode == 3 && ng4_bwd && p.gn_bwd));
     const int cw = ng4 ? 16 : 32;
     const int S = 128 / p.HJ;
@@ -1133,6 +1290,7 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     P.tilesN = (p.N + NT - 1) / NT;
     P.nphase = p.nphase;
     P.mode4d = p.istride == 2 ? 1 : 0;
+#ifdef PMP_DIAG
     P.ctr = tc_timer_buffer();
     if (P.ctr) {
         // PMP_TC_TIMERS=1|2, optional PMP_TC_TIMER_MATCH="N:C1:g" (g = gn_fwd + 2*gn_bwd) restricts the timers to one shape
@@ -1149,10 +1307,11 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
         if (dbg < 0) { const char* e = getenv("PMP_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
         P.dbg = dbg;
     }
+#endif
     P.ntiles = P.tilesM * P.tilesN * P.nphase;
     P.npairs = ((P.tilesM + 1) / 2) * P.tilesN * P.nphase;
     static int ar_on = -1;
-    if (ar_on < 0) { const char* e = getenv("PMP_TC_AR"); ar_on = e ? atoi(e) : 1; }   // 64-column tiles: measured neutral (-0.4 %), off by default
+    if (ar_on < 0) ar_on = diag_env("PMP_TC_AR", 1);   // 64-column tiles: measured neutral (-0.4 %), off by default
     // A-operand reuse for the stride-1 convs on the 256-column pair tiles and (bit 1 of PMP_TC_AR) the 64-column tiles
     const bool s1conv = p.nphase == 1 && p.istride == 1 && p.ostride == 1;
     const bool ar = m34 && te && s1conv &&
@@ -1205,6 +1364,12 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
             if ((rc = st_map(&P.mSgh, p.gy_hi, false, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os, cw, ar))) return rc;
             if ((rc = st_map(&P.mSgl, p.gy_lo, false, p.N, p.Hout, p.R, p.ldg, S, p.HJ, os, cw, ar))) return rc;
         }
+        // epilogue inputs that come in by TMA load: saved yhat (GroupNorm backward), identity planes
+        if (p.yhat && p.gn_bwd && (rc = st_map(&P.mSy, p.yhat, true, p.N, p.Hout, p.R, p.ldy, S, p.HJ, os, cw, ar))) return rc;
+        if (p.ident_hi) {
+            if ((rc = st_map(&P.mIh, p.ident_hi, false, p.N, p.Hout, p.R, p.ldi, S, p.HJ, os, cw, ar))) return rc;
+            if ((rc = st_map(&P.mIl, p.ident_lo, false, p.N, p.Hout, p.R, p.ldi, S, p.HJ, os, cw, ar))) return rc;
+        }
     }
     const bool gn = p.gn_fwd || p.gn_bwd;
     const int gs = gn ? p.N / 8 : 0;
@@ -1244,7 +1409,7 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     if (NT == 64) {
         if (te) {
             static int team = -1;
-            if (team < 0) { const char* e = getenv("PMP_TC_TEAM"); team = e ? atoi(e) : 1; }
+            if (team < 0) team = diag_env("PMP_TC_TEAM", 1);
             if (team && !acc2) {
                 if (gs == 8) return launch_t<64, 8, false, 1, true, 2, true>(P, st);
                 return launch_t<64, 0, false, 1, true, 2, true>(P, st);

@@ -218,7 +218,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const __grid_co
                 scol[2 * NT + i] = p.beta ? __ldg(p.beta + n0 + i) : 0.f;
             }
             const int h = mrow / S, s_loc = mrow - h * S;
-            const bool valid = (h < Hl) && (r0 + s_loc < p.R) && !(P.dbg & 1);
+            const bool valid = (h < Hl) && (r0 + s_loc < p.R) 
+#ifdef PMP_DIAG
+                               && !(P.dbg & 1)
+#endif
+                ;
             const int rg = valid ? r0 + s_loc : 0;
             const size_t orow = valid ? (size_t)rg * p.Hout + h : 0;
             const int slab0 = ti * 128 + s_loc * G;
@@ -535,11 +539,13 @@ int launch_conv_tc2(const ConvP& p, cudaStream_t st) {
     P.ntiles = P.tilesM * P.tilesN;
     P.nch1 = p.C1 / BK2;
     P.nch2 = p.A2 ? p.C2 / BK2 : 0;
+#ifdef PMP_DIAG
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("PMP_TC2_DBG"); dbg = e ? atoi(e) : 0; }
         P.dbg = dbg;
     }
+#endif
     int rc;
     if ((rc = act_map2(&P.mA1h, p.A1_hi, p.C1, p.Hin, p.R, p.lda1, S))) return rc;
     if ((rc = act_map2(&P.mA1l, p.A1_lo, p.C1, p.Hin, p.R, p.lda1, S))) return rc;

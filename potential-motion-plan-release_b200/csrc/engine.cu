@@ -24,6 +24,9 @@ unsigned long long* tc_timer_buffer();
 
 static thread_local char g_err[1024] = "";
 static std::atomic<uint64_t> g_launches{0};
+// pmp_set_option("uncond_dedup", 0) makes same-network compositions evaluate the unconditional half once per
+// potential instead of once (more work, bit-identical results; the equivalence test uses it)
+static std::atomic<int> g_uncond_dedup{1};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -144,7 +147,11 @@ struct pmp_model {
     float* hidb = nullptr; size_t hidb_n = 0;   // cfg3 per step hidden [R][nblk*hid]
     float* ws = nullptr; size_t ws_n = 0;       // activation workspace (floats)
     int row_chunk = 8192;   // rows of the CFG batch per pass (workspace ~1.8 MB per row for the Maze2D U-Net, grown on demand)
+#ifdef PMP_DIAG
     bool keep_fp32 = getenv("PMP_KEEP_FP32") != nullptr;   // diagnostics: fp32 copies of every activation / gradient
+#else
+    bool keep_fp32 = false;
+#endif
     int gemm_path = 3;   // 0 fp32 SIMT, 1 tcgen05 single CTA, 2 operand reuse, 3 CTA pairs + TMA-store epilogue (default)
     std::map<std::string, std::pair<float*, int64_t>> dbg;
     bool has_down(int L) const { return !(L >= nl - 1 || L >= arch.down_times); }
@@ -154,12 +161,27 @@ struct pmp_model {
 
 namespace pmp {
 
-static int grow(float** p, size_t* cur, size_t need) {
+// Entry points select the model's device and put the caller's current device back on return.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Per-model scratch buffers grow in STREAM ORDER (cudaFreeAsync / cudaMallocAsync on the caller's stream): work already
+// queued on that stream keeps its buffer until it has run, and nothing synchronises the device.  pmp_model_reserve
+// sizes them up front so that a steady workload never allocates inside a call at all.
+static int grow(float** p, size_t* cur, size_t need, cudaStream_t st) {
     if (*cur >= need) return 0;
-    if (*p) PMP_CUDA_OK(cudaFree(*p));
+    if (*p) PMP_CUDA_OK(cudaFreeAsync(*p, st));
     *p = nullptr;
     *cur = 0;
-    PMP_CUDA_OK(cudaMalloc((void**)p, need * sizeof(float)));
+    PMP_CUDA_OK(cudaMallocAsync((void**)p, need * sizeof(float), st));
     *cur = need;
     return 0;
 }
@@ -1049,7 +1071,7 @@ static int eps_rows(pmp_model* m, const float* x, const int64_t* t, const float*
     int rc;
     const int Rc_max = R < chunk ? R : chunk;
     const size_t need = workspace_floats(m, Rc_max, H);
-    if ((rc = grow(&m->ws, &m->ws_n, need))) return rc;
+    if ((rc = grow(&m->ws, &m->ws_n, need, st))) return rc;
     const int nblk = (int)m->blocks.size();
     for (int r0 = 0; r0 < R; r0 += chunk) {
         const int Rc = (R - r0) < chunk ? (R - r0) : chunk;
@@ -1061,8 +1083,8 @@ static int eps_rows(pmp_model* m, const float* x, const int64_t* t, const float*
             c.embRow = wall_tab ? wall_tab + (size_t)r0 * m->Ctot : nullptr;
         } else {
             // per-step block embeddings: E = W2 * act(Ht[t] + Hw[r]) + b2
-            if ((rc = grow(&m->hidb, &m->hidb_n, (size_t)chunk * nblk * m->hid))) return rc;
-            if ((rc = grow(&m->embE, &m->embE_n, (size_t)chunk * m->Ctot))) return rc;
+            if ((rc = grow(&m->hidb, &m->hidb_n, (size_t)chunk * nblk * m->hid, st))) return rc;
+            if ((rc = grow(&m->embE, &m->embE_n, (size_t)chunk * m->Ctot, st))) return rc;
             const float* Hw = (wall_tab && nc > 0) ? wall_tab + (size_t)r0 * nblk * m->hid : nullptr;
             if ((rc = launch_cfg3_hidden(m->embT, c.t, m->arch.n_timesteps - 1, Hw, Hw ? nc : 0, Rc, nblk * m->hid,
                                          m->arch.act, m->hidb, st)))
@@ -1117,7 +1139,7 @@ int pmp_model_create(const pmp_arch* arch, int device, pmp_model** out) {
         set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, p.major, p.minor);
         return PMP_ERR_CUDA;
     }
-    PMP_CUDA_OK(cudaSetDevice(device));
+    DeviceGuard guard(device);
     pmp_model* m = new pmp_model();
     m->arch = *arch;
     m->device = device;
@@ -1128,7 +1150,7 @@ int pmp_model_create(const pmp_arch* arch, int device, pmp_model** out) {
 
 void pmp_model_destroy(pmp_model* m) {
     if (!m) return;
-    cudaSetDevice(m->device);
+    DeviceGuard guard(m->device);
     if (m->arena16) cudaFree(m->arena16);
     float* bufs[] = {m->arena, m->temb_tab, m->embT, m->embR, m->embE, m->hidb, m->ws};
     for (float* b : bufs)
@@ -1148,7 +1170,7 @@ int pmp_model_set_weight(pmp_model* m, const char* key, const float* data, const
     }
     t.v.resize((size_t)n);
     if (on_device) {
-        PMP_CUDA_OK(cudaSetDevice(m->device));
+        DeviceGuard guard(m->device);
         PMP_CUDA_OK(cudaMemcpy(t.v.data(), data, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
     } else {
         memcpy(t.v.data(), data, (size_t)n * sizeof(float));
@@ -1160,7 +1182,7 @@ int pmp_model_set_weight(pmp_model* m, const char* key, const float* data, const
 
 int pmp_model_finalize(pmp_model* m) {
     PMP_REQUIRE(m, "null model");
-    PMP_CUDA_OK(cudaSetDevice(m->device));
+    DeviceGuard guard(m->device);
     return finalize_model(m);
 }
 
@@ -1183,7 +1205,7 @@ int pmp_wall_embed(pmp_model* m, const float* walls, int B, int wall_len, float*
     PMP_REQUIRE(m && m->finalized, "model not finalized");
     PMP_REQUIRE(wall_len > 0 && wall_len % m->arch.vit_token_dim == 0, "wall vector length %d is not a multiple of %d",
                 wall_len, m->arch.vit_token_dim);
-    PMP_CUDA_OK(cudaSetDevice(m->device));
+    DeviceGuard guard(m->device);
     return launch_vit(m->vit, walls, B, wall_len / m->arch.vit_token_dim, wemb, (cudaStream_t)stream);
 }
 
@@ -1192,9 +1214,9 @@ int pmp_unet_eps(pmp_model* m, const float* x, const int64_t* t, const float* we
     PMP_REQUIRE(m && m->finalized, "model not finalized");
     PMP_REQUIRE(x && t && eps && R >= 1 && n_cond >= 0 && n_cond <= R, "bad argument");
     PMP_REQUIRE(n_cond == 0 || wemb, "wemb required for conditional rows");
-    PMP_CUDA_OK(cudaSetDevice(m->device));
+    DeviceGuard guard(m->device);
     int rc;
-    if ((rc = grow(&m->embR, &m->embR_n, (size_t)(n_cond > 0 ? n_cond : 1) * wall_table_width(m)))) return rc;
+    if ((rc = grow(&m->embR, &m->embR_n, (size_t)(n_cond > 0 ? n_cond : 1) * wall_table_width(m), (cudaStream_t)stream))) return rc;
     if ((rc = prepare_wall_tables(m, wemb, n_cond, m->embR, (cudaStream_t)stream))) return rc;
     return eps_rows(m, x, t, m->embR, n_cond, R, H, eps, energy, u, (cudaStream_t)stream);
 }
@@ -1239,7 +1261,7 @@ int pmp_sample(const pmp_sample_args* a, void* stream) {
                     a->models[k]->arch.transition_dim, D);
         PMP_REQUIRE(a->wemb_dev[k], "wemb_dev[%d] is null", k);
     }
-    PMP_CUDA_OK(cudaSetDevice(a->models[0]->device));
+    DeviceGuard guard(a->models[0]->device);
     // plans per pass: the CFG pair doubles the rows
     int chunk = aligned_chunk(a->models[0], H);
     for (int k = 1; k < K; ++k)
@@ -1258,7 +1280,7 @@ int pmp_sample(const pmp_sample_args* a, void* stream) {
     for (int k = 0; k < K; ++k)
         PMP_CUDA_OK(cudaMallocAsync((void**)&wtab[k], (size_t)Bc * wall_table_width(a->models[k]) * sizeof(float), st));
     const long tstride = (long)(a->n_steps + 1) * H * D;
-    const bool dedup = getenv("PMP_NO_UNCOND_DEDUP") == nullptr;   // switch for the equivalence test
+    const bool dedup = g_uncond_dedup.load() != 0;
     int rc = 0;
     for (int b0 = 0; b0 < B && !rc; b0 += Bc) {
         const int Bn = (B - b0) < Bc ? (B - b0) : Bc;
@@ -1315,6 +1337,13 @@ int pmp_sample(const pmp_sample_args* a, void* stream) {
     return rc;
 }
 
+int pmp_set_option(const char* name, int value) {
+    PMP_REQUIRE(name, "null option name");
+    if (!strcmp(name, "uncond_dedup")) { g_uncond_dedup.store(value ? 1 : 0); return 0; }
+    set_error("unknown option '%s'", name);
+    return PMP_ERR_ARG;
+}
+
 int pmp_profile_enable(int on) {
     g_prof_on = on != 0;
     return 0;
@@ -1324,7 +1353,9 @@ int pmp_profile_read(int n_classes, double* ms, double* flops, int64_t* launches
     PMP_REQUIRE(ms && flops && launches && n_classes >= 1, "bad argument");
     for (int i = 0; i < n_classes; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
     FILE* dump = nullptr;
+#ifdef PMP_DIAG
     if (const char* path = getenv("PMP_PROFILE_DUMP")) dump = fopen(path, "w");
+#endif
     if (dump) fprintf(dump, "cls,R,Hout,N,C1,C2,taps,flags,ms,algo_tflops\n");
     for (auto& r : g_prof) {
         PMP_CUDA_OK(cudaEventSynchronize(r.b));
@@ -1360,7 +1391,7 @@ int64_t pmp_debug_fetch(pmp_model* m, const char* name, float* host_out, int64_t
     const int64_t n = it->second.second;
     if (host_out) {
         if (capacity < n) return -2;
-        cudaSetDevice(m->device);
+        DeviceGuard guard(m->device);
         if (cudaDeviceSynchronize() != cudaSuccess) return -3;
         if (cudaMemcpy(host_out, it->second.first, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
             return -3;

@@ -316,7 +316,7 @@ __device__ __forceinline__ void act_affine32(const float* gam, const float* bet,
             v[4 * q + 3] = silu_fast(fmaf(g4.w, v[4 * q + 3], b4.w));
         }
     } else {
-#pragma unroll 4
+#pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = act_fwd(gam[j] * v[j] + bet[j], act);
     }
 }
@@ -333,7 +333,7 @@ __device__ __forceinline__ void act_affine_bwd32(const float* gam, const float* 
             g[4 * q + 3] *= silu_bwd_fast(fmaf(g4.w, y[4 * q + 3], b4.w)) * g4.w;
         }
     } else {
-#pragma unroll 4
+#pragma unroll
         for (int j = 0; j < 32; ++j) g[j] *= act_bwd(gam[j] * y[j] + bet[j], act) * gam[j];
     }
 }
@@ -459,7 +459,7 @@ __device__ __forceinline__ void act_affinew(const float* gam, const float* bet, 
             v[4 * q + 3] = silu_fast(fmaf(g4.w, v[4 * q + 3], b4.w));
         }
     } else {
-#pragma unroll 4
+#pragma unroll
         for (int j = 0; j < CW; ++j) v[j] = act_fwd(gam[j] * v[j] + bet[j], act);
     }
 }
@@ -475,7 +475,7 @@ __device__ __forceinline__ void act_affine_bwdw(const float* gam, const float* b
             g[4 * q + 3] *= silu_bwd_fast(fmaf(g4.w, y[4 * q + 3], b4.w)) * g4.w;
         }
     } else {
-#pragma unroll 4
+#pragma unroll
         for (int j = 0; j < CW; ++j) g[j] *= act_bwd(gam[j] * y[j] + bet[j], act) * gam[j];
     }
 }
@@ -507,6 +507,50 @@ __device__ __forceinline__ void stage_planesw(uint8_t* thi, uint8_t* tlo, int r,
         for (int k = 0; k < 4; ++k) split_bf16x2(v[8 * c + 2 * k], v[8 * c + 2 * k + 1], h[k], l[k]);
         *reinterpret_cast<uint4*>(rh + ((c ^ x) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(rl + ((c ^ x) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+// planes that were split earlier (packed BF16 pairs kept in registers) into the two plane tiles
+template <int CW>
+__device__ __forceinline__ void stage_packedw(uint8_t* thi, uint8_t* tlo, int r, const uint32_t (&h)[CW / 2], const uint32_t (&l)[CW / 2]) {
+    constexpr int RB = CW * 2;
+    uint8_t* rh = thi + r * RB;
+    uint8_t* rl = tlo + r * RB;
+    const int x = swz_xor<RB>(r);
+#pragma unroll
+    for (int c = 0; c < RB / 16; ++c) {
+        *reinterpret_cast<uint4*>(rh + ((c ^ x) << 4)) = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+        *reinterpret_cast<uint4*>(rl + ((c ^ x) << 4)) = make_uint4(l[4 * c], l[4 * c + 1], l[4 * c + 2], l[4 * c + 3]);
+    }
+}
+// the reverse direction: a row of a staging tile that a TMA LOAD filled (same swizzled layouts)
+template <int CW>
+__device__ __forceinline__ void unstage_f32w(const uint8_t* tile, int r, float (&v)[CW]) {
+    constexpr int RB = CW * 4;
+    const uint8_t* row = tile + r * RB;
+    const int x = swz_xor<RB>(r);
+#pragma unroll
+    for (int c = 0; c < RB / 16; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(row + ((c ^ x) << 4));
+        v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+    }
+}
+// v[j] += hi[j] + lo[j] from the two BF16 plane tiles
+template <int CW>
+__device__ __forceinline__ void add_unstage_planesw(const uint8_t* thi, const uint8_t* tlo, int r, float (&v)[CW]) {
+    constexpr int RB = CW * 2;
+    const uint8_t* rh = thi + r * RB;
+    const uint8_t* rl = tlo + r * RB;
+    const int x = swz_xor<RB>(r);
+#pragma unroll
+    for (int c = 0; c < RB / 16; ++c) {
+        const uint4 h = *reinterpret_cast<const uint4*>(rh + ((c ^ x) << 4));
+        const uint4 l = *reinterpret_cast<const uint4*>(rl + ((c ^ x) << 4));
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[8 * c + 2 * k] += __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
+            v[8 * c + 2 * k + 1] += __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u);
+        }
     }
 }
 template <int NTHREADS>

@@ -170,7 +170,7 @@ def plan_envs_multi_horizon(policy, starts, goals, walls, env_boxes, hext, horiz
     obs_h, valid_h, nchk_h = [], [], []
     for ho in horizons:
         cond = {0: rep(starts).astype(np.float32), ho - 1: rep(goals).astype(np.float32)}
-        if hasattr(policy, 'call_multi_horizon'):
+        if hasattr(policy, 'diffusion_model_list'):     # PolicyCompose (the base Policy also has call_multi_horizon)
             traj = policy(cond, wl)[1]
         else:
             policy.diffusion_model.horizon = ho

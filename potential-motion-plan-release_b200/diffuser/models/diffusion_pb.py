@@ -37,6 +37,7 @@ class GaussianDiffusionPB(nn.Module):
         self.manual_loss_weights = diff_config.get('manual_loss_weights', {})
         self.var_temp = 1.0 if self.energy_mode else 0.5
         self.n_timesteps = int(n_timesteps)
+        self.model.n_timesteps = self.n_timesteps   # forward() and the loops share one engine / time table
         self.clip_denoised = clip_denoised
         self.predict_epsilon = predict_epsilon
         assert predict_epsilon and loss_type == 'l2'

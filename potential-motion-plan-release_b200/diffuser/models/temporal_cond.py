@@ -135,14 +135,21 @@ class TemporalUnet_WCond(nn.Module):
         self.final_conv = nn.Sequential(_conv_block(dim, dim), nn.Conv1d(dim, transition_dim, 1))
         self._engine = None
         self._engine_sig = None
+        # length of the diffusion schedule the time-embedding table is built for; GaussianDiffusionPB.__init__
+        # sets it to its own n_timesteps so that forward() and the sampling loops share one engine
+        self.n_timesteps = 100
 
     # ------------------------------------------------------------------ engine plumbing
     def _signature(self):
         ps = list(self.parameters())
         return (ps[0].device, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps[:4]))
 
-    def engine(self, n_timesteps=100):
+    def engine(self, n_timesteps=None):
         """the pmp_b200.UnetEngine holding this module's current weights (rebuilt when they change)"""
+        if n_timesteps is None:
+            n_timesteps = self.n_timesteps
+        n_timesteps = int(n_timesteps)
+        self.n_timesteps = n_timesteps
         sig = (self._signature(), n_timesteps)
         if self._engine is None or self._engine_sig != sig:
             dev = next(self.parameters()).device

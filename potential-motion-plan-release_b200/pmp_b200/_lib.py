@@ -68,6 +68,7 @@ _PROTOS = {
     "pmp_pick_first_valid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
     "pmp_launch_count": (C.c_uint64, []),
+    "pmp_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "pmp_profile_enable": (C.c_int, [C.c_int]),
     "pmp_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pmp_debug_counters": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
@@ -120,6 +121,11 @@ def launch_count():
     return int(lib().pmp_launch_count())
 
 
+def set_option(name, value):
+    """library-wide options: 'uncond_dedup' (default 1) -- same-network compositions share the unconditional half"""
+    _check(lib().pmp_set_option(name.encode(), int(value)))
+
+
 def profile_enable(on=True):
     _check(lib().pmp_profile_enable(1 if on else 0))
 
@@ -141,10 +147,12 @@ class UnetEngine:
         dev = torch.device(device)
         if dev.type != "cuda":
             raise PmpError("the planning hot path runs on a B200 only (got device %s); no CPU fallback" % dev)
+        if dev.index is None:    # torch.device('cuda') means the CURRENT device, not device 0
+            dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         self.arch = make_arch(arch_kwargs, n_timesteps)
         self.h = C.c_void_p()
-        _check(lib().pmp_model_create(C.byref(self.arch), dev.index or 0, C.byref(self.h)))
+        _check(lib().pmp_model_create(C.byref(self.arch), dev.index, C.byref(self.h)))
         self.load(state_dict, prefix)
 
     def load(self, state_dict, prefix=""):
@@ -175,7 +183,13 @@ class UnetEngine:
         """x [R,H,D], t [R] long, wemb [n_cond,64] -> eps [R,H,D]; rows >= n_cond unconditional"""
         x = _f32(x, self.device)
         R, H, D = x.shape
-        t = t.detach().to(self.device, torch.int64).contiguous()
+        t = t.detach().to(torch.int64)
+        # the time-embedding table has arch.n_timesteps rows: an index outside it is an error, not something to clamp
+        # (one small host read; the whole-loop sampler pmp_sample validates its host-side timestep list instead)
+        if t.numel() and (int(t.min()) < 0 or int(t.max()) >= self.arch.n_timesteps):
+            raise PmpError("timestep out of range: the engine was built for n_timesteps=%d, got t in [%d, %d]"
+                           % (self.arch.n_timesteps, int(t.min()), int(t.max())))
+        t = t.to(self.device).contiguous()
         n_cond = R if n_cond is None else int(n_cond)
         wemb = _f32(wemb, self.device) if wemb is not None else None
         eps = torch.empty_like(x)

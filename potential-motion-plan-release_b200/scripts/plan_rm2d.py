@@ -29,13 +29,29 @@ from diffuser.guides.plan_env_b200 import plan_envs
 from diffuser.datasets import DatasetNormalizer
 
 
+def latest_checkpoint(logdir):
+    """state_<epoch>.pt with the highest epoch number, like get_latest_epoch (utils/serialization.py:27-33)"""
+    best, path = -1, None
+    for f in glob.glob(os.path.join(logdir, 'state_*.pt')):
+        try:
+            ep = int(os.path.basename(f)[len('state_'):-len('.pt')])
+        except ValueError:
+            continue
+        if ep > best:
+            best, path = ep, f
+    if path is None:
+        raise FileNotFoundError('no state_<epoch>.pt under %s' % logdir)
+    return path
+
+
 def load_diffusion(family, logdir, device):
     a = workloads.arch(family)
     if logdir:
+        # the two config pickles are trusted input (pickled class objects, exactly like the reference's
+        # utils/serialization.py:98-129); the checkpoint holds tensors only and is loaded as such
         model = pickle.load(open(os.path.join(logdir, 'model_config.pkl'), 'rb'))()
         diffusion = pickle.load(open(os.path.join(logdir, 'diffusion_config.pkl'), 'rb'))(model)
-        ckpt = sorted(glob.glob(os.path.join(logdir, 'state_*.pt')), key=os.path.getmtime)[-1]
-        diffusion.load_state_dict(torch.load(ckpt, map_location='cpu')['ema'])
+        diffusion.load_state_dict(torch.load(latest_checkpoint(logdir), map_location='cpu', weights_only=True)['ema'])
     else:
         torch.manual_seed(0)
         model = TemporalUnet_WCond(**a['unet'])

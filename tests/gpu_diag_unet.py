@@ -85,7 +85,11 @@ def main(fams):
         ctr = (_C.c_double * 8)()
         if pmp_b200.lib().pmp_debug_counters(ctr, 1) == 0 and ctr[6] > 0:
             n = ctr[6]
-            if os.environ.get("PMP_TC_TIMERS") == "2":
+            if os.environ.get("PMP_TC_TIMERS") == "3":
+                print("    staging waits (cycles, group 0 leader) [%s]: store-drain %.0f  acquire(total) %.0f per acquire (%d) | load-wait %.0f per load (%d) | tiles %d" % (
+                    os.environ.get("PMP_TC_TIMER_MATCH", "all"), ctr[0] / max(ctr[3], 1), ctr[1] / max(ctr[3], 1), ctr[3],
+                    ctr[2] / max(ctr[4], 1), ctr[4], n))
+            elif os.environ.get("PMP_TC_TIMERS") == "2":
                 print("    epilogue laps per tile (cycles) [%s]: wait_acc %.0f  loop1 %.0f  reduce %.0f  loop2 %.0f  release %.0f  preamble %.0f  (tiles %d)" % (
                     os.environ.get("PMP_TC_TIMER_MATCH", "all"), ctr[0] / n, ctr[1] / n, ctr[2] / n, ctr[3] / n, ctr[4] / n, ctr[5] / n, n))
             else:

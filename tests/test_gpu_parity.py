@@ -238,6 +238,7 @@ a = synth.arch("m2d")
 m = TemporalUnet_WCond(**a["unet"]); m.load_state_dict(unet_ref.synth_weights(a["unet"], 1))
 d = GaussianDiffusionPB(m, **a["diffusion"]).to(DEV).eval(); eng = d.model.engine(100)
 B, H = 24, 48
+##OPT##
 pr = synth.make_problems("m2d", B, 3)
 lo, hi = pr["lo"], pr["hi"]
 start = torch.tensor(synth.normalize(pr["start"], lo, hi), device=DEV); goal = torch.tensor(synth.normalize(pr["goal"], lo, hi), device=DEV)
@@ -248,9 +249,9 @@ x = pmp_b200.sample([eng, eng, eng], [w1, w2, w3], [2.0, 1.5, 1.0], start, goal,
 print(json.dumps({"sha": hashlib.sha256(x.cpu().numpy().tobytes()).hexdigest(), "launches": int(pmp_b200.launch_count())}))
 """ % (ROOT, os.path.join(ROOT, "potential-motion-plan-release_b200"))
     outs = []
-    for env_extra in ({}, {"PMP_NO_UNCOND_DEDUP": "1"}):
-        env = dict(os.environ); env.update(env_extra)
-        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    for dedup in (1, 0):
+        r = subprocess.run([sys.executable, "-c", code.replace("##OPT##", "pmp_b200.set_option('uncond_dedup', %d)" % dedup)],
+                           capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(_json.loads(r.stdout.strip().splitlines()[-1]))
     assert outs[0]["sha"] == outs[1]["sha"], "sharing the unconditional half changed the result"
