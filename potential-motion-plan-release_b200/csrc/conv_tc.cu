@@ -20,7 +20,8 @@
 //     separate accumulator for the forward residual 1x1 conv, CG = 2 CTA pairs (tcgen05 cta_group::2: M = 256 over
 //     the two SMs of a TPC, each CTA stages its own A rows and half of the B rows; 256-column tiles use 32-channel
 //     K blocks / SWIZZLE_64B), TE the TMA-store epilogue (results staged in swizzled shared-memory tiles and written
-//     by cp.async.bulk.tensor stores); NG = 4: 16 epilogue warps on 16-column chunks (GroupNorm-backward launches);
+//     by cp.async.bulk.tensor stores; its inputs -- saved yhat, identity planes -- arrive by TMA loads); NG = 4: 16 epilogue
+//     warps on 16-column chunks (path 4);
 //     TEAM: the two epilogue warp groups take alternate tiles (64-column forward tiles); AR: A-operand reuse -- the
 //     haloed, position-major activation tile of a channel block is loaded once and the taps are descriptor offsets
 //     (stride-1 convs on the 256-column pair tiles).  DESIGN.md 3.1 has the measurements behind these choices.
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(64 + NG * 128, 1) conv_tc_kernel(const __grid_
                         const bool sl2 = cb >= P.kpt;
                         const long long tf0 = (CTRP && P.tmode == 1) ? clock64() : 0;
                         mbar_wait(&afull[ai], aphA);
-                        if (CTRP && P.tmode == 1) atomicAdd(CTRP + 0, (unsigned long long)(clock64() - tf0));
+                        if (CTRP && P.tmode == 1) atomicAdd(CTRP + 7, (unsigned long long)(clock64() - tf0));   // haloed A tile
                         tc_fence_after();
                         const uint32_t abuf = smem_u32(smem + ai * 2 * C::A_BUF_BYTES);
                         const int nt = sl2 ? 1 : p.ntaps[0];
@@ -1277,11 +1278,12 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     const int cg = (m34 && NT >= 128 && !p.inl_x) ? 2 : 1;
     const bool te = m34 && (NT == 64 || ((NT == 128 || NT == 256) && cg == 2)) && p.N >= 64 &&
                     !(p.ident_hi && p.ostride != 1);   // identity planes come in by TMA load (unit-stride box maps)
-    // 16 epilogue warps on 16-column chunks: measured 5-8 % faster for the GroupNorm-backward epilogues (two TMEM
-    // passes, yhat + identity loads), neutral or slower for the forward ones -> path 3 uses them for the former only;
-    // path 4 forces them everywhere (A/B switch)
+    // 16 epilogue warps on 16-column chunks (path 4 forces them everywhere; A/B switch).  Round 1 used them for the
+    // GroupNorm-backward launches (5-8 % faster while those epilogues were the bottleneck); since the epilogue inputs
+    // arrive by TMA and its arrays stay in registers the launches are main-loop bound and 8 warps are 4.5 % faster
+    // over the whole evaluation (same-box A/B, r2j), so path 3 no longer uses them by default
     static int ng4_bwd = -1;
-    if (ng4_bwd < 0) ng4_bwd = diag_env("PMP_TC_NG4_BWD", 1);
+    if (ng4_bwd < 0) ng4_bwd = diag_env("PMP_TC_NG4_BWD", 0);
     const bool ng4 = te && (mode == 4 || (mode == 3 && ng4_bwd && p.gn_bwd));
     const int cw = ng4 ? 16 : 32;
     const int S = 128 / p.HJ;
@@ -1311,11 +1313,11 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     P.ntiles = P.tilesM * P.tilesN * P.nphase;
     P.npairs = ((P.tilesM + 1) / 2) * P.tilesN * P.nphase;
     static int ar_on = -1;
-    if (ar_on < 0) ar_on = diag_env("PMP_TC_AR", 1);   // 64-column tiles: measured neutral (-0.4 %), off by default
+    if (ar_on < 0) ar_on = diag_env("PMP_TC_AR", 3);   // bit 1: 64-column tiles too (+2 % over the evaluation once their main loop had become the limit, r2i)
     // A-operand reuse for the stride-1 convs on the 256-column pair tiles and (bit 1 of PMP_TC_AR) the 64-column tiles
     const bool s1conv = p.nphase == 1 && p.istride == 1 && p.ostride == 1;
     const bool ar = m34 && te && s1conv &&
-                    (((ar_on & 1) && NT == 256) || ((ar_on & 2) && NT == 64 && !p.inl_x && !acc2 && !ng4));
+                    (((ar_on & 1) && NT == 256) || ((ar_on & 2) && NT == 64 && !p.inl_x && !acc2));
     const int bk = (NT == 256 || ar) ? 32 : 64;   // Cfg::BKC
     P.kpt = inl_pre ? 0 : p.C1 / bk;
     P.nkb2 = ((p.A2 || p.A2_hi) && !inl_post) ? p.C2 / bk : 0;
@@ -1374,6 +1376,10 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     const bool gn = p.gn_fwd || p.gn_bwd;
     const int gs = gn ? p.N / 8 : 0;
     if (ar && NT == 64) {
+        if (ng4) {
+            if (gs == 8) return launch_t<64, 8, false, 1, true, 4, false, true>(P, st);
+            return launch_t<64, 0, false, 1, true, 4, false, true>(P, st);
+        }
         if (gs == 8) return launch_t<64, 8, false, 1, true, 2, true, true>(P, st);
         return launch_t<64, 0, false, 1, true, 2, true, true>(P, st);
     }

@@ -93,6 +93,7 @@ def main(fams):
                 print("    epilogue laps per tile (cycles) [%s]: wait_acc %.0f  loop1 %.0f  reduce %.0f  loop2 %.0f  release %.0f  preamble %.0f  (tiles %d)" % (
                     os.environ.get("PMP_TC_TIMER_MATCH", "all"), ctr[0] / n, ctr[1] / n, ctr[2] / n, ctr[3] / n, ctr[4] / n, ctr[5] / n, n))
             else:
+              print("    [afull wait %.0f]" % (ctr[7] / n))
               print("    tc role timers per tile (cycles): mma_wait_tma %.0f  mma_wait_acc %.0f  mma_total %.0f | epi_wait %.0f  epi_busy %.0f | tma_wait_stage %.0f  (tiles %d)" % (
                 ctr[0] / n, ctr[1] / n, ctr[2] / n, ctr[3] / n, ctr[4] / n, ctr[5] / n, n))
         for cls, (pms, pfl, pn) in zip(("simt", "tc"), prof):
