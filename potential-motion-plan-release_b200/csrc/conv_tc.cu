@@ -128,7 +128,7 @@ struct Cfg {
     // AR (A-operand reuse, stride-1 convs on the 256-column pair tiles): the haloed activation tile of a 32-channel
     // block is loaded ONCE, position-major (row = h*S + s), and the taps are descriptor start offsets of S rows;
     // only the weight tiles stream per tap.  Cuts the L2->SM operand traffic of a 5-tap conv by 40 %.
-    static_assert(!AR || ((NT == 256 && CG == 2 && !TEAM) || (NT == 64 && CG == 1)), "A reuse: 256-column pair tiles, 64-column tiles");
+    static_assert(!AR || ((NT == 256 && CG == 2 && !TEAM) || NT == 64), "A reuse: 256-column pair tiles, 64-column tiles");
     static_assert(!AR || !ACC2, "A reuse: one accumulator");
     static constexpr int NA = 2;                        // haloed A buffers
     static constexpr int A_BUF_ROWS = 192;              // (HJ + 4) * S <= 128 + 4 * 16
@@ -163,7 +163,7 @@ struct Cfg {
     static constexpr int RING_BYTES = AR ? (NA * 2 * A_BUF_BYTES + NSTAGE * 2 * B_TILE_BYTES) : NSTAGE * STAGE_BYTES;
     static constexpr int STG_HALF_BYTES = 128 * CW * 4 + 2 * 128 * CW * 2 + (PIPE ? 2 * 128 * CW * 2 : 0);   // F | H | L (| Ih | Il) of one warp group
     static constexpr int STG_BYTES = TE ? NG * STG_HALF_BYTES : 0;
-    static constexpr int INL_FLOATS = NT == 64 ? 5 * 16 * 64 : 0;   // inline small-K conv weights [taps][D<=16][64]
+    static constexpr int INL_FLOATS = (NT == 64 && CG == 1) ? 5 * 16 * 64 : 0;   // inline small-K conv weights [taps][D<=16][64]
     static constexpr int ACC_COLS = NT * (ACC2 ? 2 : 1);
     // two accumulator stages when they fit next to the yhat stash of the GroupNorm-backward epilogue
     static constexpr int NACC = TEAM ? 4 : ((NT != 192 && 2 * ACC_COLS <= 512) ? 2 : 1);
@@ -1275,7 +1275,11 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     if (wide < 0) wide = diag_env("PMP_TC_WIDE", 1);
     const int NT = pick_nt(p, wide && (mode == 3 || mode == 4) && !acc2 && !p.inl_x);
     const bool m34 = mode == 3 || mode == 4;
-    const int cg = (m34 && NT >= 128 && !p.inl_x) ? 2 : 1;
+    // CTA pairs also for the 64-column tiles (no inline small-K conv): a tcgen05.mma costs ~140 cycles here whatever its
+    // N (measured, r2l), so M = 256 per instruction halves the main-loop time of the narrow layers
+    static int pair64 = -1;
+    if (pair64 < 0) pair64 = diag_env("PMP_TC_PAIR64", 1);
+    const int cg = (m34 && !p.inl_x && (NT >= 128 || (NT == 64 && pair64 && p.N == 64))) ? 2 : 1;
     const bool te = m34 && (NT == 64 || ((NT == 128 || NT == 256) && cg == 2)) && p.N >= 64 &&
                     !(p.ident_hi && p.ostride != 1);   // identity planes come in by TMA load (unit-stride box maps)
     // 16 epilogue warps on 16-column chunks (path 4 forces them everywhere; A/B switch).  Round 1 used them for the
@@ -1284,7 +1288,7 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     // over the whole evaluation (same-box A/B, r2j), so path 3 no longer uses them by default
     static int ng4_bwd = -1;
     if (ng4_bwd < 0) ng4_bwd = diag_env("PMP_TC_NG4_BWD", 0);
-    const bool ng4 = te && (mode == 4 || (mode == 3 && ng4_bwd && p.gn_bwd));
+    const bool ng4 = te && !(NT == 64 && cg == 2) && (mode == 4 || (mode == 3 && ng4_bwd && p.gn_bwd));   // the 64-column pair tiles only exist with 8 epilogue warps
     const int cw = ng4 ? 16 : 32;
     const int S = 128 / p.HJ;
     P.e.S = S;
@@ -1375,6 +1379,10 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
     }
     const bool gn = p.gn_fwd || p.gn_bwd;
     const int gs = gn ? p.N / 8 : 0;
+    if (ar && NT == 64 && cg == 2) {
+        if (gs == 8) return launch_t<64, 8, false, 2, true, 2, true, true>(P, st);
+        return launch_t<64, 0, false, 2, true, 2, true, true>(P, st);
+    }
     if (ar && NT == 64) {
         if (ng4) {
             if (gs == 8) return launch_t<64, 8, false, 1, true, 4, false, true>(P, st);
@@ -1411,6 +1419,14 @@ static int launch_conv_tc_mode(const ConvP& p, cudaStream_t st, int mode) {
         if (gs == 32) return launch_t<256, 32, false, 2, true>(P, st);
         if (gs == 64) return launch_t<256, 64, false, 2, true>(P, st);
         return launch_t<256, 0, false, 2, true>(P, st);
+    }
+    if (NT == 64 && cg == 2) {
+        if (!acc2) {
+            if (gs == 8) return launch_t<64, 8, false, 2, true, 2, true>(P, st);
+            return launch_t<64, 0, false, 2, true, 2, true>(P, st);
+        }
+        if (gs == 8) return launch_t<64, 8, true, 2, true>(P, st);
+        return launch_t<64, 0, true, 2, true>(P, st);
     }
     if (NT == 64) {
         if (te) {
