@@ -33,14 +33,25 @@ struct Maze {
     float lox, loy, hix, hiy;
 };
 
+// next float32 above / below a finite one (what nextafterf returns, without its generic slow path)
+__device__ __forceinline__ float f32_up(float f) {
+    if (f == 0.f) return __int_as_float(1);
+    const int b = __float_as_int(f);
+    return __int_as_float(f > 0.f ? b + 1 : b - 1);
+}
+__device__ __forceinline__ float f32_down(float f) {
+    if (f == 0.f) return __int_as_float((int)0x80000001u);
+    const int b = __float_as_int(f);
+    return __int_as_float(f > 0.f ? b - 1 : b + 1);
+}
 __device__ __forceinline__ float strictly_above(double t) {
     float f = __double2float_ru(t);
-    if ((double)f <= t) f = nextafterf(f, INFINITY);
+    if ((double)f <= t) f = isfinite(f) ? f32_up(f) : nextafterf(f, INFINITY);
     return f;
 }
 __device__ __forceinline__ float strictly_below(double t) {
     float f = __double2float_rd(t);
-    if ((double)f >= t) f = nextafterf(f, -INFINITY);
+    if ((double)f >= t) f = isfinite(f) ? f32_down(f) : nextafterf(f, -INFINITY);
     return f;
 }
 
@@ -139,6 +150,133 @@ __global__ void __launch_bounds__(WARPS * 32) maze2d_swept_kernel(
     if (lane == 0) {
         valid[n] = ok_all ? 1 : 0;
         nchk[n] = total;
+    }
+}
+
+// ------------------------------------------------------------------------------ swept check, horizons <= 64
+// Half a warp per trajectory, W consecutive waypoints per lane (H <= 16 W): both trajectories of a warp are evaluated
+// in ONE pass with every lane busy, each waypoint is limit- and wall-tested once (the reference tests interior
+// waypoints twice, as the end of one segment and the start of the next: same truth value, both counted), and the
+// converted walls stay in shared memory for as long as consecutive trajectories name the same environment (the
+// `samples_perprob` candidates of a problem are adjacent).  Blocks walk the batch in a grid-stride loop.
+// K = int(d / eps) interior points per segment: when |b - a|^2 < (1.8 eps)^2 the quotient is < 2 whatever the
+// rounding, the reference's `for k in range(1, K)` is empty, and the square root and the (float64) division are
+// skipped; otherwise the reference's exact operations run.  valid / n_checks are bit-identical to the sequential walk.
+struct SegR {
+    bool ok;
+    int cnt;
+};
+__device__ __forceinline__ SegR m2d_segment(const Maze& e, float2 a, float2 b, bool inl_a, bool inl_b, bool col_a,
+                                            bool col_b, double eps, float thr2, int legacy_div) {
+    SegR r;
+    if (!(inl_a && inl_b)) { r.ok = false; r.cnt = 0; return r; }
+    if (col_a) { r.ok = false; r.cnt = 1; return r; }
+    if (col_b) { r.ok = false; r.cnt = 2; return r; }
+    r.ok = true;
+    r.cnt = 2;
+    const float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y);
+    const float cx = fminf(fmaxf(b.x, e.lox), e.hix), cy = fminf(fmaxf(b.y, e.loy), e.hiy);
+    const float fx = fabsf(__fsub_rn(cx, a.x)), fy = fabsf(__fsub_rn(cy, a.y));
+    const float ss = __fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy));
+    if (ss < thr2) return r;                    // K <= 1: no interior point
+    const float d = __fsqrt_rn(ss);
+    int K;
+    if (legacy_div) K = (int)__ddiv_rn((double)d, eps);
+    else K = (int)__fdiv_rn(d, (float)eps);
+    for (int k = 1; k < K; ++k) {
+        const float coef = (float)__ddiv_rn((double)k, (double)K);
+        const float px = __fadd_rn(a.x, __fmul_rn(coef, dx));
+        const float py = __fadd_rn(a.y, __fmul_rn(coef, dy));
+        if (!m2d_state_fp(e, px, py, r.cnt)) { r.ok = false; return r; }
+    }
+    return r;
+}
+
+template <int W>
+__global__ void __launch_bounds__(WARPS * 32) maze2d_swept16_kernel(
+    const float* __restrict__ traj, const int32_t* __restrict__ env_id, int N, int H, const double* __restrict__ cen,
+    const double* __restrict__ hext, int nw, float lox, float loy, float hix, float hiy, double eps, float thr2,
+    double margin, int legacy_div, uint8_t* __restrict__ valid, int32_t* __restrict__ nchk) {
+    __shared__ float sm[2 * WARPS][4 * MAXW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = lane >> 4, hl = lane & 15;
+    float* const walls = sm[2 * warp + half];
+    Maze e;
+    e.lox = lox; e.loy = loy; e.hix = hix; e.hiy = hiy;
+    e.lo_f = walls; e.hi_f = walls + 2 * MAXW; e.nw = nw;
+    int cur_env = -1;
+    const int npair = (N + 1) >> 1;
+    // the waypoints and the environment id of the NEXT trajectory are requested before the current one is evaluated
+    float2 wn[W];
+    int envn = -1;
+    auto fetch = [&](int pair) {
+        const int n = 2 * pair + half;
+        const bool act = pair < npair && n < N;
+        const float2* t = reinterpret_cast<const float2*>(traj + (size_t)(act ? n : 0) * H * 2);
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            const int idx = hl * W + i;
+            wn[i] = (act && idx < H) ? __ldg(t + idx) : make_float2(0.f, 0.f);
+        }
+        envn = act ? __ldg(env_id + n) : -1;
+    };
+    fetch(blockIdx.x * WARPS + warp);
+    for (int pair = blockIdx.x * WARPS + warp; pair < npair; pair += gridDim.x * WARPS) {
+        const int n = 2 * pair + half;
+        const bool active = n < N;
+        float2 w[W + 1];
+#pragma unroll
+        for (int i = 0; i < W; ++i) w[i] = wn[i];
+        const int env = active ? envn : cur_env;
+        fetch(pair + gridDim.x * WARPS);
+        if (env != cur_env) {
+            // this half-warp's walls: identical double ops to the reference ((c-h)-m, (c+h)+m), then exact float32 thresholds
+            for (int i = hl; i < nw; i += 16) {
+                const double* c = cen + ((size_t)env * nw + i) * 2;
+                const double* h = hext + ((size_t)env * nw + i) * 2;
+                walls[2 * i] = strictly_above(__dsub_rn(__dsub_rn(c[0], h[0]), margin));
+                walls[2 * i + 1] = strictly_above(__dsub_rn(__dsub_rn(c[1], h[1]), margin));
+                walls[2 * MAXW + 2 * i] = strictly_below(__dadd_rn(__dadd_rn(c[0], h[0]), margin));
+                walls[2 * MAXW + 2 * i + 1] = strictly_below(__dadd_rn(__dadd_rn(c[1], h[1]), margin));
+            }
+            cur_env = env;
+        }
+        __syncwarp();
+        bool inl[W + 1], col[W + 1];
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            inl[i] = m2d_valid(e, w[i].x, w[i].y);
+            col[i] = inl[i] && m2d_collides(e, w[i].x, w[i].y);
+        }
+        // the first waypoint of the next lane closes this lane's last segment
+        w[W].x = __shfl_down_sync(0xffffffffu, w[0].x, 1, 16);
+        w[W].y = __shfl_down_sync(0xffffffffu, w[0].y, 1, 16);
+        const unsigned f0 = (inl[0] ? 1u : 0u) | (col[0] ? 2u : 0u);
+        const unsigned fn = __shfl_down_sync(0xffffffffu, f0, 1, 16);
+        inl[W] = (fn & 1u) != 0;
+        col[W] = (fn & 2u) != 0;
+        int part = 0;          // checks of this lane's segments up to and including its first failing one
+        bool failed = false;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const int sgi = hl * W + j;
+            if (active && sgi < H - 1 && !failed) {
+                const SegR r = m2d_segment(e, w[j], w[j + 1], inl[j], inl[j + 1], col[j], col[j + 1], eps, thr2, legacy_div);
+                part += r.cnt;
+                failed = !r.ok;
+            }
+        }
+        // segments after the first failing one are never evaluated by the reference: lanes past the lowest failing lane drop out
+        const unsigned fm = (__ballot_sync(0xffffffffu, failed) >> (16 * half)) & 0xffffu;
+        const int first = fm ? (__ffs(fm) - 1) : 16;
+        int c = (hl <= first) ? part : 0;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o, 16);
+        if (active && hl == 0) {
+            valid[n] = fm ? 0 : 1;
+            nchk[n] = c;
+        }
+        __syncwarp();          // the walls may be rewritten in the next iteration
     }
 }
 
@@ -326,6 +464,33 @@ extern "C" int pmp_colchk_maze2d_swept(const float* traj, const int32_t* env_id,
     PMP_REQUIRE(H >= 2, "trajectory needs >= 2 waypoints");
     PMP_REQUIRE(eps > 0, "collision eps must be > 0");
     if (N == 0) return 0;
+    if (H <= 64) {
+        // half a warp per trajectory, ceil(H / 16) waypoints per lane, persistent blocks
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            PMP_CUDA_OK(cudaGetDevice(&dev));
+            PMP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const int npair = (N + 1) / 2;
+        int blocks = (npair + WARPS - 1) / WARPS;
+        if (blocks > sms * 8) blocks = sms * 8;
+        const double t = 1.8 * eps;
+        const float thr2 = (float)(t * t);
+        const int W = (H + 15) / 16;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (W <= 2)
+            maze2d_swept16_kernel<2><<<blocks, WARPS * 32, 0, st>>>(traj, env_id, N, H, cen, hext, nw, lox, loy, hix, hiy, eps,
+                                                                   thr2, margin, legacy_div, valid, nchk);
+        else if (W == 3)
+            maze2d_swept16_kernel<3><<<blocks, WARPS * 32, 0, st>>>(traj, env_id, N, H, cen, hext, nw, lox, loy, hix, hiy, eps,
+                                                                   thr2, margin, legacy_div, valid, nchk);
+        else
+            maze2d_swept16_kernel<4><<<blocks, WARPS * 32, 0, st>>>(traj, env_id, N, H, cen, hext, nw, lox, loy, hix, hiy, eps,
+                                                                   thr2, margin, legacy_div, valid, nchk);
+        PMP_LAUNCH_OK();
+        return 0;
+    }
     maze2d_swept_kernel<<<(N + WARPS - 1) / WARPS, WARPS * 32, 0, (cudaStream_t)stream>>>(
         traj, env_id, N, H, cen, hext, nw, lox, loy, hix, hiy, eps, margin, legacy_div, valid, nchk);
     PMP_LAUNCH_OK();

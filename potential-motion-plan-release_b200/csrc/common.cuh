@@ -135,6 +135,8 @@ struct ConvP {
     // inl_mode 1: it IS the conv (no MMA slab; first conv / 1x1 seed), added before GroupNorm;
     // inl_mode 2: residual 1x1 conv of the first block, added after GroupNorm (+ bias2)
     const float* inl_x; int inl_ld; int inl_D; int inl_taps; int inl_mode;
+    // the two halves of a CFG batch share one copy of the state: inl_x row = (inl_row0 + row) wrapped at inl_wrap (0: no wrap)
+    int inl_row0; int inl_wrap;
     const float* inl_w;
     // BF16x3 operand planes (v ~= hi + lo) of `out` / `gy`, same [row][ld] indexing, for consumers
     // that run on the tcgen05 core (null when the consumer is a SIMT conv)
@@ -194,10 +196,23 @@ int launch_cfg3_hidden(const float* Ht, const int64_t* t, int tmax, const float*
                        int hid, int act, float* out, cudaStream_t st);
 
 // sampler (step.cu)
+// device-resident state of a running pmp_sample loop (see DynStep in step.cu)
+struct SamplerState {
+    int s;              // index of the current reverse step
+    int pad;
+    uint64_t seed;      // Philox seed
+    uint64_t elem0;     // global element index of the row chunk's first element
+};
+// `state` + `coef_tab` (device, [n_steps][8]) instead of `coef` / seed / draw / elem0: the per-step values are read
+// from device memory (graph replay); the alignment-dependent kernel choice then assumes elem0 % 4 == 0
 int launch_step(int kind, const float* x, const float* const* ec, const float* const* eu,
                 const float* w, int K, int base, const float* coef, const float* noise,
                 uint64_t seed, uint64_t draw, uint64_t elem0, const float* start, const float* goal,
-                float* xo, float* trace, long trace_stride, int B, int H, int D, cudaStream_t st);
+                float* xo, float* trace, long trace_stride, int B, int H, int D, cudaStream_t st,
+                const SamplerState* state = nullptr, const float* coef_tab = nullptr);
+int launch_sampler_begin(SamplerState* state, uint64_t seed, uint64_t elem0, cudaStream_t st);
+int launch_sampler_advance(SamplerState* state, cudaStream_t st);
+int launch_sampler_set_t(const SamplerState* state, const int32_t* t_tab, int64_t* t2, size_t n, cudaStream_t st);
 int launch_init_noise(float* x, const float* noise, uint64_t seed, uint64_t draw, uint64_t elem0,
                       float var_temp, const float* start, const float* goal, float* trace,
                       long trace_stride, int B, int H, int D, cudaStream_t st);

@@ -107,7 +107,9 @@ __device__ __forceinline__ void inline_conv(const ConvP& p, const float* sinl, i
     for (int t = 0; t < p.inl_taps; ++t) {
         const int hh = h + t - half;
         if (hh < 0 || hh >= Hl) continue;
-        const float* xr = p.inl_x + ((size_t)rg * Hl + hh) * p.inl_ld;
+        int xrow = rg + p.inl_row0;
+        if (p.inl_wrap && xrow >= p.inl_wrap) xrow -= p.inl_wrap;
+        const float* xr = p.inl_x + ((size_t)xrow * Hl + hh) * p.inl_ld;
         for (int d = 0; d < p.inl_D; ++d) {
             const float xd = __ldg(xr + d);
             const float4* w = reinterpret_cast<const float4*>(sinl + (t * p.inl_D + d) * NT + ch * CW);

@@ -27,6 +27,8 @@ static std::atomic<uint64_t> g_launches{0};
 // pmp_set_option("uncond_dedup", 0) makes same-network compositions evaluate the unconditional half once per
 // potential instead of once (more work, bit-identical results; the equivalence test uses it)
 static std::atomic<int> g_uncond_dedup{1};
+// pmp_set_option("cuda_graph", 0): pmp_sample launches every kernel of every step from the host (A/B, debugging)
+static std::atomic<int> g_cuda_graph{1};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -153,6 +155,17 @@ struct pmp_model {
     bool keep_fp32 = false;
 #endif
     int gemm_path = 3;   // 0 fp32 SIMT, 1 tcgen05 single CTA, 2 operand reuse, 3 CTA pairs + TMA-store epilogue (default)
+    uint64_t gen = 0;    // bumped whenever something a captured graph bakes in changes (buffers re-allocated, weights, path)
+    // ---- whole-loop sampler (pmp_sample) state owned by the FIRST model of a call: grow-only scratch + graph cache
+    float* s_eps = nullptr; size_t s_eps_n = 0;     // [K][2][Bc][H][D] eps of every potential
+    float* s_x2 = nullptr; size_t s_x2_n = 0;       // duplicated state (only when the first conv cannot share it)
+    float* s_xs = nullptr; size_t s_xs_n = 0;       // state of the row chunk [Bc][H][D]
+    float* s_sg = nullptr; size_t s_sg_n = 0;       // start | goal of the row chunk [2][Bc][D]
+    float* s_wtab = nullptr; size_t s_wtab_n = 0;   // wall tables of the K potentials, back to back
+    float* s_tabs = nullptr; size_t s_tabs_n = 0;   // t2 [2 Bc] int64 | coef_tab [n_steps][8] | t_tab [n_steps] int32 | SamplerState
+    struct GraphEnt { std::vector<uint64_t> key; cudaGraphExec_t exec; uint64_t launches; };   // kernels per replay
+    std::vector<GraphEnt> graphs;
+    cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the caller's may be the legacy default stream)
     std::map<std::string, std::pair<float*, int64_t>> dbg;
     bool has_down(int L) const { return !(L >= nl - 1 || L >= arch.down_times); }
     bool has_up(int ind) const { return !(ind >= nl - 1 || ind < (nl - arch.down_times - 1)); }
@@ -176,8 +189,9 @@ struct DeviceGuard {
 // Per-model scratch buffers grow in STREAM ORDER (cudaFreeAsync / cudaMallocAsync on the caller's stream): work already
 // queued on that stream keeps its buffer until it has run, and nothing synchronises the device.  pmp_model_reserve
 // sizes them up front so that a steady workload never allocates inside a call at all.
-static int grow(float** p, size_t* cur, size_t need, cudaStream_t st) {
+static int grow(float** p, size_t* cur, size_t need, cudaStream_t st, uint64_t* gen = nullptr) {
     if (*cur >= need) return 0;
+    if (gen) ++*gen;
     if (*p) PMP_CUDA_OK(cudaFreeAsync(*p, st));
     *p = nullptr;
     *cur = 0;
@@ -539,6 +553,7 @@ static int finalize_model(pmp_model* m) {
     PMP_CUDA_OK(cudaStreamSynchronize(st));
     cudaFree(tdev);
     m->finalized = true;
+    ++m->gen;
     return 0;
 }
 
@@ -599,6 +614,7 @@ struct Ctx {
     int R, H, n_cond;
     const int64_t* t;
     const float* embRow;   // cfg0: embR rows of this chunk; cfg3: E rows of this chunk
+    int x_row0 = 0, x_wrap = 0;   // the input holds x_wrap rows shared by both CFG halves: row r reads (x_row0 + r) mod x_wrap
     int rc = 0;
     bool tc() const { return m->gemm_path >= 1; }
     float* alloc(size_t n) {
@@ -725,6 +741,7 @@ static void res_fwd(Ctx& c, int bi, const ActP& x, ActP& out) {
     p.out = mid.p; p.ldo = Co; p.out_hi = mid.hi; p.out_lo = mid.lo;
     if (b.Cin <= 16) {   // first block: K = 5*D, evaluated inline in the tensor kernel's epilogue
         p.inl_x = x.p; p.inl_ld = x.ld; p.inl_D = b.Cin; p.inl_taps = 5; p.inl_mode = 1; p.inl_w = m->A(b.cb[0].Wf);
+        p.inl_row0 = c.x_row0; p.inl_wrap = c.x_wrap;
     }
     c.conv(p);
     ConvP q = geom_s1(R, Hl, 5);
@@ -739,6 +756,7 @@ static void res_fwd(Ctx& c, int bi, const ActP& x, ActP& out) {
         q.bias2 = m->A(b.Rbias);
         if (b.Cin <= 16) {
             q.inl_x = x.p; q.inl_ld = x.ld; q.inl_D = b.Cin; q.inl_taps = 1; q.inl_mode = 2; q.inl_w = m->A(b.Rf);
+            q.inl_row0 = c.x_row0; q.inl_wrap = c.x_wrap;
         }
     } else {
         q.ident = x.p; q.ldi = x.ld;
@@ -1062,16 +1080,37 @@ static int aligned_chunk(const pmp_model* m, int H) {
     return chunk;
 }
 
-// eps for R rows given prepared wall tables (rows < n_cond conditional)
-static int eps_rows(pmp_model* m, const float* x, const int64_t* t, const float* wall_tab, int n_cond, int R, int H,
-                    float* eps, float* energy, float* u, cudaStream_t st) {
-    const int D = m->arch.transition_dim;
+// true when the first conv of the U-Net runs inside the tensor kernel's epilogue, which can read a state shared by the
+// two CFG halves (ConvP::inl_wrap); the other cores need the duplicated batch
+static bool can_share_x(const pmp_model* m, int H) {
+    return m->gemm_path >= 1 && m->gemm_path != 2 && m->arch.transition_dim <= 16 && H <= 128 && m->dims.size() > 1 &&
+           m->dims[1] == 64;
+}
+
+// every allocation eps_rows would make for R rows, made up front (nothing may allocate while a graph is being captured)
+static int eps_rows_reserve(pmp_model* m, int R, int H, cudaStream_t st) {
     PMP_REQUIRE(H % 4 == 0 && H >= 32 && H <= 128, "horizon %d unsupported (multiple of 4 in [32,128])", H);
     const int chunk = aligned_chunk(m, H);
     int rc;
     const int Rc_max = R < chunk ? R : chunk;
     const size_t need = workspace_floats(m, Rc_max, H);
-    if ((rc = grow(&m->ws, &m->ws_n, need, st))) return rc;
+    if ((rc = grow(&m->ws, &m->ws_n, need, st, &m->gen))) return rc;
+    if (m->arch.time_mlp_config != 0) {
+        const int nblk = (int)m->blocks.size();
+        if ((rc = grow(&m->hidb, &m->hidb_n, (size_t)chunk * nblk * m->hid, st, &m->gen))) return rc;
+        if ((rc = grow(&m->embE, &m->embE_n, (size_t)chunk * m->Ctot, st, &m->gen))) return rc;
+    }
+    return 0;
+}
+
+// eps for R rows given prepared wall tables (rows < n_cond conditional).  x_wrap > 0: x holds x_wrap rows and row r
+// of the batch reads row r mod x_wrap (the CFG halves share the state)
+static int eps_rows(pmp_model* m, const float* x, const int64_t* t, const float* wall_tab, int n_cond, int R, int H,
+                    float* eps, float* energy, float* u, cudaStream_t st, int x_wrap = 0) {
+    const int D = m->arch.transition_dim;
+    const int chunk = aligned_chunk(m, H);
+    int rc;
+    if ((rc = eps_rows_reserve(m, R, H, st))) return rc;
     const int nblk = (int)m->blocks.size();
     for (int r0 = 0; r0 < R; r0 += chunk) {
         const int Rc = (R - r0) < chunk ? (R - r0) : chunk;
@@ -1083,8 +1122,6 @@ static int eps_rows(pmp_model* m, const float* x, const int64_t* t, const float*
             c.embRow = wall_tab ? wall_tab + (size_t)r0 * m->Ctot : nullptr;
         } else {
             // per-step block embeddings: E = W2 * act(Ht[t] + Hw[r]) + b2
-            if ((rc = grow(&m->hidb, &m->hidb_n, (size_t)chunk * nblk * m->hid, st))) return rc;
-            if ((rc = grow(&m->embE, &m->embE_n, (size_t)chunk * m->Ctot, st))) return rc;
             const float* Hw = (wall_tab && nc > 0) ? wall_tab + (size_t)r0 * nblk * m->hid : nullptr;
             if ((rc = launch_cfg3_hidden(m->embT, c.t, m->arch.n_timesteps - 1, Hw, Hw ? nc : 0, Rc, nblk * m->hid,
                                          m->arch.act, m->hidb, st)))
@@ -1098,7 +1135,13 @@ static int eps_rows(pmp_model* m, const float* x, const int64_t* t, const float*
             c.embRow = m->embE;
         }
         m->dbg.clear();
-        rc = run_unet(c, x + (size_t)r0 * H * D, eps + (size_t)r0 * H * D, energy ? energy + r0 : nullptr,
+        const float* xin = x + (size_t)r0 * H * D;
+        if (x_wrap > 0) {
+            c.x_row0 = r0 % x_wrap;
+            c.x_wrap = x_wrap;
+            xin = x;
+        }
+        rc = run_unet(c, xin, eps + (size_t)r0 * H * D, energy ? energy + r0 : nullptr,
                       u ? u + (size_t)r0 * H * D : nullptr);
         if (rc) return rc;
     }
@@ -1152,7 +1195,10 @@ void pmp_model_destroy(pmp_model* m) {
     if (!m) return;
     DeviceGuard guard(m->device);
     if (m->arena16) cudaFree(m->arena16);
-    float* bufs[] = {m->arena, m->temb_tab, m->embT, m->embR, m->embE, m->hidb, m->ws};
+    for (auto& g : m->graphs) cudaGraphExecDestroy(g.exec);
+    if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+    float* bufs[] = {m->arena, m->temb_tab, m->embT, m->embR, m->embE, m->hidb, m->ws,
+                     m->s_eps, m->s_x2, m->s_xs, m->s_sg, m->s_wtab, m->s_tabs};
     for (float* b : bufs)
         if (b) cudaFree(b);
     delete m;
@@ -1189,6 +1235,7 @@ int pmp_model_finalize(pmp_model* m) {
 int pmp_model_set_row_chunk(pmp_model* m, int rows) {
     PMP_REQUIRE(m && rows >= 2, "row chunk must be >= 2");
     m->row_chunk = rows;
+    ++m->gen;
     return 0;
 }
 
@@ -1196,6 +1243,7 @@ int pmp_model_set_gemm_path(pmp_model* m, int path) {
     PMP_REQUIRE(m && path >= 0 && path <= 4,
                 "gemm path must be 0 (fp32 SIMT), 1 (tcgen05), 2 (operand reuse), 3 (CTA pairs) or 4 (CTA pairs, 16 epilogue warps)");
     m->gemm_path = path;
+    ++m->gen;
     return 0;
 }
 
@@ -1248,98 +1296,235 @@ int pmp_pick_first_valid(const uint8_t* valid, const int32_t* nchk, int n_prob, 
     return launch_pick_first_valid(valid, nchk, n_prob, n_samp, chosen, success, total, (cudaStream_t)stream);
 }
 
+// One reverse-diffusion step of pmp_sample for the row chunk held in the sampler scratch: timestep rows, the K
+// potentials' CFG pairs, the fused update.  `dyn`: every per-step value is read from device memory (SamplerState),
+// which makes the launch sequence identical for all steps -> captured once as a CUDA graph and replayed.
+struct StepCtx {
+    const pmp_sample_args* a;
+    pmp_model* m0;
+    cudaStream_t st;
+    int Bn, Bc;               // plans in this chunk / chunk capacity (buffer strides)
+    bool share_x, dedup;
+    float* x;                 // state of the chunk [Bn][H][D]
+    const float *start, *goal;
+    int64_t* t2;
+    float* coef_tab;
+    int32_t* t_tab;
+    SamplerState* state;
+    float* wtab[PMP_MAX_COMPOSE];
+    // direct mode only
+    int s;
+    uint64_t elem0;
+    const float* noise_s;     // injected noise of this step or null
+    float* trace_s;
+    long tstride;
+};
+
+static int enqueue_step(const StepCtx& c, bool dyn) {
+    const pmp_sample_args* a = c.a;
+    const int K = a->K, H = a->H, D = a->D, Bn = c.Bn;
+    const size_t n = (size_t)Bn * H * D, tile = (size_t)c.Bc * H * D;
+    cudaStream_t st = c.st;
+    int rc;
+    if (dyn) rc = launch_sampler_set_t(c.state, c.t_tab, c.t2, (size_t)2 * Bn, st);
+    else rc = launch_fill_i64(c.t2, (int64_t)a->t_host[c.s], (size_t)2 * Bn, st);
+    if (rc) return rc;
+    const float* xin = c.x;
+    if (!c.share_x) {
+        // cores that read the input as a GEMM operand need the duplicated CFG batch
+        float* x2 = c.m0->s_x2;
+        if (cudaMemcpyAsync(x2, c.x, n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(x2 + n, c.x, n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            set_error("cudaMemcpyAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return PMP_ERR_CUDA;
+        }
+        xin = x2;
+    }
+    const int wrap = c.share_x ? Bn : 0;
+    const float* ec[PMP_MAX_COMPOSE];
+    const float* eu[PMP_MAX_COMPOSE];
+    for (int k = 0; k < K; ++k) {
+        float* e2 = c.m0->s_eps + (size_t)k * 2 * tile;
+        // the unconditional half does not see the walls: potentials that are the SAME network (the reference's
+        // "one model, K obstacle subsets" compositions, config/comp) share it bit for bit, so it is evaluated
+        // once and only the conditional rows are run for the repeats
+        int dup = -1;
+        for (int j = 0; j < k && c.dedup; ++j)
+            if (a->models[j] == a->models[k]) { dup = j; break; }
+        if (dup >= 0) {
+            if ((rc = eps_rows(a->models[k], xin, c.t2, c.wtab[k], Bn, Bn, H, e2, nullptr, nullptr, st, wrap))) return rc;
+            ec[k] = e2;
+            eu[k] = eu[dup];
+            continue;
+        }
+        if ((rc = eps_rows(a->models[k], xin, c.t2, c.wtab[k], Bn, 2 * Bn, H, e2, nullptr, nullptr, st, wrap))) return rc;
+        ec[k] = e2;
+        eu[k] = e2 + n;
+    }
+    if (dyn) {
+        if ((rc = launch_step(a->kind, c.x, ec, eu, a->w, K, a->base, nullptr, nullptr, 0, 0, c.elem0, c.start, c.goal, c.x,
+                              nullptr, 0, Bn, H, D, st, c.state, c.coef_tab)))
+            return rc;
+        return launch_sampler_advance(c.state, st);
+    }
+    return launch_step(a->kind, c.x, ec, eu, a->w, K, a->base, a->coef_host + 8 * c.s, c.noise_s, a->seed, (uint64_t)(c.s + 1),
+                       c.elem0, c.start, c.goal, c.x, c.trace_s, c.tstride, Bn, H, D, st);
+}
+
 int pmp_sample(const pmp_sample_args* a, void* stream) {
     PMP_REQUIRE(a, "null argument");
     PMP_REQUIRE(a->K >= 1 && a->K <= PMP_MAX_COMPOSE, "K out of range");
     PMP_REQUIRE(a->B >= 1 && a->n_steps >= 1 && a->t_host && a->coef_host && a->x_dev && a->start_dev && a->goal_dev,
                 "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    const int K = a->K, B = a->B, H = a->H, D = a->D;
+    const int K = a->K, B = a->B, H = a->H, D = a->D, n_steps = a->n_steps;
     for (int k = 0; k < K; ++k) {
         PMP_REQUIRE(a->models[k] && a->models[k]->finalized, "model %d not finalized", k);
         PMP_REQUIRE(a->models[k]->arch.transition_dim == D, "model %d has transition_dim %d, expected %d", k,
                     a->models[k]->arch.transition_dim, D);
         PMP_REQUIRE(a->wemb_dev[k], "wemb_dev[%d] is null", k);
+        PMP_REQUIRE(a->models[k]->device == a->models[0]->device, "composed models live on different devices");
     }
-    DeviceGuard guard(a->models[0]->device);
+    for (int s = 0; s < n_steps; ++s)
+        for (int k = 0; k < K; ++k)
+            PMP_REQUIRE(a->t_host[s] >= 0 && a->t_host[s] < a->models[k]->arch.n_timesteps,
+                        "step %d: timestep %d outside model %d's schedule (n_timesteps %d)", s, a->t_host[s], k,
+                        a->models[k]->arch.n_timesteps);
+    pmp_model* m0 = a->models[0];
+    DeviceGuard guard(m0->device);
     // plans per pass: the CFG pair doubles the rows
-    int chunk = aligned_chunk(a->models[0], H);
+    int chunk = aligned_chunk(m0, H);
     for (int k = 1; k < K; ++k)
         if (aligned_chunk(a->models[k], H) < chunk) chunk = aligned_chunk(a->models[k], H);
     int Bc = chunk / 2;
     if (Bc < 1) Bc = 1;
     if (Bc > B) Bc = B;
+    bool share_x = true;
+    for (int k = 0; k < K; ++k) share_x = share_x && can_share_x(a->models[k], H);
     const size_t tile = (size_t)Bc * H * D;
-    float* x2 = nullptr;
-    float* epsb = nullptr;
-    int64_t* t2 = nullptr;
-    PMP_CUDA_OK(cudaMallocAsync((void**)&x2, 2 * tile * sizeof(float), st));
-    PMP_CUDA_OK(cudaMallocAsync((void**)&epsb, (size_t)K * 2 * tile * sizeof(float), st));
-    PMP_CUDA_OK(cudaMallocAsync((void**)&t2, (size_t)2 * Bc * sizeof(int64_t), st));
-    float* wtab[PMP_MAX_COMPOSE] = {};
+    // ---- scratch of the sampler (grow-only, stream-ordered; a steady workload allocates nothing here)
+    int rc;
+    size_t wt_off[PMP_MAX_COMPOSE + 1];
+    wt_off[0] = 0;
+    for (int k = 0; k < K; ++k) wt_off[k + 1] = wt_off[k] + (((size_t)Bc * wall_table_width(a->models[k]) + 3) & ~(size_t)3);
+    const size_t t2_f = (size_t)4 * Bc, coef_f = (size_t)8 * n_steps, tt_f = ((size_t)n_steps + 3) & ~(size_t)3;
+    if ((rc = grow(&m0->s_eps, &m0->s_eps_n, (size_t)K * 2 * tile, st, &m0->gen))) return rc;
+    if (!share_x && (rc = grow(&m0->s_x2, &m0->s_x2_n, 2 * tile, st, &m0->gen))) return rc;
+    if ((rc = grow(&m0->s_xs, &m0->s_xs_n, tile, st, &m0->gen))) return rc;
+    if ((rc = grow(&m0->s_sg, &m0->s_sg_n, (size_t)2 * Bc * D + 8, st, &m0->gen))) return rc;
+    if ((rc = grow(&m0->s_wtab, &m0->s_wtab_n, wt_off[K], st, &m0->gen))) return rc;
+    if ((rc = grow(&m0->s_tabs, &m0->s_tabs_n, t2_f + coef_f + tt_f + 8, st, &m0->gen))) return rc;
     for (int k = 0; k < K; ++k)
-        PMP_CUDA_OK(cudaMallocAsync((void**)&wtab[k], (size_t)Bc * wall_table_width(a->models[k]) * sizeof(float), st));
-    const long tstride = (long)(a->n_steps + 1) * H * D;
-    const bool dedup = g_uncond_dedup.load() != 0;
-    int rc = 0;
-    for (int b0 = 0; b0 < B && !rc; b0 += Bc) {
+        if ((rc = eps_rows_reserve(a->models[k], 2 * Bc, H, st))) return rc;
+    StepCtx c;
+    memset(&c, 0, sizeof c);
+    c.a = a; c.m0 = m0; c.st = st; c.Bc = Bc; c.share_x = share_x; c.dedup = g_uncond_dedup.load() != 0;
+    c.t2 = reinterpret_cast<int64_t*>(m0->s_tabs);
+    c.coef_tab = m0->s_tabs + t2_f;
+    c.t_tab = reinterpret_cast<int32_t*>(m0->s_tabs + t2_f + coef_f);
+    c.state = reinterpret_cast<SamplerState*>(m0->s_tabs + t2_f + coef_f + tt_f);
+    for (int k = 0; k < K; ++k) c.wtab[k] = m0->s_wtab + wt_off[k];
+    // A graph per (potentials, chunk size, horizon, step kind) is replayed for every step.  Not with injected noise or a
+    // diffusion trace (their addresses change per step and per call; those are the parity / debugging modes), not while
+    // the per-launch profiler is recording, and not for a single step.
+    const bool use_graph = g_cuda_graph.load() != 0 && !a->noise_dev && !a->trace_dev && !g_prof_on && n_steps >= 2;
+    if (use_graph) {
+        // pageable host tables: the copies are staged by the runtime before the call returns
+        PMP_CUDA_OK(cudaMemcpyAsync(c.coef_tab, a->coef_host, coef_f * sizeof(float), cudaMemcpyHostToDevice, st));
+        PMP_CUDA_OK(cudaMemcpyAsync(c.t_tab, a->t_host, (size_t)n_steps * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+    const long tstride = (long)(n_steps + 1) * H * D;
+    for (int b0 = 0; b0 < B; b0 += Bc) {
         const int Bn = (B - b0) < Bc ? (B - b0) : Bc;
         const size_t n = (size_t)Bn * H * D;
-        float* x = a->x_dev + (size_t)b0 * H * D;
-        const float* start = a->start_dev + (size_t)b0 * D;
-        const float* goal = a->goal_dev + (size_t)b0 * D;
         const uint64_t elem0 = (a->row_offset + (uint64_t)b0) * (uint64_t)(H * D);
         float* tr = a->trace_dev ? a->trace_dev + (size_t)b0 * tstride : nullptr;
         const size_t nstride = (size_t)B * H * D;
         const float* nz = a->noise_dev ? a->noise_dev + (size_t)b0 * H * D : nullptr;
-        if ((rc = launch_init_noise(x, nz, a->seed, 0, elem0, a->var_temp, start, goal, tr, tstride, Bn, H, D, st))) break;
-        for (int k = 0; k < K && !rc; ++k)
-            rc = prepare_wall_tables(a->models[k], a->wemb_dev[k] + (size_t)b0 * a->models[k]->arch.wall_embed_dim, Bn,
-                                     wtab[k], st);
-        for (int s = 0; s < a->n_steps && !rc; ++s) {
-            if ((rc = launch_fill_i64(t2, (int64_t)a->t_host[s], (size_t)2 * Bn, st))) break;
-            const float* ec[PMP_MAX_COMPOSE];
-            const float* eu[PMP_MAX_COMPOSE];
-            if (cudaMemcpyAsync(x2, x, n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
-                cudaMemcpyAsync(x2 + n, x, n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
-                set_error("cudaMemcpyAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
-                rc = PMP_ERR_CUDA;
-                break;
+        c.Bn = Bn;
+        c.elem0 = elem0;
+        c.tstride = tstride;
+        for (int k = 0; k < K; ++k)
+            if ((rc = prepare_wall_tables(a->models[k], a->wemb_dev[k] + (size_t)b0 * a->models[k]->arch.wall_embed_dim, Bn,
+                                          c.wtab[k], st)))
+                return rc;
+        if (!use_graph) {
+            // direct launches, in place on the caller's buffers
+            c.x = a->x_dev + (size_t)b0 * H * D;
+            c.start = a->start_dev + (size_t)b0 * D;
+            c.goal = a->goal_dev + (size_t)b0 * D;
+            if ((rc = launch_init_noise(c.x, nz, a->seed, 0, elem0, a->var_temp, c.start, c.goal, tr, tstride, Bn, H, D, st)))
+                return rc;
+            for (int s = 0; s < n_steps; ++s) {
+                c.s = s;
+                c.noise_s = a->noise_dev ? a->noise_dev + (size_t)(s + 1) * nstride + (size_t)b0 * H * D : nullptr;
+                c.trace_s = tr ? tr + (size_t)(s + 1) * H * D : nullptr;
+                if ((rc = enqueue_step(c, false))) return rc;
             }
-            for (int k = 0; k < K && !rc; ++k) {
-                float* e2 = epsb + (size_t)k * 2 * tile;
-                // the unconditional half does not see the walls: potentials that are the SAME network (the reference's
-                // "one model, K obstacle subsets" compositions, config/comp) share it bit for bit, so it is evaluated
-                // once and only the conditional rows are run for the repeats
-                int dup = -1;
-                for (int j = 0; j < k && dedup; ++j)
-                    if (a->models[j] == a->models[k]) { dup = j; break; }
-                if (dup >= 0) {
-                    rc = eps_rows(a->models[k], x2, t2, wtab[k], Bn, Bn, H, e2, nullptr, nullptr, st);
-                    ec[k] = e2;
-                    eu[k] = eu[dup];
-                    continue;
-                }
-                rc = eps_rows(a->models[k], x2, t2, wtab[k], Bn, 2 * Bn, H, e2, nullptr, nullptr, st);
-                ec[k] = e2;
-                eu[k] = e2 + n;
-            }
-            if (rc) break;
-            const float* nzs = a->noise_dev ? a->noise_dev + (size_t)(s + 1) * nstride + (size_t)b0 * H * D : nullptr;
-            rc = launch_step(a->kind, x, ec, eu, a->w, K, a->base, a->coef_host + 8 * s, nzs, a->seed, (uint64_t)(s + 1),
-                             elem0, start, goal, x, tr ? tr + (size_t)(s + 1) * H * D : nullptr, tstride, Bn, H, D, st);
+            continue;
         }
+        // graph replay on the scratch copies of state / start / goal (fixed addresses), result copied out at the end
+        float* sstart = m0->s_sg;
+        float* sgoal = m0->s_sg + (((size_t)Bc * D + 3) & ~(size_t)3);
+        PMP_CUDA_OK(cudaMemcpyAsync(sstart, a->start_dev + (size_t)b0 * D, (size_t)Bn * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        PMP_CUDA_OK(cudaMemcpyAsync(sgoal, a->goal_dev + (size_t)b0 * D, (size_t)Bn * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        c.x = m0->s_xs;
+        c.start = sstart;
+        c.goal = sgoal;
+        if ((rc = launch_init_noise(c.x, nullptr, a->seed, 0, elem0, a->var_temp, c.start, c.goal, nullptr, 0, Bn, H, D, st)))
+            return rc;
+        if ((rc = launch_sampler_begin(c.state, a->seed, elem0, st))) return rc;
+        std::vector<uint64_t> key;
+        key.push_back((uint64_t)K); key.push_back((uint64_t)Bn); key.push_back((uint64_t)Bc); key.push_back((uint64_t)H);
+        key.push_back((uint64_t)a->kind); key.push_back((uint64_t)a->base); key.push_back((uint64_t)c.dedup);
+        key.push_back((uint64_t)n_steps);     // the tables' offsets inside the scratch depend on it
+        for (int k = 0; k < K; ++k) {
+            uint32_t wb;
+            memcpy(&wb, &a->w[k], 4);
+            key.push_back((uint64_t)(uintptr_t)a->models[k]);
+            key.push_back(a->models[k]->gen);
+            key.push_back((uint64_t)wb);
+        }
+        cudaGraphExec_t exec = nullptr;
+        uint64_t per_step = 0;
+        for (auto& g : m0->graphs)
+            if (g.key == key) { exec = g.exec; per_step = g.launches; break; }
+        if (!exec) {
+            cudaGraph_t graph = nullptr;
+            if (!m0->cap_stream) PMP_CUDA_OK(cudaStreamCreateWithFlags(&m0->cap_stream, cudaStreamNonBlocking));
+            PMP_CUDA_OK(cudaStreamBeginCapture(m0->cap_stream, cudaStreamCaptureModeRelaxed));
+            const uint64_t l0 = g_launches.load();
+            StepCtx cc = c;
+            cc.st = m0->cap_stream;              // recorded only; the graph is launched on the caller's stream
+            rc = enqueue_step(cc, true);
+            per_step = g_launches.load() - l0;
+            g_launches.fetch_sub(per_step);      // recorded, not executed: replays are counted below
+            const cudaError_t ce = cudaStreamEndCapture(m0->cap_stream, &graph);
+            if (rc || ce != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                if (!rc) { set_error("CUDA graph capture of the sampler step failed: %s", cudaGetErrorString(ce)); rc = PMP_ERR_CUDA; }
+                return rc;
+            }
+            const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); return PMP_ERR_CUDA; }
+            if (m0->graphs.size() >= 16) {     // a handful of (chunk size, horizon, steps) combinations in practice
+                cudaGraphExecDestroy(m0->graphs.front().exec);
+                m0->graphs.erase(m0->graphs.begin());
+            }
+            m0->graphs.push_back(pmp_model::GraphEnt{key, exec, per_step});
+        }
+        for (int s = 0; s < n_steps; ++s) PMP_CUDA_OK(cudaGraphLaunch(exec, st));
+        g_launches.fetch_add((uint64_t)n_steps * per_step);
+        PMP_CUDA_OK(cudaMemcpyAsync(a->x_dev + (size_t)b0 * H * D, c.x, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    cudaFreeAsync(x2, st);
-    cudaFreeAsync(epsb, st);
-    cudaFreeAsync(t2, st);
-    for (int k = 0; k < K; ++k) cudaFreeAsync(wtab[k], st);
-    return rc;
+    return 0;
 }
 
 int pmp_set_option(const char* name, int value) {
     PMP_REQUIRE(name, "null option name");
     if (!strcmp(name, "uncond_dedup")) { g_uncond_dedup.store(value ? 1 : 0); return 0; }
+    if (!strcmp(name, "cuda_graph")) { g_cuda_graph.store(value ? 1 : 0); return 0; }
     set_error("unknown option '%s'", name);
     return PMP_ERR_ARG;
 }

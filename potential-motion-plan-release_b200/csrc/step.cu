@@ -62,22 +62,46 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t draw, uin
 }
 
 // the update of one element (explicitly rounded, reference op order): shared by the scalar and the float4 kernel
-__device__ __forceinline__ float step_elem(const StepP& p, float xv, float eps, float z) {
-    float x0 = __fsub_rn(__fmul_rn(p.coef[0], xv), __fmul_rn(p.coef[1], eps));
+__device__ __forceinline__ float step_elem(const float (&cf)[8], int kind, float xv, float eps, float z) {
+    float x0 = __fsub_rn(__fmul_rn(cf[0], xv), __fmul_rn(cf[1], eps));
     x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-    if (p.kind == PMP_STEP_DDPM) {
-        const float mean = __fadd_rn(__fmul_rn(p.coef[2], x0), __fmul_rn(p.coef[3], xv));
-        return __fadd_rn(mean, __fmul_rn(p.coef[4], z));
+    if (kind == PMP_STEP_DDPM) {
+        const float mean = __fadd_rn(__fmul_rn(cf[2], x0), __fmul_rn(cf[3], xv));
+        return __fadd_rn(mean, __fmul_rn(cf[4], z));
     }
-    const float mo = __fdiv_rn(__fsub_rn(xv, __fmul_rn(p.coef[2], x0)), p.coef[3]);
-    float out = __fadd_rn(__fmul_rn(p.coef[4], x0), __fmul_rn(p.coef[5], mo));
-    if (p.coef[7] != 0.0f) out = __fadd_rn(out, __fmul_rn(p.coef[6], z));
+    const float mo = __fdiv_rn(__fsub_rn(xv, __fmul_rn(cf[2], x0)), cf[3]);
+    float out = __fadd_rn(__fmul_rn(cf[4], x0), __fmul_rn(cf[5], mo));
+    if (cf[7] != 0.0f) out = __fadd_rn(out, __fmul_rn(cf[6], z));
     return out;
+}
+
+// Per-step quantities of the whole-loop sampler that live in device memory, so that ONE captured CUDA graph of a
+// reverse-diffusion step can be replayed for every step: the step index s (advanced by a one-thread kernel at the end
+// of each replay), from which the kernels derive the timestep fed to the U-Net (t_tab[s]), the coefficient row
+// (coef_tab[s]) and the Philox draw index (s + 1); seed and global element offset are set per call / row chunk.
+struct DynStep {
+    const pmp::SamplerState* state;
+    const float* coef_tab;       // [n_steps][8]
+};
+__device__ __forceinline__ void step_inputs(const StepP& p, const DynStep& dyn, float (&cf)[8], uint64_t& seed, uint64_t& draw,
+                                            uint64_t& elem0) {
+    if (dyn.state) {
+        const int s = dyn.state->s;
+        seed = dyn.state->seed;
+        elem0 = dyn.state->elem0;
+        draw = (uint64_t)(s + 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cf[i] = __ldg(dyn.coef_tab + 8 * s + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cf[i] = p.coef[i];
+    }
 }
 
 // float4 variant (H*D and the global element offset are multiples of 4): 16-byte loads / stores, one Philox call
 // per thread.  HBM-bound: 4*(2 + 2K [+1 injected noise]) bytes per element.
-__global__ void __launch_bounds__(256) step_kernel4(const __grid_constant__ StepP p, const float* __restrict__ x,
+__global__ void __launch_bounds__(256) step_kernel4(const __grid_constant__ StepP p, const DynStep dyn,
+                                                    const float* __restrict__ x,
                                                     const float* __restrict__ noise, uint64_t seed, uint64_t draw,
                                                     uint64_t elem0, const float* __restrict__ start,
                                                     const float* __restrict__ goal, float* __restrict__ xo,
@@ -85,10 +109,13 @@ __global__ void __launch_bounds__(256) step_kernel4(const __grid_constant__ Step
                                                     size_t n4) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n4) return;
+    float cf[8];
+    step_inputs(p, dyn, cf, seed, draw, elem0);
     const size_t e = g * 4;
     const int HD = H * D;
-    const size_t b = e / HD;
-    const int rem = (int)(e - b * HD);
+    // one 32-bit division per thread (the launcher guarantees n4 < 2^32); the conditioning rows are found by comparison
+    const unsigned b = (unsigned)g / (unsigned)(HD >> 2);
+    const int rem = (int)(((unsigned)g - b * (unsigned)(HD >> 2)) << 2);
     const float4 xv4 = __ldg(reinterpret_cast<const float4*>(x + e));
     const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
     float eps[4];
@@ -112,24 +139,25 @@ __global__ void __launch_bounds__(256) step_kernel4(const __grid_constant__ Step
 #pragma unroll
         for (int j = 0; j < 4; ++j) eps[j] = __fadd_rn(ub[j], s[j]);
     }
-    const bool need_noise = (p.kind == PMP_STEP_DDPM) || (p.coef[7] != 0.0f);
+    const bool need_noise = (p.kind == PMP_STEP_DDPM) || (cf[7] != 0.0f);
     float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (need_noise) z4 = noise ? __ldg(reinterpret_cast<const float4*>(noise + e)) : philox_normal4(seed, draw, (elem0 + e) >> 2);
     const float z[4] = {z4.x, z4.y, z4.z, z4.w};
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        o[j] = step_elem(p, xv[j], eps[j], z[j]);
-        const int r = rem + j, h = r / D, d = r - h * D;
-        if (start && h == 0) o[j] = start[b * D + d];
-        if (goal && h == H - 1) o[j] = goal[b * D + d];
+        o[j] = step_elem(cf, p.kind, xv[j], eps[j], z[j]);
+        const int r = rem + j;
+        if (start && r < D) o[j] = start[(size_t)b * D + r];                        // h == 0
+        if (goal && r >= HD - D) o[j] = goal[(size_t)b * D + (r - (HD - D))];       // h == H - 1
     }
     const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
     *reinterpret_cast<float4*>(xo + e) = o4;
-    if (trace) *reinterpret_cast<float4*>(trace + b * trace_stride + rem) = o4;
+    if (trace) *reinterpret_cast<float4*>(trace + (size_t)b * trace_stride + rem) = o4;
 }
 
-__global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP p, const float* __restrict__ x,
+__global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP p, const DynStep dyn,
+                                                   const float* __restrict__ x,
                                                    const float* __restrict__ noise, uint64_t seed, uint64_t draw,
                                                    uint64_t elem0, const float* __restrict__ start,
                                                    const float* __restrict__ goal, float* __restrict__ xo,
@@ -137,6 +165,8 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
                                                    size_t n) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
+    float cf[8];
+    step_inputs(p, dyn, cf, seed, draw, elem0);
     const int HD = H * D;
     const size_t b = e / HD;
     const int rem = (int)(e - b * HD);
@@ -151,10 +181,10 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
         for (int k = 1; k < p.K; ++k) s = __fadd_rn(s, __fmul_rn(p.w[k], __fsub_rn(p.ec[k][e], p.eu[k][e])));
         eps = __fadd_rn(p.eu[p.base][e], s);
     }
-    const bool need_noise = (p.kind == PMP_STEP_DDPM) || (p.coef[7] != 0.0f);
+    const bool need_noise = (p.kind == PMP_STEP_DDPM) || (cf[7] != 0.0f);
     float z = 0.0f;
     if (need_noise) z = noise ? noise[e] : philox_normal(seed, draw, elem0 + e);
-    float out = step_elem(p, xv, eps, z);
+    float out = step_elem(cf, p.kind, xv, eps, z);
     if (start && h == 0) out = start[b * D + d];
     if (goal && h == H - 1) out = goal[b * D + d];
     xo[e] = out;
@@ -212,34 +242,68 @@ __global__ void pick_first_valid_kernel(const uint8_t* __restrict__ valid, const
     total[p] = tot;
 }
 
+__global__ void sampler_begin_kernel(SamplerState* st, uint64_t seed, uint64_t elem0) {
+    st->s = 0;
+    st->seed = seed;
+    st->elem0 = elem0;
+}
+__global__ void sampler_advance_kernel(SamplerState* st) { st->s += 1; }
+// t2[i] = timestep of the current step for every row of the CFG batch
+__global__ void sampler_set_t_kernel(const SamplerState* __restrict__ st, const int32_t* __restrict__ t_tab,
+                                     int64_t* __restrict__ t2, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) t2[i] = (int64_t)t_tab[st->s];
+}
+
 }  // namespace
+
+int launch_sampler_begin(SamplerState* state, uint64_t seed, uint64_t elem0, cudaStream_t st) {
+    sampler_begin_kernel<<<1, 1, 0, st>>>(state, seed, elem0);
+    PMP_LAUNCH_OK();
+    return 0;
+}
+int launch_sampler_advance(SamplerState* state, cudaStream_t st) {
+    sampler_advance_kernel<<<1, 1, 0, st>>>(state);
+    PMP_LAUNCH_OK();
+    return 0;
+}
+int launch_sampler_set_t(const SamplerState* state, const int32_t* t_tab, int64_t* t2, size_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    sampler_set_t_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(state, t_tab, t2, n);
+    PMP_LAUNCH_OK();
+    return 0;
+}
 
 int launch_step(int kind, const float* x, const float* const* ec, const float* const* eu, const float* w, int K,
                 int base, const float* coef, const float* noise, uint64_t seed, uint64_t draw, uint64_t elem0,
                 const float* start, const float* goal, float* xo, float* trace, long trace_stride, int B, int H,
-                int D, cudaStream_t st) {
+                int D, cudaStream_t st, const SamplerState* state, const float* coef_tab) {
     PMP_REQUIRE(K >= 1 && K <= PMP_MAX_COMPOSE, "K=%d composed potentials unsupported", K);
     PMP_REQUIRE(base >= 0 && base < K, "uncond base index %d out of range", base);
+    PMP_REQUIRE(coef || (state && coef_tab), "step coefficients missing");
+    DynStep dyn;
+    dyn.state = state;
+    dyn.coef_tab = coef_tab;
     StepP p;
     for (int k = 0; k < K; ++k) {
         p.ec[k] = ec[k];
         p.eu[k] = eu[k];
         p.w[k] = w[k];
     }
-    for (int i = 0; i < 8; ++i) p.coef[i] = coef[i];
+    for (int i = 0; i < 8; ++i) p.coef[i] = coef ? coef[i] : 0.f;
     p.K = K;
     p.base = base;
     p.kind = kind;
     const size_t n = (size_t)B * H * D;
     if (n == 0) return 0;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    bool vec = ((H * D) % 4 == 0) && (elem0 % 4 == 0) && al16(x) && al16(xo) && al16(noise) && al16(trace) && (trace_stride % 4 == 0);
+    bool vec = ((H * D) % 4 == 0) && (n / 4 < 0xffffffffull) && (elem0 % 4 == 0) && al16(x) && al16(xo) && al16(noise) && al16(trace) && (trace_stride % 4 == 0);
     for (int k = 0; k < K; ++k) vec = vec && al16(ec[k]) && al16(eu[k]);
     if (vec)
-        step_kernel4<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(p, x, noise, seed, draw, elem0, start, goal, xo, trace,
+        step_kernel4<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(p, dyn, x, noise, seed, draw, elem0, start, goal, xo, trace,
                                                                      trace_stride, H, D, n / 4);
     else
-        step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, x, noise, seed, draw, elem0, start, goal, xo, trace,
+        step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, dyn, x, noise, seed, draw, elem0, start, goal, xo, trace,
                                                                 trace_stride, H, D, n);
     PMP_LAUNCH_OK();
     return 0;

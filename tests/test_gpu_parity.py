@@ -222,6 +222,42 @@ def test_dropin_forward_api_and_philox():
     finally:
         d.rng_mode = "torch"
 
+def test_sampler_graph_replay_equals_direct_launches():
+    """pmp_sample replays one captured CUDA graph per step (device-resident step state, CFG halves sharing the state);
+    with the graph switched off every kernel is launched from the host on the caller's buffers.  Same bits, for plain
+    CFG DDPM and a K=3 same-network DDIM composition, several row chunks of unequal size, repeated calls (cached graph)"""
+    d = dropin("m2d")
+    B, H = 20, 48
+    pr = synth.make_problems("m2d", B, 8)
+    lo, hi = pr["lo"], pr["hi"]
+    start = torch.tensor(synth.normalize(pr["start"], lo, hi), device=DEV)
+    goal = torch.tensor(synth.normalize(pr["goal"], lo, hi), device=DEV)
+    eng = d.model.engine(100)
+    w1 = eng.wall_embed(torch.tensor(pr["walls"], device=DEV))
+    w2 = eng.wall_embed(torch.tensor(pr["walls"][::-1].copy(), device=DEV))
+    w3 = eng.wall_embed(torch.tensor(np.roll(pr["walls"], 3, 0), device=DEV))
+    cases = [([eng], [w1], [2.0], 0, list(range(11, -1, -1))),
+             ([eng, eng, eng], [w1, w2, w3], [2.0, 1.5, 1.0], 1, None)]
+    try:
+        for chunk in (8192, 16):              # one chunk / chunks of 8 + 8 + 4 plans
+            eng.set_row_chunk(chunk)
+            for engs, ws, gw, kind, ts in cases:
+                if kind == 1:
+                    ts = d.ddim_set_timesteps(8); coefs = d.step_coefs_ddim(ts, 0.0, 8)
+                else:
+                    coefs = d.step_coefs_ddpm(ts)
+                outs = []
+                for graph in (1, 1, 0):
+                    pmp_b200.set_option("cuda_graph", graph)
+                    n0 = pmp_b200.launch_count()
+                    outs.append(pmp_b200.sample(engs, ws, gw, start, goal, H, kind, ts, coefs, noise=None, seed=77, base=0))
+                    assert pmp_b200.launch_count() - n0 >= len(ts) * 60
+                assert torch.isfinite(outs[0]).all()
+                assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), (chunk, kind)
+    finally:
+        pmp_b200.set_option("cuda_graph", 1)
+        eng.set_row_chunk(8192)
+
 
 def test_compose_same_model_shares_unconditional_half():
     """K potentials that are one network (config/comp "gsd" compositions): the unconditional half is evaluated once;
@@ -408,6 +444,27 @@ def test_maze2d_collision_full_size_vs_oracle(legacy):
         assert np.array_equal(ch.cpu().numpy(), ch_ref) and np.array_equal(su.cpu().numpy().astype(bool), su_ref)
         assert np.array_equal(tot.cpu().numpy(), tot_ref)
         assert 0.02 < su_ref.mean() < 0.98
+
+@pytest.mark.parametrize("legacy", [True, False])
+def test_maze2d_swept_all_horizons_vs_oracle(legacy):
+    """half-warp kernel (H <= 64: 2 / 3 / 4 waypoints per lane) and the generic one-warp kernel (H > 64): odd batch sizes,
+    environments shared by runs of candidates and shuffled, long jumps with many interior points, out-of-limit points"""
+    rng = np.random.default_rng(11)
+    for H in (2, 5, 16, 17, 31, 32, 33, 36, 47, 48, 49, 63, 64, 65, 100, 128):
+        for fam, hext in (("m2d", 0.5), ("m2d_concave", 0.25)):
+            E, n_per = 37, 5
+            pr = synth.make_problems(fam, E, 100 + H)
+            sig = float(rng.choice([0.05, 0.3, 1.0]))
+            tr = np.clip(_noisy_lines(pr, n_per, H, rng, sig), -0.05, 5.05).reshape(E * n_per, H, 2)
+            env = np.repeat(np.arange(E, dtype=np.int32), n_per)
+            if H % 2:                                   # shuffled order: the wall cache must follow env_id
+                perm = rng.permutation(len(tr))
+                tr, env = tr[perm], env[perm]
+            tr, env = tr[:-1 - (H % 3)], env[:-1 - (H % 3)]
+            v_ref, c_ref = colchk_ref.maze2d_swept(tr, env, pr["boxes"], hext, legacy_div=legacy)
+            v, c = pmp_b200.colchk_maze2d_swept(torch.tensor(tr, device=DEV), env, pr["boxes"], hext, legacy_div=legacy)
+            assert np.array_equal(v.cpu().numpy(), v_ref), (H, fam)
+            assert np.array_equal(c.cpu().numpy(), c_ref), (H, fam)
 
 
 def test_pick_multi_horizon_vs_oracle():
