@@ -162,23 +162,9 @@ __global__ void __launch_bounds__(WARPS * 32) maze2d_swept_kernel(
 // K = int(d / eps) interior points per segment: when |b - a|^2 < (1.8 eps)^2 the quotient is < 2 whatever the
 // rounding, the reference's `for k in range(1, K)` is empty, and the square root and the (float64) division are
 // skipped; otherwise the reference's exact operations run.  valid / n_checks are bit-identical to the sequential walk.
-struct SegR {
-    bool ok;
-    int cnt;
-};
-__device__ __forceinline__ SegR m2d_segment(const Maze& e, float2 a, float2 b, bool inl_a, bool inl_b, bool col_a,
-                                            bool col_b, double eps, float thr2, int legacy_div) {
-    SegR r;
-    if (!(inl_a && inl_b)) { r.ok = false; r.cnt = 0; return r; }
-    if (col_a) { r.ok = false; r.cnt = 1; return r; }
-    if (col_b) { r.ok = false; r.cnt = 2; return r; }
-    r.ok = true;
-    r.cnt = 2;
-    const float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y);
-    const float cx = fminf(fmaxf(b.x, e.lox), e.hix), cy = fminf(fmaxf(b.y, e.loy), e.hiy);
-    const float fx = fabsf(__fsub_rn(cx, a.x)), fy = fabsf(__fsub_rn(cy, a.y));
-    const float ss = __fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy));
-    if (ss < thr2) return r;                    // K <= 1: no interior point
+// a segment whose endpoints are inside the limits and collision free: the reference's interior points (K = int(d / eps))
+__device__ __noinline__ bool m2d_interior(const float4* __restrict__ walls, int nw, float lox, float loy, float hix, float hiy,
+                                          float2 a, float dx, float dy, float ss, double eps, int legacy_div, int& cnt) {
     const float d = __fsqrt_rn(ss);
     int K;
     if (legacy_div) K = (int)__ddiv_rn((double)d, eps);
@@ -187,9 +173,14 @@ __device__ __forceinline__ SegR m2d_segment(const Maze& e, float2 a, float2 b, b
         const float coef = (float)__ddiv_rn((double)k, (double)K);
         const float px = __fadd_rn(a.x, __fmul_rn(coef, dx));
         const float py = __fadd_rn(a.y, __fmul_rn(coef, dy));
-        if (!m2d_state_fp(e, px, py, r.cnt)) { r.ok = false; return r; }
+        if (!(px >= lox && py >= loy && px <= hix && py <= hiy)) return false;      // _state_fp: outside the limits, not counted
+        cnt += 1;
+        for (int i = 0; i < nw; ++i) {
+            const float4 q = walls[i];
+            if (px >= q.x && py >= q.y && px <= q.z && py <= q.w) return false;
+        }
     }
-    return r;
+    return true;
 }
 
 template <int W>
@@ -197,13 +188,10 @@ __global__ void __launch_bounds__(WARPS * 32) maze2d_swept16_kernel(
     const float* __restrict__ traj, const int32_t* __restrict__ env_id, int N, int H, const double* __restrict__ cen,
     const double* __restrict__ hext, int nw, float lox, float loy, float hix, float hiy, double eps, float thr2,
     double margin, int legacy_div, uint8_t* __restrict__ valid, int32_t* __restrict__ nchk) {
-    __shared__ float sm[2 * WARPS][4 * MAXW];
+    __shared__ float4 sm[2 * WARPS][MAXW];       // per half warp: (lo.x, lo.y, hi.x, hi.y) thresholds of every wall
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int half = lane >> 4, hl = lane & 15;
-    float* const walls = sm[2 * warp + half];
-    Maze e;
-    e.lox = lox; e.loy = loy; e.hix = hix; e.hiy = hiy;
-    e.lo_f = walls; e.hi_f = walls + 2 * MAXW; e.nw = nw;
+    float4* const walls = sm[2 * warp + half];
     int cur_env = -1;
     const int npair = (N + 1) >> 1;
     // the waypoints and the environment id of the NEXT trajectory are requested before the current one is evaluated
@@ -212,15 +200,14 @@ __global__ void __launch_bounds__(WARPS * 32) maze2d_swept16_kernel(
     auto fetch = [&](int pair) {
         const int n = 2 * pair + half;
         const bool act = pair < npair && n < N;
-        const float2* t = reinterpret_cast<const float2*>(traj + (size_t)(act ? n : 0) * H * 2);
+        const float2* t = reinterpret_cast<const float2*>(traj) + (size_t)(act ? n : 0) * H + hl * W;
 #pragma unroll
-        for (int i = 0; i < W; ++i) {
-            const int idx = hl * W + i;
-            wn[i] = (act && idx < H) ? __ldg(t + idx) : make_float2(0.f, 0.f);
-        }
+        for (int i = 0; i < W; ++i) wn[i] = (act && hl * W + i < H) ? __ldg(t + i) : make_float2(0.f, 0.f);
         envn = act ? __ldg(env_id + n) : -1;
     };
     fetch(blockIdx.x * WARPS + warp);
+    // number of this lane's segments (segment s joins waypoints s, s + 1; s < H - 1)
+    const int nseg = min(W, max(0, H - 1 - hl * W));
     for (int pair = blockIdx.x * WARPS + warp; pair < npair; pair += gridDim.x * WARPS) {
         const int n = 2 * pair + half;
         const bool active = n < N;
@@ -234,36 +221,51 @@ __global__ void __launch_bounds__(WARPS * 32) maze2d_swept16_kernel(
             for (int i = hl; i < nw; i += 16) {
                 const double* c = cen + ((size_t)env * nw + i) * 2;
                 const double* h = hext + ((size_t)env * nw + i) * 2;
-                walls[2 * i] = strictly_above(__dsub_rn(__dsub_rn(c[0], h[0]), margin));
-                walls[2 * i + 1] = strictly_above(__dsub_rn(__dsub_rn(c[1], h[1]), margin));
-                walls[2 * MAXW + 2 * i] = strictly_below(__dadd_rn(__dadd_rn(c[0], h[0]), margin));
-                walls[2 * MAXW + 2 * i + 1] = strictly_below(__dadd_rn(__dadd_rn(c[1], h[1]), margin));
+                walls[i] = make_float4(strictly_above(__dsub_rn(__dsub_rn(c[0], h[0]), margin)),
+                                       strictly_above(__dsub_rn(__dsub_rn(c[1], h[1]), margin)),
+                                       strictly_below(__dadd_rn(__dadd_rn(c[0], h[0]), margin)),
+                                       strictly_below(__dadd_rn(__dadd_rn(c[1], h[1]), margin)));
             }
             cur_env = env;
         }
         __syncwarp();
+        // every waypoint once: inside the limits (bit 0), inside an inflated wall (bit 1); branch free, one broadcast
+        // shared-memory load per wall for the lane's W waypoints
         bool inl[W + 1], col[W + 1];
 #pragma unroll
         for (int i = 0; i < W; ++i) {
-            inl[i] = m2d_valid(e, w[i].x, w[i].y);
-            col[i] = inl[i] && m2d_collides(e, w[i].x, w[i].y);
+            inl[i] = w[i].x >= lox && w[i].y >= loy && w[i].x <= hix && w[i].y <= hiy;
+            col[i] = false;
+        }
+        for (int k = 0; k < nw; ++k) {
+            const float4 q = walls[k];
+#pragma unroll
+            for (int i = 0; i < W; ++i) col[i] = col[i] | ((w[i].x >= q.x) & (w[i].y >= q.y) & (w[i].x <= q.z) & (w[i].y <= q.w));
         }
         // the first waypoint of the next lane closes this lane's last segment
         w[W].x = __shfl_down_sync(0xffffffffu, w[0].x, 1, 16);
         w[W].y = __shfl_down_sync(0xffffffffu, w[0].y, 1, 16);
-        const unsigned f0 = (inl[0] ? 1u : 0u) | (col[0] ? 2u : 0u);
-        const unsigned fn = __shfl_down_sync(0xffffffffu, f0, 1, 16);
+        const unsigned fn = __shfl_down_sync(0xffffffffu, (inl[0] ? 1u : 0u) | (col[0] ? 2u : 0u), 1, 16);
         inl[W] = (fn & 1u) != 0;
         col[W] = (fn & 2u) != 0;
-        int part = 0;          // checks of this lane's segments up to and including its first failing one
-        bool failed = false;
+        // _edge_fp per segment, in order, stopping at the lane's first failure: 0 checks when an endpoint is outside the
+        // limits, 1 when the first endpoint collides, 2 when the second does, 2 + interior points otherwise
+        int part = 0;
+        bool failed = !active;
 #pragma unroll
         for (int j = 0; j < W; ++j) {
-            const int sgi = hl * W + j;
-            if (active && sgi < H - 1 && !failed) {
-                const SegR r = m2d_segment(e, w[j], w[j + 1], inl[j], inl[j + 1], col[j], col[j + 1], eps, thr2, legacy_div);
-                part += r.cnt;
-                failed = !r.ok;
+            if (j < nseg && !failed) {
+                if (!(inl[j] && inl[j + 1])) failed = true;
+                else if (col[j]) { part += 1; failed = true; }
+                else if (col[j + 1]) { part += 2; failed = true; }
+                else {
+                    part += 2;
+                    // both endpoints are inside the limits, so the reference's clipped end point is the end point itself
+                    const float dx = __fsub_rn(w[j + 1].x, w[j].x), dy = __fsub_rn(w[j + 1].y, w[j].y);
+                    const float ss = __fadd_rn(__fmul_rn(fabsf(dx), fabsf(dx)), __fmul_rn(fabsf(dy), fabsf(dy)));
+                    if (!(ss < thr2))            // K >= 2 possible: the reference's exact square root, division and points
+                        failed = !m2d_interior(walls, nw, lox, loy, hix, hiy, w[j], dx, dy, ss, eps, legacy_div, part);
+                }
             }
         }
         // segments after the first failing one are never evaluated by the reference: lanes past the lowest failing lane drop out
