@@ -175,3 +175,8 @@ class PolicyCompose(Policy):
         self.ddim_steps = ddim_steps
         for dm in self.diffusion_model_list:
             dm.ddim_num_inference_steps = ddim_steps
+
+
+from .._overlay import reference_fallback as _reference_fallback  # noqa: E402
+
+__getattr__ = _reference_fallback(__name__)   # overlay mode: symbols outside the hot path come from the reference's file

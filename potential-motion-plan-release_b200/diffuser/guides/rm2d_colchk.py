@@ -57,3 +57,8 @@ class RM2DCollisionChecker(KukaCollisionChecker):
             return self.check_single_traj(traj, env)
         finally:
             self.use_collision_eps = keep
+
+
+from .._overlay import reference_fallback as _reference_fallback  # noqa: E402
+
+__getattr__ = _reference_fallback(__name__)   # overlay mode: symbols outside the hot path come from the reference's file

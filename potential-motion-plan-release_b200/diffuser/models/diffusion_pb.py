@@ -303,3 +303,8 @@ class GaussianDiffusionPB(nn.Module):
 
     def loss(self, *args, **kwargs):
         raise NotImplementedError('training (double backward through the U-Net) is outside the B200 hot path')
+
+
+from .._overlay import reference_fallback as _reference_fallback  # noqa: E402
+
+__getattr__ = _reference_fallback(__name__)   # overlay mode: symbols outside the hot path come from the reference's file

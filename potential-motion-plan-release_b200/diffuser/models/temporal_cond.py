@@ -176,3 +176,8 @@ class TemporalUnet_WCond(nn.Module):
         eng = self.engine()
         wemb = eng.wall_embed(walls_loc[:n_cond]) if n_cond > 0 else None
         return eng.eps(x, time, wemb, n_cond=n_cond)
+
+
+from .._overlay import reference_fallback as _reference_fallback  # noqa: E402
+
+__getattr__ = _reference_fallback(__name__)   # overlay mode: symbols outside the hot path come from the reference's file

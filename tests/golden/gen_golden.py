@@ -382,7 +382,31 @@ def gen_pick():
     print("pick: success %.2f, horizon hist %s, mean checks %.1f" % (suc.mean(), np.bincount(chosen_h.ravel(), minlength=3), cnt.mean()))
 
 
+def gen_logdir():
+    """model_config.pkl / diffusion_config.pkl written by the REFERENCE's own Config class (diffuser/utils/config.py:22-39)
+    with the reference model classes as `_class`, exactly as scripts/train.py:64-102 does: the files a trained logdir
+    holds.  The drop-in must unpickle them to its own classes (tests/test_overlay_seam.py, test_gpu_parity.py)."""
+    import importlib.util
+    U, G = refshim.load_models()
+    spec = importlib.util.spec_from_file_location("diffuser.utils.config", os.path.join(refshim.REF_ROOT, "diffuser", "utils", "config.py"))
+    cfgmod = importlib.util.module_from_spec(spec)
+    out = os.path.join(HERE, "logdir_m2d")
+    os.makedirs(out, exist_ok=True)
+    a = synth.arch("m2d")
+    with refshim.quiet():
+        import sys as _sys
+        _sys.modules["diffuser.utils.config"] = cfgmod      # the pickle records the class by this dotted path
+        spec.loader.exec_module(cfgmod)
+        cfgmod.Config(U, savepath=(out, "model_config.pkl"), verbose=False, **a["unet"])
+        cfgmod.Config(G, savepath=(out, "diffusion_config.pkl"), verbose=False, **a["diffusion"])
+        del _sys.modules["diffuser.utils.config"]
+    for f in ("model_config.pkl", "diffusion_config.pkl"):
+        raw = open(os.path.join(out, f), "rb").read()
+        assert b"diffuser.utils.config" in raw and b"diffuser.models." in raw
+        print("logdir", f, len(raw), "bytes")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk", "concave", "replan", "pick", "resample", "resample_compose"]
+    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk", "concave", "replan", "pick", "resample", "resample_compose", "logdir"]
     for w in which:
         globals()["gen_" + w]()
