@@ -1,0 +1,22 @@
+#!/bin/bash
+# Collects the measured artefacts of a round on one B200 (run through gpurun from the repo root):
+#   bash profiles/collect.sh r2       -> gpurun_out/r2_*   (then `python profiles/summarize.py ...` in the build container)
+# Order: tests, plain bench, reference arm, and only then the ncu passes of the same commands.
+tag=${1:-rX}
+out=gpurun_out
+mkdir -p $out
+python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest.log
+python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err || exit 1
+python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_reference_arm.json 2> $out/${tag}_reference_arm.err
+python bench.py --workload eval200 --steps 20 --warmup 5 > $out/${tag}_eval200.json 2> $out/${tag}_eval200.err
+# launch list of the bench command (direct launches; one step of the full 10,000-problem workload)
+ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1500 -c 800 --csv --log-file $out/${tag}_launches.csv \
+    python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline > $out/${tag}_ncu_launches.log 2>&1
+# full capture: one whole eps evaluation (60 conv launches, every shape class) at the bench's chunk size
+ncu --set full --import-source on --clock-control none -k regex:conv_tc_kernel --launch-skip 120 --launch-count 60 \
+    -f -o $out/${tag}_conv python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline > $out/${tag}_ncu_conv.log 2>&1
+# full capture of the HBM-bound kernels of the path (sampler update, swept check, Kuka sphere check)
+python tests/gpu_profile_aux.py > $out/${tag}_aux_plain.log 2>&1 && \
+ncu --set full --import-source on --clock-control none -k regex:'step_kernel|swept|kuka_kernel' --launch-skip 0 --launch-count 12 \
+    -f -o $out/${tag}_aux python tests/gpu_profile_aux.py > $out/${tag}_ncu_aux.log 2>&1
+ls -la $out/${tag}_*

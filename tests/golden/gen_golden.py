@@ -406,7 +406,61 @@ def gen_logdir():
         print("logdir", f, len(raw), "bytes")
 
 
+def train_inputs(fam, B, seed):
+    """deterministic training batch: normalised trajectories [B,H,D] (noisy straight segments), their start / goal
+    conditions and the wall vectors in the dataset's [B,1,Wd] layout (diffusion_pb.py:531-534)"""
+    a = synth.arch(fam)
+    H, D = a["unet"]["horizon"], a["obs_dim"]
+    pr = synth.make_problems(fam, B, seed)
+    lo, hi = pr["lo"], pr["hi"]
+    s = torch.tensor(synth.normalize(pr["start"], lo, hi))[:, None, :]
+    g = torch.tensor(synth.normalize(pr["goal"], lo, hi))[:, None, :]
+    al = torch.linspace(0, 1, H)[None, :, None]
+    gen = torch.Generator().manual_seed(seed)
+    x = (s * (1 - al) + g * al + 0.05 * torch.randn(B, H, D, generator=gen)).clamp(-1, 1)
+    return a, x.contiguous(), torch.tensor(pr["walls"])[:, None, :].contiguous()
+
+
+def grad_digest(name, g):
+    """compact fingerprint of one gradient tensor (the full gradients of a 15-43 M parameter model do not belong in
+    the repository): L2 norm, sum, two fixed pseudo-random projections and the first 32 elements"""
+    g = g.detach().double().reshape(-1)
+    gen = torch.Generator().manual_seed(synth._name_seed(name, 77) % (2 ** 31))
+    r1 = torch.randn(g.numel(), generator=gen, dtype=torch.float64)
+    r2 = torch.randn(g.numel(), generator=gen, dtype=torch.float64)
+    head = torch.zeros(32, dtype=torch.float64)
+    head[:min(32, g.numel())] = g[:32]
+    return np.concatenate([[g.norm().item(), g.sum().item(), (g * r1).sum().item(), (g * r2).sum().item()], head.numpy()])
+
+
+def gen_train():
+    """loss value and parameter gradients of the REFERENCE's training step: GaussianDiffusionPB.loss (diffusion_pb.py:
+    518-545) in train mode + loss.backward() (training_pbdiff.py:123-129), with the random draws (t, noise, concept
+    dropout) of that call recorded so the restatement oracle/train_ref.py and the CUDA step can repeat them"""
+    for fam, B in (("m2d", 4), ("dualkuka", 2)):
+        a, x, walls = train_inputs(fam, B, 21)
+        _, m, d, sd = build_ref(fam)
+        m.train(); d.train()
+        H, D = x.shape[1], x.shape[2]
+        cond = {0: x[:, 0].clone(), H - 1: x[:, -1].clone()}
+        torch.manual_seed(5); np.random.seed(2)
+        with refshim.quiet():
+            loss, info = d.loss(x.clone(), cond, walls.clone())
+            loss.backward()
+        # the same draws, in the reference's order: t (diffusion_pb.py:536), noise (:481), dropout mask (temporal_cond.py:268-270)
+        torch.manual_seed(5); np.random.seed(2)
+        t = torch.randint(0, d.n_timesteps, (B,)).long()
+        noise = torch.randn_like(x)
+        keep = (np.random.rand(B) >= a["unet"]["network_config"]["concept_drop_prob"]).astype(np.float32)
+        names = [k for k, _ in m.named_parameters()]
+        dig = np.stack([grad_digest(k, p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in m.named_parameters()])
+        np.savez_compressed(os.path.join(HERE, "train_%s.npz" % fam), x=x.numpy(), walls=walls.numpy(), t=t.numpy(),
+                            noise=noise.numpy(), keep=keep, loss=float(loss), names=np.array(names), digest=dig,
+                            loss_weights=d.loss_fn.weights.numpy(), weight_seed=WEIGHT_SEED)
+        print("train", fam, "loss %.6f" % float(loss), "keep", keep, "t", t.tolist(), "|g| %.4e" % float(np.sqrt((dig[:, 0] ** 2).sum())))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk", "concave", "replan", "pick", "resample", "resample_compose", "logdir"]
+    which = sys.argv[1:] or ["unet", "sample", "compose", "colchk", "concave", "replan", "pick", "resample", "resample_compose", "logdir", "train"]
     for w in which:
         globals()["gen_" + w]()
