@@ -157,6 +157,45 @@ typedef struct {
 } pmp_sample_args;
 int pmp_sample(const pmp_sample_args *a, void *stream);
 
+
+/* ---- training step: GaussianDiffusionPB.loss + loss.backward() (diffuser/models/diffusion_pb.py:480-545,
+ * utils/training_pbdiff.py:118-131), i.e. the energy loss 0.5*mean(w*(dE/dx - noise)^2) and its gradient with respect to
+ * every parameter (a second-order pass through the U-Net: forward, backward-data, tangent forward, reverse over the pair),
+ * then torch.optim.Adam.step + EMA.update_model_average (training_pbdiff.py:133-140, train_utils.py:15-31).
+ *
+ * The caller owns ONE flat float32 parameter arena and ONE flat gradient arena (every nn.Parameter of the drop-in model is a
+ * view into them, reference layouts).  pmp_train_bind names the arenas: keys[i] (state-dict name without "model.") starts at
+ * element offsets[i]; every weight given to pmp_model_set_weight must appear. */
+int pmp_train_bind(pmp_model *m, int n, const char *const *keys, const int64_t *offsets,
+                   float *params_dev, float *grads_dev, int64_t total);
+/* re-layouts the current parameter arena for the kernels (call after every optimizer step / load_state_dict);
+ * rebuild_tables != 0 also rebuilds the sampler's time-embedding tables so pmp_sample sees the new weights. */
+int pmp_train_sync_weights(pmp_model *m, int rebuild_tables, void *stream);
+typedef struct {
+    const float *x_noisy_dev;        /* [B,H,D] q_sample output with the start/goal rows conditioned (:483-487) */
+    const int64_t *t_dev;            /* [B] diffusion step of every sample (:536) */
+    const float *walls_dev;          /* [B,wall_len] */
+    int32_t wall_len;
+    const float *noise_dev;          /* [B,H,D] regression target (:505) */
+    const float *keep_dev;           /* [B] 1 = keep the wall condition, 0 = concept dropped (temporal_cond.py:266-270) */
+    const float *loss_weights_dev;   /* [H,D] loss_fn.weights (:112-134) */
+    int32_t B, H;
+    float *loss_dev;                 /* [1] out: the value `loss` returns (0.5 * weighted MSE) */
+    float *eps_dev;                  /* [B,H,D] out or NULL: the model output dE/dx */
+} pmp_train_args;
+/* grads arena += d loss / d parameters (zero it first, like optimizer.zero_grad()); no host synchronisation */
+int pmp_train_loss_grad(pmp_model *m, const pmp_train_args *a, void *stream);
+/* q_sample + apply_conditioning (+ set_loss_noise) (:468-487, helpers.py:168-178): x_noisy = sqrt_acp[t] x0 +
+ * sqrt_1m_acp[t] noise with rows 0 and H-1 copied from x0 (zero_cond_noise: their noise target zeroed in place) */
+int pmp_q_sample(const float *x0_dev, float *noise_dev, const int64_t *t_dev, const float *sqrt_acp_dev,
+                 const float *sqrt_1m_acp_dev, int B, int H, int D, int zero_cond_noise, float *x_noisy_dev, void *stream);
+/* fused Adam (no weight decay / amsgrad; g is multiplied by grad_scale first, e.g. 1/world_size after an allreduce-sum)
+ * + EMA of the parameters over flat arenas.  step counts from 1.  ema_mode 0: none, 1: ema = beta*ema + (1-beta)*p,
+ * 2: ema = p (reset_parameters before step_start_ema). */
+int pmp_adam_ema_step(float *p_dev, const float *g_dev, float *m_dev, float *v_dev, float *ema_dev, int64_t n,
+                      float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                      int ema_mode, float ema_beta, void *stream);
+
 /* ---- un-normalisation: LimitsNormalizer.unnormalize (datasets/normalization.py:151-162) */
 int pmp_unnormalize(const float *x_dev, const float *lo_dev, const float *hi_dev,
                     float *out_dev, int64_t n_rows, int D, void *stream);

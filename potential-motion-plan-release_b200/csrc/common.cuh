@@ -222,4 +222,43 @@ int launch_pick_first_valid(const uint8_t* valid, const int32_t* nchk, int n_pro
                             int32_t* chosen, uint8_t* success, int32_t* total, cudaStream_t st);
 int launch_fill_i64(int64_t* p, int64_t v, size_t n, cudaStream_t st);
 
+// training step (train.cu); every pointer is a device pointer, tensors channels-last [R][H][C] unless noted
+int launch_gn_tangent(const float* yd, int ldyd, const float* yhat, const float* rstd, const float* gamma, const float* beta,
+                      const float* addend, int ldad, float* zd, int ldz, __nv_bfloat16* zh, __nv_bfloat16* zl, float* yhd, float* s,
+                      int R, int Hl, int C, cudaStream_t st);
+int launch_gn_adjoint(const float* zbar, int ldzb, const float* gz, int ldgz, const float* yhat, const float* yhd, const float* rstd,
+                      const float* s, const float* gamma, const float* beta, float* ybar, __nv_bfloat16* yh, __nv_bfloat16* yl,
+                      float* dgamma, float* dbeta, int R, int Hl, int C, cudaStream_t st);
+// dW[co][ci][k] += sum_{r,ho} O1[r,ho,co] I1[r,ho*stride+k-pad,ci] (+ the same with O2, I2 when O2 != null)
+int launch_wgrad(const float* O1, int ldo1, const float* I1, int ldi1, const float* O2, int ldo2, const float* I2, int ldi2,
+                 int Ho, int Co, int Hi, int Ci, int stride, int pad, int KS, int R, float* dW, cudaStream_t st);
+int launch_colsum(const float* X, int ld, int rows, int C, float* out, cudaStream_t st);
+int launch_hsum(const float* X, int ld, int R, int Hl, int C, float* out, int ldo, cudaStream_t st);
+int launch_lin_dgrad(const float* dout, int lddo, int nout, const float* W, int ldw, float* din, int lddi, int nin, int rows,
+                     int accumulate, cudaStream_t st);
+int launch_lin_wgrad(const float* dout, int lddo, int nout, const float* in, int ldin, int nin, int rows, float* dW, int lddw,
+                     float* db, cudaStream_t st);
+int launch_act_fwd(const float* x, int ldx, float* y, int ldy, int rows, int cols, int kind, cudaStream_t st);
+int launch_act_bwd(const float* x, int ldx, const float* dy, int lddy, float* dx, int lddx, int rows, int cols, int kind,
+                   int accumulate, cudaStream_t st);
+int launch_ln_fwd(const float* x, int ldx, int n, const float* g, const float* b, float* y, int ldy, float* xhat, float* rstd,
+                  int rows, cudaStream_t st);
+int launch_ln_bwd(const float* dy, int lddy, const float* xhat, const float* rstd, const float* g, int n, float* dx, int lddx,
+                  float* dg, float* db, int rows, int accumulate, cudaStream_t st);
+int launch_attn_fwd(const float* qkv, const float* x, float* att, float* out, int R, int nt, float scale, cudaStream_t st);
+int launch_attn_bwd(const float* qkv, const float* att, const float* dout, float* dqkv, int R, int nt, float scale, cudaStream_t st);
+int launch_pe_fwd(const float* walls, size_t n_coord, int td, int oct, float norm, float* f, cudaStream_t st);
+int launch_sinus(const int64_t* t, int R, int dim, float neg_k, float* out, cudaStream_t st);
+int launch_copy2d(const float* src, int lds, int src_rows, float* dst, int ldd, int rows, int cols, const float* rowscale,
+                  int accumulate, cudaStream_t st);
+int launch_loss(const float* eps, const float* noise, const float* w, int HD, size_t n, float* v, __nv_bfloat16* vh,
+                __nv_bfloat16* vl, float* loss, cudaStream_t st);
+int launch_qsample(const float* x0, float* noise, const int64_t* t, const float* sa, const float* sb, int R, int H, int D,
+                   int zero_cond_noise, float* xn, cudaStream_t st);
+int launch_adam_ema(float* p, const float* g, float* m, float* v, float* ema, size_t n, float lr, float beta1, float beta2,
+                    float eps, int step, float grad_scale, int ema_mode, float ema_beta, cudaStream_t st);
+int launch_repack(const float* P, const uint32_t* map, float* arena, size_t n, cudaStream_t st);
+int launch_planes(const float* w, int K, int C, int N, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
+int launch_split_planes(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);
+
 }  // namespace pmp

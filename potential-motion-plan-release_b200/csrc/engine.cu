@@ -111,6 +111,8 @@ struct ResB {
     size_t tmW = 0, tmB = 0;      // cfg 0: Linear(128->Cout); cfg 3: second Linear(256->Cout)
     size_t tm0W = 0, tm0B = 0;    // cfg 3: first Linear(128->256)
 };
+struct Packer16Rec { size_t src; int K, C, N; size_t hi, lo; };
+struct TrainState;
 struct PlainConv {  // down / up sampling
     int C = 0, KS = 0;
     size_t Wf = 0, Wb = 0, bias = 0;
@@ -141,7 +143,11 @@ struct pmp_model {
     float* arena = nullptr;   // packed weights on device
     size_t arena_n = 0;
     __nv_bfloat16* arena16 = nullptr;   // BF16x3 weight planes for the tcgen05 core
+    size_t arena16_n = 0;
+    std::vector<Packer16Rec> plane_recs;   // how arena16 derives from arena (training re-layout after an optimizer step)
+    pmp::TrainState* train = nullptr;    // bound flat parameter / gradient arenas (pmp_train_bind)
     float* temb_tab = nullptr;  // [T][dim]
+    int64_t* t_iota = nullptr;  // [T] 0..T-1
     float* embT = nullptr;      // cfg0: [T][Ctot] ; cfg3: Ht [T][nblk*hid]
     // per-call tables (grown on demand)
     float* embR = nullptr; size_t embR_n = 0;   // cfg0: [B][Ctot]; cfg3: Hw [B][nblk*hid]
@@ -227,7 +233,9 @@ struct Packer16 {
         memcpy(&f, &u, 4);
         return f;
     }
-    TcW add(const std::vector<float>& w /*[K][C][N]*/, int K, int C, int N) {
+    typedef Packer16Rec Rec;
+    std::vector<Rec> recs;   // every plane pair with the fp32 arena offset of the [K][C][N] weight it was split from
+    TcW add(const std::vector<float>& w /*[K][C][N]*/, int K, int C, int N, size_t src) {
         TcW t;
         if (C % 64 != 0) return t;   // N may be narrow (trajectory dimension): TMA zero-fills / over-reads unused columns
         const size_t n = (size_t)K * C * N;
@@ -245,6 +253,7 @@ struct Packer16 {
                     buf[off + stride + o] = l;
                 }
         t.ok = true; t.hi = off; t.lo = off + stride;
+        recs.push_back(Rec{src, K, C, N, t.hi, t.lo});
         return t;
     }
 };
@@ -304,10 +313,10 @@ static int pack_cb(pmp_model* m, Packer& pk, Packer16& pk16, const std::string& 
     std::vector<float> t;
     conv_fwd_layout(*w, t);
     cb.Wf = pk.add(t);
-    cb.tcf = pk16.add(t, 5, cb.Cin, cb.Cout);
+    cb.tcf = pk16.add(t, 5, cb.Cin, cb.Cout, cb.Wf);
     conv_bwd_layout(*w, t, true);
     cb.Wb = pk.add(t);
-    cb.tcb = pk16.add(t, 5, cb.Cout, cb.Cin);
+    cb.tcb = pk16.add(t, 5, cb.Cout, cb.Cin, cb.Wb);
     cb.bias = pk.add(b->v);
     cb.gamma = pk.add(g->v);
     cb.beta = pk.add(be->v);
@@ -331,10 +340,10 @@ static int pack_res(pmp_model* m, Packer& pk, Packer16& pk16, const std::string&
         std::vector<float> t;
         conv_fwd_layout(*w, t);
         rb.Rf = pk.add(t);
-        rb.tcRf = pk16.add(t, 1, Cin, Cout);
+        rb.tcRf = pk16.add(t, 1, Cin, Cout, rb.Rf);
         conv_bwd_layout(*w, t, false);
         rb.Rb = pk.add(t);
-        rb.tcRb = pk16.add(t, 1, Cout, Cin);
+        rb.tcRb = pk16.add(t, 1, Cout, Cin, rb.Rb);
         rb.Rbias = pk.add(b->v);
     }
     const int tdim = m->arch.dim + m->arch.wall_embed_dim;
@@ -359,7 +368,45 @@ static int pack_res(pmp_model* m, Packer& pk, Packer16& pk16, const std::string&
     return 0;
 }
 
-static int finalize_model(pmp_model* m) {
+// time-embedding tables from the packed arena: temb[t] and the t-only part of every block embedding
+static int build_time_tables(pmp_model* m, cudaStream_t st) {
+    const pmp_arch& a = m->arch;
+    int rc;
+    const int T = a.n_timesteps;
+    PMP_REQUIRE(T >= 1 && T <= 100000, "n_timesteps out of range");
+    if (!m->t_iota) {
+        PMP_CUDA_OK(cudaMalloc((void**)&m->t_iota, T * sizeof(int64_t)));
+        std::vector<int64_t> th(T);
+        for (int i = 0; i < T; ++i) th[i] = i;
+        PMP_CUDA_OK(cudaMemcpy(m->t_iota, th.data(), T * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
+    int64_t* tdev = m->t_iota;
+    const int tdim = a.dim + a.wall_embed_dim;
+    const int nblk = (int)m->blocks.size();
+    if (!m->temb_tab) PMP_CUDA_OK(cudaMalloc((void**)&m->temb_tab, (size_t)T * a.dim * sizeof(float)));
+    const float neg_k = (float)(-(log(10000.0) / (double)(a.dim / 2 - 1)));
+    if ((rc = launch_time_mlp(m->A(m->tW1), m->A(m->tB1), m->A(m->tW3), m->A(m->tB3), a.dim, a.act, neg_k, tdev, T,
+                              m->temb_tab, st)))
+        return rc;
+    if (a.time_mlp_config == 0) {
+        if (!m->embT) PMP_CUDA_OK(cudaMalloc((void**)&m->embT, (size_t)T * m->Ctot * sizeof(float)));
+        for (auto& b : m->blocks)
+            if ((rc = launch_small_linear(m->temb_tab, a.dim, a.dim, m->A(b.tmW), tdim, 0, m->A(b.tmB), 1, a.act,
+                                          m->embT + b.eoff, m->Ctot, b.Cout, T, 0, st)))
+                return rc;
+    } else {
+        if (!m->embT) PMP_CUDA_OK(cudaMalloc((void**)&m->embT, (size_t)T * nblk * m->hid * sizeof(float)));
+        for (int i = 0; i < nblk; ++i)
+            if ((rc = launch_small_linear(m->temb_tab, a.dim, a.dim, m->A(m->blocks[i].tm0W), tdim, 0,
+                                          m->A(m->blocks[i].tm0B), 0, a.act, m->embT + (size_t)i * m->hid,
+                                          nblk * m->hid, m->hid, T, 0, st)))
+                return rc;
+    }
+    return 0;
+}
+
+// lays every weight out for the kernels (offsets are stored in the model; same offsets on every call)
+static int pack_all(pmp_model* m, Packer& pk, Packer16& pk16, size_t (&v_top)[11], size_t (&v_l)[8][9]) {
     const pmp_arch& a = m->arch;
     PMP_REQUIRE(a.n_mults >= 2 && a.n_mults <= PMP_MAX_LEVELS, "n_mults must be 2..%d", PMP_MAX_LEVELS);
     PMP_REQUIRE(a.time_mlp_config == 0 || a.time_mlp_config == 3, "time_mlp_config %d is not built (0 or 3)", a.time_mlp_config);
@@ -367,8 +414,6 @@ static int finalize_model(pmp_model* m) {
     m->nl = a.n_mults;
     m->dims.assign(1, a.transition_dim);
     for (int i = 0; i < a.n_mults; ++i) m->dims.push_back(a.dim * a.dim_mults[i]);
-    Packer pk;
-    Packer16 pk16;
     int rc;
     m->blocks.clear();
     char nm[128];
@@ -416,8 +461,8 @@ static int finalize_model(pmp_model* m) {
         PlainConv& pc = m->downc[L];
         pc.present = true; pc.C = m->dims[L + 1]; pc.KS = 3;
         std::vector<float> t;
-        conv_fwd_layout(*w, t); pc.Wf = pk.add(t); pc.tcf = pk16.add(t, 3, pc.C, pc.C);
-        conv_bwd_layout(*w, t, false); pc.Wb = pk.add(t); pc.tcb = pk16.add(t, 3, pc.C, pc.C);
+        conv_fwd_layout(*w, t); pc.Wf = pk.add(t); pc.tcf = pk16.add(t, 3, pc.C, pc.C, pc.Wf);
+        conv_bwd_layout(*w, t, false); pc.Wb = pk.add(t); pc.tcb = pk16.add(t, 3, pc.C, pc.C, pc.Wb);
         pc.bias = pk.add(b->v);
     }
     for (int ind = 0; ind < m->nl - 1; ++ind) {
@@ -432,7 +477,7 @@ static int finalize_model(pmp_model* m) {
         std::vector<float> f, bw;
         convT_layouts(*w, f, bw);
         pc.Wf = pk.add(f); pc.Wb = pk.add(bw);
-        pc.tcf = pk16.add(f, 4, C, C); pc.tcb = pk16.add(bw, 4, C, C);
+        pc.tcf = pk16.add(f, 4, C, C, pc.Wf); pc.tcb = pk16.add(bw, 4, C, C, pc.Wb);
         pc.bias = pk.add(b->v);
     }
     if ((rc = pack_cb(m, pk, pk16, "final_conv.0.", m->finalcb))) return rc;
@@ -442,7 +487,7 @@ static int finalize_model(pmp_model* m) {
         PMP_REQUIRE(w->shape[0] == a.transition_dim && w->shape[1] == a.dim, "final_conv.1.weight shape");
         std::vector<float> t;
         conv_fwd_layout(*w, t); m->fin1Wf = pk.add(t);
-        m->fin1tc = pk16.add(t, 1, a.dim, a.transition_dim);
+        m->fin1tc = pk16.add(t, 1, a.dim, a.transition_dim, m->fin1Wf);
         conv_bwd_layout(*w, t, false); m->fin1Wb = pk.add(t);
         m->fin1b = pk.add(b->v);
     }
@@ -452,8 +497,9 @@ static int finalize_model(pmp_model* m) {
         m->tW1 = pk.add(w1->v); m->tB1 = pk.add(b1->v); m->tW3 = pk.add(w3->v); m->tB3 = pk.add(b3->v);
     }
     // ---- ViT
-    size_t v_ln0w = 0, v_ln0b = 0, v_l1w, v_l1b, v_l2w, v_l2b, v_l3w, v_l3b, v_ln1w, v_ln1b, v_cls;
-    size_t v_l[8][9];
+    size_t &v_ln0w = v_top[0], &v_ln0b = v_top[1], &v_l1w = v_top[2], &v_l1b = v_top[3], &v_l2w = v_top[4], &v_l2b = v_top[5],
+           &v_l3w = v_top[6], &v_l3b = v_top[7], &v_ln1w = v_top[8], &v_ln1b = v_top[9], &v_cls = v_top[10];
+    v_ln0w = v_ln0b = 0;
     {
         const std::string p = "wallLoc_encoder.";
         int i = 1;
@@ -493,6 +539,22 @@ static int finalize_model(pmp_model* m) {
             v_l[l][6] = pk.add(f0b->v); v_l[l][7] = pk.add(f3w->v); v_l[l][8] = pk.add(f3b->v);
         }
     }
+    return 0;
+}
+
+static int finalize_model(pmp_model* m) {
+    const pmp_arch& a = m->arch;
+    Packer pk;
+    Packer16 pk16;
+    size_t v_top[11], v_l[8][9];
+    int rc;
+    char nm[128];
+    (void)nm;
+    if ((rc = pack_all(m, pk, pk16, v_top, v_l))) return rc;
+    const size_t v_ln0w = v_top[0], v_ln0b = v_top[1], v_l1w = v_top[2], v_l1b = v_top[3], v_l2w = v_top[4], v_l2b = v_top[5],
+                 v_l3w = v_top[6], v_l3b = v_top[7], v_ln1w = v_top[8], v_ln1b = v_top[9], v_cls = v_top[10];
+    m->plane_recs = pk16.recs;
+    m->arena16_n = pk16.buf.size();
     // ---- upload
     if (m->arena) cudaFree(m->arena);
     m->arena = nullptr;
@@ -518,40 +580,12 @@ static int finalize_model(pmp_model* m) {
         v.fn_w[l] = m->A(v_l[l][3]); v.fn_b[l] = m->A(v_l[l][4]); v.f0_w[l] = m->A(v_l[l][5]);
         v.f0_b[l] = m->A(v_l[l][6]); v.f3_w[l] = m->A(v_l[l][7]); v.f3_b[l] = m->A(v_l[l][8]);
     }
-    // ---- time-embedding tables: temb[t] and the t-only part of every block embedding
-    const int T = a.n_timesteps;
-    PMP_REQUIRE(T >= 1 && T <= 100000, "n_timesteps out of range");
+    if (m->temb_tab) { cudaFree(m->temb_tab); m->temb_tab = nullptr; }
+    if (m->embT) { cudaFree(m->embT); m->embT = nullptr; }
+    if (m->t_iota) { cudaFree(m->t_iota); m->t_iota = nullptr; }
     cudaStream_t st = 0;
-    int64_t* tdev = nullptr;
-    PMP_CUDA_OK(cudaMalloc((void**)&tdev, T * sizeof(int64_t)));
-    std::vector<int64_t> th(T);
-    for (int i = 0; i < T; ++i) th[i] = i;
-    PMP_CUDA_OK(cudaMemcpy(tdev, th.data(), T * sizeof(int64_t), cudaMemcpyHostToDevice));
-    if (m->temb_tab) cudaFree(m->temb_tab);
-    if (m->embT) cudaFree(m->embT);
-    PMP_CUDA_OK(cudaMalloc((void**)&m->temb_tab, (size_t)T * a.dim * sizeof(float)));
-    const float neg_k = (float)(-(log(10000.0) / (double)(a.dim / 2 - 1)));
-    if ((rc = launch_time_mlp(m->A(m->tW1), m->A(m->tB1), m->A(m->tW3), m->A(m->tB3), a.dim, a.act, neg_k, tdev, T,
-                              m->temb_tab, st)))
-        return rc;
-    const int tdim = a.dim + a.wall_embed_dim;
-    const int nblk = (int)m->blocks.size();
-    if (a.time_mlp_config == 0) {
-        PMP_CUDA_OK(cudaMalloc((void**)&m->embT, (size_t)T * m->Ctot * sizeof(float)));
-        for (auto& b : m->blocks)
-            if ((rc = launch_small_linear(m->temb_tab, a.dim, a.dim, m->A(b.tmW), tdim, 0, m->A(b.tmB), 1, a.act,
-                                          m->embT + b.eoff, m->Ctot, b.Cout, T, 0, st)))
-                return rc;
-    } else {
-        PMP_CUDA_OK(cudaMalloc((void**)&m->embT, (size_t)T * nblk * m->hid * sizeof(float)));
-        for (int i = 0; i < nblk; ++i)
-            if ((rc = launch_small_linear(m->temb_tab, a.dim, a.dim, m->A(m->blocks[i].tm0W), tdim, 0,
-                                          m->A(m->blocks[i].tm0B), 0, a.act, m->embT + (size_t)i * m->hid,
-                                          nblk * m->hid, m->hid, T, 0, st)))
-                return rc;
-    }
+    if ((rc = build_time_tables(m, st))) return rc;
     PMP_CUDA_OK(cudaStreamSynchronize(st));
-    cudaFree(tdev);
     m->finalized = true;
     ++m->gen;
     return 0;
@@ -606,6 +640,42 @@ static ConvP geom_t2(int R, int Hin, int KS) {
 // ------------------------------------------------------------------ one eps evaluation
 typedef __nv_bfloat16 bf16;
 
+// forward activation view with its operand planes
+struct ActP : Act {
+    bf16* hi = nullptr;
+    bf16* lo = nullptr;
+};
+struct GradP {
+    float* raw = nullptr;
+    bf16 *raw_hi = nullptr, *raw_lo = nullptr;
+    int ldr = 0;
+    float* gy = nullptr;   // dense [R*Hl][C]
+    bf16 *gy_hi = nullptr, *gy_lo = nullptr;
+};
+// what a training step keeps of the forward (F) and backward-data (B1) passes of one eps evaluation: every tensor the
+// tangent pass and the second reverse pass read again (train_host.inc)
+struct TapeRes {
+    ActP x, mid;              // block input, CB0 output + embedding (input of CB1)
+    GradP gout;               // B1 gradient w.r.t. the block output (raw) and w.r.t. CB1's conv output (gy)
+    float* gmid = nullptr;    // B1 gradient w.r.t. mid (raw)
+    float* gy0 = nullptr;     // B1 gradient w.r.t. CB0's conv output
+    bf16 *gy0_hi = nullptr, *gy0_lo = nullptr;
+};
+struct TapePlain {
+    ActP in;                  // input of the down / up sampling conv
+    GradP gout;               // B1 gradient w.r.t. its output (raw)
+};
+struct Tape {
+    std::vector<TapeRes> res;
+    std::vector<TapePlain> down, up;
+    std::vector<int> Hl;
+    ActP fin_in;                         // input of final_conv.0
+    float* f = nullptr; bf16 *f_hi = nullptr, *f_lo = nullptr;   // its activation output
+    float* u = nullptr;                  // U-Net output
+    float* gf = nullptr;                 // B1 gradient w.r.t. f (raw)
+    float* gyf = nullptr; bf16 *gyf_hi = nullptr, *gyf_lo = nullptr;   // B1 gradient w.r.t. final_conv.0's conv output
+};
+
 struct Ctx {
     pmp_model* m;
     cudaStream_t st;
@@ -616,6 +686,8 @@ struct Ctx {
     const float* embRow;   // cfg0: embR rows of this chunk; cfg3: E rows of this chunk
     int x_row0 = 0, x_wrap = 0;   // the input holds x_wrap rows shared by both CFG halves: row r reads (x_row0 + r) mod x_wrap
     int rc = 0;
+    Tape* tape = nullptr;   // training step: keep an fp32 copy of every activation / gradient and record where they are
+    bool train() const { return tape != nullptr; }
     bool tc() const { return m->gemm_path >= 1; }
     float* alloc(size_t n) {
         n = (n + 3) & ~(size_t)3;
@@ -658,21 +730,8 @@ struct Ctx {
     }
 };
 
-// forward activation view with its operand planes
-struct ActP : Act {
-    bf16* hi = nullptr;
-    bf16* lo = nullptr;
-};
-struct GradP {
-    float* raw = nullptr;
-    bf16 *raw_hi = nullptr, *raw_lo = nullptr;
-    int ldr = 0;
-    float* gy = nullptr;   // dense [R*Hl][C]
-    bf16 *gy_hi = nullptr, *gy_lo = nullptr;
-};
-
 // tensor consumed only as the A operand of a tensor-core conv: BF16 planes suffice (no fp32 copy)
-static bool planes_only(const Ctx& c, int C) { return c.tc() && (C % 64) == 0 && c.H <= 128; }
+static bool planes_only(const Ctx& c, int C) { return !c.train() && c.tc() && (C % 64) == 0 && c.H <= 128; }
 // on gemm paths 1 and 3 the epilogue also takes residual terms as planes, so no activation or gradient between
 // 64-multiple-channel convs needs an fp32 copy at all (path 2's kernel still reads fp32 residuals)
 static bool planes_all(const Ctx& c, int C) { return planes_only(c, C) && c.m->gemm_path != 2 && !c.m->keep_fp32; }
@@ -696,7 +755,7 @@ static ActP view_act(const ActP& base, int off, int C) {
 
 static void set_emb(Ctx& c, ConvP& p, const ResB& b) {
     const pmp_model* m = c.m;
-    if (m->arch.time_mlp_config == 0) {
+    if (m->arch.time_mlp_config == 0 && !c.train()) {
         p.embT = m->embT; p.tidx = c.t; p.ldeT = m->Ctot; p.tmax = m->arch.n_timesteps - 1;
         p.embR = c.embRow; p.ldeR = m->Ctot; p.n_cond = c.n_cond;
     } else {
@@ -765,6 +824,7 @@ static void res_fwd(Ctx& c, int bi, const ActP& x, ActP& out) {
     q.out = out.p; q.ldo = out.ld; q.out_hi = out.hi; q.out_lo = out.lo;
     c.conv(q);
     out.C = Co; out.Hl = Hl; out.blk = bi;
+    if (c.train()) { c.tape->res[bi].x = x; c.tape->res[bi].mid = mid; }
     c.dbg("out:", b.pfx, out.p, out.ld == Co ? (int64_t)R * Hl * Co : 0);
 }
 
@@ -832,6 +892,12 @@ static GradP res_bwd(Ctx& c, int bi, const GradP& gout, const Act& x, const floa
     p.gn_bwd = 1; p.gamma = m->A(b.cb[0].gamma); p.beta = m->A(b.cb[0].beta);
     p.yhat = b.cb[0].yhat; p.ldy = Co; p.rstd = b.cb[0].rstd; p.gy = gy0; p.ldg = Co; p.act = m->arch.act;
     p.gy_hi = gy0_hi; p.gy_lo = gy0_lo;
+    if (c.train()) {
+        TapeRes& tr = c.tape->res[bi];
+        tr.gout = gout; tr.gy0 = gy0; tr.gy0_hi = gy0_hi; tr.gy0_lo = gy0_lo;
+        tr.gmid = c.alloc(n);
+        p.out = tr.gmid; p.ldo = Co;
+    }
     c.conv(p);
     ConvP q = geom_s1(R, Hl, 5);
     set_A1(q, gy0, gy0_hi, gy0_lo, Co, Co);
@@ -855,6 +921,13 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
     std::vector<int> Hl(nl);
     Hl[0] = H;
     for (int L = 1; L < nl; ++L) Hl[L] = m->has_down(L - 1) ? Hl[L - 1] / 2 : Hl[L - 1];
+    if (c.train()) {
+        *c.tape = Tape();
+        c.tape->res.resize(m->blocks.size());
+        c.tape->down.resize(nl);
+        c.tape->up.resize(nl);
+        c.tape->Hl = Hl;
+    }
     // concat buffers for skip levels 1..nl-1: [R][Hl][2*C]; level 0 skip is never consumed
     std::vector<ActP> cat(nl);
     for (int L = 1; L < nl; ++L) cat[L] = new_act(c, 2 * m->dims[L + 1], Hl[L]);
@@ -877,6 +950,7 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
             p.N = C; p.bias = m->A(m->downc[L].bias);
             p.out = d.p; p.ldo = d.ld; p.out_hi = d.hi; p.out_lo = d.lo;
             c.conv(p);
+            if (c.train()) c.tape->down[L].in = b;
             cur = d;
         } else {
             cur = b;
@@ -910,6 +984,7 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
             p.N = Co; p.bias = m->A(m->upc[ind].bias);
             p.out = o.p; p.ldo = o.ld; p.out_hi = o.hi; p.out_lo = o.lo;
             c.conv(p);
+            if (c.train()) c.tape->up[ind].in = b;
             cur = o;
         } else {
             cur = b;
@@ -939,6 +1014,7 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
         c.conv(p);
     }
     float* u = u_out ? u_out : c.alloc((size_t)R * H * D);
+    if (c.train()) { c.tape->fin_in = cur; c.tape->f = f; c.tape->f_hi = f_hi; c.tape->f_lo = f_lo; c.tape->u = u; }
     {
         if (energy && !c.dry && !c.rc) {
             cudaError_t e = cudaMemsetAsync(energy, 0, (size_t)R * sizeof(float), c.st);
@@ -964,6 +1040,11 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
         if (D <= 16) { p.inl_x = u; p.inl_ld = D; p.inl_D = D; p.inl_taps = 1; p.inl_mode = 1; p.inl_w = m->A(m->fin1Wb); }
         p.gn_bwd = 1; p.gamma = m->A(fcb.gamma); p.beta = m->A(fcb.beta); p.yhat = fcb.yhat; p.ldy = C0;
         p.rstd = fcb.rstd; p.gy = gyf; p.ldg = C0; p.gy_hi = gyf_hi; p.gy_lo = gyf_lo; p.act = m->arch.act;
+        if (c.train()) {
+            c.tape->gyf = gyf; c.tape->gyf_hi = gyf_hi; c.tape->gyf_lo = gyf_lo;
+            c.tape->gf = c.alloc((size_t)R * H * C0);
+            p.out = c.tape->gf; p.ldo = C0;
+        }
         c.conv(p);
     }
     GradP g;
@@ -980,6 +1061,7 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
     for (int ind = nl - 2; ind >= 0; --ind) {
         const int Ls = nl - 1 - ind, Cs = m->dims[Ls + 1], Co = m->dims[Ls], h = Hl[Ls];
         if (m->has_up(ind)) {
+            if (c.train()) c.tape->up[ind].gout = g;
             // Upsample1d backward: strided conv with the same weight (App. G item 6)
             ConvP p = geom_s2(R, h, 4);
             set_A1(p, g.raw, g.raw_hi, g.raw_lo, g.ldr, Co);
@@ -1019,6 +1101,7 @@ static int run_unet(Ctx& c, const float* x_in, float* eps_out, float* energy, fl
             g = res_bwd(c, 2 * L, g, lvl_in[L], sk ? skipg[L - 1] : nullptr, sk ? skipld[L - 1] : 0, nullptr, 0);
         } else {
             g = res_bwd(c, 2 * L, g, lvl_in[L], nullptr, 0, nullptr, 0);
+            if (c.train()) c.tape->down[L - 1].gout = g;
             // Downsample1d backward: transposed conv, output_padding 1 (App. G item 5)
             const int C = m->dims[L];
             ConvP p = geom_t2(R, Hl[L], 3);
@@ -1148,6 +1231,8 @@ static int eps_rows(pmp_model* m, const float* x, const int64_t* t, const float*
     return 0;
 }
 
+#include "train_host.inc"
+
 }  // namespace pmp
 
 // ====================================================================== C ABI
@@ -1201,6 +1286,11 @@ void pmp_model_destroy(pmp_model* m) {
                      m->s_eps, m->s_x2, m->s_xs, m->s_sg, m->s_wtab, m->s_tabs};
     for (float* b : bufs)
         if (b) cudaFree(b);
+    if (m->t_iota) cudaFree(m->t_iota);
+    if (m->train) {
+        if (m->train->map_dev) cudaFree(m->train->map_dev);
+        delete m->train;
+    }
     delete m;
 }
 
@@ -1267,6 +1357,80 @@ int pmp_unet_eps(pmp_model* m, const float* x, const int64_t* t, const float* we
     if ((rc = grow(&m->embR, &m->embR_n, (size_t)(n_cond > 0 ? n_cond : 1) * wall_table_width(m), (cudaStream_t)stream))) return rc;
     if ((rc = prepare_wall_tables(m, wemb, n_cond, m->embR, (cudaStream_t)stream))) return rc;
     return eps_rows(m, x, t, m->embR, n_cond, R, H, eps, energy, u, (cudaStream_t)stream);
+}
+
+
+// ---------------------------------------------------------------------------------------------- training step
+int pmp_train_bind(pmp_model* m, int n, const char* const* keys, const int64_t* offsets, float* params_dev, float* grads_dev,
+                   int64_t total) {
+    PMP_REQUIRE(m && m->finalized, "model not finalized");
+    PMP_REQUIRE(n > 0 && keys && offsets && params_dev && grads_dev && total > 0 && total < (int64_t)0xffffffff, "bad argument");
+    PMP_REQUIRE(m->arch.act == 0, "the training step is built for SiLU (energy-mode) networks only");
+    DeviceGuard guard(m->device);
+    if (!m->train) m->train = new TrainState();
+    TrainState* ts = m->train;
+    ts->P = params_dev; ts->G = grads_dev; ts->n = (size_t)total;
+    ts->off.clear();
+    for (int i = 0; i < n; ++i) {
+        PMP_REQUIRE(keys[i] && offsets[i] >= 0 && offsets[i] < total, "bad offset for parameter %d", i);
+        ts->off[keys[i]] = (size_t)offsets[i];
+    }
+    for (auto& kv : m->hw) {
+        auto it = ts->off.find(kv.first);
+        PMP_REQUIRE(it != ts->off.end(), "parameter '%s' has no offset", kv.first.c_str());
+        PMP_REQUIRE(it->second + kv.second.v.size() <= ts->n, "parameter '%s' exceeds the flat arena", kv.first.c_str());
+    }
+    return build_repack_map(m, ts);
+}
+
+int pmp_train_sync_weights(pmp_model* m, int rebuild_tables, void* stream) {
+    PMP_REQUIRE(m && m->finalized && m->train, "pmp_train_bind has not been called");
+    DeviceGuard guard(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = launch_repack(m->train->P, m->train->map_dev, m->arena, m->arena_n, st))) return rc;
+    if (m->arena16)
+        for (const auto& r : m->plane_recs)
+            if ((rc = launch_planes(m->arena + r.src, r.K, r.C, r.N, m->arena16 + r.hi, m->arena16 + r.lo, st))) return rc;
+    if (rebuild_tables && (rc = build_time_tables(m, st))) return rc;
+    return 0;
+}
+
+int pmp_train_loss_grad(pmp_model* m, const pmp_train_args* a, void* stream) {
+    PMP_REQUIRE(m && m->finalized && m->train, "pmp_train_bind has not been called");
+    PMP_REQUIRE(a && a->x_noisy_dev && a->t_dev && a->walls_dev && a->noise_dev && a->keep_dev && a->loss_weights_dev && a->loss_dev,
+                "bad argument");
+    PMP_REQUIRE(a->B >= 1 && a->H % 4 == 0 && a->H >= 32 && a->H <= 128, "batch %d / horizon %d unsupported", a->B, a->H);
+    PMP_REQUIRE(a->wall_len > 0 && a->wall_len % m->arch.vit_token_dim == 0 && a->wall_len / m->arch.vit_token_dim < 16,
+                "wall vector length %d does not fit the wall encoder", a->wall_len);
+    DeviceGuard guard(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    TrainIO io{a->x_noisy_dev, a->t_dev, a->walls_dev, a->wall_len, a->noise_dev, a->keep_dev, a->loss_weights_dev, a->loss_dev,
+               a->eps_dev};
+    Ctx dry;
+    dry.m = m; dry.st = st; dry.dry = true; dry.R = a->B; dry.H = a->H; dry.n_cond = a->B; dry.t = nullptr; dry.embRow = nullptr;
+    int rc = run_train(dry, m->train, io);
+    if (rc) return rc;
+    if ((rc = grow(&m->ws, &m->ws_n, dry.used + 64, st, &m->gen))) return rc;
+    Ctx c;
+    c.m = m; c.st = st; c.dry = false; c.R = a->B; c.H = a->H; c.n_cond = a->B; c.t = a->t_dev; c.embRow = nullptr;
+    m->dbg.clear();
+    return run_train(c, m->train, io);
+}
+
+int pmp_q_sample(const float* x0_dev, float* noise_dev, const int64_t* t_dev, const float* sqrt_acp_dev, const float* sqrt_1m_acp_dev,
+                 int B, int H, int D, int zero_cond_noise, float* x_noisy_dev, void* stream) {
+    PMP_REQUIRE(x0_dev && noise_dev && t_dev && sqrt_acp_dev && sqrt_1m_acp_dev && x_noisy_dev && B >= 1 && H >= 2 && D >= 1, "bad argument");
+    return launch_qsample(x0_dev, noise_dev, t_dev, sqrt_acp_dev, sqrt_1m_acp_dev, B, H, D, zero_cond_noise, x_noisy_dev,
+                          (cudaStream_t)stream);
+}
+
+int pmp_adam_ema_step(float* p_dev, const float* g_dev, float* m_dev, float* v_dev, float* ema_dev, int64_t n, float lr, float beta1,
+                      float beta2, float eps, int step, float grad_scale, int ema_mode, float ema_beta, void* stream) {
+    PMP_REQUIRE(p_dev && g_dev && m_dev && v_dev && n >= 0 && step >= 1, "bad argument");
+    PMP_REQUIRE(ema_mode == 0 || ema_dev, "ema buffer required");
+    return launch_adam_ema(p_dev, g_dev, m_dev, v_dev, ema_dev, (size_t)n, lr, beta1, beta2, eps, step, grad_scale, ema_mode, ema_beta,
+                           (cudaStream_t)stream);
 }
 
 int pmp_step(int kind, const float* x, const float* const* ec, const float* const* eu, const float* w, int K,

@@ -7,8 +7,8 @@ sampling loops run on the GPU through libpmp_b200.so:
     per-step coefficients are tabulated on the host with the reference's own float32 ops);
   * p_sample / ddim_p_sample / pred_x_tm1_luo / pred_x_tm1_ddim -> the fused pmp_step kernel;
   * pred_unet / p_mean_variance -> TemporalUnet_WCond.forward (pmp_unet_eps).
-Training (`loss`, `p_losses`) needs a double backward through the U-Net and is outside the
-built hot path.
+  * loss / p_losses -> pmp_train_loss_grad (pmp_b200/train.py): the energy loss and its parameter gradients
+    from a hand-written second-order pass (no torch autograd through the network).
 """
 import numpy as np
 import torch
@@ -297,12 +297,65 @@ class GaussianDiffusionPB(nn.Module):
             x = apply_conditioning(x, cond, 0)
         return x[0] if input2d else x
 
-    # ------------------------------------------------------------------ training (not built)
-    def p_losses(self, *args, **kwargs):
-        raise NotImplementedError('training (double backward through the U-Net) is outside the B200 hot path')
+    # ------------------------------------------------------------------ training
+    def train_engine(self):
+        """the pmp_b200.train.TrainEngine of this model: its parameters become views into one flat arena and the
+        loss / gradient kernels are bound to it (built on first use, on the device the model is on)"""
+        te = getattr(self, '_train_engine', None)
+        if te is None:
+            from pmp_b200 import train as ptrain
+            te = ptrain.TrainEngine(self.model, self.betas.device, self.n_timesteps)
+            object.__setattr__(self, '_train_engine', te)
+        return te
 
-    def loss(self, *args, **kwargs):
-        raise NotImplementedError('training (double backward through the U-Net) is outside the B200 hot path')
+    def p_losses(self, x_start, cond, t, walls_loc, return_x_recon=False):
+        """diffusion_pb.py:480-516.  The random draws keep the reference's order: noise here, then the concept-dropout
+        mask the reference's U-Net draws inside its forward (temporal_cond.py:266-270).  The returned loss is attached to
+        the parameters through an autograd node whose backward hands out the gradient the kernels have already
+        computed, so `loss.backward()` / torch optimizers work as with the reference."""
+        assert self.training and self.energy_mode and self.train_apply_condition and not return_x_recon
+        from pmp_b200 import train as ptrain
+        noise = torch.randn_like(x_start)
+        x_noisy = ptrain.q_sample(x_start.float(), noise, t, self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod)
+        x_noisy = apply_conditioning(x_noisy, cond, 0)
+        if self.set_cond_noise_to_0:
+            for k in cond.keys():
+                noise[:, k, self.action_dim:] = 0.0
+        keep = np.random.rand(x_start.shape[0]) >= self.model.concept_drop_prob
+        te = self.train_engine()
+        te.dirty = True            # a torch optimizer may have stepped since the last call
+        half = _EnergyLoss.apply(te, x_noisy, t, walls_loc, noise, torch.as_tensor(keep, dtype=torch.float32),
+                                 self.loss_fn.weights, *list(self.model.parameters()))
+        loss = 2.0 * half          # the weighted MSE `loss_fn` returns; `loss()` halves it again
+        return loss, {'a0_loss': loss.detach()}
+
+    def loss(self, x, cond, wall_locations, maze_idx=None):
+        """diffusion_pb.py:518-545"""
+        batch_size = len(x)
+        if self.is_dyn_env:
+            wall_locations = torch.flatten(wall_locations, start_dim=1, end_dim=2)
+        else:
+            wall_locations = wall_locations[:, 0, :]
+        t = torch.randint(0, self.n_timesteps, (batch_size,), device=x.device).long()
+        diffuse_loss, info = self.p_losses(x[:, :, self.action_dim:], cond, t, wall_locations)
+        loss = (1 / 2) * diffuse_loss
+        info['diffuse_loss'] = diffuse_loss.detach()
+        return loss, info
+
+
+class _EnergyLoss(torch.autograd.Function):
+    """value: 0.5 * mean(w * (dE/dx - noise)^2) from pmp_train_loss_grad, which also leaves d value / d parameters in the
+    engine's flat gradient arena; backward scales views of that arena"""
+
+    @staticmethod
+    def forward(ctx, te, x_noisy, t, walls, noise, keep, weights, *params):
+        loss = te.loss_grad(x_noisy, t, walls, noise, keep, weights)
+        ctx.te = te
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, go):
+        return (None,) * 7 + tuple(go * g for g in ctx.te.flat.views(ctx.te.G))
 
 
 from .._overlay import reference_fallback as _reference_fallback  # noqa: E402

@@ -162,8 +162,9 @@ class TemporalUnet_WCond(nn.Module):
         force_dropout+half_fd: the second half of the batch is the unconditional CFG half
         (temporal_cond.py:272-279)."""
         if self.training or use_dropout:
-            raise NotImplementedError('the training path (concept dropout + double backward) is not part of the '
-                                      'B200 hot path; call .eval() and pass use_dropout=False')
+            raise NotImplementedError('in training mode the model is driven through GaussianDiffusionPB.loss '
+                                      '(pmp_b200.train: loss and parameter gradients in one pass); '
+                                      'for eps = dE/dx call .eval() and pass use_dropout=False')
         R = x.shape[0]
         if force_dropout:
             if half_fd:

@@ -67,6 +67,14 @@ _PROTOS = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pmp_pick_first_valid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+    "pmp_train_bind": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.c_void_p, C.c_void_p,
+                                 C.c_int64]),
+    "pmp_train_sync_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "pmp_train_loss_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pmp_q_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_void_p, C.c_void_p]),
+    "pmp_adam_ema_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
+                                    C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p]),
     "pmp_launch_count": (C.c_uint64, []),
     "pmp_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "pmp_profile_enable": (C.c_int, [C.c_int]),

@@ -13,10 +13,18 @@ python bench.py --workload eval200 --steps 20 --warmup 5 > $out/${tag}_eval200.j
 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1500 -c 800 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline > $out/${tag}_ncu_launches.log 2>&1
 # full capture: one whole eps evaluation (60 conv launches, every shape class) at the bench's chunk size
-ncu --set full --import-source on --clock-control none -k regex:conv_tc_kernel --launch-skip 120 --launch-count 60 \
-    -f -o $out/${tag}_conv python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline > $out/${tag}_ncu_conv.log 2>&1
+# (the report of 60 launches is ~200 MB: it is exported to csv on the box and removed; gpurun brings back <= 64 MiB)
+ncu --set full --clock-control none -k regex:conv_tc_kernel --launch-skip 120 --launch-count 60 \
+    -f -o /tmp/${tag}_conv python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline > $out/${tag}_ncu_conv.log 2>&1
+ncu -i /tmp/${tag}_conv.ncu-rep --page raw --csv > $out/${tag}_conv_raw.csv 2>> $out/${tag}_ncu_conv.log
+# source-level capture of two launches: the 64-channel forward kernel and the dominant 512-channel kernel
+ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k regex:'conv_tc_kernel<64, 8, 0, 1, 1, 2, 1|conv_tc_kernel<256, 64, 0, 2, 1, 2' \
+    --launch-skip 40 --launch-count 2 -f -o $out/${tag}_conv_src python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline --batch 2000 \
+    > $out/${tag}_ncu_conv_src.log 2>&1
 # full capture of the HBM-bound kernels of the path (sampler update, swept check, Kuka sphere check)
 python tests/gpu_profile_aux.py > $out/${tag}_aux_plain.log 2>&1 && \
 ncu --set full --import-source on --clock-control none -k regex:'step_kernel|swept|kuka_kernel' --launch-skip 0 --launch-count 12 \
-    -f -o $out/${tag}_aux python tests/gpu_profile_aux.py > $out/${tag}_ncu_aux.log 2>&1
+    -f -o /tmp/${tag}_aux python tests/gpu_profile_aux.py > $out/${tag}_ncu_aux.log 2>&1
+ncu -i /tmp/${tag}_aux.ncu-rep --page raw --csv > $out/${tag}_aux_raw.csv 2>> $out/${tag}_ncu_aux.log
+du -sh $out
 ls -la $out/${tag}_*
