@@ -188,6 +188,113 @@ def run_eval200(args, dev, world, rank):
             "gpu_launches": res["graph"]["launches"] * args.steps}))
 
 
+TRAIN_FLOP_PER_SAMPLE = {"dualkuka_train": 6 * 1.1893e9, "maze2d_train": 6 * 0.3850e9}   # 6 conv-type passes (see run_train)
+
+
+def run_train(args, dev, world, rank):
+    """BASELINE configs[4], second half: DDP training-step throughput (Dual Kuka 14-DoF, H=56, batch 256 per GPU).  One
+    step = loss + every parameter gradient of one batch (forward, backward-data, tangent forward, reverse pass: four
+    conv-type passes plus two weight-gradient GEMM passes = 6 x the forward conv FLOPs), NCCL all-reduce of the flat
+    gradient arena (N > 1), fused Adam + EMA, weight re-layout.  value: samples/s with the batch resident in HBM;
+    e2e: through TrainerPBDiff.train_step with the batch in pinned host memory."""
+    import torch
+    import torch.distributed as dist
+    import pmp_b200
+    from pmp_b200 import shard
+    from pmp_b200 import workloads as synth
+    from diffuser.models import TemporalUnet_WCond, GaussianDiffusionPB
+    from diffuser.utils.training_pbdiff import TrainerPBDiff
+    fam = "dualkuka" if args.workload == "dualkuka_train" else "m2d"
+    a = synth.arch(fam)
+    H, D = (56 if fam == "dualkuka" else 48), a["obs_dim"]
+    B = args.train_batch
+    model = TemporalUnet_WCond(**a["unet"])
+    model.load_state_dict(synth.synth_state_dict(model.state_dict(), 1))
+    dkw = dict(a["diffusion"]); dkw["horizon"] = H
+    diffusion = GaussianDiffusionPB(model, **dkw).to(dev).train()
+    tr = TrainerPBDiff(diffusion, None, train_lr=2e-5, gradient_accumulate_every=1, save_freq=0, log_freq=0,
+                       results_folder="/tmp/pmp_bench_train")
+    if args.gemm_path != 3:
+        tr.te.engine.set_gemm_path(args.gemm_path)
+    pr = synth.make_problems(fam, B, 3000 + rank)
+    lo, hi = pr["lo"], pr["hi"]
+    s_ = torch.tensor(synth.normalize(pr["start"], lo, hi))[:, None, :]
+    g_ = torch.tensor(synth.normalize(pr["goal"], lo, hi))[:, None, :]
+    al = torch.linspace(0, 1, H)[None, :, None]
+    gen = torch.Generator().manual_seed(17 + rank)
+    x_h = (s_ * (1 - al) + g_ * al + 0.05 * torch.randn(B, H, D, generator=gen)).clamp(-1, 1).contiguous().pin_memory()
+    walls_h = torch.tensor(pr["walls"])[:, None, :].contiguous().pin_memory()
+    cond_h = {0: x_h[:, 0].clone().pin_memory(), H - 1: x_h[:, -1].clone().pin_memory()}
+    x_d, walls_d = x_h.to(dev), walls_h.to(dev)
+    cond_d = {k: v.to(dev) for k, v in cond_h.items()}
+    n_par = tr.te.flat.total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        tr.train_step([(x_d, cond_d, walls_d)])
+    barrier()
+    n0 = pmp_b200.launch_count()
+    with ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) as clk:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            loss = tr.train_step([(x_d, cond_d, walls_d)])
+        e1.record()
+        barrier()
+    ms = shard.max_over_ranks(e0.elapsed_time(e1), dev)
+    launches = pmp_b200.launch_count() - n0
+    # phases of one step, CUDA events on the launching stream (rank 0's view)
+    ph = {}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record(); l_ = tr.micro_batch((x_d, cond_d, walls_d), True); ev[1].record()
+    tr.reducer.run(); ev[2].record()
+    tr.opt.update(grad_scale=1.0 / world); tr.te.sync_weights(); ev[3].record()
+    torch.cuda.synchronize()
+    ph = {"loss_grad_ms": ev[0].elapsed_time(ev[1]), "allreduce_ms": ev[1].elapsed_time(ev[2]),
+          "adam_ema_relayout_ms": ev[2].elapsed_time(ev[3])}
+    tr.step += 1
+    # end to end: host batch -> device inside the step
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        loss = tr.train_step([(x_h, cond_h, walls_h)])
+        lv = float(loss)                  # device -> host read of the step's loss
+    barrier()
+    e2e_s = shard.max_over_ranks(time.perf_counter() - t0, dev)
+    if rank == 0:
+        pk = peaks()
+        fl = TRAIN_FLOP_PER_SAMPLE[args.workload] * (H / (56.0 if fam == "dualkuka" else 48.0))
+        sps = world * B * args.steps / (ms / 1e3)
+        ach = B * fl / (ph["loss_grad_ms"] * 1e-3) / 1e12
+        print(json.dumps({
+            "metric": "training samples/sec (energy loss double backward + Adam + EMA, DDP)", "value": sps, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (fp32-accumulate) convolutions, fp32 weight gradients", "data": "synthetic",
+            "config": {"workload": "%s: %s U-Net (%d parameters), H=%d, batch %d per GPU, one optimizer step per batch" % (
+                args.workload, fam, n_par, H, B), "steps_per_s": args.steps / (ms / 1e3), "phases": ph,
+                "allreduce": "NCCL all-reduce (sum) of the flat fp32 gradient arena (%.1f MB) in %d buckets on a side stream" % (
+                    n_par * 4 / 1e6, len(tr.reducer.bounds)) if world > 1 else "none (1 GPU)",
+                "gemm_path": args.gemm_path, "final_loss": lv, "l2": "activations of a 256-sample batch exceed the 126 MB L2"},
+            "clocks": clk.summary(),
+            "e2e": {"value": world * B * args.steps / e2e_s, "unit": "samples/s",
+                    "h2d_bytes_per_step": (x_h.numel() + walls_h.numel() + sum(v.numel() for v in cond_h.values())) * 4,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
+                         "traffic": None, "kernel": "whole loss+gradient pass (conv_tc_kernel x4 passes + wgrad_kernel x2 passes)",
+                         "note": "algorithmic FLOPs = 6 x forward conv FLOPs per sample; the weight-gradient GEMMs run on the "
+                                 "CUDA cores in fp32 (wgrad_kernel), the other four passes on tcgen05 (BF16x3)"},
+            "cpu_baseline": None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,8 +310,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch problems per GPU; strong: --batch problems in total, sharded over the GPUs (BASELINE configs[3])")
+    ap.add_argument("--train-batch", type=int, default=256, help="samples per GPU per training step (*_train workloads)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of every step from the host (A/B of the CUDA graph replay)")
-    ap.add_argument("--workload", default="maze2d", choices=["maze2d", "kuka", "dualkuka", "comp2", "comp3", "eval200"],
+    ap.add_argument("--workload", default="maze2d", choices=["maze2d", "kuka", "dualkuka", "comp2", "comp3", "eval200", "dualkuka_train", "maze2d_train"],
                     help="maze2d = BASELINE configs[1] (the bench line); kuka / dualkuka = configs[3] / [4] sampling with "
                          "sphere-model collision scoring, extra measurements under the same harness")
     args = ap.parse_args()
@@ -238,6 +346,8 @@ def main():
     # half Concave (7 concave obstacles = 21 boxes, hExt 0.25), one model per family, collision-check success scoring
     if args.workload == "eval200":
         return run_eval200(args, dev, world, rank)
+    if args.workload.endswith("_train"):
+        return run_train(args, dev, world, rank)
     if args.no_graph:
         pmp_b200.set_option("cuda_graph", 0)
     B_total = args.batch if args.scaling == "strong" else world * args.batch
@@ -443,12 +553,15 @@ def main():
     tot_conv_ms = sum(r[0] for r in prof)
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     is_tc = prof[1][0] > prof[0][0]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1e_traffic.json")
-    if is_tc and os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")   # from the committed ncu --set full capture
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if is_tc and args.workload == "maze2d" and args.batch == 10000 and os.path.exists(tpath):
+        # DRAM bytes per launch of the dominant kernel class from the committed ncu --set full capture of THIS command
+        # (same 10,000-row pass); not measured by this run -- a bench under ncu is not a bench
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r2_traffic.json (%s): %s" % (tj.get("kernel"), tj.get("source"))
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-            "frac": achieved / pk["tf_sust"], "traffic": traffic,
+            "frac": achieved / pk["tf_sust"], "traffic": traffic, "traffic_source": traffic_src,
             "kernel": "conv_tc_kernel (tcgen05 BF16x3 implicit GEMM)" if is_tc else "conv_simt_kernel (fp32 CUDA-core implicit GEMM)",
             "note": ("achieved = algorithmic conv FLOPs (2*M*N*K) / summed kernel time; the BF16x3 error-compensated "
                      "scheme issues 3 tensor passes per product, so issued tensor TFLOP/s = 3 x achieved (cap 0.333)")

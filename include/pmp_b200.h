@@ -185,6 +185,14 @@ typedef struct {
 } pmp_train_args;
 /* grads arena += d loss / d parameters (zero it first, like optimizer.zero_grad()); no host synchronisation */
 int pmp_train_loss_grad(pmp_model *m, const pmp_train_args *a, void *stream);
+/* gradient buckets for an all-reduce that overlaps the reverse pass (DDP): bucket k covers arena elements
+ * [lower_bounds[k], lower_bounds[k-1]) (lower_bounds descending, bucket 0 ends at the arena's end).  When the arena is
+ * laid out in forward module order (embeddings / wall encoder, down path, middle, up path, final conv) the reverse pass
+ * finishes it from the end towards the start, and pmp_train_loss_grad records an event per bucket as soon as every gradient
+ * at or above its lower bound is final (otherwise all events fire at the end).  pmp_train_wait_bucket makes `stream`
+ * (the communication stream) wait for bucket k of the most recent pmp_train_loss_grad. */
+int pmp_train_set_buckets(pmp_model *m, int n, const int64_t *lower_bounds);
+int pmp_train_wait_bucket(pmp_model *m, int k, void *stream);
 /* q_sample + apply_conditioning (+ set_loss_noise) (:468-487, helpers.py:168-178): x_noisy = sqrt_acp[t] x0 +
  * sqrt_1m_acp[t] noise with rows 0 and H-1 copied from x0 (zero_cond_noise: their noise target zeroed in place) */
 int pmp_q_sample(const float *x0_dev, float *noise_dev, const int64_t *t_dev, const float *sqrt_acp_dev,

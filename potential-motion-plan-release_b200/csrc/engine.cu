@@ -1288,6 +1288,7 @@ void pmp_model_destroy(pmp_model* m) {
         if (b) cudaFree(b);
     if (m->t_iota) cudaFree(m->t_iota);
     if (m->train) {
+        for (cudaEvent_t e : m->train->bucket_ev) cudaEventDestroy(e);
         if (m->train->map_dev) cudaFree(m->train->map_dev);
         delete m->train;
     }
@@ -1416,6 +1417,31 @@ int pmp_train_loss_grad(pmp_model* m, const pmp_train_args* a, void* stream) {
     c.m = m; c.st = st; c.dry = false; c.R = a->B; c.H = a->H; c.n_cond = a->B; c.t = a->t_dev; c.embRow = nullptr;
     m->dbg.clear();
     return run_train(c, m->train, io);
+}
+
+int pmp_train_set_buckets(pmp_model* m, int n, const int64_t* lower_bounds) {
+    PMP_REQUIRE(m && m->train, "pmp_train_bind has not been called");
+    PMP_REQUIRE(n >= 0 && (n == 0 || lower_bounds), "bad argument");
+    DeviceGuard guard(m->device);
+    TrainState* ts = m->train;
+    for (cudaEvent_t e : ts->bucket_ev) cudaEventDestroy(e);
+    ts->bucket_ev.clear();
+    ts->bucket_lo.clear();
+    for (int i = 0; i < n; ++i) {
+        PMP_REQUIRE(lower_bounds[i] >= 0 && (i == 0 || lower_bounds[i] < lower_bounds[i - 1]), "bucket bounds must descend");
+        cudaEvent_t e;
+        PMP_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ts->bucket_ev.push_back(e);
+        ts->bucket_lo.push_back((size_t)lower_bounds[i]);
+    }
+    return 0;
+}
+
+int pmp_train_wait_bucket(pmp_model* m, int k, void* stream) {
+    PMP_REQUIRE(m && m->train && k >= 0 && k < (int)m->train->bucket_ev.size(), "no such gradient bucket");
+    DeviceGuard guard(m->device);
+    PMP_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, m->train->bucket_ev[k], 0));
+    return 0;
 }
 
 int pmp_q_sample(const float* x0_dev, float* noise_dev, const int64_t* t_dev, const float* sqrt_acp_dev, const float* sqrt_1m_acp_dev,

@@ -75,7 +75,7 @@ class TrainerPBDiff(object):
             for k in cond.keys():
                 noise[:, k, m.action_dim:] = 0.0
         keep = torch.as_tensor(np.random.rand(B) >= m.model.concept_drop_prob, dtype=torch.float32)
-        return self.te.loss_grad(x_noisy, t, walls, noise, keep, m.loss_fn.weights, zero=first)
+        return self.te.loss_grad(x_noisy, t, walls, noise, keep, m.loss_fn.weights, zero=first, check_t=False)   # t drawn in range above
 
     def train_step(self, batches):
         """one optimizer step over `gradient_accumulate_every` micro-batches (training_pbdiff.py:121-143)"""

@@ -73,7 +73,7 @@ class TrainEngine:
         _check(lib().pmp_train_sync_weights(self.engine.h, 1 if rebuild_tables else 0, _stream(self.device)))
         self.dirty = False
 
-    def loss_grad(self, x_noisy, t, walls, noise, keep, loss_weights, want_eps=False, zero=True):
+    def loss_grad(self, x_noisy, t, walls, noise, keep, loss_weights, want_eps=False, zero=True, check_t=True):
         """loss [1] (device) of the micro-batch; its gradient is written (zero=True) or added to the flat arena `G`"""
         dev = self.device
         if self.dirty:
@@ -81,7 +81,7 @@ class TrainEngine:
         x_noisy = _f32(x_noisy, dev)
         B, H, D = x_noisy.shape
         t = t.detach().to(dev, torch.int64).contiguous()
-        if t.numel() and (int(t.min()) < 0 or int(t.max()) >= self.engine.arch.n_timesteps):
+        if check_t and t.numel() and (int(t.min()) < 0 or int(t.max()) >= self.engine.arch.n_timesteps):   # one host read
             raise PmpError("timestep out of range for n_timesteps=%d" % self.engine.arch.n_timesteps)
         walls = _f32(walls, dev)
         noise = _f32(noise, dev)

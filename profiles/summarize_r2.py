@@ -12,6 +12,8 @@ import sys
 
 import summarize
 
+import os
+HERE = os.path.dirname(os.path.abspath(__file__))
 d, tag = sys.argv[1], sys.argv[2]
 ROWS = 10000      # rows per launch in the bench (5,000 plans x CFG pair per family)
 
@@ -53,7 +55,7 @@ def algo_bytes(s):
 
 
 h, u, data = load("%s/%s_conv_raw.csv" % (d, tag))
-out = open("profiles/%s_conv_kernels.txt" % tag, "w")
+out = open("%s/%s_conv_kernels.txt" % (HERE, tag), "w")
 out.write("# ncu --set full --clock-control none, 60 consecutive conv_tc_kernel launches = ONE eps evaluation (U-Net forward +\n"
           "# analytic backward) of the bench step (`python bench.py`: 10,000 rows per launch, Maze2D Static2 model), launch order.\n"
           "# algo_MB: BF16 hi+lo planes of the inputs and of the result, fp32 yhat saved / re-read, identity planes (see\n"
@@ -102,11 +104,11 @@ json.dump({
                     "duration_us": [p["us"] for p in c64]},
     "whole_evaluation": {"dram_bytes": sum(a[2] for a in agg.values()), "algorithmic_bytes": sum(a[3] for a in agg.values()),
                          "time_us": tot},
-}, open("profiles/%s_traffic.json" % tag, "w"), indent=1)
+}, open("%s/%s_traffic.json" % (HERE, tag), "w"), indent=1)
 
 # HBM-bound kernels of the path
 h, u, data = load("%s/%s_aux_raw.csv" % (d, tag))
-with open("profiles/%s_aux_kernels.txt" % tag, "w") as f:
+with open("%s/%s_aux_kernels.txt" % (HERE, tag), "w") as f:
     f.write("# ncu --set full --clock-control none of tests/gpu_profile_aux.py: fused sampler update (400,000 plans), Maze2D swept\n"
             "# check (1,000,000 trajectories, 10 candidates per environment), Kuka sphere-link check (200,000 trajectories)\n")
     names = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -124,4 +126,4 @@ with open("profiles/%s_aux_kernels.txt" % tag, "w") as f:
         by = val(h, u, r, "dram__bytes_read.sum") + val(h, u, r, "dram__bytes_write.sum")
         f.write("    %-72s %.1f GB/s\n\n" % ("achieved DRAM bandwidth (bytes / duration)", by / (t * 1e-6) / 1e9))
 
-summarize.launches("%s/%s_launches.csv" % (d, tag), "profiles/%s_launches.txt" % tag)
+summarize.launches("%s/%s_launches.csv" % (d, tag), "%s/%s_launches.txt" % (HERE, tag))
