@@ -234,6 +234,19 @@ def run_train(args, dev, world, rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    ddp_check = None
+    if world > 1:
+        # the overlapped bucket all-reduce (events recorded inside the reverse pass) against a reduction issued after the whole
+        # pass, on the same micro-batch and draws: identical sums, and identical parameters on every rank after the steps
+        from pmp_b200 import train as ptrain
+        import numpy as np
+        torch.manual_seed(5 + rank); np.random.seed(5 + rank)
+        tr.micro_batch((x_d, cond_d, walls_d), True); tr.reducer.run(); torch.cuda.synchronize()
+        g_over = tr.te.G.clone()
+        torch.manual_seed(5 + rank); np.random.seed(5 + rank)
+        tr.micro_batch((x_d, cond_d, walls_d), True)
+        ptrain.GradAllReduce(tr.te.G, bucket_mb=1 << 20).run(); torch.cuda.synchronize()
+        ddp_check = {"overlap_vs_serial_rel_diff": float((g_over - tr.te.G).norm() / tr.te.G.norm())}
     for i in range(max(args.warmup, 3)):
         tr.train_step([(x_d, cond_d, walls_d)])
     barrier()
@@ -266,6 +279,11 @@ def run_train(args, dev, world, rank):
         lv = float(loss)                  # device -> host read of the step's loss
     barrier()
     e2e_s = shard.max_over_ranks(time.perf_counter() - t0, dev)
+    if world > 1:
+        cs = tr.te.flat.P.double().sum()
+        hi_, lo_ = cs.clone(), cs.clone()
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX); dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        ddp_check["parameters_identical_on_all_ranks"] = bool(hi_.item() == lo_.item())
     if rank == 0:
         pk = peaks()
         fl = TRAIN_FLOP_PER_SAMPLE[args.workload] * (H / (56.0 if fam == "dualkuka" else 48.0))
@@ -280,7 +298,7 @@ def run_train(args, dev, world, rank):
                 args.workload, fam, n_par, H, B), "steps_per_s": args.steps / (ms / 1e3), "phases": ph,
                 "allreduce": "NCCL all-reduce (sum) of the flat fp32 gradient arena (%.1f MB) in %d buckets on a side stream" % (
                     n_par * 4 / 1e6, len(tr.reducer.bounds)) if world > 1 else "none (1 GPU)",
-                "gemm_path": args.gemm_path, "final_loss": lv, "l2": "activations of a 256-sample batch exceed the 126 MB L2"},
+                "gemm_path": args.gemm_path, "final_loss": lv, "ddp_check": ddp_check, "l2": "activations of a 256-sample batch exceed the 126 MB L2"},
             "clocks": clk.summary(),
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": "samples/s",
                     "h2d_bytes_per_step": (x_h.numel() + walls_h.numel() + sum(v.numel() for v in cond_h.values())) * 4,

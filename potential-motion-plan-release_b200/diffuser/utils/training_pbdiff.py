@@ -51,7 +51,7 @@ class TrainerPBDiff(object):
         self.te = self.model.train_engine()
         self.opt = ptrain.FlatAdamEMA(self.te, lr=train_lr, ema_decay=ema_decay, step_start_ema=step_start_ema,
                                       update_ema_every=update_ema_every)
-        self.reducer = ptrain.GradAllReduce(self.te, bucket_mb=trainer_dict.get('bucket_mb', 32))
+        self.reducer = ptrain.GradAllReduce(self.te.G, bucket_mb=trainer_dict.get('bucket_mb', 32), engine=self.te.engine)
         self.step = 0
 
     # ------------------------------------------------------------------------------------------------------------

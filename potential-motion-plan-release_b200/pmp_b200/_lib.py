@@ -71,6 +71,8 @@ _PROTOS = {
                                  C.c_int64]),
     "pmp_train_sync_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "pmp_train_loss_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pmp_train_set_buckets": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
+    "pmp_train_wait_bucket": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "pmp_q_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_void_p, C.c_void_p]),
     "pmp_adam_ema_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,

@@ -5,7 +5,7 @@ Replaces `GaussianDiffusionPB.loss` + `loss.backward()` + `Adam.step` + `EMA.upd
 the energy loss 0.5*mean(w*(dE/dx - noise)^2) and its gradient with respect to every parameter are computed by
 hand-written kernels (pmp_train_loss_grad: forward, backward-data, tangent forward, reverse pass over the pair), the
 optimizer and the EMA copy by one fused kernel over flat arenas, and -- with more than one GPU -- the gradient arena is
-all-reduced over NCCL in buckets that overlap the reverse pass.  PyTorch supplies device memory, streams and
+all-reduced over NCCL in buckets that overlap the reverse pass (GradAllReduce).  PyTorch supplies device memory, streams and
 torch.distributed; no torch autograd, cuDNN or cuBLAS call is on this path."""
 import ctypes as C
 
@@ -29,7 +29,7 @@ class FlatParams:
     def __init__(self, module, device):
         self.names, self.offsets, self.shapes = [], [], []
         off = 0
-        params = list(module.named_parameters())
+        params = sorted(module.named_parameters(), key=lambda kp: self._rank(kp[0]))     # stable
         for k, p in params:
             self.names.append(k)
             self.offsets.append(off)
@@ -41,6 +41,15 @@ class FlatParams:
             v = self.P[o:o + p.numel()].view(p.shape)
             v.copy_(p.data)
             p.data = v
+
+    @staticmethod
+    def _rank(name):
+        """forward module order of the U-Net (embeddings / wall encoder, down path, middle, up path, final conv): the reverse
+        pass then finishes the gradient arena from its end towards its start (bucketed all-reduce, GradAllReduce)"""
+        for i, pfx in enumerate(("downs.", "mid_block1.", "mid_block2.", "ups.", "final_conv.")):
+            if name.startswith(pfx):
+                return i + 1
+        return 0
 
     def views(self, flat):
         return [flat[o:o + int(np.prod(s))].view(s) for o, s in zip(self.offsets, self.shapes)]
@@ -159,28 +168,40 @@ class FlatAdamEMA:
 
 
 class GradAllReduce:
-    """bucketed NCCL all-reduce (sum) of the flat gradient arena on a side stream, enqueued behind the reverse pass
-    (stream-ordered: the host does not wait); the optimizer kernel is ordered behind the last bucket."""
+    """bucketed all-reduce (sum) of a flat gradient arena.  On the GPU (NCCL) the buckets are reduced on a side stream from
+    the END of the arena towards its start, bucket k as soon as the reverse pass has finished every gradient at or above
+    its lower bound (pmp_train_set_buckets / pmp_train_wait_bucket: one CUDA event per bucket, recorded inside
+    pmp_train_loss_grad), so the reduction of the up path / middle / down path overlaps the rest of the reverse pass; the
+    optimizer kernel is ordered behind the last bucket.  On CPU tensors (gloo, tests) the buckets are reduced in place."""
 
-    def __init__(self, te, bucket_mb=32, group=None):
+    def __init__(self, flat_grad, bucket_mb=32, group=None, engine=None):
         import torch.distributed as dist
-        self.dist, self.te, self.group = dist, te, group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        n = te.G.numel()
-        per = max(1, int(bucket_mb * (1 << 20) // 4))
-        self.bounds = [(max(0, e - per), e) for e in range(n, 0, -per)]
-        self.stream = torch.cuda.Stream(device=te.device) if self.world > 1 else None
+        self.dist, self.G, self.group, self.engine = dist, flat_grad, group, engine
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        n = flat_grad.numel()
+        per = max(4, int(bucket_mb * (1 << 20) // 4) // 4 * 4)
+        self.bounds = [(max(0, e - per), e) for e in range(n, 0, -per)]      # back to front
+        self.stream = None
+        if self.world > 1 and flat_grad.is_cuda:
+            self.stream = torch.cuda.Stream(device=flat_grad.device)
+            if engine is not None:
+                lo = (C.c_int64 * len(self.bounds))(*[b[0] for b in self.bounds])
+                _check(lib().pmp_train_set_buckets(engine.h, len(self.bounds), lo))
 
     def run(self):
-        """call after loss_grad has been enqueued; returns when the reduction is ENQUEUED (stream-ordered)"""
+        """call right after loss_grad has been enqueued; returns when the reduction is ENQUEUED (stream-ordered)"""
         if self.world == 1:
             return
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.te.device))
-        self.stream.wait_event(ev)
-        with torch.cuda.stream(self.stream):
+        if self.stream is None:                       # CPU tensors (gloo)
             for lo, hi in self.bounds:
-                self.dist.all_reduce(self.te.G[lo:hi], op=self.dist.ReduceOp.SUM, group=self.group)
-        done = torch.cuda.Event()
-        done.record(self.stream)
-        torch.cuda.current_stream(self.te.device).wait_event(done)
+                self.dist.all_reduce(self.G[lo:hi], op=self.dist.ReduceOp.SUM, group=self.group)
+            return
+        cur = torch.cuda.current_stream(self.G.device)
+        if self.engine is None:
+            self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            for k, (lo, hi) in enumerate(self.bounds):
+                if self.engine is not None:
+                    _check(lib().pmp_train_wait_bucket(self.engine.h, k, C.c_void_p(self.stream.cuda_stream)))
+                self.dist.all_reduce(self.G[lo:hi], op=self.dist.ReduceOp.SUM, group=self.group)
+        cur.wait_stream(self.stream)

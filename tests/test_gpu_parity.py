@@ -711,6 +711,43 @@ def test_plan_entry_points():
     assert keys <= set(res) and res["num_samples"] == 4
 
 
+def test_plan_rm2d_from_a_reference_written_logdir(tmp_path):
+    """scripts/plan_rm2d.py --logdir: model_config.pkl / diffusion_config.pkl written by the REFERENCE's own Config class
+    (tests/golden/logdir_m2d, gen_golden.py:gen_logdir) + state_<epoch>.pt = {'step','model','ema'} in the reference
+    trainer's format (training_pbdiff.py:177-191).  The highest epoch's EMA weights must be the ones that plan:
+    same statistics as a model built directly with those weights, different from the other checkpoint's."""
+    import importlib.util
+    import os
+    import shutil
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in ("model_config.pkl", "diffusion_config.pkl"):
+        shutil.copy(os.path.join(root, "tests", "golden", "logdir_m2d", f), tmp_path / f)
+    d_model, d_ema, d_old = dropin("m2d", 1), dropin("m2d", 2), dropin("m2d", 3)
+    cpu = lambda sd: {k: v.detach().cpu() for k, v in sd.items()}
+    torch.save({"step": 9, "model": cpu(d_model.state_dict()), "ema": cpu(d_ema.state_dict())}, tmp_path / "state_10.pt")
+    torch.save({"step": 1, "model": cpu(d_old.state_dict()), "ema": cpu(d_old.state_dict())}, tmp_path / "state_2.pt")
+    spec = importlib.util.spec_from_file_location("plan_rm2d_b200", os.path.join(root, "potential-motion-plan-release_b200", "scripts", "plan_rm2d.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert os.path.basename(mod.latest_checkpoint(str(tmp_path))) == "state_10.pt"
+    a, loaded = mod.load_diffusion("m2d", str(tmp_path), DEV)
+    assert type(loaded).__module__ == "diffuser.models.diffusion_pb" and type(loaded.model).__module__ == "diffuser.models.temporal_cond"
+    for (k, v), (k2, v2) in zip(loaded.state_dict().items(), d_ema.state_dict().items()):
+        assert k == k2 and torch.equal(v.cpu(), v2.cpu()), k
+    argv = ["--plan_n_maze", "2", "--n_prob_env", "3", "--samples_perprob", "4"]
+    torch.manual_seed(123)
+    res = mod.main(argv + ["--logdir", str(tmp_path)])
+    assert res["num_samples"] == 6 and res["avg_num_colck"] > 0
+    # the same plan through the public classes with the EMA weights directly
+    pr_x = torch.randn(3, 48, 2, device=DEV)
+    t = torch.full((3,), 40, device=DEV, dtype=torch.long)
+    walls = torch.tensor(synth.make_problems("m2d", 3, 9)["walls"], device=DEV)
+    e1 = loaded.model(pr_x, None, t, walls, use_dropout=False, force_dropout=False)
+    e2 = d_ema.model(pr_x, None, t, walls, use_dropout=False, force_dropout=False)
+    e3 = d_model.model(pr_x, None, t, walls, use_dropout=False, force_dropout=False)
+    assert torch.equal(e1, e2) and not torch.equal(e1, e3)
+
+
 def test_ddim_replan_matches_reference_golden():
     """GaussianDiffusionPB.ddim_replan (partial re-noise + the last dn_steps DDIM steps, diffusion_pb.py:311-346) on a
     batch of four against the reference's outputs for the same trajectories and q_sample noise
