@@ -315,6 +315,7 @@ class GaussianDiffusionPB(nn.Module):
         computed, so `loss.backward()` / torch optimizers work as with the reference."""
         assert self.training and self.energy_mode and self.train_apply_condition and not return_x_recon
         from pmp_b200 import train as ptrain
+        te = self.train_engine()   # first: a model that is not on a B200 fails here (PmpError), before anything is drawn
         noise = torch.randn_like(x_start)
         x_noisy = ptrain.q_sample(x_start.float(), noise, t, self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod)
         x_noisy = apply_conditioning(x_noisy, cond, 0)
@@ -322,7 +323,6 @@ class GaussianDiffusionPB(nn.Module):
             for k in cond.keys():
                 noise[:, k, self.action_dim:] = 0.0
         keep = np.random.rand(x_start.shape[0]) >= self.model.concept_drop_prob
-        te = self.train_engine()
         te.dirty = True            # a torch optimizer may have stepped since the last call
         half = _EnergyLoss.apply(te, x_noisy, t, walls_loc, noise, torch.as_tensor(keep, dtype=torch.float32),
                                  self.loss_fn.weights, *list(self.model.parameters()))

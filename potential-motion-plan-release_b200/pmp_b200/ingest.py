@@ -12,8 +12,8 @@ and, for the concave mazes, the obstacle layouts saved by the environment genera
   rand_rec2dgrp/<env_list_name>_43[_eval].pkl   {'centers_43' [n_env,nw,2], 'mode_list' [n_env,nw] in 1..4}
                                                                                   (rand_rec_group_43.py:154-188)
 from which the evaluation scripts build the (cx, cy, mode) model input (preprocessing.py:220-234).
-`load_problems` returns that dict from an HDF5 file (needs h5py, which this image does not ship: the call then
-fails loudly) or from an `.npz` archive with the same keys (what `save_problems_npz` writes; '/' in key names is
+`load_problems` returns that dict from an HDF5 file (through h5py when it is installed, else through the built-in
+minimal reader pmp_b200/h5min.py, which covers the layouts h5py's defaults write) or from an `.npz` archive with the same keys (what `save_problems_npz` writes; '/' in key names is
 kept).  `problem_arrays` slices it into the arrays `diffuser.guides.plan_env_b200.plan_envs` takes.
 """
 import io
@@ -42,9 +42,11 @@ def load_problems(path):
     if ext in (".hdf5", ".h5"):
         try:
             import h5py
-        except ImportError as e:
-            raise ImportError("reading %s needs h5py (not installed here); convert the file once with "
-                              "pmp_b200.ingest.save_problems_npz on a machine that has it" % path) from e
+        except ImportError:
+            # no h5py in this image: the built-in reader covers what h5py's defaults write (pmp_b200/h5min.py) and
+            # raises H5FormatError for anything outside that subset
+            from . import h5min
+            return h5min.read_flat(path)
         out = {}
         with h5py.File(path, "r") as f:
             _walk_h5(f, "", out)

@@ -97,8 +97,12 @@ def test_dropin_diffusion_buffers_and_coefs():
         t2 = d.ddim_set_timesteps(n)
         assert np.array_equal(t2, sampler_ref.ddim_timesteps(n, 100))
         assert np.array_equal(d.step_coefs_ddim(t2, eta, n), ddim_coefs(tb, t2, n, 100, eta))
-    with pytest.raises(NotImplementedError):
-        d.loss(None, None, None)
+    # the training step is CUDA only: on a CPU model `loss` fails loudly instead of falling back to torch autograd
+    import pmp_b200
+    d.train()
+    x = torch.zeros(2, 48, 2)
+    with pytest.raises(pmp_b200.PmpError):
+        d.loss(x, {0: x[:, 0], 47: x[:, -1]}, torch.zeros(2, 1, 12))
 
 
 def test_config_pickle_roundtrip():
@@ -173,11 +177,38 @@ def test_problem_file_ingest_npz_roundtrip(tmp_path):
     assert w4.shape == (1, 2, 6) and np.allclose(c4[0], cen[0, 0])
     with pytest.raises(ValueError):
         ingest.problem_arrays(got, [0], prob_permaze=99, wall_dim=2)
-    try:
-        import h5py  # noqa: F401
-    except ImportError:
-        with pytest.raises(ImportError):
-            ingest.load_problems(str(tmp_path / "x-problems.hdf5"))
+    with pytest.raises((OSError, ValueError)):
+        ingest.load_problems(str(tmp_path / "x-problems.hdf5"))       # missing file: an error, never an empty dict
+
+
+def test_hdf5_problem_file_is_read_like_its_npz_twin(tmp_path):
+    """tests/golden/m2d_synth-problems.hdf5 (HDF5 in the layout h5py's defaults write: superblock 0, old-style nested
+    groups, gzip-chunked / contiguous / compact datasets; make_h5_fixture.py) through ingest.load_problems -- h5py when
+    installed, else the built-in reader pmp_b200/h5min.py -- gives the arrays of its .npz twin, bit for bit, and the
+    planner arrays cut from both are identical.  Unsupported / damaged files fail loudly."""
+    from pmp_b200 import ingest, h5min
+    gdir = os.path.join(ROOT, "tests", "golden")
+    h5 = ingest.load_problems(os.path.join(gdir, "m2d_synth-problems.hdf5"))
+    nz = ingest.load_problems(os.path.join(gdir, "m2d_synth-problems.npz"))
+    assert set(nz) <= set(h5) and {"maze_idx", "infos/is_sol_kp"} <= set(h5)
+    for k in nz:
+        assert h5[k].dtype == nz[k].dtype and np.array_equal(h5[k], nz[k]), k
+    assert h5["maze_idx"].dtype == np.int64 and np.array_equal(h5["maze_idx"][:, 0], np.arange(h5["problems"].shape[0]))
+    a = ingest.problem_arrays(h5, np.arange(4), 7, 2)
+    b = ingest.problem_arrays(nz, np.arange(4), 7, 2)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # the reader itself (also when h5py is present)
+    flat = h5min.read_flat(os.path.join(gdir, "m2d_synth-problems.hdf5"))
+    assert all(np.array_equal(flat[k], nz[k]) for k in nz)
+    raw = bytearray(open(os.path.join(gdir, "m2d_synth-problems.hdf5"), "rb").read())
+    bad = tmp_path / "bad.hdf5"
+    bad.write_bytes(b"not an hdf5 file" + bytes(raw[16:]))
+    with pytest.raises(h5min.H5FormatError):
+        h5min.read_flat(str(bad))
+    raw[8] = 3                                   # superblock version 3 (libver='latest'): outside the built subset
+    bad.write_bytes(bytes(raw))
+    with pytest.raises(h5min.H5FormatError):
+        h5min.read_flat(str(bad))
 
 
 def test_concave_layout_ingest_matches_reference_fixture(tmp_path):

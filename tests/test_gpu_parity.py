@@ -347,6 +347,12 @@ def test_plan_rm2d_from_problem_file():
     assert r.returncode == 0, r.stderr[-2000:]
     res = _json.loads(r.stdout.strip().splitlines()[-1])
     assert res["num_samples"] == 120 and 0.0 <= res["traj_srate"] <= 1.0 and res["total_num_colck"] > 0
+    # the same problems from the HDF5 file (the reference's own format, kuka_plan_utils.py:13-33): identical statistics
+    r2 = subprocess.run([sys.executable, script, "--family", "m2d", "--plan_n_maze", "6", "--n_prob_env", "20",
+                         "--problems", prob[:-4] + ".hdf5"], capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    res2 = _json.loads(r2.stdout.strip().splitlines()[-1])
+    assert res2["num_samples"] == 120 and res2["total_num_colck"] > 0
 
 
 def test_plan_rm2d_concave_problem_file(tmp_path):
