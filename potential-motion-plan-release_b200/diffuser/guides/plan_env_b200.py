@@ -17,6 +17,15 @@ import pmp_b200
 from .kuka_colchk import KukaCollisionChecker, arm_bases, TABLE_Z
 
 
+def collision_model_tag(robot):
+    """Kuka / Dual-Kuka validity comes from the analytic sphere-link model, not from the reference's pybullet mesh contact
+    query (declared deviation): result dicts say so, so that their `traj_srate` etc. are not read as
+    reference-parity numbers"""
+    if robot == 'maze2d':
+        return 'maze2d boxes, exact reference arithmetic'
+    return 'sphere-link approximation of the arm (NOT pybullet mesh contacts; success rates are sphere-model rates)'
+
+
 def compute_avg_result(ncol, norepl_suc, num_colck, n_env, n_prob, batch_runtime, repl_suc=None):
     """global statistics of a planning run, with the reference's keys and its arithmetic in its order: per
     environment the rates of check_collision (kuka_plan_utils.py:136-146: traj_srate = no_collision_rate =
@@ -134,6 +143,7 @@ def plan_envs(policy, starts, goals, walls, env_boxes, hext, horizon, samples_pe
         ncol = pmp_b200.colchk_kuka(paths, env_p, env_boxes, hext, n_arms, arm_bases(n_arms), chk.sph, TABLE_Z)['ncol']
     res = compute_avg_result(ncol.cpu().numpy(), suc.cpu().numpy(), total.cpu().numpy(), n_env, n_prob, batch_runtime,
                              repl_suc=repl_suc)
+    res['collision_model'] = collision_model_tag(robot)
     return res, paths.cpu().numpy()
 
 
@@ -217,4 +227,5 @@ def plan_envs_multi_horizon(policy, starts, goals, walls, env_boxes, hext, horiz
         ncol[sel] = nc.cpu().numpy()
     res = compute_avg_result(ncol, suc.cpu().numpy(), total.cpu().numpy(), n_env, n_prob, batch_runtime, repl_suc=repl_suc)
     res['horizon_hist'] = [int((hs == i).sum()) for i in range(len(horizons))]
+    res['collision_model'] = collision_model_tag(robot)
     return res, paths
