@@ -263,6 +263,11 @@ int pmp_profile_read(int n_classes, double *ms, double *flops, int64_t *launches
  * out8 = {mma_wait_tma, mma_wait_acc, mma_total, epi_wait_acc, epi_busy, tma_wait_stage, tiles, 0};
  * returns 1 when the timers are disabled */
 int pmp_debug_counters(double *out8, int reset);
+/* test hook: weight gradient of a stride-1 conv, dW[co][ci][k] += sum_{r,h} o[r,h,co] i[r,h+k-KS/2,ci] (two terms when o2 != NULL),
+ * on the fp32 CUDA-core kernel (use_tc 0) or the tcgen05 kernel (use_tc 1; scratch of pmp_debug_wgrad_scratch_floats floats) */
+int pmp_debug_wgrad(const float *o1, const float *i1, const float *o2, const float *i2, int H, int Co, int Ci, int KS, int R,
+                    float *dw_dev, float *scratch_dev, int use_tc, int flags, void *stream);
+size_t pmp_debug_wgrad_scratch_floats(int R, int H, int Co, int Ci, int KS);
 /* debug: copy an internal activation of the last pmp_unet_eps call (first row chunk) to the
  * host; name e.g. "yhat:downs.0.0.blocks.0." ; returns element count or <0 */
 int64_t pmp_debug_fetch(pmp_model *m, const char *name, float *host_out, int64_t capacity);

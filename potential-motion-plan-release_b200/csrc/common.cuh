@@ -228,12 +228,20 @@ int launch_gn_tangent(const float* yd, int ldyd, const float* yhat, const float*
                       int R, int Hl, int C, cudaStream_t st);
 int launch_gn_adjoint(const float* zbar, int ldzb, const float* gz, int ldgz, const float* yhat, const float* yhd, const float* rstd,
                       const float* s, const float* gamma, const float* beta, float* ybar, __nv_bfloat16* yh, __nv_bfloat16* yl,
-                      float* dgamma, float* dbeta, int R, int Hl, int C, cudaStream_t st);
+                      float* dgamma, float* dbeta, float* dbias, int R, int Hl, int C, cudaStream_t st);
 // dW[co][ci][k] += sum_{r,ho} O1[r,ho,co] I1[r,ho*stride+k-pad,ci] (+ the same with O2, I2 when O2 != null)
 int launch_wgrad(const float* O1, int ldo1, const float* I1, int ldi1, const float* O2, int ldo2, const float* I2, int ldi2,
                  int Ho, int Co, int Hi, int Ci, int stride, int pad, int KS, int R, float* dW, cudaStream_t st);
+// the same on the tcgen05 tensor cores (wgrad_tc.cu; stride-1 convs with 64-multiple channel counts): BF16x3, K-major
+// transposed planes in `scratch` (wgrad_tc_scratch_floats floats, 16-byte aligned)
+bool wgrad_tc_eligible(int H, int Co, int Ci, int stride, int KS);
+size_t wgrad_tc_scratch_floats(int R, int H, int Co, int Ci, int KS);
+int launch_wgrad_tc(const float* O1, int ldo1, const float* I1, int ldi1, const float* O2, int ldo2, const float* I2, int ldi2,
+                    int H, int Co, int Ci, int KS, int R, float* dW, float* scratch, cudaStream_t st, int dbg = 0);
 int launch_colsum(const float* X, int ld, int rows, int C, float* out, cudaStream_t st);
 int launch_hsum(const float* X, int ld, int R, int Hl, int C, float* out, int ldo, cudaStream_t st);
+int launch_lin_fwd(const float* in, int ldin, int nin, const float* W, int ldw, const float* bias, float* out, int ldo, int nout,
+                   int rows, int accumulate, cudaStream_t st);
 int launch_lin_dgrad(const float* dout, int lddo, int nout, const float* W, int ldw, float* din, int lddi, int nin, int rows,
                      int accumulate, cudaStream_t st);
 int launch_lin_wgrad(const float* dout, int lddo, int nout, const float* in, int ldin, int nin, int rows, float* dW, int lddw,

@@ -1444,6 +1444,17 @@ int pmp_train_wait_bucket(pmp_model* m, int k, void* stream) {
     return 0;
 }
 
+int pmp_debug_wgrad(const float* o1, const float* i1, const float* o2, const float* i2, int H, int Co, int Ci, int KS, int R,
+                    float* dw_dev, float* scratch_dev, int use_tc, int flags, void* stream) {
+    PMP_REQUIRE(o1 && i1 && dw_dev, "bad argument");
+    if (use_tc) {
+        PMP_REQUIRE(scratch_dev, "scratch required");
+        return launch_wgrad_tc(o1, Co, i1, Ci, o2, Co, i2, Ci, H, Co, Ci, KS, R, dw_dev, scratch_dev, (cudaStream_t)stream, flags);
+    }
+    return launch_wgrad(o1, Co, i1, Ci, o2, Co, i2, Ci, H, Co, H, Ci, 1, KS / 2, KS, R, dw_dev, (cudaStream_t)stream);
+}
+size_t pmp_debug_wgrad_scratch_floats(int R, int H, int Co, int Ci, int KS) { return wgrad_tc_scratch_floats(R, H, Co, Ci, KS); }
+
 int pmp_q_sample(const float* x0_dev, float* noise_dev, const int64_t* t_dev, const float* sqrt_acp_dev, const float* sqrt_1m_acp_dev,
                  int B, int H, int D, int zero_cond_noise, float* x_noisy_dev, void* stream) {
     PMP_REQUIRE(x0_dev && noise_dev && t_dev && sqrt_acp_dev && sqrt_1m_acp_dev && x_noisy_dev && B >= 1 && H >= 2 && D >= 1, "bad argument");

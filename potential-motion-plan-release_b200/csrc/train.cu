@@ -100,12 +100,12 @@ __global__ void __launch_bounds__(128) gn_adjoint_kernel(const float* __restrict
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          float* __restrict__ ybar, __nv_bfloat16* __restrict__ yh_,
                                                          __nv_bfloat16* __restrict__ yl_, float* __restrict__ dgamma,
-                                                         float* __restrict__ dbeta, int Hl, int C) {
+                                                         float* __restrict__ dbeta, float* __restrict__ dbias, int Hl, int C) {
     __shared__ float red[20];
-    __shared__ float chg[128], chb[128];
+    __shared__ float chg[128], chb[128], chy[128];
     const int r = blockIdx.x >> 3, g = blockIdx.x & 7, GS = C >> 3, n = Hl * GS;
     const size_t row0 = (size_t)r * Hl;
-    if (threadIdx.x < GS) { chg[threadIdx.x] = 0.f; chb[threadIdx.x] = 0.f; }
+    if (threadIdx.x < GS) { chg[threadIdx.x] = 0.f; chb[threadIdx.x] = 0.f; chy[threadIdx.x] = 0.f; }
     __syncthreads();
     float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     for (int e = threadIdx.x; e < n; e += 128) {
@@ -138,11 +138,13 @@ __global__ void __launch_bounds__(128) gn_adjoint_kernel(const float* __restrict
         const float v = rs * (Q - mQ - yh * mQy) - rs * ss * gy - rs * (yd * m2 + yh * mqd);
         ybar[i] = v;
         if (yh_) split_bf16(v, yh_[i], yl_[i]);
+        if (dbias) atomicAdd(&chy[e - h * GS], v);
     }
     __syncthreads();
     if (threadIdx.x < GS) {
         atomicAdd(dgamma + g * GS + threadIdx.x, chg[threadIdx.x]);
         atomicAdd(dbeta + g * GS + threadIdx.x, chb[threadIdx.x]);
+        if (dbias) atomicAdd(dbias + g * GS + threadIdx.x, chy[threadIdx.x]);     // conv bias gradient = column sums of ybar
     }
 }
 
@@ -251,33 +253,58 @@ __global__ void hsum_kernel(const float* __restrict__ X, int ld, int Hl, int C, 
 
 // ---------------------------------------------------------------------------------------------------------------
 // small dense layers (rows = samples or wall tokens; a few hundred to a few thousand)
-// din[r][i] (+)= sum_o dout[r][o] W[o][i]
-__global__ void lin_dgrad_kernel(const float* __restrict__ dout, int lddo, int nout, const float* __restrict__ W, int ldw,
-                                 float* __restrict__ din, int lddi, int nin, int rows, int accumulate) {
-    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= (size_t)rows * nin) return;
-    const int j = (int)(i % nin);
-    const size_t r = i / nin;
-    float s = 0.f;
-    for (int o = 0; o < nout; ++o) s = fmaf(dout[r * lddo + o], __ldg(W + (size_t)o * ldw + j), s);
-    float* d = din + r * lddi + j;
-    *d = accumulate ? *d + s : s;
-}
-// dW[o][i] += sum_r dout[r][o] in[r][i] ;  db[o] += sum_r dout[r][o]    (rows split over blockIdx.y)
-__global__ void lin_wgrad_kernel(const float* __restrict__ dout, int lddo, int nout, const float* __restrict__ in, int ldin, int nin,
-                                 int rows, float* __restrict__ dW, int lddw, float* __restrict__ db, int rows_per_block) {
-    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= (size_t)nout * nin) return;
-    const int j = (int)(i % nin), o = (int)(i / nin);
-    const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-    float s = 0.f, sb = 0.f;
-    for (int r = r0; r < r1; ++r) {
-        const float d = dout[(size_t)r * lddo + o];
-        s = fmaf(d, in[(size_t)r * ldin + j], s);
-        sb += d;
+// C[m][n] (=|+=) sum_k A(m,k) B(k,n) with arbitrary element strides: the dense layers' backward passes
+//   input gradient   din[r][i]  = sum_o dout[r][o] W[o][i]        (A = dout, B = W)
+//   weight gradient  dW[o][i]  += sum_r dout[r][o] in[r][i]       (A = dout^T, B = in)
+// These products are small (a few hundred rows); what matters is filling the GPU: 32 x 32 tiles, 16-deep K slices, 2 x 2
+// register tiles, K split over blockIdx.z (atomic accumulation) until a few hundred blocks exist.
+__global__ void __launch_bounds__(256) small_gemm_kernel(const float* __restrict__ A, long sam, long sak, const float* __restrict__ B,
+                                                         long sbk, long sbn, float* __restrict__ Cm, int ldc, int M, int N, int K,
+                                                         int k_per_split, int mode /*0 store, 1 add, 2 atomic add*/,
+                                                         float* __restrict__ colsumA /*[M] += sum_k A(m,k), or null*/,
+                                                         const float* __restrict__ biasN /*[N] added once, or null*/) {
+    __shared__ float As[16][32 + 1];
+    __shared__ float Bs[16][32 + 1];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
+    float acc[2][2] = {};
+    float rs[2] = {0.f, 0.f};
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
+        __syncthreads();
+        for (int i = tid; i < 32 * 16; i += 256) {
+            // the faster-varying smem index follows the operand's unit-stride direction
+            int mm, kk;
+            if (sam == 1) { mm = i & 31; kk = i >> 5; } else { kk = i & 15; mm = i >> 4; }
+            As[kk][mm] = (m0 + mm < M && k0 + kk < kend) ? A[(long)(m0 + mm) * sam + (long)(k0 + kk) * sak] : 0.f;
+            int nn, kb;
+            if (sbn == 1) { nn = i & 31; kb = i >> 5; } else { kb = i & 15; nn = i >> 4; }
+            Bs[kb][nn] = (n0 + nn < N && k0 + kb < kend) ? B[(long)(k0 + kb) * sbk + (long)(n0 + nn) * sbn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float a0 = As[kk][ty * 2], a1 = As[kk][ty * 2 + 1], b0 = Bs[kk][tx * 2], b1 = Bs[kk][tx * 2 + 1];
+            rs[0] += a0; rs[1] += a1;
+            acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+            acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+        }
     }
-    atomicAdd(dW + (size_t)o * lddw + j, s);
-    if (db && j == 0) atomicAdd(db + o, sb);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + ty * 2 + i;
+        if (m >= M) continue;
+        if (colsumA && blockIdx.y == 0 && tx == 0) atomicAdd(colsumA + m, rs[i]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int n = n0 + tx * 2 + j;
+            if (n >= N) continue;
+            float* o = Cm + (size_t)m * ldc + n;
+            const float v = acc[i][j] + ((biasN && blockIdx.z == 0) ? biasN[n] : 0.f);
+            if (mode == 2) atomicAdd(o, v);
+            else *o = mode ? *o + v : v;
+        }
+    }
 }
 
 __device__ __forceinline__ float small_act(float x, int kind) {
@@ -561,9 +588,10 @@ int launch_gn_tangent(const float* yd, int ldyd, const float* yhat, const float*
 }
 int launch_gn_adjoint(const float* zbar, int ldzb, const float* gz, int ldgz, const float* yhat, const float* yhd, const float* rstd,
                       const float* s, const float* gamma, const float* beta, float* ybar, __nv_bfloat16* yh, __nv_bfloat16* yl,
-                      float* dgamma, float* dbeta, int R, int Hl, int C, cudaStream_t st) {
+                      float* dgamma, float* dbeta, float* dbias, int R, int Hl, int C, cudaStream_t st) {
     PMP_REQUIRE(C % 8 == 0 && C / 8 <= 128, "GroupNorm(8) adjoint: C = %d unsupported", C);
-    gn_adjoint_kernel<<<R * 8, 128, 0, st>>>(zbar, ldzb, gz, ldgz, yhat, yhd, rstd, s, gamma, beta, ybar, yh, yl, dgamma, dbeta, Hl, C);
+    gn_adjoint_kernel<<<R * 8, 128, 0, st>>>(zbar, ldzb, gz, ldgz, yhat, yhd, rstd, s, gamma, beta, ybar, yh, yl, dgamma, dbeta, dbias,
+                                             Hl, C);
     PMP_LAUNCH_OK();
     return 0;
 }
@@ -604,8 +632,8 @@ int launch_wgrad(const float* O1, int ldo1, const float* I1, int ldi1, const flo
 
 int launch_colsum(const float* X, int ld, int rows, int C, float* out, cudaStream_t st) {
     if (rows == 0 || C == 0) return 0;
-    int nb = (rows + 511) / 512;
-    if (nb > 64) nb = 64;
+    int nb = (rows + 63) / 64;
+    if (nb > 256) nb = 256;
     const int rpb = (rows + nb - 1) / nb;
     dim3 grid((C + 63) / 64, (rows + rpb - 1) / rpb);
     colsum_kernel<<<grid, 256, 0, st>>>(X, ld, rows, C, out, rpb);
@@ -619,22 +647,54 @@ int launch_hsum(const float* X, int ld, int R, int Hl, int C, float* out, int ld
     PMP_LAUNCH_OK();
     return 0;
 }
+// K slices per block such that (tiles x splits) fills the GPU; returns the number of splits
+static int small_gemm_splits(int M, int N, int K, int* kps) {
+    const int tiles = ((M + 31) / 32) * ((N + 31) / 32);
+    int nsplit = (2 * 148 + tiles - 1) / tiles;
+    const int maxs = (K + 31) / 32;                 // at least two 16-deep slices per block
+    if (nsplit > maxs) nsplit = maxs;
+    if (nsplit < 1) nsplit = 1;
+    *kps = ((K + nsplit - 1) / nsplit + 15) / 16 * 16;
+    return (K + *kps - 1) / *kps;
+}
 int launch_lin_dgrad(const float* dout, int lddo, int nout, const float* W, int ldw, float* din, int lddi, int nin, int rows,
                      int accumulate, cudaStream_t st) {
-    const size_t n = (size_t)rows * nin;
-    if (!n) return 0;
-    lin_dgrad_kernel<<<nblk(n), 256, 0, st>>>(dout, lddo, nout, W, ldw, din, lddi, nin, rows, accumulate);
+    if (!rows || !nin) return 0;
+    int kps;
+    const int ns = small_gemm_splits(rows, nin, nout, &kps);
+    int mode = accumulate ? 1 : 0;
+    if (ns > 1) {
+        if (!accumulate) PMP_CUDA_OK(cudaMemset2DAsync(din, (size_t)lddi * 4, 0, (size_t)nin * 4, rows, st));
+        mode = 2;
+    }
+    dim3 grid((rows + 31) / 32, (nin + 31) / 32, ns);
+    small_gemm_kernel<<<grid, 256, 0, st>>>(dout, lddo, 1, W, ldw, 1, din, lddi, rows, nin, nout, kps, mode, nullptr, nullptr);
+    PMP_LAUNCH_OK();
+    return 0;
+}
+// out[r][c] (=|+=) bias[c] + sum_j in[r][j] W[c][j]
+int launch_lin_fwd(const float* in, int ldin, int nin, const float* W, int ldw, const float* bias, float* out, int ldo, int nout,
+                   int rows, int accumulate, cudaStream_t st) {
+    if (!rows || !nout) return 0;
+    int kps;
+    const int ns = small_gemm_splits(rows, nout, nin, &kps);
+    int mode = accumulate ? 1 : 0;
+    if (ns > 1) {
+        if (!accumulate) PMP_CUDA_OK(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)nout * 4, rows, st));
+        mode = 2;
+    }
+    dim3 grid((rows + 31) / 32, (nout + 31) / 32, ns);
+    small_gemm_kernel<<<grid, 256, 0, st>>>(in, ldin, 1, W, 1, ldw, out, ldo, rows, nout, nin, kps, mode, nullptr, bias);
     PMP_LAUNCH_OK();
     return 0;
 }
 int launch_lin_wgrad(const float* dout, int lddo, int nout, const float* in, int ldin, int nin, int rows, float* dW, int lddw,
                      float* db, cudaStream_t st) {
-    const size_t n = (size_t)nout * nin;
-    if (!n || !rows) return 0;
-    int nb = (rows + 127) / 128;
-    const int rpb = (rows + nb - 1) / nb;
-    dim3 grid(nblk(n), (rows + rpb - 1) / rpb);
-    lin_wgrad_kernel<<<grid, 256, 0, st>>>(dout, lddo, nout, in, ldin, nin, rows, dW, lddw, db, rpb);
+    if (!nout || !nin || !rows) return 0;
+    int kps;
+    const int ns = small_gemm_splits(nout, nin, rows, &kps);
+    dim3 grid((nout + 31) / 32, (nin + 31) / 32, ns);
+    small_gemm_kernel<<<grid, 256, 0, st>>>(dout, 1, lddo, in, ldin, 1, dW, lddw, nout, nin, rows, kps, 2, db, nullptr);
     PMP_LAUNCH_OK();
     return 0;
 }

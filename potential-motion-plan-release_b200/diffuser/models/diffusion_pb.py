@@ -324,8 +324,9 @@ class GaussianDiffusionPB(nn.Module):
                 noise[:, k, self.action_dim:] = 0.0
         keep = np.random.rand(x_start.shape[0]) >= self.model.concept_drop_prob
         te.dirty = True            # a torch optimizer may have stepped since the last call
+        named = dict(self.model.named_parameters())
         half = _EnergyLoss.apply(te, x_noisy, t, walls_loc, noise, torch.as_tensor(keep, dtype=torch.float32),
-                                 self.loss_fn.weights, *list(self.model.parameters()))
+                                 self.loss_fn.weights, *[named[k] for k in te.flat.names])     # the flat arena's order
         loss = 2.0 * half          # the weighted MSE `loss_fn` returns; `loss()` halves it again
         return loss, {'a0_loss': loss.detach()}
 

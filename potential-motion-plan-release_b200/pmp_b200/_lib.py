@@ -82,6 +82,9 @@ _PROTOS = {
     "pmp_profile_enable": (C.c_int, [C.c_int]),
     "pmp_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pmp_debug_counters": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
+    "pmp_debug_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "pmp_debug_wgrad_scratch_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "pmp_debug_fetch": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
 }
 
