@@ -33,26 +33,20 @@ struct Maze {
     float lox, loy, hix, hiy;
 };
 
-// next float32 above / below a finite one (what nextafterf returns, without its generic slow path)
-__device__ __forceinline__ float f32_up(float f) {
-    if (f == 0.f) return __int_as_float(1);
-    const int b = __float_as_int(f);
-    return __int_as_float(f > 0.f ? b + 1 : b - 1);
-}
-__device__ __forceinline__ float f32_down(float f) {
-    if (f == 0.f) return __int_as_float((int)0x80000001u);
-    const int b = __float_as_int(f);
-    return __int_as_float(f > 0.f ? b - 1 : b + 1);
-}
+// up(T) / down(T), branch free: round towards the side, then step one float32 further when the rounded value does not
+// lie strictly beyond T.  The step is the integer successor of the bit pattern (+-0 -> the smallest denormal of the right
+// sign; -inf steps up to -FLT_MAX, +inf down to FLT_MAX); +inf is never stepped up, -inf never down, NaN never compares.
 __device__ __forceinline__ float strictly_above(double t) {
-    float f = __double2float_ru(t);
-    if ((double)f <= t) f = isfinite(f) ? f32_up(f) : nextafterf(f, INFINITY);
-    return f;
+    const float f = __double2float_ru(t);
+    const int b = __float_as_int(f);
+    const int up = (b & 0x7fffffff) == 0 ? 1 : (b >= 0 ? b + 1 : b - 1);
+    return (((double)f <= t) && b != 0x7f800000) ? __int_as_float(up) : f;
 }
 __device__ __forceinline__ float strictly_below(double t) {
-    float f = __double2float_rd(t);
-    if ((double)f >= t) f = isfinite(f) ? f32_down(f) : nextafterf(f, -INFINITY);
-    return f;
+    const float f = __double2float_rd(t);
+    const int b = __float_as_int(f);
+    const int dn = (b & 0x7fffffff) == 0 ? (int)0x80000001u : (b >= 0 ? b - 1 : b + 1);
+    return (((double)f >= t) && b != (int)0xff800000u) ? __int_as_float(dn) : f;
 }
 
 __device__ __forceinline__ bool m2d_valid(const Maze& e, float x, float y) {
@@ -282,6 +276,128 @@ __global__ void __launch_bounds__(WARPS * 32) maze2d_swept16_kernel(
     }
 }
 
+// ------------------------------------------------------------------------------ swept check, one LANE per trajectory
+// The bandwidth-bound form (few walls, any horizon): a lane walks its own trajectory sequentially, exactly like the
+// reference's loop (no cross-lane prefix sums, ballots or duplicated per-lane bookkeeping: ~35 instructions per waypoint for
+// 32 trajectories at once), with the walls of its environment as float32 thresholds in registers.  The warp stages the 32
+// trajectories it owns through shared memory in chunks of 8 waypoints: global loads stay fully coalesced (every row of a
+// chunk is 64 contiguous bytes, one 16-byte load per lane and 8 rows), the next chunk is in flight while the current one is
+// walked, and the per-lane reads of the staged rows are bank-conflict free (row stride 9 float2).  A warp stops loading once
+// every lane has failed.  valid / n_checks are bit-identical to the sequential walk.
+template <int NWR>
+__device__ __forceinline__ int m2d_interior_reg(const float4 (&wl)[NWR], float lox, float loy, float hix, float hiy, float2 a,
+                                                float dx, float dy, float ss, double eps, int legacy_div) {
+    // returns (points counted << 1) | ok
+    const float d = __fsqrt_rn(ss);
+    int K;
+    if (legacy_div) K = (int)__ddiv_rn((double)d, eps);
+    else K = (int)__fdiv_rn(d, (float)eps);
+    int cnt = 0;
+    for (int k = 1; k < K; ++k) {
+        const float coef = (float)__ddiv_rn((double)k, (double)K);
+        const float px = __fadd_rn(a.x, __fmul_rn(coef, dx));
+        const float py = __fadd_rn(a.y, __fmul_rn(coef, dy));
+        if (!(px >= lox && py >= loy && px <= hix && py <= hiy)) return cnt << 1;      // outside the limits: not counted
+        cnt += 1;
+        bool c = false;
+#pragma unroll
+        for (int i = 0; i < NWR; ++i) c = c || (px >= wl[i].x && py >= wl[i].y && px <= wl[i].z && py <= wl[i].w);
+        if (c) return cnt << 1;
+    }
+    return (cnt << 1) | 1;
+}
+
+template <int NWR>
+__global__ void __launch_bounds__(WARPS * 32) maze2d_swept_lane_kernel(
+    const float* __restrict__ traj, const int32_t* __restrict__ env_id, int N, int H, const double* __restrict__ cen,
+    const double* __restrict__ hext, int nw, float lox, float loy, float hix, float hiy, double eps, float thr2,
+    double margin, int legacy_div, uint8_t* __restrict__ valid, int32_t* __restrict__ nchk) {
+    constexpr int CH = 8;
+    __shared__ float2 stage[WARPS][32][CH + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = lane & 3, rq = lane >> 2;
+    const int ngroups = (N + 31) >> 5, nchunks = (H + CH - 1) / CH;
+    for (int grp = blockIdx.x * WARPS + warp; grp < ngroups; grp += gridDim.x * WARPS) {
+        const int n = grp * 32 + lane;
+        const bool active = n < N;
+        // cooperative load of chunk c: lane (rq, q) fetches waypoints 2q, 2q+1 of rows rq, rq+8, rq+16, rq+24
+        float4 pre[4];
+        auto fetch = [&](int c) {
+            const int h0 = c * CH + 2 * q;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int nr = grp * 32 + rq + 8 * it;
+                pre[it] = (nr < N && h0 < H) ? __ldg(reinterpret_cast<const float4*>(traj + ((size_t)nr * H + h0) * 2))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        fetch(0);
+        // this lane's walls: identical double ops to the reference ((c-h)-m, (c+h)+m), then exact float32 thresholds
+        float4 wl[NWR];
+        const int env = active ? __ldg(env_id + n) : 0;
+#pragma unroll
+        for (int i = 0; i < NWR; ++i) {
+            if (active && i < nw) {
+                const double2 c = *reinterpret_cast<const double2*>(cen + ((size_t)env * nw + i) * 2);
+                const double2 h = *reinterpret_cast<const double2*>(hext + ((size_t)env * nw + i) * 2);
+                wl[i] = make_float4(strictly_above(__dsub_rn(__dsub_rn(c.x, h.x), margin)),
+                                    strictly_above(__dsub_rn(__dsub_rn(c.y, h.y), margin)),
+                                    strictly_below(__dadd_rn(__dadd_rn(c.x, h.x), margin)),
+                                    strictly_below(__dadd_rn(__dadd_rn(c.y, h.y), margin)));
+            } else {
+                wl[i] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);      // never inside
+            }
+        }
+        bool done = !active, ok = true;
+        int cnt = 0;
+        float2 pw = make_float2(0.f, 0.f);
+        bool pin = false, pcol = false;
+        for (int c = 0; c < nchunks; ++c) {
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                stage[warp][rq + 8 * it][2 * q] = make_float2(pre[it].x, pre[it].y);
+                stage[warp][rq + 8 * it][2 * q + 1] = make_float2(pre[it].z, pre[it].w);
+            }
+            __syncwarp();
+            if (c + 1 < nchunks) fetch(c + 1);
+            const int jn = min(CH, H - c * CH);
+#pragma unroll 2
+            for (int j = 0; j < jn; ++j) {
+                const float2 w = stage[warp][lane][j];
+                const bool in = w.x >= lox && w.y >= loy && w.x <= hix && w.y <= hiy;
+                bool col = false;
+#pragma unroll
+                for (int i = 0; i < NWR; ++i) col = col | ((w.x >= wl[i].x) & (w.y >= wl[i].y) & (w.x <= wl[i].z) & (w.y <= wl[i].w));
+                // _edge_fp of segment (h - 1, h), branch free: 0 checks when an endpoint is outside the limits, 1 when the first
+                // endpoint collides, 2 when the second does, 2 + interior points otherwise
+                const bool seg = (c + j > 0) & !done;
+                const bool e_in = pin & in;
+                const bool f2 = seg & e_in & pcol;
+                const bool two = seg & e_in & !pcol;                 // second endpoint tested: +2
+                const bool clear = two & !col;
+                cnt += (f2 ? 1 : 0) + (two ? 2 : 0);
+                const bool fail = seg & !clear;
+                ok = ok & !fail;
+                done = done | fail;
+                const float dx = __fsub_rn(w.x, pw.x), dy = __fsub_rn(w.y, pw.y);
+                const float ss = __fadd_rn(__fmul_rn(fabsf(dx), fabsf(dx)), __fmul_rn(fabsf(dy), fabsf(dy)));
+                if (clear && !(ss < thr2)) {      // K >= 2 possible: the reference's exact square root, division and points
+                    const int r = m2d_interior_reg<NWR>(wl, lox, loy, hix, hiy, pw, dx, dy, ss, eps, legacy_div);
+                    cnt += r >> 1;
+                    if (!(r & 1)) { ok = false; done = true; }
+                }
+                pw = w; pin = in; pcol = col;
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+        if (active) {
+            valid[n] = ok ? 1 : 0;
+            nchk[n] = cnt;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(WARPS * 32) maze2d_points_kernel(
     const float* __restrict__ traj, const int32_t* __restrict__ env_id, int N, int H, const double* __restrict__ cen,
     const double* __restrict__ hext, int nw, float lox, float loy, float hix, float hiy, double margin,
@@ -466,6 +582,31 @@ extern "C" int pmp_colchk_maze2d_swept(const float* traj, const int32_t* env_id,
     PMP_REQUIRE(H >= 2, "trajectory needs >= 2 waypoints");
     PMP_REQUIRE(eps > 0, "collision eps must be > 0");
     if (N == 0) return 0;
+    if (nw <= 6 && H % 2 == 0 && (reinterpret_cast<uintptr_t>(traj) & 15) == 0 && (reinterpret_cast<uintptr_t>(cen) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(hext) & 15) == 0) {
+        // few walls: one lane per trajectory, walls in registers, trajectories staged through shared memory
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            PMP_CUDA_OK(cudaGetDevice(&dev));
+            PMP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const int ngroups = (N + 31) / 32;
+        // one group of 32 trajectories per warp: early exits make the groups uneven, so the hardware block scheduler
+        // balances better than a grid-stride walk of few persistent blocks (measured)
+        const int blocks = (ngroups + WARPS - 1) / WARPS;
+        const double t = 1.8 * eps;
+        const float thr2 = (float)(t * t);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (nw <= 3)
+            maze2d_swept_lane_kernel<3><<<blocks, WARPS * 32, 0, st>>>(traj, env_id, N, H, cen, hext, nw, lox, loy, hix, hiy, eps, thr2,
+                                                                      margin, legacy_div, valid, nchk);
+        else
+            maze2d_swept_lane_kernel<6><<<blocks, WARPS * 32, 0, st>>>(traj, env_id, N, H, cen, hext, nw, lox, loy, hix, hiy, eps, thr2,
+                                                                      margin, legacy_div, valid, nchk);
+        PMP_LAUNCH_OK();
+        return 0;
+    }
     if (H <= 64) {
         // half a warp per trajectory, ceil(H / 16) waypoints per lane, persistent blocks
         static int sms = 0;

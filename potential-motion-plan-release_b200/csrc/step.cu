@@ -49,7 +49,10 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t draw, u
     const float u4 = ((float)(r.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
     // fast intrinsics (lg2/sin/cos.approx): the noise stream only has to be N(0,1)-distributed and reproducible,
     // it has no bit-level counterpart in the reference (torch.randn streams are injected instead when parity matters)
-    const float ra = __fsqrt_rn(-2.0f * __logf(u1)), rb = __fsqrt_rn(-2.0f * __logf(u3));
+    // -2 ln u = (-2 ln 2) lg2 u; lg2 / sqrt / sin / cos are single MUFU operations
+    float ra, rb;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(-1.3862943611198906f * __log2f(u1)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(-1.3862943611198906f * __log2f(u3)));
     float sa, ca, sb, cb;
     __sincosf(6.283185307179586f * (u2 - 0.5f), &sa, &ca);
     __sincosf(6.283185307179586f * (u4 - 0.5f), &sb, &cb);
@@ -100,26 +103,28 @@ __device__ __forceinline__ void step_inputs(const StepP& p, const DynStep& dyn, 
 
 // float4 variant (H*D and the global element offset are multiples of 4): 16-byte loads / stores, one Philox call
 // per thread.  HBM-bound: 4*(2 + 2K [+1 injected noise]) bytes per element.
+template <int KIND, bool K1>
 __global__ void __launch_bounds__(256) step_kernel4(const __grid_constant__ StepP p, const DynStep dyn,
                                                     const float* __restrict__ x,
                                                     const float* __restrict__ noise, uint64_t seed, uint64_t draw,
                                                     uint64_t elem0, const float* __restrict__ start,
                                                     const float* __restrict__ goal, float* __restrict__ xo,
                                                     float* __restrict__ trace, long trace_stride, int H, int D,
-                                                    size_t n4) {
+                                                    size_t n4, unsigned magic) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n4) return;
     float cf[8];
     step_inputs(p, dyn, cf, seed, draw, elem0);
     const size_t e = g * 4;
     const int HD = H * D;
-    // one 32-bit division per thread (the launcher guarantees n4 < 2^32); the conditioning rows are found by comparison
-    const unsigned b = (unsigned)g / (unsigned)(HD >> 2);
+    // plan index of this float4: a multiply-high by the launcher's reciprocal (exact for the whole launch, see launch_step),
+    // else one 32-bit division (the launcher guarantees n4 < 2^32); the conditioning rows are found by comparison
+    const unsigned b = magic ? __umulhi((unsigned)g, magic) : (unsigned)g / (unsigned)(HD >> 2);
     const int rem = (int)(((unsigned)g - b * (unsigned)(HD >> 2)) << 2);
     const float4 xv4 = __ldg(reinterpret_cast<const float4*>(x + e));
     const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
     float eps[4];
-    if (p.K == 1) {
+    if (K1) {
         const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.ec[0] + e)), u4 = __ldg(reinterpret_cast<const float4*>(p.eu[0] + e));
         const float c[4] = {c4.x, c4.y, c4.z, c4.w}, u[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
@@ -139,17 +144,20 @@ __global__ void __launch_bounds__(256) step_kernel4(const __grid_constant__ Step
 #pragma unroll
         for (int j = 0; j < 4; ++j) eps[j] = __fadd_rn(ub[j], s[j]);
     }
-    const bool need_noise = (p.kind == PMP_STEP_DDPM) || (cf[7] != 0.0f);
+    const bool need_noise = (KIND == PMP_STEP_DDPM) || (cf[7] != 0.0f);
     float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (need_noise) z4 = noise ? __ldg(reinterpret_cast<const float4*>(noise + e)) : philox_normal4(seed, draw, (elem0 + e) >> 2);
     const float z[4] = {z4.x, z4.y, z4.z, z4.w};
     float o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        o[j] = step_elem(cf, p.kind, xv[j], eps[j], z[j]);
-        const int r = rem + j;
-        if (start && r < D) o[j] = start[(size_t)b * D + r];                        // h == 0
-        if (goal && r >= HD - D) o[j] = goal[(size_t)b * D + (r - (HD - D))];       // h == H - 1
+    for (int j = 0; j < 4; ++j) o[j] = step_elem(cf, KIND, xv[j], eps[j], z[j]);
+    if (rem < D || rem + 4 > HD - D) {          // only the first / last float4s of a plan touch a conditioned waypoint
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = rem + j;
+            if (start && r < D) o[j] = start[(size_t)b * D + r];                        // h == 0
+            if (goal && r >= HD - D) o[j] = goal[(size_t)b * D + (r - (HD - D))];       // h == H - 1
+        }
     }
     const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
     *reinterpret_cast<float4*>(xo + e) = o4;
@@ -299,9 +307,17 @@ int launch_step(int kind, const float* x, const float* const* ec, const float* c
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     bool vec = ((H * D) % 4 == 0) && (n / 4 < 0xffffffffull) && (elem0 % 4 == 0) && al16(x) && al16(xo) && al16(noise) && al16(trace) && (trace_stride % 4 == 0);
     for (int k = 0; k < K; ++k) vec = vec && al16(ec[k]) && al16(eu[k]);
-    if (vec)
-        step_kernel4<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(p, dyn, x, noise, seed, draw, elem0, start, goal, xo, trace,
-                                                                     trace_stride, H, D, n / 4);
+    if (vec) {
+        // b = floor(g / q) as umulhi(g, ceil(2^32 / q)): exact while g * (magic * q - 2^32) < 2^32, i.e. for g < 2^32 / q
+        const unsigned q = (unsigned)(H * D) >> 2;
+        const unsigned magic = (q > 1 && n / 4 < (1ull << 32) / q) ? (unsigned)(((1ull << 32) + q - 1) / q) : 0u;
+        const unsigned grid = (unsigned)((n / 4 + 255) / 256);
+#define PMP_STEP4(KIND, K1) step_kernel4<KIND, K1><<<grid, 256, 0, st>>>(p, dyn, x, noise, seed, draw, elem0, start, goal, xo, trace, \
+                                                                          trace_stride, H, D, n / 4, magic)
+        if (kind == PMP_STEP_DDPM) { if (K == 1) PMP_STEP4(PMP_STEP_DDPM, true); else PMP_STEP4(PMP_STEP_DDPM, false); }
+        else { if (K == 1) PMP_STEP4(PMP_STEP_DDIM, true); else PMP_STEP4(PMP_STEP_DDIM, false); }
+#undef PMP_STEP4
+    }
     else
         step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, dyn, x, noise, seed, draw, elem0, start, goal, xo, trace,
                                                                 trace_stride, H, D, n);
