@@ -142,7 +142,9 @@ class TemporalUnet_WCond(nn.Module):
     # ------------------------------------------------------------------ engine plumbing
     def _signature(self):
         ps = list(self.parameters())
-        return (ps[0].device, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps[:4]))
+        # _weights_epoch: bumped by the training step's fused optimizer kernel, which updates the parameters in place
+        # without torch noticing (pmp_b200/train.py)
+        return (ps[0].device, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps[:4]), getattr(self, '_weights_epoch', 0))
 
     def engine(self, n_timesteps=None):
         """the pmp_b200.UnetEngine holding this module's current weights (rebuilt when they change)"""

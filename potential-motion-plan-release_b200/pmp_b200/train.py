@@ -157,6 +157,7 @@ class FlatAdamEMA:
         adam_ema_step(self.te.flat.P, self.te.G, self.M, self.V, self.ema, self.t, self.lr, self.betas, self.eps, grad_scale,
                       mode, self.ema_decay)
         self.te.dirty = True
+        self.te.unet._weights_epoch = getattr(self.te.unet, '_weights_epoch', 0) + 1     # the sampling engine re-reads the weights
         self.step += 1
 
     def ema_state_dict(self, like):

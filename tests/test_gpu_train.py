@@ -137,6 +137,14 @@ def test_dropin_loss_backward_and_trainer_steps():
         torch.manual_seed(7); np.random.seed(7)        # same t / noise / mask every step: the loss must go down
         losses.append(float(tr.train_step([batch])))
     assert losses[-1] < 0.9 * losses[0], losses
+    # sampling after training sees the trained weights (the fused optimizer updates them in place)
+    diffusion.eval()
+    xe = torch.randn(2, H, 2, device=dev); te_ = torch.tensor([10, 60], device=dev); we = walls[:2, 0]
+    e_trained = diffusion.model(xe, None, te_, we, use_dropout=False, force_dropout=False)
+    fresh = TemporalUnet_WCond(**a["unet"]); fresh.load_state_dict({k: v.detach().cpu() for k, v in diffusion.model.state_dict().items()})
+    e_fresh = fresh.to(dev).eval()(xe, None, te_, we, use_dropout=False, force_dropout=False)
+    assert torch.equal(e_trained, e_fresh)
+    diffusion.train()
     path = tr.save(0)
     ck = torch.load(path, map_location="cpu", weights_only=True)
     assert set(ck) == {"step", "model", "ema"} and ck["step"] == 12
