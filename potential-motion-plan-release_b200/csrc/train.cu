@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(128) gn_adjoint_kernel(const float* __restrict
     if (threadIdx.x < GS) { chg[threadIdx.x] = 0.f; chb[threadIdx.x] = 0.f; chy[threadIdx.x] = 0.f; }
     __syncthreads();
     float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool fixed_ch = (128 % GS) == 0;      // e = tid + 128 i  =>  e % GS == tid % GS
+    float acc_g = 0.f, acc_b = 0.f, acc_y = 0.f;
     for (int e = threadIdx.x; e < n; e += 128) {
         const int h = e / GS, cl = e - h * GS, c = g * GS + cl;
         const size_t i = (row0 + h) * C + c;
@@ -118,9 +120,11 @@ __global__ void __launch_bounds__(128) gn_adjoint_kernel(const float* __restrict
         const float q = gzz * a1 * ga;
         const float Q = zb * a1 * ga + gzz * a2 * ga * ga * yd;
         s[0] += q; s[1] += q * yh; s[2] += Q; s[3] += Q * yh; s[4] += q * yd;
-        atomicAdd(&chg[cl], zb * a1 * yh + gzz * (a2 * yh * ga * yd + a1 * yd));
-        atomicAdd(&chb[cl], zb * a1 + gzz * a2 * ga * yd);
+        const float dg = zb * a1 * yh + gzz * (a2 * yh * ga * yd + a1 * yd), db = zb * a1 + gzz * a2 * ga * yd;
+        if (fixed_ch) { acc_g += dg; acc_b += db; }        // this thread always sees the same channel: sum in registers
+        else { atomicAdd(&chg[cl], dg); atomicAdd(&chb[cl], db); }
     }
+    if (fixed_ch) { atomicAdd(&chg[threadIdx.x % GS], acc_g); atomicAdd(&chb[threadIdx.x % GS], acc_b); }
     block_sum<5>(s, red);
     const float inv = 1.0f / (float)n;
     const float m1 = s[0] * inv, m2 = s[1] * inv, mQ = s[2] * inv, mQy = s[3] * inv, mqd = s[4] * inv;
@@ -138,8 +142,12 @@ __global__ void __launch_bounds__(128) gn_adjoint_kernel(const float* __restrict
         const float v = rs * (Q - mQ - yh * mQy) - rs * ss * gy - rs * (yd * m2 + yh * mqd);
         ybar[i] = v;
         if (yh_) split_bf16(v, yh_[i], yl_[i]);
-        if (dbias) atomicAdd(&chy[e - h * GS], v);
+        if (dbias) {
+            if (fixed_ch) acc_y += v;
+            else atomicAdd(&chy[e - h * GS], v);
+        }
     }
+    if (dbias && fixed_ch) atomicAdd(&chy[threadIdx.x % GS], acc_y);
     __syncthreads();
     if (threadIdx.x < GS) {
         atomicAdd(dgamma + g * GS + threadIdx.x, chg[threadIdx.x]);

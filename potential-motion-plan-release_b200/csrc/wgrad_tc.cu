@@ -15,6 +15,7 @@
 // One CTA = one (128 x NT) output tile of one tap over a slice of K (split-K); the epilogue adds its tile into a
 // tap-major fp32 workspace Wt[k][co][ci] with vector reductions (red.global.add.v4.f32: 128 contiguous bytes per
 // thread), and wgrad_scatter_kernel adds the workspace into the flat gradient in the reference layout [co][ci][k].
+#include <algorithm>
 #include <map>
 #include <tuple>
 
@@ -23,6 +24,9 @@
 namespace pmp {
 namespace {
 using namespace tc;
+
+// columns of the transposed planes that `nterms` terms occupy, rounded up to whole K blocks
+static size_t wg_cols(int nterms, int R, int H) { return ((size_t)nterms * ((R + 7) / 8) * (H + 4) * 8 + 63) / 64 * 64; }
 
 constexpr int WG_THREADS = 192;      // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int WG_BK = 64;
@@ -162,25 +166,50 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 }
 
 // fp32 channels-last [R][H][ld] -> K-major BF16x3 planes: dst[c][col0 + ((g*(H+4) + 2 + h)*8 + r8] = split(src[8g + r8][h][c])
-// one block = (group of 8 samples, 16-channel tile); every channel row of the group is one contiguous run of (H+4)*8 columns;
-// the padding positions and the missing samples of a ragged last group are zeroed by a memset of the planes beforehand
-__global__ void __launch_bounds__(256) transpose_planes_kernel(const float* __restrict__ src, int ld, int R, int H, int C,
-                                                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                                               size_t Kld, size_t col0) {
+// One launch transposes all operands of a weight gradient (up to 4 jobs: O and I of both terms, blockIdx.z); one block =
+// (group of 8 samples, 16-channel tile): every channel row of the group is one contiguous run of (H+4)*8 columns, written
+// whole -- the 2 + 2 padding positions and the missing samples of a ragged last group as zeros -- and the blocks of the last
+// group of the last term also zero the columns up to `zero_end` (K rounding + tap-shift slack), so the planes need no memset.
+struct TJob {
+    const float* src; int ld, C;
+    __nv_bfloat16 *hi, *lo;
+    size_t col0;
+    int last;                 // 1: this job's last group zeroes [col_end, zero_end)
+};
+struct TJobs { TJob j[4]; int n; };
+
+__global__ void __launch_bounds__(256) transpose_planes_kernel(const __grid_constant__ TJobs jobs, int R, int H, size_t Kld,
+                                                               size_t zero_end) {
     extern __shared__ float tsm[];                 // [8][H][17]
-    const int g = blockIdx.x, c0 = blockIdx.y * 16;
+    const TJob& J = jobs.j[blockIdx.z];
+    const int g = blockIdx.x, c0 = blockIdx.y * 16, G = gridDim.x;
+    if (c0 >= J.C) return;
     const int nr = min(8, R - g * 8);
     for (int e = threadIdx.x; e < nr * H * 16; e += 256) {
         const int c = e & 15, rh = e >> 4;         // rh = r8 * H + h
-        tsm[rh * 17 + c] = (c0 + c < C) ? src[((size_t)g * 8 * H + rh) * ld + c0 + c] : 0.f;
+        tsm[rh * 17 + c] = (c0 + c < J.C) ? J.src[((size_t)g * 8 * H + rh) * J.ld + c0 + c] : 0.f;
     }
     __syncthreads();
-    const size_t base = col0 + ((size_t)g * (H + 4) + 2) * 8;
-    for (int e = threadIdx.x; e < 16 * H * 8; e += 256) {
-        const int r8 = e & 7, h = (e >> 3) % H, c = e / (8 * H);
-        if (r8 >= nr || c0 + c >= C) continue;
-        const size_t o = (size_t)(c0 + c) * Kld + base + (size_t)h * 8 + r8;
-        split_bf16(tsm[(r8 * H + h) * 17 + c], hi[o], lo[o]);
+    const int HP = H + 4;
+    const size_t base = J.col0 + (size_t)g * HP * 8;
+    const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+    for (int e = threadIdx.x; e < 16 * HP * 8; e += 256) {
+        const int r8 = e & 7, hp = (e >> 3) % HP, c = e / (8 * HP);
+        if (c0 + c >= J.C) continue;
+        const size_t o = (size_t)(c0 + c) * Kld + base + (size_t)hp * 8 + r8;
+        const int h = hp - 2;
+        if (h >= 0 && h < H && r8 < nr) split_bf16(tsm[(r8 * H + h) * 17 + c], J.hi[o], J.lo[o]);
+        else { J.hi[o] = z; J.lo[o] = z; }
+    }
+    if (J.last && g == G - 1) {
+        const size_t end = J.col0 + (size_t)G * HP * 8;
+        const int nz = (int)(zero_end - end);
+        for (int e = threadIdx.x; e < 16 * nz; e += 256) {
+            const int c = e / nz, k = e - c * nz;
+            if (c0 + c >= J.C) continue;
+            const size_t o = (size_t)(c0 + c) * Kld + end + k;
+            J.hi[o] = z; J.lo[o] = z;
+        }
     }
 }
 
@@ -252,8 +281,6 @@ bool wgrad_tc_eligible(int H, int Co, int Ci, int stride, int KS) {
 }
 
 // scratch floats launch_wgrad_tc needs for (R, H, Co, Ci, KS): planes of both operands (hi + lo) + the tap-major workspace
-static size_t wg_cols(int nterms, int R, int H) { return ((size_t)nterms * ((R + 7) / 8) * (H + 4) * 8 + 63) / 64 * 64; }
-
 size_t wgrad_tc_scratch_floats(int R, int H, int Co, int Ci, int KS) {
     const size_t K = wg_cols(2, R, H);
     const size_t Kld = K + 64;                                   // tap shifts read up to 2 columns past the end
@@ -273,11 +300,7 @@ int launch_wgrad_tc(const float* O1, int ldo1, const float* I1, int ldi1, const 
     __nv_bfloat16* il = ih + (size_t)Ci * Kld;
     float* Wt = scratch + ((size_t)(Co + Ci) * Kld * 2 * 2 + 3) / 4;
     Wt = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(Wt) + 15) & ~(uintptr_t)15);
-    PMP_CUDA_OK(cudaMemsetAsync(oh, 0, (size_t)(Co + Ci) * Kld * 2 * sizeof(__nv_bfloat16), st));
     PMP_CUDA_OK(cudaMemsetAsync(Wt, 0, (size_t)KS * Co * Ci * sizeof(float), st));
-    const float* Os[2] = {O1, O2};
-    const float* Is[2] = {I1, I2};
-    const int ldos[2] = {ldo1, ldo2}, ldis[2] = {ldi1, ldi2};
     const int G = (R + 7) / 8;
     const size_t tsmem = (size_t)8 * H * 17 * sizeof(float);
     static bool tattr = false;
@@ -285,11 +308,21 @@ int launch_wgrad_tc(const float* O1, int ldo1, const float* I1, int ldi1, const 
         PMP_CUDA_OK(cudaFuncSetAttribute(transpose_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 128 * 17 * 4));
         tattr = true;
     }
-    for (int t = 0; t < nterms; ++t) {
-        const size_t col0 = (size_t)t * G * (H + 4) * 8;
-        transpose_planes_kernel<<<dim3(G, Co / 16), 256, tsmem, st>>>(Os[t], ldos[t], R, H, Co, oh, ol, Kld, col0);
-        PMP_LAUNCH_OK();
-        transpose_planes_kernel<<<dim3(G, Ci / 16), 256, tsmem, st>>>(Is[t], ldis[t], R, H, Ci, ih, il, Kld, col0);
+    {
+        TJobs jobs;
+        memset(&jobs, 0, sizeof jobs);
+        const float* Os[2] = {O1, O2};
+        const float* Is[2] = {I1, I2};
+        const int ldos[2] = {ldo1, ldo2}, ldis[2] = {ldi1, ldi2};
+        for (int t = 0; t < nterms; ++t) {
+            const size_t col0 = (size_t)t * G * (H + 4) * 8;
+            const int last = t == nterms - 1;
+            jobs.j[jobs.n++] = TJob{Os[t], ldos[t], Co, oh, ol, col0, last};
+            jobs.j[jobs.n++] = TJob{Is[t], ldis[t], Ci, ih, il, col0, last};
+        }
+        // every column a K block or a shifted tap can touch: the used columns rounded up to 64, plus the slack
+        const size_t zero_end = wg_cols(nterms, R, H) + 64;
+        transpose_planes_kernel<<<dim3(G, (std::max(Co, Ci) + 15) / 16, jobs.n), 256, tsmem, st>>>(jobs, R, H, Kld, zero_end);
         PMP_LAUNCH_OK();
     }
     WgP P;

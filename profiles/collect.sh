@@ -9,6 +9,15 @@ python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest 
 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err || exit 1
 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_reference_arm.json 2> $out/${tag}_reference_arm.err
 python bench.py --workload eval200 --steps 20 --warmup 5 > $out/${tag}_eval200.json 2> $out/${tag}_eval200.err
+# training step and the other BASELINE configs under the same harness
+python bench.py --workload dualkuka_train --steps 10 --warmup 3 > $out/${tag}_train_dualkuka.json 2> $out/${tag}_train_dualkuka.err
+python bench.py --workload maze2d_train --steps 10 --warmup 3 > $out/${tag}_train_maze2d.json 2> $out/${tag}_train_maze2d.err
+python bench.py --workload kuka --batch 5000 --steps 2 --warmup 3 > $out/${tag}_bench_kuka.json 2> $out/${tag}_bench_kuka.err
+python bench.py --workload dualkuka --batch 5000 --steps 2 --warmup 3 > $out/${tag}_bench_dualkuka.json 2> $out/${tag}_bench_dualkuka.err
+python bench.py --workload comp2 --batch 3700 --steps 2 --warmup 3 > $out/${tag}_bench_comp2.json 2> $out/${tag}_bench_comp2.err
+python bench.py --workload comp3 --batch 3700 --steps 2 --warmup 3 > $out/${tag}_bench_comp3.json 2> $out/${tag}_bench_comp3.err
+ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 4000 -c 2400 --csv --log-file $out/${tag}_train_launches.csv \
+    python bench.py --workload dualkuka_train --steps 1 --warmup 3 > $out/${tag}_ncu_train.log 2>&1
 # launch list of the bench command (direct launches; one step of the full 10,000-problem workload)
 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1500 -c 800 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline > $out/${tag}_ncu_launches.log 2>&1
@@ -17,14 +26,13 @@ ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1500 -c 
 ncu --set full --clock-control none -k regex:conv_tc_kernel --launch-skip 120 --launch-count 60 \
     -f -o /tmp/${tag}_conv python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline > $out/${tag}_ncu_conv.log 2>&1
 ncu -i /tmp/${tag}_conv.ncu-rep --page raw --csv > $out/${tag}_conv_raw.csv 2>> $out/${tag}_ncu_conv.log
-# source-level capture of two launches: the 64-channel forward kernel and the dominant 512-channel kernel
-ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k regex:'conv_tc_kernel<64, 8, 0, 1, 1, 2, 1|conv_tc_kernel<256, 64, 0, 2, 1, 2' \
-    --launch-skip 40 --launch-count 2 -f -o $out/${tag}_conv_src python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline --batch 2000 \
-    > $out/${tag}_ncu_conv_src.log 2>&1
 # full capture of the HBM-bound kernels of the path (sampler update, swept check, Kuka sphere check)
-python tests/gpu_profile_aux.py > $out/${tag}_aux_plain.log 2>&1 && \
-ncu --set full --import-source on --clock-control none -k regex:'step_kernel|swept|kuka_kernel' --launch-skip 0 --launch-count 12 \
-    -f -o /tmp/${tag}_aux python tests/gpu_profile_aux.py > $out/${tag}_ncu_aux.log 2>&1
-ncu -i /tmp/${tag}_aux.ncu-rep --page raw --csv > $out/${tag}_aux_raw.csv 2>> $out/${tag}_ncu_aux.log
+python tests/gpu_profile_aux.py > $out/${tag}_aux_plain.log 2>&1
+: > $out/${tag}_aux_raw.csv
+for k in step_kernel4 swept_lane kuka_kernel; do
+    ncu --set full --clock-control none -k regex:$k --launch-skip 4 --launch-count 2 -f -o /tmp/${tag}_aux_$k \
+        python tests/gpu_profile_aux.py > $out/${tag}_ncu_aux_$k.log 2>&1
+    ncu -i /tmp/${tag}_aux_$k.ncu-rep --page raw --csv >> $out/${tag}_aux_raw.csv 2>> $out/${tag}_ncu_aux_$k.log
+done
 du -sh $out
 ls -la $out/${tag}_*

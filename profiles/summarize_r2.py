@@ -21,7 +21,7 @@ ROWS = 10000      # rows per launch in the bench (5,000 plans x CFG pair per fam
 def load(path):
     rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 10]
     h, u = rows[0], rows[1]
-    return h, u, rows[2:]
+    return h, u, [r for r in rows[2:] if r != h and r != u and len(r) == len(h)]      # (concatenated reports repeat the two header rows)
 
 
 def val(h, u, r, name):

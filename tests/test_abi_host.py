@@ -35,6 +35,15 @@ def test_library_exports_every_declared_symbol():
     assert lib.pmp_abi_version() == 1
 
 
+def test_release_library_has_no_work_skipping_switches():
+    """the diagnostic switches that skip work or pick other kernels (PMP_TC_DEBUG, PMP_TC_TIMERS, PMP_KEEP_FP32,
+    PMP_NO_UNCOND_DEDUP, PMP_PROFILE_DUMP ...) exist only in `make diag` builds: no such name is in the shipped library"""
+    raw = open(_lib.LIB_PATH, "rb").read()
+    for name in (b"PMP_TC_DEBUG", b"PMP_TC_TIMERS", b"PMP_TC_TIMER_MATCH", b"PMP_KEEP_FP32", b"PMP_NO_UNCOND_DEDUP",
+                 b"PMP_PROFILE_DUMP", b"PMP_TC_AR", b"PMP_TC_TEAM", b"PMP_TC_WIDE"):
+        assert name not in raw, name.decode()
+
+
 def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("GPU present")

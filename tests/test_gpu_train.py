@@ -55,6 +55,22 @@ def test_loss_and_every_parameter_gradient_match_the_oracle(fam, path):
         assert abs(got[0] - z["digest"][i][0]) <= 2e-3 * z["digest"][i][0] + GRAD_ATOL_FRAC * gn, k
 
 
+def test_ragged_batch_and_other_horizon_match_the_oracle():
+    """3 samples (a ragged group of the 8-sample interleave of the weight-gradient planes) at horizon 40 instead of 48"""
+    dev = torch.device("cuda:0")
+    cfg, sd, xn, t, walls, noise, keep, lw, z = golden_batch("m2d")
+    xn, t, walls, noise, keep, lw = xn[:3, :40].contiguous(), t[:3], walls[:3], noise[:3, :40].contiguous(), keep[:3], lw[:40].contiguous()
+    loss_ref, g_ref, _ = train_ref.loss_and_grads(sd, cfg, xn, t, walls, noise, keep, lw)
+    model, te = _engine("m2d", sd, 3, dev)
+    loss = te.loss_grad(xn, t, walls, noise, keep, lw)
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    gv = te.grad_views()
+    gn = float(torch.sqrt(sum((g.double() ** 2).sum() for g in g_ref.values())))
+    for k, ref in g_ref.items():
+        d = (gv[k].cpu().double() - ref.double()).norm().item()
+        assert d <= GRAD_RTOL * ref.double().norm().item() + GRAD_ATOL_FRAC * gn, (k, d, ref.norm().item())
+
+
 def test_gradient_accumulates_and_is_deterministic_enough():
     dev = torch.device("cuda:0")
     cfg, sd, xn, t, walls, noise, keep, lw, z = golden_batch("m2d")
@@ -150,3 +166,31 @@ def test_dropin_loss_backward_and_trainer_steps():
     assert set(ck) == {"step", "model", "ema"} and ck["step"] == 12
     assert set(ck["model"]) == set(ck["ema"]) == set(diffusion.state_dict())
     assert not torch.equal(ck["model"]["model.final_conv.1.weight"], ck["ema"]["model.final_conv.1.weight"])
+
+
+@pytest.mark.parametrize("R,H,Co,Ci,KS", [(4, 48, 64, 64, 5), (13, 24, 256, 64, 5), (5, 12, 512, 1024, 5), (9, 14, 768, 768, 1),
+                                          (64, 28, 256, 512, 5)])
+def test_weight_gradient_gemms_match_fp64(R, H, Co, Ci, KS):
+    """dW[co][ci][k] = sum_{r,h} O1 I1(shifted) + O2 I2(shifted): the fp32 CUDA-core kernel and the tcgen05 kernel (K-major
+    transposed BF16x3 planes, ragged sample groups, accumulation into an existing gradient) against an fp64 einsum"""
+    import ctypes as C
+    import pmp_b200
+    L = pmp_b200.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(R * 1000 + H)
+    o1, o2 = torch.randn(R, H, Co, generator=g).to(dev), torch.randn(R, H, Co, generator=g).to(dev)
+    i1, i2 = torch.randn(R, H, Ci, generator=g).to(dev), torch.randn(R, H, Ci, generator=g).to(dev)
+    pad = KS // 2
+    ref = torch.zeros(Co, Ci, KS, device=dev, dtype=torch.float64)
+    for o, i in ((o1, i1), (o2, i2)):
+        ip = torch.nn.functional.pad(i.double(), (0, 0, pad, pad))
+        for k in range(KS):
+            ref[:, :, k] += torch.einsum("rhc,rhd->cd", o.double(), ip[:, k:k + H])
+    scratch = torch.full((L.pmp_debug_wgrad_scratch_floats(R, H, Co, Ci, KS),), float("nan"), device=dev)   # stale garbage
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    for tc, tol in ((0, 2e-6), (1, 3e-5)):
+        dw = torch.ones(Co, Ci, KS, device=dev)                      # accumulates into what is there
+        assert L.pmp_debug_wgrad(p(o1), p(i1), p(o2), p(i2), H, Co, Ci, KS, R, p(dw), p(scratch), tc, 0, st) == 0, L.pmp_last_error()
+        err = float(((dw.double() - 1.0) - ref).norm() / ref.norm())
+        assert err <= tol, (tc, err)
