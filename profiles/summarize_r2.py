@@ -21,7 +21,22 @@ ROWS = 10000      # rows per launch in the bench (5,000 plans x CFG pair per fam
 def load(path):
     rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 10]
     h, u = rows[0], rows[1]
-    return h, u, [r for r in rows[2:] if r != h and r != u and len(r) == len(h)]      # (concatenated reports repeat the two header rows)
+    return h, u, rows[2:]
+
+
+def load_sections(path):
+    """(header, units, row) of every kernel of a file that is several `ncu --page raw --csv` reports back to back"""
+    rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 10]
+    out, h, u = [], None, None
+    i = 0
+    while i < len(rows):
+        if "Kernel Name" in rows[i] and "ID" in rows[i]:
+            h, u = rows[i], rows[i + 1]
+            i += 2
+            continue
+        out.append((h, u, rows[i]))
+        i += 1
+    return out
 
 
 def val(h, u, r, name):
@@ -107,7 +122,7 @@ json.dump({
 }, open("%s/%s_traffic.json" % (HERE, tag), "w"), indent=1)
 
 # HBM-bound kernels of the path
-h, u, data = load("%s/%s_aux_raw.csv" % (d, tag))
+data = load_sections("%s/%s_aux_raw.csv" % (d, tag))
 with open("%s/%s_aux_kernels.txt" % (HERE, tag), "w") as f:
     f.write("# ncu --set full --clock-control none of tests/gpu_profile_aux.py: fused sampler update (400,000 plans), Maze2D swept\n"
             "# check (1,000,000 trajectories, 10 candidates per environment), Kuka sphere-link check (200,000 trajectories)\n")
@@ -116,7 +131,7 @@ with open("%s/%s_aux_kernels.txt" % (HERE, tag), "w") as f:
              "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
              "smsp__inst_executed.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
              "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
-    for r in data:
+    for h, u, r in data:
         nm = re.sub(r"\(.*", "", r[h.index("Kernel Name")]).replace("void ", "").replace("pmp::<unnamed>::", "")
         f.write("%s\n" % nm)
         for n in names:
