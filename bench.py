@@ -238,15 +238,28 @@ def run_train(args, dev, world, rank):
     if world > 1:
         # the overlapped bucket all-reduce (events recorded inside the reverse pass) against a reduction issued after the whole
         # pass, on the same micro-batch and draws: identical sums, and identical parameters on every rank after the steps
+        # (on the exact-fp32 conv path: the tensor-core path is not bitwise reproducible run to run -- BF16 hi/lo splits
+        # re-drawn by last-bit differences, ~4e-5 normwise -- which would hide a race behind noise)
         from pmp_b200 import train as ptrain
         import numpy as np
+        tr.te.engine.set_gemm_path(0)
         torch.manual_seed(5 + rank); np.random.seed(5 + rank)
         tr.micro_batch((x_d, cond_d, walls_d), True); tr.reducer.run(); torch.cuda.synchronize()
         g_over = tr.te.G.clone()
         torch.manual_seed(5 + rank); np.random.seed(5 + rank)
         tr.micro_batch((x_d, cond_d, walls_d), True)
         ptrain.GradAllReduce(tr.te.G, bucket_mb=1 << 20).run(); torch.cuda.synchronize()
-        ddp_check = {"overlap_vs_serial_rel_diff": float((g_over - tr.te.G).norm() / tr.te.G.norm())}
+        g_ser = tr.te.G.clone()
+        # noise floor: the same serial reduction once more (the step is not bitwise reproducible)
+        torch.manual_seed(5 + rank); np.random.seed(5 + rank)
+        tr.micro_batch((x_d, cond_d, walls_d), True)
+        ptrain.GradAllReduce(tr.te.G, bucket_mb=1 << 20).run(); torch.cuda.synchronize()
+        worst = sorted(((float((a_ - b_).norm() / (b_.norm() + 1e-30)), k_) for k_, a_, b_ in zip(
+            tr.te.flat.names, tr.te.flat.views(g_over), tr.te.flat.views(g_ser))), reverse=True)[:4]
+        ddp_check = {"overlap_vs_serial_rel_diff": float((g_over - g_ser).norm() / g_ser.norm()), "worst_params": worst,
+                     "serial_vs_serial_rel_diff": float((tr.te.G - g_ser).norm() / g_ser.norm()),
+                     "checked_on": "gemm path 0 (fp32 CUDA-core convolutions)"}
+        tr.te.engine.set_gemm_path(args.gemm_path)
     for i in range(max(args.warmup, 3)):
         tr.train_step([(x_d, cond_d, walls_d)])
     barrier()
