@@ -82,8 +82,10 @@ class TrainerPBDiff(object):
         loss = None
         for i, batch in enumerate(batches):
             loss = self.micro_batch(batch, first=(i == 0))
-        scale = 1.0 / len(batches)
+        self.reducer.run()                               # sum over the ranks (overlaps the reverse pass of the last micro-batch)
+        scale = 1.0 / (len(batches) * self.reducer.world)
         if self.clip_grad_max or self.clip_grad:
+            # clipping acts on the averaged gradient (clip_grad_value_ / clip_grad_norm_, training_pbdiff.py:125-129)
             G = self.te.G
             G.mul_(scale)
             scale = 1.0
@@ -91,10 +93,9 @@ class TrainerPBDiff(object):
                 G.clamp_(-self.clip_grad_max, self.clip_grad_max)
             if self.clip_grad:
                 G.mul_(torch.clamp(self.clip_grad / (G.norm() + 1e-6), max=1.0))
-        self.reducer.run()
         if self.lr_warmupDecay:
             self.opt.lr = warmup_cosine_lr(self.step, self.n_train_steps, self.train_lr, self.train_lr / 100., self.warmup_steps)
-        self.opt.update(grad_scale=scale / self.reducer.world)
+        self.opt.update(grad_scale=scale)
         self.step += 1
         return loss
 

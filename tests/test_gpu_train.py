@@ -71,6 +71,33 @@ def test_ragged_batch_and_other_horizon_match_the_oracle():
         assert d <= GRAD_RTOL * ref.double().norm().item() + GRAD_ATOL_FRAC * gn, (k, d, ref.norm().item())
 
 
+def test_kuka_family_without_positional_encoding_matches_the_oracle():
+    """Kuka 7-DoF: wall encoder without the sinusoidal positional encoding / first LayerNorm (config/kuka7d/kuka_exp.py:42),
+    D = 7; synthetic batch (no reference golden for this family: the checker is the pinned oracle)"""
+    from oracle import unet_ref, sampler_ref
+    dev = torch.device("cuda:0")
+    a = synth.arch("kuka")
+    cfg = unet_ref.UnetCfg(a["unet"])
+    sd = unet_ref.synth_weights(a["unet"], 1)
+    B, H, D = 3, 48, 7
+    g = torch.Generator().manual_seed(9)
+    xn = torch.randn(B, H, D, generator=g).clamp(-1, 1)
+    noise = torch.randn(B, H, D, generator=g)
+    t = torch.tensor([3, 50, 97])
+    walls = torch.tensor(synth.make_problems("kuka", B, 4)["walls"])
+    keep = torch.tensor([1.0, 0.0, 1.0])
+    lw = torch.ones(H, D); lw[0] = 0; lw[-1] = 0
+    loss_ref, g_ref, _ = train_ref.loss_and_grads(sd, cfg, xn, t, walls, noise, keep, lw)
+    model, te = _engine("kuka", sd, 3, dev)
+    loss = te.loss_grad(xn, t, walls, noise, keep, lw)
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    gv = te.grad_views()
+    gn = float(torch.sqrt(sum((x.double() ** 2).sum() for x in g_ref.values())))
+    for k, ref in g_ref.items():
+        d = (gv[k].cpu().double() - ref.double()).norm().item()
+        assert d <= GRAD_RTOL * ref.double().norm().item() + GRAD_ATOL_FRAC * gn, (k, d, ref.norm().item())
+
+
 def test_gradient_accumulates_and_is_deterministic_enough():
     dev = torch.device("cuda:0")
     cfg, sd, xn, t, walls, noise, keep, lw, z = golden_batch("m2d")
