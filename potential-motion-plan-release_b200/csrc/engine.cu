@@ -1289,6 +1289,9 @@ void pmp_model_destroy(pmp_model* m) {
     if (m->t_iota) cudaFree(m->t_iota);
     if (m->train) {
         for (cudaEvent_t e : m->train->bucket_ev) cudaEventDestroy(e);
+        if (m->train->ev_main) cudaEventDestroy(m->train->ev_main);
+        if (m->train->ev_side) cudaEventDestroy(m->train->ev_side);
+        if (m->train->side) cudaStreamDestroy(m->train->side);
         if (m->train->map_dev) cudaFree(m->train->map_dev);
         delete m->train;
     }

@@ -52,6 +52,7 @@ __device__ __forceinline__ void silu_d012(float p, float& a0, float& a1, float& 
 // GroupNorm(8) + SiLU, tangent:  yd = d(conv output) -> zd = d(activation output)
 //   yhd = r (yd - mean(yd) - yhat mean(yhat yd)),  zd = silu'(gamma yhat + beta) gamma yhd (+ addend)
 // one block per (sample, group) slab of Hl x GS elements of the channels-last [R][Hl][C] tensors
+template <bool CACHE>
 __global__ void __launch_bounds__(128) gn_tangent_kernel(const float* __restrict__ yd, int ldyd, const float* __restrict__ yhat,
                                                          const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, const float* __restrict__ addend,
@@ -62,20 +63,29 @@ __global__ void __launch_bounds__(128) gn_tangent_kernel(const float* __restrict
     const int r = blockIdx.x >> 3, g = blockIdx.x & 7, GS = C >> 3, n = Hl * GS;
     const size_t row0 = (size_t)r * Hl;
     float s[2] = {0.f, 0.f};
-    for (int e = threadIdx.x; e < n; e += 128) {
+    constexpr int NC = CACHE ? 12 : 1;      // CACHE: at most 12 elements per thread, kept in registers between the passes
+    float cd[NC], cy[NC];
+#pragma unroll
+    for (int it = 0; it < (CACHE ? NC : 1 << 30); ++it) {
+        const int e = threadIdx.x + 128 * it;
+        if (e >= n) break;
         const int h = e / GS, c = g * GS + (e - h * GS);
-        const float d = yd[(row0 + h) * ldyd + c];
+        const float d = yd[(row0 + h) * ldyd + c], yh = yhat[(row0 + h) * C + c];
+        if (CACHE) { cd[it] = d; cy[it] = yh; }
         s[0] += d;
-        s[1] += d * yhat[(row0 + h) * C + c];
+        s[1] += d * yh;
     }
     block_sum<2>(s, red);
     const float inv = 1.0f / (float)n, md = s[0] * inv, ms = s[1] * inv, rs = rstd[r * 8 + g];
     if (threadIdx.x == 0) sOut[r * 8 + g] = ms;
-    for (int e = threadIdx.x; e < n; e += 128) {
+#pragma unroll
+    for (int it = 0; it < (CACHE ? NC : 1 << 30); ++it) {
+        const int e = threadIdx.x + 128 * it;
+        if (e >= n) break;
         const int h = e / GS, c = g * GS + (e - h * GS);
         const size_t i = (row0 + h) * C + c;
-        const float yh = yhat[i];
-        const float t = rs * (yd[(row0 + h) * ldyd + c] - md - yh * ms);
+        const float yh = CACHE ? cy[it] : yhat[i];
+        const float t = rs * ((CACHE ? cd[it] : yd[(row0 + h) * ldyd + c]) - md - yh * ms);
         yhd[i] = t;
         float a0, a1, a2;
         const float ga = gamma[c];
@@ -94,6 +104,9 @@ __global__ void __launch_bounds__(128) gn_tangent_kernel(const float* __restrict
 //   Q = zbar a1 gamma + gz a2 gamma^2 yhd
 //   ybar = r (Q - mean Q - yhat mean(Q yhat)) - r s g_y - r (yhd mean(q yhat) + yhat mean(q yhd))
 // and accumulates d gamma, d beta
+// CACHE: the slab has at most 12 elements per thread: q, Q, yhat, yhd stay in registers between the two passes (one global
+// read pass, SiLU derivatives evaluated once)
+template <bool CACHE>
 __global__ void __launch_bounds__(128) gn_adjoint_kernel(const float* __restrict__ zbar, int ldzb, const float* __restrict__ gz,
                                                          int ldgz, const float* __restrict__ yhat, const float* __restrict__ yhd,
                                                          const float* __restrict__ rstd, const float* __restrict__ sIn,
@@ -110,7 +123,12 @@ __global__ void __launch_bounds__(128) gn_adjoint_kernel(const float* __restrict
     float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     const bool fixed_ch = (128 % GS) == 0;      // e = tid + 128 i  =>  e % GS == tid % GS
     float acc_g = 0.f, acc_b = 0.f, acc_y = 0.f;
-    for (int e = threadIdx.x; e < n; e += 128) {
+    constexpr int NC = CACHE ? 12 : 1;
+    float cq[NC], cQ[NC], cyh[NC], cyd[NC];
+#pragma unroll
+    for (int it = 0; it < (CACHE ? NC : 1 << 30); ++it) {
+        const int e = threadIdx.x + 128 * it;
+        if (e >= n) break;
         const int h = e / GS, cl = e - h * GS, c = g * GS + cl;
         const size_t i = (row0 + h) * C + c;
         const float yh = yhat[i], yd = yhd[i], ga = gamma[c];
@@ -119,6 +137,7 @@ __global__ void __launch_bounds__(128) gn_adjoint_kernel(const float* __restrict
         silu_d012(ga * yh + beta[c], a0, a1, a2);
         const float q = gzz * a1 * ga;
         const float Q = zb * a1 * ga + gzz * a2 * ga * ga * yd;
+        if (CACHE) { cq[it] = q; cQ[it] = Q; cyh[it] = yh; cyd[it] = yd; }
         s[0] += q; s[1] += q * yh; s[2] += Q; s[3] += Q * yh; s[4] += q * yd;
         const float dg = zb * a1 * yh + gzz * (a2 * yh * ga * yd + a1 * yd), db = zb * a1 + gzz * a2 * ga * yd;
         if (fixed_ch) { acc_g += dg; acc_b += db; }        // this thread always sees the same channel: sum in registers
@@ -129,15 +148,24 @@ __global__ void __launch_bounds__(128) gn_adjoint_kernel(const float* __restrict
     const float inv = 1.0f / (float)n;
     const float m1 = s[0] * inv, m2 = s[1] * inv, mQ = s[2] * inv, mQy = s[3] * inv, mqd = s[4] * inv;
     const float rs = rstd[r * 8 + g], ss = sIn[r * 8 + g];
-    for (int e = threadIdx.x; e < n; e += 128) {
+#pragma unroll
+    for (int it = 0; it < (CACHE ? NC : 1 << 30); ++it) {
+        const int e = threadIdx.x + 128 * it;
+        if (e >= n) break;
         const int h = e / GS, c = g * GS + (e - h * GS);
         const size_t i = (row0 + h) * C + c;
-        const float yh = yhat[i], yd = yhd[i], ga = gamma[c];
-        const float zb = zbar[(row0 + h) * ldzb + c], gzz = gz[(row0 + h) * ldgz + c];
-        float a0, a1, a2;
-        silu_d012(ga * yh + beta[c], a0, a1, a2);
-        const float q = gzz * a1 * ga;
-        const float Q = zb * a1 * ga + gzz * a2 * ga * ga * yd;
+        float q, Q, yh, yd;
+        if (CACHE) {
+            q = cq[it]; Q = cQ[it]; yh = cyh[it]; yd = cyd[it];
+        } else {
+            yh = yhat[i]; yd = yhd[i];
+            const float ga = gamma[c];
+            const float zb = zbar[(row0 + h) * ldzb + c], gzz = gz[(row0 + h) * ldgz + c];
+            float a0, a1, a2;
+            silu_d012(ga * yh + beta[c], a0, a1, a2);
+            q = gzz * a1 * ga;
+            Q = zb * a1 * ga + gzz * a2 * ga * ga * yd;
+        }
         const float gy = rs * (q - m1 - yh * m2);
         const float v = rs * (Q - mQ - yh * mQy) - rs * ss * gy - rs * (yd * m2 + yh * mqd);
         ybar[i] = v;
@@ -590,7 +618,10 @@ int launch_gn_tangent(const float* yd, int ldyd, const float* yhat, const float*
                       const float* addend, int ldad, float* zd, int ldz, __nv_bfloat16* zh, __nv_bfloat16* zl, float* yhd, float* s,
                       int R, int Hl, int C, cudaStream_t st) {
     PMP_REQUIRE(C % 8 == 0 && C / 8 <= 128, "GroupNorm(8) tangent: C = %d unsupported", C);
-    gn_tangent_kernel<<<R * 8, 128, 0, st>>>(yd, ldyd, yhat, rstd, gamma, beta, addend, ldad, zd, ldz, zh, zl, yhd, s, Hl, C);
+    if (Hl * (C / 8) <= 12 * 128)
+        gn_tangent_kernel<true><<<R * 8, 128, 0, st>>>(yd, ldyd, yhat, rstd, gamma, beta, addend, ldad, zd, ldz, zh, zl, yhd, s, Hl, C);
+    else
+        gn_tangent_kernel<false><<<R * 8, 128, 0, st>>>(yd, ldyd, yhat, rstd, gamma, beta, addend, ldad, zd, ldz, zh, zl, yhd, s, Hl, C);
     PMP_LAUNCH_OK();
     return 0;
 }
@@ -598,8 +629,12 @@ int launch_gn_adjoint(const float* zbar, int ldzb, const float* gz, int ldgz, co
                       const float* s, const float* gamma, const float* beta, float* ybar, __nv_bfloat16* yh, __nv_bfloat16* yl,
                       float* dgamma, float* dbeta, float* dbias, int R, int Hl, int C, cudaStream_t st) {
     PMP_REQUIRE(C % 8 == 0 && C / 8 <= 128, "GroupNorm(8) adjoint: C = %d unsupported", C);
-    gn_adjoint_kernel<<<R * 8, 128, 0, st>>>(zbar, ldzb, gz, ldgz, yhat, yhd, rstd, s, gamma, beta, ybar, yh, yl, dgamma, dbeta, dbias,
-                                             Hl, C);
+    if (Hl * (C / 8) <= 12 * 128)
+        gn_adjoint_kernel<true><<<R * 8, 128, 0, st>>>(zbar, ldzb, gz, ldgz, yhat, yhd, rstd, s, gamma, beta, ybar, yh, yl, dgamma, dbeta,
+                                                       dbias, Hl, C);
+    else
+        gn_adjoint_kernel<false><<<R * 8, 128, 0, st>>>(zbar, ldzb, gz, ldgz, yhat, yhd, rstd, s, gamma, beta, ybar, yh, yl, dgamma, dbeta,
+                                                        dbias, Hl, C);
     PMP_LAUNCH_OK();
     return 0;
 }

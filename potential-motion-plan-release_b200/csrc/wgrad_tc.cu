@@ -179,29 +179,50 @@ struct TJob {
 struct TJobs { TJob j[4]; int n; };
 
 __global__ void __launch_bounds__(256) transpose_planes_kernel(const __grid_constant__ TJobs jobs, int R, int H, size_t Kld,
-                                                               size_t zero_end) {
+                                                               size_t zero_end, int vec) {
     extern __shared__ float tsm[];                 // [8][H][17]
     const TJob& J = jobs.j[blockIdx.z];
     const int g = blockIdx.x, c0 = blockIdx.y * 16, G = gridDim.x;
     if (c0 >= J.C) return;
     const int nr = min(8, R - g * 8);
-    for (int e = threadIdx.x; e < nr * H * 16; e += 256) {
-        const int c = e & 15, rh = e >> 4;         // rh = r8 * H + h
-        tsm[rh * 17 + c] = (c0 + c < J.C) ? J.src[((size_t)g * 8 * H + rh) * J.ld + c0 + c] : 0.f;
+    if (vec) {
+        // 16-byte loads: 4 lanes cover the 16 channels of one (sample, position) row
+        for (int e = threadIdx.x; e < nr * H * 4; e += 256) {
+            const int q4 = e & 3, rh = e >> 2;     // rh = r8 * H + h
+            const float4 v = __ldg(reinterpret_cast<const float4*>(J.src + ((size_t)g * 8 * H + rh) * J.ld + c0 + 4 * q4));
+            float* d = tsm + rh * 17 + 4 * q4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    } else {
+        for (int e = threadIdx.x; e < nr * H * 16; e += 256) {
+            const int c = e & 15, rh = e >> 4;
+            tsm[rh * 17 + c] = (c0 + c < J.C) ? J.src[((size_t)g * 8 * H + rh) * J.ld + c0 + c] : 0.f;
+        }
     }
     __syncthreads();
     const int HP = H + 4;
     const size_t base = J.col0 + (size_t)g * HP * 8;
-    const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
-    for (int e = threadIdx.x; e < 16 * HP * 8; e += 256) {
-        const int r8 = e & 7, hp = (e >> 3) % HP, c = e / (8 * HP);
+    // one thread = the 8 interleaved samples of one (channel, position): two 16-byte stores (hi, lo); consecutive threads
+    // take consecutive positions, so a warp writes 512 contiguous bytes per plane
+    for (int e = threadIdx.x; e < 16 * HP; e += 256) {
+        const int hp = e % HP, c = e / HP;
         if (c0 + c >= J.C) continue;
-        const size_t o = (size_t)(c0 + c) * Kld + base + (size_t)hp * 8 + r8;
         const int h = hp - 2;
-        if (h >= 0 && h < H && r8 < nr) split_bf16(tsm[(r8 * H + h) * 17 + c], J.hi[o], J.lo[o]);
-        else { J.hi[o] = z; J.lo[o] = z; }
+        uint32_t ph[4] = {0u, 0u, 0u, 0u}, pl[4] = {0u, 0u, 0u, 0u};
+        if (h >= 0 && h < H) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float a = (2 * k < nr) ? tsm[((2 * k) * H + h) * 17 + c] : 0.f;
+                const float b = (2 * k + 1 < nr) ? tsm[((2 * k + 1) * H + h) * 17 + c] : 0.f;
+                split_bf16x2(a, b, ph[k], pl[k]);
+            }
+        }
+        const size_t o = (size_t)(c0 + c) * Kld + base + (size_t)hp * 8;
+        *reinterpret_cast<uint4*>(J.hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        *reinterpret_cast<uint4*>(J.lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
     if (J.last && g == G - 1) {
+        const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
         const size_t end = J.col0 + (size_t)G * HP * 8;
         const int nz = (int)(zero_end - end);
         for (int e = threadIdx.x; e < 16 * nz; e += 256) {
@@ -322,7 +343,10 @@ int launch_wgrad_tc(const float* O1, int ldo1, const float* I1, int ldi1, const 
         }
         // every column a K block or a shifted tap can touch: the used columns rounded up to 64, plus the slack
         const size_t zero_end = wg_cols(nterms, R, H) + 64;
-        transpose_planes_kernel<<<dim3(G, (std::max(Co, Ci) + 15) / 16, jobs.n), 256, tsmem, st>>>(jobs, R, H, Kld, zero_end);
+        int vec = 1;      // 16-byte loads when every operand allows them
+        for (int i = 0; i < jobs.n; ++i)
+            if ((reinterpret_cast<uintptr_t>(jobs.j[i].src) & 15) || (jobs.j[i].ld & 3) || (jobs.j[i].C & 15)) vec = 0;
+        transpose_planes_kernel<<<dim3(G, (std::max(Co, Ci) + 15) / 16, jobs.n), 256, tsmem, st>>>(jobs, R, H, Kld, zero_end, vec);
         PMP_LAUNCH_OK();
     }
     WgP P;
