@@ -267,6 +267,8 @@ int launch_adam_ema(float* p, const float* g, float* m, float* v, float* ema, si
                     float eps, int step, float grad_scale, int ema_mode, float ema_beta, cudaStream_t st);
 int launch_repack(const float* P, const uint32_t* map, float* arena, size_t n, cudaStream_t st);
 int launch_planes(const float* w, int K, int C, int N, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
+// jobs_dev: device array of {const float* w; bf16* hi; bf16* lo; int K, C, N} (train.cu PlaneJob)
+int launch_planes_all(const void* jobs_dev, int njobs, size_t max_elems, cudaStream_t st);
 int launch_split_planes(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);
 
 }  // namespace pmp

@@ -1289,6 +1289,7 @@ void pmp_model_destroy(pmp_model* m) {
     if (m->t_iota) cudaFree(m->t_iota);
     if (m->train) {
         for (cudaEvent_t e : m->train->bucket_ev) cudaEventDestroy(e);
+        if (m->train->plane_jobs_dev) cudaFree(m->train->plane_jobs_dev);
         if (m->train->ev_main) cudaEventDestroy(m->train->ev_main);
         if (m->train->ev_side) cudaEventDestroy(m->train->ev_side);
         if (m->train->side) cudaStreamDestroy(m->train->side);
@@ -1393,9 +1394,21 @@ int pmp_train_sync_weights(pmp_model* m, int rebuild_tables, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if ((rc = launch_repack(m->train->P, m->train->map_dev, m->arena, m->arena_n, st))) return rc;
-    if (m->arena16)
-        for (const auto& r : m->plane_recs)
-            if ((rc = launch_planes(m->arena + r.src, r.K, r.C, r.N, m->arena16 + r.hi, m->arena16 + r.lo, st))) return rc;
+    if (m->arena16 && !m->plane_recs.empty()) {
+        TrainState* ts = m->train;
+        if (!ts->plane_jobs_dev) {
+            struct PJ { const float* w; __nv_bfloat16* hi; __nv_bfloat16* lo; int K, C, N; };
+            std::vector<PJ> jobs;
+            for (const auto& r : m->plane_recs) {
+                jobs.push_back(PJ{m->arena + r.src, m->arena16 + r.hi, m->arena16 + r.lo, r.K, r.C, r.N});
+                ts->max_plane_elems = std::max(ts->max_plane_elems, (size_t)r.K * r.C * r.N);
+            }
+            PMP_CUDA_OK(cudaMalloc(&ts->plane_jobs_dev, jobs.size() * sizeof(PJ)));
+            PMP_CUDA_OK(cudaMemcpy(ts->plane_jobs_dev, jobs.data(), jobs.size() * sizeof(PJ), cudaMemcpyHostToDevice));
+            ts->n_plane_jobs = (int)jobs.size();
+        }
+        if ((rc = launch_planes_all(ts->plane_jobs_dev, ts->n_plane_jobs, ts->max_plane_elems, st))) return rc;
+    }
     if (rebuild_tables && (rc = build_time_tables(m, st))) return rc;
     return 0;
 }

@@ -605,6 +605,18 @@ __global__ void planes_kernel(const float* __restrict__ w, int K, int C, int N, 
     const float v = w[((size_t)k * C + c) * N + nn];
     split_bf16(v, hi[i], lo[i]);
 }
+// all plane pairs of the model in ONE launch: blockIdx.y = weight, blockIdx.x strides over its elements
+struct PlaneJob { const float* w; __nv_bfloat16* hi; __nv_bfloat16* lo; int K, C, N; };
+__global__ void __launch_bounds__(256) planes_all_kernel(const PlaneJob* __restrict__ jobs) {
+    const PlaneJob j = jobs[blockIdx.y];
+    const size_t n = (size_t)j.K * j.C * j.N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % j.C);
+        const int nn = (int)((i / j.C) % j.N);
+        const int k = (int)(i / ((size_t)j.C * j.N));
+        split_bf16(j.w[((size_t)k * j.C + c) * j.N + nn], j.hi[i], j.lo[i]);
+    }
+}
 __global__ void split_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) split_bf16(x[i], hi[i], lo[i]);
@@ -841,6 +853,14 @@ int launch_planes(const float* w, int K, int C, int N, __nv_bfloat16* hi, __nv_b
     const size_t n = (size_t)K * C * N;
     if (!n) return 0;
     planes_kernel<<<nblk(n), 256, 0, st>>>(w, K, C, N, hi, lo);
+    PMP_LAUNCH_OK();
+    return 0;
+}
+int launch_planes_all(const void* jobs_dev, int njobs, size_t max_elems, cudaStream_t st) {
+    if (!njobs) return 0;
+    unsigned gx = nblk(max_elems / 4 + 1);
+    if (gx > 592) gx = 592;
+    planes_all_kernel<<<dim3(gx, njobs), 256, 0, st>>>(reinterpret_cast<const PlaneJob*>(jobs_dev));
     PMP_LAUNCH_OK();
     return 0;
 }
