@@ -142,3 +142,25 @@ with open("%s/%s_aux_kernels.txt" % (HERE, tag), "w") as f:
         f.write("    %-72s %.1f GB/s\n\n" % ("achieved DRAM bandwidth (bytes / duration)", by / (t * 1e-6) / 1e9))
 
 summarize.launches("%s/%s_launches.csv" % (d, tag), "%s/%s_launches.txt" % (HERE, tag))
+
+
+def train_kernels(path, out):
+    """table of an `ncu --set full` capture of training-step kernels (raw csv)"""
+    h, u, data = load(path)
+    names = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread",
+             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum"]
+    with open(out, "w") as f:
+        f.write("# ncu --set full --clock-control none of `python bench.py --workload dualkuka_train` (batch 256, H = 56), one window of\n"
+                "# the reverse pass: time_us, grid, registers, DRAM %, SM %, tensor-pipe %, DRAM MB read / written\n")
+        for r in data:
+            nm = re.sub(r"\(.*", "", r[h.index("Kernel Name")]).replace("void ", "").replace("pmp::<unnamed>::", "")
+            f.write("%-36s %9.1f %6s %4s %6.1f %6.1f %6.1f %9.1f %9.1f\n" % (
+                nm[:36], val(h, u, r, names[0]), r[h.index(names[1])], r[h.index(names[2])], val(h, u, r, names[3]),
+                val(h, u, r, names[4]), val(h, u, r, names[5]), val(h, u, r, names[6]) / 1e6, val(h, u, r, names[7]) / 1e6))
+
+
+if os.path.exists("%s/%s_train_raw.csv" % (d, tag)):
+    train_kernels("%s/%s_train_raw.csv" % (d, tag), "%s/%s_train_kernels.txt" % (HERE, tag))
+if os.path.exists("%s/%s_train_launches.csv" % (d, tag)):
+    summarize.launches("%s/%s_train_launches.csv" % (d, tag), "%s/%s_train_launches.txt" % (HERE, tag))
