@@ -107,7 +107,7 @@ def test_gradient_accumulates_and_is_deterministic_enough():
     te.loss_grad(xn, t, walls, noise, keep, lw, zero=False)
     # not bitwise: split-K partial sums meet through atomics, and a last-bit change of an embedding row re-draws the
     # BF16 hi/lo split of the activations behind it -- run-to-run differences stay at the BF16x3 error level (~3e-5)
-    assert float((te.G - 2 * g1).norm()) <= 2e-4 * float(g1.norm())
+    assert float((te.G - 2 * g1).norm()) <= 5e-4 * float(g1.norm())
 
 
 def test_fused_adam_ema_matches_torch_adam():
