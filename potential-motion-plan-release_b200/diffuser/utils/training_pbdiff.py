@@ -31,7 +31,7 @@ class TrainerPBDiff(object):
                  gradient_accumulate_every=2, step_start_ema=2000, update_ema_every=10, log_freq=100, sample_freq=1000,
                  save_freq=1000, label_freq=100000, save_parallel=False, n_reference=8, bucket=None, train_device='cuda',
                  save_checkpoints=False, results_folder='./results', n_samples=2, num_render_samples=2, clip_grad=False,
-                 clip_grad_max=False, n_train_steps=None, trainer_dict={}, num_workers=0):
+                 clip_grad_max=False, n_train_steps=None, trainer_dict={}, num_workers=0, shuffle=True):
         self.model = diffusion_model
         self.dataset = dataset
         self.batch_size = train_batch_size
@@ -45,8 +45,9 @@ class TrainerPBDiff(object):
         self.train_lr, self.n_train_steps = train_lr, n_train_steps
         self.warmup_steps = trainer_dict.get('warmup_steps_pct', 0.0) * (n_train_steps or 0)
         if dataset is not None:
+            it = isinstance(dataset, torch.utils.data.IterableDataset)
             self.dataloader = cycle(torch.utils.data.DataLoader(dataset, batch_size=train_batch_size, num_workers=num_workers,
-                                                                shuffle=True, pin_memory=True))
+                                                                shuffle=shuffle and not it, pin_memory=True))
         self.model.train()
         self.te = self.model.train_engine()
         self.opt = ptrain.FlatAdamEMA(self.te, lr=train_lr, ema_decay=ema_decay, step_start_ema=step_start_ema,

@@ -221,3 +221,27 @@ def test_weight_gradient_gemms_match_fp64(R, H, Co, Ci, KS):
         assert L.pmp_debug_wgrad(p(o1), p(i1), p(o2), p(i2), H, Co, Ci, KS, R, p(dw), p(scratch), tc, 0, st) == 0, L.pmp_last_error()
         err = float(((dw.double() - 1.0) - ref).norm() / ref.norm())
         assert err <= tol, (tc, err)
+
+
+def test_train_entry_point_writes_a_logdir_the_planner_loads(tmp_path):
+    """scripts/train.py (Config pickles + TrainerPBDiff on synthetic demonstrations) -> scripts/plan_rm2d.py --logdir: the
+    reference's train -> checkpoint -> plan flow (scripts/train.py:64-197, plan_rm2d.py:54-85) end to end on the GPU"""
+    import importlib.util
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "potential-motion-plan-release_b200", "scripts")
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name + "_b200", os.path.join(root, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    logdir = str(tmp_path / "logs")
+    tr = load("train").main(["--family", "m2d", "--logdir", logdir, "--n_train_steps", "6", "--batch_size", "16",
+                             "--step_start_ema", "2", "--update_ema_every", "1", "--log_freq", "0"])
+    assert tr.step == 6
+    assert sorted(os.listdir(logdir)) == ["diffusion_config.pkl", "model_config.pkl", "state_6.pt"]
+    ck = torch.load(os.path.join(logdir, "state_6.pt"), map_location="cpu", weights_only=True)
+    assert ck["step"] == 6 and all(torch.isfinite(v).all() for v in ck["ema"].values() if v.is_floating_point())
+    res = load("plan_rm2d").main(["--logdir", logdir, "--plan_n_maze", "2", "--n_prob_env", "3", "--samples_perprob", "4"])
+    assert res["num_samples"] == 6 and 0.0 <= res["traj_srate"] <= 1.0 and res["avg_num_colck"] > 0
