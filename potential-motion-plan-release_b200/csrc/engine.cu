@@ -1324,7 +1324,15 @@ int pmp_model_set_weight(pmp_model* m, const char* key, const float* data, const
 int pmp_model_finalize(pmp_model* m) {
     PMP_REQUIRE(m, "null model");
     DeviceGuard guard(m->device);
-    return finalize_model(m);
+    const int rc = finalize_model(m);
+    if (m->train && m->train->plane_jobs_dev) {
+        // the packed arenas were re-allocated: the device table of plane jobs points into the old ones
+        cudaFree(m->train->plane_jobs_dev);
+        m->train->plane_jobs_dev = nullptr;
+        m->train->n_plane_jobs = 0;
+        m->train->max_plane_elems = 0;
+    }
+    return rc;
 }
 
 int pmp_model_set_row_chunk(pmp_model* m, int rows) {
