@@ -182,6 +182,7 @@ typedef struct {
     int32_t B, H;
     float *loss_dev;                 /* [1] out: the value `loss` returns (0.5 * weighted MSE) */
     float *eps_dev;                  /* [B,H,D] out or NULL: the model output dE/dx */
+    float *energy_dev;               /* [1] out or NULL: sum of the batch's energies, the `engy_batch` of temporal_cond.py:324 */
 } pmp_train_args;
 /* grads arena += d loss / d parameters (zero it first, like optimizer.zero_grad()); no host synchronisation */
 int pmp_train_loss_grad(pmp_model *m, const pmp_train_args *a, void *stream);

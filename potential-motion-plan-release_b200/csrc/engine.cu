@@ -1431,7 +1431,7 @@ int pmp_train_loss_grad(pmp_model* m, const pmp_train_args* a, void* stream) {
     DeviceGuard guard(m->device);
     cudaStream_t st = (cudaStream_t)stream;
     TrainIO io{a->x_noisy_dev, a->t_dev, a->walls_dev, a->wall_len, a->noise_dev, a->keep_dev, a->loss_weights_dev, a->loss_dev,
-               a->eps_dev};
+               a->eps_dev, a->energy_dev};
     Ctx dry;
     dry.m = m; dry.st = st; dry.dry = true; dry.R = a->B; dry.H = a->H; dry.n_cond = a->B; dry.t = nullptr; dry.embRow = nullptr;
     int rc = run_train(dry, m->train, io);

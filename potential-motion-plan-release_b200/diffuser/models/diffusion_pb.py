@@ -328,7 +328,7 @@ class GaussianDiffusionPB(nn.Module):
         half = _EnergyLoss.apply(te, x_noisy, t, walls_loc, noise, torch.as_tensor(keep, dtype=torch.float32),
                                  self.loss_fn.weights, *[named[k] for k in te.flat.names])     # the flat arena's order
         loss = 2.0 * half          # the weighted MSE `loss_fn` returns; `loss()` halves it again
-        return loss, {'a0_loss': loss.detach()}
+        return loss, {'a0_loss': loss.detach(), 'engy_batch': te.energy_buf[0].clone()}
 
     def loss(self, x, cond, wall_locations, maze_idx=None):
         """diffusion_pb.py:518-545"""

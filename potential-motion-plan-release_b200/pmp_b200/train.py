@@ -18,7 +18,8 @@ from ._lib import lib, _check, _ptr, _stream, _f32, PmpError, UnetEngine
 class TrainArgs(C.Structure):
     _fields_ = [("x_noisy_dev", C.c_void_p), ("t_dev", C.c_void_p), ("walls_dev", C.c_void_p), ("wall_len", C.c_int32),
                 ("noise_dev", C.c_void_p), ("keep_dev", C.c_void_p), ("loss_weights_dev", C.c_void_p),
-                ("B", C.c_int32), ("H", C.c_int32), ("loss_dev", C.c_void_p), ("eps_dev", C.c_void_p)]
+                ("B", C.c_int32), ("H", C.c_int32), ("loss_dev", C.c_void_p), ("eps_dev", C.c_void_p),
+                ("energy_dev", C.c_void_p)]
 
 
 class FlatParams:
@@ -74,6 +75,7 @@ class TrainEngine:
         offs = (C.c_int64 * n)(*self.flat.offsets)
         _check(lib().pmp_train_bind(self.engine.h, n, keys, offs, _ptr(self.flat.P), _ptr(self.G), C.c_int64(self.flat.total)))
         self.loss_buf = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.energy_buf = torch.zeros(1, device=dev, dtype=torch.float32)   # sum of the last batch's energies (`engy_batch`)
         self.dirty = False      # parameters changed since the kernels' weight layouts were refreshed
 
     # -------------------------------------------------------------------------------------------------------------
@@ -106,6 +108,7 @@ class TrainEngine:
         a.B, a.H = B, H
         a.loss_dev = self.loss_buf.data_ptr()
         a.eps_dev = eps.data_ptr() if want_eps else None
+        a.energy_dev = self.energy_buf.data_ptr()
         _check(lib().pmp_train_loss_grad(self.engine.h, C.byref(a), _stream(dev)))
         loss = self.loss_buf.clone()
         return (loss, eps) if want_eps else loss

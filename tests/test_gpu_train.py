@@ -41,6 +41,11 @@ def test_loss_and_every_parameter_gradient_match_the_oracle(fam, path):
     loss, eps = te.loss_grad(xn, t, walls, noise, keep, lw, want_eps=True)
     assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
     assert abs(float(loss) - float(z["loss"])) <= 1e-4 * abs(float(z["loss"]))          # the reference's own value
+    with torch.enable_grad():                                                            # `engy_batch` = sum of 0.5 u^2
+        from oracle import unet_ref
+        w_ = unet_ref.wall_embed(sd, cfg, walls) * keep[:, None]
+        e_ref = float((0.5 * unet_ref.unet_u(sd, cfg, xn, t, w_) ** 2).sum())
+    assert abs(float(te.energy_buf) - e_ref) <= 1e-3 * abs(e_ref)
     assert float((eps.cpu() - eps_ref).abs().max()) <= 1e-3 * float(eps_ref.abs().max())
     gv = te.grad_views()
     gn = float(torch.sqrt(sum((g.double() ** 2).sum() for g in g_ref.values())))
