@@ -79,12 +79,29 @@ class Writer:
                 z = zlib.compress(blk.tobytes(), level)
                 keys.append((len(z), o, self.alloc(z, align=1)))
             K = 32
-            node = struct.pack("<4sBBHQQ", b"TREE", 1, 0, len(keys), UNDEF, UNDEF)
-            for n, o, a in keys:
-                node += struct.pack("<II", n, 0) + struct.pack("<%dQ" % (rank + 1), *o, 0) + struct.pack("<Q", a)
-            node += struct.pack("<II", 0, 0) + struct.pack("<%dQ" % (rank + 1), *[len(g) * c for g, c in zip(grid, chunk)], 0)
-            full = 24 + (2 * K + 1) * (8 + 8 * (rank + 1)) + 2 * K * 8
-            bt = self.alloc(node + b"\0" * (full - len(node)))
+            ksz = 8 + 8 * (rank + 1)
+            full = 24 + (2 * K + 1) * ksz + 2 * K * 8
+            end_key = struct.pack("<II", 0, 0) + struct.pack("<%dQ" % (rank + 1), *[len(g) * c for g, c in zip(grid, chunk)], 0)
+
+            def key_bytes(n, o):
+                return struct.pack("<II", n, 0) + struct.pack("<%dQ" % (rank + 1), *o, 0)
+
+            def write_node(level, entries):      # entries: (first key bytes, child address)
+                node = struct.pack("<4sBBHQQ", b"TREE", 1, level, len(entries), UNDEF, UNDEF)
+                for kb, a in entries:
+                    node += kb + struct.pack("<Q", a)
+                node += end_key
+                return self.alloc(node + b"\0" * (full - len(node)))
+
+            # leaves hold at most 2K chunks; more chunks get one more tree level (like the library does)
+            level, entries = 0, [(key_bytes(n, o), a) for n, o, a in keys]
+            while True:
+                groups = [entries[i:i + 2 * K] for i in range(0, len(entries), 2 * K)]
+                nodes = [(g[0][0], write_node(level, g)) for g in groups]
+                if len(nodes) == 1:
+                    bt = nodes[0][1]
+                    break
+                level, entries = level + 1, nodes
             msgs.append(self.msg(0x000B, struct.pack("<BB6x", 1, 1) + struct.pack("<HHHH", 1, 8, 1, 1) + b"deflate\0" +
                                  struct.pack("<I4x", level)))
             msgs.append(self.msg(0x0008, struct.pack("<BBBQ", 3, 2, rank + 1, bt) + struct.pack("<%dI" % (rank + 1), *chunk, arr.dtype.itemsize)))
@@ -104,14 +121,17 @@ class Writer:
         seg += b"\0" * max(0, 88 - len(seg))
         seg_a = self.alloc(bytes(seg))
         heap = self.alloc(struct.pack("<4sB3xQQQ", b"HEAP", 0, len(seg), UNDEF, seg_a))
-        snod = struct.pack("<4sBxH", b"SNOD", 1, len(names))
-        for n in names:
-            snod += struct.pack("<QQII16x", offs[n], entries[n], 0, 0)
-        snod += b"\0" * (8 + 8 * 40 - len(snod))           # room for 2K = 8 entries
-        assert len(names) <= 8
-        snod_a = self.alloc(snod)
+        # symbol nodes hold at most 2K = 8 entries (group leaf K = 4): larger groups get several under one B-tree node
+        chunks = [names[i:i + 8] for i in range(0, len(names), 8)]
         K = 16
-        node = struct.pack("<4sBBHQQ", b"TREE", 0, 0, 1, UNDEF, UNDEF) + struct.pack("<QQQ", 0, snod_a, offs[names[-1]])
+        assert len(chunks) <= 2 * K
+        node = struct.pack("<4sBBHQQ", b"TREE", 0, 0, len(chunks), UNDEF, UNDEF) + struct.pack("<Q", 0)
+        for ch in chunks:
+            snod = struct.pack("<4sBxH", b"SNOD", 1, len(ch))
+            for n in ch:
+                snod += struct.pack("<QQII16x", offs[n], entries[n], 0, 0)
+            snod += b"\0" * (8 + 8 * 40 - len(snod))
+            node += struct.pack("<QQ", self.alloc(snod), offs[ch[-1]])      # child, then the key = its largest name
         bt = self.alloc(node + b"\0" * (24 + (2 * K + 1) * 8 + 2 * K * 8 - len(node)))
         oh = self.object_header([self.msg(0x0011, struct.pack("<QQ", bt, heap))])
         return oh, bt, heap
@@ -135,7 +155,7 @@ def main():
         if k == "problems":
             h = w.dataset(a, chunk=(max(1, a.shape[0] // 2 + 1), max(1, a.shape[1] // 3 + 1)) + a.shape[2:])      # ragged edge chunks
         elif k == "infos/wall_locations":
-            h = w.dataset(a, chunk=(2, 5) + a.shape[2:])
+            h = w.dataset(a, chunk=(1, 1) + a.shape[2:])          # 120 chunks: a two-level chunk B-tree
         elif a.size <= 64:
             h = w.dataset(a, layout="compact")
         else:
@@ -148,6 +168,8 @@ def main():
     top["maze_idx"] = w.dataset(np.repeat(np.arange(z["problems"].shape[0], dtype=np.int64)[:, None], z["problems"].shape[1], 1),
                                 chunk=(4, 4))
     infos["is_sol_kp"] = w.dataset(np.ones(z["problems"].shape[:2], np.uint8), layout="contiguous")
+    for i in range(9):             # a real file has more members than one symbol node holds (8)
+        top["extra_%02d" % i] = w.dataset(np.arange(3 + i, dtype=np.float64) * 0.5, layout="compact")
     top["infos"] = w.group(infos)[0]
     data = w.finish(w.group(top))
     out = os.path.join(HERE, "m2d_synth-problems.hdf5")
