@@ -19,17 +19,35 @@ KUKA_LINK_AABB = [
 TABLE_Z = -0.001
 
 
-def sphere_table():
+def sphere_table(conservative=False):
+    """rows (link, cx, cy, cz, r) of the sphere-link model, at most 32.
+
+    default: the model the oracle defines (oracle/colchk_ref.py:kuka_sphere_table): spheres of the mean cross-section half
+    extent strung along the long axis of every link's collision-mesh AABB -- tight, NOT conservative (box corners and the
+    gaps between spheres are not covered), so a path it accepts can graze an obstacle the reference's mesh query reports.
+    conservative=True: up to 4 spheres per link whose union CONTAINS the link's AABB (radius^2 = half-diagonal^2 of the
+    cross-section + (segment / 2)^2), hence the link mesh: a path this table accepts is collision free for the real
+    geometry as well (voxels and table are exact boxes / a plane); the price is false alarms near obstacles."""
     rows = []
     for l, (mn, mx) in enumerate(KUKA_LINK_AABB):
         mn = np.array(mn); mx = np.array(mx)
         ext = mx - mn
         ax = int(np.argmax(ext))
         o = [i for i in range(3) if i != ax]
+        ctr = 0.5 * (mn + mx)
+        if conservative:
+            hd2 = 0.25 * (ext[o[0]] ** 2 + ext[o[1]] ** 2)
+            n = int(min(4, max(1, np.ceil(ext[ax] / np.sqrt(hd2)))))
+            seg = ext[ax] / n
+            r = float(np.sqrt(hd2 + 0.25 * seg * seg)) * (1 + 1e-6)
+            for j in range(n):
+                c = ctr.copy()
+                c[ax] = mn[ax] + (j + 0.5) * seg
+                rows.append([l, c[0], c[1], c[2], r])
+            continue
         r = min(0.10, 0.25 * (ext[o[0]] + ext[o[1]]))
         n = max(1, int(round(ext[ax] / (1.5 * r))))
         reff = min(r, ext[ax] / 2)
-        ctr = 0.5 * (mn + mx)
         for j in range(n):
             c = ctr.copy()
             if n > 1:
@@ -43,12 +61,13 @@ def arm_bases(n_arms):
 
 
 class KukaCollisionChecker:
-    def __init__(self, normalizer=None, device='cuda:0'):
+    def __init__(self, normalizer=None, device='cuda:0', conservative=False):
         self.normalizer = normalizer
         self.device = torch.device(device)
         self.use_collision_eps = False
         self.collision_eps = 0.03
-        self.sph = sphere_table()
+        self.conservative = conservative      # True: spheres that contain the link AABBs (see sphere_table)
+        self.sph = sphere_table(conservative)
 
     def check_batch(self, trajs, env_ids, boxc, hext, n_arms):
         """trajs [N,H,7*n_arms] (numpy or cuda tensor, un-normalised) -> dict of cuda tensors

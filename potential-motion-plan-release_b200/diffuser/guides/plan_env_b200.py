@@ -17,12 +17,15 @@ import pmp_b200
 from .kuka_colchk import KukaCollisionChecker, arm_bases, TABLE_Z
 
 
-def collision_model_tag(robot):
+def collision_model_tag(robot, conservative=False):
     """Kuka / Dual-Kuka validity comes from the analytic sphere-link model, not from the reference's pybullet mesh contact
     query (declared deviation): result dicts say so, so that their `traj_srate` etc. are not read as
     reference-parity numbers"""
     if robot == 'maze2d':
         return 'maze2d boxes, exact reference arithmetic'
+    if conservative:
+        return ('conservative sphere-link model (spheres containing the link AABBs: an accepted path is collision free for the '
+                'meshes too; NOT pybullet mesh contacts, success rates are lower bounds)')
     return 'sphere-link approximation of the arm (NOT pybullet mesh contacts; success rates are sphere-model rates)'
 
 
@@ -101,7 +104,7 @@ def replan_failed(replanner, candidates, walls_p, env_p, geom, suc, n_repl_max=6
 
 
 def plan_envs(policy, starts, goals, walls, env_boxes, hext, horizon, samples_perprob=10, robot='maze2d',
-              n_arms=1, collision_eps=0.08, legacy_div=True, replanner=None):
+              n_arms=1, collision_eps=0.08, legacy_div=True, replanner=None, kuka_conservative=False):
     """starts/goals [n_env, n_prob, D] (un-normalised numpy), walls [n_env, n_prob, wall_len] model input,
     env_boxes [n_env, n_boxes, dim] obstacle centres for the checker, hext half extent.
     Returns (result dict with the reference's keys, chosen paths [n_env*n_prob, H, D] numpy)."""
@@ -121,7 +124,7 @@ def plan_envs(policy, starts, goals, walls, env_boxes, hext, horizon, samples_pe
         valid, nchk = pmp_b200.colchk_maze2d_swept(obs, env_id, env_boxes, hext, eps=collision_eps,
                                                    legacy_div=legacy_div)
     else:
-        chk = KukaCollisionChecker(device=dev)
+        chk = KukaCollisionChecker(device=dev, conservative=kuka_conservative)
         r = pmp_b200.colchk_kuka(obs, env_id, env_boxes, hext, n_arms, arm_bases(n_arms), chk.sph, TABLE_Z)
         valid, nchk = r['valid'], r['nchk']
     chosen, suc, total = pmp_b200.pick_first_valid(valid, nchk, n_p, n_s)
@@ -143,7 +146,7 @@ def plan_envs(policy, starts, goals, walls, env_boxes, hext, horizon, samples_pe
         ncol = pmp_b200.colchk_kuka(paths, env_p, env_boxes, hext, n_arms, arm_bases(n_arms), chk.sph, TABLE_Z)['ncol']
     res = compute_avg_result(ncol.cpu().numpy(), suc.cpu().numpy(), total.cpu().numpy(), n_env, n_prob, batch_runtime,
                              repl_suc=repl_suc)
-    res['collision_model'] = collision_model_tag(robot)
+    res['collision_model'] = collision_model_tag(robot, kuka_conservative)
     return res, paths.cpu().numpy()
 
 
@@ -162,7 +165,8 @@ def pick_multi_horizon(valid_list, nchk_list, n_prob, n_samp):
 
 
 def plan_envs_multi_horizon(policy, starts, goals, walls, env_boxes, hext, horizons, samples_perprob=10,
-                            robot='maze2d', n_arms=1, collision_eps=0.08, legacy_div=True, replanner=None):
+                            robot='maze2d', n_arms=1, collision_eps=0.08, legacy_div=True, replanner=None,
+                            kuka_conservative=False):
     """plan_envs for the composed planner's list of planning horizons (comp_plan_env.py:54-124): every problem is
     planned at every horizon (PolicyCompose.call_multi_horizon), all candidates are collision-checked on the
     GPU and one path per problem is selected with pick_multi_horizon.  Returns (result dict, list of chosen
@@ -174,7 +178,7 @@ def plan_envs_multi_horizon(policy, starts, goals, walls, env_boxes, hext, horiz
     dev = policy.device
     env_id = np.repeat(np.arange(n_env, dtype=np.int32), n_prob * n_s)
     if robot != 'maze2d':
-        chk = KukaCollisionChecker(device=dev)
+        chk = KukaCollisionChecker(device=dev, conservative=kuka_conservative)
     torch.cuda.synchronize(dev)
     tic = time.time()
     obs_h, valid_h, nchk_h = [], [], []
@@ -227,5 +231,5 @@ def plan_envs_multi_horizon(policy, starts, goals, walls, env_boxes, hext, horiz
         ncol[sel] = nc.cpu().numpy()
     res = compute_avg_result(ncol, suc.cpu().numpy(), total.cpu().numpy(), n_env, n_prob, batch_runtime, repl_suc=repl_suc)
     res['horizon_hist'] = [int((hs == i).sum()) for i in range(len(horizons))]
-    res['collision_model'] = collision_model_tag(robot)
+    res['collision_model'] = collision_model_tag(robot, kuka_conservative)
     return res, paths

@@ -72,7 +72,7 @@ def make_replanner(args, diffusion, norm, robot):
         chk.use_collision_eps = True
         chk.collision_eps = 0.08
     else:
-        chk = KukaCollisionChecker(device=args.device)
+        chk = KukaCollisionChecker(device=args.device, conservative=bool(args.kuka_conservative))
     rp.set_collision_checker(chk)
     return rp
 
@@ -96,6 +96,9 @@ def main(argv=None, robot='maze2d'):
     ap.add_argument('--do_replan', type=int, default=0,
                     help='repair problems whose candidates all collide with the batched replanner (reference: do_replan)')
     ap.add_argument('--repl_dn_steps', type=int, default=3)
+    ap.add_argument('--kuka_conservative', type=int, default=0,
+                    help='Kuka / Dual Kuka: score with spheres that contain the link boxes (accepted paths are collision free '
+                         'for the meshes as well; lower success rates) instead of the tight sphere model')
     ap.add_argument('--device', default='cuda:0')
     args = ap.parse_args(argv)
     a, diffusion = load_diffusion(args.family, args.logdir, args.device)
@@ -123,7 +126,7 @@ def main(argv=None, robot='maze2d'):
         hext = args.hext if args.hext is not None else workloads.make_problems(args.family, 1, 0)['hext']
         res, _ = plan_envs(policy, s_, g_, w_, c_, hext, H, samples_perprob=args.samples_perprob, robot=robot,
                            n_arms=2 if args.family == 'dualkuka' else 1,
-                           replanner=make_replanner(args, diffusion, norm, robot))
+                           replanner=make_replanner(args, diffusion, norm, robot), kuka_conservative=bool(args.kuka_conservative))
         res['config'] = vars(args)
         print(json.dumps(res))
         return res
@@ -148,7 +151,7 @@ def main(argv=None, robot='maze2d'):
     res, _ = plan_envs(policy, np.array(starts, np.float32), np.array(goals, np.float32), np.array(walls, np.float32),
                        np.array(boxes), pr['hext'], H, samples_perprob=args.samples_perprob, robot=robot,
                        n_arms=2 if args.family == 'dualkuka' else 1,
-                       replanner=make_replanner(args, diffusion, norm, robot))
+                       replanner=make_replanner(args, diffusion, norm, robot), kuka_conservative=bool(args.kuka_conservative))
     res['config'] = vars(args)
     print(json.dumps(res))
     return res

@@ -44,6 +44,25 @@ def test_release_library_has_no_work_skipping_switches():
         assert name not in raw, name.decode()
 
 
+def test_conservative_kuka_sphere_table_contains_every_link_box():
+    """sphere_table(conservative=True): the union of a link's spheres contains the link's collision-mesh AABB (so a path the
+    checker accepts with it is collision free for the mesh too); the default table is the tight, non-conservative model"""
+    from diffuser.guides.kuka_colchk import sphere_table, KUKA_LINK_AABB
+    rng = np.random.default_rng(0)
+    for cons, must_cover in ((True, True), (False, False)):
+        tab = sphere_table(conservative=cons)
+        assert 1 <= len(tab) <= 32 and set(tab[:, 0].astype(int)) == set(range(len(KUKA_LINK_AABB)))
+        covered_all = True
+        for l, (mn, mx) in enumerate(KUKA_LINK_AABB):
+            mn, mx = np.array(mn), np.array(mx)
+            pts = np.concatenate([rng.uniform(mn, mx, (4000, 3)),
+                                  np.array([[x, y, z] for x in (mn[0], mx[0]) for y in (mn[1], mx[1]) for z in (mn[2], mx[2])])])
+            sp = tab[tab[:, 0] == l]
+            d = np.linalg.norm(pts[:, None, :] - sp[None, :, 1:4], axis=2) - sp[None, :, 4]
+            covered_all &= bool((d.min(1) <= 1e-6).all())
+        assert covered_all == must_cover
+
+
 def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("GPU present")

@@ -676,6 +676,15 @@ def test_kuka_collision_vs_oracle(fam, arms, hext):
         voxel_centers = pr["boxes"][0]; voxel_hext = hext; n_arms = arms
     ok, cnt = KukaCollisionChecker().check_single_traj(tr[0], Env)
     assert ok == bool(ref["valid"][0]) and cnt == int(ref["nchk"][0])
+    # the conservative table (spheres that contain the link AABBs): same kernel, still bit-equal to the C restatement run on
+    # that table, and never more permissive than the boxes it contains
+    from diffuser.guides.kuka_colchk import sphere_table
+    sphc = sphere_table(conservative=True)
+    refc = colchk_ref.kuka_points(tr, env, pr["boxes"], hext, n_arms=arms, sph=sphc)
+    gotc = pmp_b200.colchk_kuka(torch.tensor(tr, device=DEV), env, pr["boxes"], hext, arms, colchk_ref.kuka_bases(arms), sphc)
+    for k in ("valid", "nchk", "ncol", "ptcol"):
+        assert np.array_equal(gotc[k].cpu().numpy(), refc[k]), k
+    assert refc["valid"].mean() <= ref["valid"].mean() + 0.05
 
 
 def test_unnormalize_bit_exact():
@@ -714,7 +723,10 @@ def test_plan_entry_points():
     assert res["avg_num_colck"] > 0
     res = mod.main(["--family", "dualkuka", "--plan_n_maze", "2", "--n_prob_env", "2", "--samples_perprob", "3",
                     "--ddim_steps", "10"], robot="kuka")
-    assert keys <= set(res) and res["num_samples"] == 4
+    assert keys <= set(res) and res["num_samples"] == 4 and res["collision_model"].startswith("sphere-link")
+    res = mod.main(["--family", "kuka", "--plan_n_maze", "2", "--n_prob_env", "2", "--samples_perprob", "3",
+                    "--ddim_steps", "10", "--kuka_conservative", "1"], robot="kuka")
+    assert res["num_samples"] == 4 and res["collision_model"].startswith("conservative")
 
 
 def test_plan_rm2d_from_a_reference_written_logdir(tmp_path):
