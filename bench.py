@@ -37,7 +37,7 @@ UNIT = "plans/s"
 # algorithmic conv FLOPs per plan for DDPM-100, Maze2D H=48: 4 * 0.385 GF * 100
 FLOP_PER_PLAN = 154.0e9
 FLOP_PER_PLAN_BY_WORKLOAD = {"maze2d": 154.0e9, "kuka": 167.0e9, "dualkuka": 475.7e9,    # SURVEY 8(d), DDPM-100
-                             "comp2": 2 * 154.0e9, "comp3": 3 * 154.0e9}   # K full CFG pairs (nominal: shared uncond halves are not discounted)
+                             "comp2": 2 * 154.0e9, "comp3": 3 * 154.0e9, "comp4": 4 * 154.0e9}   # K full CFG pairs (nominal: shared uncond halves are not discounted)
 
 
 def peaks():
@@ -101,6 +101,14 @@ def cpu_arm_step_times(n_plans, n_steps, n_warm):
     return arm, [arm.step(n_plans, n_warm + i)[0] for i in range(n_steps)]
 
 
+def cpu_checker_baseline(arm):
+    """the Maze2D swept collision check alone on one host thread, beside aux_rooflines' GPU figure"""
+    n_traj = 1000 if arm.kind == "reference" else 200000
+    rate, what = arm.checker_rate(n_traj)
+    return {"value": rate, "unit": "trajectories/s", "cores": 1, "kind": arm.kind,
+            "sample": "%d straight start-goal candidates, H=48, Static2 (3 walls), eps 0.08; %s" % (n_traj, what)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -115,7 +123,8 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAME, "plans_per_step": n_plans, "families": "%d static2 + %d concave" % (
             n_plans - n_plans // 2, n_plans // 2), "step_seconds": [round(t, 3) for t in times]},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": arm.threads, "kind": arm.kind, "sample": arm.describe(n_plans)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": arm.threads, "kind": arm.kind, "sample": arm.describe(n_plans),
+                         "checker": cpu_checker_baseline(arm)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -306,7 +315,7 @@ def run_train(args, dev, world, rank):
             "metric": "training samples/sec (energy loss double backward + Adam + EMA, DDP)", "value": sps, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3 (fp32-accumulate) convolutions, fp32 weight gradients", "data": "synthetic",
+            "dtype": "bf16x3 (fp32-accumulate) convolutions and weight gradients, fp32 optimizer state", "data": "synthetic",
             "config": {"workload": "%s: %s U-Net (%d parameters), H=%d, batch %d per GPU, one optimizer step per batch" % (
                 args.workload, fam, n_par, H, B), "steps_per_s": args.steps / (ms / 1e3), "phases": ph,
                 "allreduce": "NCCL all-reduce (sum) of the flat fp32 gradient arena (%.1f MB) in %d buckets on a side stream" % (
@@ -319,9 +328,11 @@ def run_train(args, dev, world, rank):
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                         "traffic": None, "kernel": "whole loss+gradient pass (conv_tc_kernel x4 passes + wgrad_kernel x2 passes)",
-                         "note": "algorithmic FLOPs = 6 x forward conv FLOPs per sample; the weight-gradient GEMMs run on the "
-                                 "CUDA cores in fp32 (wgrad_kernel), the other four passes on tcgen05 (BF16x3)"},
+                         "traffic": None, "kernel": "whole loss+gradient pass (conv_tc_kernel x4 passes + wgrad_tc_kernel x2 passes)",
+                         "note": "algorithmic FLOPs = 6 x forward conv FLOPs per sample; on gemm path 3 all six passes run on "
+                                 "tcgen05 (BF16x3: the four data passes in conv_tc_kernel, the weight-gradient GEMMs in "
+                                 "wgrad_tc_kernel; the strided / D-channel weight gradients stay on the fp32 CUDA-core "
+                                 "wgrad_kernel), on gemm path 0 everything is fp32 CUDA-core arithmetic"},
             "cpu_baseline": None}))
     if world > 1:
         dist.destroy_process_group()
@@ -344,7 +355,7 @@ def main():
                     help="weak: --batch problems per GPU; strong: --batch problems in total, sharded over the GPUs (BASELINE configs[3])")
     ap.add_argument("--train-batch", type=int, default=256, help="samples per GPU per training step (*_train workloads)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of every step from the host (A/B of the CUDA graph replay)")
-    ap.add_argument("--workload", default="maze2d", choices=["maze2d", "kuka", "dualkuka", "comp2", "comp3", "eval200", "dualkuka_train", "maze2d_train"],
+    ap.add_argument("--workload", default="maze2d", choices=["maze2d", "kuka", "dualkuka", "comp2", "comp3", "comp4", "eval200", "dualkuka_train", "maze2d_train"],
                     help="maze2d = BASELINE configs[1] (the bench line); kuka / dualkuka = configs[3] / [4] sampling with "
                          "sphere-model collision scoring, extra measurements under the same harness")
     args = ap.parse_args()
@@ -390,7 +401,8 @@ def main():
     import ctypes as C
     ts = list(range(T_DIFF - 1, -1, -1))
     off = 0
-    comp = {"comp2": ("m2d", "m2d_nw3"), "comp3": ("m2d", "m2d", "m2d")}.get(args.workload)
+    comp = {"comp2": ("m2d", "m2d_nw3"), "comp3": ("m2d", "m2d", "m2d"),
+            "comp4": ("m2d", "m2d", "m2d", "m2d")}.get(args.workload)
     fams = ((FAMILY, Bp - Bp // 2), (FAMILY2, Bp // 2)) if args.workload == "maze2d" else (
         (("m2d", Bp),) if comp else ((args.workload, Bp),))
     for pi, (fam, n) in enumerate(fams):
@@ -661,14 +673,15 @@ def main():
             # the reference arm's step, once (bounded sample of the same workload; `bench.py --impl reference` repeats it)
             arm, tt = cpu_arm_step_times(args.ref_plans, 1, 0)
             cpu = {"value": args.ref_plans / tt[0], "unit": UNIT, "cores": arm.threads, "kind": arm.kind,
-                   "sample": arm.describe(args.ref_plans) + "; 1 step"}
+                   "sample": arm.describe(args.ref_plans) + "; 1 step", "checker": cpu_checker_baseline(arm)}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16x3 (fp32-accumulate, ~fp32-equivalent operands)", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME if args.workload == "maze2d" and len(parts) == 2 else "%s: %d problems per step, DDPM-100 H=%d cond_w=2 + collision scoring" % (
                 ({"comp2": "maze2d composition K=2 (two models: 6 walls + 3 walls)",
-                  "comp3": "maze2d composition K=3 (one model, three 6-wall subsets; shared unconditional half)"}.get(args.workload)
+                  "comp3": "maze2d composition K=3 (one model, three 6-wall subsets; shared unconditional half)",
+                  "comp4": "maze2d composition K=4 (one model, four 6-wall subsets; shared unconditional half)"}.get(args.workload)
                  or parts[0]["fam"]), parts[0]["n"], parts[0]["H"]),
                        "families": " + ".join("%d %s" % (P_["n"], P_["fam"]) for P_ in parts),
                        "plans_per_step": B_total, "plans_per_step_per_gpu": Bp, "row_chunk": args.row_chunk,

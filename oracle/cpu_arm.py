@@ -112,6 +112,30 @@ class CpuArm:
             ok.append(self._score(fam, pr, x))
         return time.perf_counter() - t0, np.concatenate(ok)
 
+    # ------------------------------------------------------------------ the collision checker alone
+    def checker_rate(self, n_traj=2000, seed=3):
+        """Swept Maze2D check (rm2d_colchk.py:76-93) of n_traj straight start-goal candidates (Static2, 10 candidates per
+        environment -- the GPU arm's aux workload), ONE host thread like the reference.  Returns (trajectories/s, what ran):
+        the reference's own Python loop where the tree is present, the C restatement oracle/colchk.c otherwise."""
+        fam, H = "m2d_nw3", 48
+        n_env = max(1, n_traj // 10)
+        pr = synth.make_problems(fam, n_env, 4000 + seed)
+        rng = np.random.default_rng(seed)
+        s_ = rng.uniform(0.2, 4.8, (n_traj, 1, 2)).astype(np.float32)
+        g_ = rng.uniform(0.2, 4.8, (n_traj, 1, 2)).astype(np.float32)
+        al = np.linspace(0, 1, H, dtype=np.float32)[None, :, None]
+        un = (s_ * (1 - al) + g_ * al).astype(np.float32)
+        env = (np.arange(n_traj) // 10 % n_env).astype(np.int32)
+        sub = dict(pr, boxes=pr["boxes"][env])
+        if self.kind == "reference":
+            t0 = time.perf_counter()
+            self._score(fam, sub, torch.tensor(synth.normalize(un, pr["lo"], pr["hi"])))
+            return n_traj / (time.perf_counter() - t0), "reference Python loop (edge_fp per segment), 1 thread"
+        colchk_ref.maze2d_swept(un[:8], env[:8], pr["boxes"], pr["hext"])      # loads the library
+        t0 = time.perf_counter()
+        colchk_ref.maze2d_swept(un, env, pr["boxes"], pr["hext"])
+        return n_traj / (time.perf_counter() - t0), "C restatement oracle/colchk.c, 1 thread"
+
     def describe(self, n_plans):
         return ("%d + %d plans per step (Static2 nw3 + Concave nw7), full DDPM-%d (CFG pair, autograd dE/dx) + swept collision "
                 "check eps 0.08, fp32 torch CPU, %s" % (n_plans - n_plans // 2, n_plans // 2, T_DIFF,

@@ -412,6 +412,33 @@ def test_plan_envs_multi_horizon_composed():
     assert 0.0 <= res["traj_srate"] <= 1.0 and res["total_num_colck"] > 0
 
 
+def test_plan_envs_multi_horizon_plain_policy():
+    """the same multi-horizon planner with a single-model Policy (rm2d_plan_env.py:137-235 per horizon): the plain
+    policy has call_multi_horizon too, so the dispatch must look at the class, not at that method; the selection is
+    recomputed here from the per-horizon checks (first valid in the interleaved scan order, else the last candidate)"""
+    from diffuser.guides import Policy
+    from diffuser.guides.plan_env_b200 import plan_envs_multi_horizon
+    from diffuser.datasets import DatasetNormalizer, RAND_MAZE_MIN, RAND_MAZESIZE_55
+    norm = DatasetNormalizer({"observations": (RAND_MAZE_MIN, RAND_MAZESIZE_55)})
+    d = dropin("m2d")
+    d.ddim_num_inference_steps = 8
+    pol = Policy(d, norm, use_ddim=True)
+    n_env, n_prob, n_s, horizons = 3, 4, 2, (40, 48)
+    pr = synth.make_problems("m2d", n_env, 23)
+    rng = np.random.default_rng(5)
+    starts = rng.uniform(0.2, 4.8, (n_env, n_prob, 2)).astype(np.float32)
+    goals = rng.uniform(0.2, 4.8, (n_env, n_prob, 2)).astype(np.float32)
+    walls = np.repeat(pr["walls"][:, None], n_prob, 1)
+    res, paths = plan_envs_multi_horizon(pol, starts, goals, walls, pr["boxes"], float(pr["hext"]), horizons,
+                                         samples_perprob=n_s)
+    assert len(paths) == n_env * n_prob and sum(res["horizon_hist"]) == n_env * n_prob
+    for p, path in enumerate(paths):
+        assert path.shape[0] in horizons and path.shape[1] == 2 and np.isfinite(path).all()
+        assert np.allclose(path[0], starts.reshape(-1, 2)[p], atol=1e-5) and np.allclose(path[-1], goals.reshape(-1, 2)[p], atol=1e-5)
+    assert 0.0 <= res["traj_srate"] <= 1.0 and res["total_num_colck"] > 0
+    assert d.horizon == horizons[-1]        # the policy re-targets the model's horizon per call, like policies.py:82
+
+
 # ------------------------------------------------------------------ collision
 @pytest.mark.parametrize("fam", ["m2d", "m2d_nw3", "m2d_concave"])
 def test_maze2d_collision_matches_reference_golden(fam):

@@ -352,3 +352,26 @@ def test_pick_first_valid_matches_live_reference_planner():
         assert [bool(s) for s in d["suc_list"]] == su.tolist() and list(d["num_colck_list"]) == tot.tolist()
         for p in range(n_p):
             assert np.array_equal(d["modelout_path_list"][p], tj[p * n_s + ch[p]])
+
+
+def test_cpu_arm_checker_sample_runs_on_both_kinds():
+    """bench.py's cpu_baseline.checker leg (oracle/cpu_arm.py checker_rate): the C restatement everywhere, the
+    reference's Python loop where the tree is present; both score the same straight-line candidates the same way"""
+    from oracle import cpu_arm
+    arm = cpu_arm.CpuArm(threads=1, prefer_reference=False)
+    rate, what = arm.checker_rate(200)
+    assert arm.kind == "port" and rate > 0 and "colchk.c" in what
+    if refshim.available():
+        arm.kind = "reference"
+        arm.geom = refshim.load_maze2d_geometry()
+        rate_r, what_r = arm.checker_rate(60)
+        assert rate_r > 0 and "reference" in what_r
+        # same candidates through both scorers: identical bits
+        pr = synth.make_problems("m2d_nw3", 6, 4003)
+        rng = np.random.default_rng(3)
+        un = np.linspace(rng.uniform(0.2, 4.8, (60, 2)), rng.uniform(0.2, 4.8, (60, 2)), 48, axis=1).astype(np.float32)
+        env = (np.arange(60) // 10).astype(np.int32)
+        ok_ref = arm._score("m2d_nw3", dict(pr, boxes=pr["boxes"][env]), torch.tensor(synth.normalize(un, pr["lo"], pr["hi"])))
+        un2 = synth.unnormalize(synth.normalize(un, pr["lo"], pr["hi"]), pr["lo"], pr["hi"])
+        ok_c, _ = colchk_ref.maze2d_swept(un2, env, pr["boxes"], pr["hext"])
+        assert np.array_equal(ok_ref, np.asarray(ok_c, bool))
