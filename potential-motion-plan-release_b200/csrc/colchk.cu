@@ -348,20 +348,28 @@ __global__ void __launch_bounds__(WARPS * 32) maze2d_swept_lane_kernel(
                 wl[i] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);      // never inside
             }
         }
-        // Walk state, kept small so that the per-waypoint work is the reference's compares and little else:
-        //   ps   = state of the previous waypoint: 0 outside the limits, 1 inside and colliding, 2 inside and free
-        //          -> _edge_fp of segment (h - 1, h) makes `ps` checks when waypoint h is inside the limits (0: an endpoint is
-        //          outside, 1: the first endpoint collides, 2: both endpoints tested) and is clear iff ps == 2 and h is free;
-        //   llox = the lower x limit, replaced by NaN once the trajectory has failed (or for an idle lane): every later
-        //          waypoint then tests "outside the limits", which counts nothing and keeps ok = false -- the early exit of
-        //          the reference's loop without a `done` flag.
-        float llox = active ? lox : __int_as_float(0x7fc00000);
+        // Walk state, kept small so that the per-waypoint work is the reference's compares and little else.
+        //   * _edge_fp of segment (h - 1, h) makes 0 checks when an endpoint is outside the limits, 1 when the first endpoint
+        //     collides, 2 (+ interior points) when both endpoints are tested, and is clear iff both are inside and free.
+        //   * While a trajectory is alive every earlier segment was clear, so from the second segment on the previous waypoint
+        //     is known to be inside and free: the segment makes 2 checks iff waypoint h is inside the limits and is clear iff
+        //     h is also free.  Only the FIRST segment needs the general rule (waypoint 0 may be outside or colliding).
+        //   * llox = the lower x limit, replaced by NaN once the trajectory has failed (or for an idle lane): every later
+        //     waypoint then tests "outside the limits", which counts nothing and stays failed -- the early exit of the
+        //     reference's loop without a `done` flag; valid = llox is not NaN.
+        const float qnan = __int_as_float(0x7fc00000);
+        float llox = active ? lox : qnan;
         // the other limits and the threshold in ordinary (lane-dependent, so not re-materialised) registers: as kernel
         // parameters they are re-fetched into uniform registers around every rare-path branch, three issue slots per waypoint
-        const float qnan = __int_as_float(0x7fc00000);
         const float lloy = active ? loy : qnan, lhix = active ? hix : qnan, lhiy = active ? hiy : qnan;
         const float lthr2 = active ? thr2 : qnan;
-        int ok = 1, cnt = 0, ps = 0;
+        auto hits = [&](const float2 w) {
+            bool col = false;
+#pragma unroll
+            for (int i = 0; i < NWR; ++i) col = col | ((w.x >= wl[i].x) & (w.y >= wl[i].y) & (w.x <= wl[i].z) & (w.y <= wl[i].w));
+            return col;
+        };
+        int cnt = 0;
         float2 pw = make_float2(0.f, 0.f);
         for (int c = 0; c < nchunks; ++c) {
             __syncwarp();
@@ -372,39 +380,46 @@ __global__ void __launch_bounds__(WARPS * 32) maze2d_swept_lane_kernel(
             }
             __syncwarp();
             if (c + 1 < nchunks) fetch(c + 1);
-            const int jn = min(CH, H - c * CH);
+            const int jn = min(CH, H - c * CH);      // even: the dispatch requires an even H
             int j = 0;
-            if (c == 0) {      // waypoint 0 opens no segment
-                pw = stage[warp][lane][0];
-                const bool in = pw.x >= llox && pw.y >= lloy && pw.x <= lhix && pw.y <= lhiy;
-                bool col = false;
-#pragma unroll
-                for (int i = 0; i < NWR; ++i) col = col | ((pw.x >= wl[i].x) & (pw.y >= wl[i].y) & (pw.x <= wl[i].z) & (pw.y <= wl[i].w));
-                ps = in ? (col ? 1 : 2) : 0;
-                j = 1;
+            if (c == 0) {      // waypoints 0 and 1: the first segment, general rule
+                const float2 w0 = stage[warp][lane][0];
+                const bool in0 = (w0.x >= llox) & (w0.y >= lloy) & (w0.x <= lhix) & (w0.y <= lhiy);
+                const int ps = in0 ? (hits(w0) ? 1 : 2) : 0;
+                const float2 w = stage[warp][lane][1];
+                const bool in = (w.x >= llox) & (w.y >= lloy) & (w.x <= lhix) & (w.y <= lhiy);
+                cnt = in ? ps : 0;
+                const bool clear = in & (ps == 2) & !hits(w);
+                if (!clear) llox = qnan;
+                const float dx = __fsub_rn(w.x, w0.x), dy = __fsub_rn(w.y, w0.y);
+                const float ss = __fadd_rn(__fmul_rn(fabsf(dx), fabsf(dx)), __fmul_rn(fabsf(dy), fabsf(dy)));
+                if (clear && !(ss < lthr2)) {
+                    const int r = m2d_interior_reg<NWR>(wl, lox, loy, hix, hiy, w0, dx, dy, ss, eps, legacy_div);
+                    cnt += r >> 1;
+                    if (!(r & 1)) llox = qnan;
+                }
+                pw = w;
+                j = 2;
             }
 #pragma unroll 2
             for (; j < jn; ++j) {
                 const float2 w = stage[warp][lane][j];
                 const bool in = (w.x >= llox) & (w.y >= lloy) & (w.x <= lhix) & (w.y <= lhiy);
-                bool col = false;
-#pragma unroll
-                for (int i = 0; i < NWR; ++i) col = col | ((w.x >= wl[i].x) & (w.y >= wl[i].y) & (w.x <= wl[i].z) & (w.y <= wl[i].w));
-                cnt += in ? ps : 0;
-                const bool clear = in & (ps == 2) & !col;
+                const bool clear = in & !hits(w);
+                cnt += in ? 2 : 0;
+                if (!clear) llox = qnan;
                 const float dx = __fsub_rn(w.x, pw.x), dy = __fsub_rn(w.y, pw.y);
                 const float ss = __fadd_rn(__fmul_rn(fabsf(dx), fabsf(dx)), __fmul_rn(fabsf(dy), fabsf(dy)));
-                if (!clear) { ok = 0; llox = __int_as_float(0x7fc00000); }
-                ps = in ? (col ? 1 : 2) : 0;
                 if (clear && !(ss < lthr2)) {      // K >= 2 possible: the reference's exact square root, division and points
                     const int r = m2d_interior_reg<NWR>(wl, lox, loy, hix, hiy, pw, dx, dy, ss, eps, legacy_div);
                     cnt += r >> 1;
-                    if (!(r & 1)) { ok = 0; llox = __int_as_float(0x7fc00000); }
+                    if (!(r & 1)) llox = qnan;
                 }
                 pw = w;
             }
             if (__all_sync(0xffffffffu, llox != llox)) break;
         }
+        const bool ok = !(llox != llox);
         if (active) {
             valid[n] = ok ? 1 : 0;
             nchk[n] = cnt;
