@@ -664,7 +664,7 @@ def main():
                     "achieved": by / t_chk / 1e9, "peak": pk_hbm(), "unit": "GB/s", "frac": by / t_chk / 1e9 / pk_hbm(),
                     "bytes_per_trajectory": 4 * H * D + 5, "trajectories_per_launch": ntr, "ms": t_chk * 1e3,
                     "trajectories_per_s": ntr / t_chk,
-                    "note": "one lane per trajectory, walls as float32 thresholds in registers, trajectories staged through shared memory in coalesced 8-waypoint chunks; issue-bound (ncu: 70 % of issue slots, 31 % of DRAM bandwidth) on the reference's exact per-waypoint tests"})
+                    "note": "one lane per trajectory, walls as float32 thresholds in registers, trajectories staged through shared memory in coalesced 8-waypoint chunks, 33 instructions per waypoint (16 of them the reference's exact compares); bound by issue slots, not by DRAM (profiles/README.md)"})
         del xs, ec, eu, xo, tr
 
     if rank == 0:
