@@ -540,3 +540,21 @@ def test_solution_interp_matches_live_reference():
                 with refshim.quiet():
                     ref = np.asarray(ref_f(pts))
                 assert np.array_equal(replan_ref.sol_interp(pts, density), ref)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm) on a two-plan sample: one JSON line with the contract's
+    keys, the CPU baseline described (kind / cores / sample) and the checker leg beside it; no GPU involved"""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-plans", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "plans/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["steps"] == 1 and d["gpu_launches"] == 0 and d["config"]["plans_per_step"] == 2
+    assert d["e2e"] == {"value": d["value"], "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and "DDPM-100" in cb["sample"] and cb["value"] == d["value"]
+    assert cb["checker"]["unit"] == "trajectories/s" and cb["checker"]["value"] > 0 and cb["checker"]["cores"] == 1
