@@ -197,6 +197,74 @@ def run_eval200(args, dev, world, rank):
             "gpu_launches": res["graph"]["launches"] * args.steps}))
 
 
+def run_compeval(args, dev, world, rank):
+    """The reference's composed evaluation call (comp_plan_env.py:54-265): K = 2 potentials (the
+    6-wall and the 3-wall network on their own obstacle subsets), every problem planned at three horizons with 10 samples
+    each (DDIM-8), all 600 candidates swept-checked against the union of the obstacles, interleaved first-valid pick, final
+    per-waypoint scoring -- through the public planner call `plan_envs_multi_horizon` (host arrays in, statistics and host
+    paths out).  Latency workload."""
+    import torch
+    import pmp_b200
+    from pmp_b200 import workloads as synth
+    from diffuser.models import TemporalUnet_WCond, GaussianDiffusionPB
+    from diffuser.guides import PolicyCompose
+    from diffuser.guides.plan_env_b200 import plan_envs_multi_horizon
+    from diffuser.datasets import DatasetNormalizer, RAND_MAZE_MIN, RAND_MAZESIZE_55
+    n_env, n_prob, n_samp, horizons, n_ddim = 1, 20, 10, (40, 48, 56), 8
+    dms = []
+    for k, fam in enumerate(("m2d", "m2d_nw3")):
+        a = synth.arch(fam)
+        m = TemporalUnet_WCond(**a["unet"])
+        m.load_state_dict(synth.synth_state_dict(m.state_dict(), 1 + k))
+        d = GaussianDiffusionPB(m, **a["diffusion"]).to(dev).eval()
+        d.rng_mode = "philox"
+        dms.append(d)
+    norm = DatasetNormalizer({"observations": (RAND_MAZE_MIN, RAND_MAZESIZE_55)})
+    po = dict(num_walls_c=[6, 3], wall_dim=2, comp_type="direct", ddim_steps=n_ddim, wall_is_dyn=None, uncond_base_idx=0,
+              ddim_eta=0.0)
+    comp = PolicyCompose(dms, [norm, norm], False, True, po)
+    pr6, pr3 = synth.make_problems("m2d", n_env, 5000 + rank), synth.make_problems("m2d_nw3", n_env, 6000 + rank)
+    rng = np.random.default_rng(7 + rank)
+    starts = rng.uniform(0.2, 4.8, (n_env, n_prob, 2)).astype(np.float32)
+    goals = rng.uniform(0.2, 4.8, (n_env, n_prob, 2)).astype(np.float32)
+    walls = np.repeat(np.concatenate([pr6["walls"], pr3["walls"]], 1)[:, None], n_prob, 1)
+    boxes = np.concatenate([pr6["boxes"], pr3["boxes"]], 1)                    # the checker sees the union of both sets
+    hext = np.concatenate([np.full(6, float(pr6["hext"])), np.full(3, float(pr3["hext"]))])[None, :, None]
+
+    def call():
+        return plan_envs_multi_horizon(comp, starts, goals, walls, boxes, hext, horizons, samples_perprob=n_samp)[0]
+
+    for _ in range(max(args.warmup, 3)):
+        res = call()
+    torch.cuda.synchronize()
+    n0 = pmp_b200.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        res = call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms, wall_ms = e0.elapsed_time(e1) / args.steps, 1e3 * (time.perf_counter() - t0) / args.steps
+    n = n_env * n_prob * n_samp * len(horizons)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": world * n / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (fp32-accumulate, ~fp32-equivalent operands)", "data": "synthetic",
+            "config": {"workload": "compeval: maze2d composition K=2 (6-wall + 3-wall networks), 20 problems x 10 samples x horizons "
+                                   "%s per call, DDIM-%d cond_w=2 + swept check of all candidates + interleaved first-valid pick + "
+                                   "final scoring (the reference's composed evaluation call, through plan_envs_multi_horizon)" % (
+                                       list(horizons), n_ddim),
+                       "candidate_plans_per_call": n, "latency_ms": ms, "host_wall_ms": wall_ms,
+                       "traj_srate": float(res["traj_srate"]), "total_num_colck": int(res["total_num_colck"]),
+                       "horizon_hist": res["horizon_hist"], "l2": "working set fits the 126 MB L2 (latency workload)"},
+            "e2e": {"value": world * n / (wall_ms / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(len(horizons) * (starts.nbytes + goals.nbytes + walls.nbytes) * n_samp),
+                    "d2h_bytes_per_step": int(sum(n_env * n_prob * h * 2 * 4 for h in horizons))},
+            "gpu_launches": (pmp_b200.launch_count() - n0)}))
+
+
 TRAIN_FLOP_PER_SAMPLE = {"dualkuka_train": 6 * 1.1893e9, "maze2d_train": 6 * 0.3850e9}   # 6 conv-type passes (see run_train)
 
 
@@ -355,7 +423,7 @@ def main():
                     help="weak: --batch problems per GPU; strong: --batch problems in total, sharded over the GPUs (BASELINE configs[3])")
     ap.add_argument("--train-batch", type=int, default=256, help="samples per GPU per training step (*_train workloads)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of every step from the host (A/B of the CUDA graph replay)")
-    ap.add_argument("--workload", default="maze2d", choices=["maze2d", "kuka", "dualkuka", "comp2", "comp3", "comp4", "eval200", "dualkuka_train", "maze2d_train"],
+    ap.add_argument("--workload", default="maze2d", choices=["maze2d", "kuka", "dualkuka", "comp2", "comp3", "comp4", "eval200", "compeval", "dualkuka_train", "maze2d_train"],
                     help="maze2d = BASELINE configs[1] (the bench line); kuka / dualkuka = configs[3] / [4] sampling with "
                          "sphere-model collision scoring, extra measurements under the same harness")
     args = ap.parse_args()
@@ -389,6 +457,8 @@ def main():
     # half Concave (7 concave obstacles = 21 boxes, hExt 0.25), one model per family, collision-check success scoring
     if args.workload == "eval200":
         return run_eval200(args, dev, world, rank)
+    if args.workload == "compeval":
+        return run_compeval(args, dev, world, rank)
     if args.workload.endswith("_train"):
         return run_train(args, dev, world, rank)
     if args.no_graph:
