@@ -147,6 +147,8 @@ def run_eval200(args, dev, world, rank):
     diffusion.ddim_num_inference_steps = n_ddim
     diffusion.rng_mode = "philox"
     eng = diffusion.model.engine(T_DIFF)
+    if args.gemm_path != 3:
+        eng.set_gemm_path(args.gemm_path)
     pr = synth.make_problems(fam, n_prob, 4000 + rank)
     lo, hi = pr["lo"], pr["hi"]
     rep = lambda x: np.repeat(x, n_samp, axis=0)
@@ -193,7 +195,8 @@ def run_eval200(args, dev, world, rank):
                                    "+ swept collision check + first-valid pick (the reference's evaluation batch)",
                        "plans_per_step_per_gpu": n, "latency_ms_graph": res["graph"]["ms"], "latency_ms_direct": res["direct"]["ms"],
                        "host_wall_ms_graph": res["graph"]["wall_ms"], "host_wall_ms_direct": res["direct"]["wall_ms"],
-                       "kernels_per_call": res["graph"]["launches"], "l2": "working set fits the 126 MB L2 (latency workload)"},
+                       "kernels_per_call": res["graph"]["launches"], "gemm_path": args.gemm_path,
+                       "l2": "working set fits the 126 MB L2 (latency workload)"},
             "gpu_launches": res["graph"]["launches"] * args.steps}))
 
 
